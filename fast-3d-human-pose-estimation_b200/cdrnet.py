@@ -1,0 +1,334 @@
+"""Drop-in ``CDRNet`` / ``PoseResNet`` / ``PoseDecoder`` whose head runs in libcdrhead.so.
+
+Mirrors the reference's module interface (models/cdrnet.py:88-268,
+models/poseresnet.py:10-21, models/decoder.py:7-46):
+
+* same constructor arguments, same ``state_dict`` key names and parameter
+  creation order (so ``load_state_dict(torch.load('best.pth'))`` and a seeded
+  random init both match the reference);
+* ``forward(xs, proj_list) -> (pred_2ds, pred_3ds)`` with the same shapes,
+  dtypes and device.
+
+What differs is *where the arithmetic runs*: the ResNet encoder stays an
+``nn.Module`` on torch/cuDNN; everything after it (pinv, canonical fusion with
+the feature-transform layer, deconvolution decoder, soft-argmax, DLT) is one call
+into the C ABI (``cdr_head_forward``, include/cdrhead.h) on the current CUDA
+stream.  The ``nn.Conv2d`` / ``nn.BatchNorm2d`` children of ``CF`` and
+``decoder`` are parameter containers only: they are BN-folded and re-laid-out
+into a device-side handle the first time ``forward`` runs and whenever a
+parameter changes (``load_state_dict``, ``.to()``, in-place edits).
+
+Inference only: the reference's training step (autograd through the head,
+train-mode BN) is out of scope for this build — calling ``forward`` in
+training mode raises.  There is no CPU / PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib
+from .encoder import ResNet
+
+PINV_RTOL_FP32 = 4 * float(torch.finfo(torch.float32).eps)  # torch.linalg.pinv default, (3,4) fp32
+
+
+def _conv_bn_relu(cin, cout):
+    return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=1, stride=1),
+                         nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+
+class CanonicalFusion(nn.Module):
+    """Parameter container for reference models/cdrnet.py:10-43."""
+
+    def __init__(self, in_dim=2048, hid_ch1=300, hid_ch2=300, n_views=2):
+        super().__init__()
+        self.conv_layer1 = _conv_bn_relu(in_dim, hid_ch1)
+        self.conv_layer2 = nn.Sequential(
+            nn.Conv2d(n_views * hid_ch2, hid_ch2, kernel_size=1, stride=1),
+            nn.BatchNorm2d(hid_ch2), nn.ReLU(inplace=True),
+            nn.Conv2d(hid_ch2, hid_ch2, kernel_size=1, stride=1),
+            nn.BatchNorm2d(hid_ch2), nn.ReLU(inplace=True))
+        self.out_layer = nn.ModuleList([_conv_bn_relu(hid_ch1, in_dim) for _ in range(n_views)])
+
+    def forward(self, *a, **k):
+        raise RuntimeError("CanonicalFusion is a parameter container; call CDRNet.forward")
+
+
+class PoseDecoder(nn.Module):
+    """models/decoder.py:7-46.  ``forward`` runs ``cdr_decoder_forward``."""
+
+    def __init__(self, cfg, precision="fp32"):
+        super().__init__()
+        self.deconv1 = self._deconv(2048, 256)
+        self.deconv2 = self._deconv(256, 256)
+        self.deconv3 = self._deconv(256, 256)
+        self.final_layer = nn.Conv2d(256, cfg.MODEL.NUM_JOINTS, kernel_size=1, stride=1, padding=0)
+        self.num_joints = cfg.MODEL.NUM_JOINTS
+        self._packed = _PackedWeights(self, precision, has_fusion=False)
+
+    @staticmethod
+    def _deconv(cin, cout):
+        return nn.Sequential(
+            nn.ConvTranspose2d(cin, cout, kernel_size=4, stride=2, padding=1, output_padding=0,
+                               bias=False),
+            nn.BatchNorm2d(cout, momentum=0.1), nn.ReLU(inplace=True))
+
+    def init_weights(self):
+        """models/decoder.py:48-73."""
+        for seq in (self.deconv1, self.deconv2, self.deconv3):
+            nn.init.normal_(seq[0].weight, std=0.001)
+            nn.init.constant_(seq[1].weight, 1)
+            nn.init.constant_(seq[1].bias, 0)
+        nn.init.normal_(self.final_layer.weight, std=0.001)
+        nn.init.constant_(self.final_layer.bias, 0)
+
+    def forward(self, x):
+        _require_eval(self)
+        x = _as_f32_cuda(x, "PoseDecoder input")
+        n = x.shape[0]
+        if tuple(x.shape[1:]) != (2048, 8, 8):
+            raise ValueError(f"PoseDecoder expects (N,2048,8,8) features, got {tuple(x.shape)}")
+        handle = self._packed.get(_decoder_tensors(self, ""), x.device)
+        L = _lib.lib()
+        nbytes = C.c_size_t()
+        _lib.check(L.cdr_decoder_workspace_bytes(handle, n, C.byref(nbytes)))
+        ws = _workspace(x.device, nbytes.value)
+        out = torch.empty((n, self.num_joints, 64, 64), dtype=torch.float32, device=x.device)
+        _lib.check(L.cdr_decoder_forward(handle, _lib.ptr(x), n, _lib.ptr(out), _lib.ptr(ws),
+                                         nbytes.value, _lib.current_stream_ptr(x.device)))
+        return out
+
+
+def _require_eval(m):
+    if m.training:
+        raise RuntimeError(
+            f"{type(m).__name__}: the B200 head is inference-only (eval-mode BN folded into the "
+            "convs, no autograd); call .eval() first")
+
+
+def _as_f32_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must be a CUDA tensor: the CDRNet head has no CPU path")
+    return t.detach().to(torch.float32).contiguous()
+
+
+_WS = {}
+
+
+def _workspace(device, nbytes):
+    """One growing scratch buffer per device (torch-owned; the library never allocates
+    caller-visible memory).  256-byte aligned by the caching allocator."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _WS[key] = buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+    return buf
+
+
+def _convbn(conv, bn):
+    s = _lib.CdrConvBn()
+    s.weight = conv.weight.data_ptr()
+    s.bias = conv.bias.data_ptr() if conv.bias is not None else None
+    if bn is not None:
+        s.bn_weight = bn.weight.data_ptr()
+        s.bn_bias = bn.bias.data_ptr()
+        s.bn_mean = bn.running_mean.data_ptr()
+        s.bn_var = bn.running_var.data_ptr()
+    return s
+
+
+def _decoder_tensors(dec, _prefix):
+    return [dec.deconv1, dec.deconv2, dec.deconv3, dec.final_layer]
+
+
+class _PackedWeights:
+    """Owns the CdrWeights handle of one module and re-packs it when parameters change."""
+
+    def __init__(self, owner, precision, has_fusion):
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
+        self.precision = precision
+        self.has_fusion = has_fusion
+        self._handle = None
+        self._sig = None
+
+    def _signature(self, tensors, device):
+        return (str(device), self.precision) + tuple((t.data_ptr(), t._version) for t in tensors)
+
+    def get(self, modules, device, cf=None):
+        dec = modules
+        params = []
+        mods = ([cf.conv_layer1, cf.conv_layer2, cf.out_layer[0], cf.out_layer[1]] if cf is not None
+                else []) + list(dec)
+        for m in mods:
+            params += list(m.parameters()) + list(m.buffers())
+        for t in params:
+            if t.is_floating_point() and (t.dtype != torch.float32 or t.device != device):
+                raise RuntimeError("head parameters must be float32 on the input's device "
+                                   f"(found {t.dtype} on {t.device}, input on {device})")
+        sig = self._signature(params, device)
+        if self._handle is not None and sig == self._sig:
+            return self._handle
+        self.release()
+        src = _lib.CdrWeightPtrs()
+        src.num_joints = dec[3].out_channels
+        src.has_fusion = 1 if cf is not None else 0
+        if cf is not None:
+            src.cf_conv1 = _convbn(cf.conv_layer1[0], cf.conv_layer1[1])
+            src.cf_conv2a = _convbn(cf.conv_layer2[0], cf.conv_layer2[1])
+            src.cf_conv2b = _convbn(cf.conv_layer2[3], cf.conv_layer2[4])
+            for v in range(2):
+                src.cf_out[v] = _convbn(cf.out_layer[v][0], cf.out_layer[v][1])
+        for i in range(3):
+            src.deconv[i] = _convbn(dec[i][0], dec[i][1])
+        src.final_layer = _convbn(dec[3], None)
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().cdr_weights_create(
+                C.byref(src), _lib.PRECISIONS[self.precision], _lib.current_stream_ptr(device),
+                C.byref(handle)))
+        self._handle, self._sig = handle, sig
+        return handle
+
+    def release(self):
+        if self._handle is not None:
+            _lib.lib().cdr_weights_destroy(self._handle)
+            self._handle = None
+            self._sig = None
+
+    def __deepcopy__(self, memo):
+        return _PackedWeights(None, self.precision, self.has_fusion)  # handles are not shared
+
+    def __getstate__(self):
+        return {"precision": self.precision, "has_fusion": self.has_fusion,
+                "_handle": None, "_sig": None}
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class CDRNet(nn.Module):
+    """Reference models/cdrnet.py:88-268 with the post-encoder path on libcdrhead.so.
+
+    Extra keyword ``precision`` ('fp32' parity kernels | 'bf16' tcgen05 kernels)."""
+
+    def __init__(self, cfg, n_views=2, nj=19, fusion_in_dim=2048, fusion_hid_ch1=300,
+                 fusion_hid_ch2=400, precision="fp32"):
+        super().__init__()
+        if n_views != 2 or fusion_in_dim != 2048 or fusion_hid_ch1 != 300 or fusion_hid_ch2 != 400:
+            raise NotImplementedError(
+                "libcdrhead is built for the reference's stereo configuration "
+                "(n_views=2, fusion 2048/300/400, models/cdrnet.py:89-91)")
+        self.encoder = ResNet(cfg)
+        self.CF = CanonicalFusion(in_dim=fusion_in_dim, hid_ch1=fusion_hid_ch1,
+                                  hid_ch2=fusion_hid_ch2, n_views=n_views)
+        self.decoder = PoseDecoder(cfg, precision)
+        self.n_views = n_views
+        self.nj = nj
+        self._packed = _PackedWeights(self, precision, has_fusion=True)
+
+    @property
+    def precision(self):
+        return self._packed.precision
+
+    def init_weights(self, pretrained=""):
+        """models/cdrnet.py:103-118: decoder N(0, 1e-3) init + encoder.* keys of a checkpoint."""
+        import os
+        if not os.path.isfile(pretrained):
+            raise ValueError("Pretrained model '{}' does not exist.".format(pretrained))
+        self.decoder.init_weights()
+        ckpt = torch.load(pretrained)
+        self.load_state_dict({k: v for k, v in ckpt.items() if k.startswith("encoder")},
+                             strict=False)
+
+    def head(self, feats, proj_list, proj_inv_list=None, taps=False, img_size=256):
+        """The hot path: encoder latents -> (pred_2ds, pred_3ds).  models/cdrnet.py:236-268.
+
+        feats: list[2] of (B,2048,8,8); proj_list: list[2] of (B,3,4).  ``proj_inv_list``
+        overrides the on-device pseudo-inverse.  ``taps=True`` also returns the stage
+        tensors the parity tests compare."""
+        _require_eval(self)
+        fl = _as_f32_cuda(feats[0], "features")
+        fr = _as_f32_cuda(feats[1], "features")
+        pl = _as_f32_cuda(proj_list[0], "proj_list")
+        pr = _as_f32_cuda(proj_list[1], "proj_list")
+        b = fl.shape[0]
+        if tuple(fl.shape) != (b, 2048, 8, 8) or fr.shape != fl.shape:
+            raise ValueError(f"expected two (B,2048,8,8) latents, got {tuple(fl.shape)} / {tuple(fr.shape)}")
+        if tuple(pl.shape) != (b, 3, 4) or tuple(pr.shape) != (b, 3, 4):
+            raise ValueError(f"proj_list entries must be (B,3,4), got {tuple(pl.shape)} / {tuple(pr.shape)}")
+        dev = fl.device
+        j = self.decoder.num_joints
+        if j != self.nj:
+            raise ValueError(f"nj={self.nj} but cfg.MODEL.NUM_JOINTS={j} (the reference would fail in dlt)")
+        pil = pir = None
+        if proj_inv_list is not None:
+            pil = _as_f32_cuda(proj_inv_list[0], "proj_inv_list")
+            pir = _as_f32_cuda(proj_inv_list[1], "proj_inv_list")
+        handle = self._packed.get(_decoder_tensors(self.decoder, "decoder."), dev, cf=self.CF)
+        L = _lib.lib()
+        nbytes = C.c_size_t()
+        _lib.check(L.cdr_head_workspace_bytes(handle, b, C.byref(nbytes)))
+        ws = _workspace(dev, nbytes.value)
+        kp_l = torch.empty((b, j, 2), dtype=torch.float32, device=dev)
+        kp_r = torch.empty((b, j, 2), dtype=torch.float32, device=dev)
+        xyz = torch.empty((b, j, 3), dtype=torch.float32, device=dev)
+        tap_struct, tap_out = None, None
+        if taps:
+            tap_out = {
+                "pinv": torch.empty((2, b, 4, 3), dtype=torch.float32, device=dev),
+                "cf_cat": torch.empty((b, 64, 800), dtype=torch.float32, device=dev),
+                "cf_f": torch.empty((b, 64, 400), dtype=torch.float32, device=dev),
+                "f_out": torch.empty((2, b, 64, 2048), dtype=torch.float32, device=dev),
+                "heatmaps": torch.empty((2, b, j, 64, 64), dtype=torch.float32, device=dev),
+            }
+            tap_struct = _lib.CdrHeadTaps()
+            for k, t in tap_out.items():
+                setattr(tap_struct, k, t.data_ptr())
+        with torch.cuda.device(dev):
+            _lib.check(L.cdr_head_forward(
+                handle, _lib.ptr(fl), _lib.ptr(fr), _lib.ptr(pl), _lib.ptr(pr), _lib.ptr(pil),
+                _lib.ptr(pir), PINV_RTOL_FP32, b, int(img_size), _lib.ptr(kp_l), _lib.ptr(kp_r),
+                _lib.ptr(xyz), C.byref(tap_struct) if taps else None, _lib.ptr(ws), nbytes.value,
+                _lib.current_stream_ptr(dev)))
+        if taps:
+            return [kp_l, kp_r], xyz, tap_out
+        return [kp_l, kp_r], xyz
+
+    def forward(self, xs, proj_list):
+        """xs: list[2] of (B,3,S,S) images; proj_list: list[2] of (B,3,4).
+        Returns ([kp_left, kp_right] each (B,J,2) in image pixels, xyz (B,J,3))."""
+        _require_eval(self)
+        img_size = int(xs[0].size(2))                             # models/cdrnet.py:229
+        with torch.no_grad():
+            zs = [self.encoder(xs[i]) for i in range(self.n_views)]  # :231-234 (torch/cuDNN)
+        return self.head(zs, proj_list, img_size=img_size)
+
+
+class PoseResNet(nn.Module):
+    """models/poseresnet.py:10-38: ResNet encoder (torch/cuDNN) + PoseDecoder (libcdrhead)."""
+
+    def __init__(self, cfg, precision="fp32"):
+        super().__init__()
+        self.encoder = ResNet(cfg)
+        self.decoder = PoseDecoder(cfg, precision)
+
+    def forward(self, x):
+        with torch.no_grad():
+            feats = self.encoder(x)
+        return self.decoder(feats)
+
+    def init_weights(self, pretrained=""):
+        import os
+        if not os.path.isfile(pretrained):
+            raise ValueError("Pretrained model '{}' does not exist.".format(pretrained))
+        self.decoder.init_weights()
+        ckpt = torch.load(pretrained)
+        self.load_state_dict({k: v for k, v in ckpt.items() if k.startswith("encoder")},
+                             strict=False)

@@ -1,0 +1,375 @@
+// C ABI of libcdrhead.so: error state, packed-weight handles, workspace planning and the
+// orchestration of the head / decoder forward passes (include/cdrhead.h).
+#include <new>
+#include <string.h>
+
+#include "kernels.h"
+#include "tc_api.h"
+
+namespace cdr {
+
+static thread_local char g_err[512] = "";
+static thread_local unsigned long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += (unsigned long long)n; }
+
+struct Bump {  // 256-byte aligned bump allocator over a caller-provided region
+  uint8_t* base;
+  size_t off = 0;
+  explicit Bump(void* b) : base((uint8_t*)b) {}
+  template <typename T>
+  T* take(size_t count) {
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += round_up<size_t>(count * sizeof(T), 256);
+    return p;
+  }
+};
+
+}  // namespace cdr
+
+using namespace cdr;
+
+// ------------------------------------------------------------------------------------------
+struct CdrWeights {
+  int precision = 0, joints = 0, has_fusion = 0, fin_npad = 0;
+  void* pool = nullptr;
+  // fp32 path: B operands as [K][n_pad]
+  float *w_cf1 = nullptr, *b_cf1 = nullptr, *w_cf2a = nullptr, *b_cf2a = nullptr;
+  float *w_cf2b = nullptr, *b_cf2b = nullptr, *w_out = nullptr, *b_out = nullptr;
+  float *w_dc[3] = {nullptr, nullptr, nullptr}, *b_dc[3] = {nullptr, nullptr, nullptr};
+  float *w_fin = nullptr, *b_fin = nullptr;
+  TcWeights tc;  // bf16 tensor-core path (gemm_tc.cu)
+};
+
+static constexpr int kCf1NPad = 384, kCf2NPad = 512;
+static const int kDcCin[3] = {kFeatC, kDecC, kDecC};
+
+static void plan_fp32_weights(CdrWeights& w, Bump& b) {
+  if (w.has_fusion) {
+    w.w_cf1 = b.take<float>((size_t)kFeatC * kCf1NPad);
+    w.b_cf1 = b.take<float>(kCf1NPad);
+    w.w_cf2a = b.take<float>((size_t)2 * kHid2 * kCf2NPad);
+    w.b_cf2a = b.take<float>(kCf2NPad);
+    w.w_cf2b = b.take<float>((size_t)kHid2 * kCf2NPad);
+    w.b_cf2b = b.take<float>(kCf2NPad);
+    w.w_out = b.take<float>((size_t)2 * kHid1Pad * kFeatC);
+    w.b_out = b.take<float>((size_t)2 * kFeatC);
+  }
+  for (int i = 0; i < 3; ++i) {
+    w.w_dc[i] = b.take<float>((size_t)16 * kDcCin[i] * kDecC);
+    w.b_dc[i] = b.take<float>(kDecC);
+  }
+  w.w_fin = b.take<float>((size_t)kDecC * w.fin_npad);
+  w.b_fin = b.take<float>(w.fin_npad);
+}
+
+extern "C" int cdr_abi_version(void) { return CDRHEAD_ABI_VERSION; }
+extern "C" const char* cdr_last_error(void) { return g_err; }
+extern "C" unsigned long long cdr_launch_count(void) { return g_launches; }
+extern "C" void cdr_launch_count_reset(void) { g_launches = 0; }
+
+extern "C" int cdr_weights_create(const CdrWeightPtrs* src, int precision, void* stream,
+                                  CdrWeights** out) {
+  CDR_CHECK_ARG(src && out, "cdr_weights_create: null argument");
+  CDR_CHECK_ARG(precision == CDR_PREC_FP32 || precision == CDR_PREC_BF16,
+                "cdr_weights_create: unknown precision %d", precision);
+  CDR_CHECK_ARG(src->num_joints > 0 && src->num_joints <= kMaxJoints,
+                "cdr_weights_create: num_joints must be 1..%d", kMaxJoints);
+  for (int i = 0; i < 3; ++i)
+    CDR_CHECK_ARG(src->deconv[i].weight && src->deconv[i].bn_weight && src->deconv[i].bn_bias &&
+                      src->deconv[i].bn_mean && src->deconv[i].bn_var,
+                  "cdr_weights_create: decoder.deconv%d tensors missing", i + 1);
+  CDR_CHECK_ARG(src->final_layer.weight && src->final_layer.bias,
+                "cdr_weights_create: decoder.final_layer tensors missing");
+  if (src->has_fusion) {
+    const CdrConvBn* cf[5] = {&src->cf_conv1, &src->cf_conv2a, &src->cf_conv2b, &src->cf_out[0],
+                              &src->cf_out[1]};
+    for (const CdrConvBn* c : cf)
+      CDR_CHECK_ARG(c->weight && c->bias && c->bn_weight && c->bn_bias && c->bn_mean && c->bn_var,
+                    "cdr_weights_create: a CF.* tensor is missing");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  CdrWeights* w = new (std::nothrow) CdrWeights();
+  CDR_CHECK_ARG(w, "cdr_weights_create: out of host memory");
+  w->precision = precision;
+  w->joints = src->num_joints;
+  w->has_fusion = src->has_fusion;
+  w->fin_npad = src->num_joints <= 32 ? 32 : round_up(src->num_joints, 128);
+
+  int rc = CDR_OK;
+  auto fail = [&](int code) {
+    if (w->pool) cudaFree(w->pool);
+    delete w;
+    return code;
+  };
+  if (precision == CDR_PREC_FP32) {
+    Bump sizing(nullptr);
+    plan_fp32_weights(*w, sizing);
+    cudaError_t e = cudaMalloc(&w->pool, sizing.off);
+    if (e != cudaSuccess) {
+      set_error("cdr_weights_create: cudaMalloc(%zu) failed: %s", sizing.off, cudaGetErrorString(e));
+      w->pool = nullptr;
+      return fail(CDR_ERR_CUDA);
+    }
+    Bump b(w->pool);
+    plan_fp32_weights(*w, b);
+    if (w->has_fusion) {
+      if ((rc = launch_pack_conv1x1_f32(src->cf_conv1, kHid1, kFeatC, kFeatC, kCf1NPad, w->w_cf1, w->b_cf1, st))) return fail(rc);
+      if ((rc = launch_pack_conv1x1_f32(src->cf_conv2a, kHid2, 2 * kHid2, 2 * kHid2, kCf2NPad, w->w_cf2a, w->b_cf2a, st))) return fail(rc);
+      if ((rc = launch_pack_conv1x1_f32(src->cf_conv2b, kHid2, kHid2, kHid2, kCf2NPad, w->w_cf2b, w->b_cf2b, st))) return fail(rc);
+      for (int v = 0; v < 2; ++v)
+        if ((rc = launch_pack_conv1x1_f32(src->cf_out[v], kFeatC, kHid1, kHid1Pad, kFeatC,
+                                          w->w_out + (size_t)v * kHid1Pad * kFeatC,
+                                          w->b_out + (size_t)v * kFeatC, st)))
+          return fail(rc);
+    }
+    for (int i = 0; i < 3; ++i)
+      if ((rc = launch_pack_deconv_f32(src->deconv[i], kDcCin[i], kDecC, kDecC, w->w_dc[i], w->b_dc[i], st)))
+        return fail(rc);
+    if ((rc = launch_pack_conv1x1_f32(src->final_layer, w->joints, kDecC, kDecC, w->fin_npad, w->w_fin, w->b_fin, st)))
+      return fail(rc);
+  } else {
+    if ((rc = tc_weights_create(*src, w->tc, st))) return fail(rc);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    set_error("cdr_weights_create: packing failed: %s", cudaGetErrorString(e));
+    if (precision == CDR_PREC_BF16) tc_weights_destroy(w->tc);
+    return fail(CDR_ERR_CUDA);
+  }
+  *out = w;
+  return CDR_OK;
+}
+
+extern "C" int cdr_weights_destroy(CdrWeights* w) {
+  if (!w) return CDR_OK;
+  if (w->pool) cudaFree(w->pool);
+  tc_weights_destroy(w->tc);
+  delete w;
+  return CDR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace plans
+struct HeadWs {
+  float *pinv, *x0, *y1, *z, *f1, *f2, *g, *x1, *d1, *d2, *d3, *hm;
+  size_t bytes;
+};
+static HeadWs plan_head_f32(void* base, int B, int J) {
+  Bump b(base);
+  const size_t N = 2 * (size_t)B;
+  HeadWs w;
+  w.pinv = b.take<float>(N * 12);
+  w.x0 = b.take<float>(N * kFeatHW * kFeatC);
+  w.y1 = b.take<float>(N * kFeatHW * kHid1Pad);
+  w.z = b.take<float>((size_t)B * kFeatHW * 2 * kHid2);
+  w.f1 = b.take<float>((size_t)B * kFeatHW * kHid2);
+  w.f2 = b.take<float>((size_t)B * kFeatHW * kHid2);
+  w.g = b.take<float>(N * kFeatHW * kHid1Pad);
+  w.x1 = b.take<float>(N * kFeatHW * kFeatC);
+  w.d1 = b.take<float>(N * 256 * kDecC);
+  w.d2 = b.take<float>(N * 1024 * kDecC);
+  w.d3 = b.take<float>(N * 4096 * kDecC);
+  w.hm = b.take<float>(N * J * 4096);
+  w.bytes = b.off;
+  return w;
+}
+struct DecWs {
+  float *x1, *d1, *d2, *d3;
+  size_t bytes;
+};
+static DecWs plan_dec_f32(void* base, int N) {
+  Bump b(base);
+  DecWs w;
+  w.x1 = b.take<float>((size_t)N * kFeatHW * kFeatC);
+  w.d1 = b.take<float>((size_t)N * 256 * kDecC);
+  w.d2 = b.take<float>((size_t)N * 1024 * kDecC);
+  w.d3 = b.take<float>((size_t)N * 4096 * kDecC);
+  w.bytes = b.off;
+  return w;
+}
+
+extern "C" int cdr_head_workspace_bytes(const CdrWeights* w, int batch, size_t* bytes) {
+  CDR_CHECK_ARG(w && bytes && batch > 0, "cdr_head_workspace_bytes: bad args");
+  CDR_CHECK_ARG(w->has_fusion, "cdr_head_workspace_bytes: decoder-only weights");
+  if (w->precision == CDR_PREC_BF16) return tc_head_workspace_bytes(w->tc, batch, bytes);
+  *bytes = plan_head_f32(nullptr, batch, w->joints).bytes;
+  return CDR_OK;
+}
+extern "C" int cdr_decoder_workspace_bytes(const CdrWeights* w, int n_images, size_t* bytes) {
+  CDR_CHECK_ARG(w && bytes && n_images > 0, "cdr_decoder_workspace_bytes: bad args");
+  if (w->precision == CDR_PREC_BF16) return tc_decoder_workspace_bytes(w->tc, n_images, bytes);
+  *bytes = plan_dec_f32(nullptr, n_images).bytes;
+  return CDR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 decoder: three transposed convs + the 1x1 head (models/decoder.py:39-46)
+static int decoder_f32(const CdrWeights* w, const float* x1, int N, float* d1, float* d2, float* d3,
+                       float* heat, cudaStream_t st) {
+  const float* in = x1;
+  float* outs[3] = {d1, d2, d3};
+  int side = 8;
+  for (int i = 0; i < 3; ++i) {
+    TapGemmParams p{};
+    p.A = in;
+    p.a_pitch = kDcCin[i];
+    p.n_img = N;
+    p.H = p.W = side;
+    p.cin = kDcCin[i];
+    p.deconv = 1;
+    p.Wp = w->w_dc[i];
+    p.w_group_stride = (long long)4 * kDcCin[i] * kDecC;
+    p.bias = w->b_dc[i];
+    p.bias_group_stride = 0;
+    p.n_pad = kDecC;
+    p.n = kDecC;
+    p.C = outs[i];
+    p.c_pitch = kDecC;
+    p.c_fill = kDecC;
+    p.relu = 1;
+    p.out_mode = kOutDeconv;
+    if (int rc = launch_tap_gemm_ffma(p, 4, st)) return rc;
+    in = outs[i];
+    side *= 2;
+  }
+  TapGemmParams p{};
+  p.A = d3;
+  p.a_pitch = kDecC;
+  p.n_img = N;
+  p.H = p.W = kHeat;
+  p.cin = kDecC;
+  p.Wp = w->w_fin;
+  p.bias = w->b_fin;
+  p.n_pad = w->fin_npad;
+  p.n = w->joints;
+  p.C = heat;
+  p.c_pitch = 4;
+  p.c_fill = 4;
+  p.relu = 0;
+  p.out_mode = kOutPlanar;
+  return launch_tap_gemm_ffma(p, 1, st);
+}
+
+static int copy_tap(float* dst, const float* src, size_t count, cudaStream_t st) {
+  if (!dst) return CDR_OK;
+  CDR_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return CDR_OK;
+}
+
+extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const float* feat_r,
+                                const float* P_l, const float* P_r, const float* pinv_l,
+                                const float* pinv_r, double pinv_rtol, int batch, int img_size,
+                                float* kp2d_l, float* kp2d_r, float* xyz, const CdrHeadTaps* taps,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  CDR_CHECK_ARG(w && feat_l && feat_r && P_l && P_r && kp2d_l && kp2d_r && xyz && workspace,
+                "cdr_head_forward: null pointer");
+  CDR_CHECK_ARG(w->has_fusion, "cdr_head_forward: weights were created without the fusion block");
+  CDR_CHECK_ARG(batch > 0 && img_size > 0, "cdr_head_forward: bad batch/img_size");
+  CDR_CHECK_ARG((pinv_l == nullptr) == (pinv_r == nullptr),
+                "cdr_head_forward: give both pseudo-inverses or neither");
+  CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "cdr_head_forward: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float scale = (float)img_size / (float)kHeat;   // models/cdrnet.py:250
+  if (w->precision == CDR_PREC_BF16)
+    return tc_head_forward(w->tc, feat_l, feat_r, P_l, P_r, pinv_l, pinv_r, pinv_rtol, batch, scale,
+                           kp2d_l, kp2d_r, xyz, taps, workspace, workspace_bytes, st);
+
+  const int B = batch, N = 2 * batch, J = w->joints;
+  HeadWs ws = plan_head_f32(workspace, B, J);
+  if (ws.bytes > workspace_bytes) {
+    set_error("cdr_head_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
+    return CDR_ERR_WORKSPACE;
+  }
+  int rc;
+  // (1) P^+  — models/cdrnet.py:236-237
+  const float* pinv[2] = {pinv_l, pinv_r};
+  if (!pinv_l) {
+    if ((rc = cdr_pinv(P_l, B, pinv_rtol, ws.pinv, st))) return rc;
+    if ((rc = cdr_pinv(P_r, B, pinv_rtol, ws.pinv + (size_t)B * 12, st))) return rc;
+    pinv[0] = ws.pinv;
+    pinv[1] = ws.pinv + (size_t)B * 12;
+  }
+  // (2) encoder latents NCHW -> pixel-major rows, views stacked (conv_layer1 is shared)
+  if ((rc = launch_nchw_to_rows_f32(feat_l, B, kFeatC, kFeatHW, ws.x0, kFeatC, st))) return rc;
+  if ((rc = launch_nchw_to_rows_f32(feat_r, B, kFeatC, kFeatHW, ws.x0 + (size_t)B * kFeatHW * kFeatC, kFeatC, st))) return rc;
+  // (3) conv_layer1 2048 -> 300 (+BN+ReLU) — :62
+  {
+    TapGemmParams p{};
+    p.A = ws.x0; p.a_pitch = kFeatC; p.n_img = N; p.H = p.W = 8; p.cin = kFeatC;
+    p.Wp = w->w_cf1; p.bias = w->b_cf1; p.n_pad = kCf1NPad; p.n = kHid1;
+    p.C = ws.y1; p.c_pitch = kHid1Pad; p.c_fill = kHid1Pad; p.relu = 1; p.out_mode = kOutRows;
+    if ((rc = launch_tap_gemm_ffma(p, 1, st))) return rc;
+  }
+  // (4) inverse FTL into the concatenated (B,64,800) buffer — :65,70
+  for (int v = 0; v < 2; ++v)
+    if ((rc = launch_ftl<float>(ws.y1 + (size_t)v * B * kFeatHW * kHid1Pad, kHid1Pad, pinv[v], 4, 3,
+                                kFtlBlk, B, kFeatHW, ws.z + v * kHid2, 2 * kHid2, kHid2, st)))
+      return rc;
+  // (5) conv_layer2: 800 -> 400 -> 400 — :74
+  {
+    TapGemmParams p{};
+    p.A = ws.z; p.a_pitch = 2 * kHid2; p.n_img = B; p.H = p.W = 8; p.cin = 2 * kHid2;
+    p.Wp = w->w_cf2a; p.bias = w->b_cf2a; p.n_pad = kCf2NPad; p.n = kHid2;
+    p.C = ws.f1; p.c_pitch = kHid2; p.c_fill = kHid2; p.relu = 1; p.out_mode = kOutRows;
+    if ((rc = launch_tap_gemm_ffma(p, 1, st))) return rc;
+    p.A = ws.f1; p.a_pitch = kHid2; p.cin = kHid2; p.Wp = w->w_cf2b; p.bias = w->b_cf2b; p.C = ws.f2;
+    if ((rc = launch_tap_gemm_ffma(p, 1, st))) return rc;
+  }
+  // (6) forward FTL per view — :79
+  const float* Pv[2] = {P_l, P_r};
+  for (int v = 0; v < 2; ++v)
+    if ((rc = launch_ftl<float>(ws.f2, kHid2, Pv[v], 3, 4, kFtlBlk, B, kFeatHW,
+                                ws.g + (size_t)v * B * kFeatHW * kHid1Pad, kHid1Pad, kHid1Pad, st)))
+      return rc;
+  // (7) out_layer[v] 300 -> 2048, per-view weights = 2 groups — :81
+  {
+    TapGemmParams p{};
+    p.A = ws.g; p.a_group_stride = (long long)B * kFeatHW * kHid1Pad; p.a_pitch = kHid1Pad;
+    p.n_img = B; p.H = p.W = 8; p.cin = kHid1Pad;
+    p.Wp = w->w_out; p.w_group_stride = (long long)kHid1Pad * kFeatC;
+    p.bias = w->b_out; p.bias_group_stride = kFeatC; p.n_pad = kFeatC; p.n = kFeatC;
+    p.C = ws.x1; p.c_group_stride = (long long)B * kFeatHW * kFeatC; p.c_pitch = kFeatC;
+    p.c_fill = kFeatC; p.relu = 1; p.out_mode = kOutRows;
+    if ((rc = launch_tap_gemm_ffma(p, 2, st))) return rc;
+  }
+  // (8) decoder on both views at once (shared weights) — :243-244
+  if ((rc = decoder_f32(w, ws.x1, N, ws.d1, ws.d2, ws.d3, ws.hm, st))) return rc;
+  // (9) soft-argmax + DLT — :247-266
+  if ((rc = cdr_softargmax_dlt(ws.hm, ws.hm + (size_t)B * J * 4096, 0, P_l, P_r, B, J, kHeat, kHeat,
+                               scale, kp2d_l, kp2d_r, xyz, nullptr, nullptr, nullptr, nullptr,
+                               nullptr, st)))
+    return rc;
+  if (taps) {
+    if ((rc = copy_tap(taps->pinv, pinv[0], (size_t)B * 12, st))) return rc;
+    if ((rc = copy_tap(taps->pinv ? taps->pinv + (size_t)B * 12 : nullptr, pinv[1], (size_t)B * 12, st))) return rc;
+    if ((rc = copy_tap(taps->cf_cat, ws.z, (size_t)B * kFeatHW * 2 * kHid2, st))) return rc;
+    if ((rc = copy_tap(taps->cf_f, ws.f2, (size_t)B * kFeatHW * kHid2, st))) return rc;
+    if ((rc = copy_tap(taps->f_out, ws.x1, (size_t)N * kFeatHW * kFeatC, st))) return rc;
+    if ((rc = copy_tap(taps->heatmaps, ws.hm, (size_t)N * J * 4096, st))) return rc;
+  }
+  return CDR_OK;
+}
+
+extern "C" int cdr_decoder_forward(const CdrWeights* w, const float* feat, int n_images,
+                                   float* heatmaps, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  CDR_CHECK_ARG(w && feat && heatmaps && workspace && n_images > 0, "cdr_decoder_forward: bad args");
+  CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "cdr_decoder_forward: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (w->precision == CDR_PREC_BF16)
+    return tc_decoder_forward(w->tc, feat, n_images, heatmaps, workspace, workspace_bytes, st);
+  DecWs ws = plan_dec_f32(workspace, n_images);
+  if (ws.bytes > workspace_bytes) {
+    set_error("cdr_decoder_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
+    return CDR_ERR_WORKSPACE;
+  }
+  if (int rc = launch_nchw_to_rows_f32(feat, n_images, kFeatC, kFeatHW, ws.x1, kFeatC, st)) return rc;
+  return decoder_f32(w, ws.x1, n_images, ws.d1, ws.d2, ws.d3, heatmaps, st);
+}

@@ -1,0 +1,73 @@
+// Shared helpers for libcdrhead.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/cdrhead.h"
+
+namespace cdr {
+
+// thread-local error string + launch counter (the only mutable global state)
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define CDR_CHECK_ARG(cond, ...)                 \
+  do {                                           \
+    if (!(cond)) {                               \
+      cdr::set_error(__VA_ARGS__);               \
+      return CDR_ERR_INVALID;                    \
+    }                                            \
+  } while (0)
+
+#define CDR_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      cdr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),        \
+                     __FILE__, __LINE__);                                           \
+      return CDR_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+// check the launch that just happened
+#define CDR_LAUNCH_OK(name)                                                         \
+  do {                                                                              \
+    cudaError_t _e = cudaGetLastError();                                            \
+    if (_e != cudaSuccess) {                                                        \
+      cdr::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));      \
+      return CDR_ERR_CUDA;                                                          \
+    }                                                                               \
+    cdr::count_launch();                                                            \
+  } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
+template <typename T>
+__host__ __device__ constexpr T round_up(T a, T b) { return ceil_div(a, b) * b; }
+
+// ---- fixed geometry of the head (models/cdrnet.py:89-91, models/decoder.py:8-13) ----
+constexpr int kFeatC = 2048;   // encoder channels = fusion_in_dim
+constexpr int kFeatHW = 64;    // 8x8 latent
+constexpr int kHid1 = 300;     // fusion_hid_ch1
+constexpr int kHid1Pad = 304;  // channel pitch of 300-channel buffers (16-B rows for bf16, K%16 for fp32)
+constexpr int kHid2 = 400;     // fusion_hid_ch2
+constexpr int kFtlBlk = 100;   // channels per FTL "coordinate" block: 300/3 = 400/4
+constexpr int kDecC = 256;     // deconv output channels
+constexpr int kHeat = 64;      // heat-map side
+constexpr int kMaxJoints = 64;
+
+}  // namespace cdr

@@ -1,0 +1,137 @@
+// One-sided (Hestenes) Jacobi SVD on tiny matrices held in registers, fp64.
+//
+// Why not eig(A^T A): the DLT system has entries ~4e5 next to ~1 (P = K[R|t] in pixels x
+// millimetres), so forming A^T A squares a condition number of ~1e6.
+// Rotating the columns of A directly keeps the relative accuracy of the small singular
+// vectors at ~eps*cond(A) in fp64, far below the 1e-2 mm parity gate.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace cdr {
+
+// Orthogonalise the C columns of G (R x C, column access G[r][c]) in place by plane
+// rotations from the right, accumulating them into V (C x C, starts as identity).
+// On exit G = U*Sigma (column norms are the singular values) and A_original * V = G.
+template <int R, int C>
+__host__ __device__ __forceinline__ void jacobi_onesided(double (&G)[R][C], double (&V)[C][C]) {
+#pragma unroll
+  for (int i = 0; i < C; ++i)
+#pragma unroll
+    for (int j = 0; j < C; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+
+  const double tol = 1e-15;
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    bool rotated = false;
+#pragma unroll
+    for (int p = 0; p < C - 1; ++p) {
+#pragma unroll
+      for (int q = p + 1; q < C; ++q) {
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          alpha = fma(G[r][p], G[r][p], alpha);
+          beta = fma(G[r][q], G[r][q], beta);
+          gamma = fma(G[r][p], G[r][q], gamma);
+        }
+        // skip when the pair is already orthogonal to working precision (also covers
+        // zero columns: gamma == 0)
+        if (fabs(gamma) > tol * sqrt(alpha * beta) && gamma != 0.0) {
+          rotated = true;
+          const double zeta = (beta - alpha) / (2.0 * gamma);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + t * t);
+          const double s = c * t;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const double gp = G[r][p], gq = G[r][q];
+            G[r][p] = c * gp - s * gq;
+            G[r][q] = s * gp + c * gq;
+          }
+#pragma unroll
+          for (int r = 0; r < C; ++r) {
+            const double vp = V[r][p], vq = V[r][q];
+            V[r][p] = c * vp - s * vq;
+            V[r][q] = s * vp + c * vq;
+          }
+        }
+      }
+    }
+    if (!rotated) break;
+  }
+}
+
+// Null-space direction of a 4x4 DLT system: right singular vector of the smallest
+// singular value, de-homogenised (x/w, y/w, z/w).  No guard on w ~ 0: like the reference
+// (models/cdrnet.py:175-177) this returns inf/nan for points at infinity.
+__host__ __device__ __forceinline__ void dlt_solve4(double (&A)[4][4], double& x, double& y, double& z) {
+  double V[4][4];
+  jacobi_onesided<4, 4>(A, V);
+  double best = INFINITY;
+  int k = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    double n2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) n2 = fma(A[r][c], A[r][c], n2);
+    if (n2 < best) { best = n2; k = c; }
+  }
+  double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {   // select without dynamic register indexing
+    if (c == k) { v0 = V[0][c]; v1 = V[1][c]; v2 = V[2][c]; v3 = V[3][c]; }
+  }
+  x = v0 / v3;
+  y = v1 / v3;
+  z = v2 / v3;
+}
+
+// Rows of the reference's DLT system for one view (models/cdrnet.py:169-171):
+//   [u*P[2] - P[0] ; v*P[2] - P[1]]   with P row-major 3x4.
+template <typename TP>
+__host__ __device__ __forceinline__ void dlt_rows(const TP* __restrict__ P, double u, double v,
+                                         double (&A)[4][4], int row0) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const double p2 = (double)P[8 + c];
+    A[row0][c] = u * p2 - (double)P[c];
+    A[row0 + 1][c] = v * p2 - (double)P[4 + c];
+  }
+}
+
+// Moore-Penrose pseudo-inverse of a row-major 3x4 matrix with torch.linalg.pinv's
+// semantics (models/cdrnet.py:236-237): singular values <= rtol*sigma_max are dropped.
+// Works on G = P^T (4x3): G V = U Sigma, so pinv(P) = sum_i G_i V_i^T / sigma_i^2 (4x3).
+template <typename TIn, typename TOut>
+__host__ __device__ __forceinline__ void pinv_3x4(const TIn* __restrict__ P, double rtol,
+                                                  TOut* __restrict__ out) {
+  double G[4][3], V[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) G[c][r] = (double)P[r * 4 + c];
+  jacobi_onesided<4, 3>(G, V);
+  double s2[3], smax2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    s2[i] = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s2[i] = fma(G[r][i], G[r][i], s2[i]);
+    smax2 = s2[i] > smax2 ? s2[i] : smax2;
+  }
+  const double cut2 = rtol * rtol * smax2;
+  double inv[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) inv[i] = (s2[i] > cut2 && s2[i] > 0.0) ? 1.0 / s2[i] : 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) acc = fma(G[a][i] * inv[i], V[b][i], acc);
+      out[a * 3 + b] = (TOut)acc;
+    }
+}
+
+}  // namespace cdr

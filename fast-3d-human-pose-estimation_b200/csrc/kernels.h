@@ -1,0 +1,50 @@
+// Internal launcher declarations shared by the translation units of libcdrhead.so.
+#pragma once
+#include "common.cuh"
+
+namespace cdr {
+
+enum OutMode { kOutRows = 0, kOutDeconv = 1, kOutPlanar = 2 };
+
+// One "tap-GEMM" problem (see gemm_ffma.cu / gemm_tc.cu for the arithmetic).
+struct TapGemmParams {
+  const void* A;            // pixel-major activations (n_img, H, W, a_pitch); fp32 or bf16
+  long long a_group_stride; // elements between groups (non-deconv grouped launches)
+  int a_pitch;              // channel pitch in elements
+  int n_img, H, W;          // M = n_img*H*W
+  int cin;                  // K per tap
+  int deconv;               // 1: 4 taps, group index = output phase (py*2+px)
+  const void* Wp;           // packed weights, layout depends on the path (pack.cu)
+  long long w_group_stride; // elements between groups / phases
+  const float* bias;        // (groups, n_pad) folded bias, fp32
+  int bias_group_stride;
+  int n_pad;                // padded output channels of the packed weights
+  int n;                    // valid output channels
+  void* C;
+  long long c_group_stride;
+  int c_pitch;              // output row pitch (elements) for kOutRows / kOutDeconv
+  int c_fill;               // columns [n, c_fill) are written as zeros
+  int relu;
+  int out_mode;
+};
+
+int launch_tap_gemm_ffma(const TapGemmParams& p, int groups, cudaStream_t st);
+
+// layout.cu
+int launch_nchw_to_rows_f32(const float* in, int n_img, int C, int HW, float* out, int out_pitch,
+                            cudaStream_t st);
+int launch_nchw_to_rows_bf16(const float* in, int n_img, int C, int HW, __nv_bfloat16* out,
+                             int out_pitch, cudaStream_t st);
+template <typename T>
+int launch_ftl(const T* in, int in_pitch, const float* mats, int rows, int cols, int blk, int n,
+               int hw, T* out, int out_pitch, int out_fill, cudaStream_t st);
+
+// pack.cu: BN folding + re-layout of the reference's parameter tensors
+//   conv 1x1 (Cout,Cin) -> fp32 [k_pad][n_pad] (rows k >= Cin and cols n >= Cout zero)
+int launch_pack_conv1x1_f32(const CdrConvBn& src, int cout, int cin, int k_pad, int n_pad,
+                            float* w_out, float* bias_out, cudaStream_t st);
+//   deconv (Cin,Cout,4,4) -> fp32 [phase][tap][Cin][n_pad]
+int launch_pack_deconv_f32(const CdrConvBn& src, int cin, int cout, int n_pad, float* w_out,
+                           float* bias_out, cudaStream_t st);
+
+}  // namespace cdr

@@ -1,0 +1,107 @@
+// Layout kernels: NCHW -> pixel-major rows, and the feature transform layer (FTL).
+// Both are pure data movement / AXPY work: HBM-bound, coalesced 128-byte accesses.
+#include "kernels.h"
+
+namespace cdr {
+
+// (n_img, C, HW) fp32  ->  (n_img*HW, out_pitch) rows of C channels.  One 32-channel x
+// 64-pixel tile per block through padded shared memory so that both the reads (along
+// pixels) and the writes (along channels) are full 128-byte lines.
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+nchw_to_rows_kernel(const float* __restrict__ in, int C, int HW, TOut* __restrict__ out,
+                    int out_pitch) {
+  __shared__ float tile[32][65];
+  const int c0 = blockIdx.x * 32, p0 = blockIdx.y * 64, img = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int c = ty; c < 32; c += 8) {
+    const float* src = in + ((size_t)img * C + c0 + c) * HW + p0;
+    if (c0 + c < C) {
+      if (p0 + tx < HW) tile[c][tx] = src[tx];
+      if (p0 + tx + 32 < HW) tile[c][tx + 32] = src[tx + 32];
+    }
+  }
+  __syncthreads();
+  if (c0 + tx < C) {
+    for (int pp = ty; pp < 64; pp += 8) {
+      if (p0 + pp < HW)
+        out[((size_t)img * HW + p0 + pp) * out_pitch + c0 + tx] = (TOut)tile[tx][pp];
+    }
+  }
+}
+
+template <typename TOut>
+static int launch_nchw_to_rows(const float* in, int n_img, int C, int HW, TOut* out, int out_pitch,
+                               cudaStream_t st) {
+  CDR_CHECK_ARG(in && out && n_img > 0 && C > 0 && HW > 0 && out_pitch >= C, "nchw_to_rows: bad args");
+  dim3 grid(ceil_div(C, 32), ceil_div(HW, 64), n_img);
+  nchw_to_rows_kernel<TOut><<<grid, 256, 0, st>>>(in, C, HW, out, out_pitch);
+  CDR_LAUNCH_OK("nchw_to_rows_kernel");
+  return CDR_OK;
+}
+int launch_nchw_to_rows_f32(const float* in, int n_img, int C, int HW, float* out, int out_pitch,
+                            cudaStream_t st) {
+  return launch_nchw_to_rows<float>(in, n_img, C, HW, out, out_pitch, st);
+}
+int launch_nchw_to_rows_bf16(const float* in, int n_img, int C, int HW, __nv_bfloat16* out,
+                             int out_pitch, cudaStream_t st) {
+  return launch_nchw_to_rows<__nv_bfloat16>(in, n_img, C, HW, out, out_pitch, st);
+}
+
+// FTL (models/cdrnet.py:45-56) on pixel-major rows.  With z.reshape(b, N, -1) the k-th
+// "coordinate" of channel c is channel k*blk + c of the same pixel, so
+//   out[row, r*blk + c] = sum_k mats[img(row)][r][k] * in[row, k*blk + c].
+// One thread per (row, c); consecutive threads walk consecutive channels.
+template <typename T, int ROWS, int COLS>
+__global__ void __launch_bounds__(256)
+ftl_kernel(const T* __restrict__ in, int in_pitch, const float* __restrict__ mats, int blk,
+           long long total, int hw, T* __restrict__ out, int out_pitch, int out_fill) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long row = idx / blk;
+  const int c = (int)(idx - row * blk);
+  const float* m = mats + (row / hw) * (ROWS * COLS);
+  float x[COLS];
+#pragma unroll
+  for (int k = 0; k < COLS; ++k) x[k] = (float)in[row * in_pitch + k * blk + c];
+  T* o = out + row * out_pitch;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) acc = fmaf(__ldg(m + r * COLS + k), x[k], acc);
+    o[r * blk + c] = (T)acc;
+  }
+  if (c < out_fill - ROWS * blk) o[ROWS * blk + c] = (T)0.f;  // zero the pad columns
+}
+
+template <typename T>
+int launch_ftl(const T* in, int in_pitch, const float* mats, int rows, int cols, int blk, int n,
+               int hw, T* out, int out_pitch, int out_fill, cudaStream_t st) {
+  CDR_CHECK_ARG(in && mats && out && n > 0 && hw > 0 && blk > 0, "cdr_ftl: bad args");
+  CDR_CHECK_ARG(in_pitch >= cols * blk && out_pitch >= rows * blk && out_fill >= rows * blk &&
+                    out_fill <= out_pitch && out_fill - rows * blk <= blk,
+                "cdr_ftl: pitches too small for %dx%d blocks of %d", rows, cols, blk);
+  const long long total = (long long)n * hw * blk;
+  const unsigned grid = (unsigned)ceil_div<long long>(total, 256);
+  if (rows == 4 && cols == 3)
+    ftl_kernel<T, 4, 3><<<grid, 256, 0, st>>>(in, in_pitch, mats, blk, total, hw, out, out_pitch, out_fill);
+  else if (rows == 3 && cols == 4)
+    ftl_kernel<T, 3, 4><<<grid, 256, 0, st>>>(in, in_pitch, mats, blk, total, hw, out, out_pitch, out_fill);
+  else {
+    set_error("cdr_ftl: only (4x3) and (3x4) matrices are supported, got %dx%d", rows, cols);
+    return CDR_ERR_UNSUPPORTED;
+  }
+  CDR_LAUNCH_OK("ftl_kernel");
+  return CDR_OK;
+}
+template int launch_ftl<float>(const float*, int, const float*, int, int, int, int, int, float*, int, int, cudaStream_t);
+template int launch_ftl<__nv_bfloat16>(const __nv_bfloat16*, int, const float*, int, int, int, int, int, __nv_bfloat16*, int, int, cudaStream_t);
+
+}  // namespace cdr
+
+extern "C" int cdr_ftl(const float* in, int in_pitch, const float* mats, int rows, int cols, int blk,
+                       int n, int hw, float* out, int out_pitch, int out_fill, void* stream) {
+  return cdr::launch_ftl<float>(in, in_pitch, mats, rows, cols, blk, n, hw, out, out_pitch, out_fill,
+                                (cudaStream_t)stream);
+}

@@ -1,0 +1,73 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, stereo pairs split across ranks.
+
+Every stereo pair is independent in eval mode (BN uses running stats; FTL, softmax and DLT are
+per-sample — SURVEY.md §8e), so the data path needs no collective: rank r runs the whole head
+on pairs [r*ceil(B/G), (r+1)*ceil(B/G)) with replicated weights.  The only exchange is the
+result: ONE all-gather per batch that carries each rank's (n_r, J, 3) fp32 3D joints together
+with its four fp64 MPJPE partial sums (32 trailing bytes).  Every rank then adds the partial
+sums in rank order, so the global MPJPE is deterministic and equals ``calc_mpjpe`` on the
+concatenated batch (sum/count).  Over NVLink 5 / NVSwitch the message is tens of KB — latency
+bound — hence one collective, enqueued on the compute stream, no host synchronisation.
+
+Works with any torch.distributed backend: NCCL on GPUs, gloo on CPU tensors (tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+_SUM_BYTES = 4 * 8
+
+
+def shard_range(n, rank, world):
+    """Contiguous shard [lo, hi) of n items for `rank`; all shards but the tail have
+    ceil(n/world) items (tail shards may be short or empty)."""
+    per = -(-n // world)
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)
+
+
+def pack_result(xyz_local, sums_local, per):
+    """(n_r,J,3) fp32 + (4,) fp64 -> flat uint8 message of fixed size for a shard of `per` poses."""
+    j = xyz_local.shape[1]
+    buf = torch.zeros(per * j * 12 + _SUM_BYTES, dtype=torch.uint8, device=xyz_local.device)
+    n = xyz_local.shape[0]
+    if n:
+        buf[: n * j * 12] = xyz_local.contiguous().view(torch.uint8).reshape(-1)
+    buf[per * j * 12:] = sums_local.to(torch.float64).contiguous().view(torch.uint8).reshape(-1)
+    return buf
+
+
+def unpack_results(gathered, n_total, joints, world):
+    """Inverse of pack_result over the all-gathered (world, msg) buffer:
+    returns xyz (n_total, J, 3) fp32 and sums (4,) fp64 added in rank order."""
+    per = -(-n_total // world)
+    body = per * joints * 12
+    g = gathered.reshape(world, body + _SUM_BYTES)
+    xyz = g[:, :body].contiguous().view(torch.float32).reshape(world * per, joints, 3)[:n_total]
+    parts = g[:, body:].contiguous().view(torch.float64).reshape(world, 4)
+    sums = parts[0].clone()
+    for r in range(1, world):          # fixed order -> bit-reproducible
+        sums += parts[r]
+    return xyz, sums
+
+
+def gather_results(xyz_local, sums_local, n_total, group=None):
+    """The one collective of the path.  xyz_local: this rank's (n_r,J,3) fp32 3D joints;
+    sums_local: (4,) fp64 [sum|d2d_l|, sum|d2d_r|, sum|d3d|, count] (metrics.mpjpe_sums).
+    Returns (xyz (n_total,J,3), sums (4,)) identical on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    joints = xyz_local.shape[1]
+    per = -(-n_total // world)
+    msg = pack_result(xyz_local, sums_local, per)
+    if world == 1:
+        return unpack_results(msg, n_total, joints, 1)
+    out = torch.empty(world * msg.numel(), dtype=torch.uint8, device=msg.device)
+    dist.all_gather_into_tensor(out, msg, group=group)
+    return unpack_results(out, n_total, joints, world)
+
+
+def mpjpe_from_sums(sums):
+    """(error_2d, error_3d) of models/metrics.py:90-95 from the global sums."""
+    s = sums.detach().cpu().double()
+    return float((s[0] / s[3] + s[1] / s[3]) / 2), float(s[2] / s[3])

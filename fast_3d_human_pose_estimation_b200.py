@@ -1,0 +1,13 @@
+"""Import alias: the package directory is named ``fast-3d-human-pose-estimation_b200`` (not a
+valid Python identifier), so this module loads it under the importable name
+``fast_3d_human_pose_estimation_b200`` and replaces itself with it in ``sys.modules``."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fast-3d-human-pose-estimation_b200")
+_spec = importlib.util.spec_from_file_location(
+    __name__, os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,110 @@
+"""CPU: the oracle restatement (oracle/cdr_oracle.py) replays the vectors the REFERENCE produced
+(tests/golden/make_golden.py).  fp64 must agree to rounding; fp32 to a few ulps of the conv
+stack (CPU conv kernels may differ between hosts, so this is a tolerance, not bit-equality)."""
+import numpy as np
+import pytest
+import torch
+
+from fast_3d_human_pose_estimation_b200 import synth
+from oracle import cdr_oracle as O
+
+CASES = [("head_b2", 2, 19, True, True, "wide"),
+         ("head_b3_default_init", 3, 19, False, False, "wide"),
+         ("head_b1_j16_narrow", 1, 16, True, True, "narrow")]
+
+
+def _inputs(b, joints, calib, rbn, rig):
+    sd = synth.make_head_state_dict(seed=0, joints=joints, calibrated=calib, randomize_bn=rbn)
+    feats = synth.make_features(b, seed=1)
+    cams = synth.make_cameras(b, seed=2, rig=rig)
+    return sd, feats, cams
+
+
+@pytest.mark.parametrize("name,b,joints,calib,rbn,rig", CASES)
+def test_head_fp64_matches_reference(golden, name, b, joints, calib, rbn, rig):
+    sd, feats, cams = _inputs(b, joints, calib, rbn, rig)
+    sd64 = O.cast_state_dict(sd, torch.float64)
+    taps = {}
+    with torch.no_grad():
+        p2, p3 = O.head_forward(sd64, [f.double() for f in feats],
+                                [torch.from_numpy(cams["P_l"]).double(), torch.from_numpy(cams["P_r"]).double()],
+                                taps=taps)
+    np.testing.assert_allclose(p2[0].numpy(), golden[f"{name}.f64.kp_l"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(p2[1].numpy(), golden[f"{name}.f64.kp_r"], rtol=0, atol=1e-9)
+    ref3 = golden[f"{name}.f64.xyz"]
+    np.testing.assert_allclose(p3.numpy(), ref3, rtol=1e-9, atol=1e-6)
+    hm = torch.stack(taps["heatmaps"]).numpy()
+    np.testing.assert_allclose(hm[:, :, :, ::8, ::8], golden[f"{name}.f64.heat_sub"], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(taps["cf_f"].numpy()[:, ::16], golden[f"{name}.f64.cf_f_sub"], rtol=1e-10, atol=1e-9)
+
+
+@pytest.mark.parametrize("name,b,joints,calib,rbn,rig", CASES[:1])
+def test_head_fp32_matches_reference(golden, name, b, joints, calib, rbn, rig):
+    sd, feats, cams = _inputs(b, joints, calib, rbn, rig)
+    with torch.no_grad():
+        p2, p3 = O.head_forward(sd, feats, [torch.from_numpy(cams["P_l"]), torch.from_numpy(cams["P_r"])])
+    # same torch kernels as the reference -> identical up to CPU-kernel selection
+    np.testing.assert_allclose(p2[0].numpy(), golden[f"{name}.f32.kp_l"], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(p2[1].numpy(), golden[f"{name}.f32.kp_r"], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(p3.numpy(), golden[f"{name}.f32.xyz"], rtol=0, atol=0.5)
+
+
+@pytest.mark.parametrize("name,b,joints,calib,rbn,rig", CASES)
+def test_mpjpe_matches_reference(golden, name, b, joints, calib, rbn, rig):
+    cams = synth.make_cameras(b, seed=2, rig=rig)
+    gt = synth.make_gt(cams, joints=joints, seed=3)
+    p2 = [golden[f"{name}.f32.kp_l"], golden[f"{name}.f32.kp_r"]]
+    e = O.calc_mpjpe(p2, golden[f"{name}.f32.xyz"], gt["gt3d"], gt["gt2d_l"], gt["gt2d_r"],
+                     gt["vis"].astype(np.float32))
+    np.testing.assert_allclose(np.array(e), golden[f"{name}.mpjpe"], rtol=1e-12)
+    e = O.calc_mpjpe([p2[0][0], p2[1][0]], golden[f"{name}.f32.xyz"][0], gt["gt3d"][0], gt["gt2d_l"][0],
+                     gt["gt2d_r"][0], gt["vis"][0].astype(bool))
+    np.testing.assert_allclose(np.array(e), golden[f"{name}.mpjpe_frame0"], rtol=1e-12)
+
+
+def baseline_inputs():
+    rng = np.random.default_rng(11)
+    heat = rng.normal(size=(3, 19, 64, 64)).astype(np.float32)
+    heat[0, 0] = -np.abs(heat[0, 0])
+    heat[0, 1, 5, 7] = heat[0, 1, 40, 2] = 9.0
+    heat[1, 2] = 0.0
+    heat_r = rng.normal(size=(3, 19, 64, 64)).astype(np.float32)
+    return heat, heat_r, synth.make_cameras(3, seed=5)
+
+
+def test_baseline_path_matches_reference(golden):
+    heat, heat_r, cams = baseline_inputs()
+    preds, maxv = O.get_max_preds(heat)
+    assert np.array_equal(preds, golden["base.preds"]) and np.array_equal(maxv, golden["base.maxvals"])
+    assert preds[0, 0].tolist() == [0, 0] and preds[0, 1].tolist() == [7, 5]
+    u8_l, u8_r = O.baseline_keypoints(heat), O.baseline_keypoints(heat_r)
+    assert np.array_equal(u8_l, golden["base.u8_l"]) and np.array_equal(u8_r, golden["base.u8_r"])
+    for i in range(3):
+        PL = O.get_projection_matrix(cams["K"], cams["R_l"][i], cams["T_l"][i])
+        PR = O.get_projection_matrix(cams["K"], cams["R_r"][i], cams["T_r"][i])
+        np.testing.assert_allclose(O.triangulation(PL, PR, u8_l[i], u8_r[i]), golden["base.xyz"][i],
+                                   rtol=1e-9, atol=1e-6)
+
+
+def test_kats(golden):
+    """SURVEY.md §4 T1/T3/T5/T6."""
+    assert golden["kat.t1_err"] < 1e-6
+    np.testing.assert_allclose(golden["kat.t3"], [(18 / 19 * np.sqrt(2)) / 2, 5 * 18 / 19], rtol=1e-12)
+    p3 = np.zeros((19, 3)); g3 = np.zeros((19, 3)); g3[:, 0] = 3; g3[:, 1] = 4
+    p2l = np.ones((19, 2)); g2 = np.zeros((19, 2)); vis = np.ones((19, 1), bool); vis[4] = False
+    np.testing.assert_allclose(np.array(O.calc_mpjpe([p2l, g2.copy()], p3, g3, g2, g2, vis)), golden["kat.t3"], rtol=1e-14)
+    # T5: flat heat-map -> centre (31.5, 31.5)
+    kp = O.process_heatmap(torch.zeros(1, 2, 64, 64, dtype=torch.float64))
+    np.testing.assert_allclose(kp.numpy(), 31.5, atol=1e-12)
+    # T6: ftl(ftl(x, P^+), P) == x for full-row-rank P
+    cams = synth.make_cameras(2, seed=9)
+    P = torch.from_numpy(cams["P_l64"])
+    x = torch.randn(2, 300, 8, 8, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    y = O.ftl(O.ftl(x, torch.linalg.pinv(P)), P)
+    np.testing.assert_allclose(y.numpy(), x.numpy(), atol=1e-8)
+    # DLT recovers X from exact projections (T2, fp64)
+    gt = synth.make_gt(cams, seed=4)
+    projs = torch.stack([torch.from_numpy(cams["P_l64"]), torch.from_numpy(cams["P_r64"])], 1)
+    for j in range(19):
+        pts = torch.stack([torch.from_numpy(gt["gt2d_l"][:, j]), torch.from_numpy(gt["gt2d_r"][:, j])], 1)
+        np.testing.assert_allclose(O.dlt(projs, pts).numpy(), gt["gt3d"][:, j], atol=1e-6)
