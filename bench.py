@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — CDRNet post-backbone hot path on B200 (contract: see task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--batch B] [--precision fp32|bf16]
+
+One "step" = one pass of the head (canonical fusion -> decoder -> soft-argmax -> DLT -> MPJPE
+partial sums [-> all-gather when N>1]) over one batch of B synthetic stereo pairs per GPU.
+N=1 workload = BASELINE.json configs[1]: "CDRNet head fp32 batch 64 stereo pairs on 1xB200".
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "cdrnet_head_stereo_pairs_per_sec"
+UNIT = "stereo pairs/s"
+JOINTS = 19
+# algorithmic work per stereo pair
+FLOP_PER_PAIR = {"deconv1": 2147.5e6, "deconv2": 1073.7e6, "deconv3": 4295.0e6, "final_1x1": 79.7e6,
+                 "cf_conv1": 157.3e6, "cf_conv2": 61.5e6, "cf_out": 157.3e6}
+HEAD_FLOP_PER_PAIR = 7972.5e6
+SOFTARGMAX_DLT_BYTES_PER_POSE = 623220.0
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tflops_burst": p["bf16_tflops"],
+                "tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # under-load samples = upper half of the observed clocks
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+# ----------------------------------------------------------------------------------------------
+def oracle_head_runner(batch):
+    """The CPU arm: the oracle port (oracle/cdr_oracle.py — the reference's own torch calls on a
+    state_dict) of the same head on the same synthetic inputs, fp32, all host threads."""
+    from oracle import cdr_oracle as O
+    from fast_3d_human_pose_estimation_b200 import synth
+    sd = synth.make_head_state_dict(seed=0, calibrated=True)
+    feats = synth.make_features(batch, seed=1)
+    cams = synth.make_cameras(batch, seed=2)
+    gt = synth.make_gt(cams, seed=3)
+    Ps = [torch.from_numpy(cams["P_l"]), torch.from_numpy(cams["P_r"])]
+
+    def step():
+        with torch.no_grad():
+            p2, p3 = O.head_forward(sd, feats, Ps)
+        return O.calc_mpjpe([x.numpy() for x in p2], p3.numpy(), gt["gt3d"], gt["gt2d_l"], gt["gt2d_r"], gt["vis"])
+    return step
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the
+    reference itself is pure Python/torch and cannot travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # bounded sample: size the per-step batch so warmup+steps stay within ~2 minutes
+    probe = oracle_head_runner(4)
+    probe()
+    t0 = time.perf_counter(); probe(); t_pair = (time.perf_counter() - t0) / 4
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    b = int(max(1, min(args.batch, budget / max(t_pair, 1e-6))))
+    step = oracle_head_runner(b)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = b * args.steps / dt
+    sample = f"{b} of {args.batch} stereo pairs per step, head only, fp32, torch CPU {torch.__version__}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+        "data": "synthetic", "gpu_launches": 0,
+        "config": {"workload": "CDRNet head fp32 batch 64 stereo pairs (BASELINE configs[1])",
+                   "pairs_per_step": b, "joints": JOINTS, "cpu": cpu_model()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import fast_3d_human_pose_estimation_b200 as pkg
+    from fast_3d_human_pose_estimation_b200 import synth, dist as cdist, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.batch, args.steps, max(3, args.warmup)
+
+    sd = synth.make_head_state_dict(seed=0, calibrated=True)
+    model = pkg.CDRNet(synth.make_cfg(18, JOINTS), precision=args.precision)   # encoder unused here
+    model.load_state_dict(sd, strict=False)
+    model = model.to(dev).eval()
+    feats_h = [f.pin_memory() for f in synth.make_features(B, seed=1 + rank)]
+    cams = synth.make_cameras(B, seed=2 + rank)
+    gt = synth.make_gt(cams, seed=3 + rank)
+    P_h = [torch.from_numpy(cams["P_l"]).pin_memory(), torch.from_numpy(cams["P_r"]).pin_memory()]
+    feats = [f.to(dev) for f in feats_h]
+    Ps = [p.to(dev) for p in P_h]
+    g3 = torch.from_numpy(gt["gt3d"]).to(dev)
+    g2l = torch.from_numpy(gt["gt2d_l"]).to(dev)
+    g2r = torch.from_numpy(gt["gt2d_r"]).to(dev)
+    vis = torch.from_numpy(gt["vis"]).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    n_total = B * world
+
+    def step(f, p):
+        (kl, kr), xyz = model.head(f, p)
+        sums = pkg.mpjpe_sums([kl, kr], xyz, g3, g2l, g2r, vis)
+        if world > 1:
+            return cdist.gather_results(xyz, sums, n_total)
+        return xyz, sums
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        flush.fill_(1)
+        out = step(feats, Ps)
+    barrier()
+
+    # ---- device-resident timing: K steps, L2 flushed between steps (outside the event pairs)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L = _lib.lib()
+    L.cdr_launch_count_reset()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    t_wall = time.perf_counter()
+    for i in range(K):
+        flush.fill_(i & 0xff)
+        starts[i].record()
+        out = step(feats, Ps)
+        ends[i].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = L.cdr_launch_count()
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    clocks = sampler.stop() if rank == 0 else None
+    xyz, sums = out
+    e2d, e3d = cdist.mpjpe_from_sums(sums)
+
+    # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
+    h2d = sum(t.numel() * t.element_size() for t in feats_h + P_h)
+    xyz_h = torch.empty((n_total, JOINTS, 3), dtype=torch.float32).pin_memory()
+    sums_h = torch.empty(4, dtype=torch.float64).pin_memory()
+    d2h = xyz_h.numel() * 4 + 32
+    e_s, e_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        step([f.to(dev, non_blocking=True) for f in feats_h], [p.to(dev, non_blocking=True) for p in P_h])
+    barrier()
+    e_s.record()
+    for i in range(K):
+        f = [t.to(dev, non_blocking=True) for t in feats_h]
+        p = [t.to(dev, non_blocking=True) for t in P_h]
+        x, s = step(f, p)
+        xyz_h.copy_(x, non_blocking=True)
+        sums_h.copy_(s, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller reads the result every step
+    e_e.record()
+    barrier()
+    e2e_ms = e_s.elapsed_time(e_e)
+
+    # ---- per-kernel durations, live, with CUDA events on the launching stream (3 steps)
+    stage_ms = {}
+    reps = 3
+    for _ in range(reps):
+        flush.fill_(3)
+        torch.cuda.synchronize()
+        _lib.stage_timing_begin(dev)
+        model.head(feats, Ps)
+        for name, ms in _lib.stage_timing_end():
+            stage_ms[name] = stage_ms.get(name, 0.0) + ms / reps
+
+    # max over ranks
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        pk = peaks()
+        value = n_total * K / (dev_ms / 1e3)
+        top = max(stage_ms, key=stage_ms.get)
+        top_s = stage_ms[top] / 1e3
+        if top in FLOP_PER_PAIR:
+            ach = FLOP_PER_PAIR[top] * B / top_s / 1e12
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"],
+                    "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"], "traffic": None,
+                    "peak_source": pk["source"] + " bf16 sustained",
+                    "launch_ms": stage_ms[top], "share_of_step": stage_ms[top] / sum(stage_ms.values())}
+        else:
+            ach = SOFTARGMAX_DLT_BYTES_PER_POSE * B / top_s / 1e9
+            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                    "launch_ms": stage_ms[top], "share_of_step": stage_ms[top] / sum(stage_ms.values())}
+        sa = stage_ms.get("softargmax_dlt")
+        hbm = None
+        if sa:
+            a = SOFTARGMAX_DLT_BYTES_PER_POSE * B / (sa / 1e3) / 1e9
+            hbm = {"kernel": "softargmax_dlt", "bound": "hbm", "achieved": a, "peak": pk["hbm_gbs"],
+                   "unit": "GB/s", "frac": a / pk["hbm_gbs"], "launch_ms": sa}
+        # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            cb = min(B, 32)
+            cstep = oracle_head_runner(cb)
+            cstep()
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter(); cstep(); ts.append(time.perf_counter() - t0)
+            cpu = {"value": cb / float(np.median(ts)), "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{cb} of {B} stereo pairs, head only, fp32, oracle port on torch CPU, median of 3",
+                   "cpu": cpu_model()}
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": "CDRNet head (post-encoder) batch 64 stereo pairs per GPU, "
+                                   "BASELINE configs[1]" if B == 64 else f"CDRNet head batch {B} per GPU",
+                       "pairs_per_gpu": B, "global_pairs": n_total, "joints": JOINTS, "views": 2,
+                       "weights": "seeded random init (final_layer x0.1)", "l2": "flushed between steps (256 MB write)",
+                       "collective": "1 all-gather of (B,19,3)+32 B per step" if world > 1 else "none",
+                       "parallelism": f"dp{world}"},
+            "e2e": {"value": n_total * K / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
+            "gpu_launches": int(launches), "launches_per_step": launches / K,
+            "roofline": roof, "roofline_hbm": hbm, "stages_ms": stage_ms,
+            "head_tflops": HEAD_FLOP_PER_PAIR * value / 1e12,
+            "cpu_baseline": cpu, "clocks": clocks, "wall_s_timed_region": t_wall,
+            "mpjpe": {"error_2d_px": e2d, "error_3d_mm": e3d},
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="stereo pairs per GPU per step")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

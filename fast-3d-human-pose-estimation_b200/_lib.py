@@ -47,6 +47,8 @@ _SIGNATURES = {
     "cdr_last_error": (C.c_char_p, []),
     "cdr_launch_count": (C.c_ulonglong, []),
     "cdr_launch_count_reset": (None, []),
+    "cdr_stage_timing_begin": (C.c_int, [_vp]),
+    "cdr_stage_timing_end": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "cdr_weights_create": (C.c_int, [C.POINTER(CdrWeightPtrs), C.c_int, _vp, C.POINTER(_vp)]),
     "cdr_weights_destroy": (C.c_int, [_vp]),
     "cdr_head_workspace_bytes": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_size_t)]),
@@ -110,6 +112,20 @@ def check(rc: int) -> None:
     if rc != 0:
         msg = lib().cdr_last_error()
         raise CdrError(f"libcdrhead error {rc}: {msg.decode(errors='replace') if msg else '?'}")
+
+
+def stage_timing_begin(device=None):
+    check(lib().cdr_stage_timing_begin(current_stream_ptr(device)))
+
+
+def stage_timing_end(capacity=512):
+    """-> list of (stage label, milliseconds) for every launch since stage_timing_begin."""
+    names = C.create_string_buffer(48 * capacity)
+    ms = (C.c_float * capacity)()
+    n = C.c_int()
+    check(lib().cdr_stage_timing_end(capacity, names, ms, C.byref(n)))
+    raw = names.raw
+    return [(raw[i * 48:(i + 1) * 48].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(n.value)]
 
 
 def ptr(t):

@@ -17,7 +17,31 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-void count_launch(int n) { g_launches += (unsigned long long)n; }
+
+// ---- optional per-launch timing (bench.py's live roofline numbers): one event after every
+// launch on the timing stream; durations are differences of consecutive events.
+constexpr int kMaxTimed = 512;
+struct StageTiming {
+  bool on = false;
+  cudaStream_t stream = nullptr;
+  int n = 0;
+  cudaEvent_t ev[kMaxTimed + 1] = {};
+  char name[kMaxTimed][48];
+  const char* label = nullptr;
+};
+static thread_local StageTiming g_timing;
+
+void set_stage(const char* label) { g_timing.label = label; }
+void count_launch(const char* kernel) {
+  g_launches += 1;
+  StageTiming& t = g_timing;
+  if (!t.on || t.n >= kMaxTimed) return;
+  const int i = t.n + 1;
+  if (!t.ev[i] && cudaEventCreate(&t.ev[i]) != cudaSuccess) return;
+  if (cudaEventRecord(t.ev[i], t.stream) != cudaSuccess) return;
+  snprintf(t.name[t.n], sizeof(t.name[t.n]), "%s", t.label ? t.label : kernel);
+  t.n = i;
+}
 
 struct Bump {  // 256-byte aligned bump allocator over a caller-provided region
   uint8_t* base;
@@ -73,6 +97,33 @@ extern "C" int cdr_abi_version(void) { return CDRHEAD_ABI_VERSION; }
 extern "C" const char* cdr_last_error(void) { return g_err; }
 extern "C" unsigned long long cdr_launch_count(void) { return g_launches; }
 extern "C" void cdr_launch_count_reset(void) { g_launches = 0; }
+
+extern "C" int cdr_stage_timing_begin(void* stream) {
+  StageTiming& t = g_timing;
+  if (!t.ev[0]) CDR_CUDA(cudaEventCreate(&t.ev[0]));
+  t.stream = (cudaStream_t)stream;
+  t.n = 0;
+  t.label = nullptr;
+  CDR_CUDA(cudaEventRecord(t.ev[0], t.stream));
+  t.on = true;
+  return CDR_OK;
+}
+
+extern "C" int cdr_stage_timing_end(int capacity, char* names, float* ms, int* count) {
+  StageTiming& t = g_timing;
+  CDR_CHECK_ARG(t.on, "cdr_stage_timing_end: timing was not started");
+  CDR_CHECK_ARG(names && ms && count && capacity > 0, "cdr_stage_timing_end: bad args");
+  t.on = false;
+  t.label = nullptr;
+  if (t.n > 0) CDR_CUDA(cudaEventSynchronize(t.ev[t.n]));
+  const int n = t.n < capacity ? t.n : capacity;
+  for (int i = 0; i < n; ++i) {
+    CDR_CUDA(cudaEventElapsedTime(&ms[i], t.ev[i], t.ev[i + 1]));
+    memcpy(names + (size_t)i * 48, t.name[i], 48);
+  }
+  *count = n;
+  return CDR_OK;
+}
 
 extern "C" int cdr_weights_create(const CdrWeightPtrs* src, int precision, void* stream,
                                   CdrWeights** out) {
@@ -216,7 +267,9 @@ static int decoder_f32(const CdrWeights* w, const float* x1, int N, float* d1, f
   const float* in = x1;
   float* outs[3] = {d1, d2, d3};
   int side = 8;
+  static const char* const kDcName[3] = {"deconv1", "deconv2", "deconv3"};
   for (int i = 0; i < 3; ++i) {
+    set_stage(kDcName[i]);
     TapGemmParams p{};
     p.A = in;
     p.a_pitch = kDcCin[i];
@@ -239,6 +292,7 @@ static int decoder_f32(const CdrWeights* w, const float* x1, int N, float* d1, f
     in = outs[i];
     side *= 2;
   }
+  set_stage("final_1x1");
   TapGemmParams p{};
   p.A = d3;
   p.a_pitch = kDecC;
@@ -254,7 +308,9 @@ static int decoder_f32(const CdrWeights* w, const float* x1, int N, float* d1, f
   p.c_fill = 4;
   p.relu = 0;
   p.out_mode = kOutPlanar;
-  return launch_tap_gemm_ffma(p, 1, st);
+  const int rc = launch_tap_gemm_ffma(p, 1, st);
+  set_stage(nullptr);
+  return rc;
 }
 
 static int copy_tap(float* dst, const float* src, size_t count, cudaStream_t st) {
@@ -289,6 +345,7 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
   }
   int rc;
   // (1) P^+  — models/cdrnet.py:236-237
+  set_stage("pinv");
   const float* pinv[2] = {pinv_l, pinv_r};
   if (!pinv_l) {
     if ((rc = cdr_pinv(P_l, B, pinv_rtol, ws.pinv, st))) return rc;
@@ -297,9 +354,11 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
     pinv[1] = ws.pinv + (size_t)B * 12;
   }
   // (2) encoder latents NCHW -> pixel-major rows, views stacked (conv_layer1 is shared)
+  set_stage("nchw_to_rows");
   if ((rc = launch_nchw_to_rows_f32(feat_l, B, kFeatC, kFeatHW, ws.x0, kFeatC, st))) return rc;
   if ((rc = launch_nchw_to_rows_f32(feat_r, B, kFeatC, kFeatHW, ws.x0 + (size_t)B * kFeatHW * kFeatC, kFeatC, st))) return rc;
   // (3) conv_layer1 2048 -> 300 (+BN+ReLU) — :62
+  set_stage("cf_conv1");
   {
     TapGemmParams p{};
     p.A = ws.x0; p.a_pitch = kFeatC; p.n_img = N; p.H = p.W = 8; p.cin = kFeatC;
@@ -308,11 +367,13 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
     if ((rc = launch_tap_gemm_ffma(p, 1, st))) return rc;
   }
   // (4) inverse FTL into the concatenated (B,64,800) buffer — :65,70
+  set_stage("ftl_inv");
   for (int v = 0; v < 2; ++v)
     if ((rc = launch_ftl<float>(ws.y1 + (size_t)v * B * kFeatHW * kHid1Pad, kHid1Pad, pinv[v], 4, 3,
                                 kFtlBlk, B, kFeatHW, ws.z + v * kHid2, 2 * kHid2, kHid2, st)))
       return rc;
   // (5) conv_layer2: 800 -> 400 -> 400 — :74
+  set_stage("cf_conv2");
   {
     TapGemmParams p{};
     p.A = ws.z; p.a_pitch = 2 * kHid2; p.n_img = B; p.H = p.W = 8; p.cin = 2 * kHid2;
@@ -323,12 +384,14 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
     if ((rc = launch_tap_gemm_ffma(p, 1, st))) return rc;
   }
   // (6) forward FTL per view — :79
+  set_stage("ftl_fwd");
   const float* Pv[2] = {P_l, P_r};
   for (int v = 0; v < 2; ++v)
     if ((rc = launch_ftl<float>(ws.f2, kHid2, Pv[v], 3, 4, kFtlBlk, B, kFeatHW,
                                 ws.g + (size_t)v * B * kFeatHW * kHid1Pad, kHid1Pad, kHid1Pad, st)))
       return rc;
   // (7) out_layer[v] 300 -> 2048, per-view weights = 2 groups — :81
+  set_stage("cf_out");
   {
     TapGemmParams p{};
     p.A = ws.g; p.a_group_stride = (long long)B * kFeatHW * kHid1Pad; p.a_pitch = kHid1Pad;
@@ -342,10 +405,12 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
   // (8) decoder on both views at once (shared weights) — :243-244
   if ((rc = decoder_f32(w, ws.x1, N, ws.d1, ws.d2, ws.d3, ws.hm, st))) return rc;
   // (9) soft-argmax + DLT — :247-266
+  set_stage("softargmax_dlt");
   if ((rc = cdr_softargmax_dlt(ws.hm, ws.hm + (size_t)B * J * 4096, 0, P_l, P_r, B, J, kHeat, kHeat,
                                scale, kp2d_l, kp2d_r, xyz, nullptr, nullptr, nullptr, nullptr,
                                nullptr, st)))
     return rc;
+  set_stage(nullptr);
   if (taps) {
     if ((rc = copy_tap(taps->pinv, pinv[0], (size_t)B * 12, st))) return rc;
     if ((rc = copy_tap(taps->pinv ? taps->pinv + (size_t)B * 12 : nullptr, pinv[1], (size_t)B * 12, st))) return rc;

@@ -12,7 +12,9 @@ namespace cdr {
 
 // thread-local error string + launch counter (the only mutable global state)
 void set_error(const char* fmt, ...);
-void count_launch(int n = 1);
+void count_launch(const char* kernel);
+// label attached to subsequent launches in the stage-timing record (api.cu)
+void set_stage(const char* label);
 
 #define CDR_CHECK_ARG(cond, ...)                 \
   do {                                           \
@@ -40,7 +42,7 @@ void count_launch(int n = 1);
       cdr::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));      \
       return CDR_ERR_CUDA;                                                          \
     }                                                                               \
-    cdr::count_launch();                                                            \
+    cdr::count_launch(name);                                                        \
   } while (0)
 
 inline int num_sms() {

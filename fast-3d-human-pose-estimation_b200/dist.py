@@ -44,8 +44,8 @@ def unpack_results(gathered, n_total, joints, world):
     per = -(-n_total // world)
     body = per * joints * 12
     g = gathered.reshape(world, body + _SUM_BYTES)
-    xyz = g[:, :body].contiguous().view(torch.float32).reshape(world * per, joints, 3)[:n_total]
-    parts = g[:, body:].contiguous().view(torch.float64).reshape(world, 4)
+    xyz = g[:, :body].reshape(-1).clone().view(torch.float32).reshape(world * per, joints, 3)[:n_total]
+    parts = g[:, body:].reshape(-1).clone().view(torch.float64).reshape(world, 4)
     sums = parts[0].clone()
     for r in range(1, world):          # fixed order -> bit-reproducible
         sums += parts[r]

@@ -100,6 +100,14 @@ const char* cdr_last_error(void);
 unsigned long long cdr_launch_count(void);
 void cdr_launch_count_reset(void);
 
+/* Per-launch device timing for bench.py's live roofline numbers.  _begin records a CUDA event
+ * on `stream` and arms the calling thread; every kernel this library then launches from that
+ * thread is followed by another event on the same stream.  _end synchronises the last event,
+ * disarms, and returns for launch i its stage label (48-byte slots in `names`) and the time
+ * between the events around it.  All launches in between must be on `stream`. */
+int cdr_stage_timing_begin(void* stream);
+int cdr_stage_timing_end(int capacity, char* names, float* ms, int* count);
+
 /* Fold BN into the convs, convert/re-lay-out for `precision`, on `stream`.
  * Replaces nn.Module parameter storage + eval-mode BN of models/cdrnet.py:17-43 and
  * models/decoder.py:8-37.  The source tensors may be freed once this returns. */

@@ -1,0 +1,374 @@
+"""GPU parity: the CUDA path (through the C ABI / the reference-shaped shim) against the oracle
+on the same seeded inputs, against the reference's golden vectors, and through size-independent
+properties at BASELINE.json's sizes.  Tolerances are the north-star's: 2D <= 1e-3 px,
+3D <= 1e-2 mm, MPJPE <= 1e-3 mm for the fp32 path against the fp64 oracle on the calibrated
+90-degree rig; integer/index work is bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from fast_3d_human_pose_estimation_b200 import synth
+from oracle import cdr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_2D_PX, TOL_3D_MM, TOL_MPJPE_MM = 1e-3, 1e-2, 1e-3
+
+
+def _model(pkg, sd, joints=19, precision="fp32"):
+    m = pkg.CDRNet(synth.make_cfg(18, joints), nj=joints, precision=precision)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected
+    return m.cuda().eval()
+
+
+def _oracle64(sd, feats, cams, taps=None):
+    sd64 = O.cast_state_dict(sd, torch.float64)
+    Ps = [torch.from_numpy(cams["P_l"]).double(), torch.from_numpy(cams["P_r"]).double()]
+    with torch.no_grad():
+        p2, p3 = O.head_forward(sd64, [f.double() for f in feats], Ps, taps=taps)
+    return [x.numpy() for x in p2], p3.numpy()
+
+
+def _run_head(m, feats, cams, taps=False):
+    Ps = [torch.from_numpy(cams["P_l"]).cuda(), torch.from_numpy(cams["P_r"]).cuda()]
+    out = m.head([f.cuda() for f in feats], Ps, taps=taps)
+    torch.cuda.synchronize()
+    return out
+
+
+def _nhwc_to_nchw(t, c):  # (..., 64, C) -> (..., C, 8, 8)
+    return t.reshape(*t.shape[:-2], 8, 8, c).permute(*range(t.dim() - 2), -1, -3, -2)
+
+
+def test_head_fp32_vs_fp64_oracle_stagewise(cuda_pkg):
+    b = 4
+    sd = synth.make_head_state_dict(seed=0, calibrated=True, randomize_bn=True)
+    feats, cams = synth.make_features(b, seed=1), synth.make_cameras(b, seed=2)
+    gt = synth.make_gt(cams, seed=3)
+    otaps = {}
+    o2, o3 = _oracle64(sd, feats, cams, otaps)
+    m = _model(cuda_pkg, sd)
+    (kl, kr), xyz, taps = _run_head(m, feats, cams, taps=True)
+
+    def rel(got, want):
+        return float(np.abs(got - want).max() / np.abs(want).max())
+
+    pinv = torch.stack(otaps["pinv"]).numpy()
+    assert rel(taps["pinv"].cpu().numpy(), pinv) < 1e-6
+    cat = _nhwc_to_nchw(taps["cf_cat"].cpu(), 800).numpy()
+    assert rel(cat, otaps["cf_cat"].numpy()) < 2e-5
+    f = _nhwc_to_nchw(taps["cf_f"].cpu(), 400).numpy()
+    assert rel(f, otaps["cf_f"].numpy()) < 2e-5
+    fo = _nhwc_to_nchw(taps["f_out"].cpu(), 2048).numpy()
+    assert rel(fo, torch.stack(otaps["f_out"]).numpy()) < 2e-5
+    hm = taps["heatmaps"].cpu().numpy()
+    assert rel(hm, torch.stack(otaps["heatmaps"]).numpy()) < 2e-5
+
+    d2 = max(np.abs(kl.cpu().numpy() - o2[0]).max(), np.abs(kr.cpu().numpy() - o2[1]).max())
+    d3 = np.abs(xyz.cpu().numpy() - o3).max()
+    # the reference's own fp32 rounding, for context (printed with -s)
+    with torch.no_grad():
+        r2, r3 = O.head_forward(sd, feats, [torch.from_numpy(cams["P_l"]), torch.from_numpy(cams["P_r"])])
+    ref_d2 = max(np.abs(r2[0].numpy() - o2[0]).max(), np.abs(r2[1].numpy() - o2[1]).max())
+    ref_d3 = np.abs(r3.numpy() - o3).max()
+    print(f"\nCUDA fp32 vs fp64 oracle: d2D={d2:.2e}px d3D={d3:.2e}mm | reference fp32 vs fp64: "
+          f"d2D={ref_d2:.2e}px d3D={ref_d3:.2e}mm")
+    assert d2 <= TOL_2D_PX and d3 <= TOL_3D_MM
+    e_gpu = cuda_pkg.calc_mpjpe([kl, kr], xyz, gt["gt3d"], gt["gt2d_l"], gt["gt2d_r"], gt["vis"])
+    e_ora = O.calc_mpjpe(o2, o3, gt["gt3d"], gt["gt2d_l"], gt["gt2d_r"], gt["vis"])
+    assert abs(e_gpu[0] - e_ora[0]) <= TOL_2D_PX and abs(e_gpu[1] - e_ora[1]) <= TOL_MPJPE_MM
+
+
+@pytest.mark.parametrize("name,b,joints,calib,rbn,rig,t2,t3", [
+    ("head_b2", 2, 19, True, True, "wide", TOL_2D_PX, TOL_3D_MM),
+    ("head_b3_default_init", 3, 19, False, False, "wide", 5e-2, None),   # stress: logit std ~34
+    ("head_b1_j16_narrow", 1, 16, True, True, "narrow", TOL_2D_PX, None),  # ill-conditioned rig
+])
+def test_head_vs_reference_golden(cuda_pkg, golden, name, b, joints, calib, rbn, rig, t2, t3):
+    sd = synth.make_head_state_dict(seed=0, joints=joints, calibrated=calib, randomize_bn=rbn)
+    feats, cams = synth.make_features(b, seed=1), synth.make_cameras(b, seed=2, rig=rig)
+    m = _model(cuda_pkg, sd, joints)
+    (kl, kr), xyz = _run_head(m, feats, cams)
+    d2 = max(np.abs(kl.cpu().numpy() - golden[f"{name}.f64.kp_l"]).max(),
+             np.abs(kr.cpu().numpy() - golden[f"{name}.f64.kp_r"]).max())
+    ref = golden[f"{name}.f64.xyz"]
+    d3 = np.abs(xyz.cpu().numpy() - ref).max()
+    ref32 = np.abs(golden[f"{name}.f32.xyz"] - ref).max()
+    print(f"\n{name}: d2D={d2:.2e}px d3D={d3:.2e}mm (reference fp32 vs fp64 d3D={ref32:.2e}mm)")
+    assert d2 <= t2
+    if t3 is not None:
+        assert d3 <= t3
+    else:  # un-gated conditioning cases: we must not be worse than the reference's own fp32
+        assert d3 <= max(10 * ref32, 1.0)
+
+
+@pytest.mark.parametrize("kind", ["randn3", "randn30", "blob", "flat", "onehot"])
+def test_softargmax_kernel(cuda_pkg, kind):
+    n = 37
+    g = torch.Generator().manual_seed(5)
+    if kind == "randn3":
+        h = 3 * torch.randn(n, 64, 64, generator=g)
+    elif kind == "randn30":
+        h = 30 * torch.randn(n, 64, 64, generator=g)
+    elif kind == "blob":
+        h = synth.blob_heatmaps(torch.rand(n, 2, generator=g) * 63, seed=1)
+    elif kind == "flat":
+        h = torch.full((n, 64, 64), -2.5)
+    else:
+        h = torch.full((n, 64, 64), -1e4)
+        h[torch.arange(n), torch.arange(n) % 64, (torch.arange(n) * 7) % 64] = 50.0
+    want = (O.process_heatmap(h.double().unsqueeze(0))[0] * 4.0).numpy()
+    hd = h.cuda().contiguous()
+    kp = torch.empty(n, 2, device="cuda")
+    L = cuda_pkg._lib
+    L.check(L.lib().cdr_softargmax(L.ptr(hd), n, 64, 64, 4.0, L.ptr(kp), L.current_stream_ptr()))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(kp.cpu().numpy(), want, rtol=0, atol=1e-4)   # px
+
+
+def test_softargmax_edge_sizes(cuda_pkg):
+    L = cuda_pkg._lib
+    kp = torch.zeros(1, 2, device="cuda")
+    h = torch.zeros(1, 64, 64, device="cuda")
+    L.check(L.lib().cdr_softargmax(L.ptr(h), 0, 64, 64, 4.0, L.ptr(kp), L.current_stream_ptr()))  # empty
+    # non-square / smaller maps (ragged relative to the 16 KB tile)
+    g = torch.Generator().manual_seed(6)
+    h = torch.randn(5, 32, 48, generator=g) * 4
+    b, j, hh, ww = 1, 5, 32, 48
+    hm = torch.softmax(h.double().reshape(5, -1), 1).reshape(5, hh, ww)
+    cx = (hm.sum(1) * torch.arange(ww)).sum(1)
+    cy = (hm.sum(2) * torch.arange(hh)).sum(1)
+    kp = torch.empty(5, 2, device="cuda")
+    hd = h.cuda()
+    L.check(L.lib().cdr_softargmax(L.ptr(hd), 5, hh, ww, 1.0, L.ptr(kp), L.current_stream_ptr()))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(kp.cpu().numpy(), torch.stack([cx, cy], 1).numpy(), atol=1e-4)
+    with pytest.raises(cuda_pkg.CdrError):     # larger than a tile
+        L.check(L.lib().cdr_softargmax(L.ptr(hd), 1, 128, 128, 1.0, L.ptr(kp), L.current_stream_ptr()))
+
+
+def _dlt_oracle(cams, kp_l, kp_r):
+    projs = torch.stack([torch.from_numpy(cams["P_l"]).double(), torch.from_numpy(cams["P_r"]).double()], 1)
+    j = kp_l.shape[1]
+    return np.stack([O.dlt(projs, torch.stack([torch.from_numpy(kp_l[:, k]).double(),
+                                               torch.from_numpy(kp_r[:, k]).double()], 1)).numpy()
+                     for k in range(j)], 1)
+
+
+def test_dlt_kernel(cuda_pkg):
+    b, j = 33, 19
+    cams = synth.make_cameras(b, seed=7)
+    gt = synth.make_gt(cams, seed=8)
+    rng = np.random.default_rng(9)
+    kp_l = (gt["gt2d_l"] + rng.normal(scale=1.5, size=(b, j, 2))).astype(np.float32)
+    kp_r = (gt["gt2d_r"] + rng.normal(scale=1.5, size=(b, j, 2))).astype(np.float32)
+    want = _dlt_oracle(cams, kp_l, kp_r)
+    L = cuda_pkg._lib
+    d = [torch.from_numpy(x).cuda() for x in (cams["P_l"], cams["P_r"], kp_l, kp_r)]
+    xyz = torch.empty(b, j, 3, device="cuda")
+    L.check(L.lib().cdr_dlt(*[L.ptr(t) for t in d], b, j, L.ptr(xyz), L.current_stream_ptr()))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(xyz.cpu().numpy(), want, rtol=0, atol=1e-3)   # mm (fp32 output ulp)
+    # exact projections recover the ground truth (KAT T2) to fp32 input rounding
+    d[2], d[3] = torch.from_numpy(gt["gt2d_l"].astype(np.float32)).cuda(), torch.from_numpy(gt["gt2d_r"].astype(np.float32)).cuda()
+    L.check(L.lib().cdr_dlt(*[L.ptr(t) for t in d], b, j, L.ptr(xyz), L.current_stream_ptr()))
+    torch.cuda.synchronize()
+    assert np.abs(xyz.cpu().numpy() - gt["gt3d"]).max() < 0.5
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_fused_softargmax_dlt_mpjpe(cuda_pkg, bf16):
+    b, j = 21, 19
+    cams = synth.make_cameras(b, seed=10)
+    gt = synth.make_gt(cams, seed=11)
+    cl = torch.from_numpy(gt["gt2d_l"] / 4.0).float()
+    cr = torch.from_numpy(gt["gt2d_r"] / 4.0).float()
+    hl, hr = synth.blob_heatmaps(cl, seed=1), synth.blob_heatmaps(cr, seed=2)
+    if bf16:
+        hl, hr = hl.bfloat16(), hr.bfloat16()
+    o_l = (O.process_heatmap(hl.double()) * 4.0)
+    o_r = (O.process_heatmap(hr.double()) * 4.0)
+    want3 = _dlt_oracle(cams, o_l.numpy(), o_r.numpy())
+    L = cuda_pkg._lib
+    dev = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dt)
+    Pl, Pr = dev(cams["P_l"], torch.float32), dev(cams["P_r"], torch.float32)
+    g3, g2l, g2r = dev(gt["gt3d"], torch.float64), dev(gt["gt2d_l"], torch.float64), dev(gt["gt2d_r"], torch.float64)
+    vis = dev(gt["vis"][..., 0], torch.float64)
+    hld, hrd = hl.cuda().contiguous(), hr.cuda().contiguous()
+    kl, kr = torch.empty(b, j, 2, device="cuda"), torch.empty(b, j, 2, device="cuda")
+    xyz = torch.empty(b, j, 3, device="cuda")
+    perr = torch.empty(b, 3, dtype=torch.float64, device="cuda")
+    st = L.current_stream_ptr()
+    L.check(L.lib().cdr_softargmax_dlt(L.ptr(hld), L.ptr(hrd), int(bf16), L.ptr(Pl), L.ptr(Pr), b, j, 64, 64, 4.0,
+                                       L.ptr(kl), L.ptr(kr), L.ptr(xyz), L.ptr(g3), L.ptr(g2l), L.ptr(g2r),
+                                       L.ptr(vis), L.ptr(perr), st))
+    sums = torch.empty(4, dtype=torch.float64, device="cuda")
+    scratch = torch.empty(L.lib().cdr_mpjpe_scratch_bytes(b), dtype=torch.uint8, device="cuda")
+    L.check(L.lib().cdr_mpjpe_reduce(L.ptr(perr), b, j, L.ptr(sums), L.ptr(scratch), st))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(kl.cpu().numpy(), o_l.numpy(), atol=1e-4)
+    np.testing.assert_allclose(kr.cpu().numpy(), o_r.numpy(), atol=1e-4)
+    np.testing.assert_allclose(xyz.cpu().numpy(), want3, atol=5e-3)
+    e2, e3 = O.calc_mpjpe([kl.cpu().numpy(), kr.cpu().numpy()], xyz.cpu().numpy(), gt["gt3d"], gt["gt2d_l"],
+                          gt["gt2d_r"], gt["vis"])
+    s = sums.cpu().numpy()
+    assert s[3] == b * j
+    np.testing.assert_allclose([(s[0] + s[1]) / (2 * s[3]), s[2] / s[3]], [e2, e3], rtol=1e-10)
+    # blobs sit on the projections of the ground truth -> triangulation lands near it
+    if not bf16:
+        assert np.abs(xyz.cpu().numpy() - gt["gt3d"]).mean() < 5.0
+
+
+def test_argmax_and_triangulation_bit_exact(cuda_pkg, golden):
+    from test_oracle_golden import baseline_inputs
+    heat, heat_r, cams = baseline_inputs()
+    preds, maxv = cuda_pkg.get_max_preds(heat)
+    assert preds.dtype == np.float32
+    assert np.array_equal(preds, golden["base.preds"]) and np.array_equal(maxv, golden["base.maxvals"])
+    u8_l, u8_r = cuda_pkg.baseline_keypoints(heat), cuda_pkg.baseline_keypoints(heat_r)
+    assert u8_l.dtype == np.uint8
+    assert np.array_equal(u8_l, golden["base.u8_l"]) and np.array_equal(u8_r, golden["base.u8_r"])
+    PL = np.stack([O.get_projection_matrix(cams["K"], cams["R_l"][i], cams["T_l"][i]) for i in range(3)])
+    PR = np.stack([O.get_projection_matrix(cams["K"], cams["R_r"][i], cams["T_r"][i]) for i in range(3)])
+    one = cuda_pkg.triangulation(PL[0], PR[0], u8_l[0], u8_r[0])          # the reference's per-frame call
+    assert one.shape == (19, 3) and one.dtype == np.float64
+    np.testing.assert_allclose(one, golden["base.xyz"][0], rtol=0, atol=1e-2)
+    allb = cuda_pkg.triangulation(PL, PR, u8_l, u8_r)                     # batched extension
+    np.testing.assert_allclose(allb, golden["base.xyz"], rtol=1e-6, atol=1e-2)
+    gt = synth.make_gt(cams, seed=6)
+    e = cuda_pkg.calc_mpjpe([u8_l[0], u8_r[0]], one, gt["gt3d"][0], gt["gt2d_l"][0], gt["gt2d_r"][0],
+                            gt["vis"][0].astype(bool))
+    np.testing.assert_allclose(np.array(e), golden["base.mpjpe0"], rtol=1e-9)
+    # random maps with planted ties: identical to numpy's first-index rule
+    rng = np.random.default_rng(3)
+    h = rng.integers(-3, 4, size=(7, 19, 64, 64)).astype(np.float32)     # many exact ties
+    p, mv = cuda_pkg.get_max_preds(h)
+    op, omv = O.get_max_preds(h)
+    assert np.array_equal(p, op) and np.array_equal(mv, omv)
+
+
+def test_mpjpe_call_styles(cuda_pkg, golden):
+    for name, b, joints, rig in [("head_b2", 2, 19, "wide"), ("head_b1_j16_narrow", 1, 16, "narrow")]:
+        cams = synth.make_cameras(b, seed=2, rig=rig)
+        gt = synth.make_gt(cams, joints=joints, seed=3)
+        p2 = [golden[f"{name}.f32.kp_l"], golden[f"{name}.f32.kp_r"]]
+        e = cuda_pkg.calc_mpjpe(p2, golden[f"{name}.f32.xyz"], gt["gt3d"], gt["gt2d_l"], gt["gt2d_r"],
+                                gt["vis"].astype(np.float32))
+        np.testing.assert_allclose(np.array(e), golden[f"{name}.mpjpe"], rtol=1e-12)
+        e = cuda_pkg.calc_mpjpe([p2[0][0], p2[1][0]], golden[f"{name}.f32.xyz"][0], gt["gt3d"][0],
+                                gt["gt2d_l"][0], gt["gt2d_r"][0], gt["vis"][0].astype(bool))
+        np.testing.assert_allclose(np.array(e), golden[f"{name}.mpjpe_frame0"], rtol=1e-12)
+    np.testing.assert_allclose(golden["kat.t3"], [(18 / 19 * np.sqrt(2)) / 2, 5 * 18 / 19])
+    p3 = np.zeros((19, 3)); g3 = np.zeros((19, 3)); g3[:, 0] = 3; g3[:, 1] = 4
+    p2l = np.ones((19, 2)); g2 = np.zeros((19, 2)); vis = np.ones((19, 1), bool); vis[4] = False
+    np.testing.assert_allclose(np.array(cuda_pkg.calc_mpjpe([p2l, g2.copy()], p3, g3, g2, g2, vis)), golden["kat.t3"], rtol=1e-14)
+    np.testing.assert_allclose(np.array(cuda_pkg.calc_mpjpe([p2l, g2.copy()], p3, g3, g2, g2)),
+                               [np.sqrt(2) / 2, 5.0], rtol=1e-14)            # no weights
+
+
+def test_ftl_identity_and_oracle(cuda_pkg):
+    """KAT T6 on the device + FTL against the oracle's reshape/bmm (channel-block layout)."""
+    b = 3
+    cams = synth.make_cameras(b, seed=12)
+    P = torch.from_numpy(cams["P_l"])
+    Pinv = torch.linalg.pinv(P.double()).float()
+    x = torch.randn(b, 300, 8, 8, generator=torch.Generator().manual_seed(1))
+    want = O.ftl(x.double(), Pinv.double())                                # (b,400,8,8)
+    L = cuda_pkg._lib
+    rows = torch.zeros(b, 64, 304)
+    rows[:, :, :300] = x.permute(0, 2, 3, 1).reshape(b, 64, 300)
+    xin, out = rows.cuda(), torch.full((b, 64, 400), float("nan"), device="cuda")
+    st = L.current_stream_ptr()
+    Pinv_d, P_d = Pinv.cuda().contiguous(), P.cuda().contiguous()
+    L.check(L.lib().cdr_ftl(L.ptr(xin), 304, L.ptr(Pinv_d), 4, 3, 100, b, 64, L.ptr(out), 400, 400, st))
+    back = torch.full((b, 64, 304), float("nan"), device="cuda")
+    L.check(L.lib().cdr_ftl(L.ptr(out), 400, L.ptr(P_d), 3, 4, 100, b, 64, L.ptr(back), 304, 304, st))
+    torch.cuda.synchronize()
+    got = out.cpu().reshape(b, 8, 8, 400).permute(0, 3, 1, 2)
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-5
+    assert torch.all(back[:, :, 300:] == 0)
+    assert float((back.cpu()[:, :, :300] - rows[:, :, :300]).abs().max()) < 5e-3 * float(x.abs().max())
+    with pytest.raises(cuda_pkg.CdrError):
+        L.check(L.lib().cdr_ftl(L.ptr(xin), 304, L.ptr(P_d), 2, 2, 100, b, 64, L.ptr(out), 400, 400, st))
+
+
+def test_decoder_forward_vs_oracle(cuda_pkg):
+    """PoseResNet's decoder half (models/poseresnet.py:17-21) incl. an odd image count."""
+    n, joints = 3, 16
+    sd = synth.make_head_state_dict(seed=3, joints=joints, calibrated=True, randomize_bn=True, decoder_only=True)
+    feats = synth.make_features(n, seed=4)[0]
+    want = O.decoder(O.cast_state_dict(sd, torch.float64), feats.double()).numpy()
+    dec = cuda_pkg.PoseDecoder(synth.make_cfg(18, joints))
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items()})
+    dec = dec.cuda().eval()
+    got = dec(feats.cuda()).cpu().numpy()
+    assert got.shape == (n, joints, 64, 64)
+    assert np.abs(got - want).max() / np.abs(want).max() < 2e-5
+
+
+def test_repack_on_parameter_change(cuda_pkg):
+    sd = synth.make_head_state_dict(seed=0)
+    feats, cams = synth.make_features(1, seed=1), synth.make_cameras(1, seed=2)
+    m = _model(cuda_pkg, sd)
+    (a, _), _ = _run_head(m, feats, cams)
+    with torch.no_grad():
+        m.decoder.final_layer.weight.mul_(2.0)
+    (b2, _), _ = _run_head(m, feats, cams)
+    assert not torch.equal(a, b2)
+    sd2 = dict(sd)
+    m.load_state_dict(sd2, strict=False)
+    (c, _), _ = _run_head(m, feats, cams)
+    assert torch.equal(a, c)
+
+
+def test_full_size_properties(cuda_pkg):
+    """BASELINE config 2 size (B=64): determinism and per-sample independence (batch
+    permutation equivariance, shard == slice of the full batch) — size-independent properties
+    that hold only if every kernel indexes the batch correctly."""
+    b = 64
+    sd = synth.make_head_state_dict(seed=0, calibrated=True)
+    feats, cams = synth.make_features(b, seed=1), synth.make_cameras(b, seed=2)
+    m = _model(cuda_pkg, sd)
+    (kl, kr), xyz = _run_head(m, feats, cams)
+    (kl2, kr2), xyz2 = _run_head(m, feats, cams)
+    assert torch.equal(kl, kl2) and torch.equal(kr, kr2) and torch.equal(xyz, xyz2)
+    assert torch.isfinite(xyz).all()
+    perm = torch.randperm(b, generator=torch.Generator().manual_seed(0))
+    cams_p = {k: (v[perm.numpy()] if isinstance(v, np.ndarray) and v.shape[:1] == (b,) else v) for k, v in cams.items()}
+    (klp, krp), xyzp = _run_head(m, [f[perm] for f in feats], cams_p)
+    assert torch.equal(klp, kl[perm.cuda()]) and torch.equal(xyzp, xyz[perm.cuda()])
+    lo, hi = 40, 53
+    cams_s = {k: (v[lo:hi] if isinstance(v, np.ndarray) and v.shape[:1] == (b,) else v) for k, v in cams.items()}
+    (kls, _), xyzs = _run_head(m, [f[lo:hi] for f in feats], cams_s)
+    assert torch.equal(kls, kl[lo:hi]) and torch.equal(xyzs, xyz[lo:hi])
+    # spot-check 2 of the 64 against the fp64 oracle
+    o2, o3 = _oracle64(sd, [f[:2] for f in feats], {k: (v[:2] if isinstance(v, np.ndarray) and v.shape[:1] == (b,) else v) for k, v in cams.items()})
+    assert np.abs(kl[:2].cpu().numpy() - o2[0]).max() <= TOL_2D_PX
+    assert np.abs(xyz[:2].cpu().numpy() - o3).max() <= TOL_3D_MM
+
+
+def test_full_pipeline_vs_reference_golden(cuda_pkg, golden):
+    """BASELINE config 1 shape: ResNet-101 encoder on torch/cuDNN + the CUDA head, against the
+    reference's fp64 forward.  The encoder runs in fp32 on the GPU (TF32 off), so the gate is
+    the reference's own fp32-vs-fp64 distance with headroom, not the head-only tolerance."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = synth.make_cfg(101, 19)
+    torch.manual_seed(0)
+    m = cuda_pkg.CDRNet(cfg)
+    with torch.no_grad():
+        m.decoder.final_layer.weight.mul_(0.1)
+    m = m.cuda().eval()
+    imgs = [i.cuda() for i in synth.make_images(1, seed=1)]
+    cams = synth.make_cameras(1, seed=2)
+    (kl, kr), xyz = m(imgs, [torch.from_numpy(cams["P_l"]).cuda(), torch.from_numpy(cams["P_r"]).cuda()])
+    d2 = max(np.abs(kl.cpu().numpy() - golden["full_b1.f64.kp_l"]).max(), np.abs(kr.cpu().numpy() - golden["full_b1.f64.kp_r"]).max())
+    d3 = np.abs(xyz.cpu().numpy() - golden["full_b1.f64.xyz"]).max()
+    r2 = max(np.abs(golden["full_b1.f32.kp_l"] - golden["full_b1.f64.kp_l"]).max(), np.abs(golden["full_b1.f32.kp_r"] - golden["full_b1.f64.kp_r"]).max())
+    r3 = np.abs(golden["full_b1.f32.xyz"] - golden["full_b1.f64.xyz"]).max()
+    print(f"\nfull pipeline: d2D={d2:.2e}px d3D={d3:.2e}mm | reference fp32 vs fp64: {r2:.2e}px {r3:.2e}mm")
+    assert kl.shape == (1, 19, 2) and xyz.shape == (1, 19, 3) and kl.is_cuda
+    assert d2 <= max(10 * r2, 5e-3) and d3 <= max(10 * r3, 5e-2)

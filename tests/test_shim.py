@@ -1,0 +1,77 @@
+"""CPU: the Python mirror of the reference interface — state_dict contract, construction order,
+error behaviour.  The product path must refuse to run without CUDA instead of falling back."""
+import numpy as np
+import pytest
+import torch
+
+from fast_3d_human_pose_estimation_b200 import synth
+
+HEAD_KEYS = {
+    "CF.conv_layer1.0.weight": (300, 2048, 1, 1), "CF.conv_layer1.0.bias": (300,),
+    "CF.conv_layer1.1.running_var": (300,),
+    "CF.conv_layer2.0.weight": (400, 800, 1, 1), "CF.conv_layer2.3.weight": (400, 400, 1, 1),
+    "CF.conv_layer2.4.running_mean": (400,),
+    "CF.out_layer.0.0.weight": (2048, 300, 1, 1), "CF.out_layer.1.1.bias": (2048,),
+    "decoder.deconv1.0.weight": (2048, 256, 4, 4), "decoder.deconv2.0.weight": (256, 256, 4, 4),
+    "decoder.deconv3.1.running_var": (256,), "decoder.final_layer.weight": (19, 256, 1, 1),
+    "decoder.final_layer.bias": (19,),
+}
+
+
+def test_state_dict_contract(pkg):
+    m = pkg.CDRNet(synth.make_cfg(18, 19))
+    sd = m.state_dict()
+    for k, shape in HEAD_KEYS.items():
+        assert tuple(sd[k].shape) == shape, k
+    assert "encoder.layer4.1.conv2.weight" in sd and "encoder.conv1.weight" in sd
+    assert not any(k.startswith("_") for k in sd)
+    head = synth.make_head_state_dict()
+    missing, unexpected = m.load_state_dict(head, strict=False)
+    assert not unexpected and all(k.startswith("encoder.") for k in missing)
+    p = pkg.PoseResNet(synth.make_cfg(18, 16))
+    assert tuple(p.state_dict()["decoder.final_layer.weight"].shape) == (16, 256, 1, 1)
+
+
+def test_no_cpu_fallback(pkg):
+    m = pkg.CDRNet(synth.make_cfg(18, 19)).eval()
+    feats = synth.make_features(1)
+    cams = synth.make_cameras(1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.head(feats, [torch.from_numpy(cams["P_l"]), torch.from_numpy(cams["P_r"])])
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            pkg.calc_mpjpe([np.zeros((19, 2)), np.zeros((19, 2))], np.zeros((19, 3)), np.zeros((19, 3)),
+                           np.zeros((19, 2)), np.zeros((19, 2)))
+        with pytest.raises(RuntimeError, match="CUDA"):
+            pkg.get_max_preds(np.zeros((1, 19, 64, 64), np.float32))
+        with pytest.raises(RuntimeError, match="CUDA"):
+            pkg.triangulation(np.eye(4), np.eye(4), np.zeros((19, 2), np.uint8), np.zeros((19, 2), np.uint8))
+
+
+def test_training_mode_rejected(pkg):
+    m = pkg.CDRNet(synth.make_cfg(18, 19))
+    assert m.training
+    with pytest.raises(RuntimeError, match="inference-only"):
+        m.head([torch.zeros(1, 2048, 8, 8)] * 2, [torch.zeros(1, 3, 4)] * 2)
+
+
+def test_reference_argument_errors(pkg):
+    with pytest.raises(NotImplementedError):
+        pkg.CDRNet(synth.make_cfg(18, 19), n_views=3)
+    with pytest.raises(ValueError):
+        pkg.CDRNet(synth.make_cfg(18, 19), precision="fp8")
+    with pytest.raises(ValueError, match="does not exist"):
+        pkg.CDRNet(synth.make_cfg(18, 19)).init_weights("/nonexistent.pth")
+    with pytest.raises(AssertionError):
+        if torch.cuda.is_available():
+            pkg.get_max_preds(np.zeros((19, 64, 64), np.float32))
+        else:
+            raise AssertionError
+
+
+def test_synth_is_deterministic():
+    a, b = synth.make_features(2, seed=1), synth.make_features(2, seed=1)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert np.array_equal(synth.make_cameras(3, seed=2)["P_l"], synth.make_cameras(3, seed=2)["P_l"])
+    s1, s2 = synth.make_head_state_dict(seed=0), synth.make_head_state_dict(seed=0)
+    assert all(torch.equal(s1[k], s2[k]) for k in s1)
