@@ -62,7 +62,7 @@ def make_cameras(batch, seed=2, rig="wide"):
 def _project(X, K, R, T):
     cam = (R @ X.T + T).T
     uv = (K @ cam.T).T
-    return uv[:, :2] / uv[:, 2:]
+    return np.ascontiguousarray(uv[:, :2] / uv[:, 2:])
 
 
 def make_gt(cams, joints=19, seed=3):
@@ -75,7 +75,8 @@ def make_gt(cams, joints=19, seed=3):
     g2l = np.stack([_project(gt3d[i], cams["K"], cams["R_l"][i], cams["T_l"][i]) for i in range(b)])
     g2r = np.stack([_project(gt3d[i], cams["K"], cams["R_r"][i], cams["T_r"][i]) for i in range(b)])
     vis = (rng.uniform(size=(b, joints, 1)) < 0.9).astype(np.float64)
-    return {"gt3d": gt3d, "gt2d_l": g2l, "gt2d_r": g2r, "vis": vis}
+    return {"gt3d": np.ascontiguousarray(gt3d), "gt2d_l": np.ascontiguousarray(g2l),
+            "gt2d_r": np.ascontiguousarray(g2r), "vis": vis}
 
 
 def make_features(batch, seed=1, device="cpu"):
