@@ -50,8 +50,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Spin on try_wait (which itself suspends the thread for a HW-defined time).  A protocol bug
+// must not hang the GPU: after ~4 s of waiting the kernel traps (cudaErrorLaunchFailure).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xfff) == 0 && clock64() - t0 > 8000000000LL) __trap();
   }
 }
 

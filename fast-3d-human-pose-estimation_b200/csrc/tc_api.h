@@ -6,6 +6,7 @@ namespace cdr {
 
 struct TcWeights {
   void* pool = nullptr;
+  void* maps = nullptr;   // TcMaps: tensor maps of the packed weights (gemm_tc.cu)
   int joints = 0, has_fusion = 0, fin_npad = 0;
   // bf16 B operands, K-major: [n_pad][k_pad] (1x1) or [phase][n][tap*cin] (deconv)
   __nv_bfloat16 *w_cf1 = nullptr, *w_cf2a = nullptr, *w_cf2b = nullptr, *w_out = nullptr;
