@@ -153,37 +153,19 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------
-def run_ours(args):
+def measure(args, precision, ctx):
+    """Time the head at one precision.  Returns the per-precision part of the JSON line."""
     import torch.distributed as dist
     import fast_3d_human_pose_estimation_b200 as pkg
     from fast_3d_human_pose_estimation_b200 import synth, dist as cdist, _lib
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B, K, W = args.batch, args.steps, max(3, args.warmup)
-
-    sd = synth.make_head_state_dict(seed=0, calibrated=True)
-    model = pkg.CDRNet(synth.make_cfg(18, JOINTS), precision=args.precision)   # encoder unused here
-    model.load_state_dict(sd, strict=False)
-    model = model.to(dev).eval()
-    feats_h = [f.pin_memory() for f in synth.make_features(B, seed=1 + rank)]
-    cams = synth.make_cameras(B, seed=2 + rank)
-    gt = synth.make_gt(cams, seed=3 + rank)
-    P_h = [torch.from_numpy(cams["P_l"]).pin_memory(), torch.from_numpy(cams["P_r"]).pin_memory()]
-    feats = [f.to(dev) for f in feats_h]
-    Ps = [p.to(dev) for p in P_h]
-    g3 = torch.from_numpy(gt["gt3d"]).to(dev)
-    g2l = torch.from_numpy(gt["gt2d_l"]).to(dev)
-    g2r = torch.from_numpy(gt["gt2d_r"]).to(dev)
-    vis = torch.from_numpy(gt["vis"]).to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    world, rank, dev, B, K, W = ctx["world"], ctx["rank"], ctx["dev"], args.batch, args.steps, ctx["W"]
+    feats_h, P_h, feats, Ps = ctx["feats_h"], ctx["P_h"], ctx["feats"], ctx["Ps"]
+    g3, g2l, g2r, vis, flush = ctx["g3"], ctx["g2l"], ctx["g2r"], ctx["vis"], ctx["flush"]
     n_total = B * world
+
+    model = pkg.CDRNet(synth.make_cfg(18, JOINTS), precision=precision)   # encoder unused here
+    model.load_state_dict(ctx["sd"], strict=False)
+    model = model.to(dev).eval()
 
     def step(f, p):
         (kl, kr), xyz = model.head(f, p)
@@ -203,7 +185,7 @@ def run_ours(args):
     barrier()
 
     # ---- device-resident timing: K steps, L2 flushed between steps (outside the event pairs)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(ctx["local"])
     if rank == 0:
         sampler.start()
     L = _lib.lib()
@@ -246,9 +228,9 @@ def run_ours(args):
     barrier()
     e2e_ms = e_s.elapsed_time(e_e)
 
-    # ---- per-kernel durations, live, with CUDA events on the launching stream (3 steps)
+    # ---- per-kernel durations, live, with CUDA events on the launching stream
     stage_ms = {}
-    reps = 3
+    reps = 5
     for _ in range(reps):
         flush.fill_(3)
         torch.cuda.synchronize()
@@ -257,37 +239,89 @@ def run_ours(args):
         for name, ms in _lib.stage_timing_end():
             stage_ms[name] = stage_ms.get(name, 0.0) + ms / reps
 
-    # max over ranks
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        return None
+
+    pk = peaks()
+    value = n_total * K / (dev_ms / 1e3)
+    top = max(stage_ms, key=stage_ms.get)
+    share = stage_ms[top] / sum(stage_ms.values())
+    if top in FLOP_PER_PAIR:
+        ach = FLOP_PER_PAIR[top] * B / (stage_ms[top] / 1e3) / 1e12
+        roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"],
+                "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"], "traffic": None,
+                "peak_source": pk["source"] + " bf16 sustained (cuBLAS)", "launch_ms": stage_ms[top],
+                "share_of_step": share,
+                "note": ("tcgen05 kind::f16 kernel" if precision == "bf16" else
+                         "fp32 FFMA parity kernel: no tensor-core peak applies; fp32 FFMA peak is "
+                         "148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s")}
+    else:
+        ach = SOFTARGMAX_DLT_BYTES_PER_POSE * B / (stage_ms[top] / 1e3) / 1e9
+        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "launch_ms": stage_ms[top], "share_of_step": share}
+    sa = stage_ms.get("softargmax_dlt")
+    hbm = None
+    if sa:
+        a = SOFTARGMAX_DLT_BYTES_PER_POSE * B / (sa / 1e3) / 1e9
+        hbm = {"kernel": "softargmax_dlt", "bound": "hbm", "achieved": a, "peak": pk["hbm_gbs"],
+               "unit": "GB/s", "frac": a / pk["hbm_gbs"], "launch_ms": sa}
+    dec_ms = sum(stage_ms.get(k, 0.0) for k in ("deconv1", "deconv2", "deconv3", "final_1x1"))
+    dec_tf = 7595.9e6 * B / (dec_ms / 1e3) / 1e12 if dec_ms else None
+    return {
+        "value": value, "ms_per_step": dev_ms / K, "dtype": precision,
+        "e2e": {"value": n_total * K / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
+        "gpu_launches": int(launches), "launches_per_step": launches / K,
+        "roofline": roof, "roofline_hbm": hbm, "stages_ms": stage_ms,
+        "decoder_tflops": dec_tf, "decoder_frac_of_peak": dec_tf / pk["tflops_sustained"] if dec_tf else None,
+        "head_tflops": HEAD_FLOP_PER_PAIR * value / 1e12,
+        "clocks": clocks, "wall_s_timed_region": t_wall,
+        "mpjpe": {"error_2d_px": e2d, "error_3d_mm": e3d},
+    }
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from fast_3d_human_pose_estimation_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.batch, args.steps, max(3, args.warmup)
+
+    ctx = {"world": world, "rank": rank, "local": local, "dev": dev, "W": W,
+           "sd": synth.make_head_state_dict(seed=0, calibrated=True)}
+    ctx["feats_h"] = [f.pin_memory() for f in synth.make_features(B, seed=1 + rank)]
+    cams = synth.make_cameras(B, seed=2 + rank)
+    gt = synth.make_gt(cams, seed=3 + rank)
+    ctx["P_h"] = [torch.from_numpy(cams["P_l"]).pin_memory(), torch.from_numpy(cams["P_r"]).pin_memory()]
+    ctx["feats"] = [f.to(dev) for f in ctx["feats_h"]]
+    ctx["Ps"] = [p.to(dev) for p in ctx["P_h"]]
+    ctx["g3"] = torch.from_numpy(gt["gt3d"]).to(dev)
+    ctx["g2l"] = torch.from_numpy(gt["gt2d_l"]).to(dev)
+    ctx["g2r"] = torch.from_numpy(gt["gt2d_r"]).to(dev)
+    ctx["vis"] = torch.from_numpy(gt["vis"]).to(dev)
+    ctx["flush"] = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    main_res = measure(args, args.precision, ctx)
+    other = None
+    if args.precision == "fp32" and not args.single_precision:
+        other = measure(args, "bf16", ctx)      # the tensor-core configuration, reported alongside
 
     if rank == 0:
-        pk = peaks()
-        value = n_total * K / (dev_ms / 1e3)
-        top = max(stage_ms, key=stage_ms.get)
-        top_s = stage_ms[top] / 1e3
-        if top in FLOP_PER_PAIR:
-            ach = FLOP_PER_PAIR[top] * B / top_s / 1e12
-            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"],
-                    "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"], "traffic": None,
-                    "peak_source": pk["source"] + " bf16 sustained",
-                    "launch_ms": stage_ms[top], "share_of_step": stage_ms[top] / sum(stage_ms.values())}
-        else:
-            ach = SOFTARGMAX_DLT_BYTES_PER_POSE * B / top_s / 1e9
-            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-                    "launch_ms": stage_ms[top], "share_of_step": stage_ms[top] / sum(stage_ms.values())}
-        sa = stage_ms.get("softargmax_dlt")
-        hbm = None
-        if sa:
-            a = SOFTARGMAX_DLT_BYTES_PER_POSE * B / (sa / 1e3) / 1e9
-            hbm = {"kernel": "softargmax_dlt", "bound": "hbm", "achieved": a, "peak": pk["hbm_gbs"],
-                   "unit": "GB/s", "frac": a / pk["hbm_gbs"], "launch_ms": sa}
-        # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
+            # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
             cb = min(B, 32)
@@ -299,24 +333,25 @@ def run_ours(args):
             cpu = {"value": cb / float(np.median(ts)), "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{cb} of {B} stereo pairs, head only, fp32, oracle port on torch CPU, median of 3",
                    "cpu": cpu_model()}
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": "CDRNet head (post-encoder) batch 64 stereo pairs per GPU, "
-                                   "BASELINE configs[1]" if B == 64 else f"CDRNet head batch {B} per GPU",
-                       "pairs_per_gpu": B, "global_pairs": n_total, "joints": JOINTS, "views": 2,
-                       "weights": "seeded random init (final_layer x0.1)", "l2": "flushed between steps (256 MB write)",
+        line = {
+            "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": ("CDRNet head (post-encoder) batch 64 stereo pairs per GPU, BASELINE configs[1]"
+                                    if B == 64 else f"CDRNet head (post-encoder) batch {B} stereo pairs per GPU"),
+                       "pairs_per_gpu": B, "global_pairs": B * world, "joints": JOINTS, "views": 2,
+                       "weights": "seeded random init (final_layer x0.1)",
+                       "l2": "flushed between steps (256 MB write)",
                        "collective": "1 all-gather of (B,19,3)+32 B per step" if world > 1 else "none",
                        "parallelism": f"dp{world}"},
-            "e2e": {"value": n_total * K / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
-            "gpu_launches": int(launches), "launches_per_step": launches / K,
-            "roofline": roof, "roofline_hbm": hbm, "stages_ms": stage_ms,
-            "head_tflops": HEAD_FLOP_PER_PAIR * value / 1e12,
-            "cpu_baseline": cpu, "clocks": clocks, "wall_s_timed_region": t_wall,
-            "mpjpe": {"error_2d_px": e2d, "error_3d_mm": e3d},
-        }))
+        }
+        for k in ("e2e", "gpu_launches", "launches_per_step", "roofline", "roofline_hbm", "stages_ms",
+                  "decoder_tflops", "decoder_frac_of_peak", "head_tflops", "clocks", "wall_s_timed_region", "mpjpe"):
+            line[k] = main_res[k]
+        line["cpu_baseline"] = cpu
+        if other is not None:
+            line["bf16"] = other
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -330,6 +365,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="stereo pairs per GPU per step")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--single-precision", action="store_true",
+                    help="fp32 run only: skip the bf16 tensor-core measurement reported alongside")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Turn the raw ncu artefacts in gpurun_out/ into the tracked summaries under profiles/.
+
+    python profiles/summarize.py r01
+
+ - launches_<tag>.csv (ncu --metrics gpu__time_duration.sum): per-kernel totals and the share of
+   one timed step per stage (cold-cache, serialised: compare SHARES, not absolutes);
+ - prof_*.ncu-rep (ncu --set full): the roofline-relevant raw metrics per captured launch.
+"""
+import collections
+import csv
+import io
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed_pipe_fma.sum", "sm__cycles_elapsed.max", "l1tex__data_bank_conflicts_pipe_lsu.sum"]
+
+
+def short(name):
+    m = re.match(r"(?:void )?(?:cdr::)?([A-Za-z0-9_]+)(<[^(]*>)?\(", name)
+    if not m:
+        return name[:40]
+    t = m.group(2) or ""
+    t = t.replace("__nv_bfloat16", "bf16").replace("(bool)", "").replace("(int)", "")
+    return m.group(1) + t
+
+
+def launches(tag, rnd):
+    path = os.path.join(OUT, f"launches_{tag}.csv")
+    if not os.path.exists(path):
+        return
+    rows = list(csv.reader(open(path)))
+    h = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    recs = [(short(r[4]), r[8], float(r[-1].replace(",", ""))) for r in rows[h + 1:] if len(r) > 10 and r[12] == "gpu__time_duration.sum"]
+    tot = collections.OrderedDict()
+    for n, grid, ns in recs:
+        k = tot.setdefault(n, [0, 0.0])
+        k[0] += 1
+        k[1] += ns
+    # one step = from one heat_stream launch to the next; take the LAST complete step in the list
+    idx = [i for i, r in enumerate(recs) if r[0].startswith("heat_stream")]
+    step = recs[idx[-2] + 1: idx[-1] + 1] if len(idx) >= 2 else []
+    lines = [f"# ncu launch list, {tag} head, B=64 — `ncu --metrics gpu__time_duration.sum --clock-control none` "
+             f"on `python bench.py --steps 2 --warmup 3 --precision {tag} --no-cpu-baseline`",
+             "# cold-cache, serialised launches: the SHARES are comparable with bench.py's live CUDA-event stage times, not the absolutes",
+             "", "## totals over the whole run", "kernel,launches,total_us"]
+    for n, (c, ns) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+        lines.append(f"{n},{c},{ns / 1e3:.1f}")
+    if step:
+        s_tot = sum(ns for _, _, ns in step)
+        lines += ["", f"## one head step (last complete one in the capture): {s_tot / 1e3:.1f} us over {len(step)} launches",
+                  "order,kernel,grid,us,share"]
+        for i, (n, grid, ns) in enumerate(step):
+            lines.append(f"{i},{n},{grid.replace(',', 'x')},{ns / 1e3:.1f},{ns / s_tot:.3f}")
+    open(os.path.join(ROOT, "profiles", f"{rnd}_launches_{tag}.csv"), "w").write("\n".join(lines) + "\n")
+    print("wrote", f"profiles/{rnd}_launches_{tag}.csv")
+
+
+def full(rep, rnd):
+    path = os.path.join(OUT, rep + ".ncu-rep")
+    if not os.path.exists(path):
+        return
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    out = []
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        rec = {"kernel": short(d.get("Kernel Name", "")), "grid": d.get("Grid Size"), "block": d.get("Block Size")}
+        for k in KEYS:
+            if k in d:
+                rec[k] = d[k]
+        out.append(rec)
+    unit = {k: units[hdr.index(k)] for k in KEYS if k in hdr}
+    json.dump({"units": unit, "launches": out}, open(os.path.join(ROOT, "profiles", f"{rnd}_{rep}_raw.json"), "w"), indent=1)
+    print("wrote", f"profiles/{rnd}_{rep}_raw.json", len(out), "launches")
+    for rec in out:
+        print("  ", rec["kernel"], rec["grid"], {k.split(".")[0]: v for k, v in rec.items() if k not in ("kernel", "grid", "block")})
+
+
+if __name__ == "__main__":
+    rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    for tag in ("bf16", "fp32"):
+        launches(tag, rnd)
+    for rep in ("prof_tc", "prof_ffma", "prof_heat"):
+        full(rep, rnd)
