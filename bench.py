@@ -256,9 +256,10 @@ def measure(args, precision, ctx):
                 "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"], "traffic": None,
                 "peak_source": pk["source"] + " bf16 sustained (cuBLAS)", "launch_ms": stage_ms[top],
                 "share_of_step": share,
-                "note": ("tcgen05 kind::f16 kernel" if precision == "bf16" else
-                         "fp32 FFMA parity kernel: no tensor-core peak applies; fp32 FFMA peak is "
-                         "148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s")}
+                "note": {"bf16": "tcgen05 kind::f16, bf16 operands",
+                         "fp32": "tcgen05 kind::tf32, 3 MMAs per product (3xTF32 split) at half the bf16 rate: "
+                                 "at most 1/6 of the bf16 peak in algorithmic FLOPs",
+                         "fp32_ffma": "fp32 FFMA kernel on CUDA cores; fp32 FFMA peak is 74.4 TFLOP/s"}[precision]}
     else:
         ach = SOFTARGMAX_DLT_BYTES_PER_POSE * B / (stage_ms[top] / 1e3) / 1e9
         roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -315,7 +316,7 @@ def run_ours(args):
 
     main_res = measure(args, args.precision, ctx)
     other = None
-    if args.precision == "fp32" and not args.single_precision:
+    if args.precision != "bf16" and not args.single_precision:
         other = measure(args, "bf16", ctx)      # the tensor-core configuration, reported alongside
 
     if rank == 0:
@@ -363,7 +364,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="stereo pairs per GPU per step")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_ffma", "bf16"],
+                    help="fp32 = fp32 results via 3xTF32 on tcgen05 (default); fp32_ffma = CUDA cores; bf16 = tcgen05 bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--single-precision", action="store_true",
                     help="fp32 run only: skip the bf16 tensor-core measurement reported alongside")

@@ -32,6 +32,12 @@ struct StageTiming {
 static thread_local StageTiming g_timing;
 
 void set_stage(const char* label) { g_timing.label = label; }
+// called at the entry of a forward: if nothing has been timed yet, move the start marker here so
+// the first stage does not include the caller's host-side latency
+void timing_restart() {
+  StageTiming& t = g_timing;
+  if (t.on && t.n == 0) cudaEventRecord(t.ev[0], t.stream);
+}
 void count_launch(const char* kernel) {
   g_launches += 1;
   StageTiming& t = g_timing;
@@ -128,7 +134,7 @@ extern "C" int cdr_stage_timing_end(int capacity, char* names, float* ms, int* c
 extern "C" int cdr_weights_create(const CdrWeightPtrs* src, int precision, void* stream,
                                   CdrWeights** out) {
   CDR_CHECK_ARG(src && out, "cdr_weights_create: null argument");
-  CDR_CHECK_ARG(precision == CDR_PREC_FP32 || precision == CDR_PREC_BF16,
+  CDR_CHECK_ARG(precision == CDR_PREC_FP32 || precision == CDR_PREC_BF16 || precision == CDR_PREC_TF32X3,
                 "cdr_weights_create: unknown precision %d", precision);
   CDR_CHECK_ARG(src->num_joints > 0 && src->num_joints <= kMaxJoints,
                 "cdr_weights_create: num_joints must be 1..%d", kMaxJoints);
@@ -186,12 +192,12 @@ extern "C" int cdr_weights_create(const CdrWeightPtrs* src, int precision, void*
     if ((rc = launch_pack_conv1x1_f32(src->final_layer, w->joints, kDecC, kDecC, w->fin_npad, w->w_fin, w->b_fin, st)))
       return fail(rc);
   } else {
-    if ((rc = tc_weights_create(*src, w->tc, st))) return fail(rc);
+    if ((rc = tc_weights_create(*src, precision == CDR_PREC_BF16 ? 0 : 1, w->tc, st))) return fail(rc);
   }
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {
     set_error("cdr_weights_create: packing failed: %s", cudaGetErrorString(e));
-    if (precision == CDR_PREC_BF16) tc_weights_destroy(w->tc);
+    if (precision != CDR_PREC_FP32) tc_weights_destroy(w->tc);
     return fail(CDR_ERR_CUDA);
   }
   *out = w;
@@ -249,13 +255,13 @@ static DecWs plan_dec_f32(void* base, int N) {
 extern "C" int cdr_head_workspace_bytes(const CdrWeights* w, int batch, size_t* bytes) {
   CDR_CHECK_ARG(w && bytes && batch > 0, "cdr_head_workspace_bytes: bad args");
   CDR_CHECK_ARG(w->has_fusion, "cdr_head_workspace_bytes: decoder-only weights");
-  if (w->precision == CDR_PREC_BF16) return tc_head_workspace_bytes(w->tc, batch, bytes);
+  if (w->precision != CDR_PREC_FP32) return tc_head_workspace_bytes(w->tc, batch, bytes);
   *bytes = plan_head_f32(nullptr, batch, w->joints).bytes;
   return CDR_OK;
 }
 extern "C" int cdr_decoder_workspace_bytes(const CdrWeights* w, int n_images, size_t* bytes) {
   CDR_CHECK_ARG(w && bytes && n_images > 0, "cdr_decoder_workspace_bytes: bad args");
-  if (w->precision == CDR_PREC_BF16) return tc_decoder_workspace_bytes(w->tc, n_images, bytes);
+  if (w->precision != CDR_PREC_FP32) return tc_decoder_workspace_bytes(w->tc, n_images, bytes);
   *bytes = plan_dec_f32(nullptr, n_images).bytes;
   return CDR_OK;
 }
@@ -332,8 +338,9 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
                 "cdr_head_forward: give both pseudo-inverses or neither");
   CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "cdr_head_forward: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  timing_restart();
   const float scale = (float)img_size / (float)kHeat;   // models/cdrnet.py:250
-  if (w->precision == CDR_PREC_BF16)
+  if (w->precision != CDR_PREC_FP32)
     return tc_head_forward(w->tc, feat_l, feat_r, P_l, P_r, pinv_l, pinv_r, pinv_rtol, batch, scale,
                            kp2d_l, kp2d_r, xyz, taps, workspace, workspace_bytes, st);
 
@@ -428,7 +435,7 @@ extern "C" int cdr_decoder_forward(const CdrWeights* w, const float* feat, int n
   CDR_CHECK_ARG(w && feat && heatmaps && workspace && n_images > 0, "cdr_decoder_forward: bad args");
   CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "cdr_decoder_forward: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (w->precision == CDR_PREC_BF16)
+  if (w->precision != CDR_PREC_FP32)
     return tc_decoder_forward(w->tc, feat, n_images, heatmaps, workspace, workspace_bytes, st);
   DecWs ws = plan_dec_f32(workspace, n_images);
   if (ws.bytes > workspace_bytes) {

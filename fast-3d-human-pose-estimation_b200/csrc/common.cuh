@@ -15,6 +15,7 @@ void set_error(const char* fmt, ...);
 void count_launch(const char* kernel);
 // label attached to subsequent launches in the stage-timing record (api.cu)
 void set_stage(const char* label);
+void timing_restart();
 
 #define CDR_CHECK_ARG(cond, ...)                 \
   do {                                           \
@@ -60,6 +61,22 @@ template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 template <typename T>
 __host__ __device__ constexpr T round_up(T a, T b) { return ceil_div(a, b) * b; }
+
+// ---- 3xTF32 operand split.  hi = x rounded to nearest-even at tf32 precision (11 significant
+// bits, exactly a tf32 value), lo = x - hi (exact, |lo| <= 2^-11 |x|, random sign), so hi + lo
+// reproduces x bit for bit for the consumers that add the planes.  The tensor core sees lo
+// through its own 11-bit window; because lo's sign is random that residue (<= 2^-21 |x|) is
+// unbiased.  (A truncating split hi = x & ~0x1fff leaves a same-signed residue in every
+// product, which does not average out over K: ~1e-5 relative error in the heat-maps.)
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u = __float_as_uint(x);
+  u += 0xFFFu + ((u >> 13) & 1u);
+  return __uint_as_float(u & 0xFFFFE000u);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = tf32_rn(x);
+  lo = x - hi;
+}
 
 // ---- fixed geometry of the head (models/cdrnet.py:89-91, models/decoder.py:8-13) ----
 constexpr int kFeatC = 2048;   // encoder channels = fusion_in_dim

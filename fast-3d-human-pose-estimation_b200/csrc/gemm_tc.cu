@@ -45,9 +45,9 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-// bf16 tensor, dims[0] innermost (contiguous); strides in elements for dims 1..rank-1
-static int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                          const uint64_t* strides_elems, const uint32_t* box) {
+// dims[0] innermost (contiguous); strides in elements for dims 1..rank-1; elem_bytes 2 (bf16) or 4 (fp32)
+static int make_tmap(CUtensorMap* map, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                     const uint64_t* strides_elems, const uint32_t* box) {
   auto enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -59,9 +59,10 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const ui
     gdim[i] = dims[i];
     bdim[i] = box[i];
     estr[i] = 1;
-    if (i > 0) gstr[i - 1] = strides_elems[i - 1] * 2;
+    if (i > 0) gstr[i - 1] = strides_elems[i - 1] * (uint64_t)elem_bytes;
   }
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+  CUresult r = enc(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                   (cuuint32_t)rank, const_cast<void*>(base),
                    gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -74,19 +75,32 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const ui
 
 // ------------------------------------------------------------------------------------------
 constexpr int kTcBM = 128;
-constexpr int kTcBK = 64;                        // 64 bf16 = one 128-byte swizzle row
 constexpr int kTcThreads = 192;
-constexpr int kABytes = kTcBM * kTcBK * 2;       // 16 KB
+constexpr int kABytes = kTcBM * 128;             // 128 rows x one 128-byte swizzle row = 16 KB
 constexpr int kSmemBudget = 200 * 1024;
 
-template <int BN>
+// Operand kinds.
+//   kKindBF16  : bf16 operands, kind::f16, one MMA per K=16 step.
+//   kKindTF32X3: fp32 accuracy on the tensor cores.  Every fp32 operand is stored as two fp32
+//                planes hi = rn_tf32(x), lo = x - hi (common.cuh: split_tf32); x*y ~= hi*hi' + hi*lo' + lo*hi' with kind::tf32 MMAs accumulating in
+//                fp32 (dropped lo*lo' term ~2^-22 relative, random sign).
+enum TcKind { kKindBF16 = 0, kKindTF32X3 = 1 };
+template <int KIND> struct KindTraits;
+template <> struct KindTraits<kKindBF16>   { static constexpr int kElem = 2, kBK = 64, kPlanes = 1; };
+template <> struct KindTraits<kKindTF32X3> { static constexpr int kElem = 4, kBK = 32, kPlanes = 2; };
+
+template <int BN, int KIND>
 struct TcCfg {
-  static constexpr int kBBytes = BN * kTcBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBK = KindTraits<KIND>::kBK;
+  static constexpr int kPlanes = KindTraits<KIND>::kPlanes;
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
-  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
-                                   : (2 * BN <= 256) ? 256 : 512;
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kAccBufs = KIND == kKindTF32X3 ? 4 : 2;   // see the TMEM column map in the kernel
+  static constexpr int kTmemCols = (kAccBufs * BN <= 32) ? 32 : (kAccBufs * BN <= 64) ? 64
+                                   : (kAccBufs * BN <= 128) ? 128 : (kAccBufs * BN <= 256) ? 256 : 512;
+  static_assert(kAccBufs * BN <= 512, "TMEM has 512 columns");
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 512 /*barriers*/;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
   static_assert(kStages >= 2, "pipeline too shallow");
 };
@@ -105,30 +119,100 @@ struct TcGemmParams {
   int n;                  // valid output channels
   const float* bias;      // (groups?, n_pad)
   int bias_group_stride;
-  void* C;
+  void* C;                // bf16 rows, or the fp32 hi plane (tf32x3), or planar fp32 heat-maps
+  void* C_lo;             // tf32x3: the lo plane
   long long c_group_stride;
   int c_pitch, c_fill;
   int relu;
-  int out_mode;           // kOutRows / kOutDeconv (bf16) or kOutPlanar (fp32)
+  int out_mode;           // kOutRows / kOutDeconv or kOutPlanar (fp32)
   int num_tiles;
 };
 
-template <int BN>
+// Epilogue for one 32-column slab of a finished row: + bias, ReLU, mask, convert, store.
+template <int KIND>
+__device__ __forceinline__ void store_slab(const TcGemmParams& p, const float (&acc)[32], int n0c, int g, bool row_ok,
+                                           size_t orow, int img, int pix, int HW, const float* __restrict__ bias) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = acc[j];
+    if (bias) x += __ldg(bias + n0c + j);
+    if (p.relu) x = fmaxf(x, 0.f);
+    v[j] = (n0c + j < p.n) ? x : 0.f;
+  }
+  if (!row_ok) return;
+  if (p.out_mode == kOutPlanar) {
+    float* __restrict__ C = reinterpret_cast<float*>(p.C);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n0c + j < p.n) C[((size_t)img * p.n + n0c + j) * HW + pix] = v[j];
+    return;
+  }
+  const size_t off = (p.out_mode == kOutDeconv ? 0 : (size_t)g * p.c_group_stride) + orow * p.c_pitch + n0c;
+  if constexpr (KIND == kKindTF32X3) {
+    float* __restrict__ Ch = reinterpret_cast<float*>(p.C) + off;
+    float* __restrict__ Cl = reinterpret_cast<float*>(p.C_lo) + off;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      if (n0c + j4 * 4 < p.c_fill) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_tf32(v[j4 * 4 + e], hi[e], lo[e]);
+        *reinterpret_cast<float4*>(Ch + j4 * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(Cl + j4 * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  } else {
+    __nv_bfloat16* __restrict__ C = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      if (n0c + j8 * 8 < p.c_fill) {
+        uint4 o;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j8 * 8 + 0], v[j8 * 8 + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j8 * 8 + 2], v[j8 * 8 + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j8 * 8 + 4], v[j8 * 8 + 5]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j8 * 8 + 6], v[j8 * 8 + 7]);
+        o.x = *reinterpret_cast<uint32_t*>(&h0);
+        o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2);
+        o.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(C + j8 * 8) = o;
+      }
+    }
+  }
+}
+
+// K-blocks accumulated inside TMEM before the 3xTF32 main term is drained into fp32 registers.
+// The tensor core adds into its fp32 accumulator with round-toward-zero; over a long K chain
+// of same-signed partial sums that bias grows linearly (measured: 1e-5 relative at K=2048, 40x
+// worse than FFMA).  Chains of 4 K-blocks (16 MMAs) keep it below 1e-6; the cross-chunk sum is
+// done by the epilogue warps in registers with round-to-nearest.
+constexpr int kSplitChunk = 4;
+
+template <int BN, int KIND>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                   const __grid_constant__ CUtensorMap tmap_b, const TcGemmParams p) {
-  using Cfg = TcCfg<BN>;
+tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
+                   const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo,
+                   const TcGemmParams p) {
+  using Cfg = TcCfg<BN, KIND>;
   constexpr int S = Cfg::kStages;
+  constexpr int kTcBK = Cfg::kBK;
+  constexpr bool kSplit = KIND == kKindTF32X3;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;                                  // S x 16 KB, each 1024-aligned
-  uint8_t* smem_b = smem + (size_t)S * kABytes;            // S x BN*128 B
+  // stage s: [A (16 KB) | A_lo (tf32x3) | B (BN*128 B) | B_lo (tf32x3)], every piece 1024-aligned
+  auto stage_a = [&](int s, int plane) { return smem + (size_t)s * Cfg::kStageBytes + (size_t)plane * kABytes; };
+  auto stage_b = [&](int s, int plane) {
+    return smem + (size_t)s * Cfg::kStageBytes + (size_t)Cfg::kPlanes * kABytes + (size_t)plane * Cfg::kBBytes;
+  };
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * Cfg::kStageBytes);
-  uint64_t* full = bars;                // [S]
-  uint64_t* empty = bars + S;           // [S]
-  uint64_t* tmem_full = bars + 2 * S;   // [2]
-  uint64_t* tmem_empty = bars + 2 * S + 2;  // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  uint64_t* full = bars;                      // [S]  TMA -> MMA
+  uint64_t* empty = bars + S;                 // [S]  MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * S;         // [2]  finished tile accumulator (bf16) / correction accumulator (tf32x3)
+  uint64_t* tmem_empty = bars + 2 * S + 2;    // [2]
+  uint64_t* chunk_full = bars + 2 * S + 4;    // [2]  tf32x3: main-term chunk accumulator
+  uint64_t* chunk_empty = bars + 2 * S + 6;   // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -136,6 +220,10 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
+    if (kSplit) {
+      ptx::prefetch_tmap(&tmap_a_lo);
+      ptx::prefetch_tmap(&tmap_b_lo);
+    }
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
@@ -143,6 +231,8 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
       ptx::mbar_init(&tmem_empty[a], 4);     // one arrive per epilogue warp
+      ptx::mbar_init(&chunk_full[a], 1);
+      ptx::mbar_init(&chunk_empty[a], 4);
     }
     ptx::fence_mbar_init();
   }
@@ -151,6 +241,9 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  // TMEM columns: bf16  : [0,BN) [BN,2BN)               two tile accumulators
+  //               tf32x3: [0,BN) [BN,2BN)               two main-term chunk accumulators
+  //                       [2BN,3BN) [3BN,4BN)           two correction-term tile accumulators
 
   const int kb_per_tap = (p.cin + kTcBK - 1) / kTcBK;
   const int num_kb = p.ntaps * kb_per_tap;
@@ -175,59 +268,84 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const int k0 = (kb - tap * kb_per_tap) * kTcBK;
           if (p.a4d) {
             const int dy = py - (tap >> 1), dx = px - (tap & 1);
-            ptx::tma_load_4d(smem_a + (size_t)s * kABytes, &tmap_a, &full[s], k0, dx, y0 + dy, img0);
+            ptx::tma_load_4d(stage_a(s, 0), &tmap_a, &full[s], k0, dx, y0 + dy, img0);
+            if (kSplit) ptx::tma_load_4d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, dx, y0 + dy, img0);
           } else {
-            ptx::tma_load_2d(smem_a + (size_t)s * kABytes, &tmap_a, &full[s], k0, g * p.a_group_rows + m0);
+            ptx::tma_load_2d(stage_a(s, 0), &tmap_a, &full[s], k0, g * p.a_group_rows + m0);
+            if (kSplit) ptx::tma_load_2d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, g * p.a_group_rows + m0);
           }
-          ptx::tma_load_2d(smem_b + (size_t)s * Cfg::kBBytes, &tmap_b, &full[s], tap * p.cin + k0,
-                           g * p.b_group_rows + n_tile * BN);
+          ptx::tma_load_2d(stage_b(s, 0), &tmap_b, &full[s], tap * p.cin + k0, g * p.b_group_rows + n_tile * BN);
+          if (kSplit)
+            ptx::tma_load_2d(stage_b(s, 1), &tmap_b_lo, &full[s], tap * p.cin + k0, g * p.b_group_rows + n_tile * BN);
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+      // instruction descriptor: D=f32, A/B format (1 = bf16, 2 = tf32), both K-major, N=BN, M=128
+      constexpr uint32_t fmt = kSplit ? 2u : 1u;
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
                                  ((uint32_t)(kTcBM >> 4) << 24);
       // smem matrix descriptor (K-major, SWIZZLE_128B): LBO=1, SBO=1024 B, version=1, layout=2
       constexpr uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
                                    ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-      uint32_t it = 0, tl = 0;
+      auto desc = [&](const uint8_t* ptr) { return desc_hi | (uint64_t)((ptx::smem_u32(ptr) >> 4) & 0x3FFF); };
+      uint32_t it = 0, tl = 0, ch = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
         const int acc = tl & 1;
-        const uint32_t acc_par = (tl >> 1) & 1;
-        ptx::mbar_wait(&tmem_empty[acc], acc_par ^ 1u);
+        ptx::mbar_wait(&tmem_empty[acc], ((tl >> 1) & 1) ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % S;
-          const uint32_t par = (it / S) & 1;
-          ptx::mbar_wait(&full[s], par);
-          ptx::tc_fence_after();
-          const uint64_t da = desc_hi | (uint64_t)((ptx::smem_u32(smem_a + (size_t)s * kABytes) >> 4) & 0x3FFF);
-          const uint64_t db = desc_hi | (uint64_t)((ptx::smem_u32(smem_b + (size_t)s * Cfg::kBBytes) >> 4) & 0x3FFF);
+        if constexpr (!kSplit) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const int s = it % S;
+            ptx::mbar_wait(&full[s], (it / S) & 1);
+            ptx::tc_fence_after();
+            const uint64_t da = desc(stage_a(s, 0)), db = desc(stage_b(s, 0));
 #pragma unroll
-          for (int k = 0; k < kTcBK / 16; ++k)    // +32 bytes (= 2 x 16 B) per K=16 step inside the swizzle row
-            ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-          ptx::umma_commit(&empty[s]);             // smem stage reusable once these MMAs retire
+            for (int k = 0; k < 4; ++k)    // +32 bytes (= 2 x 16 B) per K step (16 bf16) inside the swizzle row
+              ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            ptx::umma_commit(&empty[s]);           // smem stage reusable once these MMAs retire
+          }
+        } else {
+          const uint32_t d_corr = tmem_base + (uint32_t)((2 + acc) * BN);
+          for (int kb0 = 0; kb0 < num_kb; kb0 += kSplitChunk, ++ch) {
+            const int buf = ch & 1;
+            ptx::mbar_wait(&chunk_empty[buf], ((ch >> 1) & 1) ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t d_main = tmem_base + (uint32_t)(buf * BN);
+            const int kb1 = kb0 + kSplitChunk < num_kb ? kb0 + kSplitChunk : num_kb;
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+              const int s = it % S;
+              ptx::mbar_wait(&full[s], (it / S) & 1);
+              ptx::tc_fence_after();
+              const uint64_t da = desc(stage_a(s, 0)), dal = desc(stage_a(s, 1));
+              const uint64_t db = desc(stage_b(s, 0)), dbl = desc(stage_b(s, 1));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {        // K step = 8 tf32 = 32 bytes
+                const uint64_t o = (uint64_t)(2 * k);
+                ptx::umma_tf32(d_corr, dal + o, db + o, idesc, (kb | k) != 0);   // lo*hi  } whole-tile chain: these
+                ptx::umma_tf32(d_corr, da + o, dbl + o, idesc, 1u);              // hi*lo  } terms are 2^-11 of the main one
+                ptx::umma_tf32(d_main, da + o, db + o, idesc, (kb > kb0 || k > 0));  // hi*hi, short chain
+              }
+              ptx::umma_commit(&empty[s]);
+            }
+            ptx::umma_commit(&chunk_full[buf]);    // main-term chunk ready to be drained
+          }
         }
-        ptx::umma_commit(&tmem_full[acc]);         // accumulator complete
+        ptx::umma_commit(&tmem_full[acc]);         // tile (bf16) / correction accumulator (tf32x3) complete
       }
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
-    uint32_t tl = 0;
+    uint32_t tl = 0, ch = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
       const int n_tile = tile % p.n_tiles;
       const int g = (tile / p.n_tiles) % p.groups;
       const int m0 = (tile / (p.n_tiles * p.groups)) * kTcBM;
       const int acc = tl & 1;
-      const uint32_t acc_par = (tl >> 1) & 1;
-      ptx::mbar_wait(&tmem_full[acc], acc_par);
-      ptx::tc_fence_after();
-
       const int m = m0 + q * 32 + lane;            // this thread's pixel
       const bool row_ok = m < p.M;
       const int n0 = n_tile * BN;
@@ -243,51 +361,67 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         img = (int)(orow / HW);
         pix = (int)(orow - (size_t)img * HW);
       }
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+
+      if constexpr (!kSplit) {
+        ptx::mbar_wait(&tmem_full[acc], (tl >> 1) & 1);
+        ptx::tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c, r);
-        ptx::tmem_ld_wait();
-        float v[32];
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(acc * BN + c), r);
+          ptx::tmem_ld_wait();
+          float a32[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
-          if (bias) x += __ldg(bias + n0 + c + j);
-          if (p.relu) x = fmaxf(x, 0.f);
-          v[j] = (n0 + c + j < p.n) ? x : 0.f;
+          for (int j = 0; j < 32; ++j) a32[j] = __uint_as_float(r[j]);
+          store_slab<KIND>(p, a32, n0 + c, g, row_ok, orow, img, pix, HW, bias);
         }
-        if (!row_ok) continue;
-        if (p.out_mode == kOutPlanar) {
-          float* __restrict__ C = reinterpret_cast<float*>(p.C);
+        // all TMEM reads of this accumulator are complete (wait::ld above) -> hand it back
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      } else {
+        // running fp32 sum of this thread's output row, round-to-nearest
+        float sum[BN];
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c + j < p.n) C[((size_t)img * p.n + n0 + c + j) * HW + pix] = v[j];
-        } else {
-          __nv_bfloat16* __restrict__ C = reinterpret_cast<__nv_bfloat16*>(p.C) +
-                                          (p.out_mode == kOutDeconv ? 0 : (size_t)g * p.c_group_stride) +
-                                          orow * p.c_pitch + n0 + c;
+        for (int j = 0; j < BN; ++j) sum[j] = 0.f;
+        for (int kb0 = 0; kb0 < num_kb; kb0 += kSplitChunk, ++ch) {
+          const int buf = ch & 1;
+          ptx::mbar_wait(&chunk_full[buf], (ch >> 1) & 1);
+          ptx::tc_fence_after();
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            if (n0 + c + j8 * 8 < p.c_fill) {
-              uint4 o;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j8 * 8 + 0], v[j8 * 8 + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j8 * 8 + 2], v[j8 * 8 + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j8 * 8 + 4], v[j8 * 8 + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j8 * 8 + 6], v[j8 * 8 + 7]);
-              o.x = *reinterpret_cast<uint32_t*>(&h0);
-              o.y = *reinterpret_cast<uint32_t*>(&h1);
-              o.z = *reinterpret_cast<uint32_t*>(&h2);
-              o.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(C + j8 * 8) = o;
-            }
+          for (int c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(buf * BN + c), r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c + j] += __uint_as_float(r[j]);
           }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&chunk_empty[buf]);
+        }
+        ptx::mbar_wait(&tmem_full[acc], (tl >> 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)((2 + acc) * BN + c), r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c + j] += __uint_as_float(r[j]);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+#pragma unroll
+        for (int c = 0; c < BN; c += 32) {
+          float a32[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a32[j] = sum[c + j];
+          store_slab<KIND>(p, a32, n0 + c, g, row_ok, orow, img, pix, HW, bias);
         }
       }
-      // all TMEM reads of this accumulator are complete (wait::ld above) -> hand it back
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
     }
   }
 
@@ -301,26 +435,48 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
 }
 
 // ------------------------------------------------------------------------------------------
+// host side: packed layers, launches, orchestration
+struct TcLayer {            // one packed conv: K-major B operand (1 plane bf16 / 2 planes fp32) + bias
+  void* w[2] = {nullptr, nullptr};
+  float* bias = nullptr;
+  CUtensorMap map[2];
+  int rows = 0, k = 0, k_pitch = 0, bn = 0, n_pad = 0;
+};
+struct TcPack {
+  int kind = kKindBF16;
+  TcLayer cf1, cf2a, cf2b, out, dc[3], fin;
+};
+struct Act {                // an activation buffer: 1 plane (bf16) or hi/lo planes (fp32)
+  void* p[2] = {nullptr, nullptr};
+};
+static inline Act act_offset(const Act& a, size_t elems, int elem_bytes) {
+  Act r;
+  r.p[0] = a.p[0] ? (uint8_t*)a.p[0] + elems * elem_bytes : nullptr;
+  r.p[1] = a.p[1] ? (uint8_t*)a.p[1] + elems * elem_bytes : nullptr;
+  return r;
+}
+
 struct TcLaunch {
-  const __nv_bfloat16* A;   // activations
+  Act A;                    // activations
   int a_pitch;
   int n_img, H, W, cin, deconv, groups;
   long long a_rows_total;   // 2-D map: total rows addressable (groups stacked)
-  const CUtensorMap* tmap_b;
-  int b_group_rows, n, n_pad;
-  const float* bias;
+  const TcLayer* layer;
+  int b_group_rows, n;
   int bias_group_stride;
-  void* C;
+  Act C;                    // output planes (or planar fp32 heat-maps in C.p[0])
   long long c_group_stride;
   int c_pitch, c_fill, relu, out_mode;
 };
 
-template <int BN>
-static int launch_tc(const TcLaunch& l, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+template <int BN, int KIND>
+static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
+  using Cfg = TcCfg<BN, KIND>;
+  constexpr int kElem = KindTraits<KIND>::kElem;
+  constexpr int kBK = Cfg::kBK;
   static bool attr_set = false;
   if (!attr_set) {
-    CDR_CUDA(cudaFuncSetAttribute(tap_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CDR_CUDA(cudaFuncSetAttribute(tap_gemm_tc_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -333,44 +489,64 @@ static int launch_tc(const TcLaunch& l, cudaStream_t st) {
   p.groups = l.groups;
   p.a_group_rows = l.deconv ? 0 : p.M;
   p.b_group_rows = l.b_group_rows;
-  p.n_tiles = l.n_pad / BN;
+  p.n_tiles = l.layer->n_pad / BN;
   p.n = l.n;
-  p.bias = l.bias; p.bias_group_stride = l.bias_group_stride;
-  p.C = l.C; p.c_group_stride = l.c_group_stride; p.c_pitch = l.c_pitch; p.c_fill = l.c_fill;
+  p.bias = l.layer->bias; p.bias_group_stride = l.bias_group_stride;
+  p.C = l.C.p[0]; p.C_lo = l.C.p[1];
+  p.c_group_stride = l.c_group_stride; p.c_pitch = l.c_pitch; p.c_fill = l.c_fill;
   p.relu = l.relu; p.out_mode = l.out_mode;
   const int m_tiles = ceil_div(p.M, kTcBM);
   p.num_tiles = m_tiles * p.groups * p.n_tiles;
-  CDR_CHECK_ARG(l.n_pad % BN == 0 && l.a_pitch % 8 == 0 && ((uintptr_t)l.A & 15) == 0,
-                "tap_gemm_tc: n_pad %% BN, a_pitch %% 8 or A alignment violated");
-  CDR_CHECK_ARG(l.out_mode == kOutPlanar || (l.c_pitch % 8 == 0 && l.c_fill % 8 == 0),
-                "tap_gemm_tc: bf16 output needs c_pitch %% 8 == 0 and c_fill %% 8 == 0");
+  CDR_CHECK_ARG(l.layer->bn == BN && l.layer->n_pad % BN == 0, "tap_gemm_tc: layer packed for BN=%d, launched with %d",
+                l.layer->bn, BN);
+  CDR_CHECK_ARG((l.a_pitch * kElem) % 16 == 0 && ((uintptr_t)l.A.p[0] & 15) == 0, "tap_gemm_tc: A pitch/alignment");
+  CDR_CHECK_ARG(l.out_mode == kOutPlanar || ((l.c_pitch * kElem) % 16 == 0 && (l.c_fill * kElem) % 16 == 0),
+                "tap_gemm_tc: output pitch / fill must be 16-byte multiples");
 
-  CUtensorMap tmap_a;
-  if (l.deconv) {
-    CDR_CHECK_ARG(l.W <= kTcBM && kTcBM % l.W == 0, "tap_gemm_tc: W=%d must divide 128", l.W);
-    int rows = kTcBM / l.W;
-    if (rows > l.H) rows = l.H;
-    const int imgs = kTcBM / (l.W * rows);
-    CDR_CHECK_ARG(l.H % rows == 0 && l.cin % kTcBK == 0, "tap_gemm_tc: unsupported deconv geometry");
-    p.box_rows = rows; p.box_imgs = imgs;
-    const uint64_t dims[4] = {(uint64_t)l.cin, (uint64_t)l.W, (uint64_t)l.H, (uint64_t)l.n_img};
-    const uint64_t strides[3] = {(uint64_t)l.a_pitch, (uint64_t)l.a_pitch * l.W, (uint64_t)l.a_pitch * HW};
-    const uint32_t box[4] = {(uint32_t)kTcBK, (uint32_t)l.W, (uint32_t)rows, (uint32_t)imgs};
-    if (int rc = make_tmap_bf16(&tmap_a, l.A, 4, dims, strides, box)) return rc;
-  } else {
-    const uint64_t dims[2] = {(uint64_t)l.cin, (uint64_t)l.a_rows_total};
-    const uint64_t strides[1] = {(uint64_t)l.a_pitch};
-    const uint32_t box[2] = {(uint32_t)kTcBK, (uint32_t)kTcBM};
-    if (int rc = make_tmap_bf16(&tmap_a, l.A, 2, dims, strides, box)) return rc;
+  CUtensorMap tmap_a[2];
+  for (int pl = 0; pl < KindTraits<KIND>::kPlanes; ++pl) {
+    if (l.deconv) {
+      CDR_CHECK_ARG(l.W <= kTcBM && kTcBM % l.W == 0, "tap_gemm_tc: W=%d must divide 128", l.W);
+      int rows = kTcBM / l.W;
+      if (rows > l.H) rows = l.H;
+      const int imgs = kTcBM / (l.W * rows);
+      CDR_CHECK_ARG(l.H % rows == 0 && l.cin % kBK == 0, "tap_gemm_tc: unsupported deconv geometry");
+      p.box_rows = rows; p.box_imgs = imgs;
+      const uint64_t dims[4] = {(uint64_t)l.cin, (uint64_t)l.W, (uint64_t)l.H, (uint64_t)l.n_img};
+      const uint64_t strides[3] = {(uint64_t)l.a_pitch, (uint64_t)l.a_pitch * l.W, (uint64_t)l.a_pitch * HW};
+      const uint32_t box[4] = {(uint32_t)kBK, (uint32_t)l.W, (uint32_t)rows, (uint32_t)imgs};
+      if (int rc = make_tmap(&tmap_a[pl], l.A.p[pl], kElem, 4, dims, strides, box)) return rc;
+    } else {
+      const uint64_t dims[2] = {(uint64_t)l.cin, (uint64_t)l.a_rows_total};
+      const uint64_t strides[1] = {(uint64_t)l.a_pitch};
+      const uint32_t box[2] = {(uint32_t)kBK, (uint32_t)kTcBM};
+      if (int rc = make_tmap(&tmap_a[pl], l.A.p[pl], kElem, 2, dims, strides, box)) return rc;
+    }
   }
-  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  tap_gemm_tc_kernel<BN><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tmap_a, *l.tmap_b, p);
+  if (KindTraits<KIND>::kPlanes == 1) tmap_a[1] = tmap_a[0];
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  tap_gemm_tc_kernel<BN, KIND><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(
+      tmap_a[0], tmap_a[1], l.layer->map[0], l.layer->map[KindTraits<KIND>::kPlanes - 1], p);
   CDR_LAUNCH_OK("tap_gemm_tc_kernel");
   return CDR_OK;
 }
 
+static int launch_tc(int kind, const TcLaunch& l, cudaStream_t st) {
+  const int bn = l.layer->bn;
+  if (kind == kKindBF16) {
+    if (bn == 256) return launch_tc_t<256, kKindBF16>(l, st);
+    if (bn == 128) return launch_tc_t<128, kKindBF16>(l, st);
+    if (bn == 32) return launch_tc_t<32, kKindBF16>(l, st);
+  } else {
+    if (bn == 128) return launch_tc_t<128, kKindTF32X3>(l, st);
+    if (bn == 32) return launch_tc_t<32, kKindTF32X3>(l, st);
+  }
+  set_error("tap_gemm_tc: no kernel for kind %d BN %d", kind, bn);
+  return CDR_ERR_UNSUPPORTED;
+}
+
 // ------------------------------------------------------------------------------------------
-// bf16 weight packing (K-major B operands) — BN folded as in pack.cu
+// weight packing (K-major B operands) — BN folded in fp64 as in pack.cu
 constexpr double kBnEpsTc = 1e-5;
 __device__ __forceinline__ double tc_bn_scale(const CdrConvBn& s, int co) {
   return s.bn_weight ? (double)s.bn_weight[co] / sqrt((double)s.bn_var[co] + kBnEpsTc) : 1.0;
@@ -380,20 +556,33 @@ __device__ __forceinline__ float tc_folded_bias(const CdrConvBn& s, int co) {
   if (!s.bn_weight) return (float)b;
   return (float)((b - (double)s.bn_mean[co]) * tc_bn_scale(s, co) + (double)s.bn_bias[co]);
 }
-// (Cout,Cin) -> [n_pad][k_pitch] bf16
-__global__ void pack_conv1x1_bf16_kernel(CdrConvBn s, int cout, int cin, int k_pitch, int n_pad,
-                                         __nv_bfloat16* __restrict__ w_out, float* __restrict__ bias_out) {
+template <bool kSplit>
+__device__ __forceinline__ void store_weight(void* w0, void* w1, long long idx, float v) {
+  if constexpr (kSplit) {
+    float hi, lo;
+    split_tf32(v, hi, lo);
+    reinterpret_cast<float*>(w0)[idx] = hi;
+    reinterpret_cast<float*>(w1)[idx] = lo;
+  } else {
+    reinterpret_cast<__nv_bfloat16*>(w0)[idx] = __float2bfloat16_rn(v);
+  }
+}
+// (Cout,Cin) -> [n_pad][k_pitch]
+template <bool kSplit>
+__global__ void pack_conv1x1_tc_kernel(CdrConvBn s, int cout, int cin, int k_pitch, int n_pad, void* w0,
+                                       void* w1, float* __restrict__ bias_out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n_pad) bias_out[idx] = idx < cout ? tc_folded_bias(s, (int)idx) : 0.f;
   if (idx >= (long long)n_pad * k_pitch) return;
   const int n = (int)(idx / k_pitch), k = (int)(idx % k_pitch);
   float v = 0.f;
   if (n < cout && k < cin) v = (float)((double)s.weight[(size_t)n * cin + k] * tc_bn_scale(s, n));
-  w_out[idx] = __float2bfloat16_rn(v);
+  store_weight<kSplit>(w0, w1, idx, v);
 }
-// (Cin,Cout,4,4) -> [phase][n_pad][tap*Cin + ci] bf16
-__global__ void pack_deconv_bf16_kernel(CdrConvBn s, int cin, int cout, int n_pad,
-                                        __nv_bfloat16* __restrict__ w_out, float* __restrict__ bias_out) {
+// (Cin,Cout,4,4) -> [phase][n_pad][tap*Cin + ci]
+template <bool kSplit>
+__global__ void pack_deconv_tc_kernel(CdrConvBn s, int cin, int cout, int n_pad, void* w0, void* w1,
+                                      float* __restrict__ bias_out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n_pad) bias_out[idx] = idx < cout ? tc_folded_bias(s, (int)idx) : 0.f;
   const long long K = 4LL * cin, total = 4LL * n_pad * K;
@@ -406,174 +595,216 @@ __global__ void pack_deconv_bf16_kernel(CdrConvBn s, int cin, int cout, int n_pa
   const int ky = 1 - py + 2 * ty, kx = 1 - px + 2 * tx;
   float v = 0.f;
   if (n < cout) v = (float)((double)s.weight[(((size_t)ci * cout + n) * 4 + ky) * 4 + kx] * tc_bn_scale(s, n));
-  w_out[idx] = __float2bfloat16_rn(v);
+  store_weight<kSplit>(w0, w1, idx, v);
 }
 
-__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out,
-                                   long long rows, int in_pitch, int cols) {
+// plane(s) -> fp32 (parity taps)
+__global__ void act_to_f32_kernel(const void* __restrict__ p0, const void* __restrict__ p1, int split,
+                                  float* __restrict__ out, long long rows, int in_pitch, int cols) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cols) return;
   const long long r = idx / cols;
   const int c = (int)(idx - r * cols);
-  out[idx] = __bfloat162float(in[r * in_pitch + c]);
+  const long long i = r * in_pitch + c;
+  out[idx] = split ? reinterpret_cast<const float*>(p0)[i] + reinterpret_cast<const float*>(p1)[i]
+                   : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p0)[i]);
 }
 
 // ------------------------------------------------------------------------------------------
-struct TcMaps {  // weight tensor maps live with the weights
-  CUtensorMap cf1, cf2a, cf2b, out, dc[3], fin;
-};
-static constexpr int kTcCf1NPad = 384, kTcCf2NPad = 512;   // BN=128 tiles
 static const int kTcDcCin[3] = {kFeatC, kDecC, kDecC};
 
-template <typename T>
-static T* bump(uint8_t*& p, size_t count) {
-  T* r = (T*)p;
-  p += round_up<size_t>(count * sizeof(T), 1024);
-  return r;
+struct Bump1K {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Bump1K(void* b) : base((uint8_t*)b) {}
+  void* take(size_t bytes) {
+    void* r = base ? base + off : nullptr;
+    off += round_up<size_t>(bytes, 1024);
+    return r;
+  }
+};
+
+static void plan_layer(TcLayer& L, Bump1K& b, int kind, int rows, int k, int k_pitch, int bn, int n_pad, int bias_n) {
+  const int elem = kind == kKindBF16 ? 2 : 4;
+  L.rows = rows; L.k = k; L.k_pitch = k_pitch; L.bn = bn; L.n_pad = n_pad;
+  L.w[0] = b.take((size_t)rows * k_pitch * elem);
+  L.w[1] = kind == kKindTF32X3 ? b.take((size_t)rows * k_pitch * elem) : nullptr;
+  L.bias = (float*)b.take((size_t)bias_n * sizeof(float));
 }
 
-static size_t plan_tc_weights(TcWeights& w, uint8_t* base) {
-  uint8_t* p = base;
+static size_t plan_tc_weights(TcPack& pk, const TcWeights& w, void* base) {
+  Bump1K b(base);
+  const int kind = pk.kind;
+  const int bn_wide = kind == kKindBF16 ? 256 : 128;
   if (w.has_fusion) {
-    w.w_cf1 = bump<__nv_bfloat16>(p, (size_t)kTcCf1NPad * kFeatC);
-    w.w_cf2a = bump<__nv_bfloat16>(p, (size_t)kTcCf2NPad * 2 * kHid2);
-    w.w_cf2b = bump<__nv_bfloat16>(p, (size_t)kTcCf2NPad * kHid2);
-    w.w_out = bump<__nv_bfloat16>(p, (size_t)2 * kFeatC * kHid1Pad);
-    w.b_cf1 = bump<float>(p, kTcCf1NPad);
-    w.b_cf2a = bump<float>(p, kTcCf2NPad);
-    w.b_cf2b = bump<float>(p, kTcCf2NPad);
-    w.b_out = bump<float>(p, (size_t)2 * kFeatC);
+    plan_layer(pk.cf1, b, kind, 384, kFeatC, kFeatC, 128, 384, 384);
+    plan_layer(pk.cf2a, b, kind, 512, 2 * kHid2, 2 * kHid2, 128, 512, 512);
+    plan_layer(pk.cf2b, b, kind, 512, kHid2, kHid2, 128, 512, 512);
+    plan_layer(pk.out, b, kind, 2 * kFeatC, kHid1, kHid1Pad, bn_wide, kFeatC, 2 * kFeatC);
   }
-  for (int i = 0; i < 3; ++i) {
-    w.w_dc[i] = bump<__nv_bfloat16>(p, (size_t)4 * kDecC * 4 * kTcDcCin[i]);
-    w.b_dc[i] = bump<float>(p, kDecC);
-  }
-  w.w_fin = bump<__nv_bfloat16>(p, (size_t)w.fin_npad * kDecC);
-  w.b_fin = bump<float>(p, w.fin_npad);
-  return (size_t)(p - base);
+  for (int i = 0; i < 3; ++i)
+    plan_layer(pk.dc[i], b, kind, 4 * kDecC, 4 * kTcDcCin[i], 4 * kTcDcCin[i], bn_wide, kDecC, kDecC);
+  plan_layer(pk.fin, b, kind, w.fin_npad, kDecC, kDecC, 32, w.fin_npad, w.fin_npad);
+  return b.off;
 }
 
-static int weight_map(CUtensorMap* m, const __nv_bfloat16* w, int rows, int k, int k_pitch, int bn) {
-  const uint64_t dims[2] = {(uint64_t)k, (uint64_t)rows};
-  const uint64_t strides[1] = {(uint64_t)k_pitch};
-  const uint32_t box[2] = {(uint32_t)kTcBK, (uint32_t)bn};
-  return make_tmap_bf16(m, w, 2, dims, strides, box);
+static int layer_maps(TcLayer& L, int kind) {
+  const int elem = kind == kKindBF16 ? 2 : 4;
+  const int bk = kind == kKindBF16 ? 64 : 32;
+  for (int pl = 0; pl < (kind == kKindTF32X3 ? 2 : 1); ++pl) {
+    const uint64_t dims[2] = {(uint64_t)L.k, (uint64_t)L.rows};
+    const uint64_t strides[1] = {(uint64_t)L.k_pitch};
+    const uint32_t box[2] = {(uint32_t)bk, (uint32_t)L.bn};
+    if (int rc = make_tmap(&L.map[pl], L.w[pl], elem, 2, dims, strides, box)) return rc;
+  }
+  return CDR_OK;
 }
 
-int tc_weights_create(const CdrWeightPtrs& src, TcWeights& w, cudaStream_t st) {
+int tc_weights_create(const CdrWeightPtrs& src, int kind, TcWeights& w, cudaStream_t st) {
   w.joints = src.num_joints;
   w.has_fusion = src.has_fusion;
   w.fin_npad = round_up(src.num_joints, 32);
-  const size_t bytes = plan_tc_weights(w, nullptr);
+  w.kind = kind;
+  TcPack* pk = new TcPack();
+  pk->kind = kind;
+  w.impl = pk;
+  const size_t bytes = plan_tc_weights(*pk, w, nullptr);
   CDR_CUDA(cudaMalloc(&w.pool, bytes));
-  plan_tc_weights(w, (uint8_t*)w.pool);
-  auto pack1 = [&](const CdrConvBn& s, int cout, int cin, int k_pitch, int n_pad, __nv_bfloat16* wo,
-                   float* bo) -> int {
-    const long long total = (long long)n_pad * k_pitch;
-    pack_conv1x1_bf16_kernel<<<(unsigned)ceil_div<long long>(total, 256), 256, 0, st>>>(s, cout, cin, k_pitch, n_pad, wo, bo);
-    CDR_LAUNCH_OK("pack_conv1x1_bf16_kernel");
+  plan_tc_weights(*pk, w, w.pool);
+  const bool split = kind == kKindTF32X3;
+  auto pack1 = [&](const CdrConvBn& s, int cout, int cin, TcLayer& L, size_t row_off, size_t bias_off) -> int {
+    const int rows = cout <= L.n_pad ? L.n_pad : cout;   // rows packed by this call
+    const long long total = (long long)rows * L.k_pitch;
+    const int elem = split ? 4 : 2;
+    void* w0 = (uint8_t*)L.w[0] + row_off * L.k_pitch * elem;
+    void* w1 = split ? (uint8_t*)L.w[1] + row_off * L.k_pitch * elem : nullptr;
+    const unsigned grid = (unsigned)ceil_div<long long>(total, 256);
+    if (split)
+      pack_conv1x1_tc_kernel<true><<<grid, 256, 0, st>>>(s, cout, cin, L.k_pitch, rows, w0, w1, L.bias + bias_off);
+    else
+      pack_conv1x1_tc_kernel<false><<<grid, 256, 0, st>>>(s, cout, cin, L.k_pitch, rows, w0, w1, L.bias + bias_off);
+    CDR_LAUNCH_OK("pack_conv1x1_tc_kernel");
     return CDR_OK;
   };
   int rc;
-  TcMaps* maps = new TcMaps();
-  w.maps = maps;
   if (w.has_fusion) {
-    if ((rc = pack1(src.cf_conv1, kHid1, kFeatC, kFeatC, kTcCf1NPad, w.w_cf1, w.b_cf1))) return rc;
-    if ((rc = pack1(src.cf_conv2a, kHid2, 2 * kHid2, 2 * kHid2, kTcCf2NPad, w.w_cf2a, w.b_cf2a))) return rc;
-    if ((rc = pack1(src.cf_conv2b, kHid2, kHid2, kHid2, kTcCf2NPad, w.w_cf2b, w.b_cf2b))) return rc;
+    if ((rc = pack1(src.cf_conv1, kHid1, kFeatC, pk->cf1, 0, 0))) return rc;
+    if ((rc = pack1(src.cf_conv2a, kHid2, 2 * kHid2, pk->cf2a, 0, 0))) return rc;
+    if ((rc = pack1(src.cf_conv2b, kHid2, kHid2, pk->cf2b, 0, 0))) return rc;
     for (int v = 0; v < 2; ++v)
-      if ((rc = pack1(src.cf_out[v], kFeatC, kHid1, kHid1Pad, kFeatC, w.w_out + (size_t)v * kFeatC * kHid1Pad,
-                      w.b_out + (size_t)v * kFeatC)))
-        return rc;
-    if ((rc = weight_map(&maps->cf1, w.w_cf1, kTcCf1NPad, kFeatC, kFeatC, 128))) return rc;
-    if ((rc = weight_map(&maps->cf2a, w.w_cf2a, kTcCf2NPad, 2 * kHid2, 2 * kHid2, 128))) return rc;
-    if ((rc = weight_map(&maps->cf2b, w.w_cf2b, kTcCf2NPad, kHid2, kHid2, 128))) return rc;
-    if ((rc = weight_map(&maps->out, w.w_out, 2 * kFeatC, kHid1, kHid1Pad, 256))) return rc;
+      if ((rc = pack1(src.cf_out[v], kFeatC, kHid1, pk->out, (size_t)v * kFeatC, (size_t)v * kFeatC))) return rc;
+    if ((rc = layer_maps(pk->cf1, kind)) || (rc = layer_maps(pk->cf2a, kind)) || (rc = layer_maps(pk->cf2b, kind)) ||
+        (rc = layer_maps(pk->out, kind)))
+      return rc;
   }
   for (int i = 0; i < 3; ++i) {
     const long long total = 4LL * kDecC * 4 * kTcDcCin[i];
-    pack_deconv_bf16_kernel<<<(unsigned)ceil_div<long long>(total, 256), 256, 0, st>>>(
-        src.deconv[i], kTcDcCin[i], kDecC, kDecC, w.w_dc[i], w.b_dc[i]);
-    CDR_LAUNCH_OK("pack_deconv_bf16_kernel");
-    if ((rc = weight_map(&maps->dc[i], w.w_dc[i], 4 * kDecC, 4 * kTcDcCin[i], 4 * kTcDcCin[i], 256))) return rc;
+    const unsigned grid = (unsigned)ceil_div<long long>(total, 256);
+    TcLayer& L = pk->dc[i];
+    if (split)
+      pack_deconv_tc_kernel<true><<<grid, 256, 0, st>>>(src.deconv[i], kTcDcCin[i], kDecC, kDecC, L.w[0], L.w[1], L.bias);
+    else
+      pack_deconv_tc_kernel<false><<<grid, 256, 0, st>>>(src.deconv[i], kTcDcCin[i], kDecC, kDecC, L.w[0], L.w[1], L.bias);
+    CDR_LAUNCH_OK("pack_deconv_tc_kernel");
+    if ((rc = layer_maps(L, kind))) return rc;
   }
-  if ((rc = pack1(src.final_layer, w.joints, kDecC, kDecC, w.fin_npad, w.w_fin, w.b_fin))) return rc;
-  if ((rc = weight_map(&maps->fin, w.w_fin, w.fin_npad, kDecC, kDecC, 32))) return rc;
-  return CDR_OK;
+  if ((rc = pack1(src.final_layer, w.joints, kDecC, pk->fin, 0, 0))) return rc;
+  return layer_maps(pk->fin, kind);
 }
 
 void tc_weights_destroy(TcWeights& w) {
   if (w.pool) cudaFree(w.pool);
   w.pool = nullptr;
-  delete (TcMaps*)w.maps;
-  w.maps = nullptr;
+  delete (TcPack*)w.impl;
+  w.impl = nullptr;
 }
 
 // ------------------------------------------------------------------------------------------
 struct TcHeadWs {
   float* pinv;
-  __nv_bfloat16 *x0, *y1, *z, *f1, *f2, *g, *x1, *d1, *d2, *d3;
+  Act x0, y1, z, f1, f2, g, x1, d1, d2, d3;
   float* hm;
   size_t bytes;
 };
-static TcHeadWs plan_tc_head(void* base, int B, int J) {
-  uint8_t* p = (uint8_t*)base;
+static Act take_act(Bump1K& b, size_t elems, int kind) {
+  Act a;
+  const int elem = kind == kKindBF16 ? 2 : 4;
+  a.p[0] = b.take(elems * elem);
+  a.p[1] = kind == kKindTF32X3 ? b.take(elems * elem) : nullptr;
+  return a;
+}
+static TcHeadWs plan_tc_head(void* base, int B, int J, int kind) {
+  Bump1K b(base);
   const size_t N = 2 * (size_t)B;
   TcHeadWs w;
-  w.pinv = bump<float>(p, N * 12);
-  w.x0 = bump<__nv_bfloat16>(p, N * kFeatHW * kFeatC);
-  w.y1 = bump<__nv_bfloat16>(p, N * kFeatHW * kHid1Pad);
-  w.z = bump<__nv_bfloat16>(p, (size_t)B * kFeatHW * 2 * kHid2);
-  w.f1 = bump<__nv_bfloat16>(p, (size_t)B * kFeatHW * kHid2);
-  w.f2 = bump<__nv_bfloat16>(p, (size_t)B * kFeatHW * kHid2);
-  w.g = bump<__nv_bfloat16>(p, N * kFeatHW * kHid1Pad);
-  w.x1 = bump<__nv_bfloat16>(p, N * kFeatHW * kFeatC);
-  w.d1 = bump<__nv_bfloat16>(p, N * 256 * kDecC);
-  w.d2 = bump<__nv_bfloat16>(p, N * 1024 * kDecC);
-  w.d3 = bump<__nv_bfloat16>(p, N * 4096 * kDecC);
-  w.hm = bump<float>(p, N * J * 4096);
-  w.bytes = (size_t)(p - (uint8_t*)base);
+  w.pinv = (float*)b.take(N * 12 * sizeof(float));
+  w.x0 = take_act(b, N * kFeatHW * kFeatC, kind);
+  w.y1 = take_act(b, N * kFeatHW * kHid1Pad, kind);
+  w.z = take_act(b, (size_t)B * kFeatHW * 2 * kHid2, kind);
+  w.f1 = take_act(b, (size_t)B * kFeatHW * kHid2, kind);
+  w.f2 = take_act(b, (size_t)B * kFeatHW * kHid2, kind);
+  w.g = take_act(b, N * kFeatHW * kHid1Pad, kind);
+  w.x1 = take_act(b, N * kFeatHW * kFeatC, kind);
+  w.d1 = take_act(b, N * 256 * kDecC, kind);
+  w.d2 = take_act(b, N * 1024 * kDecC, kind);
+  w.d3 = take_act(b, N * 4096 * kDecC, kind);
+  w.hm = (float*)b.take(N * J * 4096 * sizeof(float));
+  w.bytes = b.off;
   return w;
 }
 struct TcDecWs {
-  __nv_bfloat16 *x1, *d1, *d2, *d3;
+  Act x1, d1, d2, d3;
   size_t bytes;
 };
-static TcDecWs plan_tc_dec(void* base, int N) {
-  uint8_t* p = (uint8_t*)base;
+static TcDecWs plan_tc_dec(void* base, int N, int kind) {
+  Bump1K b(base);
   TcDecWs w;
-  w.x1 = bump<__nv_bfloat16>(p, (size_t)N * kFeatHW * kFeatC);
-  w.d1 = bump<__nv_bfloat16>(p, (size_t)N * 256 * kDecC);
-  w.d2 = bump<__nv_bfloat16>(p, (size_t)N * 1024 * kDecC);
-  w.d3 = bump<__nv_bfloat16>(p, (size_t)N * 4096 * kDecC);
-  w.bytes = (size_t)(p - (uint8_t*)base);
+  w.x1 = take_act(b, (size_t)N * kFeatHW * kFeatC, kind);
+  w.d1 = take_act(b, (size_t)N * 256 * kDecC, kind);
+  w.d2 = take_act(b, (size_t)N * 1024 * kDecC, kind);
+  w.d3 = take_act(b, (size_t)N * 4096 * kDecC, kind);
+  w.bytes = b.off;
   return w;
 }
 
 int tc_head_workspace_bytes(const TcWeights& w, int batch, size_t* bytes) {
-  *bytes = plan_tc_head(nullptr, batch, w.joints).bytes;
+  *bytes = plan_tc_head(nullptr, batch, w.joints, w.kind).bytes;
   return CDR_OK;
 }
-int tc_decoder_workspace_bytes(const TcWeights&, int n_images, size_t* bytes) {
-  *bytes = plan_tc_dec(nullptr, n_images).bytes;
+int tc_decoder_workspace_bytes(const TcWeights& w, int n_images, size_t* bytes) {
+  *bytes = plan_tc_dec(nullptr, n_images, w.kind).bytes;
   return CDR_OK;
 }
 
-static int tc_decoder(const TcWeights& w, const __nv_bfloat16* x1, int N, __nv_bfloat16* d1,
-                      __nv_bfloat16* d2, __nv_bfloat16* d3, float* heat, cudaStream_t st) {
-  const TcMaps* maps = (const TcMaps*)w.maps;
+static int to_rows(const float* feat, int n_img, const Act& out, int kind, cudaStream_t st) {
+  if (kind == kKindBF16)
+    return launch_nchw_to_rows_bf16(feat, n_img, kFeatC, kFeatHW, (__nv_bfloat16*)out.p[0], kFeatC, st);
+  return launch_nchw_to_rows_split(feat, n_img, kFeatC, kFeatHW, (float*)out.p[0], (float*)out.p[1], kFeatC, st);
+}
+static int ftl_act(const Act& in, int in_pitch, const float* mats, int rows, int cols, int n, const Act& out,
+                   int out_pitch, int out_fill, int kind, cudaStream_t st) {
+  if (kind == kKindBF16)
+    return launch_ftl<__nv_bfloat16>((const __nv_bfloat16*)in.p[0], in_pitch, mats, rows, cols, kFtlBlk, n, kFeatHW,
+                                     (__nv_bfloat16*)out.p[0], out_pitch, out_fill, st);
+  return launch_ftl_split((const float*)in.p[0], (const float*)in.p[1], in_pitch, mats, rows, cols, kFtlBlk, n,
+                          kFeatHW, (float*)out.p[0], (float*)out.p[1], out_pitch, out_fill, st);
+}
+
+static int tc_decoder(const TcWeights& w, const Act& x1, int N, const Act& d1, const Act& d2, const Act& d3,
+                      float* heat, cudaStream_t st) {
+  const TcPack* pk = (const TcPack*)w.impl;
   static const char* const kDcName[3] = {"deconv1", "deconv2", "deconv3"};
-  const __nv_bfloat16* in = x1;
-  __nv_bfloat16* outs[3] = {d1, d2, d3};
+  Act in = x1;
+  const Act outs[3] = {d1, d2, d3};
   int side = 8;
   for (int i = 0; i < 3; ++i) {
     set_stage(kDcName[i]);
     TcLaunch l{};
     l.A = in; l.a_pitch = kTcDcCin[i]; l.n_img = N; l.H = l.W = side; l.cin = kTcDcCin[i];
-    l.deconv = 1; l.groups = 4; l.tmap_b = &maps->dc[i]; l.b_group_rows = kDecC; l.n = kDecC; l.n_pad = kDecC;
-    l.bias = w.b_dc[i]; l.bias_group_stride = 0;
+    l.deconv = 1; l.groups = 4; l.layer = &pk->dc[i]; l.b_group_rows = kDecC; l.n = kDecC;
+    l.bias_group_stride = 0;
     l.C = outs[i]; l.c_pitch = kDecC; l.c_fill = kDecC; l.relu = 1; l.out_mode = kOutDeconv;
-    if (int rc = launch_tc<256>(l, st)) return rc;
+    if (int rc = launch_tc(w.kind, l, st)) return rc;
     in = outs[i];
     side *= 2;
   }
@@ -581,17 +812,18 @@ static int tc_decoder(const TcWeights& w, const __nv_bfloat16* x1, int N, __nv_b
   TcLaunch l{};
   l.A = d3; l.a_pitch = kDecC; l.n_img = N; l.H = l.W = kHeat; l.cin = kDecC; l.groups = 1;
   l.a_rows_total = (long long)N * 4096;
-  l.tmap_b = &maps->fin; l.n = w.joints; l.n_pad = w.fin_npad; l.bias = w.b_fin;
-  l.C = heat; l.relu = 0; l.out_mode = kOutPlanar;
-  const int rc = launch_tc<32>(l, st);
+  l.layer = &pk->fin; l.n = w.joints;
+  l.C.p[0] = heat; l.relu = 0; l.out_mode = kOutPlanar;
+  const int rc = launch_tc(w.kind, l, st);
   set_stage(nullptr);
   return rc;
 }
 
-static int tap_to_f32(float* dst, const __nv_bfloat16* src, long long rows, int pitch, int cols, cudaStream_t st) {
+static int tap_to_f32(float* dst, const Act& src, int kind, long long rows, int pitch, int cols, cudaStream_t st) {
   if (!dst) return CDR_OK;
-  bf16_to_f32_kernel<<<(unsigned)ceil_div<long long>(rows * cols, 256), 256, 0, st>>>(src, dst, rows, pitch, cols);
-  CDR_LAUNCH_OK("bf16_to_f32_kernel");
+  act_to_f32_kernel<<<(unsigned)ceil_div<long long>(rows * cols, 256), 256, 0, st>>>(
+      src.p[0], src.p[1], kind == kKindTF32X3, dst, rows, pitch, cols);
+  CDR_LAUNCH_OK("act_to_f32_kernel");
   return CDR_OK;
 }
 
@@ -599,9 +831,11 @@ int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r
                     const float* P_r, const float* pinv_l, const float* pinv_r, double pinv_rtol,
                     int batch, float scale, float* kp2d_l, float* kp2d_r, float* xyz,
                     const CdrHeadTaps* taps, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  const TcMaps* maps = (const TcMaps*)w.maps;
+  const TcPack* pk = (const TcPack*)w.impl;
+  const int kind = w.kind;
+  const int elem = kind == kKindBF16 ? 2 : 4;
   const int B = batch, N = 2 * batch, J = w.joints;
-  TcHeadWs ws = plan_tc_head(workspace, B, J);
+  TcHeadWs ws = plan_tc_head(workspace, B, J, kind);
   if (ws.bytes > workspace_bytes) {
     set_error("cdr_head_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
     return CDR_ERR_WORKSPACE;
@@ -616,49 +850,48 @@ int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r
     pinv[1] = ws.pinv + (size_t)B * 12;
   }
   set_stage("nchw_to_rows");
-  if ((rc = launch_nchw_to_rows_bf16(feat_l, B, kFeatC, kFeatHW, ws.x0, kFeatC, st))) return rc;
-  if ((rc = launch_nchw_to_rows_bf16(feat_r, B, kFeatC, kFeatHW, ws.x0 + (size_t)B * kFeatHW * kFeatC, kFeatC, st))) return rc;
+  if ((rc = to_rows(feat_l, B, ws.x0, kind, st))) return rc;
+  if ((rc = to_rows(feat_r, B, act_offset(ws.x0, (size_t)B * kFeatHW * kFeatC, elem), kind, st))) return rc;
   set_stage("cf_conv1");
   {
     TcLaunch l{};
     l.A = ws.x0; l.a_pitch = kFeatC; l.n_img = N; l.H = l.W = 8; l.cin = kFeatC; l.groups = 1;
     l.a_rows_total = (long long)N * kFeatHW;
-    l.tmap_b = &maps->cf1; l.n = kHid1; l.n_pad = kTcCf1NPad; l.bias = w.b_cf1;
+    l.layer = &pk->cf1; l.n = kHid1;
     l.C = ws.y1; l.c_pitch = kHid1Pad; l.c_fill = kHid1Pad; l.relu = 1; l.out_mode = kOutRows;
-    if ((rc = launch_tc<128>(l, st))) return rc;
+    if ((rc = launch_tc(kind, l, st))) return rc;
   }
   set_stage("ftl_inv");
   for (int v = 0; v < 2; ++v)
-    if ((rc = launch_ftl<__nv_bfloat16>(ws.y1 + (size_t)v * B * kFeatHW * kHid1Pad, kHid1Pad, pinv[v], 4, 3,
-                                        kFtlBlk, B, kFeatHW, ws.z + v * kHid2, 2 * kHid2, kHid2, st)))
+    if ((rc = ftl_act(act_offset(ws.y1, (size_t)v * B * kFeatHW * kHid1Pad, elem), kHid1Pad, pinv[v], 4, 3, B,
+                      act_offset(ws.z, (size_t)v * kHid2, elem), 2 * kHid2, kHid2, kind, st)))
       return rc;
   set_stage("cf_conv2");
   {
     TcLaunch l{};
     l.A = ws.z; l.a_pitch = 2 * kHid2; l.n_img = B; l.H = l.W = 8; l.cin = 2 * kHid2; l.groups = 1;
     l.a_rows_total = (long long)B * kFeatHW;
-    l.tmap_b = &maps->cf2a; l.n = kHid2; l.n_pad = kTcCf2NPad; l.bias = w.b_cf2a;
+    l.layer = &pk->cf2a; l.n = kHid2;
     l.C = ws.f1; l.c_pitch = kHid2; l.c_fill = kHid2; l.relu = 1; l.out_mode = kOutRows;
-    if ((rc = launch_tc<128>(l, st))) return rc;
-    l.A = ws.f1; l.a_pitch = kHid2; l.cin = kHid2; l.tmap_b = &maps->cf2b; l.bias = w.b_cf2b; l.C = ws.f2;
-    if ((rc = launch_tc<128>(l, st))) return rc;
+    if ((rc = launch_tc(kind, l, st))) return rc;
+    l.A = ws.f1; l.a_pitch = kHid2; l.cin = kHid2; l.layer = &pk->cf2b; l.C = ws.f2;
+    if ((rc = launch_tc(kind, l, st))) return rc;
   }
   set_stage("ftl_fwd");
   const float* Pv[2] = {P_l, P_r};
   for (int v = 0; v < 2; ++v)
-    if ((rc = launch_ftl<__nv_bfloat16>(ws.f2, kHid2, Pv[v], 3, 4, kFtlBlk, B, kFeatHW,
-                                        ws.g + (size_t)v * B * kFeatHW * kHid1Pad, kHid1Pad, kHid1Pad, st)))
+    if ((rc = ftl_act(ws.f2, kHid2, Pv[v], 3, 4, B, act_offset(ws.g, (size_t)v * B * kFeatHW * kHid1Pad, elem),
+                      kHid1Pad, kHid1Pad, kind, st)))
       return rc;
   set_stage("cf_out");
   {
     TcLaunch l{};
     l.A = ws.g; l.a_pitch = kHid1Pad; l.n_img = B; l.H = l.W = 8; l.cin = kHid1; l.groups = 2;
     l.a_rows_total = (long long)N * kFeatHW;
-    l.tmap_b = &maps->out; l.b_group_rows = kFeatC; l.n = kFeatC; l.n_pad = kFeatC;
-    l.bias = w.b_out; l.bias_group_stride = kFeatC;
+    l.layer = &pk->out; l.b_group_rows = kFeatC; l.n = kFeatC; l.bias_group_stride = kFeatC;
     l.C = ws.x1; l.c_group_stride = (long long)B * kFeatHW * kFeatC; l.c_pitch = kFeatC; l.c_fill = kFeatC;
     l.relu = 1; l.out_mode = kOutRows;
-    if ((rc = launch_tc<256>(l, st))) return rc;
+    if ((rc = launch_tc(kind, l, st))) return rc;
   }
   if ((rc = tc_decoder(w, ws.x1, N, ws.d1, ws.d2, ws.d3, ws.hm, st))) return rc;
   set_stage("softargmax_dlt");
@@ -671,9 +904,9 @@ int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r
       CDR_CUDA(cudaMemcpyAsync(taps->pinv, pinv[0], (size_t)B * 48, cudaMemcpyDeviceToDevice, st));
       CDR_CUDA(cudaMemcpyAsync(taps->pinv + (size_t)B * 12, pinv[1], (size_t)B * 48, cudaMemcpyDeviceToDevice, st));
     }
-    if ((rc = tap_to_f32(taps->cf_cat, ws.z, (long long)B * kFeatHW, 2 * kHid2, 2 * kHid2, st))) return rc;
-    if ((rc = tap_to_f32(taps->cf_f, ws.f2, (long long)B * kFeatHW, kHid2, kHid2, st))) return rc;
-    if ((rc = tap_to_f32(taps->f_out, ws.x1, (long long)N * kFeatHW, kFeatC, kFeatC, st))) return rc;
+    if ((rc = tap_to_f32(taps->cf_cat, ws.z, kind, (long long)B * kFeatHW, 2 * kHid2, 2 * kHid2, st))) return rc;
+    if ((rc = tap_to_f32(taps->cf_f, ws.f2, kind, (long long)B * kFeatHW, kHid2, kHid2, st))) return rc;
+    if ((rc = tap_to_f32(taps->f_out, ws.x1, kind, (long long)N * kFeatHW, kFeatC, kFeatC, st))) return rc;
     if (taps->heatmaps)
       CDR_CUDA(cudaMemcpyAsync(taps->heatmaps, ws.hm, (size_t)N * J * 4096 * 4, cudaMemcpyDeviceToDevice, st));
   }
@@ -682,13 +915,13 @@ int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r
 
 int tc_decoder_forward(const TcWeights& w, const float* feat, int n_images, float* heatmaps,
                        void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  TcDecWs ws = plan_tc_dec(workspace, n_images);
+  TcDecWs ws = plan_tc_dec(workspace, n_images, w.kind);
   if (ws.bytes > workspace_bytes) {
     set_error("cdr_decoder_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
     return CDR_ERR_WORKSPACE;
   }
   set_stage("nchw_to_rows");
-  if (int rc = launch_nchw_to_rows_bf16(feat, n_images, kFeatC, kFeatHW, ws.x1, kFeatC, st)) return rc;
+  if (int rc = to_rows(feat, n_images, ws.x1, w.kind, st)) return rc;
   return tc_decoder(w, ws.x1, n_images, ws.d1, ws.d2, ws.d3, heatmaps, st);
 }
 

@@ -8,6 +8,10 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#if defined(CDR_JACOBI_STATS)
+static long long cdr_jacobi_sweeps = 0;   // host-side instrumentation (tests/host)
+#endif
+
 namespace cdr {
 
 // Orthogonalise the C columns of G (R x C, column access G[r][c]) in place by plane
@@ -58,6 +62,9 @@ __host__ __device__ __forceinline__ void jacobi_onesided(double (&G)[R][C], doub
       }
     }
     if (!rotated) break;
+#if defined(CDR_JACOBI_STATS) && !defined(__CUDA_ARCH__)
+    ++cdr_jacobi_sweeps;
+#endif
   }
 }
 

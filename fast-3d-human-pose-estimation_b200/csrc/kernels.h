@@ -35,6 +35,12 @@ int launch_nchw_to_rows_f32(const float* in, int n_img, int C, int HW, float* ou
                             cudaStream_t st);
 int launch_nchw_to_rows_bf16(const float* in, int n_img, int C, int HW, __nv_bfloat16* out,
                              int out_pitch, cudaStream_t st);
+// fp32 hi/lo planes for the 3xTF32 tensor-core path (common.cuh: split_tf32)
+int launch_nchw_to_rows_split(const float* in, int n_img, int C, int HW, float* out_hi, float* out_lo,
+                              int out_pitch, cudaStream_t st);
+int launch_ftl_split(const float* in_hi, const float* in_lo, int in_pitch, const float* mats, int rows, int cols,
+                     int blk, int n, int hw, float* out_hi, float* out_lo, int out_pitch, int out_fill,
+                     cudaStream_t st);
 template <typename T>
 int launch_ftl(const T* in, int in_pitch, const float* mats, int rows, int cols, int blk, int n,
                int hw, T* out, int out_pitch, int out_fill, cudaStream_t st);

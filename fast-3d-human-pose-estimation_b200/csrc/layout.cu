@@ -48,6 +48,43 @@ int launch_nchw_to_rows_bf16(const float* in, int n_img, int C, int HW, __nv_bfl
   return launch_nchw_to_rows<__nv_bfloat16>(in, n_img, C, HW, out, out_pitch, st);
 }
 
+// split-plane variant for the 3xTF32 path (common.cuh: split_tf32)
+__global__ void __launch_bounds__(256)
+nchw_to_rows_split_kernel(const float* __restrict__ in, int C, int HW, float* __restrict__ out_hi,
+                          float* __restrict__ out_lo, int out_pitch) {
+  __shared__ float tile[32][65];
+  const int c0 = blockIdx.x * 32, p0 = blockIdx.y * 64, img = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int c = ty; c < 32; c += 8) {
+    const float* src = in + ((size_t)img * C + c0 + c) * HW + p0;
+    if (c0 + c < C) {
+      if (p0 + tx < HW) tile[c][tx] = src[tx];
+      if (p0 + tx + 32 < HW) tile[c][tx + 32] = src[tx + 32];
+    }
+  }
+  __syncthreads();
+  if (c0 + tx < C) {
+    for (int pp = ty; pp < 64; pp += 8) {
+      if (p0 + pp < HW) {
+        const float v = tile[tx][pp];
+        float hi, lo;
+        split_tf32(v, hi, lo);
+        const size_t o = ((size_t)img * HW + p0 + pp) * out_pitch + c0 + tx;
+        out_hi[o] = hi;
+        out_lo[o] = lo;
+      }
+    }
+  }
+}
+int launch_nchw_to_rows_split(const float* in, int n_img, int C, int HW, float* out_hi, float* out_lo,
+                              int out_pitch, cudaStream_t st) {
+  CDR_CHECK_ARG(in && out_hi && out_lo && n_img > 0 && C > 0 && HW > 0 && out_pitch >= C, "nchw_to_rows_split: bad args");
+  dim3 grid(ceil_div(C, 32), ceil_div(HW, 64), n_img);
+  nchw_to_rows_split_kernel<<<grid, 256, 0, st>>>(in, C, HW, out_hi, out_lo, out_pitch);
+  CDR_LAUNCH_OK("nchw_to_rows_split_kernel");
+  return CDR_OK;
+}
+
 // FTL (models/cdrnet.py:45-56) on pixel-major rows.  With z.reshape(b, N, -1) the k-th
 // "coordinate" of channel c is channel k*blk + c of the same pixel, so
 //   out[row, r*blk + c] = sum_k mats[img(row)][r][k] * in[row, k*blk + c].
@@ -73,6 +110,57 @@ ftl_kernel(const T* __restrict__ in, int in_pitch, const float* __restrict__ mat
     o[r * blk + c] = (T)acc;
   }
   if (c < out_fill - ROWS * blk) o[ROWS * blk + c] = (T)0.f;  // zero the pad columns
+}
+
+template <int ROWS, int COLS>
+__global__ void __launch_bounds__(256)
+ftl_split_kernel(const float* __restrict__ in_hi, const float* __restrict__ in_lo, int in_pitch,
+                 const float* __restrict__ mats, int blk, long long total, int hw, float* __restrict__ out_hi,
+                 float* __restrict__ out_lo, int out_pitch, int out_fill) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long row = idx / blk;
+  const int c = (int)(idx - row * blk);
+  const float* m = mats + (row / hw) * (ROWS * COLS);
+  float x[COLS];
+#pragma unroll
+  for (int k = 0; k < COLS; ++k) {
+    const long long i = row * in_pitch + k * blk + c;
+    x[k] = in_hi[i] + in_lo[i];          // exact: hi + lo reconstructs the fp32 value
+  }
+  const long long o = row * out_pitch;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) acc = fmaf(__ldg(m + r * COLS + k), x[k], acc);
+    float hi, lo;
+    split_tf32(acc, hi, lo);
+    out_hi[o + r * blk + c] = hi;
+    out_lo[o + r * blk + c] = lo;
+  }
+  if (c < out_fill - ROWS * blk) {
+    out_hi[o + ROWS * blk + c] = 0.f;
+    out_lo[o + ROWS * blk + c] = 0.f;
+  }
+}
+
+int launch_ftl_split(const float* in_hi, const float* in_lo, int in_pitch, const float* mats, int rows, int cols,
+                     int blk, int n, int hw, float* out_hi, float* out_lo, int out_pitch, int out_fill,
+                     cudaStream_t st) {
+  CDR_CHECK_ARG(in_hi && in_lo && mats && out_hi && out_lo && n > 0 && hw > 0 && blk > 0, "ftl_split: bad args");
+  const long long total = (long long)n * hw * blk;
+  const unsigned grid = (unsigned)ceil_div<long long>(total, 256);
+  if (rows == 4 && cols == 3)
+    ftl_split_kernel<4, 3><<<grid, 256, 0, st>>>(in_hi, in_lo, in_pitch, mats, blk, total, hw, out_hi, out_lo, out_pitch, out_fill);
+  else if (rows == 3 && cols == 4)
+    ftl_split_kernel<3, 4><<<grid, 256, 0, st>>>(in_hi, in_lo, in_pitch, mats, blk, total, hw, out_hi, out_lo, out_pitch, out_fill);
+  else {
+    set_error("ftl_split: only (4x3) and (3x4) matrices are supported");
+    return CDR_ERR_UNSUPPORTED;
+  }
+  CDR_LAUNCH_OK("ftl_split_kernel");
+  return CDR_OK;
 }
 
 template <typename T>

@@ -53,8 +53,10 @@ typedef enum CdrStatus {
 /* Arithmetic the convolutions run in.  Soft-argmax, pinv, DLT and MPJPE always use
  * fp32 inputs with fp64 internals. */
 typedef enum CdrPrecision {
-  CDR_PREC_FP32 = 0, /* fp32 FFMA implicit-GEMM kernels: the parity configuration */
-  CDR_PREC_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulation in TMEM */
+  CDR_PREC_FP32 = 0,  /* fp32 FFMA implicit-GEMM kernels (CUDA cores) */
+  CDR_PREC_BF16 = 1,  /* bf16 operands on tcgen05 tensor cores, fp32 accumulation in TMEM */
+  CDR_PREC_TF32X3 = 2 /* fp32 accuracy on tcgen05: every operand split into two tf32 terms,
+                         three kind::tf32 MMAs per product, fp32 accumulation in TMEM */
 } CdrPrecision;
 
 /* One conv (or transposed conv) + eval-mode BatchNorm2d, reference tensor layouts. */

@@ -37,5 +37,8 @@ int main(int argc, char** argv) {
   }
   fclose(o);
   fclose(f);
+#ifdef CDR_JACOBI_STATS
+  fprintf(stderr, "avg sweeps per item: %.2f\n", (double)cdr_jacobi_sweeps / (double)n);
+#endif
   return 0;
 }

@@ -84,37 +84,40 @@ def _nhwc_to_nchw(t, c):  # (..., 64, C) -> (..., C, 8, 8)
     return t.reshape(*t.shape[:-2], 8, 8, c).permute(*range(t.dim() - 2), -1, -3, -2)
 
 
-def test_head_fp32_vs_fp64_oracle_stagewise(cuda_pkg):
+@pytest.mark.parametrize("precision", ["fp32", "fp32_ffma"])
+def test_head_fp32_vs_fp64_oracle_stagewise(cuda_pkg, precision):
+    """fp32 results: 'fp32' = 3xTF32 split on the tcgen05 tensor cores (default), 'fp32_ffma' = CUDA cores."""
     b = 4
     sd = synth.make_head_state_dict(seed=0, calibrated=True, randomize_bn=True)
     feats, cams = synth.make_features(b, seed=1), synth.make_cameras(b, seed=2)
     gt = synth.make_gt(cams, seed=3)
     otaps = {}
     o2, o3 = _oracle64(sd, feats, cams, otaps)
-    m = _model(cuda_pkg, sd)
+    m = _model(cuda_pkg, sd, precision=precision)
     (kl, kr), xyz, taps = _run_head(m, feats, cams, taps=True)
 
     def rel(got, want):
         return float(np.abs(got - want).max() / np.abs(want).max())
 
     pinv = torch.stack(otaps["pinv"]).numpy()
-    assert rel(taps["pinv"].cpu().numpy(), pinv) < 1e-6
     cat = _nhwc_to_nchw(taps["cf_cat"].cpu(), 800).numpy()
-    assert rel(cat, otaps["cf_cat"].numpy()) < 2e-5
     f = _nhwc_to_nchw(taps["cf_f"].cpu(), 400).numpy()
-    assert rel(f, otaps["cf_f"].numpy()) < 2e-5
     fo = _nhwc_to_nchw(taps["f_out"].cpu(), 2048).numpy()
-    assert rel(fo, torch.stack(otaps["f_out"]).numpy()) < 2e-5
     hm = taps["heatmaps"].cpu().numpy()
-    assert rel(hm, torch.stack(otaps["heatmaps"]).numpy()) < 2e-5
+    r = {"pinv": rel(taps["pinv"].cpu().numpy(), pinv), "cf_cat": rel(cat, otaps["cf_cat"].numpy()),
+         "cf_f": rel(f, otaps["cf_f"].numpy()), "f_out": rel(fo, torch.stack(otaps["f_out"]).numpy()),
+         "heat": rel(hm, torch.stack(otaps["heatmaps"]).numpy())}
+    print(f"\nstage taps [{precision}] max|err|/max|ref|: " + " ".join(f"{k}={v:.2e}" for k, v in r.items()))
+    assert r["pinv"] < 1e-6
+    assert r["cf_cat"] < 2e-5 and r["cf_f"] < 2e-5 and r["f_out"] < 2e-5 and r["heat"] < 2e-5
 
-    d2, d3 = check_3d(cams, kl, kr, xyz, o2, o3, "head B=4:")
+    d2, d3 = check_3d(cams, kl, kr, xyz, o2, o3, f"head B=4 [{precision}]:")
     # the reference's own fp32 rounding, for context (printed with -s)
     with torch.no_grad():
         r2, r3 = O.head_forward(sd, feats, [torch.from_numpy(cams["P_l"]), torch.from_numpy(cams["P_r"])])
     ref_d2 = max(np.abs(r2[0].numpy() - o2[0]).max(), np.abs(r2[1].numpy() - o2[1]).max())
     ref_d3 = np.abs(r3.numpy() - o3).max()
-    print(f"\nCUDA fp32 vs fp64 oracle: d2D={d2:.2e}px d3D={d3:.2e}mm | reference fp32 vs fp64: "
+    print(f"\nCUDA {precision} vs fp64 oracle: d2D={d2:.2e}px d3D={d3:.2e}mm | reference fp32 vs fp64: "
           f"d2D={ref_d2:.2e}px d3D={ref_d3:.2e}mm")
     assert d2 <= TOL_2D_PX
     assert d3 <= max(TOL_3D_MM, 3 * ref_d3), "worse than 3x the reference's own fp32 rounding"
@@ -344,16 +347,18 @@ def test_ftl_identity_and_oracle(cuda_pkg):
         L.check(L.lib().cdr_ftl(L.ptr(xin), 304, L.ptr(P_d), 2, 2, 100, b, 64, L.ptr(out), 400, 400, st))
 
 
-def test_decoder_forward_vs_oracle(cuda_pkg):
+@pytest.mark.parametrize("precision", ["fp32", "fp32_ffma"])
+def test_decoder_forward_vs_oracle(cuda_pkg, precision):
     """PoseResNet's decoder half (models/poseresnet.py:17-21) incl. an odd image count."""
     n, joints = 3, 16
     sd = synth.make_head_state_dict(seed=3, joints=joints, calibrated=True, randomize_bn=True, decoder_only=True)
     feats = synth.make_features(n, seed=4)[0]
     want = O.decoder(O.cast_state_dict(sd, torch.float64), feats.double()).numpy()
-    dec = cuda_pkg.PoseDecoder(synth.make_cfg(18, joints))
+    dec = cuda_pkg.PoseDecoder(synth.make_cfg(18, joints), precision=precision)
     dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items()})
     dec = dec.cuda().eval()
     got = dec(feats.cuda()).cpu().numpy()
+    print(f"\ndecoder [{precision}] rel err {np.abs(got - want).max() / np.abs(want).max():.2e}")
     assert got.shape == (n, joints, 64, 64)
     assert np.abs(got - want).max() / np.abs(want).max() < 2e-5
 
