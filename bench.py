@@ -286,6 +286,48 @@ def measure(args, precision, ctx):
     }
 
 
+def stream_microbench(dev, poses=8192, reps=5):
+    """BASELINE configs[3] in miniature: the fused soft-argmax + DLT kernel streaming `poses` stereo
+    poses x 19 joints x 2 views x 64x64 fp32 logits (>> L2) — its HBM roofline at scale (the B=64
+    head launch is latency-bound: 64 CTAs, 40 MB)."""
+    from fast_3d_human_pose_estimation_b200 import synth, _lib
+    L = _lib.lib()
+    cams = synth.make_cameras(64, seed=4)
+    P_l = torch.from_numpy(cams["P_l"]).to(dev).repeat(poses // 64, 1, 1).contiguous()
+    P_r = torch.from_numpy(cams["P_r"]).to(dev).repeat(poses // 64, 1, 1).contiguous()
+    g = torch.Generator(device=dev).manual_seed(0)
+    heat = torch.empty((2, poses, JOINTS, 64, 64), dtype=torch.float32, device=dev)
+    for v in range(2):
+        for lo in range(0, poses, 1024):
+            heat[v, lo:lo + 1024].normal_(0.0, 3.0, generator=g)
+    kl = torch.empty((poses, JOINTS, 2), device=dev)
+    kr = torch.empty_like(kl)
+    xyz = torch.empty((poses, JOINTS, 3), device=dev)
+    st = _lib.current_stream_ptr(dev)
+
+    def run():
+        _lib.check(L.cdr_softargmax_dlt(_lib.ptr(heat[0]), _lib.ptr(heat[1]), 0, _lib.ptr(P_l), _lib.ptr(P_r), poses,
+                                        JOINTS, 64, 64, 4.0, _lib.ptr(kl), _lib.ptr(kr), _lib.ptr(xyz), None, None,
+                                        None, None, None, st))
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); run(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = float(np.median(ts))
+    pk = peaks()
+    gbs = SOFTARGMAX_DLT_BYTES_PER_POSE * poses / (ms / 1e3) / 1e9
+    del heat
+    return {"kernel": "softargmax_dlt (streaming microbench)", "bound": "hbm", "poses": poses,
+            "bytes_per_pose": SOFTARGMAX_DLT_BYTES_PER_POSE, "launch_ms": ms, "poses_per_s": poses / (ms / 1e3),
+            "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+            "peak_source": pk["source"], "input": "resident in HBM (5.1 GB, >> L2), fp32 logits N(0,3)"}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from fast_3d_human_pose_estimation_b200 import synth
@@ -350,6 +392,8 @@ def run_ours(args):
                   "decoder_tflops", "decoder_frac_of_peak", "head_tflops", "clocks", "wall_s_timed_region", "mpjpe"):
             line[k] = main_res[k]
         line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_stream_microbench:
+            line["roofline_hbm_stream"] = stream_microbench(dev)
         if other is not None:
             line["bf16"] = other
         print(json.dumps(line))
@@ -367,6 +411,7 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_ffma", "bf16"],
                     help="fp32 = fp32 results via 3xTF32 on tcgen05 (default); fp32_ffma = CUDA cores; bf16 = tcgen05 bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stream-microbench", action="store_true")
     ap.add_argument("--single-precision", action="store_true",
                     help="fp32 run only: skip the bf16 tensor-core measurement reported alongside")
     args = ap.parse_args()

@@ -3,8 +3,8 @@
 //
 // Structure (one persistent CTA per SM, 320 threads):
 //   warp 0      producer: one elected lane streams whole heat-maps (one 16 KB tile each) into a
-//               12-deep shared-memory ring with 1-D TMA bulk copies (cp.async.bulk) that
-//               complete on per-stage mbarriers -> ~190 KB in flight per SM with one thread.
+//               8-deep shared-memory ring with 1-D TMA bulk copies (cp.async.bulk) that
+//               complete on per-stage mbarriers -> 128 KB in flight per SM with one thread.
 //   warps 1..8  consumers: one warp per tile, two passes over the tile in shared memory
 //               (max, then exp/sum/centre of mass) with warp-shuffle reductions; exact
 //               "global max first" softmax like ATen, sums carried in fp64.
@@ -20,8 +20,14 @@
 namespace cdr {
 
 constexpr int kTileBytes = 16384;  // one 64x64 fp32 heat-map
-constexpr int kStages = 12;
 constexpr int kConsumerWarps = 8;
+// The ring depth must be a multiple of the consumer-warp count: tiles q and q+kStages share a
+// stage and its mbarrier, and only if the SAME warp consumes both (q % warps) is its wait for
+// phase(q+kStages) ordered after phase(q).  With 12 stages and 8 warps a starved warp could reach
+// the barrier while it was still in the older, incomplete phase, whose parity test reads as
+// "complete" — stale data, then a protocol deadlock (seen in the arg-max stress at 20 000 maps).
+constexpr int kStages = 8;
+static_assert(kStages % kConsumerWarps == 0, "see above");
 constexpr int kPoseBufs = 4;
 constexpr int kMaxTilesPerPose = 2 * kMaxJoints;
 constexpr int kHeatThreads = 32 * (kConsumerWarps + 2);
@@ -122,6 +128,62 @@ __device__ __forceinline__ void tile_softargmax(const uint8_t* tile, int hw, int
     SX += fma((double)col, sed, (double)sxl);
     SY = fma((double)row, sed, SY);
   }
+  S = warp_sum(S);
+  SX = warp_sum(SX);
+  SY = warp_sum(SY);
+  cx = SX / S;
+  cy = SY / S;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // one MUFU.EX2, rel. error 2^-22
+  return y;
+}
+
+// Fast path for the decoder's 64x64 maps.  With 32 lanes x 16 bytes per step a lane always sits in
+// the same columns (col0..col0+E-1) and walks R = 32*E/64 rows per step, so the centre of mass is
+//   sum_x = col0 * S + sum(k * e),   sum_y = row0 * S + R * sum(step * S_step)
+// and the inner loop carries no index arithmetic: 1 LDS.128 + E x (FFMA, EX2, FADD, FFMA) + two
+// fp32->fp64 conversions and four fp64 adds/FMAs per step.
+template <typename T>
+__device__ __forceinline__ void tile_softargmax_64(const uint8_t* tile, int lane, double& cx, double& cy) {
+  constexpr int E = Vec16<T>::kElems;        // 4 (fp32) / 8 (bf16)
+  constexpr int IT = 4096 / E / 32;          // 32 / 16 steps
+  constexpr int LPR = 64 / E;                // lanes per row
+  constexpr int R = 32 / LPR;                // rows per step
+  float m = -INFINITY;
+#pragma unroll 8
+  for (int it = 0; it < IT; ++it) {
+    float v[E];
+    Vec16<T>::load(tile, it * 32 + lane, v);
+#pragma unroll
+    for (int k = 0; k < E; ++k) m = fmaxf(m, v[k]);
+  }
+  m = warp_max(m);
+  const float kLog2e = 1.4426950408889634f;
+  const float ml2 = m * kLog2e;
+  double S = 0.0, SXL = 0.0, TY = 0.0, itd = 0.0;
+#pragma unroll 4
+  for (int it = 0; it < IT; ++it) {
+    float v[E];
+    Vec16<T>::load(tile, it * 32 + lane, v);
+    float se = 0.f, sxl = 0.f;
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+      const float e = ex2_approx(fmaf(v[k], kLog2e, -ml2));
+      se += e;
+      sxl = fmaf((float)k, e, sxl);
+    }
+    const double sed = (double)se;
+    S += sed;
+    SXL += (double)sxl;
+    TY = fma(itd, sed, TY);
+    itd += 1.0;
+  }
+  const double col0 = (double)((lane % LPR) * E), row0 = (double)(lane / LPR);
+  double SX = fma(col0, S, SXL);
+  double SY = fma(row0, S, (double)R * TY);
   S = warp_sum(S);
   SX = warp_sum(SX);
   SY = warp_sum(SY);
@@ -233,7 +295,10 @@ __global__ void __launch_bounds__(kHeatThreads, 1) heat_stream_kernel(const Heat
         }
       } else {
         double cx, cy;
-        tile_softargmax<T>(tile, hw, p.W, lane, cx, cy);
+        if (p.H == 64 && p.W == 64)
+          tile_softargmax_64<T>(tile, lane, cx, cy);
+        else
+          tile_softargmax<T>(tile, hw, p.W, lane, cx, cy);
         __syncwarp();
         if (lane == 0) {
           ptx::mbar_arrive(&sm.empty[stage]);
@@ -362,6 +427,17 @@ extern "C" int cdr_softargmax_dlt(const void* heat_l, const void* heat_r, int he
   CDR_CHECK_ARG(!gt3d || (gt2d_l && gt2d_r && pose_err),
                 "cdr_softargmax_dlt: gt3d given without gt2d/pose_err");
   if (batch == 0) return CDR_OK;
+  // the pose hand-off (pose_empty) assumes every consumer warp sees every pose: 2J >= #warps
+  CDR_CHECK_ARG(2 * joints >= kConsumerWarps || !gt3d,
+                "cdr_softargmax_dlt: fused MPJPE needs joints >= %d", kConsumerWarps / 2);
+  if (2 * joints < kConsumerWarps) {   // tiny skeletons: unfused (two soft-argmax launches + cdr_dlt)
+    CDR_CHECK_ARG(!heat_is_bf16 && kp2d_l && kp2d_r, "cdr_softargmax_dlt: joints < %d needs fp32 maps and 2D outputs",
+                  kConsumerWarps / 2);
+    if (int rc = cdr_softargmax((const float*)heat_l, batch * joints, H, W, scale, kp2d_l, stream)) return rc;
+    if (int rc = cdr_softargmax((const float*)heat_r, batch * joints, H, W, scale, kp2d_r, stream)) return rc;
+    CDR_CHECK_ARG(batch <= 0x7fffffff, "cdr_softargmax_dlt: batch too large for the unfused path");
+    return cdr_dlt(P_l, P_r, kp2d_l, kp2d_r, (int)batch, joints, xyz, stream);
+  }
   HeatParams p{};
   p.heat[0] = heat_l;
   p.heat[1] = heat_r;
