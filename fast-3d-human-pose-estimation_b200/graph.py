@@ -1,0 +1,97 @@
+"""CUDA-graph replay of the end-to-end head step for fixed host buffers.
+
+``HeadGraph(model, feats_host, P_host, gt=...)`` captures, once,
+
+    pinned host latents / P  --H2D-->  cdr_head_forward  [--> MPJPE partial sums]  --D2H-->  pinned host results
+
+into one CUDA graph (the library's calls allocate nothing and never synchronise, so they are
+capturable — include/cdrhead.h).  ``replay()`` then costs one graph launch instead of ~25 kernel
+launches plus the Python shim; the caller refills the same pinned input tensors between replays
+(the usual CUDA-graph contract).  Used for the `e2e` number of bench.py and for low-latency
+per-frame inference (inference.py's B=1 loop).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import cdrnet as _cdrnet
+from .metrics import mpjpe_sums
+
+
+class HeadGraph:
+    def __init__(self, model, feats_host, P_host, gt=None, img_size=256, warmup=2, chunks=None):
+        """feats_host: list[2] of pinned (B,2048,8,8) fp32; P_host: list[2] of pinned (B,3,4) fp32;
+        gt: optional dict of DEVICE tensors gt3d/gt2d_l/gt2d_r/vis for fused MPJPE sums.
+        chunks: the batch is cut into this many slices; slice i+1 crosses PCIe on a copy stream
+        while slice i computes (fork/join inside the graph).  Default: 2 when B >= 32 (small H2D copies are slow on PCIe, more chunks lose)."""
+        for t in list(feats_host) + list(P_host):
+            if not (isinstance(t, torch.Tensor) and t.is_pinned() and t.dtype == torch.float32):
+                raise ValueError("HeadGraph inputs must be pinned float32 host tensors")
+        self.model = model
+        self.dev = next(model.CF.parameters()).device
+        self.feats_host, self.P_host = list(feats_host), list(P_host)
+        self.gt, self.img_size = gt, img_size
+        b, j = feats_host[0].shape[0], model.decoder.num_joints
+        self.chunks = chunks if chunks else (2 if b >= 32 else 1)   # measured best at B=64 (profiles/)
+        self.bounds = [(b * c // self.chunks, b * (c + 1) // self.chunks) for c in range(self.chunks)]
+        self.bounds = [(lo, hi) for lo, hi in self.bounds if hi > lo]
+        self.feats_dev = [torch.empty(t.shape, dtype=torch.float32, device=self.dev) for t in feats_host]
+        self.P_dev = [torch.empty(t.shape, dtype=torch.float32, device=self.dev) for t in P_host]
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.kp_host = [torch.empty((b, j, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.xyz_host = torch.empty((b, j, 3), dtype=torch.float32).pin_memory()
+        self.sums_host = torch.empty(4, dtype=torch.float64).pin_memory() if gt is not None else None
+        self.xyz_dev = torch.empty((b, j, 3), dtype=torch.float32, device=self.dev)
+        self.sums_dev = torch.zeros(4, dtype=torch.float64, device=self.dev) if gt is not None else None
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):          # warm-up: packs weights, sizes the workspace, sets kernel attributes
+            for _ in range(max(1, warmup)):
+                self._step()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        # keep the workspace this graph's pointers refer to alive even if eager calls grow it later
+        key = (self.dev.type, self.dev.index if self.dev.index is not None else torch.cuda.current_device())
+        self._workspace = _cdrnet._WS.get(key)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step()
+
+    def _step(self):
+        cur = torch.cuda.current_stream(self.dev)
+        self.copy_stream.wait_stream(cur)                       # fork
+        events = []
+        with torch.cuda.stream(self.copy_stream):
+            for lo, hi in self.bounds:
+                for d, h in zip(self.feats_dev + self.P_dev, self.feats_host + self.P_host):
+                    d[lo:hi].copy_(h[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                events.append(ev)
+        if self.sums_dev is not None:
+            self.sums_dev.zero_()
+        for (lo, hi), ev in zip(self.bounds, events):
+            cur.wait_event(ev)
+            (kl, kr), xyz = self.model.head([f[lo:hi] for f in self.feats_dev], [p[lo:hi] for p in self.P_dev],
+                                            img_size=self.img_size)
+            self.xyz_dev[lo:hi].copy_(xyz)
+            self.kp_host[0][lo:hi].copy_(kl, non_blocking=True)
+            self.kp_host[1][lo:hi].copy_(kr, non_blocking=True)
+            if self.gt is not None:
+                g = self.gt
+                vis = g.get("vis")
+                self.sums_dev += mpjpe_sums([kl, kr], xyz, g["gt3d"][lo:hi], g["gt2d_l"][lo:hi], g["gt2d_r"][lo:hi],
+                                            vis[lo:hi] if vis is not None and vis.shape[0] == g["gt3d"].shape[0] else vis)
+        self.xyz_host.copy_(self.xyz_dev, non_blocking=True)
+        if self.gt is not None:
+            self.sums_host.copy_(self.sums_dev, non_blocking=True)
+        cur.wait_stream(self.copy_stream)                       # join
+
+    def replay(self, sync=True):
+        """One end-to-end step on the current contents of the pinned input tensors.
+        Returns (kp_host list[2], xyz_host, sums_host) — valid after the sync."""
+        self.graph.replay()
+        if sync:
+            torch.cuda.current_stream(self.dev).synchronize()
+        return self.kp_host, self.xyz_host, self.sums_host

@@ -482,3 +482,27 @@ def test_bf16_head_vs_emulated_and_fp64_oracle(cuda_pkg):
     d3 = np.abs(xyz.cpu().numpy() - o3).max(-1)
     print(f"bf16 3D on well-conditioned joints: max {d3[good].max():.2f} mean {d3[good].mean():.2f} mm")
     assert d3[good].max() <= 10.0 and d3[good].mean() <= 3.0
+
+
+def test_head_graph_replay_matches_eager(cuda_pkg):
+    """CUDA-graph capture of H2D -> head -> MPJPE -> D2H (the e2e path of bench.py): bit-identical to
+    the eager call, and re-playable after the pinned inputs are refilled."""
+    b = 3
+    sd = synth.make_head_state_dict(seed=0, calibrated=True)
+    m = _model(cuda_pkg, sd, precision="bf16")
+    feats = [f.pin_memory() for f in synth.make_features(b, seed=1)]
+    cams = synth.make_cameras(b, seed=2)
+    gt = synth.make_gt(cams, seed=3)
+    Ps = [torch.from_numpy(cams["P_l"]).pin_memory(), torch.from_numpy(cams["P_r"]).pin_memory()]
+    gtd = {k: torch.from_numpy(gt[k]).cuda() for k in ("gt3d", "gt2d_l", "gt2d_r", "vis")}
+    hg = cuda_pkg.HeadGraph(m, feats, Ps, gt=gtd)
+    (kl, kr), xyz = m.head([f.cuda() for f in feats], [p.cuda() for p in Ps])
+    sums = cuda_pkg.mpjpe_sums([kl, kr], xyz, gtd["gt3d"], gtd["gt2d_l"], gtd["gt2d_r"], gtd["vis"])
+    kp_h, xyz_h, sums_h = hg.replay()
+    assert torch.equal(kp_h[0], kl.cpu()) and torch.equal(kp_h[1], kr.cpu()) and torch.equal(xyz_h, xyz.cpu())
+    assert torch.equal(sums_h, sums.cpu())
+    new = synth.make_features(b, seed=7)                 # refill the same pinned tensors
+    feats[0].copy_(new[0]); feats[1].copy_(new[1])
+    (kl2, _), xyz2 = m.head([f.cuda() for f in feats], [p.cuda() for p in Ps])
+    kp_h, xyz_h, _ = hg.replay()
+    assert torch.equal(kp_h[0], kl2.cpu()) and torch.equal(xyz_h, xyz2.cpu()) and not torch.equal(xyz2, xyz)
