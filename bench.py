@@ -45,6 +45,13 @@ def peaks():
     return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch from the latest committed ncu capture (profiles/rNN_traffic.json)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    return json.load(open(files[-1])) if files else {}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -259,7 +266,9 @@ def measure(args, precision, ctx):
     if top in FLOP_PER_PAIR:
         ach = FLOP_PER_PAIR[top] * B / (stage_ms[top] / 1e3) / 1e12
         roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"],
-                "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"], "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"],
+                "traffic": ncu_traffic().get(precision, {}).get(top) if B == 64 else None,
+                "traffic_source": ncu_traffic().get("source"),
                 "peak_source": pk["source"] + " bf16 sustained (cuBLAS)", "launch_ms": stage_ms[top],
                 "share_of_step": share,
                 "note": {"bf16": "tcgen05 kind::f16, bf16 operands",
@@ -331,7 +340,9 @@ def stream_microbench(dev, poses=8192, reps=5):
     return {"kernel": "softargmax_dlt (streaming microbench)", "bound": "hbm", "poses": poses,
             "bytes_per_pose": SOFTARGMAX_DLT_BYTES_PER_POSE, "launch_ms": ms, "poses_per_s": poses / (ms / 1e3),
             "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-            "peak_source": pk["source"], "input": "resident in HBM (5.1 GB, >> L2), fp32 logits N(0,3)"}
+            "peak_source": pk["source"], "input": "resident in HBM (5.1 GB, >> L2), fp32 logits N(0,3)",
+            "algorithmic_bytes": SOFTARGMAX_DLT_BYTES_PER_POSE * poses,
+            "traffic": ncu_traffic().get("softargmax_dlt_stream") if poses == 8192 else None}
 
 
 def run_ours(args):

@@ -54,7 +54,7 @@ def launches(tag, rnd):
     idx = [i for i, r in enumerate(recs) if r[0].startswith("heat_stream")]
     step = recs[idx[-2] + 1: idx[-1] + 1] if len(idx) >= 2 else []
     lines = [f"# ncu launch list, {tag} head, B=64 — `ncu --metrics gpu__time_duration.sum --clock-control none` "
-             f"on `python bench.py --steps 2 --warmup 3 --precision {tag} --no-cpu-baseline`",
+             f"on `python bench.py --steps 2 --warmup 3 --single-precision --no-cpu-baseline --no-stream-microbench --precision {tag}`",
              "# cold-cache, serialised launches: the SHARES are comparable with bench.py's live CUDA-event stage times, not the absolutes",
              "", "## totals over the whole run", "kernel,launches,total_us"]
     for n, (c, ns) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
@@ -91,9 +91,41 @@ def full(rep, rnd):
         print("  ", rec["kernel"], rec["grid"], {k.split(".")[0]: v for k, v in rec.items() if k not in ("kernel", "grid", "block")})
 
 
+def to_bytes(value, unit):
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    return float(value.replace(",", "")) * scale[unit]
+
+
+def traffic(rnd):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the profiled kernels, keyed the
+    way bench.py names stages (prof_tc / prof_tf32 capture deconv1, deconv2, deconv3, final_1x1 of
+    one step in launch order; prof_heat captures the streaming microbench launch)."""
+    out = {}
+    for rep, key in (("prof_tc", "bf16"), ("prof_tf32", "fp32")):
+        path = os.path.join(ROOT, "profiles", f"{rnd}_{rep}_raw.json")
+        if not os.path.exists(path):
+            continue
+        d = json.load(open(path))
+        u = d["units"]
+        names = ["deconv1", "deconv2", "deconv3", "final_1x1"]
+        out[key] = {n: to_bytes(l["dram__bytes_read.sum"], u["dram__bytes_read.sum"]) +
+                       to_bytes(l["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
+                    for n, l in zip(names, d["launches"])}
+    path = os.path.join(ROOT, "profiles", f"{rnd}_prof_heat_raw.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        u, l = d["units"], d["launches"][0]
+        out["softargmax_dlt_stream"] = to_bytes(l["dram__bytes_read.sum"], u["dram__bytes_read.sum"]) + \
+            to_bytes(l["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
+    out["source"] = f"ncu --set full --clock-control none, profiles/{rnd}_prof_*_raw.json (B=64 head; 8192-pose stream)"
+    json.dump(out, open(os.path.join(ROOT, "profiles", f"{rnd}_traffic.json"), "w"), indent=1)
+    print("wrote", f"profiles/{rnd}_traffic.json", out)
+
+
 if __name__ == "__main__":
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
     for tag in ("bf16", "fp32"):
         launches(tag, rnd)
-    for rep in ("prof_tc", "prof_ffma", "prof_heat"):
+    for rep in ("prof_tc", "prof_tf32", "prof_ffma", "prof_heat"):
         full(rep, rnd)
+    traffic(rnd)
