@@ -220,25 +220,45 @@ def measure(args, precision, ctx):
     sums_h = torch.empty(4, dtype=torch.float64).pin_memory()
     d2h = xyz_h.numel() * 4 + 32
     e_s, e_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # public API for fixed host buffers: pkg.HeadGraph = one CUDA graph of H2D -> head -> MPJPE -> D2H
-    hg = pkg.HeadGraph(model, feats_h, P_h, gt={"gt3d": g3, "gt2d_l": g2l, "gt2d_r": g2r, "vis": vis})
+    # public API for host buffers: pkg.HeadPipeline — per batch: H2D of the pinned latents / P on a copy
+    # stream, one CUDA graph (head -> MPJPE sums -> D2H of 2D/3D joints + sums) on the compute stream;
+    # batch i+1 crosses PCIe while batch i computes (depth 2).  Every step copies its inputs in and its
+    # results out; a step's results are read on the host one submit later.
+    pipe = pkg.HeadPipeline(model, B, gt={"gt3d": g3, "gt2d_l": g2l, "gt2d_r": g2r, "vis": vis})
 
-    def e2e_step():
-        _, x_h, s_h = hg.replay(sync=(world == 1))     # the caller reads the result every step
+    def post(slot):
         if world > 1:
-            x, s = cdist.gather_results(hg.xyz_dev, hg.sums_dev, n_total)
+            x, s = cdist.gather_results(pipe.xyz_dev[slot], pipe.sums_dev[slot], n_total)
             xyz_h.copy_(x, non_blocking=True)
             sums_h.copy_(s, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-    for _ in range(2):
-        e2e_step()
+
+    def e2e_run(k):
+        checksum = 0.0
+        pipe.submit(feats_h, P_h, post)
+        for _ in range(k - 1):
+            pipe.submit(feats_h, P_h, post)
+            _, _, x_h, s_h = pipe.collect()
+            checksum += float(x_h[0, 0, 0])            # the caller reads every step's result
+        _, _, x_h, s_h = pipe.collect()
+        return checksum + float(x_h[0, 0, 0])
+    e2e_run(3)
     barrier()
     e_s.record()
-    for i in range(K):
-        e2e_step()
+    e2e_run(K)
     e_e.record()
     barrier()
     e2e_ms = e_s.elapsed_time(e_e)
+    # latency form (no cross-step overlap): one CUDA graph of H2D -> head -> D2H, synchronised per step
+    hg = pkg.HeadGraph(model, feats_h, P_h, gt={"gt3d": g3, "gt2d_l": g2l, "gt2d_r": g2r, "vis": vis})
+    for _ in range(2):
+        hg.replay(sync=True)
+    l_s, l_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l_s.record()
+    for _ in range(K):
+        hg.replay(sync=True)
+    l_e.record()
+    torch.cuda.synchronize()
+    e2e_latency_ms = l_s.elapsed_time(l_e) / K
     d2h += 2 * B * JOINTS * 2 * 4                      # the graph also returns the two 2D joint sets
 
     # ---- per-kernel durations, live, with CUDA events on the launching stream
@@ -272,8 +292,10 @@ def measure(args, precision, ctx):
                 "peak_source": pk["source"] + " bf16 sustained (cuBLAS)", "launch_ms": stage_ms[top],
                 "share_of_step": share,
                 "note": {"bf16": "tcgen05 kind::f16, bf16 operands",
-                         "fp32": "tcgen05 kind::tf32, 3 MMAs per product (3xTF32 split) at half the bf16 rate: "
-                                 "at most 1/6 of the bf16 peak in algorithmic FLOPs",
+                         "fp32": "tcgen05 kind::f16 on fp16 two-term operands, 3 MMAs per product at the full 16-bit "
+                                 "rate: at most 1/3 of the bf16 peak in algorithmic FLOPs",
+                         "tf32x3": "tcgen05 kind::tf32, 3 MMAs per product (3xTF32 split) at half the bf16 rate: "
+                                   "at most 1/6 of the bf16 peak in algorithmic FLOPs",
                          "fp32_ffma": "fp32 FFMA kernel on CUDA cores; fp32 FFMA peak is 74.4 TFLOP/s"}[precision]}
     else:
         ach = SOFTARGMAX_DLT_BYTES_PER_POSE * B / (stage_ms[top] / 1e3) / 1e9
@@ -291,7 +313,9 @@ def measure(args, precision, ctx):
     return {
         "value": value, "ms_per_step": dev_ms / K, "dtype": precision,
         "e2e": {"value": n_total * K / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
+                "api": "HeadPipeline (depth-2: H2D of batch i+1 overlaps compute of batch i)",
+                "unpipelined_ms_per_step": e2e_latency_ms},
         "gpu_launches": int(launches), "launches_per_step": launches / K,
         "roofline": roof, "roofline_hbm": hbm, "stages_ms": stage_ms,
         "decoder_tflops": dec_tf, "decoder_frac_of_peak": dec_tf / pk["tflops_sustained"] if dec_tf else None,
@@ -343,6 +367,59 @@ def stream_microbench(dev, poses=8192, reps=5):
             "peak_source": pk["source"], "input": "resident in HBM (5.1 GB, >> L2), fp32 logits N(0,3)",
             "algorithmic_bytes": SOFTARGMAX_DLT_BYTES_PER_POSE * poses,
             "traffic": ncu_traffic().get("softargmax_dlt_stream") if poses == 8192 else None}
+
+
+def full_pipeline(args, ctx, precision):
+    """pairs/s of the whole CDRNet.forward — ResNet-101 encoder on torch/cuDNN (not
+    ours, by decree) + our head — on device-resident (B,3,256,256) image pairs.  Two encoder
+    settings: torch default fp32 (cuDNN may use TF32) and bf16 autocast + channels_last."""
+    import fast_3d_human_pose_estimation_b200 as pkg
+    from fast_3d_human_pose_estimation_b200 import synth
+    dev, B = ctx["dev"], args.batch
+    torch.manual_seed(0)
+    model = pkg.CDRNet(synth.make_cfg(101, JOINTS), precision=precision)
+    model.load_state_dict(ctx["sd"], strict=False)
+    model = model.to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(1)
+    xs = [torch.randn((B, 3, 256, 256), generator=g, device=dev) for _ in range(2)]
+    out = {}
+
+    def timed(fn, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    ms = timed(lambda: model(xs, ctx["Ps"]))
+    enc_ms = timed(lambda: [model.encoder(x) for x in xs])
+    out["encoder_fp32_cudnn"] = {"pairs_per_s": B / (ms / 1e3), "ms_per_step": ms, "encoder_ms": enc_ms,
+                                 "head_share": max(0.0, 1.0 - enc_ms / ms)}
+    enc = model.encoder.to(memory_format=torch.channels_last)
+    xcl = [x.contiguous(memory_format=torch.channels_last) for x in xs]
+
+    def bf16_step():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            zs = [enc(x) for x in xcl]
+        return model.head([z.float() for z in zs], ctx["Ps"])
+
+    def bf16_enc():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            return [enc(x) for x in xcl]
+    ms = timed(bf16_step)
+    enc_ms = timed(bf16_enc)
+    out["encoder_bf16_autocast_channels_last"] = {"pairs_per_s": B / (ms / 1e3), "ms_per_step": ms,
+                                                  "encoder_ms": enc_ms, "head_share": max(0.0, 1.0 - enc_ms / ms)}
+    out["note"] = ("ResNet-101 encoder = 40.7 GF/pair on torch/cuDNN (out of scope, SURVEY §8f rank 1); head = "
+                   f"{precision} kernels of this repo; images resident in HBM")
+    del model, xs, xcl
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -413,6 +490,11 @@ def run_ours(args):
             line["roofline_hbm_stream"] = stream_microbench(dev)
         if other is not None:
             line["bf16"] = other
+        if world == 1 and not args.no_full_pipeline:
+            try:
+                line["full_pipeline"] = full_pipeline(args, ctx, args.precision)
+            except Exception as e:                      # secondary number: never lose the main line
+                line["full_pipeline"] = {"error": repr(e)[:200]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -426,10 +508,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="stereo pairs per GPU per step")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_ffma", "bf16"],
-                    help="fp32 = fp32 results via 3xTF32 on tcgen05 (default); fp32_ffma = CUDA cores; bf16 = tcgen05 bf16")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "fp32_ffma", "bf16"],
+                    help="fp32 = fp32 results on tcgen05: decoder on scaled fp16 two-term operands, fusion block 3xTF32 "
+                         "(default); tf32x3 = 3xTF32 everywhere; fp32_ffma = CUDA cores; bf16 = tcgen05 bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stream-microbench", action="store_true")
+    ap.add_argument("--no-full-pipeline", action="store_true")
     ap.add_argument("--single-precision", action="store_true",
                     help="fp32 run only: skip the bf16 tensor-core measurement reported alongside")
     args = ap.parse_args()

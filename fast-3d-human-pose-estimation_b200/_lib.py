@@ -16,10 +16,11 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cdrhead.h")
 CDR_PREC_FP32 = 0
 CDR_PREC_BF16 = 1
 CDR_PREC_TF32X3 = 2
+CDR_PREC_F16X2 = 3
 # "fp32"   : fp32 results on the tensor cores (3xTF32 split, tcgen05) — the default
 # "fp32_ffma": the same arithmetic on CUDA cores (FFMA), kept as the in-library cross-check
 # "bf16"   : bf16 operands on the tensor cores
-PRECISIONS = {"fp32": CDR_PREC_TF32X3, "tf32x3": CDR_PREC_TF32X3, "fp32_ffma": CDR_PREC_FP32,
+PRECISIONS = {"fp32": CDR_PREC_F16X2, "f16x2": CDR_PREC_F16X2, "tf32x3": CDR_PREC_TF32X3, "fp32_ffma": CDR_PREC_FP32,
               "bf16": CDR_PREC_BF16}
 
 _f32p = C.POINTER(C.c_float)

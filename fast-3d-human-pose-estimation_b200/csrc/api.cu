@@ -134,7 +134,8 @@ extern "C" int cdr_stage_timing_end(int capacity, char* names, float* ms, int* c
 extern "C" int cdr_weights_create(const CdrWeightPtrs* src, int precision, void* stream,
                                   CdrWeights** out) {
   CDR_CHECK_ARG(src && out, "cdr_weights_create: null argument");
-  CDR_CHECK_ARG(precision == CDR_PREC_FP32 || precision == CDR_PREC_BF16 || precision == CDR_PREC_TF32X3,
+  CDR_CHECK_ARG(precision == CDR_PREC_FP32 || precision == CDR_PREC_BF16 || precision == CDR_PREC_TF32X3 ||
+                    precision == CDR_PREC_F16X2,
                 "cdr_weights_create: unknown precision %d", precision);
   CDR_CHECK_ARG(src->num_joints > 0 && src->num_joints <= kMaxJoints,
                 "cdr_weights_create: num_joints must be 1..%d", kMaxJoints);
@@ -192,7 +193,8 @@ extern "C" int cdr_weights_create(const CdrWeightPtrs* src, int precision, void*
     if ((rc = launch_pack_conv1x1_f32(src->final_layer, w->joints, kDecC, kDecC, w->fin_npad, w->w_fin, w->b_fin, st)))
       return fail(rc);
   } else {
-    if ((rc = tc_weights_create(*src, precision == CDR_PREC_BF16 ? 0 : 1, w->tc, st))) return fail(rc);
+    const int mode = precision == CDR_PREC_BF16 ? 0 : precision == CDR_PREC_TF32X3 ? 1 : 2;
+    if ((rc = tc_weights_create(*src, mode, w->tc, st))) return fail(rc);
   }
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {

@@ -25,11 +25,26 @@
 // shifted A tiles they share hit in L2; the packed weights (<= 16 MB) stay L2-resident.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 
 #include "ptx.cuh"
 #include "tc_api.h"
 
 namespace cdr {
+
+// ------------------------------------------------------------------------------------------
+// Storage formats of an activation / weight tensor.
+//   kFmtBF16 : one bf16 plane.
+//   kFmtTF32P: two fp32 planes hi = rn_tf32(x), lo = x - hi (common.cuh: split_tf32).
+//   kFmtF16P : two fp16 planes of X = x * s (s a power of two, per tensor for activations, per
+//              output channel for weights): hi = rn_f16(X), lo = rn_f16((X - hi) * 2^11).
+//              X = hi + lo * 2^-11 to 2^-24 relative (fp16 subnormals: 2^-36 absolute), i.e. fp32
+//              precision for every value within 2^-27 of the scaled maximum.
+enum ActFmt { kFmtBF16 = 0, kFmtTF32P = 1, kFmtF16P = 2 };
+__host__ __device__ constexpr int fmt_elem(int fmt) { return fmt == kFmtTF32P ? 4 : 2; }
+__host__ __device__ constexpr int fmt_planes(int fmt) { return fmt == kFmtBF16 ? 1 : 2; }
+constexpr float kLoScale = 2048.f;            // 2^11: the lo plane of kFmtF16P is stored times this
+constexpr int kF16TargetExp = 13;             // scaled maxima land in [2^13, 2^14): 4x below fp16 max
 
 // ------------------------------------------------------------------------------------------
 // tensor maps
@@ -45,9 +60,13 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-// dims[0] innermost (contiguous); strides in elements for dims 1..rank-1; elem_bytes 2 (bf16) or 4 (fp32)
-static int make_tmap(CUtensorMap* map, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+// dims[0] innermost (contiguous); strides in elements for dims 1..rank-1; fmt = ActFmt of the tensor
+static int make_tmap(CUtensorMap* map, const void* base, int fmt, int rank, const uint64_t* dims,
                      const uint64_t* strides_elems, const uint32_t* box) {
+  const int elem_bytes = fmt_elem(fmt);
+  const CUtensorMapDataType dtype = fmt == kFmtBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                    : fmt == kFmtTF32P ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                       : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   auto enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -61,8 +80,7 @@ static int make_tmap(CUtensorMap* map, const void* base, int elem_bytes, int ran
     estr[i] = 1;
     if (i > 0) gstr[i - 1] = strides_elems[i - 1] * (uint64_t)elem_bytes;
   }
-  CUresult r = enc(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                   (cuuint32_t)rank, const_cast<void*>(base),
+  CUresult r = enc(map, dtype, (cuuint32_t)rank, const_cast<void*>(base),
                    gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -84,10 +102,23 @@ constexpr int kSmemBudget = 200 * 1024;
 //   kKindTF32X3: fp32 accuracy on the tensor cores.  Every fp32 operand is stored as two fp32
 //                planes hi = rn_tf32(x), lo = x - hi (common.cuh: split_tf32); x*y ~= hi*hi' + hi*lo' + lo*hi' with kind::tf32 MMAs accumulating in
 //                fp32 (dropped lo*lo' term ~2^-22 relative, random sign).
-enum TcKind { kKindBF16 = 0, kKindTF32X3 = 1 };
+//   kKindF16X2 : fp32 accuracy at the full 16-bit tensor rate.  Operands in kFmtF16P; with
+//                x = (xh + xl 2^-11)/s and w = (wh + wl 2^-11)/t:  x*w*s*t = xh*wh + 2^-11 (xh*wl + xl*wh)
+//                + 2^-22 xl*wl.  The main term and the (2^11-scaled) correction terms accumulate in
+//                separate TMEM accumulators (the same two the 3xTF32 kernel uses); the epilogue
+//                adds main + 2^-11 corr and undoes s*t.  Dropped term: 2^-24 relative.  fp16
+//                products are exact in fp32, so this is strictly more accurate than 3xTF32 (2^-22)
+//                while each product costs 3 kind::f16 MMAs instead of 3 half-rate kind::tf32 MMAs,
+//                and the activations move half the bytes (2 x fp16 instead of 2 x fp32).
+//                The tensor scale s is data-dependent: the producing kernel derives it from a
+//                rigorous bound |out| <= amax(in) * max_row ||W||_1 + max|bias| (amax(in) measured by
+//                ITS producer with atomicMax), so nothing can overflow fp16 and one layer of bound
+//                looseness (~2^7) is far inside the format's 2^27 full-precision window.
+enum TcKind { kKindBF16 = 0, kKindTF32X3 = 1, kKindF16X2 = 2 };
 template <int KIND> struct KindTraits;
-template <> struct KindTraits<kKindBF16>   { static constexpr int kElem = 2, kBK = 64, kPlanes = 1; };
-template <> struct KindTraits<kKindTF32X3> { static constexpr int kElem = 4, kBK = 32, kPlanes = 2; };
+template <> struct KindTraits<kKindBF16>   { static constexpr int kElem = 2, kBK = 64, kPlanes = 1, kFmt = kFmtBF16; };
+template <> struct KindTraits<kKindTF32X3> { static constexpr int kElem = 4, kBK = 32, kPlanes = 2, kFmt = kFmtTF32P; };
+template <> struct KindTraits<kKindF16X2>  { static constexpr int kElem = 2, kBK = 64, kPlanes = 2, kFmt = kFmtF16P; };
 
 template <int BN, int KIND>
 struct TcCfg {
@@ -96,7 +127,7 @@ struct TcCfg {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
-  static constexpr int kAccBufs = KIND == kKindTF32X3 ? 4 : 2;   // see the TMEM column map in the kernel
+  static constexpr int kAccBufs = KIND != kKindBF16 ? 4 : 2;     // see the TMEM column map in the kernel
   static constexpr int kTmemCols = (kAccBufs * BN <= 32) ? 32 : (kAccBufs * BN <= 64) ? 64
                                    : (kAccBufs * BN <= 128) ? 128 : (kAccBufs * BN <= 256) ? 256 : 512;
   static_assert(kAccBufs * BN <= 512, "TMEM has 512 columns");
@@ -119,8 +150,16 @@ struct TcGemmParams {
   int n;                  // valid output channels
   const float* bias;      // (groups?, n_pad)
   int bias_group_stride;
-  void* C;                // bf16 rows, or the fp32 hi plane (tf32x3), or planar fp32 heat-maps
-  void* C_lo;             // tf32x3: the lo plane
+  void* C;                // bf16 rows, or the hi plane (kFmtTF32P / kFmtF16P), or planar fp32 heat-maps
+  void* C_lo;             // the lo plane
+  // kKindF16X2 operands / kFmtF16P outputs (device scalars live in the workspace "slots")
+  const float* wsi;       // per packed weight row: 2^-t (undoes the weight scale)
+  int wsi_group_stride;
+  const float* scale_in;  // s of the A tensor
+  const float* amax_in;   // max |x| of the A tensor (unscaled)   } bound for the output scale
+  const float* norms;     // layer {max_row ||W||_1, max |bias|}   }
+  float* amax_out;        // atomicMax target: max |out| (unscaled), pre-zeroed
+  float* scale_out;       // s chosen for the output tensor
   long long c_group_stride;
   int c_pitch, c_fill;
   int relu;
@@ -129,13 +168,20 @@ struct TcGemmParams {
 };
 
 // Epilogue for one 32-column slab of a finished row: + bias, ReLU, mask, convert, store.
-template <int KIND>
+struct EpiScale {          // per-thread epilogue constants of the scaled formats
+  float a_inv = 1.f;       // 1 / s(A tensor)
+  float s_out = 1.f;       // s(output tensor)
+  float amax = 0.f;        // running max |out| of this thread
+};
+template <int KIND, int OFMT>
 __device__ __forceinline__ void store_slab(const TcGemmParams& p, const float (&acc)[32], int n0c, int g, bool row_ok,
-                                           size_t orow, int img, int pix, int HW, const float* __restrict__ bias) {
+                                           size_t orow, int img, int pix, int HW, const float* __restrict__ bias,
+                                           const float* __restrict__ wsi, EpiScale& es) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float x = acc[j];
+    if constexpr (KIND == kKindF16X2) x *= es.a_inv * __ldg(wsi + n0c + j);
     if (bias) x += __ldg(bias + n0c + j);
     if (p.relu) x = fmaxf(x, 0.f);
     v[j] = (n0c + j < p.n) ? x : 0.f;
@@ -149,7 +195,29 @@ __device__ __forceinline__ void store_slab(const TcGemmParams& p, const float (&
     return;
   }
   const size_t off = (p.out_mode == kOutDeconv ? 0 : (size_t)g * p.c_group_stride) + orow * p.c_pitch + n0c;
-  if constexpr (KIND == kKindTF32X3) {
+  if constexpr (OFMT == kFmtF16P) {
+    __half* __restrict__ Ch = reinterpret_cast<__half*>(p.C) + off;
+    __half* __restrict__ Cl = reinterpret_cast<__half*>(p.C_lo) + off;
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      if (n0c + j8 * 8 < p.c_fill) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x0 = v[j8 * 8 + 2 * e], x1 = v[j8 * 8 + 2 * e + 1];
+          es.amax = fmaxf(es.amax, fmaxf(fabsf(x0), fabsf(x1)));
+          const float X0 = x0 * es.s_out, X1 = x1 * es.s_out;
+          const __half2 hh = __floats2half2_rn(X0, X1);
+          const float2 hf = __half22float2(hh);
+          const __half2 ll = __floats2half2_rn((X0 - hf.x) * kLoScale, (X1 - hf.y) * kLoScale);
+          h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+          l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        *reinterpret_cast<uint4*>(Ch + j8 * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(Cl + j8 * 8) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    }
+  } else if constexpr (OFMT == kFmtTF32P) {
     float* __restrict__ Ch = reinterpret_cast<float*>(p.C) + off;
     float* __restrict__ Cl = reinterpret_cast<float*>(p.C_lo) + off;
 #pragma unroll
@@ -189,7 +257,7 @@ __device__ __forceinline__ void store_slab(const TcGemmParams& p, const float (&
 // done by the epilogue warps in registers with round-to-nearest.
 constexpr int kSplitChunk = 4;
 
-template <int BN, int KIND>
+template <int BN, int KIND, int OFMT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
                    const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo,
@@ -197,7 +265,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   using Cfg = TcCfg<BN, KIND>;
   constexpr int S = Cfg::kStages;
   constexpr int kTcBK = Cfg::kBK;
-  constexpr bool kSplit = KIND == kKindTF32X3;
+  constexpr bool kSplit = KIND != kKindBF16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // stage s: [A (16 KB) | A_lo (tf32x3) | B (BN*128 B) | B_lo (tf32x3)], every piece 1024-aligned
@@ -283,10 +351,15 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      // instruction descriptor: D=f32, A/B format (1 = bf16, 2 = tf32), both K-major, N=BN, M=128
-      constexpr uint32_t fmt = kSplit ? 2u : 1u;
+      // instruction descriptor: D=f32, A/B format (kind::f16: 0 = f16, 1 = bf16; kind::tf32: 2), both K-major,
+      // N=BN, M=128
+      constexpr uint32_t fmt = KIND == kKindTF32X3 ? 2u : KIND == kKindBF16 ? 1u : 0u;
       constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
                                  ((uint32_t)(kTcBM >> 4) << 24);
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc_flag) {
+        if constexpr (KIND == kKindTF32X3) ptx::umma_tf32(d, a, b, idesc, acc_flag);
+        else ptx::umma_f16(d, a, b, idesc, acc_flag);
+      };
       // smem matrix descriptor (K-major, SWIZZLE_128B): LBO=1, SBO=1024 B, version=1, layout=2
       constexpr uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
                                    ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
@@ -323,11 +396,11 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               const uint64_t da = desc(stage_a(s, 0)), dal = desc(stage_a(s, 1));
               const uint64_t db = desc(stage_b(s, 0)), dbl = desc(stage_b(s, 1));
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {        // K step = 8 tf32 = 32 bytes
+              for (int k = 0; k < 4; ++k) {        // K step = 8 tf32 / 16 f16 = 32 bytes
                 const uint64_t o = (uint64_t)(2 * k);
-                ptx::umma_tf32(d_corr, dal + o, db + o, idesc, (kb | k) != 0);   // lo*hi  } whole-tile chain: these
-                ptx::umma_tf32(d_corr, da + o, dbl + o, idesc, 1u);              // hi*lo  } terms are 2^-11 of the main one
-                ptx::umma_tf32(d_main, da + o, db + o, idesc, (kb > kb0 || k > 0));  // hi*hi, short chain
+                mma(d_corr, dal + o, db + o, (kb | k) != 0);       // lo*hi  } whole-tile chain: these
+                mma(d_corr, da + o, dbl + o, 1u);                  // hi*lo  } terms are 2^-11 of the main one
+                mma(d_main, da + o, db + o, (kb > kb0 || k > 0));  // hi*hi, short chain
               }
               ptx::umma_commit(&empty[s]);
             }
@@ -341,6 +414,15 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // ===================================================================== epilogue (warps 2..5)
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     uint32_t tl = 0, ch = 0;
+    EpiScale es;
+    if constexpr (KIND == kKindF16X2) es.a_inv = 1.f / __ldg(p.scale_in);   // powers of two: exact
+    if constexpr (OFMT == kFmtF16P) {
+      if (p.out_mode != kOutPlanar) {
+        const float bound = __ldg(p.amax_in) * __ldg(p.norms) + __ldg(p.norms + 1);
+        if (bound > 0.f && bound < 3.0e38f) es.s_out = ldexpf(1.f, kF16TargetExp - ilogbf(bound));
+        if (blockIdx.x == 0 && threadIdx.x == 64) *p.scale_out = es.s_out;
+      }
+    }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
       const int n_tile = tile % p.n_tiles;
       const int g = (tile / p.n_tiles) % p.groups;
@@ -350,6 +432,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const bool row_ok = m < p.M;
       const int n0 = n_tile * BN;
       const float* __restrict__ bias = p.bias ? p.bias + (size_t)g * p.bias_group_stride : nullptr;
+      const float* __restrict__ wsi = KIND == kKindF16X2 ? p.wsi + (size_t)g * p.wsi_group_stride : nullptr;
       size_t orow = (size_t)(row_ok ? m : 0);
       int img = 0, pix = 0;
       if (p.out_mode == kOutDeconv) {
@@ -374,7 +457,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           float a32[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) a32[j] = __uint_as_float(r[j]);
-          store_slab<KIND>(p, a32, n0 + c, g, row_ok, orow, img, pix, HW, bias);
+          store_slab<KIND, OFMT>(p, a32, n0 + c, g, row_ok, orow, img, pix, HW, bias, wsi, es);
         }
         // all TMEM reads of this accumulator are complete (wait::ld above) -> hand it back
         ptx::tc_fence_before();
@@ -409,7 +492,10 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)((2 + acc) * BN + c), r);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum[c + j] += __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) {
+            if constexpr (KIND == kKindF16X2) sum[c + j] = fmaf(__uint_as_float(r[j]), 1.f / kLoScale, sum[c + j]);
+            else sum[c + j] += __uint_as_float(r[j]);
+          }
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -419,8 +505,16 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           float a32[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) a32[j] = sum[c + j];
-          store_slab<KIND>(p, a32, n0 + c, g, row_ok, orow, img, pix, HW, bias);
+          store_slab<KIND, OFMT>(p, a32, n0 + c, g, row_ok, orow, img, pix, HW, bias, wsi, es);
         }
+      }
+    }
+    if constexpr (OFMT == kFmtF16P) {
+      if (p.out_mode != kOutPlanar && p.amax_out) {
+        float m = es.amax;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), __float_as_uint(m));   // m >= 0
       }
     }
   }
@@ -436,25 +530,48 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
 // ------------------------------------------------------------------------------------------
 // host side: packed layers, launches, orchestration
-struct TcLayer {            // one packed conv: K-major B operand (1 plane bf16 / 2 planes fp32) + bias
+struct TcLayer {            // one packed conv: K-major B operand (1 plane bf16 / 2 planes fp32 or fp16) + bias
+  int kind = kKindBF16;
   void* w[2] = {nullptr, nullptr};
   float* bias = nullptr;
+  float* wsi = nullptr;     // kKindF16X2: per packed row 2^-t
+  float* norms = nullptr;   // {max_row ||W'||_1, max |bias'|} (layers whose output is stored in kFmtF16P)
   CUtensorMap map[2];
   int rows = 0, k = 0, k_pitch = 0, bn = 0, n_pad = 0;
 };
+// Pack modes (TcWeights.kind): 0 = every layer bf16, 1 = every layer 3xTF32,
+// 2 = "hybrid" fp32: fusion block 3xTF32 (its activations carry P's 1e5 dynamic range between
+//     the two FTLs, and it is 5 % of the FLOPs), decoder f16x2.
+enum TcMode { kModeBF16 = 0, kModeTF32X3 = 1, kModeHybrid = 2 };
+static inline int mode_fusion_kind(int mode) { return mode == kModeBF16 ? kKindBF16 : kKindTF32X3; }
+static inline int mode_decoder_kind(int mode) {
+  return mode == kModeBF16 ? kKindBF16 : mode == kModeTF32X3 ? kKindTF32X3 : kKindF16X2;
+}
+static inline int kind_fmt(int kind) {
+  return kind == kKindBF16 ? kFmtBF16 : kind == kKindTF32X3 ? kFmtTF32P : kFmtF16P;
+}
 struct TcPack {
-  int kind = kKindBF16;
+  int mode = kModeBF16;
   TcLayer cf1, cf2a, cf2b, out, dc[3], fin;
 };
-struct Act {                // an activation buffer: 1 plane (bf16) or hi/lo planes (fp32)
+struct Act {                // an activation buffer: 1 plane (bf16) or hi/lo planes
   void* p[2] = {nullptr, nullptr};
+  int fmt = kFmtBF16;
 };
-static inline Act act_offset(const Act& a, size_t elems, int elem_bytes) {
+static inline Act act_offset(const Act& a, size_t elems) {
   Act r;
+  r.fmt = a.fmt;
+  const int elem_bytes = fmt_elem(a.fmt);
   r.p[0] = a.p[0] ? (uint8_t*)a.p[0] + elems * elem_bytes : nullptr;
   r.p[1] = a.p[1] ? (uint8_t*)a.p[1] + elems * elem_bytes : nullptr;
   return r;
 }
+
+// Device scalars of the scaled fp16 tensors, one pair per tensor, in the workspace.
+struct ScaleSlot {
+  float* amax = nullptr;    // max |x| (atomicMax by the producer; zeroed at the start of a forward)
+  float* scale = nullptr;   // s
+};
 
 struct TcLaunch {
   Act A;                    // activations
@@ -467,16 +584,19 @@ struct TcLaunch {
   Act C;                    // output planes (or planar fp32 heat-maps in C.p[0])
   long long c_group_stride;
   int c_pitch, c_fill, relu, out_mode;
+  ScaleSlot in_slot, out_slot;   // kFmtF16P tensors
+  const float* amax_in;          // overrides in_slot.amax (input stored in another format)
 };
 
-template <int BN, int KIND>
+template <int BN, int KIND, int OFMT>
 static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
   using Cfg = TcCfg<BN, KIND>;
   constexpr int kElem = KindTraits<KIND>::kElem;
   constexpr int kBK = Cfg::kBK;
+  constexpr int kAFmt = KindTraits<KIND>::kFmt;
   static bool attr_set = false;
   if (!attr_set) {
-    CDR_CUDA(cudaFuncSetAttribute(tap_gemm_tc_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CDR_CUDA(cudaFuncSetAttribute(tap_gemm_tc_kernel<BN, KIND, OFMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -495,13 +615,25 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
   p.C = l.C.p[0]; p.C_lo = l.C.p[1];
   p.c_group_stride = l.c_group_stride; p.c_pitch = l.c_pitch; p.c_fill = l.c_fill;
   p.relu = l.relu; p.out_mode = l.out_mode;
+  p.wsi = l.layer->wsi; p.wsi_group_stride = l.b_group_rows;
+  p.scale_in = l.in_slot.scale;
+  p.amax_in = l.amax_in ? l.amax_in : l.in_slot.amax;
+  p.norms = l.layer->norms;
+  p.amax_out = l.out_slot.amax; p.scale_out = l.out_slot.scale;
   const int m_tiles = ceil_div(p.M, kTcBM);
   p.num_tiles = m_tiles * p.groups * p.n_tiles;
   CDR_CHECK_ARG(l.layer->bn == BN && l.layer->n_pad % BN == 0, "tap_gemm_tc: layer packed for BN=%d, launched with %d",
                 l.layer->bn, BN);
+  CDR_CHECK_ARG(l.A.fmt == kAFmt, "tap_gemm_tc: A stored as format %d, kernel kind %d wants %d", l.A.fmt, KIND, kAFmt);
   CDR_CHECK_ARG((l.a_pitch * kElem) % 16 == 0 && ((uintptr_t)l.A.p[0] & 15) == 0, "tap_gemm_tc: A pitch/alignment");
-  CDR_CHECK_ARG(l.out_mode == kOutPlanar || ((l.c_pitch * kElem) % 16 == 0 && (l.c_fill * kElem) % 16 == 0),
-                "tap_gemm_tc: output pitch / fill must be 16-byte multiples");
+  if (l.out_mode != kOutPlanar) {
+    CDR_CHECK_ARG(l.C.fmt == OFMT, "tap_gemm_tc: output format %d, kernel writes %d", l.C.fmt, OFMT);
+    CDR_CHECK_ARG((l.c_pitch * fmt_elem(OFMT)) % 16 == 0 && (l.c_fill * fmt_elem(OFMT)) % 16 == 0,
+                  "tap_gemm_tc: output pitch / fill must be 16-byte multiples");
+    if (OFMT == kFmtF16P)
+      CDR_CHECK_ARG(p.amax_in && p.norms && p.scale_out, "tap_gemm_tc: fp16-plane output needs its scale slots");
+  }
+  if (KIND == kKindF16X2) CDR_CHECK_ARG(p.wsi && p.scale_in, "tap_gemm_tc: f16x2 operands need their scales");
 
   CUtensorMap tmap_a[2];
   for (int pl = 0; pl < KindTraits<KIND>::kPlanes; ++pl) {
@@ -515,33 +647,39 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
       const uint64_t dims[4] = {(uint64_t)l.cin, (uint64_t)l.W, (uint64_t)l.H, (uint64_t)l.n_img};
       const uint64_t strides[3] = {(uint64_t)l.a_pitch, (uint64_t)l.a_pitch * l.W, (uint64_t)l.a_pitch * HW};
       const uint32_t box[4] = {(uint32_t)kBK, (uint32_t)l.W, (uint32_t)rows, (uint32_t)imgs};
-      if (int rc = make_tmap(&tmap_a[pl], l.A.p[pl], kElem, 4, dims, strides, box)) return rc;
+      if (int rc = make_tmap(&tmap_a[pl], l.A.p[pl], kAFmt, 4, dims, strides, box)) return rc;
     } else {
       const uint64_t dims[2] = {(uint64_t)l.cin, (uint64_t)l.a_rows_total};
       const uint64_t strides[1] = {(uint64_t)l.a_pitch};
       const uint32_t box[2] = {(uint32_t)kBK, (uint32_t)kTcBM};
-      if (int rc = make_tmap(&tmap_a[pl], l.A.p[pl], kElem, 2, dims, strides, box)) return rc;
+      if (int rc = make_tmap(&tmap_a[pl], l.A.p[pl], kAFmt, 2, dims, strides, box)) return rc;
     }
   }
   if (KindTraits<KIND>::kPlanes == 1) tmap_a[1] = tmap_a[0];
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  tap_gemm_tc_kernel<BN, KIND><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(
+  tap_gemm_tc_kernel<BN, KIND, OFMT><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(
       tmap_a[0], tmap_a[1], l.layer->map[0], l.layer->map[KindTraits<KIND>::kPlanes - 1], p);
   CDR_LAUNCH_OK("tap_gemm_tc_kernel");
   return CDR_OK;
 }
 
-static int launch_tc(int kind, const TcLaunch& l, cudaStream_t st) {
-  const int bn = l.layer->bn;
-  if (kind == kKindBF16) {
-    if (bn == 256) return launch_tc_t<256, kKindBF16>(l, st);
-    if (bn == 128) return launch_tc_t<128, kKindBF16>(l, st);
-    if (bn == 32) return launch_tc_t<32, kKindBF16>(l, st);
-  } else {
-    if (bn == 128) return launch_tc_t<128, kKindTF32X3>(l, st);
-    if (bn == 32) return launch_tc_t<32, kKindTF32X3>(l, st);
+static int launch_tc(const TcLaunch& l, cudaStream_t st) {
+  const int bn = l.layer->bn, kind = l.layer->kind;
+  const int ofmt = l.out_mode == kOutPlanar ? kind_fmt(kind) : l.C.fmt;
+  if (kind == kKindBF16 && ofmt == kFmtBF16) {
+    if (bn == 256) return launch_tc_t<256, kKindBF16, kFmtBF16>(l, st);
+    if (bn == 128) return launch_tc_t<128, kKindBF16, kFmtBF16>(l, st);
+    if (bn == 32) return launch_tc_t<32, kKindBF16, kFmtBF16>(l, st);
+  } else if (kind == kKindTF32X3 && ofmt == kFmtTF32P) {
+    if (bn == 128) return launch_tc_t<128, kKindTF32X3, kFmtTF32P>(l, st);
+    if (bn == 32) return launch_tc_t<32, kKindTF32X3, kFmtTF32P>(l, st);
+  } else if (kind == kKindTF32X3 && ofmt == kFmtF16P) {
+    if (bn == 128) return launch_tc_t<128, kKindTF32X3, kFmtF16P>(l, st);
+  } else if (kind == kKindF16X2 && ofmt == kFmtF16P) {
+    if (bn == 128) return launch_tc_t<128, kKindF16X2, kFmtF16P>(l, st);
+    if (bn == 32) return launch_tc_t<32, kKindF16X2, kFmtF16P>(l, st);
   }
-  set_error("tap_gemm_tc: no kernel for kind %d BN %d", kind, bn);
+  set_error("tap_gemm_tc: no kernel for kind %d BN %d output format %d", kind, bn, ofmt);
   return CDR_ERR_UNSUPPORTED;
 }
 
@@ -555,6 +693,19 @@ __device__ __forceinline__ float tc_folded_bias(const CdrConvBn& s, int co) {
   const double b = s.bias ? (double)s.bias[co] : 0.0;
   if (!s.bn_weight) return (float)b;
   return (float)((b - (double)s.bn_mean[co]) * tc_bn_scale(s, co) + (double)s.bn_bias[co]);
+}
+// folded weight of a 1x1 conv (Cout,Cin) at packed position (n, k)
+__device__ __forceinline__ float conv1x1_weight(const CdrConvBn& s, int cout, int cin, int n, int k) {
+  if (n >= cout || k >= cin) return 0.f;
+  return (float)((double)s.weight[(size_t)n * cin + k] * tc_bn_scale(s, n));
+}
+// folded weight of a transposed conv (Cin,Cout,4,4) at packed position (phase, n, tap*Cin + ci)
+__device__ __forceinline__ float deconv_weight(const CdrConvBn& s, int cin, int cout, int phase, int n, int kk) {
+  if (n >= cout) return 0.f;
+  const int tap = kk / cin, ci = kk - tap * cin;
+  const int py = phase >> 1, px = phase & 1, ty = tap >> 1, tx = tap & 1;
+  const int ky = 1 - py + 2 * ty, kx = 1 - px + 2 * tx;
+  return (float)((double)s.weight[(((size_t)ci * cout + n) * 4 + ky) * 4 + kx] * tc_bn_scale(s, n));
 }
 template <bool kSplit>
 __device__ __forceinline__ void store_weight(void* w0, void* w1, long long idx, float v) {
@@ -575,9 +726,7 @@ __global__ void pack_conv1x1_tc_kernel(CdrConvBn s, int cout, int cin, int k_pit
   if (idx < n_pad) bias_out[idx] = idx < cout ? tc_folded_bias(s, (int)idx) : 0.f;
   if (idx >= (long long)n_pad * k_pitch) return;
   const int n = (int)(idx / k_pitch), k = (int)(idx % k_pitch);
-  float v = 0.f;
-  if (n < cout && k < cin) v = (float)((double)s.weight[(size_t)n * cin + k] * tc_bn_scale(s, n));
-  store_weight<kSplit>(w0, w1, idx, v);
+  store_weight<kSplit>(w0, w1, idx, conv1x1_weight(s, cout, cin, n, k));
 }
 // (Cin,Cout,4,4) -> [phase][n_pad][tap*Cin + ci]
 template <bool kSplit>
@@ -590,24 +739,83 @@ __global__ void pack_deconv_tc_kernel(CdrConvBn s, int cin, int cout, int n_pad,
   const int kk = (int)(idx % K);
   long long r = idx / K;
   const int n = (int)(r % n_pad), phase = (int)(r / n_pad);
-  const int tap = kk / cin, ci = kk - tap * cin;
-  const int py = phase >> 1, px = phase & 1, ty = tap >> 1, tx = tap & 1;
-  const int ky = 1 - py + 2 * ty, kx = 1 - px + 2 * tx;
-  float v = 0.f;
-  if (n < cout) v = (float)((double)s.weight[(((size_t)ci * cout + n) * 4 + ky) * 4 + kx] * tc_bn_scale(s, n));
-  store_weight<kSplit>(w0, w1, idx, v);
+  store_weight<kSplit>(w0, w1, idx, deconv_weight(s, cin, cout, phase, n, kk));
+}
+
+// One block per packed weight row: max |w| and ||w||_1 of the row (block reduction), then
+//   kWrite: the row scaled by 2^t (max lands in [2^13, 2^14)) as fp16 hi/lo planes, wsi[row] = 2^-t;
+//   always: atomicMax of the row's L1 norm and |bias| into norms[0..1] (the output-scale bound).
+template <bool kDeconv, bool kWrite>
+__global__ void __launch_bounds__(256)
+pack_rows_f16_kernel(CdrConvBn s, int cout, int cin, int k_pitch, int n_pad, __half* __restrict__ w_hi,
+                     __half* __restrict__ w_lo, float* __restrict__ wsi, float* __restrict__ bias_out,
+                     float* __restrict__ norms) {
+  __shared__ float red_max[8], red_sum[8];
+  const int row = blockIdx.x;
+  const int n = row % n_pad, phase = row / n_pad;
+  auto val = [&](int kk) -> float {
+    return kDeconv ? deconv_weight(s, cin, cout, phase, n, kk) : conv1x1_weight(s, cout, cin, n, kk);
+  };
+  float mx = 0.f, l1 = 0.f;
+  for (int kk = threadIdx.x; kk < k_pitch; kk += blockDim.x) {
+    const float a = fabsf(val(kk));
+    mx = fmaxf(mx, a);
+    l1 += a;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red_max[threadIdx.x >> 5] = mx;
+    red_sum[threadIdx.x >> 5] = l1;
+  }
+  __syncthreads();
+  mx = 0.f;
+  l1 = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+    mx = fmaxf(mx, red_max[i]);
+    l1 += red_sum[i];
+  }
+  const int t = mx > 0.f ? kF16TargetExp - ilogbf(mx) : 0;
+  if (threadIdx.x == 0) {
+    const float b = n < cout ? tc_folded_bias(s, n) : 0.f;
+    if (kWrite) {
+      wsi[row] = ldexpf(1.f, -t);
+      if (phase == 0) bias_out[n] = b;
+    }
+    if (norms) {
+      atomicMax(reinterpret_cast<unsigned int*>(norms), __float_as_uint(l1 * 1.001f));   // non-negative floats
+      atomicMax(reinterpret_cast<unsigned int*>(norms + 1), __float_as_uint(fabsf(b)));
+    }
+  }
+  if (!kWrite) return;
+  const float up = ldexpf(1.f, t);
+  for (int kk = threadIdx.x; kk < k_pitch; kk += blockDim.x) {
+    const float X = val(kk) * up;
+    const __half h = __float2half_rn(X);
+    w_hi[(size_t)row * k_pitch + kk] = h;
+    w_lo[(size_t)row * k_pitch + kk] = __float2half_rn((X - __half2float(h)) * kLoScale);
+  }
 }
 
 // plane(s) -> fp32 (parity taps)
-__global__ void act_to_f32_kernel(const void* __restrict__ p0, const void* __restrict__ p1, int split,
-                                  float* __restrict__ out, long long rows, int in_pitch, int cols) {
+__global__ void act_to_f32_kernel(const void* __restrict__ p0, const void* __restrict__ p1, int fmt,
+                                  const float* __restrict__ scale, float* __restrict__ out, long long rows,
+                                  int in_pitch, int cols) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cols) return;
   const long long r = idx / cols;
   const int c = (int)(idx - r * cols);
   const long long i = r * in_pitch + c;
-  out[idx] = split ? reinterpret_cast<const float*>(p0)[i] + reinterpret_cast<const float*>(p1)[i]
-                   : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p0)[i]);
+  if (fmt == kFmtTF32P)
+    out[idx] = reinterpret_cast<const float*>(p0)[i] + reinterpret_cast<const float*>(p1)[i];
+  else if (fmt == kFmtF16P)
+    out[idx] = (__half2float(reinterpret_cast<const __half*>(p0)[i]) +
+                __half2float(reinterpret_cast<const __half*>(p1)[i]) * (1.f / kLoScale)) / *scale;
+  else
+    out[idx] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p0)[i]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -624,66 +832,83 @@ struct Bump1K {
   }
 };
 
-static void plan_layer(TcLayer& L, Bump1K& b, int kind, int rows, int k, int k_pitch, int bn, int n_pad, int bias_n) {
-  const int elem = kind == kKindBF16 ? 2 : 4;
+static void plan_layer(TcLayer& L, Bump1K& b, int kind, int rows, int k, int k_pitch, int bn, int n_pad, int bias_n,
+                       bool want_norms) {
+  const int elem = (kind == kKindTF32X3 ? 4 : 2);
+  L.kind = kind;
   L.rows = rows; L.k = k; L.k_pitch = k_pitch; L.bn = bn; L.n_pad = n_pad;
   L.w[0] = b.take((size_t)rows * k_pitch * elem);
-  L.w[1] = kind == kKindTF32X3 ? b.take((size_t)rows * k_pitch * elem) : nullptr;
+  L.w[1] = kind != kKindBF16 ? b.take((size_t)rows * k_pitch * elem) : nullptr;
   L.bias = (float*)b.take((size_t)bias_n * sizeof(float));
+  L.wsi = kind == kKindF16X2 ? (float*)b.take((size_t)rows * sizeof(float)) : nullptr;
+  L.norms = want_norms ? (float*)b.take(2 * sizeof(float)) : nullptr;
 }
 
 static size_t plan_tc_weights(TcPack& pk, const TcWeights& w, void* base) {
   Bump1K b(base);
-  const int kind = pk.kind;
-  const int bn_wide = kind == kKindBF16 ? 256 : 128;
+  const int fk = mode_fusion_kind(pk.mode), dk = mode_decoder_kind(pk.mode);
+  const int bn_f = fk == kKindBF16 ? 256 : 128, bn_d = dk == kKindBF16 ? 256 : 128;
+  const bool scaled = dk == kKindF16X2;          // outputs feeding the decoder are stored in kFmtF16P
   if (w.has_fusion) {
-    plan_layer(pk.cf1, b, kind, 384, kFeatC, kFeatC, 128, 384, 384);
-    plan_layer(pk.cf2a, b, kind, 512, 2 * kHid2, 2 * kHid2, 128, 512, 512);
-    plan_layer(pk.cf2b, b, kind, 512, kHid2, kHid2, 128, 512, 512);
-    plan_layer(pk.out, b, kind, 2 * kFeatC, kHid1, kHid1Pad, bn_wide, kFeatC, 2 * kFeatC);
+    plan_layer(pk.cf1, b, fk, 384, kFeatC, kFeatC, 128, 384, 384, false);
+    plan_layer(pk.cf2a, b, fk, 512, 2 * kHid2, 2 * kHid2, 128, 512, 512, false);
+    plan_layer(pk.cf2b, b, fk, 512, kHid2, kHid2, 128, 512, 512, false);
+    plan_layer(pk.out, b, fk, 2 * kFeatC, kHid1, kHid1Pad, bn_f, kFeatC, 2 * kFeatC, scaled);
   }
   for (int i = 0; i < 3; ++i)
-    plan_layer(pk.dc[i], b, kind, 4 * kDecC, 4 * kTcDcCin[i], 4 * kTcDcCin[i], bn_wide, kDecC, kDecC);
-  plan_layer(pk.fin, b, kind, w.fin_npad, kDecC, kDecC, 32, w.fin_npad, w.fin_npad);
+    plan_layer(pk.dc[i], b, dk, 4 * kDecC, 4 * kTcDcCin[i], 4 * kTcDcCin[i], bn_d, kDecC, kDecC, scaled);
+  plan_layer(pk.fin, b, dk, w.fin_npad, kDecC, kDecC, 32, w.fin_npad, w.fin_npad, false);
   return b.off;
 }
 
-static int layer_maps(TcLayer& L, int kind) {
-  const int elem = kind == kKindBF16 ? 2 : 4;
-  const int bk = kind == kKindBF16 ? 64 : 32;
-  for (int pl = 0; pl < (kind == kKindTF32X3 ? 2 : 1); ++pl) {
+static int layer_maps(TcLayer& L) {
+  const int fmt = kind_fmt(L.kind);
+  const int bk = L.kind == kKindTF32X3 ? 32 : 64;
+  for (int pl = 0; pl < fmt_planes(fmt); ++pl) {
     const uint64_t dims[2] = {(uint64_t)L.k, (uint64_t)L.rows};
     const uint64_t strides[1] = {(uint64_t)L.k_pitch};
     const uint32_t box[2] = {(uint32_t)bk, (uint32_t)L.bn};
-    if (int rc = make_tmap(&L.map[pl], L.w[pl], elem, 2, dims, strides, box)) return rc;
+    if (int rc = make_tmap(&L.map[pl], L.w[pl], fmt, 2, dims, strides, box)) return rc;
   }
   return CDR_OK;
 }
 
-int tc_weights_create(const CdrWeightPtrs& src, int kind, TcWeights& w, cudaStream_t st) {
+int tc_weights_create(const CdrWeightPtrs& src, int mode, TcWeights& w, cudaStream_t st) {
   w.joints = src.num_joints;
   w.has_fusion = src.has_fusion;
   w.fin_npad = round_up(src.num_joints, 32);
-  w.kind = kind;
+  w.kind = mode;
   TcPack* pk = new TcPack();
-  pk->kind = kind;
+  pk->mode = mode;
   w.impl = pk;
   const size_t bytes = plan_tc_weights(*pk, w, nullptr);
   CDR_CUDA(cudaMalloc(&w.pool, bytes));
+  CDR_CUDA(cudaMemsetAsync(w.pool, 0, bytes, st));      // norms start at 0 for the atomicMax
   plan_tc_weights(*pk, w, w.pool);
-  const bool split = kind == kKindTF32X3;
+  // 1x1 conv (cout, cin) into rows [row_off, row_off + rows) of layer L
   auto pack1 = [&](const CdrConvBn& s, int cout, int cin, TcLayer& L, size_t row_off, size_t bias_off) -> int {
     const int rows = cout <= L.n_pad ? L.n_pad : cout;   // rows packed by this call
     const long long total = (long long)rows * L.k_pitch;
-    const int elem = split ? 4 : 2;
+    const int elem = (L.kind == kKindTF32X3 ? 4 : 2);
     void* w0 = (uint8_t*)L.w[0] + row_off * L.k_pitch * elem;
-    void* w1 = split ? (uint8_t*)L.w[1] + row_off * L.k_pitch * elem : nullptr;
+    void* w1 = L.w[1] ? (uint8_t*)L.w[1] + row_off * L.k_pitch * elem : nullptr;
     const unsigned grid = (unsigned)ceil_div<long long>(total, 256);
-    if (split)
+    if (L.kind == kKindF16X2) {
+      pack_rows_f16_kernel<false, true><<<rows, 256, 0, st>>>(s, cout, cin, L.k_pitch, rows, (__half*)w0, (__half*)w1,
+                                                              L.wsi + row_off, L.bias + bias_off, L.norms);
+      CDR_LAUNCH_OK("pack_rows_f16_kernel");
+      return CDR_OK;
+    }
+    if (L.kind == kKindTF32X3)
       pack_conv1x1_tc_kernel<true><<<grid, 256, 0, st>>>(s, cout, cin, L.k_pitch, rows, w0, w1, L.bias + bias_off);
     else
       pack_conv1x1_tc_kernel<false><<<grid, 256, 0, st>>>(s, cout, cin, L.k_pitch, rows, w0, w1, L.bias + bias_off);
     CDR_LAUNCH_OK("pack_conv1x1_tc_kernel");
+    if (L.norms) {   // only the norms (the layer itself is not fp16-scaled, its output is)
+      pack_rows_f16_kernel<false, false><<<rows, 256, 0, st>>>(s, cout, cin, L.k_pitch, rows, nullptr, nullptr, nullptr,
+                                                               nullptr, L.norms);
+      CDR_LAUNCH_OK("pack_rows_f16_kernel");
+    }
     return CDR_OK;
   };
   int rc;
@@ -693,23 +918,30 @@ int tc_weights_create(const CdrWeightPtrs& src, int kind, TcWeights& w, cudaStre
     if ((rc = pack1(src.cf_conv2b, kHid2, kHid2, pk->cf2b, 0, 0))) return rc;
     for (int v = 0; v < 2; ++v)
       if ((rc = pack1(src.cf_out[v], kFeatC, kHid1, pk->out, (size_t)v * kFeatC, (size_t)v * kFeatC))) return rc;
-    if ((rc = layer_maps(pk->cf1, kind)) || (rc = layer_maps(pk->cf2a, kind)) || (rc = layer_maps(pk->cf2b, kind)) ||
-        (rc = layer_maps(pk->out, kind)))
+    if ((rc = layer_maps(pk->cf1)) || (rc = layer_maps(pk->cf2a)) || (rc = layer_maps(pk->cf2b)) ||
+        (rc = layer_maps(pk->out)))
       return rc;
   }
   for (int i = 0; i < 3; ++i) {
-    const long long total = 4LL * kDecC * 4 * kTcDcCin[i];
-    const unsigned grid = (unsigned)ceil_div<long long>(total, 256);
     TcLayer& L = pk->dc[i];
-    if (split)
-      pack_deconv_tc_kernel<true><<<grid, 256, 0, st>>>(src.deconv[i], kTcDcCin[i], kDecC, kDecC, L.w[0], L.w[1], L.bias);
-    else
-      pack_deconv_tc_kernel<false><<<grid, 256, 0, st>>>(src.deconv[i], kTcDcCin[i], kDecC, kDecC, L.w[0], L.w[1], L.bias);
-    CDR_LAUNCH_OK("pack_deconv_tc_kernel");
-    if ((rc = layer_maps(L, kind))) return rc;
+    const int K = 4 * kTcDcCin[i];
+    if (L.kind == kKindF16X2) {
+      pack_rows_f16_kernel<true, true><<<4 * kDecC, 256, 0, st>>>(src.deconv[i], kDecC, kTcDcCin[i], K, kDecC,
+                                                                  (__half*)L.w[0], (__half*)L.w[1], L.wsi, L.bias, L.norms);
+      CDR_LAUNCH_OK("pack_rows_f16_kernel");
+    } else {
+      const long long total = 4LL * kDecC * K;
+      const unsigned grid = (unsigned)ceil_div<long long>(total, 256);
+      if (L.kind == kKindTF32X3)
+        pack_deconv_tc_kernel<true><<<grid, 256, 0, st>>>(src.deconv[i], kTcDcCin[i], kDecC, kDecC, L.w[0], L.w[1], L.bias);
+      else
+        pack_deconv_tc_kernel<false><<<grid, 256, 0, st>>>(src.deconv[i], kTcDcCin[i], kDecC, kDecC, L.w[0], L.w[1], L.bias);
+      CDR_LAUNCH_OK("pack_deconv_tc_kernel");
+    }
+    if ((rc = layer_maps(L))) return rc;
   }
   if ((rc = pack1(src.final_layer, w.joints, kDecC, pk->fin, 0, 0))) return rc;
-  return layer_maps(pk->fin, kind);
+  return layer_maps(pk->fin);
 }
 
 void tc_weights_destroy(TcWeights& w) {
@@ -720,49 +952,62 @@ void tc_weights_destroy(TcWeights& w) {
 }
 
 // ------------------------------------------------------------------------------------------
+constexpr int kNumSlots = 8;       // ScaleSlot pairs: 0 g (amax only), 1 x1, 2 d1, 3 d2, 4 d3
 struct TcHeadWs {
   float* pinv;
+  float* slots;
   Act x0, y1, z, f1, f2, g, x1, d1, d2, d3;
   float* hm;
   size_t bytes;
 };
-static Act take_act(Bump1K& b, size_t elems, int kind) {
+static ScaleSlot slot(float* slots, int i) {
+  ScaleSlot s;
+  s.amax = slots + 2 * i;
+  s.scale = slots + 2 * i + 1;
+  return s;
+}
+static Act take_act(Bump1K& b, size_t elems, int fmt) {
   Act a;
-  const int elem = kind == kKindBF16 ? 2 : 4;
-  a.p[0] = b.take(elems * elem);
-  a.p[1] = kind == kKindTF32X3 ? b.take(elems * elem) : nullptr;
+  a.fmt = fmt;
+  a.p[0] = b.take(elems * fmt_elem(fmt));
+  a.p[1] = fmt_planes(fmt) == 2 ? b.take(elems * fmt_elem(fmt)) : nullptr;
   return a;
 }
-static TcHeadWs plan_tc_head(void* base, int B, int J, int kind) {
+static TcHeadWs plan_tc_head(void* base, int B, int J, int mode) {
   Bump1K b(base);
   const size_t N = 2 * (size_t)B;
+  const int ff = kind_fmt(mode_fusion_kind(mode)), df = kind_fmt(mode_decoder_kind(mode));
   TcHeadWs w;
   w.pinv = (float*)b.take(N * 12 * sizeof(float));
-  w.x0 = take_act(b, N * kFeatHW * kFeatC, kind);
-  w.y1 = take_act(b, N * kFeatHW * kHid1Pad, kind);
-  w.z = take_act(b, (size_t)B * kFeatHW * 2 * kHid2, kind);
-  w.f1 = take_act(b, (size_t)B * kFeatHW * kHid2, kind);
-  w.f2 = take_act(b, (size_t)B * kFeatHW * kHid2, kind);
-  w.g = take_act(b, N * kFeatHW * kHid1Pad, kind);
-  w.x1 = take_act(b, N * kFeatHW * kFeatC, kind);
-  w.d1 = take_act(b, N * 256 * kDecC, kind);
-  w.d2 = take_act(b, N * 1024 * kDecC, kind);
-  w.d3 = take_act(b, N * 4096 * kDecC, kind);
+  w.slots = (float*)b.take(2 * kNumSlots * sizeof(float));
+  w.x0 = take_act(b, N * kFeatHW * kFeatC, ff);
+  w.y1 = take_act(b, N * kFeatHW * kHid1Pad, ff);
+  w.z = take_act(b, (size_t)B * kFeatHW * 2 * kHid2, ff);
+  w.f1 = take_act(b, (size_t)B * kFeatHW * kHid2, ff);
+  w.f2 = take_act(b, (size_t)B * kFeatHW * kHid2, ff);
+  w.g = take_act(b, N * kFeatHW * kHid1Pad, ff);
+  w.x1 = take_act(b, N * kFeatHW * kFeatC, df);
+  w.d1 = take_act(b, N * 256 * kDecC, df);
+  w.d2 = take_act(b, N * 1024 * kDecC, df);
+  w.d3 = take_act(b, N * 4096 * kDecC, df);
   w.hm = (float*)b.take(N * J * 4096 * sizeof(float));
   w.bytes = b.off;
   return w;
 }
 struct TcDecWs {
+  float* slots;
   Act x1, d1, d2, d3;
   size_t bytes;
 };
-static TcDecWs plan_tc_dec(void* base, int N, int kind) {
+static TcDecWs plan_tc_dec(void* base, int N, int mode) {
   Bump1K b(base);
+  const int df = kind_fmt(mode_decoder_kind(mode));
   TcDecWs w;
-  w.x1 = take_act(b, (size_t)N * kFeatHW * kFeatC, kind);
-  w.d1 = take_act(b, (size_t)N * 256 * kDecC, kind);
-  w.d2 = take_act(b, (size_t)N * 1024 * kDecC, kind);
-  w.d3 = take_act(b, (size_t)N * 4096 * kDecC, kind);
+  w.slots = (float*)b.take(2 * kNumSlots * sizeof(float));
+  w.x1 = take_act(b, (size_t)N * kFeatHW * kFeatC, df);
+  w.d1 = take_act(b, (size_t)N * 256 * kDecC, df);
+  w.d2 = take_act(b, (size_t)N * 1024 * kDecC, df);
+  w.d3 = take_act(b, (size_t)N * 4096 * kDecC, df);
   w.bytes = b.off;
   return w;
 }
@@ -776,22 +1021,28 @@ int tc_decoder_workspace_bytes(const TcWeights& w, int n_images, size_t* bytes) 
   return CDR_OK;
 }
 
-static int to_rows(const float* feat, int n_img, const Act& out, int kind, cudaStream_t st) {
-  if (kind == kKindBF16)
+// NCHW fp32 latents -> pixel-major rows in the format of `out`.  kFmtF16P: the tensor scale comes
+// from the exact amax of the input (one extra pass over 0.5 MB / image).
+static int to_rows(const float* feat, int n_img, const Act& out, ScaleSlot sl, cudaStream_t st) {
+  if (out.fmt == kFmtBF16)
     return launch_nchw_to_rows_bf16(feat, n_img, kFeatC, kFeatHW, (__nv_bfloat16*)out.p[0], kFeatC, st);
-  return launch_nchw_to_rows_split(feat, n_img, kFeatC, kFeatHW, (float*)out.p[0], (float*)out.p[1], kFeatC, st);
+  if (out.fmt == kFmtTF32P)
+    return launch_nchw_to_rows_split(feat, n_img, kFeatC, kFeatHW, (float*)out.p[0], (float*)out.p[1], kFeatC, st);
+  if (int rc = launch_amax_f32(feat, (long long)n_img * kFeatC * kFeatHW, sl.amax, st)) return rc;
+  return launch_nchw_to_rows_f16p(feat, n_img, kFeatC, kFeatHW, out.p[0], out.p[1], kFeatC, sl.amax, sl.scale, st);
 }
 static int ftl_act(const Act& in, int in_pitch, const float* mats, int rows, int cols, int n, const Act& out,
-                   int out_pitch, int out_fill, int kind, cudaStream_t st) {
-  if (kind == kKindBF16)
+                   int out_pitch, int out_fill, float* amax_out, cudaStream_t st) {
+  if (in.fmt == kFmtBF16)
     return launch_ftl<__nv_bfloat16>((const __nv_bfloat16*)in.p[0], in_pitch, mats, rows, cols, kFtlBlk, n, kFeatHW,
                                      (__nv_bfloat16*)out.p[0], out_pitch, out_fill, st);
   return launch_ftl_split((const float*)in.p[0], (const float*)in.p[1], in_pitch, mats, rows, cols, kFtlBlk, n,
-                          kFeatHW, (float*)out.p[0], (float*)out.p[1], out_pitch, out_fill, st);
+                          kFeatHW, (float*)out.p[0], (float*)out.p[1], out_pitch, out_fill, amax_out, st);
 }
 
+// slots: x1 -> 1, d1 -> 2, d2 -> 3, d3 -> 4
 static int tc_decoder(const TcWeights& w, const Act& x1, int N, const Act& d1, const Act& d2, const Act& d3,
-                      float* heat, cudaStream_t st) {
+                      float* slots, float* heat, cudaStream_t st) {
   const TcPack* pk = (const TcPack*)w.impl;
   static const char* const kDcName[3] = {"deconv1", "deconv2", "deconv3"};
   Act in = x1;
@@ -804,7 +1055,8 @@ static int tc_decoder(const TcWeights& w, const Act& x1, int N, const Act& d1, c
     l.deconv = 1; l.groups = 4; l.layer = &pk->dc[i]; l.b_group_rows = kDecC; l.n = kDecC;
     l.bias_group_stride = 0;
     l.C = outs[i]; l.c_pitch = kDecC; l.c_fill = kDecC; l.relu = 1; l.out_mode = kOutDeconv;
-    if (int rc = launch_tc(w.kind, l, st)) return rc;
+    l.in_slot = slot(slots, 1 + i); l.out_slot = slot(slots, 2 + i);
+    if (int rc = launch_tc(l, st)) return rc;
     in = outs[i];
     side *= 2;
   }
@@ -814,15 +1066,17 @@ static int tc_decoder(const TcWeights& w, const Act& x1, int N, const Act& d1, c
   l.a_rows_total = (long long)N * 4096;
   l.layer = &pk->fin; l.n = w.joints;
   l.C.p[0] = heat; l.relu = 0; l.out_mode = kOutPlanar;
-  const int rc = launch_tc(w.kind, l, st);
+  l.in_slot = slot(slots, 4);
+  const int rc = launch_tc(l, st);
   set_stage(nullptr);
   return rc;
 }
 
-static int tap_to_f32(float* dst, const Act& src, int kind, long long rows, int pitch, int cols, cudaStream_t st) {
+static int tap_to_f32(float* dst, const Act& src, const float* scale, long long rows, int pitch, int cols,
+                      cudaStream_t st) {
   if (!dst) return CDR_OK;
   act_to_f32_kernel<<<(unsigned)ceil_div<long long>(rows * cols, 256), 256, 0, st>>>(
-      src.p[0], src.p[1], kind == kKindTF32X3, dst, rows, pitch, cols);
+      src.p[0], src.p[1], src.fmt, scale, dst, rows, pitch, cols);
   CDR_LAUNCH_OK("act_to_f32_kernel");
   return CDR_OK;
 }
@@ -832,15 +1086,16 @@ int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r
                     int batch, float scale, float* kp2d_l, float* kp2d_r, float* xyz,
                     const CdrHeadTaps* taps, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const TcPack* pk = (const TcPack*)w.impl;
-  const int kind = w.kind;
-  const int elem = kind == kKindBF16 ? 2 : 4;
+  const int mode = w.kind;
+  const bool scaled = mode_decoder_kind(mode) == kKindF16X2;
   const int B = batch, N = 2 * batch, J = w.joints;
-  TcHeadWs ws = plan_tc_head(workspace, B, J, kind);
+  TcHeadWs ws = plan_tc_head(workspace, B, J, mode);
   if (ws.bytes > workspace_bytes) {
     set_error("cdr_head_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
     return CDR_ERR_WORKSPACE;
   }
   int rc;
+  if (scaled) CDR_CUDA(cudaMemsetAsync(ws.slots, 0, 2 * kNumSlots * sizeof(float), st));
   set_stage("pinv");
   const float* pinv[2] = {pinv_l, pinv_r};
   if (!pinv_l) {
@@ -850,8 +1105,8 @@ int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r
     pinv[1] = ws.pinv + (size_t)B * 12;
   }
   set_stage("nchw_to_rows");
-  if ((rc = to_rows(feat_l, B, ws.x0, kind, st))) return rc;
-  if ((rc = to_rows(feat_r, B, act_offset(ws.x0, (size_t)B * kFeatHW * kFeatC, elem), kind, st))) return rc;
+  if ((rc = to_rows(feat_l, B, ws.x0, ScaleSlot(), st))) return rc;
+  if ((rc = to_rows(feat_r, B, act_offset(ws.x0, (size_t)B * kFeatHW * kFeatC), ScaleSlot(), st))) return rc;
   set_stage("cf_conv1");
   {
     TcLaunch l{};
@@ -859,12 +1114,12 @@ int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r
     l.a_rows_total = (long long)N * kFeatHW;
     l.layer = &pk->cf1; l.n = kHid1;
     l.C = ws.y1; l.c_pitch = kHid1Pad; l.c_fill = kHid1Pad; l.relu = 1; l.out_mode = kOutRows;
-    if ((rc = launch_tc(kind, l, st))) return rc;
+    if ((rc = launch_tc(l, st))) return rc;
   }
   set_stage("ftl_inv");
   for (int v = 0; v < 2; ++v)
-    if ((rc = ftl_act(act_offset(ws.y1, (size_t)v * B * kFeatHW * kHid1Pad, elem), kHid1Pad, pinv[v], 4, 3, B,
-                      act_offset(ws.z, (size_t)v * kHid2, elem), 2 * kHid2, kHid2, kind, st)))
+    if ((rc = ftl_act(act_offset(ws.y1, (size_t)v * B * kFeatHW * kHid1Pad), kHid1Pad, pinv[v], 4, 3, B,
+                      act_offset(ws.z, (size_t)v * kHid2), 2 * kHid2, kHid2, nullptr, st)))
       return rc;
   set_stage("cf_conv2");
   {
@@ -873,15 +1128,15 @@ int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r
     l.a_rows_total = (long long)B * kFeatHW;
     l.layer = &pk->cf2a; l.n = kHid2;
     l.C = ws.f1; l.c_pitch = kHid2; l.c_fill = kHid2; l.relu = 1; l.out_mode = kOutRows;
-    if ((rc = launch_tc(kind, l, st))) return rc;
+    if ((rc = launch_tc(l, st))) return rc;
     l.A = ws.f1; l.a_pitch = kHid2; l.cin = kHid2; l.layer = &pk->cf2b; l.C = ws.f2;
-    if ((rc = launch_tc(kind, l, st))) return rc;
+    if ((rc = launch_tc(l, st))) return rc;
   }
   set_stage("ftl_fwd");
   const float* Pv[2] = {P_l, P_r};
   for (int v = 0; v < 2; ++v)
-    if ((rc = ftl_act(ws.f2, kHid2, Pv[v], 3, 4, B, act_offset(ws.g, (size_t)v * B * kFeatHW * kHid1Pad, elem),
-                      kHid1Pad, kHid1Pad, kind, st)))
+    if ((rc = ftl_act(ws.f2, kHid2, Pv[v], 3, 4, B, act_offset(ws.g, (size_t)v * B * kFeatHW * kHid1Pad),
+                      kHid1Pad, kHid1Pad, scaled ? slot(ws.slots, 0).amax : nullptr, st)))
       return rc;
   set_stage("cf_out");
   {
@@ -891,9 +1146,10 @@ int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r
     l.layer = &pk->out; l.b_group_rows = kFeatC; l.n = kFeatC; l.bias_group_stride = kFeatC;
     l.C = ws.x1; l.c_group_stride = (long long)B * kFeatHW * kFeatC; l.c_pitch = kFeatC; l.c_fill = kFeatC;
     l.relu = 1; l.out_mode = kOutRows;
-    if ((rc = launch_tc(kind, l, st))) return rc;
+    l.amax_in = slot(ws.slots, 0).amax; l.out_slot = slot(ws.slots, 1);
+    if ((rc = launch_tc(l, st))) return rc;
   }
-  if ((rc = tc_decoder(w, ws.x1, N, ws.d1, ws.d2, ws.d3, ws.hm, st))) return rc;
+  if ((rc = tc_decoder(w, ws.x1, N, ws.d1, ws.d2, ws.d3, ws.slots, ws.hm, st))) return rc;
   set_stage("softargmax_dlt");
   if ((rc = cdr_softargmax_dlt(ws.hm, ws.hm + (size_t)B * J * 4096, 0, P_l, P_r, B, J, kHeat, kHeat, scale,
                                kp2d_l, kp2d_r, xyz, nullptr, nullptr, nullptr, nullptr, nullptr, st)))
@@ -904,9 +1160,10 @@ int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r
       CDR_CUDA(cudaMemcpyAsync(taps->pinv, pinv[0], (size_t)B * 48, cudaMemcpyDeviceToDevice, st));
       CDR_CUDA(cudaMemcpyAsync(taps->pinv + (size_t)B * 12, pinv[1], (size_t)B * 48, cudaMemcpyDeviceToDevice, st));
     }
-    if ((rc = tap_to_f32(taps->cf_cat, ws.z, kind, (long long)B * kFeatHW, 2 * kHid2, 2 * kHid2, st))) return rc;
-    if ((rc = tap_to_f32(taps->cf_f, ws.f2, kind, (long long)B * kFeatHW, kHid2, kHid2, st))) return rc;
-    if ((rc = tap_to_f32(taps->f_out, ws.x1, kind, (long long)N * kFeatHW, kFeatC, kFeatC, st))) return rc;
+    if ((rc = tap_to_f32(taps->cf_cat, ws.z, nullptr, (long long)B * kFeatHW, 2 * kHid2, 2 * kHid2, st))) return rc;
+    if ((rc = tap_to_f32(taps->cf_f, ws.f2, nullptr, (long long)B * kFeatHW, kHid2, kHid2, st))) return rc;
+    if ((rc = tap_to_f32(taps->f_out, ws.x1, slot(ws.slots, 1).scale, (long long)N * kFeatHW, kFeatC, kFeatC, st)))
+      return rc;
     if (taps->heatmaps)
       CDR_CUDA(cudaMemcpyAsync(taps->heatmaps, ws.hm, (size_t)N * J * 4096 * 4, cudaMemcpyDeviceToDevice, st));
   }
@@ -920,9 +1177,10 @@ int tc_decoder_forward(const TcWeights& w, const float* feat, int n_images, floa
     set_error("cdr_decoder_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
     return CDR_ERR_WORKSPACE;
   }
+  if (ws.x1.fmt == kFmtF16P) CDR_CUDA(cudaMemsetAsync(ws.slots, 0, 2 * kNumSlots * sizeof(float), st));
   set_stage("nchw_to_rows");
-  if (int rc = to_rows(feat, n_images, ws.x1, w.kind, st)) return rc;
-  return tc_decoder(w, ws.x1, n_images, ws.d1, ws.d2, ws.d3, heatmaps, st);
+  if (int rc = to_rows(feat, n_images, ws.x1, slot(ws.slots, 1), st)) return rc;
+  return tc_decoder(w, ws.x1, n_images, ws.d1, ws.d2, ws.d3, ws.slots, heatmaps, st);
 }
 
 }  // namespace cdr

@@ -38,9 +38,14 @@ int launch_nchw_to_rows_bf16(const float* in, int n_img, int C, int HW, __nv_bfl
 // fp32 hi/lo planes for the 3xTF32 tensor-core path (common.cuh: split_tf32)
 int launch_nchw_to_rows_split(const float* in, int n_img, int C, int HW, float* out_hi, float* out_lo,
                               int out_pitch, cudaStream_t st);
+// amax_out (optional): atomicMax of max |out| (pre-zeroed device float)
 int launch_ftl_split(const float* in_hi, const float* in_lo, int in_pitch, const float* mats, int rows, int cols,
                      int blk, int n, int hw, float* out_hi, float* out_lo, int out_pitch, int out_fill,
-                     cudaStream_t st);
+                     float* amax_out, cudaStream_t st);
+// scaled fp16 hi/lo planes for the f16x2 tensor-core path (gemm_tc.cu: kFmtF16P)
+int launch_amax_f32(const float* in, long long n, float* amax, cudaStream_t st);
+int launch_nchw_to_rows_f16p(const float* in, int n_img, int C, int HW, void* out_hi, void* out_lo, int out_pitch,
+                             const float* amax, float* scale_out, cudaStream_t st);
 template <typename T>
 int launch_ftl(const T* in, int in_pitch, const float* mats, int rows, int cols, int blk, int n,
                int hw, T* out, int out_pitch, int out_fill, cudaStream_t st);

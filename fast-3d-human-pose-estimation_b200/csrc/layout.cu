@@ -1,5 +1,7 @@
 // Layout kernels: NCHW -> pixel-major rows, and the feature transform layer (FTL).
 // Both are pure data movement / AXPY work: HBM-bound, coalesced 128-byte accesses.
+#include <cuda_fp16.h>
+
 #include "kernels.h"
 
 namespace cdr {
@@ -85,6 +87,74 @@ int launch_nchw_to_rows_split(const float* in, int n_img, int C, int HW, float* 
   return CDR_OK;
 }
 
+// max |x| over a flat fp32 array -> atomicMax into *amax (pre-zeroed; non-negative floats order
+// like their bit patterns)
+__global__ void __launch_bounds__(256)
+amax_f32_kernel(const float* __restrict__ in, long long n, float* __restrict__ amax) {
+  float m = 0.f;
+  const long long n4 = n >> 2;
+  const float4* in4 = reinterpret_cast<const float4*>(in);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(in4 + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(in[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(m));
+}
+int launch_amax_f32(const float* in, long long n, float* amax, cudaStream_t st) {
+  CDR_CHECK_ARG(in && amax && n > 0 && ((uintptr_t)in & 15) == 0, "amax_f32: bad args");
+  const long long want = ceil_div<long long>(n >> 2, 256 * 4);
+  const unsigned grid = (unsigned)(want < 1 ? 1 : want > 8 * num_sms() ? 8 * num_sms() : want);
+  amax_f32_kernel<<<grid, 256, 0, st>>>(in, n, amax);
+  CDR_LAUNCH_OK("amax_f32_kernel");
+  return CDR_OK;
+}
+
+// scaled fp16 hi/lo planes (gemm_tc.cu: kFmtF16P): X = x * s with s = 2^(13 - ilogb(amax)),
+// hi = rn_f16(X), lo = rn_f16((X - hi) * 2^11); block (0,0,0) publishes s.
+__global__ void __launch_bounds__(256)
+nchw_to_rows_f16p_kernel(const float* __restrict__ in, int C, int HW, __half* __restrict__ out_hi,
+                         __half* __restrict__ out_lo, int out_pitch, const float* __restrict__ amax,
+                         float* __restrict__ scale_out) {
+  __shared__ float tile[32][65];
+  const float a = __ldg(amax);
+  const float s = (a > 0.f && a < 3.0e38f) ? ldexpf(1.f, 13 - ilogbf(a)) : 1.f;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *scale_out = s;
+  const int c0 = blockIdx.x * 32, p0 = blockIdx.y * 64, img = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int c = ty; c < 32; c += 8) {
+    const float* src = in + ((size_t)img * C + c0 + c) * HW + p0;
+    if (c0 + c < C) {
+      if (p0 + tx < HW) tile[c][tx] = src[tx];
+      if (p0 + tx + 32 < HW) tile[c][tx + 32] = src[tx + 32];
+    }
+  }
+  __syncthreads();
+  if (c0 + tx < C) {
+    for (int pp = ty; pp < 64; pp += 8) {
+      if (p0 + pp < HW) {
+        const float X = tile[tx][pp] * s;
+        const __half h = __float2half_rn(X);
+        const size_t o = ((size_t)img * HW + p0 + pp) * out_pitch + c0 + tx;
+        out_hi[o] = h;
+        out_lo[o] = __float2half_rn((X - __half2float(h)) * 2048.f);
+      }
+    }
+  }
+}
+int launch_nchw_to_rows_f16p(const float* in, int n_img, int C, int HW, void* out_hi, void* out_lo, int out_pitch,
+                             const float* amax, float* scale_out, cudaStream_t st) {
+  CDR_CHECK_ARG(in && out_hi && out_lo && amax && scale_out && n_img > 0 && C > 0 && HW > 0 && out_pitch >= C,
+                "nchw_to_rows_f16p: bad args");
+  dim3 grid(ceil_div(C, 32), ceil_div(HW, 64), n_img);
+  nchw_to_rows_f16p_kernel<<<grid, 256, 0, st>>>(in, C, HW, (__half*)out_hi, (__half*)out_lo, out_pitch, amax, scale_out);
+  CDR_LAUNCH_OK("nchw_to_rows_f16p_kernel");
+  return CDR_OK;
+}
+
 // FTL (models/cdrnet.py:45-56) on pixel-major rows.  With z.reshape(b, N, -1) the k-th
 // "coordinate" of channel c is channel k*blk + c of the same pixel, so
 //   out[row, r*blk + c] = sum_k mats[img(row)][r][k] * in[row, k*blk + c].
@@ -116,9 +186,10 @@ template <int ROWS, int COLS>
 __global__ void __launch_bounds__(256)
 ftl_split_kernel(const float* __restrict__ in_hi, const float* __restrict__ in_lo, int in_pitch,
                  const float* __restrict__ mats, int blk, long long total, int hw, float* __restrict__ out_hi,
-                 float* __restrict__ out_lo, int out_pitch, int out_fill) {
+                 float* __restrict__ out_lo, int out_pitch, int out_fill, float* __restrict__ amax_out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+  float amax = 0.f;
+  if (idx < total) {
   const long long row = idx / blk;
   const int c = (int)(idx - row * blk);
   const float* m = mats + (row / hw) * (ROWS * COLS);
@@ -138,23 +209,30 @@ ftl_split_kernel(const float* __restrict__ in_hi, const float* __restrict__ in_l
     split_tf32(acc, hi, lo);
     out_hi[o + r * blk + c] = hi;
     out_lo[o + r * blk + c] = lo;
+    amax = fmaxf(amax, fabsf(acc));
   }
   if (c < out_fill - ROWS * blk) {
     out_hi[o + ROWS * blk + c] = 0.f;
     out_lo[o + ROWS * blk + c] = 0.f;
   }
+  }
+  if (amax_out) {   // max |out| for the scale of the tensor the next conv writes (gemm_tc.cu: kFmtF16P)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(amax_out), __float_as_uint(amax));
+  }
 }
 
 int launch_ftl_split(const float* in_hi, const float* in_lo, int in_pitch, const float* mats, int rows, int cols,
                      int blk, int n, int hw, float* out_hi, float* out_lo, int out_pitch, int out_fill,
-                     cudaStream_t st) {
+                     float* amax_out, cudaStream_t st) {
   CDR_CHECK_ARG(in_hi && in_lo && mats && out_hi && out_lo && n > 0 && hw > 0 && blk > 0, "ftl_split: bad args");
   const long long total = (long long)n * hw * blk;
   const unsigned grid = (unsigned)ceil_div<long long>(total, 256);
   if (rows == 4 && cols == 3)
-    ftl_split_kernel<4, 3><<<grid, 256, 0, st>>>(in_hi, in_lo, in_pitch, mats, blk, total, hw, out_hi, out_lo, out_pitch, out_fill);
+    ftl_split_kernel<4, 3><<<grid, 256, 0, st>>>(in_hi, in_lo, in_pitch, mats, blk, total, hw, out_hi, out_lo, out_pitch, out_fill, amax_out);
   else if (rows == 3 && cols == 4)
-    ftl_split_kernel<3, 4><<<grid, 256, 0, st>>>(in_hi, in_lo, in_pitch, mats, blk, total, hw, out_hi, out_lo, out_pitch, out_fill);
+    ftl_split_kernel<3, 4><<<grid, 256, 0, st>>>(in_hi, in_lo, in_pitch, mats, blk, total, hw, out_hi, out_lo, out_pitch, out_fill, amax_out);
   else {
     set_error("ftl_split: only (4x3) and (3x4) matrices are supported");
     return CDR_ERR_UNSUPPORTED;

@@ -8,10 +8,10 @@ struct TcWeights {
   void* pool = nullptr;   // one cudaMalloc holding every packed layer
   void* impl = nullptr;   // TcPack (gemm_tc.cu): per-layer pointers + weight tensor maps
   int joints = 0, has_fusion = 0, fin_npad = 0;
-  int kind = 0;           // 0 = bf16, 1 = tf32x3
+  int kind = 0;           // pack mode: 0 = bf16, 1 = tf32x3, 2 = hybrid (fusion tf32x3, decoder f16x2)
 };
 
-int tc_weights_create(const CdrWeightPtrs& src, int kind, TcWeights& w, cudaStream_t st);
+int tc_weights_create(const CdrWeightPtrs& src, int mode, TcWeights& w, cudaStream_t st);
 void tc_weights_destroy(TcWeights& w);
 int tc_head_workspace_bytes(const TcWeights& w, int batch, size_t* bytes);
 int tc_decoder_workspace_bytes(const TcWeights& w, int n_images, size_t* bytes);

@@ -95,3 +95,99 @@ class HeadGraph:
         if sync:
             torch.cuda.current_stream(self.dev).synchronize()
         return self.kp_host, self.xyz_host, self.sums_host
+
+
+class HeadPipeline:
+    """Throughput form of the end-to-end step: a depth-2 software pipeline over batches.
+
+        submit(i):  copy stream    pinned host latents / P  --H2D-->  device input buffers [i % 2]
+                    compute stream (waits for that copy) one CUDA graph: cdr_head_forward
+                                   [-> MPJPE partial sums] -> D2H of 2D/3D joints (+ sums) into
+                                   pinned host results [i % 2]
+        collect():  waits for the oldest submitted batch and returns its host results.
+
+    While batch i computes, batch i+1 crosses PCIe, so a steady-state step costs
+    max(H2D, compute) instead of their sum.  Every batch is still copied host->device and its
+    results device->host; only the order of waiting changes.  The two graphs share the library
+    workspace — legal because both replay on the one compute stream, in submission order.
+    """
+
+    def __init__(self, model, batch, gt=None, img_size=256, warmup=2):
+        self.model = model
+        self.dev = next(model.CF.parameters()).device
+        self.gt, self.img_size, self.batch = gt, img_size, batch
+        b, j = batch, model.decoder.num_joints
+        dev = self.dev
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.compute_stream = torch.cuda.Stream(dev)
+        self.feats_dev = [[torch.empty((b, 2048, 8, 8), dtype=torch.float32, device=dev) for _ in range(2)] for _ in range(2)]
+        self.P_dev = [[torch.empty((b, 3, 4), dtype=torch.float32, device=dev) for _ in range(2)] for _ in range(2)]
+        self.kp_host = [[torch.empty((b, j, 2), dtype=torch.float32).pin_memory() for _ in range(2)] for _ in range(2)]
+        self.xyz_host = [torch.empty((b, j, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.xyz_dev = [torch.empty((b, j, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.sums_host = [torch.empty(4, dtype=torch.float64).pin_memory() for _ in range(2)] if gt is not None else None
+        self.sums_dev = [torch.zeros(4, dtype=torch.float64, device=dev) for _ in range(2)] if gt is not None else None
+        self.h2d_done = [torch.cuda.Event() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        self.n_submitted = 0
+        self.n_collected = 0
+        cur = torch.cuda.current_stream(dev)
+        self.compute_stream.wait_stream(cur)
+        with torch.cuda.stream(self.compute_stream):
+            for s in range(2):
+                for t in self.feats_dev[s] + self.P_dev[s]:
+                    t.zero_()
+                self.P_dev[s][0][:, :, :3] = torch.eye(3, device=dev)   # any full-rank P for the warm-up
+                self.P_dev[s][1][:, :, :3] = torch.eye(3, device=dev)
+            for _ in range(max(1, warmup)):
+                self._compute(0)
+        torch.cuda.synchronize(dev)
+        key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+        self._workspace = _cdrnet._WS.get(key)
+        self.graphs = []
+        for s in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.compute_stream):
+                self._compute(s)
+            self.graphs.append(g)
+        torch.cuda.synchronize(dev)
+
+    def _compute(self, s):
+        (kl, kr), xyz = self.model.head(self.feats_dev[s], self.P_dev[s], img_size=self.img_size)
+        self.xyz_dev[s].copy_(xyz)
+        self.kp_host[s][0].copy_(kl, non_blocking=True)
+        self.kp_host[s][1].copy_(kr, non_blocking=True)
+        self.xyz_host[s].copy_(xyz, non_blocking=True)
+        if self.gt is not None:
+            g = self.gt
+            self.sums_dev[s].copy_(mpjpe_sums([kl, kr], xyz, g["gt3d"], g["gt2d_l"], g["gt2d_r"], g.get("vis")))
+            self.sums_host[s].copy_(self.sums_dev[s], non_blocking=True)
+
+    def submit(self, feats_host, P_host, post=None):
+        """Enqueue one batch (pinned fp32 host tensors).  `post(slot)` — optional — runs under the
+        compute stream after the head (e.g. the multi-GPU gather)."""
+        if self.n_submitted - self.n_collected >= 2:
+            raise RuntimeError("HeadPipeline: two batches already in flight — collect() first")
+        s = self.n_submitted % 2
+        with torch.cuda.stream(self.copy_stream):
+            # the compute that last read these device buffers (batch n-2) was collected => finished
+            for d, h in zip(self.feats_dev[s] + self.P_dev[s], list(feats_host) + list(P_host)):
+                d.copy_(h, non_blocking=True)
+            self.h2d_done[s].record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(self.h2d_done[s])
+            self.graphs[s].replay()
+            if post is not None:
+                post(s)
+            self.done[s].record(self.compute_stream)
+        self.n_submitted += 1
+        return s
+
+    def collect(self):
+        """Wait for the oldest batch in flight; returns (slot, kp_host list[2], xyz_host, sums_host)."""
+        if self.n_collected >= self.n_submitted:
+            raise RuntimeError("HeadPipeline: nothing in flight")
+        s = self.n_collected % 2
+        self.done[s].synchronize()
+        self.n_collected += 1
+        return s, self.kp_host[s], self.xyz_host[s], (self.sums_host[s] if self.sums_host is not None else None)

@@ -55,8 +55,11 @@ typedef enum CdrStatus {
 typedef enum CdrPrecision {
   CDR_PREC_FP32 = 0,  /* fp32 FFMA implicit-GEMM kernels (CUDA cores) */
   CDR_PREC_BF16 = 1,  /* bf16 operands on tcgen05 tensor cores, fp32 accumulation in TMEM */
-  CDR_PREC_TF32X3 = 2 /* fp32 accuracy on tcgen05: every operand split into two tf32 terms,
+  CDR_PREC_TF32X3 = 2,/* fp32 accuracy on tcgen05: every operand split into two tf32 terms,
                          three kind::tf32 MMAs per product, fp32 accumulation in TMEM */
+  CDR_PREC_F16X2 = 3  /* fp32 accuracy on tcgen05 at the full 16-bit rate: decoder operands as two
+                         scaled fp16 terms (data-dependent power-of-two tensor scales), three
+                         kind::f16 MMAs per product; the fusion block stays 3xTF32 */
 } CdrPrecision;
 
 /* One conv (or transposed conv) + eval-mode BatchNorm2d, reference tensor layouts. */

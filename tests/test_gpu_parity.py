@@ -84,9 +84,10 @@ def _nhwc_to_nchw(t, c):  # (..., 64, C) -> (..., C, 8, 8)
     return t.reshape(*t.shape[:-2], 8, 8, c).permute(*range(t.dim() - 2), -1, -3, -2)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp32_ffma"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "fp32_ffma"])
 def test_head_fp32_vs_fp64_oracle_stagewise(cuda_pkg, precision):
-    """fp32 results: 'fp32' = 3xTF32 split on the tcgen05 tensor cores (default), 'fp32_ffma' = CUDA cores."""
+    """fp32 results: 'fp32' = tcgen05 with the decoder on scaled fp16 two-term operands (f16x2) and
+    the fusion block on 3xTF32 (default); 'tf32x3' = 3xTF32 everywhere; 'fp32_ffma' = CUDA cores."""
     b = 4
     sd = synth.make_head_state_dict(seed=0, calibrated=True, randomize_bn=True)
     feats, cams = synth.make_features(b, seed=1), synth.make_cameras(b, seed=2)
@@ -347,7 +348,27 @@ def test_ftl_identity_and_oracle(cuda_pkg):
         L.check(L.lib().cdr_ftl(L.ptr(xin), 304, L.ptr(P_d), 2, 2, 100, b, 64, L.ptr(out), 400, 400, st))
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp32_ffma"])
+@pytest.mark.parametrize("gain", [1.0, 3.0e4, 1.0e-5])
+def test_decoder_f16x2_dynamic_range(cuda_pkg, gain):
+    """The f16x2 decoder scales every tensor by a data-dependent power of two: the relative error of
+    the heat-maps must not depend on the magnitude of the latents (fp16 alone would overflow at
+    gain 3e4 and flush to zero at 1e-5).  BN is the identity here so the network stays positively
+    homogeneous up to the final bias."""
+    n, joints = 2, 19
+    sd = synth.make_head_state_dict(seed=5, joints=joints, calibrated=True, randomize_bn=False, decoder_only=True)
+    feats = synth.make_features(n, seed=6)[0] * gain
+    want = O.decoder(O.cast_state_dict(sd, torch.float64), feats.double()).numpy()
+    dec = cuda_pkg.PoseDecoder(synth.make_cfg(18, joints), precision="f16x2")
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items()})
+    dec = dec.cuda().eval()
+    got = dec(feats.cuda()).cpu().numpy()
+    rel = np.abs(got - want).max() / np.abs(want).max()
+    print(f"\ndecoder [f16x2] latents x{gain:g}: rel err {rel:.2e}, max |heat| {np.abs(want).max():.3e}")
+    assert np.isfinite(got).all()
+    assert rel < 2e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "fp32_ffma"])
 def test_decoder_forward_vs_oracle(cuda_pkg, precision):
     """PoseResNet's decoder half (models/poseresnet.py:17-21) incl. an odd image count."""
     n, joints = 3, 16
