@@ -93,9 +93,9 @@ static int make_tmap(CUtensorMap* map, const void* base, int fmt, int rank, cons
 
 // ------------------------------------------------------------------------------------------
 constexpr int kTcBM = 128;
-constexpr int kTcThreads = 192;
 constexpr int kABytes = kTcBM * 128;             // 128 rows x one 128-byte swizzle row = 16 KB
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudget = 224 * 1024;          // of the 227 KB a CTA may own
+constexpr int kStageBufBytes = 32 * 128;         // TMA-store staging per epilogue warp: 32 rows x 128 B
 
 // Operand kinds.
 //   kKindBF16  : bf16 operands, kind::f16, one MMA per K=16 step.
@@ -120,20 +120,32 @@ template <> struct KindTraits<kKindBF16>   { static constexpr int kElem = 2, kBK
 template <> struct KindTraits<kKindTF32X3> { static constexpr int kElem = 4, kBK = 32, kPlanes = 2, kFmt = kFmtTF32P; };
 template <> struct KindTraits<kKindF16X2>  { static constexpr int kElem = 2, kBK = 64, kPlanes = 2, kFmt = kFmtF16P; };
 
-template <int BN, int KIND>
+template <int BN, int KIND, int OFMT>
 struct TcCfg {
   static constexpr int kBK = KindTraits<KIND>::kBK;
   static constexpr int kPlanes = KindTraits<KIND>::kPlanes;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+  // Epilogue: 8 warps for wide tiles — two per TMEM lane quarter, each owning half of the columns —
+  // because with short K loops (the 256-channel transposed convs: 16 K-blocks per tile) the epilogue,
+  // not the MMA, paces the kernel (measured: the MMA issuer spinning on tmem_empty).
+  static constexpr int kEpiWarps = BN >= 128 ? 8 : 4;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+  // 16-bit row-major outputs leave through swizzled smem staging + TMA tensor stores (full 128-byte
+  // lines, issued by one lane, asynchronous) instead of 32 scattered 16-byte stores per warp instruction.
+  static constexpr bool kTmaStore = BN >= 128 && OFMT != kFmtTF32P;
+  static constexpr int kStagingBytes = kTmaStore ? kEpiWarps * kStageBufBytes : 0;
+  static constexpr int kStagesFit = (kSmemBudget - kStagingBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kAccBufs = KIND != kKindBF16 ? 4 : 2;     // see the TMEM column map in the kernel
   static constexpr int kTmemCols = (kAccBufs * BN <= 32) ? 32 : (kAccBufs * BN <= 64) ? 64
                                    : (kAccBufs * BN <= 128) ? 128 : (kAccBufs * BN <= 256) ? 256 : 512;
   static_assert(kAccBufs * BN <= 512, "TMEM has 512 columns");
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 512 /*barriers*/;
-  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 512 /*barriers*/;
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N for M=128; 32-column epilogue slabs");
   static_assert(kStages >= 2, "pipeline too shallow");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
 struct TcGemmParams {
@@ -167,25 +179,68 @@ struct TcGemmParams {
   int num_tiles;
 };
 
-// Epilogue for one 32-column slab of a finished row: + bias, ReLU, mask, convert, store.
 struct EpiScale {          // per-thread epilogue constants of the scaled formats
   float a_inv = 1.f;       // 1 / s(A tensor)
   float s_out = 1.f;       // s(output tensor)
   float amax = 0.f;        // running max |out| of this thread
 };
+
+// + scale (f16x2), bias, ReLU, column mask for one 32-column slab of a finished row
+template <int KIND>
+__device__ __forceinline__ void finish_slab(const TcGemmParams& p, const float (&acc)[32], float (&v)[32], int n0c,
+                                            const float* __restrict__ bias, const float* __restrict__ wsi,
+                                            const EpiScale& es) {
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    float x[4] = {acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]};
+    if constexpr (KIND == kKindF16X2) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wsi + n0c) + j4);
+      x[0] *= es.a_inv * w4.x; x[1] *= es.a_inv * w4.y; x[2] *= es.a_inv * w4.z; x[3] *= es.a_inv * w4.w;
+    }
+    if (bias) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0c) + j4);
+      x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (p.relu) x[e] = fmaxf(x[e], 0.f);
+      v[4 * j4 + e] = (n0c + 4 * j4 + e < p.n) ? x[e] : 0.f;
+    }
+  }
+}
+
+// 16-bit encodings of a finished slab: 16 packed words per plane
+template <int OFMT>
+__device__ __forceinline__ void encode_slab(const float (&v)[32], uint32_t (&hi)[16], uint32_t (&lo)[16],
+                                            bool row_ok, EpiScale& es) {
+  if constexpr (OFMT == kFmtF16P) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const float x0 = v[2 * e], x1 = v[2 * e + 1];
+      if (row_ok) es.amax = fmaxf(es.amax, fmaxf(fabsf(x0), fabsf(x1)));
+      const float X0 = x0 * es.s_out, X1 = x1 * es.s_out;
+      const __half2 hh = __floats2half2_rn(X0, X1);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn((X0 - hf.x) * kLoScale, (X1 - hf.y) * kLoScale);
+      hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+      hi[e] = *reinterpret_cast<const uint32_t*>(&b);
+    }
+  }
+}
+
+// Direct global stores of one finished slab (planar heat-maps, fp32 planes, and the narrow tiles).
 template <int KIND, int OFMT>
 __device__ __forceinline__ void store_slab(const TcGemmParams& p, const float (&acc)[32], int n0c, int g, bool row_ok,
                                            size_t orow, int img, int pix, int HW, const float* __restrict__ bias,
                                            const float* __restrict__ wsi, EpiScale& es) {
   float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float x = acc[j];
-    if constexpr (KIND == kKindF16X2) x *= es.a_inv * __ldg(wsi + n0c + j);
-    if (bias) x += __ldg(bias + n0c + j);
-    if (p.relu) x = fmaxf(x, 0.f);
-    v[j] = (n0c + j < p.n) ? x : 0.f;
-  }
+  finish_slab<KIND>(p, acc, v, n0c, bias, wsi, es);
   if (!row_ok) return;
   if (p.out_mode == kOutPlanar) {
     float* __restrict__ C = reinterpret_cast<float*>(p.C);
@@ -195,29 +250,7 @@ __device__ __forceinline__ void store_slab(const TcGemmParams& p, const float (&
     return;
   }
   const size_t off = (p.out_mode == kOutDeconv ? 0 : (size_t)g * p.c_group_stride) + orow * p.c_pitch + n0c;
-  if constexpr (OFMT == kFmtF16P) {
-    __half* __restrict__ Ch = reinterpret_cast<__half*>(p.C) + off;
-    __half* __restrict__ Cl = reinterpret_cast<__half*>(p.C_lo) + off;
-#pragma unroll
-    for (int j8 = 0; j8 < 4; ++j8) {
-      if (n0c + j8 * 8 < p.c_fill) {
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float x0 = v[j8 * 8 + 2 * e], x1 = v[j8 * 8 + 2 * e + 1];
-          es.amax = fmaxf(es.amax, fmaxf(fabsf(x0), fabsf(x1)));
-          const float X0 = x0 * es.s_out, X1 = x1 * es.s_out;
-          const __half2 hh = __floats2half2_rn(X0, X1);
-          const float2 hf = __half22float2(hh);
-          const __half2 ll = __floats2half2_rn((X0 - hf.x) * kLoScale, (X1 - hf.y) * kLoScale);
-          h[e] = *reinterpret_cast<const uint32_t*>(&hh);
-          l[e] = *reinterpret_cast<const uint32_t*>(&ll);
-        }
-        *reinterpret_cast<uint4*>(Ch + j8 * 8) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(Cl + j8 * 8) = make_uint4(l[0], l[1], l[2], l[3]);
-      }
-    }
-  } else if constexpr (OFMT == kFmtTF32P) {
+  if constexpr (OFMT == kFmtTF32P) {
     float* __restrict__ Ch = reinterpret_cast<float*>(p.C) + off;
     float* __restrict__ Cl = reinterpret_cast<float*>(p.C_lo) + off;
 #pragma unroll
@@ -231,26 +264,50 @@ __device__ __forceinline__ void store_slab(const TcGemmParams& p, const float (&
       }
     }
   } else {
-    __nv_bfloat16* __restrict__ C = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
+    uint32_t hi[16], lo[16];
+    encode_slab<OFMT>(v, hi, lo, true, es);
+    uint16_t* __restrict__ Ch = reinterpret_cast<uint16_t*>(p.C) + off;
 #pragma unroll
-    for (int j8 = 0; j8 < 4; ++j8) {
-      if (n0c + j8 * 8 < p.c_fill) {
-        uint4 o;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j8 * 8 + 0], v[j8 * 8 + 1]);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j8 * 8 + 2], v[j8 * 8 + 3]);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j8 * 8 + 4], v[j8 * 8 + 5]);
-        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j8 * 8 + 6], v[j8 * 8 + 7]);
-        o.x = *reinterpret_cast<uint32_t*>(&h0);
-        o.y = *reinterpret_cast<uint32_t*>(&h1);
-        o.z = *reinterpret_cast<uint32_t*>(&h2);
-        o.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(C + j8 * 8) = o;
-      }
+    for (int j8 = 0; j8 < 4; ++j8)
+      if (n0c + j8 * 8 < p.c_fill)
+        *reinterpret_cast<uint4*>(Ch + j8 * 8) = make_uint4(hi[4 * j8], hi[4 * j8 + 1], hi[4 * j8 + 2], hi[4 * j8 + 3]);
+    if constexpr (OFMT == kFmtF16P) {
+      uint16_t* __restrict__ Cl = reinterpret_cast<uint16_t*>(p.C_lo) + off;
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8)
+        if (n0c + j8 * 8 < p.c_fill)
+          *reinterpret_cast<uint4*>(Cl + j8 * 8) = make_uint4(lo[4 * j8], lo[4 * j8 + 1], lo[4 * j8 + 2], lo[4 * j8 + 3]);
     }
   }
 }
 
-// K-blocks accumulated inside TMEM before the 3xTF32 main term is drained into fp32 registers.
+// One warp's 32 rows x 64 columns of 16-bit output: registers -> 128B-swizzled staging -> one TMA
+// tensor store.  `words` = this lane's row, 32 packed words (64 values).  The staging buffer is
+// private to the warp; the previous store's read of it is awaited first.
+struct StoreCoord {
+  int rows;      // kOutRows: (c, m, g)
+  int m, g;
+  int px, x0, py, r0;   // kOutDeconv: (c, px, x, py, img*H + y)
+};
+__device__ __forceinline__ void tma_store_block(const TcGemmParams& p, const void* tmap, uint8_t* stage, int lane,
+                                                const uint32_t (&words)[32], int c0, const StoreCoord& sc) {
+  if (lane == 0) ptx::bulk_wait_read0();
+  __syncwarp();
+  const uint32_t base = ptx::smem_u32(stage) + (uint32_t)lane * 128u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    ptx::st_shared_v4(base + (uint32_t)((j ^ (lane & 7)) << 4), words[4 * j], words[4 * j + 1], words[4 * j + 2],
+                      words[4 * j + 3]);
+  ptx::fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    if (p.out_mode == kOutDeconv) ptx::tma_store_5d(tmap, stage, c0, sc.px, sc.x0, sc.py, sc.r0);
+    else ptx::tma_store_3d(tmap, stage, c0, sc.m, sc.g);
+    ptx::bulk_commit();
+  }
+}
+
+// K-blocks accumulated inside TMEM before the split kinds' main term is drained into fp32 registers.
 // The tensor core adds into its fp32 accumulator with round-toward-zero; over a long K chain
 // of same-signed partial sums that bias grows linearly (measured: 1e-5 relative at K=2048, 40x
 // worse than FFMA).  Chains of 4 K-blocks (16 MMAs) keep it below 1e-6; the cross-chunk sum is
@@ -258,27 +315,31 @@ __device__ __forceinline__ void store_slab(const TcGemmParams& p, const float (&
 constexpr int kSplitChunk = 4;
 
 template <int BN, int KIND, int OFMT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(TcCfg<BN, KIND, OFMT>::kThreads, 1)
 tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
                    const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo,
+                   const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c_lo,
                    const TcGemmParams p) {
-  using Cfg = TcCfg<BN, KIND>;
+  using Cfg = TcCfg<BN, KIND, OFMT>;
   constexpr int S = Cfg::kStages;
   constexpr int kTcBK = Cfg::kBK;
   constexpr bool kSplit = KIND != kKindBF16;
+  constexpr int kEpiWarps = Cfg::kEpiWarps;
+  constexpr int kCols = Cfg::kColsPerWarp;       // columns of the tile owned by one epilogue warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // stage s: [A (16 KB) | A_lo (tf32x3) | B (BN*128 B) | B_lo (tf32x3)], every piece 1024-aligned
+  // stage s: [A (16 KB) | A_lo (split kinds) | B (BN*128 B) | B_lo (split kinds)], every piece 1024-aligned
   auto stage_a = [&](int s, int plane) { return smem + (size_t)s * Cfg::kStageBytes + (size_t)plane * kABytes; };
   auto stage_b = [&](int s, int plane) {
     return smem + (size_t)s * Cfg::kStageBytes + (size_t)Cfg::kPlanes * kABytes + (size_t)plane * Cfg::kBBytes;
   };
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * Cfg::kStageBytes);
+  uint8_t* staging = smem + (size_t)S * Cfg::kStageBytes;               // [kEpiWarps][4 KB], 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* full = bars;                      // [S]  TMA -> MMA
   uint64_t* empty = bars + S;                 // [S]  MMA -> TMA
-  uint64_t* tmem_full = bars + 2 * S;         // [2]  finished tile accumulator (bf16) / correction accumulator (tf32x3)
+  uint64_t* tmem_full = bars + 2 * S;         // [2]  finished tile accumulator (bf16) / correction accumulator (split)
   uint64_t* tmem_empty = bars + 2 * S + 2;    // [2]
-  uint64_t* chunk_full = bars + 2 * S + 4;    // [2]  tf32x3: main-term chunk accumulator
+  uint64_t* chunk_full = bars + 2 * S + 4;    // [2]  split kinds: main-term chunk accumulator
   uint64_t* chunk_empty = bars + 2 * S + 6;   // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
 
@@ -292,15 +353,19 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       ptx::prefetch_tmap(&tmap_a_lo);
       ptx::prefetch_tmap(&tmap_b_lo);
     }
+    if (Cfg::kTmaStore && p.out_mode != kOutPlanar) {
+      ptx::prefetch_tmap(&tmap_c);
+      if (OFMT == kFmtF16P) ptx::prefetch_tmap(&tmap_c_lo);
+    }
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 4);     // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty[a], kEpiWarps);     // one arrive per epilogue warp
       ptx::mbar_init(&chunk_full[a], 1);
-      ptx::mbar_init(&chunk_empty[a], 4);
+      ptx::mbar_init(&chunk_empty[a], kEpiWarps);
     }
     ptx::fence_mbar_init();
   }
@@ -309,9 +374,9 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
-  // TMEM columns: bf16  : [0,BN) [BN,2BN)               two tile accumulators
-  //               tf32x3: [0,BN) [BN,2BN)               two main-term chunk accumulators
-  //                       [2BN,3BN) [3BN,4BN)           two correction-term tile accumulators
+  // TMEM columns: bf16 : [0,BN) [BN,2BN)               two tile accumulators
+  //               split: [0,BN) [BN,2BN)               two main-term chunk accumulators
+  //                      [2BN,3BN) [3BN,4BN)           two correction-term tile accumulators
 
   const int kb_per_tap = (p.cin + kTcBK - 1) / kTcBK;
   const int num_kb = p.ntaps * kb_per_tap;
@@ -378,7 +443,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const uint64_t da = desc(stage_a(s, 0)), db = desc(stage_b(s, 0));
 #pragma unroll
             for (int k = 0; k < 4; ++k)    // +32 bytes (= 2 x 16 B) per K step (16 bf16) inside the swizzle row
-              ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+              mma(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (kb | k) != 0);
             ptx::umma_commit(&empty[s]);           // smem stage reusable once these MMAs retire
           }
         } else {
@@ -407,12 +472,15 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             ptx::umma_commit(&chunk_full[buf]);    // main-term chunk ready to be drained
           }
         }
-        ptx::umma_commit(&tmem_full[acc]);         // tile (bf16) / correction accumulator (tf32x3) complete
+        ptx::umma_commit(&tmem_full[acc]);         // tile (bf16) / correction accumulator (split) complete
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (warps 2..)
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int ew = warp - 2;                       // epilogue warp index
+    const int cb0 = (ew >> 2) * kCols;             // first tile column owned by this warp
+    uint8_t* stage = staging + (size_t)ew * kStageBufBytes;
     uint32_t tl = 0, ch = 0;
     EpiScale es;
     if constexpr (KIND == kKindF16X2) es.a_inv = 1.f / __ldg(p.scale_in);   // powers of two: exact
@@ -423,59 +491,104 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (blockIdx.x == 0 && threadIdx.x == 64) *p.scale_out = es.s_out;
       }
     }
+    const bool use_tma = Cfg::kTmaStore && p.out_mode != kOutPlanar;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
       const int n_tile = tile % p.n_tiles;
       const int g = (tile / p.n_tiles) % p.groups;
       const int m0 = (tile / (p.n_tiles * p.groups)) * kTcBM;
       const int acc = tl & 1;
-      const int m = m0 + q * 32 + lane;            // this thread's pixel
+      const int mw = m0 + q * 32;                  // first pixel of this warp
+      const int m = mw + lane;                     // this thread's pixel
       const bool row_ok = m < p.M;
-      const int n0 = n_tile * BN;
+      const int n0 = n_tile * BN + cb0;            // first output channel of this warp
       const float* __restrict__ bias = p.bias ? p.bias + (size_t)g * p.bias_group_stride : nullptr;
       const float* __restrict__ wsi = KIND == kKindF16X2 ? p.wsi + (size_t)g * p.wsi_group_stride : nullptr;
       size_t orow = (size_t)(row_ok ? m : 0);
       int img = 0, pix = 0;
+      StoreCoord sc{};
       if (p.out_mode == kOutDeconv) {
         img = (int)(orow / HW);
         pix = (int)(orow - (size_t)img * HW);
         const int y = pix / p.W, x = pix - y * p.W;
         orow = ((size_t)img * 2 * p.H + 2 * y + (g >> 1)) * (size_t)(2 * p.W) + 2 * x + (g & 1);
+        sc.px = g & 1; sc.py = g >> 1;
+        sc.x0 = mw % p.W; sc.r0 = mw / p.W;        // merged (img, y) row index of the warp's first pixel
       } else if (p.out_mode == kOutPlanar) {
         img = (int)(orow / HW);
         pix = (int)(orow - (size_t)img * HW);
+      } else {
+        sc.m = mw; sc.g = g;
       }
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+
+      // one finished 32-column slab (fp32, scale/bias/ReLU still to apply) -> its destination
+      auto emit = [&](const float (&a32)[32], int c, uint32_t (&wh)[32], uint32_t (&wl)[32]) {
+        // c = column inside the warp's range; TMA path gathers two slabs (64 columns) per store
+        if (!use_tma) {
+          store_slab<KIND, OFMT>(p, a32, n0 + c, g, row_ok, orow, img, pix, HW, bias, wsi, es);
+          return;
+        }
+        if constexpr (Cfg::kTmaStore) {
+          float v[32];
+          finish_slab<KIND>(p, a32, v, n0 + c, bias, wsi, es);
+          const int half = (c >> 5) & 1;
+          uint32_t h16[16], l16[16];
+          encode_slab<OFMT>(v, h16, l16, row_ok, es);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            wh[half * 16 + e] = h16[e];
+            if constexpr (OFMT == kFmtF16P) wl[half * 16 + e] = l16[e];
+          }
+          if (half == 1) {
+            const int c0 = n0 + c - 32;            // first channel of the 64-column block
+            if (c0 < p.c_fill) {
+              tma_store_block(p, &tmap_c, stage, lane, wh, c0, sc);
+              if constexpr (OFMT == kFmtF16P) tma_store_block(p, &tmap_c_lo, stage, lane, wl, c0, sc);
+            }
+          }
+        }
+      };
 
       if constexpr (!kSplit) {
         ptx::mbar_wait(&tmem_full[acc], (tl >> 1) & 1);
         ptx::tc_fence_after();
+        uint32_t wh[32], wl[32];
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(acc * BN + c), r);
+        for (int c = 0; c < kCols; c += 64) {
+          // 64 columns per TMEM round trip (one wait for two loads) when the warp owns that many
+          uint32_t r0[32], r1[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(acc * BN + cb0 + c), r0);
+          if (kCols >= 64) ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(acc * BN + cb0 + c + 32), r1);
           ptx::tmem_ld_wait();
+          if (c + 64 >= kCols) {
+            // all TMEM reads of this accumulator are complete -> hand it back before the stores
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+          }
           float a32[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) a32[j] = __uint_as_float(r[j]);
-          store_slab<KIND, OFMT>(p, a32, n0 + c, g, row_ok, orow, img, pix, HW, bias, wsi, es);
+          for (int j = 0; j < 32; ++j) a32[j] = __uint_as_float(r0[j]);
+          emit(a32, c, wh, wl);
+          if (kCols >= 64) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a32[j] = __uint_as_float(r1[j]);
+            emit(a32, c + 32, wh, wl);
+          }
         }
-        // all TMEM reads of this accumulator are complete (wait::ld above) -> hand it back
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       } else {
         // running fp32 sum of this thread's output row, round-to-nearest
-        float sum[BN];
+        float sum[kCols];
 #pragma unroll
-        for (int j = 0; j < BN; ++j) sum[j] = 0.f;
+        for (int j = 0; j < kCols; ++j) sum[j] = 0.f;
         for (int kb0 = 0; kb0 < num_kb; kb0 += kSplitChunk, ++ch) {
           const int buf = ch & 1;
           ptx::mbar_wait(&chunk_full[buf], (ch >> 1) & 1);
           ptx::tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < BN; c += 32) {
+          for (int c = 0; c < kCols; c += 32) {
             uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(buf * BN + c), r);
+            ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(buf * BN + cb0 + c), r);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) sum[c + j] += __uint_as_float(r[j]);
@@ -487,9 +600,9 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         ptx::mbar_wait(&tmem_full[acc], (tl >> 1) & 1);
         ptx::tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = 0; c < kCols; c += 32) {
           uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)((2 + acc) * BN + c), r);
+          ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)((2 + acc) * BN + cb0 + c), r);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -500,21 +613,25 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        uint32_t wh[32], wl[32];
 #pragma unroll
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = 0; c < kCols; c += 32) {
           float a32[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) a32[j] = sum[c + j];
-          store_slab<KIND, OFMT>(p, a32, n0 + c, g, row_ok, orow, img, pix, HW, bias, wsi, es);
+          emit(a32, c, wh, wl);
         }
       }
     }
+    if constexpr (Cfg::kTmaStore) {
+      if (use_tma && lane == 0) ptx::bulk_wait_all0();     // our stores have landed before the CTA retires
+    }
     if constexpr (OFMT == kFmtF16P) {
       if (p.out_mode != kOutPlanar && p.amax_out) {
-        float m = es.amax;
+        float mx = es.amax;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), __float_as_uint(m));   // m >= 0
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), __float_as_uint(mx));   // mx >= 0
       }
     }
   }
@@ -590,7 +707,7 @@ struct TcLaunch {
 
 template <int BN, int KIND, int OFMT>
 static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
-  using Cfg = TcCfg<BN, KIND>;
+  using Cfg = TcCfg<BN, KIND, OFMT>;
   constexpr int kElem = KindTraits<KIND>::kElem;
   constexpr int kBK = Cfg::kBK;
   constexpr int kAFmt = KindTraits<KIND>::kFmt;
@@ -656,9 +773,33 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
     }
   }
   if (KindTraits<KIND>::kPlanes == 1) tmap_a[1] = tmap_a[0];
+  // output maps for the TMA-store epilogue: one warp stores 32 pixels x 64 channels per instruction
+  CUtensorMap tmap_c[2] = {tmap_a[0], tmap_a[0]};
+  if (Cfg::kTmaStore && l.out_mode != kOutPlanar) {
+    for (int pl = 0; pl < fmt_planes(OFMT); ++pl) {
+      CDR_CHECK_ARG(((uintptr_t)l.C.p[pl] & 15) == 0, "tap_gemm_tc: output alignment");
+      if (l.out_mode == kOutDeconv) {
+        // (n_img, 2H, 2W, C) seen from one output phase: offset = c + px*C + x*2C + py*2W*C + (img*H + y)*4W*C
+        CDR_CHECK_ARG(l.W == 8 || l.W == 16 || l.W == 32, "tap_gemm_tc: deconv store box needs W in {8,16,32}");
+        const uint64_t cp = (uint64_t)l.c_pitch;
+        const uint64_t dims[5] = {(uint64_t)l.c_fill, 2, (uint64_t)l.W, 2, (uint64_t)l.n_img * l.H};
+        const uint64_t strides[4] = {cp, 2 * cp, 2 * (uint64_t)l.W * cp, 4 * (uint64_t)l.W * cp};
+        const uint32_t box[5] = {64, 1, (uint32_t)l.W, 1, (uint32_t)(32 / l.W)};
+        if (int rc = make_tmap(&tmap_c[pl], l.C.p[pl], OFMT, 5, dims, strides, box)) return rc;
+      } else {
+        const uint64_t gs = l.groups > 1 ? (uint64_t)l.c_group_stride : (uint64_t)p.M * l.c_pitch;
+        CDR_CHECK_ARG(gs % 8 == 0, "tap_gemm_tc: output group stride must be a 16-byte multiple");
+        const uint64_t dims[3] = {(uint64_t)l.c_fill, (uint64_t)p.M, (uint64_t)l.groups};
+        const uint64_t strides[2] = {(uint64_t)l.c_pitch, gs};
+        const uint32_t box[3] = {64, 32, 1};
+        if (int rc = make_tmap(&tmap_c[pl], l.C.p[pl], OFMT, 3, dims, strides, box)) return rc;
+      }
+    }
+    if (fmt_planes(OFMT) == 1) tmap_c[1] = tmap_c[0];
+  }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  tap_gemm_tc_kernel<BN, KIND, OFMT><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(
-      tmap_a[0], tmap_a[1], l.layer->map[0], l.layer->map[KindTraits<KIND>::kPlanes - 1], p);
+  tap_gemm_tc_kernel<BN, KIND, OFMT><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(
+      tmap_a[0], tmap_a[1], l.layer->map[0], l.layer->map[KindTraits<KIND>::kPlanes - 1], tmap_c[0], tmap_c[1], p);
   CDR_LAUNCH_OK("tap_gemm_tc_kernel");
   return CDR_OK;
 }
