@@ -357,15 +357,13 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
   set_stage("pinv");
   const float* pinv[2] = {pinv_l, pinv_r};
   if (!pinv_l) {
-    if ((rc = cdr_pinv(P_l, B, pinv_rtol, ws.pinv, st))) return rc;
-    if ((rc = cdr_pinv(P_r, B, pinv_rtol, ws.pinv + (size_t)B * 12, st))) return rc;
+    if ((rc = launch_pinv2(P_l, P_r, B, pinv_rtol, ws.pinv, st))) return rc;
     pinv[0] = ws.pinv;
     pinv[1] = ws.pinv + (size_t)B * 12;
   }
   // (2) encoder latents NCHW -> pixel-major rows, views stacked (conv_layer1 is shared)
   set_stage("nchw_to_rows");
-  if ((rc = launch_nchw_to_rows_f32(feat_l, B, kFeatC, kFeatHW, ws.x0, kFeatC, st))) return rc;
-  if ((rc = launch_nchw_to_rows_f32(feat_r, B, kFeatC, kFeatHW, ws.x0 + (size_t)B * kFeatHW * kFeatC, kFeatC, st))) return rc;
+  if ((rc = launch_nchw_to_rows_f32(feat_l, feat_r, B, kFeatC, kFeatHW, ws.x0, kFeatC, st))) return rc;
   // (3) conv_layer1 2048 -> 300 (+BN+ReLU) — :62
   set_stage("cf_conv1");
   {
@@ -377,10 +375,12 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
   }
   // (4) inverse FTL into the concatenated (B,64,800) buffer — :65,70
   set_stage("ftl_inv");
-  for (int v = 0; v < 2; ++v)
-    if ((rc = launch_ftl<float>(ws.y1 + (size_t)v * B * kFeatHW * kHid1Pad, kHid1Pad, pinv[v], 4, 3,
-                                kFtlBlk, B, kFeatHW, ws.z + v * kHid2, 2 * kHid2, kHid2, st)))
+  {
+    const float* ins[2] = {ws.y1, ws.y1 + (size_t)B * kFeatHW * kHid1Pad};
+    float* outs[2] = {ws.z, ws.z + kHid2};
+    if ((rc = launch_ftl2<float>(ins, kHid1Pad, pinv, 4, 3, kFtlBlk, B, kFeatHW, outs, 2 * kHid2, kHid2, 2, st)))
       return rc;
+  }
   // (5) conv_layer2: 800 -> 400 -> 400 — :74
   set_stage("cf_conv2");
   {
@@ -395,10 +395,12 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
   // (6) forward FTL per view — :79
   set_stage("ftl_fwd");
   const float* Pv[2] = {P_l, P_r};
-  for (int v = 0; v < 2; ++v)
-    if ((rc = launch_ftl<float>(ws.f2, kHid2, Pv[v], 3, 4, kFtlBlk, B, kFeatHW,
-                                ws.g + (size_t)v * B * kFeatHW * kHid1Pad, kHid1Pad, kHid1Pad, st)))
+  {
+    const float* ins[2] = {ws.f2, ws.f2};
+    float* outs[2] = {ws.g, ws.g + (size_t)B * kFeatHW * kHid1Pad};
+    if ((rc = launch_ftl2<float>(ins, kHid2, Pv, 3, 4, kFtlBlk, B, kFeatHW, outs, kHid1Pad, kHid1Pad, 2, st)))
       return rc;
+  }
   // (7) out_layer[v] 300 -> 2048, per-view weights = 2 groups — :81
   set_stage("cf_out");
   {
@@ -444,6 +446,6 @@ extern "C" int cdr_decoder_forward(const CdrWeights* w, const float* feat, int n
     set_error("cdr_decoder_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
     return CDR_ERR_WORKSPACE;
   }
-  if (int rc = launch_nchw_to_rows_f32(feat, n_images, kFeatC, kFeatHW, ws.x1, kFeatC, st)) return rc;
+  if (int rc = launch_nchw_to_rows_f32(feat, nullptr, n_images, kFeatC, kFeatHW, ws.x1, kFeatC, st)) return rc;
   return decoder_f32(w, ws.x1, n_images, ws.d1, ws.d2, ws.d3, heatmaps, st);
 }

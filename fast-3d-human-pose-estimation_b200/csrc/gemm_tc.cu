@@ -1162,23 +1162,32 @@ int tc_decoder_workspace_bytes(const TcWeights& w, int n_images, size_t* bytes) 
   return CDR_OK;
 }
 
-// NCHW fp32 latents -> pixel-major rows in the format of `out`.  kFmtF16P: the tensor scale comes
-// from the exact amax of the input (one extra pass over 0.5 MB / image).
-static int to_rows(const float* feat, int n_img, const Act& out, ScaleSlot sl, cudaStream_t st) {
+// NCHW fp32 latents (one tensor, or two whose rows are stacked: the stereo views) -> pixel-major rows
+// in the format of `out`.  kFmtF16P (single tensor only): the tensor scale comes from the exact amax
+// of the input (one extra pass over 0.5 MB / image).
+static int to_rows(const float* feat, const float* feat2, int n_img, const Act& out, ScaleSlot sl, cudaStream_t st) {
   if (out.fmt == kFmtBF16)
-    return launch_nchw_to_rows_bf16(feat, n_img, kFeatC, kFeatHW, (__nv_bfloat16*)out.p[0], kFeatC, st);
+    return launch_nchw_to_rows_bf16(feat, feat2, n_img, kFeatC, kFeatHW, (__nv_bfloat16*)out.p[0], kFeatC, st);
   if (out.fmt == kFmtTF32P)
-    return launch_nchw_to_rows_split(feat, n_img, kFeatC, kFeatHW, (float*)out.p[0], (float*)out.p[1], kFeatC, st);
+    return launch_nchw_to_rows_split(feat, feat2, n_img, kFeatC, kFeatHW, (float*)out.p[0], (float*)out.p[1], kFeatC, st);
+  CDR_CHECK_ARG(!feat2, "to_rows: the fp16-plane format takes one tensor");
   if (int rc = launch_amax_f32(feat, (long long)n_img * kFeatC * kFeatHW, sl.amax, st)) return rc;
   return launch_nchw_to_rows_f16p(feat, n_img, kFeatC, kFeatHW, out.p[0], out.p[1], kFeatC, sl.amax, sl.scale, st);
 }
-static int ftl_act(const Act& in, int in_pitch, const float* mats, int rows, int cols, int n, const Act& out,
-                   int out_pitch, int out_fill, float* amax_out, cudaStream_t st) {
-  if (in.fmt == kFmtBF16)
-    return launch_ftl<__nv_bfloat16>((const __nv_bfloat16*)in.p[0], in_pitch, mats, rows, cols, kFtlBlk, n, kFeatHW,
-                                     (__nv_bfloat16*)out.p[0], out_pitch, out_fill, st);
-  return launch_ftl_split((const float*)in.p[0], (const float*)in.p[1], in_pitch, mats, rows, cols, kFtlBlk, n,
-                          kFeatHW, (float*)out.p[0], (float*)out.p[1], out_pitch, out_fill, amax_out, st);
+// FTL of both views in one launch
+static int ftl_act2(const Act& in0, const Act& in1, int in_pitch, const float* const mats[2], int rows, int cols, int n,
+                    const Act& out0, const Act& out1, int out_pitch, int out_fill, float* amax_out, cudaStream_t st) {
+  if (in0.fmt == kFmtBF16) {
+    const __nv_bfloat16* ins[2] = {(const __nv_bfloat16*)in0.p[0], (const __nv_bfloat16*)in1.p[0]};
+    __nv_bfloat16* outs[2] = {(__nv_bfloat16*)out0.p[0], (__nv_bfloat16*)out1.p[0]};
+    return launch_ftl2<__nv_bfloat16>(ins, in_pitch, mats, rows, cols, kFtlBlk, n, kFeatHW, outs, out_pitch, out_fill, 2, st);
+  }
+  const float* ih[2] = {(const float*)in0.p[0], (const float*)in1.p[0]};
+  const float* il[2] = {(const float*)in0.p[1], (const float*)in1.p[1]};
+  float* oh[2] = {(float*)out0.p[0], (float*)out1.p[0]};
+  float* ol[2] = {(float*)out0.p[1], (float*)out1.p[1]};
+  return launch_ftl_split2(ih, il, in_pitch, mats, rows, cols, kFtlBlk, n, kFeatHW, oh, ol, out_pitch, out_fill, 2,
+                           amax_out, st);
 }
 
 // slots: x1 -> 1, d1 -> 2, d2 -> 3, d3 -> 4
@@ -1240,14 +1249,12 @@ int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r
   set_stage("pinv");
   const float* pinv[2] = {pinv_l, pinv_r};
   if (!pinv_l) {
-    if ((rc = cdr_pinv(P_l, B, pinv_rtol, ws.pinv, st))) return rc;
-    if ((rc = cdr_pinv(P_r, B, pinv_rtol, ws.pinv + (size_t)B * 12, st))) return rc;
+    if ((rc = launch_pinv2(P_l, P_r, B, pinv_rtol, ws.pinv, st))) return rc;
     pinv[0] = ws.pinv;
     pinv[1] = ws.pinv + (size_t)B * 12;
   }
   set_stage("nchw_to_rows");
-  if ((rc = to_rows(feat_l, B, ws.x0, ScaleSlot(), st))) return rc;
-  if ((rc = to_rows(feat_r, B, act_offset(ws.x0, (size_t)B * kFeatHW * kFeatC), ScaleSlot(), st))) return rc;
+  if ((rc = to_rows(feat_l, feat_r, B, ws.x0, ScaleSlot(), st))) return rc;
   set_stage("cf_conv1");
   {
     TcLaunch l{};
@@ -1258,10 +1265,9 @@ int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r
     if ((rc = launch_tc(l, st))) return rc;
   }
   set_stage("ftl_inv");
-  for (int v = 0; v < 2; ++v)
-    if ((rc = ftl_act(act_offset(ws.y1, (size_t)v * B * kFeatHW * kHid1Pad), kHid1Pad, pinv[v], 4, 3, B,
-                      act_offset(ws.z, (size_t)v * kHid2), 2 * kHid2, kHid2, nullptr, st)))
-      return rc;
+  if ((rc = ftl_act2(ws.y1, act_offset(ws.y1, (size_t)B * kFeatHW * kHid1Pad), kHid1Pad, pinv, 4, 3, B, ws.z,
+                     act_offset(ws.z, (size_t)kHid2), 2 * kHid2, kHid2, nullptr, st)))
+    return rc;
   set_stage("cf_conv2");
   {
     TcLaunch l{};
@@ -1275,10 +1281,9 @@ int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r
   }
   set_stage("ftl_fwd");
   const float* Pv[2] = {P_l, P_r};
-  for (int v = 0; v < 2; ++v)
-    if ((rc = ftl_act(ws.f2, kHid2, Pv[v], 3, 4, B, act_offset(ws.g, (size_t)v * B * kFeatHW * kHid1Pad),
-                      kHid1Pad, kHid1Pad, scaled ? slot(ws.slots, 0).amax : nullptr, st)))
-      return rc;
+  if ((rc = ftl_act2(ws.f2, ws.f2, kHid2, Pv, 3, 4, B, ws.g, act_offset(ws.g, (size_t)B * kFeatHW * kHid1Pad),
+                     kHid1Pad, kHid1Pad, scaled ? slot(ws.slots, 0).amax : nullptr, st)))
+    return rc;
   set_stage("cf_out");
   {
     TcLaunch l{};
@@ -1320,7 +1325,7 @@ int tc_decoder_forward(const TcWeights& w, const float* feat, int n_images, floa
   }
   if (ws.x1.fmt == kFmtF16P) CDR_CUDA(cudaMemsetAsync(ws.slots, 0, 2 * kNumSlots * sizeof(float), st));
   set_stage("nchw_to_rows");
-  if (int rc = to_rows(feat, n_images, ws.x1, slot(ws.slots, 1), st)) return rc;
+  if (int rc = to_rows(feat, nullptr, n_images, ws.x1, slot(ws.slots, 1), st)) return rc;
   return tc_decoder(w, ws.x1, n_images, ws.d1, ws.d2, ws.d3, ws.slots, heatmaps, st);
 }
 

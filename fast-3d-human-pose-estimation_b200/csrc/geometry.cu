@@ -13,6 +13,20 @@ __global__ void pinv_kernel(const float* __restrict__ P, int n, double rtol,
   pinv_3x4<float, float>(P + (size_t)i * 12, rtol, out + (size_t)i * 12);
 }
 
+__global__ void pinv2_kernel(const float* __restrict__ P_a, const float* __restrict__ P_b, int n, double rtol,
+                             float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * n) return;
+  const float* P = i < n ? P_a + (size_t)i * 12 : P_b + (size_t)(i - n) * 12;
+  pinv_3x4<float, float>(P, rtol, out + (size_t)i * 12);
+}
+int launch_pinv2(const float* P_a, const float* P_b, int n, double rtol, float* out, cudaStream_t st) {
+  CDR_CHECK_ARG(P_a && P_b && out && n > 0, "pinv2: bad args");
+  pinv2_kernel<<<ceil_div(2 * n, 32), 32, 0, st>>>(P_a, P_b, n, rtol, out);   // one warp per block: spread over SMs
+  CDR_LAUNCH_OK("pinv_kernel");
+  return CDR_OK;
+}
+
 // ---------------------------------------------------------------- DLT (models/cdrnet.py:151-179)
 __global__ void dlt_kernel(const float* __restrict__ P_l, const float* __restrict__ P_r,
                            const float* __restrict__ kp_l, const float* __restrict__ kp_r,

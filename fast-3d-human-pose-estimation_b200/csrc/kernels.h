@@ -31,17 +31,23 @@ struct TapGemmParams {
 int launch_tap_gemm_ffma(const TapGemmParams& p, int groups, cudaStream_t st);
 
 // layout.cu
-int launch_nchw_to_rows_f32(const float* in, int n_img, int C, int HW, float* out, int out_pitch,
+// in2 (may be NULL): a second (n_img, C, HW) tensor converted by the same launch; its rows follow in `out`
+int launch_nchw_to_rows_f32(const float* in, const float* in2, int n_img, int C, int HW, float* out, int out_pitch,
                             cudaStream_t st);
-int launch_nchw_to_rows_bf16(const float* in, int n_img, int C, int HW, __nv_bfloat16* out,
+int launch_nchw_to_rows_bf16(const float* in, const float* in2, int n_img, int C, int HW, __nv_bfloat16* out,
                              int out_pitch, cudaStream_t st);
 // fp32 hi/lo planes for the 3xTF32 tensor-core path (common.cuh: split_tf32)
-int launch_nchw_to_rows_split(const float* in, int n_img, int C, int HW, float* out_hi, float* out_lo,
+int launch_nchw_to_rows_split(const float* in, const float* in2, int n_img, int C, int HW, float* out_hi, float* out_lo,
                               int out_pitch, cudaStream_t st);
-// amax_out (optional): atomicMax of max |out| (pre-zeroed device float)
-int launch_ftl_split(const float* in_hi, const float* in_lo, int in_pitch, const float* mats, int rows, int cols,
-                     int blk, int n, int hw, float* out_hi, float* out_lo, int out_pitch, int out_fill,
-                     float* amax_out, cudaStream_t st);
+// FTL of `views` (1 or 2) tensors in one launch.  amax_out (optional): atomicMax of max |out| (pre-zeroed float)
+int launch_ftl_split2(const float* const in_hi[2], const float* const in_lo[2], int in_pitch, const float* const mats[2],
+                      int rows, int cols, int blk, int n, int hw, float* const out_hi[2], float* const out_lo[2],
+                      int out_pitch, int out_fill, int views, float* amax_out, cudaStream_t st);
+template <typename T>
+int launch_ftl2(const T* const in[2], int in_pitch, const float* const mats[2], int rows, int cols, int blk, int n,
+                int hw, T* const out[2], int out_pitch, int out_fill, int views, cudaStream_t st);
+// pinv of two (n,3,4) stacks in one launch: out[0..n) from P_a, out[n..2n) from P_b
+int launch_pinv2(const float* P_a, const float* P_b, int n, double rtol, float* out, cudaStream_t st);
 // scaled fp16 hi/lo planes for the f16x2 tensor-core path (gemm_tc.cu: kFmtF16P)
 int launch_amax_f32(const float* in, long long n, float* amax, cudaStream_t st);
 int launch_nchw_to_rows_f16p(const float* in, int n_img, int C, int HW, void* out_hi, void* out_lo, int out_pitch,

@@ -11,13 +11,14 @@ namespace cdr {
 // pixels) and the writes (along channels) are full 128-byte lines.
 template <typename TOut>
 __global__ void __launch_bounds__(256)
-nchw_to_rows_kernel(const float* __restrict__ in, int C, int HW, TOut* __restrict__ out,
-                    int out_pitch) {
+nchw_to_rows_kernel(const float* __restrict__ in, const float* __restrict__ in2, int n_first, int C, int HW,
+                    TOut* __restrict__ out, int out_pitch) {
   __shared__ float tile[32][65];
   const int c0 = blockIdx.x * 32, p0 = blockIdx.y * 64, img = blockIdx.z;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* base = img < n_first ? in + (size_t)img * C * HW : in2 + (size_t)(img - n_first) * C * HW;
   for (int c = ty; c < 32; c += 8) {
-    const float* src = in + ((size_t)img * C + c0 + c) * HW + p0;
+    const float* src = base + (size_t)(c0 + c) * HW + p0;
     if (c0 + c < C) {
       if (p0 + tx < HW) tile[c][tx] = src[tx];
       if (p0 + tx + 32 < HW) tile[c][tx + 32] = src[tx + 32];
@@ -32,33 +33,35 @@ nchw_to_rows_kernel(const float* __restrict__ in, int C, int HW, TOut* __restric
   }
 }
 
+// in2 (optional): a second (n_img, C, HW) tensor whose rows follow the first one's in `out`
 template <typename TOut>
-static int launch_nchw_to_rows(const float* in, int n_img, int C, int HW, TOut* out, int out_pitch,
+static int launch_nchw_to_rows(const float* in, const float* in2, int n_img, int C, int HW, TOut* out, int out_pitch,
                                cudaStream_t st) {
   CDR_CHECK_ARG(in && out && n_img > 0 && C > 0 && HW > 0 && out_pitch >= C, "nchw_to_rows: bad args");
-  dim3 grid(ceil_div(C, 32), ceil_div(HW, 64), n_img);
-  nchw_to_rows_kernel<TOut><<<grid, 256, 0, st>>>(in, C, HW, out, out_pitch);
+  dim3 grid(ceil_div(C, 32), ceil_div(HW, 64), in2 ? 2 * n_img : n_img);
+  nchw_to_rows_kernel<TOut><<<grid, 256, 0, st>>>(in, in2, n_img, C, HW, out, out_pitch);
   CDR_LAUNCH_OK("nchw_to_rows_kernel");
   return CDR_OK;
 }
-int launch_nchw_to_rows_f32(const float* in, int n_img, int C, int HW, float* out, int out_pitch,
+int launch_nchw_to_rows_f32(const float* in, const float* in2, int n_img, int C, int HW, float* out, int out_pitch,
                             cudaStream_t st) {
-  return launch_nchw_to_rows<float>(in, n_img, C, HW, out, out_pitch, st);
+  return launch_nchw_to_rows<float>(in, in2, n_img, C, HW, out, out_pitch, st);
 }
-int launch_nchw_to_rows_bf16(const float* in, int n_img, int C, int HW, __nv_bfloat16* out,
+int launch_nchw_to_rows_bf16(const float* in, const float* in2, int n_img, int C, int HW, __nv_bfloat16* out,
                              int out_pitch, cudaStream_t st) {
-  return launch_nchw_to_rows<__nv_bfloat16>(in, n_img, C, HW, out, out_pitch, st);
+  return launch_nchw_to_rows<__nv_bfloat16>(in, in2, n_img, C, HW, out, out_pitch, st);
 }
 
 // split-plane variant for the 3xTF32 path (common.cuh: split_tf32)
 __global__ void __launch_bounds__(256)
-nchw_to_rows_split_kernel(const float* __restrict__ in, int C, int HW, float* __restrict__ out_hi,
-                          float* __restrict__ out_lo, int out_pitch) {
+nchw_to_rows_split_kernel(const float* __restrict__ in, const float* __restrict__ in2, int n_first, int C, int HW,
+                          float* __restrict__ out_hi, float* __restrict__ out_lo, int out_pitch) {
   __shared__ float tile[32][65];
   const int c0 = blockIdx.x * 32, p0 = blockIdx.y * 64, img = blockIdx.z;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* base = img < n_first ? in + (size_t)img * C * HW : in2 + (size_t)(img - n_first) * C * HW;
   for (int c = ty; c < 32; c += 8) {
-    const float* src = in + ((size_t)img * C + c0 + c) * HW + p0;
+    const float* src = base + (size_t)(c0 + c) * HW + p0;
     if (c0 + c < C) {
       if (p0 + tx < HW) tile[c][tx] = src[tx];
       if (p0 + tx + 32 < HW) tile[c][tx + 32] = src[tx + 32];
@@ -78,11 +81,11 @@ nchw_to_rows_split_kernel(const float* __restrict__ in, int C, int HW, float* __
     }
   }
 }
-int launch_nchw_to_rows_split(const float* in, int n_img, int C, int HW, float* out_hi, float* out_lo,
+int launch_nchw_to_rows_split(const float* in, const float* in2, int n_img, int C, int HW, float* out_hi, float* out_lo,
                               int out_pitch, cudaStream_t st) {
   CDR_CHECK_ARG(in && out_hi && out_lo && n_img > 0 && C > 0 && HW > 0 && out_pitch >= C, "nchw_to_rows_split: bad args");
-  dim3 grid(ceil_div(C, 32), ceil_div(HW, 64), n_img);
-  nchw_to_rows_split_kernel<<<grid, 256, 0, st>>>(in, C, HW, out_hi, out_lo, out_pitch);
+  dim3 grid(ceil_div(C, 32), ceil_div(HW, 64), in2 ? 2 * n_img : n_img);
+  nchw_to_rows_split_kernel<<<grid, 256, 0, st>>>(in, in2, n_img, C, HW, out_hi, out_lo, out_pitch);
   CDR_LAUNCH_OK("nchw_to_rows_split_kernel");
   return CDR_OK;
 }
@@ -159,12 +162,24 @@ int launch_nchw_to_rows_f16p(const float* in, int n_img, int C, int HW, void* ou
 // "coordinate" of channel c is channel k*blk + c of the same pixel, so
 //   out[row, r*blk + c] = sum_k mats[img(row)][r][k] * in[row, k*blk + c].
 // One thread per (row, c); consecutive threads walk consecutive channels.
+// Both views in one launch: blockIdx.y = view picks (in, mats, out) from FtlViews.
+template <typename T>
+struct FtlViews {
+  const T* in[2];
+  const T* in_lo[2];
+  const float* mats[2];
+  T* out[2];
+  T* out_lo[2];
+};
 template <typename T, int ROWS, int COLS>
 __global__ void __launch_bounds__(256)
-ftl_kernel(const T* __restrict__ in, int in_pitch, const float* __restrict__ mats, int blk,
-           long long total, int hw, T* __restrict__ out, int out_pitch, int out_fill) {
+ftl_kernel(const FtlViews<T> fv, int in_pitch, int blk, long long total, int hw, int out_pitch, int out_fill) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
+  const int view = blockIdx.y;
+  const T* __restrict__ in = fv.in[view];
+  const float* __restrict__ mats = fv.mats[view];
+  T* __restrict__ out = fv.out[view];
   const long long row = idx / blk;
   const int c = (int)(idx - row * blk);
   const float* m = mats + (row / hw) * (ROWS * COLS);
@@ -184,10 +199,15 @@ ftl_kernel(const T* __restrict__ in, int in_pitch, const float* __restrict__ mat
 
 template <int ROWS, int COLS>
 __global__ void __launch_bounds__(256)
-ftl_split_kernel(const float* __restrict__ in_hi, const float* __restrict__ in_lo, int in_pitch,
-                 const float* __restrict__ mats, int blk, long long total, int hw, float* __restrict__ out_hi,
-                 float* __restrict__ out_lo, int out_pitch, int out_fill, float* __restrict__ amax_out) {
+ftl_split_kernel(const FtlViews<float> fv, int in_pitch, int blk, long long total, int hw, int out_pitch, int out_fill,
+                 float* __restrict__ amax_out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int view = blockIdx.y;
+  const float* __restrict__ in_hi = fv.in[view];
+  const float* __restrict__ in_lo = fv.in_lo[view];
+  const float* __restrict__ mats = fv.mats[view];
+  float* __restrict__ out_hi = fv.out[view];
+  float* __restrict__ out_lo = fv.out_lo[view];
   float amax = 0.f;
   if (idx < total) {
   const long long row = idx / blk;
@@ -223,16 +243,22 @@ ftl_split_kernel(const float* __restrict__ in_hi, const float* __restrict__ in_l
   }
 }
 
-int launch_ftl_split(const float* in_hi, const float* in_lo, int in_pitch, const float* mats, int rows, int cols,
-                     int blk, int n, int hw, float* out_hi, float* out_lo, int out_pitch, int out_fill,
-                     float* amax_out, cudaStream_t st) {
-  CDR_CHECK_ARG(in_hi && in_lo && mats && out_hi && out_lo && n > 0 && hw > 0 && blk > 0, "ftl_split: bad args");
+int launch_ftl_split2(const float* const in_hi[2], const float* const in_lo[2], int in_pitch, const float* const mats[2],
+                      int rows, int cols, int blk, int n, int hw, float* const out_hi[2], float* const out_lo[2],
+                      int out_pitch, int out_fill, int views, float* amax_out, cudaStream_t st) {
+  CDR_CHECK_ARG(views == 1 || views == 2, "ftl_split: 1 or 2 views");
+  FtlViews<float> fv{};
+  for (int v = 0; v < views; ++v) {
+    CDR_CHECK_ARG(in_hi[v] && in_lo[v] && mats[v] && out_hi[v] && out_lo[v], "ftl_split: bad args");
+    fv.in[v] = in_hi[v]; fv.in_lo[v] = in_lo[v]; fv.mats[v] = mats[v]; fv.out[v] = out_hi[v]; fv.out_lo[v] = out_lo[v];
+  }
+  CDR_CHECK_ARG(n > 0 && hw > 0 && blk > 0, "ftl_split: bad args");
   const long long total = (long long)n * hw * blk;
-  const unsigned grid = (unsigned)ceil_div<long long>(total, 256);
+  const dim3 grid((unsigned)ceil_div<long long>(total, 256), views);
   if (rows == 4 && cols == 3)
-    ftl_split_kernel<4, 3><<<grid, 256, 0, st>>>(in_hi, in_lo, in_pitch, mats, blk, total, hw, out_hi, out_lo, out_pitch, out_fill, amax_out);
+    ftl_split_kernel<4, 3><<<grid, 256, 0, st>>>(fv, in_pitch, blk, total, hw, out_pitch, out_fill, amax_out);
   else if (rows == 3 && cols == 4)
-    ftl_split_kernel<3, 4><<<grid, 256, 0, st>>>(in_hi, in_lo, in_pitch, mats, blk, total, hw, out_hi, out_lo, out_pitch, out_fill, amax_out);
+    ftl_split_kernel<3, 4><<<grid, 256, 0, st>>>(fv, in_pitch, blk, total, hw, out_pitch, out_fill, amax_out);
   else {
     set_error("ftl_split: only (4x3) and (3x4) matrices are supported");
     return CDR_ERR_UNSUPPORTED;
@@ -242,24 +268,41 @@ int launch_ftl_split(const float* in_hi, const float* in_lo, int in_pitch, const
 }
 
 template <typename T>
-int launch_ftl(const T* in, int in_pitch, const float* mats, int rows, int cols, int blk, int n,
-               int hw, T* out, int out_pitch, int out_fill, cudaStream_t st) {
-  CDR_CHECK_ARG(in && mats && out && n > 0 && hw > 0 && blk > 0, "cdr_ftl: bad args");
+int launch_ftl2(const T* const in[2], int in_pitch, const float* const mats[2], int rows, int cols, int blk, int n,
+                int hw, T* const out[2], int out_pitch, int out_fill, int views, cudaStream_t st) {
+  CDR_CHECK_ARG(views == 1 || views == 2, "cdr_ftl: 1 or 2 views");
+  FtlViews<T> fv{};
+  for (int v = 0; v < views; ++v) {
+    CDR_CHECK_ARG(in[v] && mats[v] && out[v], "cdr_ftl: bad args");
+    fv.in[v] = in[v]; fv.mats[v] = mats[v]; fv.out[v] = out[v];
+  }
+  CDR_CHECK_ARG(n > 0 && hw > 0 && blk > 0, "cdr_ftl: bad args");
   CDR_CHECK_ARG(in_pitch >= cols * blk && out_pitch >= rows * blk && out_fill >= rows * blk &&
                     out_fill <= out_pitch && out_fill - rows * blk <= blk,
                 "cdr_ftl: pitches too small for %dx%d blocks of %d", rows, cols, blk);
   const long long total = (long long)n * hw * blk;
-  const unsigned grid = (unsigned)ceil_div<long long>(total, 256);
+  const dim3 grid((unsigned)ceil_div<long long>(total, 256), views);
   if (rows == 4 && cols == 3)
-    ftl_kernel<T, 4, 3><<<grid, 256, 0, st>>>(in, in_pitch, mats, blk, total, hw, out, out_pitch, out_fill);
+    ftl_kernel<T, 4, 3><<<grid, 256, 0, st>>>(fv, in_pitch, blk, total, hw, out_pitch, out_fill);
   else if (rows == 3 && cols == 4)
-    ftl_kernel<T, 3, 4><<<grid, 256, 0, st>>>(in, in_pitch, mats, blk, total, hw, out, out_pitch, out_fill);
+    ftl_kernel<T, 3, 4><<<grid, 256, 0, st>>>(fv, in_pitch, blk, total, hw, out_pitch, out_fill);
   else {
     set_error("cdr_ftl: only (4x3) and (3x4) matrices are supported, got %dx%d", rows, cols);
     return CDR_ERR_UNSUPPORTED;
   }
   CDR_LAUNCH_OK("ftl_kernel");
   return CDR_OK;
+}
+template int launch_ftl2<float>(const float* const[2], int, const float* const[2], int, int, int, int, int, float* const[2], int, int, int, cudaStream_t);
+template int launch_ftl2<__nv_bfloat16>(const __nv_bfloat16* const[2], int, const float* const[2], int, int, int, int, int, __nv_bfloat16* const[2], int, int, int, cudaStream_t);
+
+template <typename T>
+int launch_ftl(const T* in, int in_pitch, const float* mats, int rows, int cols, int blk, int n,
+               int hw, T* out, int out_pitch, int out_fill, cudaStream_t st) {
+  const T* ins[2] = {in, nullptr};
+  const float* ms[2] = {mats, nullptr};
+  T* outs[2] = {out, nullptr};
+  return launch_ftl2<T>(ins, in_pitch, ms, rows, cols, blk, n, hw, outs, out_pitch, out_fill, 1, st);
 }
 template int launch_ftl<float>(const float*, int, const float*, int, int, int, int, int, float*, int, int, cudaStream_t);
 template int launch_ftl<__nv_bfloat16>(const __nv_bfloat16*, int, const float*, int, int, int, int, int, __nv_bfloat16*, int, int, cudaStream_t);

@@ -30,12 +30,17 @@ def _conv(x, sd, conv, bn, relu=True):
     return F.relu(y) if relu else y
 
 
-def decoder_bf16(sd, x, prefix="decoder."):
+def decoder_bf16(sd, x, prefix="decoder.", fused_final=False):
+    """fused_final: emulate a kernel that fuses final_layer into deconv3's epilogue (deconv3's
+    activation never rounded to bf16, fp32 1x1 weights).  Tried on B200 and rejected: 19 x 256 FMAs
+    per pixel on the CUDA cores made deconv3's epilogue 3x slower than the MMA main loop."""
     for name in ("deconv1", "deconv2", "deconv3"):
         w, b = _fold(sd, f"{prefix}{name}.0", f"{prefix}{name}.1", transposed=True)
-        x = bf(F.relu(F.conv_transpose2d(x, bf(w), b.float().double(), stride=2, padding=1)))
+        x = F.relu(F.conv_transpose2d(x, bf(w), b.float().double(), stride=2, padding=1))
+        if not (fused_final and name == "deconv3"):
+            x = bf(x)
     w, b = _fold(sd, prefix + "final_layer", None)
-    return F.conv2d(x, bf(w), b.float().double())          # heat-maps stay fp32 on the device
+    return F.conv2d(x, w if fused_final else bf(w), b.float().double())   # heat-maps stay fp32 on the device
 
 
 def head_bf16(sd, feats, proj_list, pinv_list, taps=None):

@@ -505,6 +505,56 @@ def test_bf16_head_vs_emulated_and_fp64_oracle(cuda_pkg):
     assert d3[good].max() <= 10.0 and d3[good].mean() <= 3.0
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_decoder_many_joints(cuda_pkg, precision):
+    """A joint count other than MADS's 19 (24: final layer padded to 32 columns)."""
+    n, joints = 2, 24
+    sd = synth.make_head_state_dict(seed=7, joints=joints, calibrated=True, randomize_bn=True, decoder_only=True)
+    feats = synth.make_features(n, seed=8)[0]
+    want = O.decoder(O.cast_state_dict(sd, torch.float64), feats.double()).numpy()
+    dec = cuda_pkg.PoseDecoder(synth.make_cfg(18, joints), precision=precision)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items()})
+    got = dec.cuda().eval()(feats.cuda()).cpu().numpy()
+    rel = np.abs(got - want).max() / np.abs(want).max()
+    print(f"\ndecoder [{precision}] 24 joints: rel err {rel:.2e}")
+    assert rel < (2e-5 if precision == "fp32" else 2e-2)
+
+
+def test_head_pipeline_matches_eager(cuda_pkg):
+    """HeadPipeline (bench.py's e2e path): depth-2 submit/collect over changing batches returns, per
+    batch, exactly what the eager call returns."""
+    b = 3
+    sd = synth.make_head_state_dict(seed=0, calibrated=True)
+    m = _model(cuda_pkg, sd, precision="fp32")
+    batches = []
+    for i in range(4):
+        feats = [f.pin_memory() for f in synth.make_features(b, seed=10 + i)]
+        cams = synth.make_cameras(b, seed=20 + i)
+        Ps = [torch.from_numpy(cams["P_l"]).pin_memory(), torch.from_numpy(cams["P_r"]).pin_memory()]
+        batches.append((feats, Ps))
+    gt = synth.make_gt(synth.make_cameras(b, seed=2), seed=3)
+    gtd = {k: torch.from_numpy(gt[k]).cuda() for k in ("gt3d", "gt2d_l", "gt2d_r", "vis")}
+    pipe = cuda_pkg.HeadPipeline(m, b, gt=gtd)
+    got = []
+    pipe.submit(*batches[0])
+    for i in range(1, 4):
+        pipe.submit(*batches[i])
+        _, kp, xyz, sums = pipe.collect()
+        got.append((kp[0].clone(), kp[1].clone(), xyz.clone(), sums.clone()))
+    with pytest.raises(RuntimeError):
+        pipe.submit(*batches[0]); pipe.submit(*batches[0])
+    while pipe.n_collected < pipe.n_submitted:
+        _, kp, xyz, sums = pipe.collect()
+        if len(got) < 4:
+            got.append((kp[0].clone(), kp[1].clone(), xyz.clone(), sums.clone()))
+    for (feats, Ps), (kl_h, kr_h, xyz_h, sums_h) in zip(batches, got):
+        (kl, kr), xyz = m.head([f.cuda() for f in feats], [p.cuda() for p in Ps])
+        sums = cuda_pkg.mpjpe_sums([kl, kr], xyz, gtd["gt3d"], gtd["gt2d_l"], gtd["gt2d_r"], gtd["vis"])
+        torch.cuda.synchronize()
+        assert torch.equal(kl.cpu(), kl_h) and torch.equal(kr.cpu(), kr_h) and torch.equal(xyz.cpu(), xyz_h)
+        assert torch.equal(sums.cpu(), sums_h)
+
+
 def test_head_graph_replay_matches_eager(cuda_pkg):
     """CUDA-graph capture of H2D -> head -> MPJPE -> D2H (the e2e path of bench.py): bit-identical to
     the eager call, and re-playable after the pinned inputs are refilled."""
