@@ -54,7 +54,7 @@ def launches(tag, rnd):
     idx = [i for i, r in enumerate(recs) if r[0].startswith("heat_stream")]
     step = recs[idx[-2] + 1: idx[-1] + 1] if len(idx) >= 2 else []
     lines = [f"# ncu launch list, {tag} head, B=64 — `ncu --metrics gpu__time_duration.sum --clock-control none` "
-             f"on `python bench.py --steps 2 --warmup 3 --single-precision --no-cpu-baseline --no-stream-microbench --precision {tag}`",
+             f"on `python bench.py --steps 2 --warmup 3 --single-precision --no-cpu-baseline --no-stream-microbench --no-full-pipeline --precision {tag}`",
              "# cold-cache, serialised launches: the SHARES are comparable with bench.py's live CUDA-event stage times, not the absolutes",
              "", "## totals over the whole run", "kernel,launches,total_us"]
     for n, (c, ns) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
@@ -101,7 +101,7 @@ def traffic(rnd):
     way bench.py names stages (prof_tc / prof_tf32 capture deconv1, deconv2, deconv3, final_1x1 of
     one step in launch order; prof_heat captures the streaming microbench launch)."""
     out = {}
-    for rep, key in (("prof_tc", "bf16"), ("prof_tf32", "fp32")):
+    for rep, key in (("prof_tc", "bf16"), ("prof_f16x2", "fp32"), ("prof_tf32", "tf32x3")):
         path = os.path.join(ROOT, "profiles", f"{rnd}_{rep}_raw.json")
         if not os.path.exists(path):
             continue
@@ -126,6 +126,6 @@ if __name__ == "__main__":
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
     for tag in ("bf16", "fp32"):
         launches(tag, rnd)
-    for rep in ("prof_tc", "prof_tf32", "prof_ffma", "prof_heat"):
+    for rep in ("prof_tc", "prof_f16x2", "prof_tf32", "prof_ffma", "prof_heat"):
         full(rep, rnd)
     traffic(rnd)
