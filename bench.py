@@ -374,7 +374,7 @@ def full_pipeline(args, ctx, precision):
     ours, by decree) + our head — on device-resident (B,3,256,256) image pairs.  Two encoder
     settings: torch default fp32 (cuDNN may use TF32) and bf16 autocast + channels_last."""
     import fast_3d_human_pose_estimation_b200 as pkg
-    from fast_3d_human_pose_estimation_b200 import synth
+    from fast_3d_human_pose_estimation_b200 import synth, _lib
     dev, B = ctx["dev"], args.batch
     torch.manual_seed(0)
     model = pkg.CDRNet(synth.make_cfg(101, JOINTS), precision=precision)
@@ -415,9 +415,31 @@ def full_pipeline(args, ctx, precision):
     enc_ms = timed(bf16_enc)
     out["encoder_bf16_autocast_channels_last"] = {"pairs_per_s": B / (ms / 1e3), "ms_per_step": ms,
                                                   "encoder_ms": enc_ms, "head_share": max(0.0, 1.0 - enc_ms / ms)}
+    # the Bottleneck stages on this repo's tcgen05 kernel (stem on cuDNN bf16)
+    del enc, xcl
+    torch.manual_seed(0)
+    m2 = pkg.CDRNet(synth.make_cfg(101, JOINTS), precision=precision, encoder_precision="bf16")
+    m2.load_state_dict(ctx["sd"], strict=False)
+    m2 = m2.to(dev).eval()
+    ms = timed(lambda: m2(xs, ctx["Ps"]))
+    x2 = torch.cat(xs, 0)
+    enc_ms = timed(lambda: m2._tc_encoder.rows(x2))
+    stem_ms = timed(lambda: m2._tc_encoder.stem(x2))
+    _lib.stage_timing_begin(dev)
+    m2._tc_encoder.rows(x2)
+    blocks = {}
+    for name, t in _lib.stage_timing_end():
+        blocks[name] = blocks.get(name, 0.0) + t
+    out["encoder_bf16_tcgen05"] = {"pairs_per_s": B / (ms / 1e3), "ms_per_step": ms, "encoder_ms": enc_ms,
+                                   "stem_ms_cudnn": stem_ms, "head_share": max(0.0, 1.0 - enc_ms / ms),
+                                   "encoder_tflops": 40747.7e6 * B / (enc_ms / 1e3) / 1e12,
+                                   "layer_ms": {f"layer{i + 1}": sum(v for k, v in blocks.items()
+                                                                     if k.startswith("enc_block") and lo <= int(k[9:]) < hi)
+                                                for i, (lo, hi) in enumerate(((0, 3), (3, 7), (7, 30), (30, 33)))}}
+    del m2, x2
     out["note"] = ("ResNet-101 encoder = 40.7 GF/pair on torch/cuDNN (out of scope, SURVEY §8f rank 1); head = "
                    f"{precision} kernels of this repo; images resident in HBM")
-    del model, xs, xcl
+    del model, xs
     torch.cuda.empty_cache()
     return out
 

@@ -43,6 +43,15 @@ class CdrHeadTaps(C.Structure):
     _fields_ = [(n, _vp) for n in ("pinv", "cf_cat", "cf_f", "f_out", "heatmaps")]
 
 
+class CdrEncoderBlock(C.Structure):
+    _fields_ = [("conv1", CdrConvBn), ("conv2", CdrConvBn), ("conv3", CdrConvBn), ("downsample", CdrConvBn),
+                ("planes", C.c_int), ("stride", C.c_int)]
+
+
+class CdrEncoderSpec(C.Structure):
+    _fields_ = [("num_blocks", C.c_int), ("blocks", C.POINTER(CdrEncoderBlock)), ("in_channels", C.c_int)]
+
+
 class CdrError(RuntimeError):
     pass
 
@@ -62,6 +71,14 @@ _SIGNATURES = {
     "cdr_head_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_int, C.c_int,
                                    _vp, _vp, _vp, C.POINTER(CdrHeadTaps), _vp, C.c_size_t, _vp]),
     "cdr_decoder_forward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_size_t, _vp]),
+    "cdr_head_forward_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_int, C.c_int,
+                                        _vp, _vp, _vp, C.POINTER(CdrHeadTaps), _vp, C.c_size_t, _vp]),
+    "cdr_encoder_create": (C.c_int, [C.POINTER(CdrEncoderSpec), _vp, C.POINTER(_vp)]),
+    "cdr_encoder_destroy": (C.c_int, [_vp]),
+    "cdr_encoder_workspace_bytes": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "cdr_encoder_out_shape": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                        C.POINTER(C.c_int)]),
+    "cdr_encoder_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_size_t, _vp]),
     "cdr_pinv": (C.c_int, [_vp, C.c_int, C.c_double, _vp, _vp]),
     "cdr_ftl": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
                           C.c_int, C.c_int, _vp]),

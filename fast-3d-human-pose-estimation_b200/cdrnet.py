@@ -30,7 +30,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .encoder import ResNet
+from .encoder import ResNet, TcEncoder
 
 PINV_RTOL_FP32 = 4 * float(torch.finfo(torch.float32).eps)  # torch.linalg.pinv default, (3,4) fp32
 
@@ -219,8 +219,13 @@ class CDRNet(nn.Module):
     Extra keyword ``precision`` ('fp32' parity kernels | 'bf16' tcgen05 kernels)."""
 
     def __init__(self, cfg, n_views=2, nj=19, fusion_in_dim=2048, fusion_hid_ch1=300,
-                 fusion_hid_ch2=400, precision="fp32"):
+                 fusion_hid_ch2=400, precision="fp32", encoder_precision="torch"):
+        """encoder_precision: 'torch' (default — the reference's nn.Module on torch/cuDNN, fp32) or
+        'bf16' (Bottleneck stages on libcdrhead's tcgen05 kernels, stem on cuDNN bf16)."""
         super().__init__()
+        if encoder_precision not in ("torch", "bf16"):
+            raise ValueError(f"encoder_precision must be 'torch' or 'bf16', got {encoder_precision!r}")
+        self.encoder_precision = encoder_precision
         if n_views != 2 or fusion_in_dim != 2048 or fusion_hid_ch1 != 300 or fusion_hid_ch2 != 400:
             raise NotImplementedError(
                 "libcdrhead is built for the reference's stereo configuration "
@@ -232,6 +237,7 @@ class CDRNet(nn.Module):
         self.n_views = n_views
         self.nj = nj
         self._packed = _PackedWeights(self, precision, has_fusion=True)
+        self._tc_encoder = TcEncoder(self.encoder) if encoder_precision == "bf16" else None
 
     @property
     def precision(self):
@@ -247,23 +253,30 @@ class CDRNet(nn.Module):
         self.load_state_dict({k: v for k, v in ckpt.items() if k.startswith("encoder")},
                              strict=False)
 
-    def head(self, feats, proj_list, proj_inv_list=None, taps=False, img_size=256):
+    def head(self, feats, proj_list, proj_inv_list=None, taps=False, img_size=256, feat_rows=None):
         """The hot path: encoder latents -> (pred_2ds, pred_3ds).  models/cdrnet.py:236-268.
 
         feats: list[2] of (B,2048,8,8); proj_list: list[2] of (B,3,4).  ``proj_inv_list``
         overrides the on-device pseudo-inverse.  ``taps=True`` also returns the stage
-        tensors the parity tests compare."""
+        tensors the parity tests compare.  ``feat_rows`` (instead of ``feats``): the latents as
+        bf16 pixel-major rows (2*B*64, 2048), left view first — the tcgen05 encoder's output."""
         _require_eval(self)
-        fl = _as_f32_cuda(feats[0], "features")
-        fr = _as_f32_cuda(feats[1], "features")
         pl = _as_f32_cuda(proj_list[0], "proj_list")
         pr = _as_f32_cuda(proj_list[1], "proj_list")
-        b = fl.shape[0]
-        if tuple(fl.shape) != (b, 2048, 8, 8) or fr.shape != fl.shape:
-            raise ValueError(f"expected two (B,2048,8,8) latents, got {tuple(fl.shape)} / {tuple(fr.shape)}")
+        b = pl.shape[0]
+        fl = fr = None
+        if feat_rows is not None:
+            if not (feat_rows.is_cuda and feat_rows.dtype == torch.bfloat16 and feat_rows.is_contiguous()
+                    and tuple(feat_rows.shape) == (2 * b * 64, 2048)):
+                raise ValueError("feat_rows must be a contiguous CUDA bf16 tensor of shape (2*B*64, 2048)")
+        else:
+            fl = _as_f32_cuda(feats[0], "features")
+            fr = _as_f32_cuda(feats[1], "features")
+            if tuple(fl.shape) != (b, 2048, 8, 8) or fr.shape != fl.shape:
+                raise ValueError(f"expected two (B,2048,8,8) latents, got {tuple(fl.shape)} / {tuple(fr.shape)}")
         if tuple(pl.shape) != (b, 3, 4) or tuple(pr.shape) != (b, 3, 4):
             raise ValueError(f"proj_list entries must be (B,3,4), got {tuple(pl.shape)} / {tuple(pr.shape)}")
-        dev = fl.device
+        dev = pl.device
         j = self.decoder.num_joints
         if j != self.nj:
             raise ValueError(f"nj={self.nj} but cfg.MODEL.NUM_JOINTS={j} (the reference would fail in dlt)")
@@ -292,11 +305,18 @@ class CDRNet(nn.Module):
             for k, t in tap_out.items():
                 setattr(tap_struct, k, t.data_ptr())
         with torch.cuda.device(dev):
-            _lib.check(L.cdr_head_forward(
-                handle, _lib.ptr(fl), _lib.ptr(fr), _lib.ptr(pl), _lib.ptr(pr), _lib.ptr(pil),
-                _lib.ptr(pir), PINV_RTOL_FP32, b, int(img_size), _lib.ptr(kp_l), _lib.ptr(kp_r),
-                _lib.ptr(xyz), C.byref(tap_struct) if taps else None, _lib.ptr(ws), nbytes.value,
-                _lib.current_stream_ptr(dev)))
+            if feat_rows is not None:
+                _lib.check(L.cdr_head_forward_rows(
+                    handle, _lib.ptr(feat_rows), _lib.ptr(pl), _lib.ptr(pr), _lib.ptr(pil),
+                    _lib.ptr(pir), PINV_RTOL_FP32, b, int(img_size), _lib.ptr(kp_l), _lib.ptr(kp_r),
+                    _lib.ptr(xyz), C.byref(tap_struct) if taps else None, _lib.ptr(ws), nbytes.value,
+                    _lib.current_stream_ptr(dev)))
+            else:
+                _lib.check(L.cdr_head_forward(
+                    handle, _lib.ptr(fl), _lib.ptr(fr), _lib.ptr(pl), _lib.ptr(pr), _lib.ptr(pil),
+                    _lib.ptr(pir), PINV_RTOL_FP32, b, int(img_size), _lib.ptr(kp_l), _lib.ptr(kp_r),
+                    _lib.ptr(xyz), C.byref(tap_struct) if taps else None, _lib.ptr(ws), nbytes.value,
+                    _lib.current_stream_ptr(dev)))
         if taps:
             return [kp_l, kp_r], xyz, tap_out
         return [kp_l, kp_r], xyz
@@ -306,6 +326,10 @@ class CDRNet(nn.Module):
         Returns ([kp_left, kp_right] each (B,J,2) in image pixels, xyz (B,J,3))."""
         _require_eval(self)
         img_size = int(xs[0].size(2))                             # models/cdrnet.py:229
+        if self._tc_encoder is not None and xs[0].shape[-1] == 256 and xs[0].shape[-2] == 256:
+            # both views through the tcgen05 encoder as one batch; its bf16 rows feed the head directly
+            rows, _ = self._tc_encoder.rows(torch.cat([xs[0], xs[1]], 0))
+            return self.head(None, proj_list, img_size=img_size, feat_rows=rows)
         with torch.no_grad():
             zs = [self.encoder(xs[i]) for i in range(self.n_views)]  # :231-234 (torch/cuDNN)
         return self.head(zs, proj_list, img_size=img_size)

@@ -343,7 +343,7 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
   timing_restart();
   const float scale = (float)img_size / (float)kHeat;   // models/cdrnet.py:250
   if (w->precision != CDR_PREC_FP32)
-    return tc_head_forward(w->tc, feat_l, feat_r, P_l, P_r, pinv_l, pinv_r, pinv_rtol, batch, scale,
+    return tc_head_forward(w->tc, nullptr, feat_l, feat_r, P_l, P_r, pinv_l, pinv_r, pinv_rtol, batch, scale,
                            kp2d_l, kp2d_r, xyz, taps, workspace, workspace_bytes, st);
 
   const int B = batch, N = 2 * batch, J = w->joints;
@@ -448,4 +448,71 @@ extern "C" int cdr_decoder_forward(const CdrWeights* w, const float* feat, int n
   }
   if (int rc = launch_nchw_to_rows_f32(feat, nullptr, n_images, kFeatC, kFeatHW, ws.x1, kFeatC, st)) return rc;
   return decoder_f32(w, ws.x1, n_images, ws.d1, ws.d2, ws.d3, heatmaps, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// tcgen05 encoder + head on its row-major output
+extern "C" int cdr_head_forward_rows(const CdrWeights* w, const void* feat_rows, const float* P_l, const float* P_r,
+                                     const float* pinv_l, const float* pinv_r, double pinv_rtol, int batch,
+                                     int img_size, float* kp2d_l, float* kp2d_r, float* xyz,
+                                     const CdrHeadTaps* taps, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  CDR_CHECK_ARG(w && feat_rows && P_l && P_r && kp2d_l && kp2d_r && xyz && workspace,
+                "cdr_head_forward_rows: null pointer");
+  CDR_CHECK_ARG(w->has_fusion, "cdr_head_forward_rows: weights were created without the fusion block");
+  CDR_CHECK_ARG(w->precision != CDR_PREC_FP32, "cdr_head_forward_rows: needs a tensor-core precision");
+  CDR_CHECK_ARG(batch > 0 && img_size > 0, "cdr_head_forward_rows: bad batch/img_size");
+  CDR_CHECK_ARG((pinv_l == nullptr) == (pinv_r == nullptr), "cdr_head_forward_rows: give both pseudo-inverses or neither");
+  CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)feat_rows & 15) == 0,
+                "cdr_head_forward_rows: workspace must be 256-byte, features 16-byte aligned");
+  timing_restart();
+  return tc_head_forward(w->tc, feat_rows, nullptr, nullptr, P_l, P_r, pinv_l, pinv_r, pinv_rtol, batch,
+                         (float)img_size / (float)kHeat, kp2d_l, kp2d_r, xyz, taps, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
+}
+
+struct CdrEncoder {
+  void* impl = nullptr;
+};
+
+extern "C" int cdr_encoder_create(const CdrEncoderSpec* spec, void* stream, CdrEncoder** out) {
+  CDR_CHECK_ARG(spec && out, "cdr_encoder_create: null argument");
+  CdrEncoder* e = new (std::nothrow) CdrEncoder();
+  CDR_CHECK_ARG(e, "cdr_encoder_create: out of host memory");
+  int rc = tc_encoder_create(*spec, &e->impl, (cudaStream_t)stream);
+  if (rc == CDR_OK && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+    set_error("cdr_encoder_create: packing failed: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = CDR_ERR_CUDA;
+  }
+  if (rc != CDR_OK) {
+    tc_encoder_destroy(e->impl);
+    delete e;
+    return rc;
+  }
+  *out = e;
+  return CDR_OK;
+}
+extern "C" int cdr_encoder_destroy(CdrEncoder* e) {
+  if (!e) return CDR_OK;
+  tc_encoder_destroy(e->impl);
+  delete e;
+  return CDR_OK;
+}
+extern "C" int cdr_encoder_workspace_bytes(const CdrEncoder* e, int n_images, int in_h, int in_w, size_t* bytes) {
+  CDR_CHECK_ARG(e && bytes && n_images > 0 && in_h > 0 && in_w > 0, "cdr_encoder_workspace_bytes: bad args");
+  return tc_encoder_workspace_bytes(e->impl, n_images, in_h, in_w, bytes);
+}
+extern "C" int cdr_encoder_out_shape(const CdrEncoder* e, int in_h, int in_w, int* out_h, int* out_w, int* out_c) {
+  CDR_CHECK_ARG(e && out_h && out_w && out_c, "cdr_encoder_out_shape: bad args");
+  return tc_encoder_out_shape(e->impl, in_h, in_w, out_h, out_w, out_c);
+}
+extern "C" int cdr_encoder_forward(const CdrEncoder* e, const void* x_nhwc_bf16, int n_images, int in_h, int in_w,
+                                   void* out_rows_bf16, void* workspace, size_t workspace_bytes, void* stream) {
+  CDR_CHECK_ARG(e && x_nhwc_bf16 && out_rows_bf16 && workspace && n_images > 0, "cdr_encoder_forward: bad args");
+  CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)x_nhwc_bf16 & 15) == 0 &&
+                    ((uintptr_t)out_rows_bf16 & 15) == 0,
+                "cdr_encoder_forward: workspace must be 256-byte, tensors 16-byte aligned");
+  timing_restart();
+  return tc_encoder_forward(e->impl, x_nhwc_bf16, n_images, in_h, in_w, out_rows_bf16, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
 }

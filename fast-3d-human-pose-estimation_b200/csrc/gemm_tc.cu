@@ -26,6 +26,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
+#include <type_traits>
 
 #include "ptx.cuh"
 #include "tc_api.h"
@@ -62,7 +63,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 // dims[0] innermost (contiguous); strides in elements for dims 1..rank-1; fmt = ActFmt of the tensor
 static int make_tmap(CUtensorMap* map, const void* base, int fmt, int rank, const uint64_t* dims,
-                     const uint64_t* strides_elems, const uint32_t* box) {
+                     const uint64_t* strides_elems, const uint32_t* box, const uint32_t* elem_strides = nullptr) {
   const int elem_bytes = fmt_elem(fmt);
   const CUtensorMapDataType dtype = fmt == kFmtBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                     : fmt == kFmtTF32P ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
@@ -77,7 +78,7 @@ static int make_tmap(CUtensorMap* map, const void* base, int fmt, int rank, cons
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     if (i > 0) gstr[i - 1] = strides_elems[i - 1] * (uint64_t)elem_bytes;
   }
   CUresult r = enc(map, dtype, (cuuint32_t)rank, const_cast<void*>(base),
@@ -115,6 +116,7 @@ constexpr int kStageBufBytes = 32 * 128;         // TMA-store staging per epilog
 //                ITS producer with atomicMax), so nothing can overflow fp16 and one layer of bound
 //                looseness (~2^7) is far inside the format's 2^27 full-precision window.
 enum TcKind { kKindBF16 = 0, kKindTF32X3 = 1, kKindF16X2 = 2 };
+enum TapMode { kTapNone = 0, kTapDeconv = 1, kTapConv3 = 2 };
 template <int KIND> struct KindTraits;
 template <> struct KindTraits<kKindBF16>   { static constexpr int kElem = 2, kBK = 64, kPlanes = 1, kFmt = kFmtBF16; };
 template <> struct KindTraits<kKindTF32X3> { static constexpr int kElem = 4, kBK = 32, kPlanes = 2, kFmt = kFmtTF32P; };
@@ -134,7 +136,7 @@ struct TcCfg {
   static constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
   // 16-bit row-major outputs leave through swizzled smem staging + TMA tensor stores (full 128-byte
   // lines, issued by one lane, asynchronous) instead of 32 scattered 16-byte stores per warp instruction.
-  static constexpr bool kTmaStore = BN >= 128 && OFMT != kFmtTF32P;
+  static constexpr bool kTmaStore = BN >= 64 && OFMT != kFmtTF32P;
   static constexpr int kStagingBytes = kTmaStore ? kEpiWarps * kStageBufBytes : 0;
   static constexpr int kStagesFit = (kSmemBudget - kStagingBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
@@ -153,7 +155,10 @@ struct TcGemmParams {
   int n_img, H, W;        // pixel grid of the A operand
   int cin;                // K per tap
   int ntaps;              // 1 or 4
-  int a4d;                // 1: A through the 4-D NHWC map (transposed conv), 0: 2-D (rows, channels)
+  int a4d;                // 1: A through the 4-D NHWC map (shifted / strided taps), 0: 2-D (rows, channels)
+  int tap_mode;           // kTapNone: 1 tap; kTapDeconv: 4 taps of output phase g; kTapConv3: 9 taps (3x3, pad 1)
+  int stride;             // 4-D A: input pixel = stride * output pixel + tap shift (map carries the element stride)
+  int has_res;            // residual tensor (same row layout as C, bf16) added before the ReLU (TMA-store path)
   int box_rows, box_imgs; // 4-D box: W x box_rows x box_imgs pixels = 128
   int groups;             // phases (deconv) or independent problems stacked along rows
   int a_group_rows;       // 2-D A: row offset per group
@@ -189,7 +194,7 @@ struct EpiScale {          // per-thread epilogue constants of the scaled format
 template <int KIND>
 __device__ __forceinline__ void finish_slab(const TcGemmParams& p, const float (&acc)[32], float (&v)[32], int n0c,
                                             const float* __restrict__ bias, const float* __restrict__ wsi,
-                                            const EpiScale& es) {
+                                            const EpiScale& es, bool relu) {
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
     float x[4] = {acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]};
@@ -203,7 +208,7 @@ __device__ __forceinline__ void finish_slab(const TcGemmParams& p, const float (
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      if (p.relu) x[e] = fmaxf(x[e], 0.f);
+      if (relu) x[e] = fmaxf(x[e], 0.f);
       v[4 * j4 + e] = (n0c + 4 * j4 + e < p.n) ? x[e] : 0.f;
     }
   }
@@ -240,7 +245,7 @@ __device__ __forceinline__ void store_slab(const TcGemmParams& p, const float (&
                                            size_t orow, int img, int pix, int HW, const float* __restrict__ bias,
                                            const float* __restrict__ wsi, EpiScale& es) {
   float v[32];
-  finish_slab<KIND>(p, acc, v, n0c, bias, wsi, es);
+  finish_slab<KIND>(p, acc, v, n0c, bias, wsi, es, p.relu != 0);
   if (!row_ok) return;
   if (p.out_mode == kOutPlanar) {
     float* __restrict__ C = reinterpret_cast<float*>(p.C);
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(TcCfg<BN, KIND, OFMT>::kThreads, 1)
 tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
                    const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c_lo,
-                   const TcGemmParams p) {
+                   const __grid_constant__ CUtensorMap tmap_r, const TcGemmParams p) {
   using Cfg = TcCfg<BN, KIND, OFMT>;
   constexpr int S = Cfg::kStages;
   constexpr int kTcBK = Cfg::kBK;
@@ -342,6 +347,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint64_t* chunk_full = bars + 2 * S + 4;    // [2]  split kinds: main-term chunk accumulator
   uint64_t* chunk_empty = bars + 2 * S + 6;   // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
+  uint64_t* res_bar = bars + 2 * S + 9;       // [kEpiWarps]  residual tile landed in the warp's staging buffer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -367,6 +373,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       ptx::mbar_init(&chunk_full[a], 1);
       ptx::mbar_init(&chunk_empty[a], kEpiWarps);
     }
+    for (int w = 0; w < kEpiWarps; ++w) ptx::mbar_init(&res_bar[w], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_base_slot);
@@ -400,9 +407,15 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           const int tap = kb / kb_per_tap;
           const int k0 = (kb - tap * kb_per_tap) * kTcBK;
           if (p.a4d) {
-            const int dy = py - (tap >> 1), dx = px - (tap & 1);
-            ptx::tma_load_4d(stage_a(s, 0), &tmap_a, &full[s], k0, dx, y0 + dy, img0);
-            if (kSplit) ptx::tma_load_4d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, dx, y0 + dy, img0);
+            int dy = 0, dx = 0;
+            if (p.tap_mode == kTapDeconv) {
+              dy = py - (tap >> 1); dx = px - (tap & 1);
+            } else if (p.tap_mode == kTapConv3) {
+              dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1;
+            }
+            const int ys = p.stride * y0 + dy;
+            ptx::tma_load_4d(stage_a(s, 0), &tmap_a, &full[s], k0, dx, ys, img0);
+            if (kSplit) ptx::tma_load_4d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, dx, ys, img0);
           } else {
             ptx::tma_load_2d(stage_a(s, 0), &tmap_a, &full[s], k0, g * p.a_group_rows + m0);
             if (kSplit) ptx::tma_load_2d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, g * p.a_group_rows + m0);
@@ -481,7 +494,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int ew = warp - 2;                       // epilogue warp index
     const int cb0 = (ew >> 2) * kCols;             // first tile column owned by this warp
     uint8_t* stage = staging + (size_t)ew * kStageBufBytes;
-    uint32_t tl = 0, ch = 0;
+    uint32_t tl = 0, ch = 0, res_phase = 0;
     EpiScale es;
     if constexpr (KIND == kKindF16X2) es.a_inv = 1.f / __ldg(p.scale_in);   // powers of two: exact
     if constexpr (OFMT == kFmtF16P) {
@@ -522,7 +535,8 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
 
       // one finished 32-column slab (fp32, scale/bias/ReLU still to apply) -> its destination
-      auto emit = [&](const float (&a32)[32], int c, uint32_t (&wh)[32], uint32_t (&wl)[32]) {
+      auto emit = [&](const float (&a32)[32], int c, auto half_c, uint32_t (&wh)[32], uint32_t (&wl)[32]) {
+        constexpr int half = decltype(half_c)::value;     // which 32-column half of a 64-column store block
         // c = column inside the warp's range; TMA path gathers two slabs (64 columns) per store
         if (!use_tma) {
           store_slab<KIND, OFMT>(p, a32, n0 + c, g, row_ok, orow, img, pix, HW, bias, wsi, es);
@@ -530,8 +544,26 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         if constexpr (Cfg::kTmaStore) {
           float v[32];
-          finish_slab<KIND>(p, a32, v, n0 + c, bias, wsi, es);
-          const int half = (c >> 5) & 1;
+          const bool res = p.has_res && (n0 + c - 32 * half) < p.c_fill;
+          finish_slab<KIND>(p, a32, v, n0 + c, bias, wsi, es, p.relu != 0 && !res);
+          if (res) {
+            // the residual block (bf16, swizzled like the store) is in the staging buffer: add, then ReLU
+            const uint32_t rbase = ptx::smem_u32(stage) + (uint32_t)lane * 128u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+              ptx::ld_shared_v4(rbase + (uint32_t)(((half * 4 + j) ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[8 * j + 2 * e] += __uint_as_float(w[e] << 16);
+                v[8 * j + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+          }
           uint32_t h16[16], l16[16];
           encode_slab<OFMT>(v, h16, l16, row_ok, es);
 #pragma unroll
@@ -555,6 +587,16 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         uint32_t wh[32], wl[32];
 #pragma unroll 1
         for (int c = 0; c < kCols; c += 64) {
+          bool res_blk = false;
+          if constexpr (Cfg::kTmaStore) {
+            // residual tile of this 64-column block -> the warp's staging buffer, overlapped with the TMEM loads
+            res_blk = use_tma && p.has_res && (n0 + c) < p.c_fill;
+            if (res_blk && lane == 0) {
+              ptx::bulk_wait_read0();               // the previous store has finished reading the buffer
+              ptx::mbar_arrive_expect_tx(&res_bar[ew], kStageBufBytes);
+              ptx::tma_load_3d(stage, &tmap_r, &res_bar[ew], n0 + c, sc.m, sc.g);
+            }
+          }
           // 64 columns per TMEM round trip (one wait for two loads) when the warp owns that many
           uint32_t r0[32], r1[32];
           ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(acc * BN + cb0 + c), r0);
@@ -566,14 +608,18 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
           }
+          if (res_blk) {
+            ptx::mbar_wait(&res_bar[ew], res_phase);
+            res_phase ^= 1u;
+          }
           float a32[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) a32[j] = __uint_as_float(r0[j]);
-          emit(a32, c, wh, wl);
+          emit(a32, c, std::integral_constant<int, 0>{}, wh, wl);
           if (kCols >= 64) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) a32[j] = __uint_as_float(r1[j]);
-            emit(a32, c + 32, wh, wl);
+            emit(a32, c + 32, std::integral_constant<int, 1>{}, wh, wl);
           }
         }
       } else {
@@ -615,11 +661,16 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
         uint32_t wh[32], wl[32];
 #pragma unroll
-        for (int c = 0; c < kCols; c += 32) {
+        for (int c = 0; c < kCols; c += 64) {
           float a32[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) a32[j] = sum[c + j];
-          emit(a32, c, wh, wl);
+          emit(a32, c, std::integral_constant<int, 0>{}, wh, wl);
+          if (kCols >= 64) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a32[j] = sum[(c + 32) % kCols + j];
+            emit(a32, c + 32, std::integral_constant<int, 1>{}, wh, wl);
+          }
         }
       }
     }
@@ -703,6 +754,11 @@ struct TcLaunch {
   int c_pitch, c_fill, relu, out_mode;
   ScaleSlot in_slot, out_slot;   // kFmtF16P tensors
   const float* amax_in;          // overrides in_slot.amax (input stored in another format)
+  // encoder convs: H, W above are the OUTPUT pixel grid; the input grid is (stride*H, stride*W)
+  int conv3;                     // 3x3, pad 1 (9 taps)
+  int stride;                    // 0/1 or 2
+  const void* res;               // residual rows (bf16, n channels, pitch res_pitch) added before the ReLU
+  int res_pitch;
 };
 
 template <int BN, int KIND, int OFMT>
@@ -721,10 +777,15 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
   const int HW = l.H * l.W;
   p.M = l.n_img * HW;
   p.n_img = l.n_img; p.H = l.H; p.W = l.W; p.cin = l.cin;
-  p.ntaps = l.deconv ? 4 : 1;
-  p.a4d = l.deconv;
+  const int stride = l.stride > 1 ? l.stride : 1;
+  const bool a4d = l.deconv || l.conv3 || stride > 1;
+  p.tap_mode = l.deconv ? kTapDeconv : l.conv3 ? kTapConv3 : kTapNone;
+  p.ntaps = l.deconv ? 4 : l.conv3 ? 9 : 1;
+  p.a4d = a4d;
+  p.stride = stride;
+  p.has_res = l.res != nullptr;
   p.groups = l.groups;
-  p.a_group_rows = l.deconv ? 0 : p.M;
+  p.a_group_rows = a4d ? 0 : p.M;
   p.b_group_rows = l.b_group_rows;
   p.n_tiles = l.layer->n_pad / BN;
   p.n = l.n;
@@ -754,17 +815,21 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
 
   CUtensorMap tmap_a[2];
   for (int pl = 0; pl < KindTraits<KIND>::kPlanes; ++pl) {
-    if (l.deconv) {
+    if (a4d) {
       CDR_CHECK_ARG(l.W <= kTcBM && kTcBM % l.W == 0, "tap_gemm_tc: W=%d must divide 128", l.W);
       int rows = kTcBM / l.W;
       if (rows > l.H) rows = l.H;
       const int imgs = kTcBM / (l.W * rows);
-      CDR_CHECK_ARG(l.H % rows == 0 && l.cin % kBK == 0, "tap_gemm_tc: unsupported deconv geometry");
+      CDR_CHECK_ARG(l.H % rows == 0 && l.cin % kBK == 0 && stride * l.W <= 256 && stride * rows <= 256,
+                    "tap_gemm_tc: unsupported tap-conv geometry");
       p.box_rows = rows; p.box_imgs = imgs;
-      const uint64_t dims[4] = {(uint64_t)l.cin, (uint64_t)l.W, (uint64_t)l.H, (uint64_t)l.n_img};
-      const uint64_t strides[3] = {(uint64_t)l.a_pitch, (uint64_t)l.a_pitch * l.W, (uint64_t)l.a_pitch * HW};
-      const uint32_t box[4] = {(uint32_t)kBK, (uint32_t)l.W, (uint32_t)rows, (uint32_t)imgs};
-      if (int rc = make_tmap(&tmap_a[pl], l.A.p[pl], kAFmt, 4, dims, strides, box)) return rc;
+      const uint64_t iw = (uint64_t)stride * l.W, ih = (uint64_t)stride * l.H;      // input pixel grid
+      const uint64_t dims[4] = {(uint64_t)l.cin, iw, ih, (uint64_t)l.n_img};
+      const uint64_t strides[3] = {(uint64_t)l.a_pitch, (uint64_t)l.a_pitch * iw, (uint64_t)l.a_pitch * iw * ih};
+      // a strided box spans stride*count input pixels and the TMA unit keeps every stride-th of them
+      const uint32_t box[4] = {(uint32_t)kBK, (uint32_t)(stride * l.W), (uint32_t)(stride * rows), (uint32_t)imgs};
+      const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+      if (int rc = make_tmap(&tmap_a[pl], l.A.p[pl], kAFmt, 4, dims, strides, box, estr)) return rc;
     } else {
       const uint64_t dims[2] = {(uint64_t)l.cin, (uint64_t)l.a_rows_total};
       const uint64_t strides[1] = {(uint64_t)l.a_pitch};
@@ -797,9 +862,20 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
     }
     if (fmt_planes(OFMT) == 1) tmap_c[1] = tmap_c[0];
   }
+  CUtensorMap tmap_r = tmap_a[0];
+  if (l.res) {
+    CDR_CHECK_ARG(Cfg::kTmaStore && KIND == kKindBF16 && OFMT == kFmtBF16 && l.out_mode == kOutRows && l.groups == 1,
+                  "tap_gemm_tc: the residual add needs the bf16 TMA-store epilogue");
+    CDR_CHECK_ARG(((uintptr_t)l.res & 15) == 0 && (l.res_pitch * 2) % 16 == 0, "tap_gemm_tc: residual alignment");
+    const uint64_t dims[3] = {(uint64_t)l.c_fill, (uint64_t)p.M, 1};
+    const uint64_t strides[2] = {(uint64_t)l.res_pitch, (uint64_t)p.M * l.res_pitch};
+    const uint32_t box[3] = {64, 32, 1};
+    if (int rc = make_tmap(&tmap_r, l.res, kFmtBF16, 3, dims, strides, box)) return rc;
+  }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   tap_gemm_tc_kernel<BN, KIND, OFMT><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(
-      tmap_a[0], tmap_a[1], l.layer->map[0], l.layer->map[KindTraits<KIND>::kPlanes - 1], tmap_c[0], tmap_c[1], p);
+      tmap_a[0], tmap_a[1], l.layer->map[0], l.layer->map[KindTraits<KIND>::kPlanes - 1], tmap_c[0], tmap_c[1], tmap_r,
+      p);
   CDR_LAUNCH_OK("tap_gemm_tc_kernel");
   return CDR_OK;
 }
@@ -810,6 +886,7 @@ static int launch_tc(const TcLaunch& l, cudaStream_t st) {
   if (kind == kKindBF16 && ofmt == kFmtBF16) {
     if (bn == 256) return launch_tc_t<256, kKindBF16, kFmtBF16>(l, st);
     if (bn == 128) return launch_tc_t<128, kKindBF16, kFmtBF16>(l, st);
+    if (bn == 64) return launch_tc_t<64, kKindBF16, kFmtBF16>(l, st);
     if (bn == 32) return launch_tc_t<32, kKindBF16, kFmtBF16>(l, st);
   } else if (kind == kKindTF32X3 && ofmt == kFmtTF32P) {
     if (bn == 128) return launch_tc_t<128, kKindTF32X3, kFmtTF32P>(l, st);
@@ -1231,7 +1308,26 @@ static int tap_to_f32(float* dst, const Act& src, const float* scale, long long 
   return CDR_OK;
 }
 
-int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r, const float* P_l,
+// encoder output (bf16 rows) -> the fusion block's fp32 hi/lo planes: a bf16 value is a tf32 value, lo = 0
+__global__ void bf16_rows_to_tf32p_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ hi,
+                                          float* __restrict__ lo, long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 q = reinterpret_cast<const uint4*>(in)[i];
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+  float4 a, b;
+  a.x = __uint_as_float(w[0] << 16); a.y = __uint_as_float(w[0] & 0xffff0000u);
+  a.z = __uint_as_float(w[1] << 16); a.w = __uint_as_float(w[1] & 0xffff0000u);
+  b.x = __uint_as_float(w[2] << 16); b.y = __uint_as_float(w[2] & 0xffff0000u);
+  b.z = __uint_as_float(w[3] << 16); b.w = __uint_as_float(w[3] & 0xffff0000u);
+  reinterpret_cast<float4*>(hi)[2 * i] = a;
+  reinterpret_cast<float4*>(hi)[2 * i + 1] = b;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  reinterpret_cast<float4*>(lo)[2 * i] = z;
+  reinterpret_cast<float4*>(lo)[2 * i + 1] = z;
+}
+
+int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat_l, const float* feat_r, const float* P_l,
                     const float* P_r, const float* pinv_l, const float* pinv_r, double pinv_rtol,
                     int batch, float scale, float* kp2d_l, float* kp2d_r, float* xyz,
                     const CdrHeadTaps* taps, void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -1253,12 +1349,26 @@ int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r
     pinv[0] = ws.pinv;
     pinv[1] = ws.pinv + (size_t)B * 12;
   }
-  set_stage("nchw_to_rows");
-  if ((rc = to_rows(feat_l, feat_r, B, ws.x0, ScaleSlot(), st))) return rc;
+  Act x0 = ws.x0;
+  if (feat_rows) {
+    // latents already pixel-major bf16 rows, views stacked (the tcgen05 encoder's output layout)
+    if (x0.fmt == kFmtBF16) {
+      x0.p[0] = const_cast<void*>(feat_rows);
+    } else {
+      set_stage("rows_to_planes");
+      const long long n8 = (long long)N * kFeatHW * kFeatC / 8;
+      bf16_rows_to_tf32p_kernel<<<(unsigned)ceil_div<long long>(n8, 256), 256, 0, st>>>(
+          (const __nv_bfloat16*)feat_rows, (float*)x0.p[0], (float*)x0.p[1], n8);
+      CDR_LAUNCH_OK("bf16_rows_to_tf32p_kernel");
+    }
+  } else {
+    set_stage("nchw_to_rows");
+    if ((rc = to_rows(feat_l, feat_r, B, ws.x0, ScaleSlot(), st))) return rc;
+  }
   set_stage("cf_conv1");
   {
     TcLaunch l{};
-    l.A = ws.x0; l.a_pitch = kFeatC; l.n_img = N; l.H = l.W = 8; l.cin = kFeatC; l.groups = 1;
+    l.A = x0; l.a_pitch = kFeatC; l.n_img = N; l.H = l.W = 8; l.cin = kFeatC; l.groups = 1;
     l.a_rows_total = (long long)N * kFeatHW;
     l.layer = &pk->cf1; l.n = kHid1;
     l.C = ws.y1; l.c_pitch = kHid1Pad; l.c_fill = kHid1Pad; l.relu = 1; l.out_mode = kOutRows;
@@ -1327,6 +1437,214 @@ int tc_decoder_forward(const TcWeights& w, const float* feat, int n_images, floa
   set_stage("nchw_to_rows");
   if (int rc = to_rows(feat, nullptr, n_images, ws.x1, slot(ws.slots, 1), st)) return rc;
   return tc_decoder(w, ws.x1, n_images, ws.d1, ws.d2, ws.d3, ws.slots, heatmaps, st);
+}
+
+
+// ==========================================================================================
+// ResNet bottleneck encoder on the same tap-GEMM kernel (reference
+// models/encoder.py:38-131).  bf16 activations as pixel-major rows, BN folded into bf16 weights,
+// fp32 accumulation; per Bottleneck: 1x1 (+ReLU) -> 3x3 stride s as 9 shifted TMA taps (+ReLU) ->
+// 1x1 with the residual (identity, or the 1x1 stride-s downsample conv) added in the epilogue
+// (+ReLU).  The stride-2 convs read their input through tensor maps with element stride 2.
+// (Cout,Cin,kh,kw) -> [n_pad][tap*Cin + ci], tap = ky*kw + kx
+__global__ void pack_conv_tc_kernel(CdrConvBn s, int cout, int cin, int taps, int n_pad, __nv_bfloat16* __restrict__ w,
+                                    float* __restrict__ bias_out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n_pad) bias_out[idx] = idx < cout ? tc_folded_bias(s, (int)idx) : 0.f;
+  const long long K = (long long)taps * cin;
+  if (idx >= (long long)n_pad * K) return;
+  const int n = (int)(idx / K), kk = (int)(idx % K);
+  const int tap = kk / cin, ci = kk - tap * cin;
+  float v = 0.f;
+  if (n < cout) v = (float)((double)s.weight[((size_t)n * cin + ci) * taps + tap] * tc_bn_scale(s, n));
+  w[idx] = __float2bfloat16_rn(v);
+}
+
+struct EncBlock {
+  TcLayer c1, c2, c3, ds;
+  int cin = 0, planes = 0, stride = 1, has_ds = 0;
+};
+struct EncPack {
+  void* pool = nullptr;
+  int n_blocks = 0, in_channels = 0, out_channels = 0, total_stride = 1;
+  EncBlock* blocks = nullptr;
+};
+
+static int enc_bn(int n) { return n >= 256 ? 256 : n >= 128 ? 128 : 64; }
+
+static size_t plan_encoder(EncPack& e, const CdrEncoderSpec& spec, void* base) {
+  Bump1K b(base);
+  int cin = spec.in_channels;
+  for (int i = 0; i < spec.num_blocks; ++i) {
+    const CdrEncoderBlock& sb = spec.blocks[i];
+    EncBlock& blk = e.blocks[i];
+    blk.cin = cin; blk.planes = sb.planes; blk.stride = sb.stride; blk.has_ds = sb.downsample.weight != nullptr;
+    const int p = sb.planes, o = 4 * sb.planes;
+    plan_layer(blk.c1, b, kKindBF16, p, cin, cin, enc_bn(p), p, p, false);
+    plan_layer(blk.c2, b, kKindBF16, p, 9 * p, 9 * p, enc_bn(p), p, p, false);
+    plan_layer(blk.c3, b, kKindBF16, o, p, p, enc_bn(o), o, o, false);
+    if (blk.has_ds) plan_layer(blk.ds, b, kKindBF16, o, cin, cin, enc_bn(o), o, o, false);
+    cin = o;
+  }
+  return b.off;
+}
+
+int tc_encoder_create(const CdrEncoderSpec& spec, void** out, cudaStream_t st) {
+  CDR_CHECK_ARG(spec.num_blocks > 0 && spec.blocks && spec.in_channels > 0 && spec.in_channels % 64 == 0,
+                "cdr_encoder_create: bad spec");
+  int cin = spec.in_channels, total_stride = 1;
+  for (int i = 0; i < spec.num_blocks; ++i) {
+    const CdrEncoderBlock& sb = spec.blocks[i];
+    CDR_CHECK_ARG(sb.planes >= 64 && sb.planes % 64 == 0 && (sb.stride == 1 || sb.stride == 2),
+                  "cdr_encoder_create: block %d: planes must be a multiple of 64, stride 1 or 2", i);
+    const CdrConvBn* cs[3] = {&sb.conv1, &sb.conv2, &sb.conv3};
+    for (const CdrConvBn* c : cs)
+      CDR_CHECK_ARG(c->weight && c->bn_weight && c->bn_bias && c->bn_mean && c->bn_var,
+                    "cdr_encoder_create: block %d: missing conv / BN tensor", i);
+    const bool need_ds = sb.stride != 1 || cin != 4 * sb.planes;
+    CDR_CHECK_ARG(need_ds == (sb.downsample.weight != nullptr),
+                  "cdr_encoder_create: block %d: downsample present iff stride != 1 or cin != 4*planes", i);
+    cin = 4 * sb.planes;
+    total_stride *= sb.stride;
+  }
+  EncPack* e = new EncPack();
+  e->n_blocks = spec.num_blocks;
+  e->in_channels = spec.in_channels;
+  e->out_channels = cin;
+  e->total_stride = total_stride;
+  e->blocks = new EncBlock[spec.num_blocks];
+  *out = e;
+  const size_t bytes = plan_encoder(*e, spec, nullptr);
+  CDR_CUDA(cudaMalloc(&e->pool, bytes));
+  plan_encoder(*e, spec, e->pool);
+  auto pack = [&](const CdrConvBn& s, TcLayer& L, int cout, int cin_l, int taps) -> int {
+    const long long total = (long long)L.n_pad * taps * cin_l;
+    pack_conv_tc_kernel<<<(unsigned)ceil_div<long long>(total, 256), 256, 0, st>>>(s, cout, cin_l, taps, L.n_pad,
+                                                                                    (__nv_bfloat16*)L.w[0], L.bias);
+    CDR_LAUNCH_OK("pack_conv_tc_kernel");
+    return layer_maps(L);
+  };
+  for (int i = 0; i < spec.num_blocks; ++i) {
+    const CdrEncoderBlock& sb = spec.blocks[i];
+    EncBlock& blk = e->blocks[i];
+    int rc;
+    if ((rc = pack(sb.conv1, blk.c1, blk.planes, blk.cin, 1))) return rc;
+    if ((rc = pack(sb.conv2, blk.c2, blk.planes, blk.planes, 9))) return rc;
+    if ((rc = pack(sb.conv3, blk.c3, 4 * blk.planes, blk.planes, 1))) return rc;
+    if (blk.has_ds && (rc = pack(sb.downsample, blk.ds, 4 * blk.planes, blk.cin, 1))) return rc;
+  }
+  return CDR_OK;
+}
+
+void tc_encoder_destroy(void* enc) {
+  EncPack* e = (EncPack*)enc;
+  if (!e) return;
+  if (e->pool) cudaFree(e->pool);
+  delete[] e->blocks;
+  delete e;
+}
+
+struct EncWs {
+  __nv_bfloat16 *x[2], *t1, *t2, *r;
+  size_t bytes;
+};
+static EncWs plan_enc_ws(const EncPack& e, void* base, int n, int h, int w) {
+  size_t mx = 0, mt1 = 0, mt2 = 0, mr = 0;
+  int H = h, W = w;
+  for (int i = 0; i < e.n_blocks; ++i) {
+    const EncBlock& b = e.blocks[i];
+    const size_t m_in = (size_t)n * H * W;
+    H /= b.stride; W /= b.stride;
+    const size_t m_out = (size_t)n * H * W;
+    mt1 = m_in * b.planes > mt1 ? m_in * b.planes : mt1;
+    mt2 = m_out * b.planes > mt2 ? m_out * b.planes : mt2;
+    if (b.has_ds) mr = m_out * 4 * b.planes > mr ? m_out * 4 * b.planes : mr;
+    if (i + 1 < e.n_blocks) mx = m_out * 4 * b.planes > mx ? m_out * 4 * b.planes : mx;
+  }
+  Bump1K bp(base);
+  EncWs ws;
+  ws.x[0] = (__nv_bfloat16*)bp.take(mx * 2);
+  ws.x[1] = (__nv_bfloat16*)bp.take(mx * 2);
+  ws.t1 = (__nv_bfloat16*)bp.take(mt1 * 2);
+  ws.t2 = (__nv_bfloat16*)bp.take(mt2 * 2);
+  ws.r = (__nv_bfloat16*)bp.take(mr * 2);
+  ws.bytes = bp.off;
+  return ws;
+}
+
+static int enc_check_grid(const EncPack& e, int h, int w) {
+  int H = h, W = w;
+  for (int i = 0; i < e.n_blocks; ++i) {
+    const int s = e.blocks[i].stride;
+    CDR_CHECK_ARG(H % s == 0 && W % s == 0, "cdr_encoder: %dx%d grid is not divisible by the strides", h, w);
+    H /= s; W /= s;
+    CDR_CHECK_ARG(W >= 8 && W <= 128 && (W & (W - 1)) == 0, "cdr_encoder: feature-map width %d (block %d) must be a "
+                  "power of two in 8..128", W, i);
+    const int rows = 128 / W < H ? 128 / W : H;
+    CDR_CHECK_ARG(H % rows == 0 && (128 % (W * rows)) == 0, "cdr_encoder: feature map %dx%d (block %d) does not tile", H, W, i);
+  }
+  return CDR_OK;
+}
+
+int tc_encoder_workspace_bytes(const void* enc, int n, int h, int w, size_t* bytes) {
+  const EncPack& e = *(const EncPack*)enc;
+  if (int rc = enc_check_grid(e, h, w)) return rc;
+  *bytes = plan_enc_ws(e, nullptr, n, h, w).bytes;
+  return CDR_OK;
+}
+
+int tc_encoder_out_shape(const void* enc, int h, int w, int* oh, int* ow, int* oc) {
+  const EncPack& e = *(const EncPack*)enc;
+  *oh = h / e.total_stride; *ow = w / e.total_stride; *oc = e.out_channels;
+  return CDR_OK;
+}
+
+static int enc_conv(const TcLayer& L, const __nv_bfloat16* in, int cin, int n, int H, int W, int conv3, int stride,
+                    __nv_bfloat16* out, int cout, int relu, const __nv_bfloat16* res, cudaStream_t st) {
+  TcLaunch l{};
+  l.A.p[0] = (void*)in; l.A.fmt = kFmtBF16; l.a_pitch = cin;
+  l.n_img = n; l.H = H; l.W = W; l.cin = cin; l.groups = 1;       // H, W: output grid
+  l.conv3 = conv3; l.stride = stride;
+  l.a_rows_total = (long long)n * H * W;
+  l.layer = &L; l.n = cout;
+  l.C.p[0] = out; l.C.fmt = kFmtBF16; l.c_pitch = cout; l.c_fill = cout; l.relu = relu; l.out_mode = kOutRows;
+  l.res = res; l.res_pitch = cout;
+  return launch_tc(l, st);
+}
+
+int tc_encoder_forward(const void* enc, const void* x, int n, int h, int w, void* out_rows, void* workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
+  const EncPack& e = *(const EncPack*)enc;
+  if (int rc = enc_check_grid(e, h, w)) return rc;
+  EncWs ws = plan_enc_ws(e, workspace, n, h, w);
+  if (ws.bytes > workspace_bytes) {
+    set_error("cdr_encoder_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
+    return CDR_ERR_WORKSPACE;
+  }
+  const __nv_bfloat16* cur = (const __nv_bfloat16*)x;
+  int H = h, W = w, pp = 0;
+  char label[48];
+  for (int i = 0; i < e.n_blocks; ++i) {
+    const EncBlock& b = e.blocks[i];
+    const int s = b.stride, Ho = H / s, Wo = W / s, o = 4 * b.planes;
+    __nv_bfloat16* out = i + 1 == e.n_blocks ? (__nv_bfloat16*)out_rows : ws.x[pp];
+    int rc;
+    snprintf(label, sizeof(label), "enc_block%d", i);
+    set_stage(label);
+    if ((rc = enc_conv(b.c1, cur, b.cin, n, H, W, 0, 1, ws.t1, b.planes, 1, nullptr, st))) return rc;
+    if ((rc = enc_conv(b.c2, ws.t1, b.planes, n, Ho, Wo, 1, s, ws.t2, b.planes, 1, nullptr, st))) return rc;
+    const __nv_bfloat16* res = cur;
+    if (b.has_ds) {
+      if ((rc = enc_conv(b.ds, cur, b.cin, n, Ho, Wo, 0, s, ws.r, o, 0, nullptr, st))) return rc;
+      res = ws.r;
+    }
+    if ((rc = enc_conv(b.c3, ws.t2, b.planes, n, Ho, Wo, 0, 1, out, o, 1, res, st))) return rc;
+    cur = out;
+    pp ^= 1;
+    H = Ho; W = Wo;
+  }
+  set_stage(nullptr);
+  return CDR_OK;
 }
 
 }  // namespace cdr

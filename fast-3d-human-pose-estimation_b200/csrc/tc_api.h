@@ -15,12 +15,21 @@ int tc_weights_create(const CdrWeightPtrs& src, int mode, TcWeights& w, cudaStre
 void tc_weights_destroy(TcWeights& w);
 int tc_head_workspace_bytes(const TcWeights& w, int batch, size_t* bytes);
 int tc_decoder_workspace_bytes(const TcWeights& w, int n_images, size_t* bytes);
-int tc_head_forward(const TcWeights& w, const float* feat_l, const float* feat_r, const float* P_l,
+// feat_rows != NULL: latents given as bf16 pixel-major rows (2*batch*64, 2048), left view first
+int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat_l, const float* feat_r, const float* P_l,
                     const float* P_r, const float* pinv_l, const float* pinv_r, double pinv_rtol,
                     int batch, float scale, float* kp2d_l, float* kp2d_r, float* xyz,
                     const CdrHeadTaps* taps, void* workspace, size_t workspace_bytes,
                     cudaStream_t st);
 int tc_decoder_forward(const TcWeights& w, const float* feat, int n_images, float* heatmaps,
                        void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+// ResNet bottleneck encoder (bf16, tcgen05) — gemm_tc.cu
+int tc_encoder_create(const CdrEncoderSpec& spec, void** out, cudaStream_t st);
+void tc_encoder_destroy(void* enc);
+int tc_encoder_workspace_bytes(const void* enc, int n, int h, int w, size_t* bytes);
+int tc_encoder_out_shape(const void* enc, int h, int w, int* oh, int* ow, int* oc);
+int tc_encoder_forward(const void* enc, const void* x, int n, int h, int w, void* out_rows, void* workspace,
+                       size_t workspace_bytes, cudaStream_t st);
 
 }  // namespace cdr

@@ -7,6 +7,10 @@ conv2,bn2,conv3,bn3,downsample.0,downsample.1}``; reference
 models/encoder.py:79-131) so ``best.pth`` / ``latest.pth`` checkpoints load,
 and creates parameters in the same order so a seeded random init matches.
 """
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
 from torch import nn
 
 _SPEC = {18: ("basic", (2, 2, 2, 2)), 34: ("basic", (3, 4, 6, 3)),
@@ -79,3 +83,125 @@ class ResNet(nn.Module):
     def forward(self, x):
         x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
         return self.layer4(self.layer3(self.layer2(self.layer1(x))))
+
+
+class TcEncoder:
+    """The bottleneck stages (layer1..layer4) of a ``ResNet`` on libcdrhead's tcgen05 tap-GEMM kernel
+    (include/cdrhead.h ``cdr_encoder_*``): bf16 activations, eval-mode BN folded,
+    fp32 accumulation.  The 7x7 stem + max-pool run on torch/cuDNN in bf16 channels-last with BN
+    folded into the conv (their output IS the NHWC layout the kernels read).  Inference only;
+    weights are re-packed when a parameter changes.  ``rows(x)`` returns the latents as bf16
+    pixel-major rows (n*h*w, 2048) — what ``cdr_head_forward_rows`` consumes; ``__call__`` returns
+    the reference's (n, 2048, h, w) fp32 tensor."""
+
+    def __init__(self, resnet):
+        blocks = [b for li in range(1, 5) for b in getattr(resnet, f"layer{li}")]
+        if any(b.kind != "bottleneck" for b in blocks):
+            raise NotImplementedError("the tcgen05 encoder covers the Bottleneck ResNets (50/101/152)")
+        self.resnet, self.blocks = resnet, blocks
+        self._handle, self._key, self._stem = None, None, None
+        self._ws = {}
+
+    def _tensors(self):
+        r = self.resnet
+        ts = [r.conv1.weight, r.bn1.weight, r.bn1.bias, r.bn1.running_mean, r.bn1.running_var]
+        for b in self.blocks:
+            mods = [(b.conv1, b.bn1), (b.conv2, b.bn2), (b.conv3, b.bn3)]
+            if b.downsample is not None:
+                mods.append((b.downsample[0], b.downsample[1]))
+            for c, n in mods:
+                ts += [c.weight, n.weight, n.bias, n.running_mean, n.running_var]
+        return ts
+
+    def _pack(self, device):
+        from . import _lib
+        ts = self._tensors()
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in ts)
+        if key == self._key:
+            return self._handle
+        self.release()
+        L = _lib.lib()
+        keep = []
+
+        def cb(conv, bn):
+            v = _lib.CdrConvBn()
+            for name, t in (("weight", conv.weight), ("bn_weight", bn.weight), ("bn_bias", bn.bias),
+                            ("bn_mean", bn.running_mean), ("bn_var", bn.running_var)):
+                t = t.detach().to(device=device, dtype=torch.float32).contiguous()
+                keep.append(t)
+                setattr(v, name, t.data_ptr())
+            return v
+        arr = (_lib.CdrEncoderBlock * len(self.blocks))()
+        for i, b in enumerate(self.blocks):
+            arr[i].conv1, arr[i].conv2, arr[i].conv3 = cb(b.conv1, b.bn1), cb(b.conv2, b.bn2), cb(b.conv3, b.bn3)
+            if b.downsample is not None:
+                arr[i].downsample = cb(b.downsample[0], b.downsample[1])
+            arr[i].planes, arr[i].stride = b.conv2.out_channels, b.conv2.stride[0]
+        spec = _lib.CdrEncoderSpec(len(self.blocks), arr, self.resnet.conv1.out_channels)
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(L.cdr_encoder_create(C.byref(spec), _lib.current_stream_ptr(device), C.byref(handle)))
+        # stem: BN folded into the conv, bf16 channels-last
+        r = self.resnet
+        sc = (r.bn1.weight.double() / torch.sqrt(r.bn1.running_var.double() + r.bn1.eps))
+        w = (r.conv1.weight.double() * sc.reshape(-1, 1, 1, 1)).to(device=device, dtype=torch.bfloat16)
+        bias = (r.bn1.bias.double() - r.bn1.running_mean.double() * sc).to(device=device, dtype=torch.bfloat16)
+        self._stem = (w.contiguous(memory_format=torch.channels_last), bias)
+        self._handle, self._key = handle, key
+        return handle
+
+    def release(self):
+        if self._handle is not None:
+            from . import _lib
+            _lib.lib().cdr_encoder_destroy(self._handle)
+        self._handle, self._key = None, None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def stem(self, x):
+        """(n,3,S,S) -> (n, S/4, S/4, 64) bf16 NHWC (conv 7x7 s2 + BN + ReLU + max-pool 3x3 s2)."""
+        w, b = self._stem
+        r = self.resnet
+        y = F.conv2d(x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), w, b,
+                     stride=r.conv1.stride, padding=r.conv1.padding)
+        y = F.max_pool2d(F.relu_(y), 3, 2, 1)
+        return y.permute(0, 2, 3, 1)          # a view: channels-last storage is NHWC
+
+    def rows(self, x, out=None):
+        """x (n,3,S,S) CUDA -> (rows (n*h*w, C) bf16, (h, w, C))."""
+        from . import _lib
+        if not x.is_cuda:
+            raise RuntimeError("the tcgen05 encoder has no CPU path")
+        if self.resnet.training:
+            raise RuntimeError("the tcgen05 encoder is inference-only; call .eval() first")
+        dev = x.device
+        handle = self._pack(dev)
+        L = _lib.lib()
+        with torch.no_grad():
+            y = self.stem(x)
+        if not y.is_contiguous():
+            y = y.contiguous()
+        n, h, w, _ = y.shape
+        oh, ow, oc = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(L.cdr_encoder_out_shape(handle, h, w, C.byref(oh), C.byref(ow), C.byref(oc)))
+        nbytes = C.c_size_t()
+        _lib.check(L.cdr_encoder_workspace_bytes(handle, n, h, w, C.byref(nbytes)))
+        key = (str(dev), nbytes.value)
+        ws = self._ws.get(key)
+        if ws is None:
+            self._ws.clear()
+            ws = self._ws[key] = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
+        if out is None:
+            out = torch.empty((n * oh.value * ow.value, oc.value), dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.cdr_encoder_forward(handle, _lib.ptr(y), n, h, w, _lib.ptr(out), _lib.ptr(ws), nbytes.value,
+                                             _lib.current_stream_ptr(dev)))
+        return out, (oh.value, ow.value, oc.value)
+
+    def __call__(self, x):
+        rows, (h, w, c) = self.rows(x)
+        return rows.reshape(x.shape[0], h, w, c).permute(0, 3, 1, 2).float()

@@ -134,6 +134,38 @@ int cdr_head_forward(const CdrWeights* w, const float* feat_l, const float* feat
                      float* kp2d_l, float* kp2d_r, float* xyz, const CdrHeadTaps* taps,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* cdr_head_forward on latents that are already pixel-major bf16 rows: feat_rows (2*B*64, 2048),
+ * the left view's B*64 rows first — the layout cdr_encoder_forward writes.  Tensor-core
+ * precisions only. */
+int cdr_head_forward_rows(const CdrWeights* w, const void* feat_rows, const float* P_l, const float* P_r,
+                          const float* pinv_l, const float* pinv_r, double pinv_rtol, int batch,
+                          int img_size, float* kp2d_l, float* kp2d_r, float* xyz, const CdrHeadTaps* taps,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the ResNet bottleneck stages of the encoder (models/encoder.py:38-131,
+ * layer1..layer4) on the same tcgen05 tap-GEMM kernel, bf16 activations, eval-mode BN folded.
+ * The 7x7 stem + max-pool (models/encoder.py:93-97,122-125) stay with the caller (torch/cuDNN);
+ * their output, NHWC bf16, is this function's input. */
+typedef struct CdrEncoderBlock {  /* one Bottleneck, models/encoder.py:38-76 */
+  CdrConvBn conv1, conv2, conv3;  /* conv weight (Cout,Cin,kh,kw) fp32, bias NULL, + BN tensors        */
+  CdrConvBn downsample;           /* weight NULL when the block has no downsample branch              */
+  int planes;                     /* conv1: Cin->planes 1x1; conv2: 3x3 stride; conv3: ->4*planes 1x1 */
+  int stride;
+} CdrEncoderBlock;
+typedef struct CdrEncoderSpec {
+  int num_blocks;                 /* over layer1..layer4, in order (ResNet-101: 3+4+23+3)             */
+  const CdrEncoderBlock* blocks;  /* HOST array of device-pointer structs                             */
+  int in_channels;                /* 64                                                                */
+} CdrEncoderSpec;
+typedef struct CdrEncoder CdrEncoder;
+int cdr_encoder_create(const CdrEncoderSpec* spec, void* stream, CdrEncoder** out);
+int cdr_encoder_destroy(CdrEncoder* e);
+int cdr_encoder_workspace_bytes(const CdrEncoder* e, int n_images, int in_h, int in_w, size_t* bytes);
+int cdr_encoder_out_shape(const CdrEncoder* e, int in_h, int in_w, int* out_h, int* out_w, int* out_c);
+/* x (n_images, in_h, in_w, 64) bf16 NHWC -> out_rows (n_images*out_h*out_w, out_c) bf16 pixel-major rows. */
+int cdr_encoder_forward(const CdrEncoder* e, const void* x_nhwc_bf16, int n_images, int in_h, int in_w,
+                        void* out_rows_bf16, void* workspace, size_t workspace_bytes, void* stream);
+
 /* PoseDecoder.forward — models/decoder.py:39-46 (also the decoder half of
  * PoseResNet.forward, models/poseresnet.py:17-21).  feat (N,2048,8,8) -> heatmaps
  * (N,J,64,64) fp32 NCHW. */

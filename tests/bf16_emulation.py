@@ -66,3 +66,30 @@ def head_bf16(sd, feats, proj_list, pinv_list, taps=None):
     if taps is not None:
         taps.update(cf_cat=cat, cf_f=f, f_out=fo, heatmaps=hms)
     return kps, xyz
+
+
+def encoder_bf16(resnet, x):
+    """fp64 evaluation of a Bottleneck ``ResNet`` (fast_3d_human_pose_estimation_b200.encoder, module
+    tree identical to models/encoder.py:79-131) with bf16 rounding where the tcgen05 encoder rounds:
+    BN-folded weights, and every activation written to memory (stem output, conv1/conv2 outputs,
+    the downsample branch, the block output after residual + ReLU)."""
+    def fold(conv, bn):
+        s = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
+        return conv.weight.double() * s.reshape(-1, 1, 1, 1), bn.bias.double() - bn.running_mean.double() * s
+
+    def cbr(x, conv, bn, relu):
+        w, b = fold(conv, bn)
+        y = F.conv2d(x, bf(w), b.float().double(), stride=conv.stride, padding=conv.padding)
+        return F.relu(y) if relu else y
+
+    r = resnet
+    w, b = fold(r.conv1, r.bn1)
+    y = bf(F.conv2d(bf(x), bf(w), bf(b), stride=r.conv1.stride, padding=r.conv1.padding))   # cuDNN bf16 stem
+    y = F.max_pool2d(F.relu(y), 3, 2, 1)
+    for li in range(1, 5):
+        for blk in getattr(r, f"layer{li}"):
+            t = bf(cbr(y, blk.conv1, blk.bn1, True))
+            t = bf(cbr(t, blk.conv2, blk.bn2, True))
+            res = y if blk.downsample is None else bf(cbr(y, blk.downsample[0], blk.downsample[1], False))
+            y = bf(F.relu(cbr(t, blk.conv3, blk.bn3, False) + res))
+    return y

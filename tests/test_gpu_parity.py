@@ -577,3 +577,66 @@ def test_head_graph_replay_matches_eager(cuda_pkg):
     (kl2, _), xyz2 = m.head([f.cuda() for f in feats], [p.cuda() for p in Ps])
     kp_h, xyz_h, _ = hg.replay()
     assert torch.equal(kp_h[0], kl2.cpu()) and torch.equal(xyz_h, xyz2.cpu()) and not torch.equal(xyz2, xyz)
+
+
+def _seeded_resnet(layers, seed=0, randomize_bn=True):
+    from fast_3d_human_pose_estimation_b200.encoder import ResNet
+    torch.manual_seed(seed)
+    r = ResNet(synth.make_cfg(layers, 19))
+    if randomize_bn:
+        g = torch.Generator().manual_seed(seed + 77)
+        for m in r.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                n = m.num_features
+                m.weight.data = 1.0 + 0.2 * (torch.rand(n, generator=g) - 0.5)
+                m.bias.data = 0.05 * (torch.rand(n, generator=g) - 0.5)
+                m.running_mean.data = 0.05 * (torch.rand(n, generator=g) - 0.5)
+                m.running_var.data = 1.0 + 0.4 * (torch.rand(n, generator=g) - 0.5)
+    return r.eval()
+
+
+def test_tc_encoder_resnet50_vs_emulated_and_fp32(cuda_pkg):
+    """layer1..layer4 of the encoder on the tcgen05 tap-GEMM kernel (3x3 = 9 shifted
+    TMA taps, stride 2 through element-strided tensor maps, residual add in the epilogue) against
+    (i) the fp64 evaluation with bf16 rounding at the same points, (ii) the fp32 torch module."""
+    from bf16_emulation import encoder_bf16
+    from fast_3d_human_pose_estimation_b200.encoder import TcEncoder
+    r = _seeded_resnet(50)
+    x = torch.randn(3, 3, 256, 256, generator=torch.Generator().manual_seed(5))      # odd image count
+    with torch.no_grad():
+        want_e = encoder_bf16(r, x.double()).numpy()
+        want_32 = r(x).numpy()
+    enc = TcEncoder(r.cuda())
+    got = enc(x.cuda()).cpu().numpy()
+    assert got.shape == (3, 2048, 8, 8)
+    e_e = np.abs(got - want_e).max() / np.abs(want_e).max()
+    e_32 = np.abs(got - want_32).max() / np.abs(want_32).max()
+    m_32 = np.abs(got - want_32).mean() / np.abs(want_32).mean()
+    print(f"\ntcgen05 ResNet-50 encoder: vs bf16-emulated fp64 {e_e:.2e} | vs fp32 torch max {e_32:.2e} mean {m_32:.2e}")
+    assert e_e < 2e-2
+    assert e_32 < 6e-2 and m_32 < 2e-2          # stated bf16 bounds for ~50 layers of bf16 activations
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_pipeline_tc_encoder(cuda_pkg, precision):
+    """CDRNet.forward with encoder_precision='bf16': encoder rows feed cdr_head_forward_rows directly.
+    Compared with the same head fed the fp32 torch encoder's latents (the head's sensitivity to
+    bf16 latents) under the stated bf16 bounds."""
+    b = 2
+    torch.manual_seed(0)
+    m = cuda_pkg.CDRNet(synth.make_cfg(50, 19), precision=precision, encoder_precision="bf16")
+    m.load_state_dict(synth.make_head_state_dict(seed=0, calibrated=True), strict=False)
+    m = m.cuda().eval()
+    cams = synth.make_cameras(b, seed=2)
+    Ps = [torch.from_numpy(cams["P_l"]).cuda(), torch.from_numpy(cams["P_r"]).cuda()]
+    g = torch.Generator().manual_seed(1)
+    xs = [torch.randn(b, 3, 256, 256, generator=g).cuda() for _ in range(2)]
+    (kl, kr), xyz = m(xs, Ps)
+    with torch.no_grad():
+        zs = [m.encoder(x) for x in xs]
+    (rl, rr), rxyz = m.head(zs, Ps)
+    torch.cuda.synchronize()
+    d2 = max(float((kl - rl).abs().max()), float((kr - rr).abs().max()))
+    print(f"\nfull pipeline [{precision}] tcgen05 bf16 encoder vs torch fp32 encoder: d2D max {d2:.3f} px")
+    assert torch.isfinite(xyz).all() and kl.shape == (b, 19, 2) and xyz.shape == (b, 19, 3)
+    assert d2 < 1.5
