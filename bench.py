@@ -434,7 +434,7 @@ def full_pipeline(args, ctx, precision):
                                    "stem_ms_cudnn": stem_ms, "head_share": max(0.0, 1.0 - enc_ms / ms),
                                    "encoder_tflops": 40747.7e6 * B / (enc_ms / 1e3) / 1e12,
                                    "layer_ms": {f"layer{i + 1}": sum(v for k, v in blocks.items()
-                                                                     if k.startswith("enc_block") and lo <= int(k[9:]) < hi)
+                                                                     if k.startswith("enc_block") and lo <= int(k[9:].split(".")[0]) < hi)
                                                 for i, (lo, hi) in enumerate(((0, 3), (3, 7), (7, 30), (30, 33)))}}
     del m2, x2
     out["note"] = ("ResNet-101 encoder = 40.7 GF/pair on torch/cuDNN (out of scope, SURVEY §8f rank 1); head = "

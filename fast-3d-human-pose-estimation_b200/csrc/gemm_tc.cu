@@ -137,7 +137,10 @@ struct TcCfg {
   // 16-bit row-major outputs leave through swizzled smem staging + TMA tensor stores (full 128-byte
   // lines, issued by one lane, asynchronous) instead of 32 scattered 16-byte stores per warp instruction.
   static constexpr bool kTmaStore = BN >= 64 && OFMT != kFmtTF32P;
-  static constexpr int kStagingBytes = kTmaStore ? kEpiWarps * kStageBufBytes : 0;
+  // two staging buffers per warp where smem allows (bf16, BN <= 128): a warp never waits for its previous
+  // store to drain — the memory-bound encoder layers are paced by epilogue bytes in flight
+  static constexpr int kStageBufs = (KIND == kKindBF16 && BN <= 128) ? 2 : 1;
+  static constexpr int kStagingBytes = kTmaStore ? kEpiWarps * kStageBufs * kStageBufBytes : 0;
   static constexpr int kStagesFit = (kSmemBudget - kStagingBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kAccBufs = KIND != kKindBF16 ? 4 : 2;     // see the TMEM column map in the kernel
@@ -158,7 +161,8 @@ struct TcGemmParams {
   int a4d;                // 1: A through the 4-D NHWC map (shifted / strided taps), 0: 2-D (rows, channels)
   int tap_mode;           // kTapNone: 1 tap; kTapDeconv: 4 taps of output phase g; kTapConv3: 9 taps (3x3, pad 1)
   int stride;             // 4-D A: input pixel = stride * output pixel + tap shift (map carries the element stride)
-  int has_res;            // residual tensor (same row layout as C, bf16) added before the ReLU (TMA-store path)
+  int has_res;            // residual tensor (rows like C, bf16) added before the ReLU: its 128 x 128 tile travels
+                          // through the operand ring as one extra stage per tile (BN = 128, bf16 kind)
   int box_rows, box_imgs; // 4-D box: W x box_rows x box_imgs pixels = 128
   int groups;             // phases (deconv) or independent problems stacked along rows
   int a_group_rows;       // 2-D A: row offset per group
@@ -190,27 +194,31 @@ struct EpiScale {          // per-thread epilogue constants of the scaled format
   float amax = 0.f;        // running max |out| of this thread
 };
 
-// + scale (f16x2), bias, ReLU, column mask for one 32-column slab of a finished row
+// + scale (f16x2), bias, ReLU for one 32-column slab of a finished row.  `floor` = 0 (ReLU) or -inf
+// (none): one FMNMX per element instead of a branch; the column mask only runs on the slab that
+// straddles the layer's last channel.  (The first version spent ~35 instructions per element here —
+// per-element predicates and masks — and made every short-K layer epilogue-issue-bound.)
 template <int KIND>
 __device__ __forceinline__ void finish_slab(const TcGemmParams& p, const float (&acc)[32], float (&v)[32], int n0c,
                                             const float* __restrict__ bias, const float* __restrict__ wsi,
-                                            const EpiScale& es, bool relu) {
+                                            const EpiScale& es, float floor) {
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
-    float x[4] = {acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]};
+    float4 x = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
     if constexpr (KIND == kKindF16X2) {
       const float4 w4 = __ldg(reinterpret_cast<const float4*>(wsi + n0c) + j4);
-      x[0] *= es.a_inv * w4.x; x[1] *= es.a_inv * w4.y; x[2] *= es.a_inv * w4.z; x[3] *= es.a_inv * w4.w;
+      x.x *= es.a_inv * w4.x; x.y *= es.a_inv * w4.y; x.z *= es.a_inv * w4.z; x.w *= es.a_inv * w4.w;
     }
-    if (bias) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0c) + j4);
-      x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
-    }
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0c) + j4);
+    v[4 * j4] = fmaxf(x.x + b4.x, floor);
+    v[4 * j4 + 1] = fmaxf(x.y + b4.y, floor);
+    v[4 * j4 + 2] = fmaxf(x.z + b4.z, floor);
+    v[4 * j4 + 3] = fmaxf(x.w + b4.w, floor);
+  }
+  if (n0c + 32 > p.n) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (relu) x[e] = fmaxf(x[e], 0.f);
-      v[4 * j4 + e] = (n0c + 4 * j4 + e < p.n) ? x[e] : 0.f;
-    }
+    for (int j = 0; j < 32; ++j)
+      if (n0c + j >= p.n) v[j] = 0.f;
   }
 }
 
@@ -245,7 +253,7 @@ __device__ __forceinline__ void store_slab(const TcGemmParams& p, const float (&
                                            size_t orow, int img, int pix, int HW, const float* __restrict__ bias,
                                            const float* __restrict__ wsi, EpiScale& es) {
   float v[32];
-  finish_slab<KIND>(p, acc, v, n0c, bias, wsi, es, p.relu != 0);
+  finish_slab<KIND>(p, acc, v, n0c, bias, wsi, es, p.relu ? 0.f : -INFINITY);
   if (!row_ok) return;
   if (p.out_mode == kOutPlanar) {
     float* __restrict__ C = reinterpret_cast<float*>(p.C);
@@ -294,9 +302,10 @@ struct StoreCoord {
   int m, g;
   int px, x0, py, r0;   // kOutDeconv: (c, px, x, py, img*H + y)
 };
+template <int kPending>
 __device__ __forceinline__ void tma_store_block(const TcGemmParams& p, const void* tmap, uint8_t* stage, int lane,
                                                 const uint32_t (&words)[32], int c0, const StoreCoord& sc) {
-  if (lane == 0) ptx::bulk_wait_read0();
+  if (lane == 0) ptx::bulk_wait_read<kPending>();   // the store that last used THIS buffer has read it
   __syncwarp();
   const uint32_t base = ptx::smem_u32(stage) + (uint32_t)lane * 128u;
 #pragma unroll
@@ -347,7 +356,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint64_t* chunk_full = bars + 2 * S + 4;    // [2]  split kinds: main-term chunk accumulator
   uint64_t* chunk_empty = bars + 2 * S + 6;   // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
-  uint64_t* res_bar = bars + 2 * S + 9;       // [kEpiWarps]  residual tile landed in the warp's staging buffer
+  uint32_t* res_cnt = reinterpret_cast<uint32_t*>(bars + 2 * S + 9);   // [S] epilogue warps done with a residual stage
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -373,7 +382,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       ptx::mbar_init(&chunk_full[a], 1);
       ptx::mbar_init(&chunk_empty[a], kEpiWarps);
     }
-    for (int w = 0; w < kEpiWarps; ++w) ptx::mbar_init(&res_bar[w], 1);
+    for (int s = 0; s < S; ++s) res_cnt[s] = 0;
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_base_slot);
@@ -423,6 +432,18 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           ptx::tma_load_2d(stage_b(s, 0), &tmap_b, &full[s], tap * p.cin + k0, g * p.b_group_rows + n_tile * BN);
           if (kSplit)
             ptx::tma_load_2d(stage_b(s, 1), &tmap_b_lo, &full[s], tap * p.cin + k0, g * p.b_group_rows + n_tile * BN);
+        }
+        if constexpr (KIND == kKindBF16 && BN == 128) {
+          if (p.has_res) {
+            // the tile's residual (128 rows x 128 channels bf16 = one 32 KB stage) rides the ring: prefetched
+            // up to S stages ahead of the epilogue that consumes it, released by the epilogue warps
+            const int s = it % S;
+            ptx::mbar_wait(&empty[s], ((it / S) & 1) ^ 1u);
+            ptx::mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+            ptx::tma_load_3d(stage_a(s, 0), &tmap_r, &full[s], n_tile * BN, m0, 0);
+            ptx::tma_load_3d(stage_a(s, 0) + kABytes, &tmap_r, &full[s], n_tile * BN + 64, m0, 0);
+            ++it;
+          }
         }
       }
     }
@@ -486,6 +507,9 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
         }
         ptx::umma_commit(&tmem_full[acc]);         // tile (bf16) / correction accumulator (split) complete
+        if constexpr (KIND == kKindBF16 && BN == 128) {
+          if (p.has_res) ++it;                     // the residual stage belongs to the epilogue
+        }
       }
     }
   } else {
@@ -493,8 +517,9 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     const int ew = warp - 2;                       // epilogue warp index
     const int cb0 = (ew >> 2) * kCols;             // first tile column owned by this warp
-    uint8_t* stage = staging + (size_t)ew * kStageBufBytes;
-    uint32_t tl = 0, ch = 0, res_phase = 0;
+    uint8_t* stage = staging + (size_t)ew * Cfg::kStageBufs * kStageBufBytes;
+    int sbuf = 0;                                  // staging buffer of this warp's next store
+    uint32_t tl = 0, ch = 0, it_e = 0;             // it_e: ring position of the current tile's residual stage
     EpiScale es;
     if constexpr (KIND == kKindF16X2) es.a_inv = 1.f / __ldg(p.scale_in);   // powers of two: exact
     if constexpr (OFMT == kFmtF16P) {
@@ -505,6 +530,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
     const bool use_tma = Cfg::kTmaStore && p.out_mode != kOutPlanar;
+    const float relu_floor = p.relu ? 0.f : -INFINITY;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
       const int n_tile = tile % p.n_tiles;
       const int g = (tile / p.n_tiles) % p.groups;
@@ -514,7 +540,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int m = mw + lane;                     // this thread's pixel
       const bool row_ok = m < p.M;
       const int n0 = n_tile * BN + cb0;            // first output channel of this warp
-      const float* __restrict__ bias = p.bias ? p.bias + (size_t)g * p.bias_group_stride : nullptr;
+      const float* __restrict__ bias = p.bias + (size_t)g * p.bias_group_stride;
       const float* __restrict__ wsi = KIND == kKindF16X2 ? p.wsi + (size_t)g * p.wsi_group_stride : nullptr;
       size_t orow = (size_t)(row_ok ? m : 0);
       int img = 0, pix = 0;
@@ -535,6 +561,8 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
 
       // one finished 32-column slab (fp32, scale/bias/ReLU still to apply) -> its destination
+      uint32_t resw[32];               // this thread's 64 residual values (bf16 pairs) of the current tile
+      bool has_res_vals = false;
       auto emit = [&](const float (&a32)[32], int c, auto half_c, uint32_t (&wh)[32], uint32_t (&wl)[32]) {
         constexpr int half = decltype(half_c)::value;     // which 32-column half of a 64-column store block
         // c = column inside the warp's range; TMA path gathers two slabs (64 columns) per store
@@ -544,24 +572,12 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         if constexpr (Cfg::kTmaStore) {
           float v[32];
-          const bool res = p.has_res && (n0 + c - 32 * half) < p.c_fill;
-          finish_slab<KIND>(p, a32, v, n0 + c, bias, wsi, es, p.relu != 0 && !res);
-          if (res) {
-            // the residual block (bf16, swizzled like the store) is in the staging buffer: add, then ReLU
-            const uint32_t rbase = ptx::smem_u32(stage) + (uint32_t)lane * 128u;
+          finish_slab<KIND>(p, a32, v, n0 + c, bias, wsi, es, has_res_vals ? -INFINITY : relu_floor);
+          if (has_res_vals) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t w[4];
-              ptx::ld_shared_v4(rbase + (uint32_t)(((half * 4 + j) ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[8 * j + 2 * e] += __uint_as_float(w[e] << 16);
-                v[8 * j + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int j = 0; j < 16; ++j) {
+              v[2 * j] = fmaxf(v[2 * j] + __uint_as_float(resw[half * 16 + j] << 16), relu_floor);
+              v[2 * j + 1] = fmaxf(v[2 * j + 1] + __uint_as_float(resw[half * 16 + j] & 0xffff0000u), relu_floor);
             }
           }
           uint32_t h16[16], l16[16];
@@ -574,8 +590,9 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           if (half == 1) {
             const int c0 = n0 + c - 32;            // first channel of the 64-column block
             if (c0 < p.c_fill) {
-              tma_store_block(p, &tmap_c, stage, lane, wh, c0, sc);
-              if constexpr (OFMT == kFmtF16P) tma_store_block(p, &tmap_c_lo, stage, lane, wl, c0, sc);
+              tma_store_block<Cfg::kStageBufs - 1>(p, &tmap_c, stage + sbuf * kStageBufBytes, lane, wh, c0, sc);
+              if constexpr (Cfg::kStageBufs > 1) sbuf ^= 1;
+              if constexpr (OFMT == kFmtF16P) tma_store_block<0>(p, &tmap_c_lo, stage, lane, wl, c0, sc);
             }
           }
         }
@@ -587,16 +604,6 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         uint32_t wh[32], wl[32];
 #pragma unroll 1
         for (int c = 0; c < kCols; c += 64) {
-          bool res_blk = false;
-          if constexpr (Cfg::kTmaStore) {
-            // residual tile of this 64-column block -> the warp's staging buffer, overlapped with the TMEM loads
-            res_blk = use_tma && p.has_res && (n0 + c) < p.c_fill;
-            if (res_blk && lane == 0) {
-              ptx::bulk_wait_read0();               // the previous store has finished reading the buffer
-              ptx::mbar_arrive_expect_tx(&res_bar[ew], kStageBufBytes);
-              ptx::tma_load_3d(stage, &tmap_r, &res_bar[ew], n0 + c, sc.m, sc.g);
-            }
-          }
           // 64 columns per TMEM round trip (one wait for two loads) when the warp owns that many
           uint32_t r0[32], r1[32];
           ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(acc * BN + cb0 + c), r0);
@@ -608,9 +615,27 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
           }
-          if (res_blk) {
-            ptx::mbar_wait(&res_bar[ew], res_phase);
-            res_phase ^= 1u;
+          if constexpr (KIND == kKindBF16 && BN == 128) {
+            if (p.has_res) {
+              // residual stage of this tile: after the tile's K-blocks in ring order
+              it_e += (uint32_t)num_kb;
+              const int s = it_e % S;
+              ptx::mbar_wait(&full[s], (it_e / S) & 1);
+              const uint32_t rb = ptx::smem_u32(stage_a(s, 0)) + (uint32_t)((ew >> 2) * kABytes) +
+                                  (uint32_t)(q * 32 + lane) * 128u;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                ptx::ld_shared_v4(rb + (uint32_t)((j ^ (lane & 7)) << 4), resw[4 * j], resw[4 * j + 1], resw[4 * j + 2],
+                                  resw[4 * j + 3]);
+              has_res_vals = true;
+              __threadfence_block();
+              __syncwarp();
+              if (lane == 0 && atomicAdd(&res_cnt[s], 1u) == (uint32_t)(kEpiWarps - 1)) {
+                res_cnt[s] = 0;
+                ptx::mbar_arrive(&empty[s]);       // last of the 8 warps hands the stage back to the producer
+              }
+              ++it_e;
+            }
           }
           float a32[32];
 #pragma unroll
@@ -675,7 +700,8 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
     if constexpr (Cfg::kTmaStore) {
-      if (use_tma && lane == 0) ptx::bulk_wait_all0();     // our stores have landed before the CTA retires
+      if (use_tma && lane == 0) ptx::bulk_wait_all0();
+      (void)it_e;     // our stores have landed before the CTA retires
     }
     if constexpr (OFMT == kFmtF16P) {
       if (p.out_mode != kOutPlanar && p.amax_out) {
@@ -802,6 +828,7 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
   p.num_tiles = m_tiles * p.groups * p.n_tiles;
   CDR_CHECK_ARG(l.layer->bn == BN && l.layer->n_pad % BN == 0, "tap_gemm_tc: layer packed for BN=%d, launched with %d",
                 l.layer->bn, BN);
+  CDR_CHECK_ARG(p.bias != nullptr, "tap_gemm_tc: every packed layer carries a (possibly zero) bias vector");
   CDR_CHECK_ARG(l.A.fmt == kAFmt, "tap_gemm_tc: A stored as format %d, kernel kind %d wants %d", l.A.fmt, KIND, kAFmt);
   CDR_CHECK_ARG((l.a_pitch * kElem) % 16 == 0 && ((uintptr_t)l.A.p[0] & 15) == 0, "tap_gemm_tc: A pitch/alignment");
   if (l.out_mode != kOutPlanar) {
@@ -864,12 +891,13 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
   }
   CUtensorMap tmap_r = tmap_a[0];
   if (l.res) {
-    CDR_CHECK_ARG(Cfg::kTmaStore && KIND == kKindBF16 && OFMT == kFmtBF16 && l.out_mode == kOutRows && l.groups == 1,
-                  "tap_gemm_tc: the residual add needs the bf16 TMA-store epilogue");
+    CDR_CHECK_ARG(BN == 128 && KIND == kKindBF16 && OFMT == kFmtBF16 && l.out_mode == kOutRows && l.groups == 1 &&
+                      l.n % BN == 0 && l.c_fill == l.n,
+                  "tap_gemm_tc: the residual add needs the bf16 BN=128 kernel and a multiple of 128 channels");
     CDR_CHECK_ARG(((uintptr_t)l.res & 15) == 0 && (l.res_pitch * 2) % 16 == 0, "tap_gemm_tc: residual alignment");
     const uint64_t dims[3] = {(uint64_t)l.c_fill, (uint64_t)p.M, 1};
     const uint64_t strides[2] = {(uint64_t)l.res_pitch, (uint64_t)p.M * l.res_pitch};
-    const uint32_t box[3] = {64, 32, 1};
+    const uint32_t box[3] = {64, 128, 1};     // half a residual tile: 128 rows x 64 channels
     if (int rc = make_tmap(&tmap_r, l.res, kFmtBF16, 3, dims, strides, box)) return rc;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
@@ -1470,7 +1498,9 @@ struct EncPack {
   EncBlock* blocks = nullptr;
 };
 
-static int enc_bn(int n) { return n >= 256 ? 256 : n >= 128 ? 128 : 64; }
+// N tile: 128 for the layers that carry a residual (it rides the ring as one 32 KB stage) and for the
+// memory-bound 1x1 projections (two staging buffers per warp); 256 for the MMA-bound 3x3 / reduce convs
+static int enc_bn(int n, bool wide) { return n >= 256 && wide ? 256 : n >= 128 ? 128 : 64; }
 
 static size_t plan_encoder(EncPack& e, const CdrEncoderSpec& spec, void* base) {
   Bump1K b(base);
@@ -1480,10 +1510,10 @@ static size_t plan_encoder(EncPack& e, const CdrEncoderSpec& spec, void* base) {
     EncBlock& blk = e.blocks[i];
     blk.cin = cin; blk.planes = sb.planes; blk.stride = sb.stride; blk.has_ds = sb.downsample.weight != nullptr;
     const int p = sb.planes, o = 4 * sb.planes;
-    plan_layer(blk.c1, b, kKindBF16, p, cin, cin, enc_bn(p), p, p, false);
-    plan_layer(blk.c2, b, kKindBF16, p, 9 * p, 9 * p, enc_bn(p), p, p, false);
-    plan_layer(blk.c3, b, kKindBF16, o, p, p, enc_bn(o), o, o, false);
-    if (blk.has_ds) plan_layer(blk.ds, b, kKindBF16, o, cin, cin, enc_bn(o), o, o, false);
+    plan_layer(blk.c1, b, kKindBF16, p, cin, cin, enc_bn(p, true), p, p, false);
+    plan_layer(blk.c2, b, kKindBF16, p, 9 * p, 9 * p, enc_bn(p, true), p, p, false);
+    plan_layer(blk.c3, b, kKindBF16, o, p, p, enc_bn(o, false), o, o, false);
+    if (blk.has_ds) plan_layer(blk.ds, b, kKindBF16, o, cin, cin, enc_bn(o, false), o, o, false);
     cin = o;
   }
   return b.off;
@@ -1629,15 +1659,21 @@ int tc_encoder_forward(const void* enc, const void* x, int n, int h, int w, void
     const int s = b.stride, Ho = H / s, Wo = W / s, o = 4 * b.planes;
     __nv_bfloat16* out = i + 1 == e.n_blocks ? (__nv_bfloat16*)out_rows : ws.x[pp];
     int rc;
-    snprintf(label, sizeof(label), "enc_block%d", i);
-    set_stage(label);
+    auto stage = [&](const char* conv) {
+      snprintf(label, sizeof(label), "enc_block%d.%s", i, conv);
+      set_stage(label);
+    };
+    stage("conv1");
     if ((rc = enc_conv(b.c1, cur, b.cin, n, H, W, 0, 1, ws.t1, b.planes, 1, nullptr, st))) return rc;
+    stage("conv2");
     if ((rc = enc_conv(b.c2, ws.t1, b.planes, n, Ho, Wo, 1, s, ws.t2, b.planes, 1, nullptr, st))) return rc;
     const __nv_bfloat16* res = cur;
     if (b.has_ds) {
+      stage("downsample");
       if ((rc = enc_conv(b.ds, cur, b.cin, n, Ho, Wo, 0, s, ws.r, o, 0, nullptr, st))) return rc;
       res = ws.r;
     }
+    stage("conv3");
     if ((rc = enc_conv(b.c3, ws.t2, b.planes, n, Ho, Wo, 0, 1, out, o, 1, res, st))) return rc;
     cur = out;
     pp ^= 1;
