@@ -49,7 +49,8 @@ class CdrEncoderBlock(C.Structure):
 
 
 class CdrEncoderSpec(C.Structure):
-    _fields_ = [("num_blocks", C.c_int), ("blocks", C.POINTER(CdrEncoderBlock)), ("in_channels", C.c_int)]
+    _fields_ = [("num_blocks", C.c_int), ("blocks", C.POINTER(CdrEncoderBlock)), ("in_channels", C.c_int),
+                ("stem", CdrConvBn)]
 
 
 class CdrError(RuntimeError):
@@ -79,6 +80,8 @@ _SIGNATURES = {
     "cdr_encoder_out_shape": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                         C.POINTER(C.c_int)]),
     "cdr_encoder_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_size_t, _vp]),
+    "cdr_encoder_workspace_bytes_images": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "cdr_encoder_forward_images": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_size_t, _vp]),
     "cdr_pinv": (C.c_int, [_vp, C.c_int, C.c_double, _vp, _vp]),
     "cdr_ftl": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
                           C.c_int, C.c_int, _vp]),

@@ -516,3 +516,17 @@ extern "C" int cdr_encoder_forward(const CdrEncoder* e, const void* x_nhwc_bf16,
   return tc_encoder_forward(e->impl, x_nhwc_bf16, n_images, in_h, in_w, out_rows_bf16, workspace, workspace_bytes,
                             (cudaStream_t)stream);
 }
+extern "C" int cdr_encoder_workspace_bytes_images(const CdrEncoder* e, int n_images, int img_h, int img_w,
+                                                  size_t* bytes) {
+  CDR_CHECK_ARG(e && bytes && n_images > 0 && img_h > 0 && img_w > 0, "cdr_encoder_workspace_bytes_images: bad args");
+  return tc_encoder_workspace_bytes_images(e->impl, n_images, img_h, img_w, bytes);
+}
+extern "C" int cdr_encoder_forward_images(const CdrEncoder* e, const float* images, int n_images, int img_h, int img_w,
+                                          void* out_rows_bf16, void* workspace, size_t workspace_bytes, void* stream) {
+  CDR_CHECK_ARG(e && images && out_rows_bf16 && workspace && n_images > 0, "cdr_encoder_forward_images: bad args");
+  CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)images & 15) == 0 && ((uintptr_t)out_rows_bf16 & 15) == 0,
+                "cdr_encoder_forward_images: workspace must be 256-byte, tensors 16-byte aligned");
+  timing_restart();
+  return tc_encoder_forward_images(e->impl, images, n_images, img_h, img_w, out_rows_bf16, workspace, workspace_bytes,
+                                   (cudaStream_t)stream);
+}

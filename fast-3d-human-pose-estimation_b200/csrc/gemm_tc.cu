@@ -1494,6 +1494,8 @@ struct EncBlock {
 };
 struct EncPack {
   void* pool = nullptr;
+  void* stem_w = nullptr;        // stem.cu: packed conv1 + bn1 (NULL: no stem in this handle)
+  float* stem_b = nullptr;
   int n_blocks = 0, in_channels = 0, out_channels = 0, total_stride = 1;
   EncBlock* blocks = nullptr;
 };
@@ -1515,6 +1517,10 @@ static size_t plan_encoder(EncPack& e, const CdrEncoderSpec& spec, void* base) {
     plan_layer(blk.c3, b, kKindBF16, o, p, p, enc_bn(o, false), o, o, false);
     if (blk.has_ds) plan_layer(blk.ds, b, kKindBF16, o, cin, cin, enc_bn(o, false), o, o, false);
     cin = o;
+  }
+  if (spec.stem.weight) {
+    e.stem_w = b.take(stem_weight_bytes());
+    e.stem_b = (float*)b.take(64 * sizeof(float));
   }
   return b.off;
 }
@@ -1554,6 +1560,10 @@ int tc_encoder_create(const CdrEncoderSpec& spec, void** out, cudaStream_t st) {
     CDR_LAUNCH_OK("pack_conv_tc_kernel");
     return layer_maps(L);
   };
+  if (spec.stem.weight) {
+    CDR_CHECK_ARG(spec.in_channels == 64, "cdr_encoder_create: the stem produces 64 channels");
+    if (int rc = launch_pack_stem(spec.stem, e->stem_w, e->stem_b, st)) return rc;
+  }
   for (int i = 0; i < spec.num_blocks; ++i) {
     const CdrEncoderBlock& sb = spec.blocks[i];
     EncBlock& blk = e->blocks[i];
@@ -1621,6 +1631,46 @@ int tc_encoder_workspace_bytes(const void* enc, int n, int h, int w, size_t* byt
   if (int rc = enc_check_grid(e, h, w)) return rc;
   *bytes = plan_enc_ws(e, nullptr, n, h, w).bytes;
   return CDR_OK;
+}
+
+// images (n,3,H,W): [conv_out (n,H/2,W/2,64) | pooled (n,H/4,W/4,64) | layer workspace]
+struct EncImgWs {
+  void *conv_out, *pooled, *layers;
+  size_t layer_bytes, bytes;
+};
+static EncImgWs plan_enc_img_ws(const EncPack& e, void* base, int n, int H, int W) {
+  Bump1K bp(base);
+  EncImgWs ws;
+  ws.conv_out = bp.take((size_t)n * (H / 2) * (W / 2) * 64 * 2);
+  ws.pooled = bp.take((size_t)n * (H / 4) * (W / 4) * 64 * 2);
+  ws.layer_bytes = plan_enc_ws(e, nullptr, n, H / 4, W / 4).bytes;
+  ws.layers = bp.take(ws.layer_bytes);
+  ws.bytes = bp.off;
+  return ws;
+}
+int tc_encoder_workspace_bytes_images(const void* enc, int n, int H, int W, size_t* bytes) {
+  const EncPack& e = *(const EncPack*)enc;
+  CDR_CHECK_ARG(e.stem_w, "cdr_encoder: this handle was created without a stem");
+  CDR_CHECK_ARG(H % 16 == 0 && W % 64 == 0, "cdr_encoder: image %dx%d must have H %% 16 == 0 and W %% 64 == 0", H, W);
+  if (int rc = enc_check_grid(e, H / 4, W / 4)) return rc;
+  *bytes = plan_enc_img_ws(e, nullptr, n, H, W).bytes;
+  return CDR_OK;
+}
+int tc_encoder_forward(const void* enc, const void* x, int n, int h, int w, void* out_rows, void* workspace,
+                       size_t workspace_bytes, cudaStream_t st);
+int tc_encoder_forward_images(const void* enc, const float* images, int n, int H, int W, void* out_rows,
+                              void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const EncPack& e = *(const EncPack*)enc;
+  CDR_CHECK_ARG(e.stem_w, "cdr_encoder_forward_images: this handle was created without a stem");
+  CDR_CHECK_ARG(H % 16 == 0 && W % 64 == 0, "cdr_encoder: image %dx%d must have H %% 16 == 0 and W %% 64 == 0", H, W);
+  EncImgWs ws = plan_enc_img_ws(e, workspace, n, H, W);
+  if (ws.bytes > workspace_bytes) {
+    set_error("cdr_encoder_forward_images: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
+    return CDR_ERR_WORKSPACE;
+  }
+  set_stage("enc_stem");
+  if (int rc = launch_stem(images, n, H, W, e.stem_w, e.stem_b, ws.conv_out, ws.pooled, st)) return rc;
+  return tc_encoder_forward(enc, ws.pooled, n, H / 4, W / 4, out_rows, ws.layers, ws.layer_bytes, st);
 }
 
 int tc_encoder_out_shape(const void* enc, int h, int w, int* oh, int* ow, int* oc) {

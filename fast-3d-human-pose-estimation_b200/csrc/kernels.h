@@ -64,4 +64,10 @@ int launch_pack_conv1x1_f32(const CdrConvBn& src, int cout, int cin, int k_pad, 
 int launch_pack_deconv_f32(const CdrConvBn& src, int cin, int cout, int n_pad, float* w_out,
                            float* bias_out, cudaStream_t st);
 
+// stem.cu: ResNet stem (conv 7x7 s2 + BN + ReLU, max-pool 3x3 s2), fp32 NCHW -> bf16 NHWC
+int launch_pack_stem(const CdrConvBn& s, void* w, float* bias, cudaStream_t st);
+size_t stem_weight_bytes();
+int launch_stem(const float* x, int n, int H, int W, const void* w, const float* bias, void* conv_out, void* pooled,
+                cudaStream_t st);
+
 }  // namespace cdr

@@ -1,0 +1,200 @@
+// ResNet stem on B200: conv 7x7 stride 2 pad 3 (3 -> 64) + eval BN + ReLU, then max-pool 3x3 stride 2
+// pad 1 (reference models/encoder.py:93-97,122-125), fp32 NCHW images in, bf16 NHWC rows out — the
+// layout the tcgen05 bottleneck kernels read.
+//
+// Cin = 3 rules out the TMA/UMMA operand path (a pixel is 6 bytes), and K = 147 is tiny, so the conv
+// is an implicit GEMM on warp-level mma.sync (m16n8k16 bf16, fp32 accumulate) fed from a shared-memory
+// image patch: A[m][k] = patch[base(m) + off(k)], with the K axis laid out as 7 rows of 22 (21 taps*
+// channels + 1 zero pad) so that a fragment's (k, k+1) pair is one aligned 32-bit LDS.  HBM-bound by
+// design (100 MB in, 268 MB out per 128 images); the pool is a second, purely streaming kernel.
+#include <cuda_bf16.h>
+
+#include "kernels.h"
+
+namespace cdr {
+
+constexpr int kStemCo = 64;
+constexpr int kStemKy = 7, kStemRow = 22;          // K' = ky * 22 + (kx * 3 + ci), slot 21 of a row is a zero weight
+constexpr int kStemK = 160;                        // 7 * 22 = 154, padded to a multiple of 16
+constexpr int kStemWPitch = 168;                   // weight row pitch (elements): conflict-free B-fragment loads
+constexpr int kTileH = 8, kTileW = 32;             // conv-output tile of one CTA pass: one row per warp
+constexpr int kPatchH = 2 * kTileH + 5;            // 21 input rows
+constexpr int kPatchW = 2 * kTileW + 5;            // 69 input columns
+constexpr int kPatchPitch = 208;                   // 69 * 3 = 207 elements per patch row, padded to even
+
+// conv1 (64,3,7,7) + bn1 -> bf16 [64][kStemWPitch] in the K' order above, fp32 folded bias [64]
+__global__ void pack_stem_kernel(CdrConvBn s, __nv_bfloat16* __restrict__ w, float* __restrict__ bias) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= kStemCo * kStemWPitch) return;
+  const int n = idx / kStemWPitch, k = idx - n * kStemWPitch;
+  const double sc = (double)s.bn_weight[n] / sqrt((double)s.bn_var[n] + 1e-5);
+  if (k == 0) bias[n] = (float)((double)s.bn_bias[n] - (double)s.bn_mean[n] * sc);
+  float v = 0.f;
+  const int ky = k / kStemRow, r = k - ky * kStemRow;
+  if (ky < kStemKy && r < 21) {
+    const int kx = r / 3, ci = r - kx * 3;
+    v = (float)((double)s.weight[((n * 3 + ci) * 7 + ky) * 7 + kx] * sc);
+  }
+  w[idx] = __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// grid (conv rows / 8, images); each CTA walks the W/64 column tiles of its row band.
+__global__ void __launch_bounds__(256)
+stem_conv_kernel(const float* __restrict__ x, int H, int W, const __nv_bfloat16* __restrict__ wpk,
+                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(16) __nv_bfloat16 s_w[kStemCo * kStemWPitch];     // 21.5 KB
+  __shared__ __align__(16) __nv_bfloat16 s_p[kPatchH * kPatchPitch];     // 8.7 KB
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int img = blockIdx.y, oy0 = blockIdx.x * kTileH;
+  const int Ho = H >> 1, Wo = W >> 1;
+  for (int i = threadIdx.x; i < kStemCo * kStemWPitch / 8; i += 256)
+    reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(wpk) + i);
+  float bv[8][2];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    bv[nt][0] = __ldg(bias + nt * 8 + 2 * t);
+    bv[nt][1] = __ldg(bias + nt * 8 + 2 * t + 1);
+  }
+  // per-lane patch offsets of the two k-pairs of every k-step: off(k') = ky * pitch + r
+  int koff[kStemK / 16][2];
+#pragma unroll
+  for (int s = 0; s < kStemK / 16; ++s) {
+#pragma unroll
+    for (int hk = 0; hk < 2; ++hk) {
+      const int k = 16 * s + 8 * hk + 2 * t;
+      const int ky = k / kStemRow, r = k - ky * kStemRow;
+      koff[s][hk] = ky < kStemKy ? ky * kPatchPitch + r : 0;       // padded k: weight is zero, any address does
+    }
+  }
+  const float* xi = x + (size_t)img * 3 * H * W;
+  for (int ox0 = 0; ox0 < Wo; ox0 += kTileW) {
+    __syncthreads();                                   // previous pass done with the patch (and s_w visible)
+    const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
+    for (int i = threadIdx.x; i < kPatchH * 3 * kPatchW; i += 256) {
+      const int col = i % kPatchW, rc = i / kPatchW;
+      const int ci = rc % 3, row = rc / 3;
+      const int iy = iy0 + row, ix = ix0 + col;
+      float v = 0.f;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xi + ((size_t)ci * H + iy) * W + ix);
+      s_p[row * kPatchPitch + col * 3 + ci] = __float2bfloat16_rn(v);
+    }
+    if (threadIdx.x < kPatchH) s_p[threadIdx.x * kPatchPitch + 207] = __float2bfloat16_rn(0.f);
+    __syncthreads();
+    float acc[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+    // this warp: conv row `warp` of the tile, columns mt*16 + {g, g+8}
+    const int base0 = (2 * warp) * kPatchPitch + 6 * g;          // pixel (warp, g): patch origin, in elements
+#pragma unroll
+    for (int s = 0; s < kStemK / 16; ++s) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int b = base0 + 6 * 16 * mt;
+        a[mt][0] = *reinterpret_cast<const uint32_t*>(s_p + b + koff[s][0]);
+        a[mt][1] = *reinterpret_cast<const uint32_t*>(s_p + b + 48 + koff[s][0]);       // column g + 8
+        a[mt][2] = *reinterpret_cast<const uint32_t*>(s_p + b + koff[s][1]);
+        a[mt][3] = *reinterpret_cast<const uint32_t*>(s_p + b + 48 + koff[s][1]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const __nv_bfloat16* wr = s_w + (nt * 8 + g) * kStemWPitch + 16 * s + 2 * t;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
+        mma_bf16_16816(acc[0][nt], a[0], b0, b1);
+        mma_bf16_16816(acc[1][nt], a[1], b0, b1);
+      }
+    }
+    // + bias, ReLU, bf16, NHWC: pixel (oy0 + warp, ox0 + mt*16 + g [+8]), channels nt*8 + 2t, +1
+    const int oy = oy0 + warp;
+    if (oy < Ho) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+          const int ox = ox0 + mt * 16 + g + 8 * hr;
+          if (ox < Wo) {
+            __nv_bfloat16* o = out + (((size_t)img * Ho + oy) * Wo + ox) * kStemCo + 2 * t;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+              const float v0 = fmaxf(acc[mt][nt][2 * hr] + bv[nt][0], 0.f);
+              const float v1 = fmaxf(acc[mt][nt][2 * hr + 1] + bv[nt][1], 0.f);
+              *reinterpret_cast<__nv_bfloat162*>(o + nt * 8) = __floats2bfloat162_rn(v0, v1);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// max-pool 3x3 stride 2 pad 1 on NHWC bf16 (values are post-ReLU, so 0 is the identity of the max)
+__global__ void __launch_bounds__(256)
+maxpool3s2_nhwc_kernel(const __nv_bfloat16* __restrict__ in, int Hi, int Wi, int C8, long long total,
+                       __nv_bfloat16* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % C8);
+  long long r = idx / C8;
+  const int Wo = Wi >> 1, Ho = Hi >> 1;
+  const int ox = (int)(r % Wo);
+  r /= Wo;
+  const int oy = (int)(r % Ho);
+  const long long img = r / Ho;
+  __nv_bfloat162 m[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) m[e] = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int iy = 2 * oy + dy;
+    if (iy < 0 || iy >= Hi) continue;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int ix = 2 * ox + dx;
+      if (ix < 0 || ix >= Wi) continue;
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + ((img * Hi + iy) * Wi + ix) * (long long)(C8 * 8)) + c8);
+      const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], v[e]);
+    }
+  }
+  reinterpret_cast<uint4*>(out + ((img * Ho + oy) * Wo + ox) * (long long)(C8 * 8))[c8] = *reinterpret_cast<const uint4*>(m);
+}
+
+int launch_pack_stem(const CdrConvBn& s, void* w, float* bias, cudaStream_t st) {
+  CDR_CHECK_ARG(s.weight && s.bn_weight && s.bn_bias && s.bn_mean && s.bn_var && w && bias, "pack_stem: bad args");
+  pack_stem_kernel<<<ceil_div(kStemCo * kStemWPitch, 256), 256, 0, st>>>(s, (__nv_bfloat16*)w, bias);
+  CDR_LAUNCH_OK("pack_stem_kernel");
+  return CDR_OK;
+}
+size_t stem_weight_bytes() { return (size_t)kStemCo * kStemWPitch * sizeof(__nv_bfloat16); }
+
+// x (n,3,H,W) fp32 -> conv_out (n,H/2,W/2,64) bf16 scratch -> pooled (n,H/4,W/4,64) bf16
+int launch_stem(const float* x, int n, int H, int W, const void* w, const float* bias, void* conv_out, void* pooled,
+                cudaStream_t st) {
+  CDR_CHECK_ARG(x && w && bias && conv_out && pooled && n > 0, "stem: bad args");
+  CDR_CHECK_ARG(H % 16 == 0 && W % 64 == 0, "stem: image %dx%d must have H %% 16 == 0 and W %% 64 == 0", H, W);
+  CDR_CHECK_ARG(((uintptr_t)conv_out & 15) == 0 && ((uintptr_t)pooled & 15) == 0 && ((uintptr_t)w & 15) == 0, "stem: alignment");
+  const int Ho = H / 2, Wo = W / 2;
+  stem_conv_kernel<<<dim3(Ho / kTileH, n), 256, 0, st>>>(x, H, W, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)conv_out);
+  CDR_LAUNCH_OK("stem_conv_kernel");
+  const long long total = (long long)n * (Ho / 2) * (Wo / 2) * (kStemCo / 8);
+  maxpool3s2_nhwc_kernel<<<(unsigned)ceil_div<long long>(total, 256), 256, 0, st>>>(
+      (const __nv_bfloat16*)conv_out, Ho, Wo, kStemCo / 8, total, (__nv_bfloat16*)pooled);
+  CDR_LAUNCH_OK("maxpool3s2_nhwc_kernel");
+  return CDR_OK;
+}
+
+}  // namespace cdr

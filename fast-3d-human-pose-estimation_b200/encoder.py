@@ -86,10 +86,11 @@ class ResNet(nn.Module):
 
 
 class TcEncoder:
-    """The bottleneck stages (layer1..layer4) of a ``ResNet`` on libcdrhead's tcgen05 tap-GEMM kernel
-    (include/cdrhead.h ``cdr_encoder_*``): bf16 activations, eval-mode BN folded,
-    fp32 accumulation.  The 7x7 stem + max-pool run on torch/cuDNN in bf16 channels-last with BN
-    folded into the conv (their output IS the NHWC layout the kernels read).  Inference only;
+    """A Bottleneck ``ResNet`` on libcdrhead (include/cdrhead.h ``cdr_encoder_*``):
+    layer1..layer4 on the tcgen05 tap-GEMM kernel, the 7x7 stem + max-pool on a warp-MMA kernel
+    (``cdr_encoder_forward_images``; images with H % 16 or W % 64 != 0 fall back to a cuDNN bf16
+    stem whose channels-last output is the same NHWC layout).  bf16 activations, eval-mode BN
+    folded, fp32 accumulation.  Inference only;
     weights are re-packed when a parameter changes.  ``rows(x)`` returns the latents as bf16
     pixel-major rows (n*h*w, 2048) — what ``cdr_head_forward_rows`` consumes; ``__call__`` returns
     the reference's (n, 2048, h, w) fp32 tensor."""
@@ -101,6 +102,7 @@ class TcEncoder:
         self.resnet, self.blocks = resnet, blocks
         self._handle, self._key, self._stem = None, None, None
         self._ws = {}
+        self.torch_stem = False          # True: force the cuDNN stem (A/B timing)
 
     def _tensors(self):
         r = self.resnet
@@ -137,7 +139,8 @@ class TcEncoder:
             if b.downsample is not None:
                 arr[i].downsample = cb(b.downsample[0], b.downsample[1])
             arr[i].planes, arr[i].stride = b.conv2.out_channels, b.conv2.stride[0]
-        spec = _lib.CdrEncoderSpec(len(self.blocks), arr, self.resnet.conv1.out_channels)
+        spec = _lib.CdrEncoderSpec(len(self.blocks), arr, self.resnet.conv1.out_channels,
+                                   cb(self.resnet.conv1, self.resnet.bn1))
         handle = C.c_void_p()
         with torch.cuda.device(device):
             _lib.check(L.cdr_encoder_create(C.byref(spec), _lib.current_stream_ptr(device), C.byref(handle)))
@@ -181,15 +184,24 @@ class TcEncoder:
         dev = x.device
         handle = self._pack(dev)
         L = _lib.lib()
-        with torch.no_grad():
-            y = self.stem(x)
-        if not y.is_contiguous():
-            y = y.contiguous()
-        n, h, w, _ = y.shape
+        n, _, H, W = x.shape
+        native_stem = H % 16 == 0 and W % 64 == 0 and not self.torch_stem
+        if native_stem:
+            xin = x.detach().to(torch.float32).contiguous()
+            h, w = H // 4, W // 4
+        else:
+            with torch.no_grad():
+                xin = self.stem(x)
+            if not xin.is_contiguous():
+                xin = xin.contiguous()
+            _, h, w, _ = xin.shape
         oh, ow, oc = C.c_int(), C.c_int(), C.c_int()
         _lib.check(L.cdr_encoder_out_shape(handle, h, w, C.byref(oh), C.byref(ow), C.byref(oc)))
         nbytes = C.c_size_t()
-        _lib.check(L.cdr_encoder_workspace_bytes(handle, n, h, w, C.byref(nbytes)))
+        if native_stem:
+            _lib.check(L.cdr_encoder_workspace_bytes_images(handle, n, H, W, C.byref(nbytes)))
+        else:
+            _lib.check(L.cdr_encoder_workspace_bytes(handle, n, h, w, C.byref(nbytes)))
         key = (str(dev), nbytes.value)
         ws = self._ws.get(key)
         if ws is None:
@@ -198,8 +210,12 @@ class TcEncoder:
         if out is None:
             out = torch.empty((n * oh.value * ow.value, oc.value), dtype=torch.bfloat16, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(L.cdr_encoder_forward(handle, _lib.ptr(y), n, h, w, _lib.ptr(out), _lib.ptr(ws), nbytes.value,
-                                             _lib.current_stream_ptr(dev)))
+            if native_stem:
+                _lib.check(L.cdr_encoder_forward_images(handle, _lib.ptr(xin), n, H, W, _lib.ptr(out), _lib.ptr(ws),
+                                                        nbytes.value, _lib.current_stream_ptr(dev)))
+            else:
+                _lib.check(L.cdr_encoder_forward(handle, _lib.ptr(xin), n, h, w, _lib.ptr(out), _lib.ptr(ws),
+                                                 nbytes.value, _lib.current_stream_ptr(dev)))
         return out, (oh.value, ow.value, oc.value)
 
     def __call__(self, x):

@@ -156,6 +156,8 @@ typedef struct CdrEncoderSpec {
   int num_blocks;                 /* over layer1..layer4, in order (ResNet-101: 3+4+23+3)             */
   const CdrEncoderBlock* blocks;  /* HOST array of device-pointer structs                             */
   int in_channels;                /* 64                                                                */
+  CdrConvBn stem;                 /* conv1 (64,3,7,7) + bn1 — models/encoder.py:93-95; weight NULL: the
+                                     caller runs the stem itself and uses cdr_encoder_forward only      */
 } CdrEncoderSpec;
 typedef struct CdrEncoder CdrEncoder;
 int cdr_encoder_create(const CdrEncoderSpec* spec, void* stream, CdrEncoder** out);
@@ -165,6 +167,13 @@ int cdr_encoder_out_shape(const CdrEncoder* e, int in_h, int in_w, int* out_h, i
 /* x (n_images, in_h, in_w, 64) bf16 NHWC -> out_rows (n_images*out_h*out_w, out_c) bf16 pixel-major rows. */
 int cdr_encoder_forward(const CdrEncoder* e, const void* x_nhwc_bf16, int n_images, int in_h, int in_w,
                         void* out_rows_bf16, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The whole encoder, models/encoder.py:121-131: images (n,3,H,W) fp32 NCHW (H % 16 == 0, W % 64 == 0) ->
+ * stem (conv 7x7 s2 + BN + ReLU on warp-level tensor-core MMAs, max-pool 3x3 s2) -> layer1..4.
+ * Needs a spec with `stem` set; workspace from cdr_encoder_workspace_bytes_images. */
+int cdr_encoder_workspace_bytes_images(const CdrEncoder* e, int n_images, int img_h, int img_w, size_t* bytes);
+int cdr_encoder_forward_images(const CdrEncoder* e, const float* images, int n_images, int img_h, int img_w,
+                               void* out_rows_bf16, void* workspace, size_t workspace_bytes, void* stream);
 
 /* PoseDecoder.forward — models/decoder.py:39-46 (also the decoder half of
  * PoseResNet.forward, models/poseresnet.py:17-21).  feat (N,2048,8,8) -> heatmaps

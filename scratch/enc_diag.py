@@ -8,6 +8,7 @@ torch.manual_seed(0)
 r = ResNet(synth.make_cfg(101, 19)).cuda().eval()
 enc = TcEncoder(r)
 x = torch.randn(128, 3, 256, 256, device="cuda")
+print("native stem" if not enc.torch_stem else "torch stem")
 for _ in range(3):
     enc.rows(x)
 torch.cuda.synchronize()

@@ -84,8 +84,8 @@ def encoder_bf16(resnet, x):
 
     r = resnet
     w, b = fold(r.conv1, r.bn1)
-    y = bf(F.conv2d(bf(x), bf(w), bf(b), stride=r.conv1.stride, padding=r.conv1.padding))   # cuDNN bf16 stem
-    y = F.max_pool2d(F.relu(y), 3, 2, 1)
+    y = bf(F.relu(F.conv2d(bf(x), bf(w), b.float().double(), stride=r.conv1.stride, padding=r.conv1.padding)))
+    y = F.max_pool2d(y, 3, 2, 1)
     for li in range(1, 5):
         for blk in getattr(r, f"layer{li}"):
             t = bf(cbr(y, blk.conv1, blk.bn1, True))

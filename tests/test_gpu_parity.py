@@ -609,6 +609,9 @@ def test_tc_encoder_resnet50_vs_emulated_and_fp32(cuda_pkg):
     enc = TcEncoder(r.cuda())
     got = enc(x.cuda()).cpu().numpy()
     assert got.shape == (3, 2048, 8, 8)
+    enc.torch_stem = True                       # the cuDNN-stem fallback feeds the same kernels
+    got_t = enc(x.cuda()).cpu().numpy()
+    assert np.abs(got_t - got).max() / np.abs(got).max() < 2e-2
     e_e = np.abs(got - want_e).max() / np.abs(want_e).max()
     e_32 = np.abs(got - want_32).max() / np.abs(want_32).max()
     m_32 = np.abs(got - want_32).mean() / np.abs(want_32).mean()
