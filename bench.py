@@ -436,6 +436,35 @@ def full_pipeline(args, ctx, precision):
                                    "layer_ms": {f"layer{i + 1}": sum(v for k, v in blocks.items()
                                                                      if k.startswith("enc_block") and lo <= int(k[9:].split(".")[0]) < hi)
                                                 for i, (lo, hi) in enumerate(((0, 3), (3, 7), (7, 30), (30, 33)))}}
+    # production-shaped end to end: raw uint8 stereo frames in pinned HOST memory -> 3D joints on the host
+    try:
+        gen = torch.Generator().manual_seed(7)
+        frames_h = torch.randint(0, 256, (2, B, 256, 256, 3), dtype=torch.uint8, generator=gen).pin_memory()
+        pipe = pkg.FramePipeline(m2, B, gt={"gt3d": ctx["g3"], "gt2d_l": ctx["g2l"], "gt2d_r": ctx["g2r"], "vis": ctx["vis"]})
+
+        def run(k):
+            pipe.submit(frames_h, ctx["P_h"])
+            for _ in range(k - 1):
+                pipe.submit(frames_h, ctx["P_h"])
+                pipe.collect()
+            return pipe.collect()
+        run(3)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kk = 10
+        a.record()
+        run(kk)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / kk
+        out["e2e_uint8_frames_host"] = {
+            "pairs_per_s": B / (ms / 1e3), "ms_per_step": ms, "h2d_bytes_per_step": frames_h.numel() + 2 * B * 48,
+            "d2h_bytes_per_step": B * JOINTS * (3 + 2 + 2) * 4 + 32,
+            "api": "FramePipeline: H2D of uint8 frames (copy stream) overlapped with one CUDA graph of "
+                   "normalise+stem+layer1-4+head+MPJPE+D2H (depth 2)"}
+        del pipe
+    except Exception as e:
+        out["e2e_uint8_frames_host"] = {"error": repr(e)[:200]}
     del m2, x2
     out["note"] = ("ResNet-101 encoder = 40.7 GF/pair on torch/cuDNN (out of scope, SURVEY §8f rank 1); head = "
                    f"{precision} kernels of this repo; images resident in HBM")
@@ -523,7 +552,11 @@ def run_ours(args):
 
 
 def main():
-    os.environ["NCCL_DEBUG"] = os.environ.get("CDR_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+    # keep stdout to the one JSON line: NCCL prints its version banner there at WARN and above
+    if "CDR_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["CDR_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -12,10 +12,10 @@ from . import _lib
 from ._lib import CdrError, build
 from .cdrnet import CDRNet, CanonicalFusion, PoseDecoder, PoseResNet
 from .encoder import ResNet
-from .graph import HeadGraph, HeadPipeline
+from .graph import HeadGraph, HeadPipeline, FramePipeline
 from .geometry import baseline_keypoints, get_max_preds, triangulation
 from .metrics import calc_mpjpe, mpjpe_sums
 
 __all__ = ["CDRNet", "CanonicalFusion", "PoseDecoder", "PoseResNet", "ResNet", "calc_mpjpe",
-           "mpjpe_sums", "HeadGraph", "HeadPipeline", "get_max_preds", "baseline_keypoints", "triangulation", "build",
+           "mpjpe_sums", "HeadGraph", "HeadPipeline", "FramePipeline", "get_max_preds", "baseline_keypoints", "triangulation", "build",
            "CdrError"]

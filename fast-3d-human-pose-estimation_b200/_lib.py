@@ -82,6 +82,8 @@ _SIGNATURES = {
     "cdr_encoder_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_size_t, _vp]),
     "cdr_encoder_workspace_bytes_images": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "cdr_encoder_forward_images": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_size_t, _vp]),
+    "cdr_encoder_forward_frames_u8": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int,
+                                                C.c_int, _vp, _vp, C.c_size_t, _vp]),
     "cdr_pinv": (C.c_int, [_vp, C.c_int, C.c_double, _vp, _vp]),
     "cdr_ftl": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
                           C.c_int, C.c_int, _vp]),

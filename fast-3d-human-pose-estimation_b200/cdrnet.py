@@ -335,6 +335,19 @@ class CDRNet(nn.Module):
         return self.head(zs, proj_list, img_size=img_size)
 
 
+    def forward_frames(self, frames, proj_list, mean=None, std=None, img_size=None):
+        """Device-side input pipeline: frames = [left, right] raw uint8 CUDA tensors
+        (B,H,W,3) — or one (2B,H,W,3) tensor, left half first — instead of inference.py:40-52's
+        PIL -> ToTensor -> Normalize -> .to(device).  Needs ``encoder_precision='bf16'``."""
+        from .encoder import IMAGENET_MEAN, IMAGENET_STD
+        _require_eval(self)
+        if self._tc_encoder is None:
+            raise RuntimeError("forward_frames needs CDRNet(..., encoder_precision='bf16')")
+        x = frames if isinstance(frames, torch.Tensor) else torch.cat([frames[0], frames[1]], 0)
+        rows, _ = self._tc_encoder.rows(x, mean=mean or IMAGENET_MEAN, std=std or IMAGENET_STD)
+        return self.head(None, proj_list, img_size=int(img_size or x.shape[1]), feat_rows=rows)
+
+
 class PoseResNet(nn.Module):
     """models/poseresnet.py:10-38: ResNet encoder (torch/cuDNN) + PoseDecoder (libcdrhead)."""
 

@@ -527,6 +527,18 @@ extern "C" int cdr_encoder_forward_images(const CdrEncoder* e, const float* imag
   CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)images & 15) == 0 && ((uintptr_t)out_rows_bf16 & 15) == 0,
                 "cdr_encoder_forward_images: workspace must be 256-byte, tensors 16-byte aligned");
   timing_restart();
-  return tc_encoder_forward_images(e->impl, images, n_images, img_h, img_w, out_rows_bf16, workspace, workspace_bytes,
-                                   (cudaStream_t)stream);
+  return tc_encoder_forward_images(e->impl, images, 0, nullptr, nullptr, n_images, img_h, img_w, out_rows_bf16, workspace,
+                                   workspace_bytes, (cudaStream_t)stream);
+}
+extern "C" int cdr_encoder_forward_frames_u8(const CdrEncoder* e, const uint8_t* frames, const float* mean_host,
+                                             const float* std_host, int n_images, int img_h, int img_w,
+                                             void* out_rows_bf16, void* workspace, size_t workspace_bytes,
+                                             void* stream) {
+  CDR_CHECK_ARG(e && frames && mean_host && std_host && out_rows_bf16 && workspace && n_images > 0,
+                "cdr_encoder_forward_frames_u8: bad args");
+  CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)out_rows_bf16 & 15) == 0,
+                "cdr_encoder_forward_frames_u8: workspace must be 256-byte, output 16-byte aligned");
+  timing_restart();
+  return tc_encoder_forward_images(e->impl, frames, 1, mean_host, std_host, n_images, img_h, img_w, out_rows_bf16,
+                                   workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -1658,8 +1658,9 @@ int tc_encoder_workspace_bytes_images(const void* enc, int n, int H, int W, size
 }
 int tc_encoder_forward(const void* enc, const void* x, int n, int h, int w, void* out_rows, void* workspace,
                        size_t workspace_bytes, cudaStream_t st);
-int tc_encoder_forward_images(const void* enc, const float* images, int n, int H, int W, void* out_rows,
-                              void* workspace, size_t workspace_bytes, cudaStream_t st) {
+int tc_encoder_forward_images(const void* enc, const void* images, int is_u8, const float* mean, const float* std,
+                              int n, int H, int W, void* out_rows, void* workspace, size_t workspace_bytes,
+                              cudaStream_t st) {
   const EncPack& e = *(const EncPack*)enc;
   CDR_CHECK_ARG(e.stem_w, "cdr_encoder_forward_images: this handle was created without a stem");
   CDR_CHECK_ARG(H % 16 == 0 && W % 64 == 0, "cdr_encoder: image %dx%d must have H %% 16 == 0 and W %% 64 == 0", H, W);
@@ -1669,7 +1670,7 @@ int tc_encoder_forward_images(const void* enc, const float* images, int n, int H
     return CDR_ERR_WORKSPACE;
   }
   set_stage("enc_stem");
-  if (int rc = launch_stem(images, n, H, W, e.stem_w, e.stem_b, ws.conv_out, ws.pooled, st)) return rc;
+  if (int rc = launch_stem(images, is_u8, mean, std, n, H, W, e.stem_w, e.stem_b, ws.conv_out, ws.pooled, st)) return rc;
   return tc_encoder_forward(enc, ws.pooled, n, H / 4, W / 4, out_rows, ws.layers, ws.layer_bytes, st);
 }
 

@@ -67,7 +67,8 @@ int launch_pack_deconv_f32(const CdrConvBn& src, int cin, int cout, int n_pad, f
 // stem.cu: ResNet stem (conv 7x7 s2 + BN + ReLU, max-pool 3x3 s2), fp32 NCHW -> bf16 NHWC
 int launch_pack_stem(const CdrConvBn& s, void* w, float* bias, cudaStream_t st);
 size_t stem_weight_bytes();
-int launch_stem(const float* x, int n, int H, int W, const void* w, const float* bias, void* conv_out, void* pooled,
-                cudaStream_t st);
+// x: fp32 NCHW (is_u8 = 0) or uint8 NHWC frames normalised on the fly with HOST arrays mean[3], std[3]
+int launch_stem(const void* x, int is_u8, const float* mean, const float* std, int n, int H, int W, const void* w,
+                const float* bias, void* conv_out, void* pooled, cudaStream_t st);
 
 }  // namespace cdr

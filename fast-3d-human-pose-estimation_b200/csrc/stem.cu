@@ -45,9 +45,19 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// Input pixel fetch.  kU8 = false: fp32 NCHW tensors as the reference feeds its model (already normalised).
+// kU8 = true: raw uint8 HWC frames with torchvision's ToTensor + Normalize (inference.py:40-44) applied on
+// the fly in the same fp32 operation order — x / 255, - mean, / std — so the bf16 patch is bit-identical
+// to converting the reference's preprocessed tensor (4x fewer bytes over PCIe, no
+// host-side torchvision pass).
+struct StemNorm {
+  float mean[3], std[3];
+};
+
 // grid (conv rows / 8, images); each CTA walks the W/64 column tiles of its row band.
+template <bool kU8>
 __global__ void __launch_bounds__(256)
-stem_conv_kernel(const float* __restrict__ x, int H, int W, const __nv_bfloat16* __restrict__ wpk,
+stem_conv_kernel(const void* __restrict__ xin, int H, int W, const StemNorm nrm, const __nv_bfloat16* __restrict__ wpk,
                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
   __shared__ __align__(16) __nv_bfloat16 s_w[kStemCo * kStemWPitch];     // 21.5 KB
   __shared__ __align__(16) __nv_bfloat16 s_p[kPatchH * kPatchPitch];     // 8.7 KB
@@ -74,17 +84,32 @@ stem_conv_kernel(const float* __restrict__ x, int H, int W, const __nv_bfloat16*
       koff[s][hk] = ky < kStemKy ? ky * kPatchPitch + r : 0;       // padded k: weight is zero, any address does
     }
   }
-  const float* xi = x + (size_t)img * 3 * H * W;
+  const float* xi = reinterpret_cast<const float*>(xin) + (size_t)img * 3 * H * W;
+  const uint8_t* xu = reinterpret_cast<const uint8_t*>(xin) + (size_t)img * 3 * H * W;
   for (int ox0 = 0; ox0 < Wo; ox0 += kTileW) {
     __syncthreads();                                   // previous pass done with the patch (and s_w visible)
     const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
-    for (int i = threadIdx.x; i < kPatchH * 3 * kPatchW; i += 256) {
-      const int col = i % kPatchW, rc = i / kPatchW;
-      const int ci = rc % 3, row = rc / 3;
-      const int iy = iy0 + row, ix = ix0 + col;
-      float v = 0.f;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xi + ((size_t)ci * H + iy) * W + ix);
-      s_p[row * kPatchPitch + col * 3 + ci] = __float2bfloat16_rn(v);
+    if constexpr (!kU8) {
+      for (int i = threadIdx.x; i < kPatchH * 3 * kPatchW; i += 256) {
+        const int col = i % kPatchW, rc = i / kPatchW;
+        const int ci = rc % 3, row = rc / 3;
+        const int iy = iy0 + row, ix = ix0 + col;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xi + ((size_t)ci * H + iy) * W + ix);
+        s_p[row * kPatchPitch + col * 3 + ci] = __float2bfloat16_rn(v);
+      }
+    } else {
+      for (int i = threadIdx.x; i < kPatchH * 3 * kPatchW; i += 256) {
+        const int e = i % (3 * kPatchW), row = i / (3 * kPatchW);     // e = col * 3 + ci: contiguous in HWC
+        const int col = e / 3, ci = e - col * 3;
+        const int iy = iy0 + row, ix = ix0 + col;
+        float v = 0.f;                                                 // zero padding applies AFTER normalisation
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          const float u = (float)__ldg(xu + ((size_t)iy * W + ix) * 3 + ci);
+          v = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.f), nrm.mean[ci]), nrm.std[ci]);
+        }
+        s_p[row * kPatchPitch + e] = __float2bfloat16_rn(v);
+      }
     }
     if (threadIdx.x < kPatchH) s_p[threadIdx.x * kPatchPitch + 207] = __float2bfloat16_rn(0.f);
     __syncthreads();
@@ -182,13 +207,24 @@ int launch_pack_stem(const CdrConvBn& s, void* w, float* bias, cudaStream_t st) 
 size_t stem_weight_bytes() { return (size_t)kStemCo * kStemWPitch * sizeof(__nv_bfloat16); }
 
 // x (n,3,H,W) fp32 -> conv_out (n,H/2,W/2,64) bf16 scratch -> pooled (n,H/4,W/4,64) bf16
-int launch_stem(const float* x, int n, int H, int W, const void* w, const float* bias, void* conv_out, void* pooled,
-                cudaStream_t st) {
+int launch_stem(const void* x, int is_u8, const float* mean, const float* std, int n, int H, int W, const void* w,
+                const float* bias, void* conv_out, void* pooled, cudaStream_t st) {
   CDR_CHECK_ARG(x && w && bias && conv_out && pooled && n > 0, "stem: bad args");
+  CDR_CHECK_ARG(!is_u8 || (mean && std), "stem: uint8 frames need mean / std");
+  StemNorm nrm{};
+  for (int c = 0; c < 3; ++c) {
+    nrm.mean[c] = is_u8 ? mean[c] : 0.f;
+    nrm.std[c] = is_u8 ? std[c] : 1.f;
+  }
   CDR_CHECK_ARG(H % 16 == 0 && W % 64 == 0, "stem: image %dx%d must have H %% 16 == 0 and W %% 64 == 0", H, W);
   CDR_CHECK_ARG(((uintptr_t)conv_out & 15) == 0 && ((uintptr_t)pooled & 15) == 0 && ((uintptr_t)w & 15) == 0, "stem: alignment");
   const int Ho = H / 2, Wo = W / 2;
-  stem_conv_kernel<<<dim3(Ho / kTileH, n), 256, 0, st>>>(x, H, W, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)conv_out);
+  if (is_u8)
+    stem_conv_kernel<true><<<dim3(Ho / kTileH, n), 256, 0, st>>>(x, H, W, nrm, (const __nv_bfloat16*)w, bias,
+                                                               (__nv_bfloat16*)conv_out);
+  else
+    stem_conv_kernel<false><<<dim3(Ho / kTileH, n), 256, 0, st>>>(x, H, W, nrm, (const __nv_bfloat16*)w, bias,
+                                                                (__nv_bfloat16*)conv_out);
   CDR_LAUNCH_OK("stem_conv_kernel");
   const long long total = (long long)n * (Ho / 2) * (Wo / 2) * (kStemCo / 8);
   maxpool3s2_nhwc_kernel<<<(unsigned)ceil_div<long long>(total, 256), 256, 0, st>>>(

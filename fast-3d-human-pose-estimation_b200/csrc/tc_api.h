@@ -29,8 +29,9 @@ int tc_encoder_create(const CdrEncoderSpec& spec, void** out, cudaStream_t st);
 void tc_encoder_destroy(void* enc);
 int tc_encoder_workspace_bytes(const void* enc, int n, int h, int w, size_t* bytes);
 int tc_encoder_workspace_bytes_images(const void* enc, int n, int H, int W, size_t* bytes);
-int tc_encoder_forward_images(const void* enc, const float* images, int n, int H, int W, void* out_rows,
-                              void* workspace, size_t workspace_bytes, cudaStream_t st);
+int tc_encoder_forward_images(const void* enc, const void* images, int is_u8, const float* mean, const float* std,
+                              int n, int H, int W, void* out_rows, void* workspace, size_t workspace_bytes,
+                              cudaStream_t st);
 int tc_encoder_out_shape(const void* enc, int h, int w, int* oh, int* ow, int* oc);
 int tc_encoder_forward(const void* enc, const void* x, int n, int h, int w, void* out_rows, void* workspace,
                        size_t workspace_bytes, cudaStream_t st);

@@ -85,6 +85,10 @@ class ResNet(nn.Module):
         return self.layer4(self.layer3(self.layer2(self.layer1(x))))
 
 
+IMAGENET_MEAN = (0.485, 0.456, 0.406)      # inference.py:42-43
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
 class TcEncoder:
     """A Bottleneck ``ResNet`` on libcdrhead (include/cdrhead.h ``cdr_encoder_*``):
     layer1..layer4 on the tcgen05 tap-GEMM kernel, the 7x7 stem + max-pool on a warp-MMA kernel
@@ -174,8 +178,10 @@ class TcEncoder:
         y = F.max_pool2d(F.relu_(y), 3, 2, 1)
         return y.permute(0, 2, 3, 1)          # a view: channels-last storage is NHWC
 
-    def rows(self, x, out=None):
-        """x (n,3,S,S) CUDA -> (rows (n*h*w, C) bf16, (h, w, C))."""
+    def rows(self, x, out=None, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+        """x: (n,3,S,S) float CUDA images as the reference feeds its model, or raw (n,S,S,3) uint8 CUDA
+        frames, normalised on the fly with torchvision's ToTensor + Normalize(mean, std)
+        (inference.py:40-44).  -> (rows (n*h*w, C) bf16, (h, w, C))."""
         from . import _lib
         if not x.is_cuda:
             raise RuntimeError("the tcgen05 encoder has no CPU path")
@@ -184,10 +190,18 @@ class TcEncoder:
         dev = x.device
         handle = self._pack(dev)
         L = _lib.lib()
-        n, _, H, W = x.shape
-        native_stem = H % 16 == 0 and W % 64 == 0 and not self.torch_stem
+        u8 = x.dtype == torch.uint8
+        if u8:
+            n, H, W, c = x.shape
+            if c != 3:
+                raise ValueError(f"uint8 frames must be (n,H,W,3), got {tuple(x.shape)}")
+            if H % 16 or W % 64:
+                raise ValueError("uint8 frames need H % 16 == 0 and W % 64 == 0")
+        else:
+            n, _, H, W = x.shape
+        native_stem = H % 16 == 0 and W % 64 == 0 and (u8 or not self.torch_stem)
         if native_stem:
-            xin = x.detach().to(torch.float32).contiguous()
+            xin = x.detach().contiguous() if u8 else x.detach().to(torch.float32).contiguous()
             h, w = H // 4, W // 4
         else:
             with torch.no_grad():
@@ -209,13 +223,18 @@ class TcEncoder:
             ws = self._ws[key] = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
         if out is None:
             out = torch.empty((n * oh.value * ow.value, oc.value), dtype=torch.bfloat16, device=dev)
+        st = _lib.current_stream_ptr(dev)
         with torch.cuda.device(dev):
-            if native_stem:
+            if u8:
+                m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+                _lib.check(L.cdr_encoder_forward_frames_u8(handle, _lib.ptr(xin), m3, s3, n, H, W, _lib.ptr(out),
+                                                           _lib.ptr(ws), nbytes.value, st))
+            elif native_stem:
                 _lib.check(L.cdr_encoder_forward_images(handle, _lib.ptr(xin), n, H, W, _lib.ptr(out), _lib.ptr(ws),
-                                                        nbytes.value, _lib.current_stream_ptr(dev)))
+                                                        nbytes.value, st))
             else:
                 _lib.check(L.cdr_encoder_forward(handle, _lib.ptr(xin), n, h, w, _lib.ptr(out), _lib.ptr(ws),
-                                                 nbytes.value, _lib.current_stream_ptr(dev)))
+                                                 nbytes.value, st))
         return out, (oh.value, ow.value, oc.value)
 
     def __call__(self, x):

@@ -191,3 +191,96 @@ class HeadPipeline:
         self.done[s].synchronize()
         self.n_collected += 1
         return s, self.kp_host[s], self.xyz_host[s], (self.sums_host[s] if self.sums_host is not None else None)
+
+
+class FramePipeline:
+    """The whole CDRNet pipeline as a depth-2 software pipeline over batches of raw stereo frames:
+
+        submit(i):  copy stream    pinned host uint8 frames (2,B,H,W,3) + P  --H2D-->  device buffers [i % 2]
+                    compute stream one CUDA graph: ToTensor/Normalize + stem + layer1-4 (cdr_encoder_forward_frames_u8)
+                                   -> cdr_head_forward_rows [-> MPJPE sums] -> D2H of 2D/3D joints (+ sums)
+        collect():  waits for the oldest batch in flight, returns its pinned host results.
+
+    12 bytes per pixel of fp32 tensors shrink to 3 on PCIe and the host never runs torchvision.
+    Needs ``CDRNet(..., encoder_precision='bf16')``."""
+
+    def __init__(self, model, batch, img_hw=(256, 256), gt=None, mean=None, std=None, warmup=2):
+        if model._tc_encoder is None:
+            raise RuntimeError("FramePipeline needs CDRNet(..., encoder_precision='bf16')")
+        self.model, self.gt, self.batch = model, gt, batch
+        self.mean, self.std = mean, std
+        self.dev = dev = next(model.CF.parameters()).device
+        b, j, (H, W) = batch, model.decoder.num_joints, img_hw
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.compute_stream = torch.cuda.Stream(dev)
+        self.frames_dev = [torch.zeros((2 * b, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.P_dev = [[torch.zeros((b, 3, 4), dtype=torch.float32, device=dev) for _ in range(2)] for _ in range(2)]
+        self.kp_host = [[torch.empty((b, j, 2), dtype=torch.float32).pin_memory() for _ in range(2)] for _ in range(2)]
+        self.xyz_host = [torch.empty((b, j, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.xyz_dev = [torch.empty((b, j, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.sums_host = [torch.empty(4, dtype=torch.float64).pin_memory() for _ in range(2)] if gt is not None else None
+        self.sums_dev = [torch.zeros(4, dtype=torch.float64, device=dev) for _ in range(2)] if gt is not None else None
+        self.h2d_done = [torch.cuda.Event() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        self.n_submitted = self.n_collected = 0
+        self.compute_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.compute_stream):
+            for s in range(2):
+                for v in range(2):
+                    self.P_dev[s][v][:, :, :3] = torch.eye(3, device=dev)    # any full-rank P for the warm-up
+            for _ in range(max(1, warmup)):
+                self._compute(0)
+        torch.cuda.synchronize(dev)
+        key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+        self._workspace = _cdrnet._WS.get(key)
+        self._enc_workspace = dict(model._tc_encoder._ws)       # keep the encoder scratch the graphs point into alive
+        self.graphs = []
+        for s in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.compute_stream):
+                self._compute(s)
+            self.graphs.append(g)
+        torch.cuda.synchronize(dev)
+
+    def _compute(self, s):
+        (kl, kr), xyz = self.model.forward_frames(self.frames_dev[s], self.P_dev[s], mean=self.mean, std=self.std)
+        self.xyz_dev[s].copy_(xyz)
+        self.kp_host[s][0].copy_(kl, non_blocking=True)
+        self.kp_host[s][1].copy_(kr, non_blocking=True)
+        self.xyz_host[s].copy_(xyz, non_blocking=True)
+        if self.gt is not None:
+            g = self.gt
+            self.sums_dev[s].copy_(mpjpe_sums([kl, kr], xyz, g["gt3d"], g["gt2d_l"], g["gt2d_r"], g.get("vis")))
+            self.sums_host[s].copy_(self.sums_dev[s], non_blocking=True)
+
+    def submit(self, frames_host, P_host, post=None):
+        """frames_host: pinned uint8 (2,B,H,W,3) or [left, right] each (B,H,W,3); P_host: [P_l, P_r] pinned fp32."""
+        if self.n_submitted - self.n_collected >= 2:
+            raise RuntimeError("FramePipeline: two batches already in flight — collect() first")
+        s = self.n_submitted % 2
+        b = self.batch
+        with torch.cuda.stream(self.copy_stream):
+            if isinstance(frames_host, torch.Tensor):
+                self.frames_dev[s].copy_(frames_host.reshape(self.frames_dev[s].shape), non_blocking=True)
+            else:
+                self.frames_dev[s][:b].copy_(frames_host[0], non_blocking=True)
+                self.frames_dev[s][b:].copy_(frames_host[1], non_blocking=True)
+            for d, h in zip(self.P_dev[s], P_host):
+                d.copy_(h, non_blocking=True)
+            self.h2d_done[s].record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(self.h2d_done[s])
+            self.graphs[s].replay()
+            if post is not None:
+                post(s)
+            self.done[s].record(self.compute_stream)
+        self.n_submitted += 1
+        return s
+
+    def collect(self):
+        if self.n_collected >= self.n_submitted:
+            raise RuntimeError("FramePipeline: nothing in flight")
+        s = self.n_collected % 2
+        self.done[s].synchronize()
+        self.n_collected += 1
+        return s, self.kp_host[s], self.xyz_host[s], (self.sums_host[s] if self.sums_host is not None else None)

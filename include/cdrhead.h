@@ -175,6 +175,13 @@ int cdr_encoder_workspace_bytes_images(const CdrEncoder* e, int n_images, int im
 int cdr_encoder_forward_images(const CdrEncoder* e, const float* images, int n_images, int img_h, int img_w,
                                void* out_rows_bf16, void* workspace, size_t workspace_bytes, void* stream);
 
+/* SURVEY §8f rank 2 — device-side input pipeline: the same from raw uint8 frames (n, H, W, 3) HWC with
+ * torchvision's ToTensor + Normalize(mean, std) of inference.py:40-44 fused into the stem's patch load
+ * (x / 255, - mean, / std in fp32, the reference's operation order).  mean/std: HOST float[3]. */
+int cdr_encoder_forward_frames_u8(const CdrEncoder* e, const uint8_t* frames, const float* mean_host,
+                                  const float* std_host, int n_images, int img_h, int img_w, void* out_rows_bf16,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* PoseDecoder.forward — models/decoder.py:39-46 (also the decoder half of
  * PoseResNet.forward, models/poseresnet.py:17-21).  feat (N,2048,8,8) -> heatmaps
  * (N,J,64,64) fp32 NCHW. */

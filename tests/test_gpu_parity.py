@@ -643,3 +643,34 @@ def test_full_pipeline_tc_encoder(cuda_pkg, precision):
     print(f"\nfull pipeline [{precision}] tcgen05 bf16 encoder vs torch fp32 encoder: d2D max {d2:.3f} px")
     assert torch.isfinite(xyz).all() and kl.shape == (b, 19, 2) and xyz.shape == (b, 19, 3)
     assert d2 < 1.5
+
+
+def test_frames_u8_match_reference_preprocessing(cuda_pkg):
+    """uint8 HWC frames through the fused ToTensor + Normalize stem give exactly
+    the latents of the reference's host-side preprocessing (inference.py:40-44) fed as fp32 tensors,
+    and FramePipeline (graph replay, H2D/compute overlap) returns the eager forward_frames result."""
+    from fast_3d_human_pose_estimation_b200.encoder import TcEncoder, IMAGENET_MEAN, IMAGENET_STD
+    b = 2
+    torch.manual_seed(0)
+    m = cuda_pkg.CDRNet(synth.make_cfg(50, 19), precision="fp32", encoder_precision="bf16")
+    m.load_state_dict(synth.make_head_state_dict(seed=0, calibrated=True), strict=False)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(3)
+    frames = [torch.randint(0, 256, (b, 256, 256, 3), dtype=torch.uint8, generator=g) for _ in range(2)]
+    mean = torch.tensor(IMAGENET_MEAN).reshape(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD).reshape(1, 3, 1, 1)
+    pre = [(f.permute(0, 3, 1, 2).float().div(255).sub_(mean).div_(std)) for f in frames]   # ToTensor + Normalize
+    rows_u8, _ = m._tc_encoder.rows(torch.cat(frames, 0).cuda())
+    rows_f32, _ = m._tc_encoder.rows(torch.cat(pre, 0).cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(rows_u8, rows_f32), "fused normalisation must be bit-identical to the reference's preprocessing"
+    cams = synth.make_cameras(b, seed=2)
+    Ps = [torch.from_numpy(cams["P_l"]), torch.from_numpy(cams["P_r"])]
+    (kl, kr), xyz = m.forward_frames([f.cuda() for f in frames], [p.cuda() for p in Ps])
+    pipe = cuda_pkg.FramePipeline(m, b)
+    fh = torch.stack(frames, 0).pin_memory()
+    pipe.submit(fh, [p.pin_memory() for p in Ps])
+    pipe.submit([f.pin_memory() for f in frames], [p.pin_memory() for p in Ps])
+    for _ in range(2):
+        _, kp_h, xyz_h, _ = pipe.collect()
+        assert torch.equal(kp_h[0], kl.cpu()) and torch.equal(kp_h[1], kr.cpu()) and torch.equal(xyz_h, xyz.cpu())
