@@ -415,57 +415,65 @@ def full_pipeline(args, ctx, precision):
     enc_ms = timed(bf16_enc)
     out["encoder_bf16_autocast_channels_last"] = {"pairs_per_s": B / (ms / 1e3), "ms_per_step": ms,
                                                   "encoder_ms": enc_ms, "head_share": max(0.0, 1.0 - enc_ms / ms)}
-    # the whole encoder on this repo's kernels (stem: warp-MMA, layer1-4: tcgen05 tap-GEMM)
+    # the whole encoder on this repo's kernels (stem: warp-MMA, layer1-4: tcgen05 tap-GEMM),
+    # with the fp32-accurate head and with the bf16 head (the natural partner of a bf16 encoder)
     del enc, xcl
-    torch.manual_seed(0)
-    m2 = pkg.CDRNet(synth.make_cfg(101, JOINTS), precision=precision, encoder_precision="bf16")
-    m2.load_state_dict(ctx["sd"], strict=False)
-    m2 = m2.to(dev).eval()
-    ms = timed(lambda: m2(xs, ctx["Ps"]))
     x2 = torch.cat(xs, 0)
-    enc_ms = timed(lambda: m2._tc_encoder.rows(x2))
-    _lib.stage_timing_begin(dev)
-    m2._tc_encoder.rows(x2)
-    blocks = {}
-    for name, t in _lib.stage_timing_end():
-        blocks[name] = blocks.get(name, 0.0) + t
-    stem_ms = blocks.get("enc_stem", 0.0)
-    out["encoder_bf16_tcgen05"] = {"pairs_per_s": B / (ms / 1e3), "ms_per_step": ms, "encoder_ms": enc_ms,
-                                   "stem_ms": stem_ms, "head_share": max(0.0, 1.0 - enc_ms / ms),
-                                   "encoder_tflops": 40747.7e6 * B / (enc_ms / 1e3) / 1e12,
-                                   "layer_ms": {f"layer{i + 1}": sum(v for k, v in blocks.items()
-                                                                     if k.startswith("enc_block") and lo <= int(k[9:].split(".")[0]) < hi)
-                                                for i, (lo, hi) in enumerate(((0, 3), (3, 7), (7, 30), (30, 33)))}}
-    # production-shaped end to end: raw uint8 stereo frames in pinned HOST memory -> 3D joints on the host
-    try:
-        gen = torch.Generator().manual_seed(7)
-        frames_h = torch.randint(0, 256, (2, B, 256, 256, 3), dtype=torch.uint8, generator=gen).pin_memory()
-        pipe = pkg.FramePipeline(m2, B, gt={"gt3d": ctx["g3"], "gt2d_l": ctx["g2l"], "gt2d_r": ctx["g2r"], "vis": ctx["vis"]})
+    gt = {"gt3d": ctx["g3"], "gt2d_l": ctx["g2l"], "gt2d_r": ctx["g2r"], "vis": ctx["vis"]}
+    for head_prec in dict.fromkeys([precision, "bf16"]):
+        torch.manual_seed(0)
+        m2 = pkg.CDRNet(synth.make_cfg(101, JOINTS), precision=head_prec, encoder_precision="bf16")
+        m2.load_state_dict(ctx["sd"], strict=False)
+        m2 = m2.to(dev).eval()
+        ms = timed(lambda: m2(xs, ctx["Ps"]))
+        enc_ms = timed(lambda: m2._tc_encoder.rows(x2))
+        _lib.stage_timing_begin(dev)
+        m2._tc_encoder.rows(x2)
+        blocks = {}
+        for name, t in _lib.stage_timing_end():
+            blocks[name] = blocks.get(name, 0.0) + t
+        rec = {"pairs_per_s": B / (ms / 1e3), "ms_per_step": ms, "encoder_ms": enc_ms,
+               "stem_ms": blocks.get("enc_stem", 0.0), "head_share": max(0.0, 1.0 - enc_ms / ms),
+               "encoder_tflops": 40747.7e6 * B / (enc_ms / 1e3) / 1e12,
+               "layer_ms": {f"layer{i + 1}": sum(v for k, v in blocks.items()
+                                                 if k.startswith("enc_block") and lo <= int(k[9:].split(".")[0]) < hi)
+                            for i, (lo, hi) in enumerate(((0, 3), (3, 7), (7, 30), (30, 33)))}}
+        # production-shaped end to end: raw uint8 stereo frames in pinned HOST memory -> 3D joints on the host
+        for bb in (B, 2 * B):
+            try:
+                gen = torch.Generator().manual_seed(7)
+                frames_h = torch.randint(0, 256, (2, bb, 256, 256, 3), dtype=torch.uint8, generator=gen).pin_memory()
+                P_h = [p.repeat(bb // B, 1, 1).pin_memory() for p in ctx["P_h"]]
+                pipe = pkg.FramePipeline(m2, bb, gt={k: v.repeat(bb // B, *([1] * (v.dim() - 1))) for k, v in gt.items()})
 
-        def run(k):
-            pipe.submit(frames_h, ctx["P_h"])
-            for _ in range(k - 1):
-                pipe.submit(frames_h, ctx["P_h"])
-                pipe.collect()
-            return pipe.collect()
-        run(3)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kk = 10
-        a.record()
-        run(kk)
-        b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / kk
-        out["e2e_uint8_frames_host"] = {
-            "pairs_per_s": B / (ms / 1e3), "ms_per_step": ms, "h2d_bytes_per_step": frames_h.numel() + 2 * B * 48,
-            "d2h_bytes_per_step": B * JOINTS * (3 + 2 + 2) * 4 + 32,
-            "api": "FramePipeline: H2D of uint8 frames (copy stream) overlapped with one CUDA graph of "
-                   "normalise+stem+layer1-4+head+MPJPE+D2H (depth 2)"}
-        del pipe
-    except Exception as e:
-        out["e2e_uint8_frames_host"] = {"error": repr(e)[:200]}
-    del m2, x2
+                def run(k):
+                    pipe.submit(frames_h, P_h)
+                    for _ in range(k - 1):
+                        pipe.submit(frames_h, P_h)
+                        pipe.collect()
+                    return pipe.collect()
+                run(3)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                kk = 10
+                a.record()
+                run(kk)
+                b.record()
+                torch.cuda.synchronize()
+                e_ms = a.elapsed_time(b) / kk
+                rec["e2e_uint8_frames_host" + ("" if bb == B else f"_batch{bb}")] = {
+                    "pairs_per_s": bb / (e_ms / 1e3), "ms_per_step": e_ms, "pairs_per_step": bb,
+                    "h2d_bytes_per_step": frames_h.numel() + 2 * bb * 48,
+                    "d2h_bytes_per_step": bb * JOINTS * (3 + 2 + 2) * 4 + 32,
+                    "api": "FramePipeline: H2D of uint8 frames (copy stream) overlapped with one CUDA graph of "
+                           "normalise+stem+layer1-4+head+MPJPE+D2H (depth 2)"}
+                del pipe, frames_h
+            except Exception as e:
+                rec["e2e_uint8_frames_host" + ("" if bb == B else f"_batch{bb}")] = {"error": repr(e)[:200]}
+        out["encoder_bf16_tcgen05" + ("" if head_prec == precision else "_head_bf16")] = rec
+        del m2
+        torch.cuda.empty_cache()
+    del x2
     out["note"] = ("ResNet-101 encoder = 40.7 GF/pair on torch/cuDNN (out of scope, SURVEY §8f rank 1); head = "
                    f"{precision} kernels of this repo; images resident in HBM")
     del model, xs
