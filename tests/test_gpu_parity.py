@@ -674,3 +674,25 @@ def test_frames_u8_match_reference_preprocessing(cuda_pkg):
     for _ in range(2):
         _, kp_h, xyz_h, _ = pipe.collect()
         assert torch.equal(kp_h[0], kl.cpu()) and torch.equal(kp_h[1], kr.cpu()) and torch.equal(xyz_h, xyz.cpu())
+
+
+def test_tc_encoder_shapes_and_errors(cuda_pkg):
+    """Other image sizes / batch 1 through the tcgen05 encoder; unsupported geometry fails loudly."""
+    from fast_3d_human_pose_estimation_b200.encoder import TcEncoder
+    r = _seeded_resnet(50, seed=3).cuda()
+    enc = TcEncoder(r)
+    for n, hw in ((1, (256, 256)), (2, (128, 256)), (1, (512, 512))):
+        x = torch.randn(n, 3, *hw, generator=torch.Generator().manual_seed(n)).cuda()
+        with torch.no_grad():
+            want = r(x)
+        got = enc(x)
+        assert got.shape == want.shape == (n, 2048, hw[0] // 32, hw[1] // 32)
+        rel = float((got - want).abs().max() / want.abs().max())
+        print(f"\ntcgen05 encoder {n}x{hw}: rel err vs fp32 torch {rel:.2e}")
+        assert rel < 6e-2
+    with pytest.raises(cuda_pkg.CdrError):
+        enc(torch.randn(1, 3, 192, 192).cuda())        # 48-wide feature maps do not tile into 128-pixel boxes
+    with pytest.raises(RuntimeError):
+        enc(torch.randn(1, 3, 256, 256))               # no CPU path
+    with pytest.raises(NotImplementedError):
+        TcEncoder(_seeded_resnet(18))                  # BasicBlock ResNets stay on torch
