@@ -61,6 +61,7 @@ class CdrError(RuntimeError):
 _SIGNATURES = {
     "cdr_abi_version": (C.c_int, []),
     "cdr_last_error": (C.c_char_p, []),
+    "cdr_debug_words": (C.POINTER(C.c_uint), []),
     "cdr_launch_count": (C.c_ulonglong, []),
     "cdr_launch_count_reset": (None, []),
     "cdr_stage_timing_begin": (C.c_int, [_vp]),

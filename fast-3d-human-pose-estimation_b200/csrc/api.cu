@@ -8,6 +8,10 @@
 
 namespace cdr {
 
+static unsigned int* g_debug_host = nullptr;
+int tc_set_debug(unsigned int* d);      // gemm_tc.cu / heatmap.cu: point their copy of g_cdr_debug at the words
+int heat_set_debug(unsigned int* d);
+
 static thread_local char g_err[512] = "";
 static thread_local unsigned long long g_launches = 0;
 
@@ -541,4 +545,19 @@ extern "C" int cdr_encoder_forward_frames_u8(const CdrEncoder* e, const uint8_t*
   timing_restart();
   return tc_encoder_forward_images(e->impl, frames, 1, mean_host, std_host, n_images, img_h, img_w, out_rows_bf16,
                                    workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// Diagnostics: 16 host-mapped words; word 0 == 0xdeadbeef after an mbarrier wait inside a kernel timed out
+// (then 1..6 = block, thread, shared-memory address of the barrier, parity, gridDim.x, blockDim.x).
+extern "C" const unsigned int* cdr_debug_words(void) {
+  if (!g_debug_host) {
+    unsigned int* h = nullptr;
+    if (cudaHostAlloc(&h, 16 * sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    for (int i = 0; i < 16; ++i) h[i] = 0;
+    unsigned int* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) return nullptr;
+    if (tc_set_debug(d) != CDR_OK || heat_set_debug(d) != CDR_OK) return nullptr;
+    g_debug_host = h;
+  }
+  return g_debug_host;
 }

@@ -362,9 +362,11 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+#ifdef CDR_ENABLE_PDL
   // Programmatic dependent launch: let the next tap-GEMM's CTAs take over SMs as ours retire (its barrier
   // init / TMEM alloc / descriptor prefetch then overlap our tail and the wave-quantisation gap) ...
   ptx::grid_dep_launch();
+#endif
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
@@ -393,8 +395,10 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+#ifdef CDR_ENABLE_PDL
   // ... and do not touch anything the previous kernel wrote (activations, scale slots) before it is complete
   ptx::grid_dep_wait();
+#endif
   const uint32_t tmem_base = *tmem_base_slot;
   // TMEM columns: bf16 : [0,BN) [BN,2BN)               two tile accumulators
   //               split: [0,BN) [BN,2BN)               two main-term chunk accumulators
@@ -514,7 +518,16 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         ptx::umma_commit(&tmem_full[acc]);         // tile (bf16) / correction accumulator (split) complete
         if constexpr (KIND == kKindBF16 && BN == 128) {
-          if (p.has_res) ++it;                     // the residual stage belongs to the epilogue
+          if (p.has_res) {
+            // The residual stage belongs to the epilogue, but this thread must still OBSERVE its phase: an
+            // mbarrier wait can only tell the current phase from the one before it.  Skipping the phase let a
+            // later wait on the same stage (S uses on) mistake "residual still loading" for "next K-block
+            // landed" whenever the residual's HBM load outlasted S-1 K-blocks of MMAs — the tensor core then
+            // consumed the residual as operands and empty[s] got two arrivals: a launch failure once in
+            // ~10^7 tiles (found by stressing the encoder; the tests never hit it).
+            ptx::mbar_wait(&full[it % S], (it / S) & 1);
+            ++it;
+          }
         }
       }
     }
@@ -793,10 +806,8 @@ struct TcLaunch {
   int res_pitch;
 };
 
-// CDR_PDL=1 launches the tap-GEMMs with programmatic stream serialization (the kernel already carries
-// griddepcontrol.launch_dependents / .wait).  Measured on B200: encoder 4.50 -> 4.30 ms, head -1 %; OFF by
-// default because a bench run that replays the captured graphs back to back died with a launch failure
-// under it (eager runs and all GPU tests pass) — to be root-caused in round 2.
+// Programmatic dependent launch is compiled out unless the library is built with -DCDR_ENABLE_PDL (then
+// CDR_PDL=1 turns it on at run time).  Measured on B200 with it on: encoder 4.50 -> 4.30 ms, head -1 %.
 static bool tc_use_pdl() {
   static int v = -1;
   if (v < 0) {
@@ -929,7 +940,12 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
+#ifdef CDR_ENABLE_PDL
   cfg.numAttrs = tc_use_pdl() ? 1 : 0;
+#else
+  cfg.numAttrs = 0;
+  (void)tc_use_pdl;
+#endif
   CDR_CUDA(cudaLaunchKernelEx(&cfg, tap_gemm_tc_kernel<BN, KIND, OFMT>, tmap_a[0], tmap_a[1], l.layer->map[0],
                               l.layer->map[KindTraits<KIND>::kPlanes - 1], tmap_c[0], tmap_c[1], tmap_r, p));
   CDR_LAUNCH_OK("tap_gemm_tc_kernel");
@@ -1759,6 +1775,11 @@ int tc_encoder_forward(const void* enc, const void* x, int n, int h, int w, void
     H = Ho; W = Wo;
   }
   set_stage(nullptr);
+  return CDR_OK;
+}
+
+int tc_set_debug(unsigned int* d) {
+  CDR_CUDA(cudaMemcpyToSymbol(ptx::g_cdr_debug, &d, sizeof(d)));
   return CDR_OK;
 }
 

@@ -390,6 +390,11 @@ static int check_heat_shape(const char* who, int H, int W, int elem_bytes) {
   return CDR_OK;
 }
 
+int heat_set_debug(unsigned int* d) {
+  CDR_CUDA(cudaMemcpyToSymbol(ptx::g_cdr_debug, &d, sizeof(d)));
+  return CDR_OK;
+}
+
 }  // namespace cdr
 
 using namespace cdr;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace cdr {
 namespace ptx {
@@ -59,12 +60,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Spin on try_wait (which itself suspends the thread for a HW-defined time).  A protocol bug
 // must not hang the GPU: after ~4 s of waiting the kernel traps (cudaErrorLaunchFailure).
+// host-mapped words a timed-out wait writes before trapping (api.cu: cdr_debug_words) — device printf
+// output is lost when the context dies, a store to mapped pinned memory is not
+static __device__ unsigned int* g_cdr_debug = nullptr;   // one copy per translation unit (no -rdc)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xfff) == 0 && clock64() - t0 > 8000000000LL) __trap();
+    if ((++spins & 0xfff) == 0 && clock64() - t0 > 8000000000LL) {
+      if (g_cdr_debug) {
+        volatile unsigned int* d = g_cdr_debug;
+        d[1] = blockIdx.x; d[2] = threadIdx.x; d[3] = smem_u32(bar); d[4] = parity; d[5] = gridDim.x; d[6] = blockDim.x;
+        d[0] = 0xdeadbeefu;
+        __threadfence_system();
+      }
+      __trap();
+    }
   }
 }
 

@@ -99,6 +99,10 @@ typedef struct CdrHeadTaps {
 } CdrHeadTaps;
 
 int cdr_abi_version(void);
+/* Diagnostics: arms (first call) and returns 16 host-mapped words.  Word 0 becomes 0xdeadbeef if an
+ * mbarrier wait inside a kernel timed out (a protocol bug): 1..6 = block, thread, shared-memory address
+ * of the barrier, parity, gridDim.x, blockDim.x. */
+const unsigned int* cdr_debug_words(void);
 const char* cdr_last_error(void);
 /* Number of kernels this library has launched from the calling thread since the last
  * reset (bench.py's `gpu_launches`). */
