@@ -474,6 +474,28 @@ def full_pipeline(args, ctx, precision):
         del m2
         torch.cuda.empty_cache()
     del x2
+    # BASELINE configs[2]: baseline.py — PoseResNet-101 2D heat-maps on both views, arg-max x4 -> uint8, DLT
+    # triangulation; 256 images (128 pairs), bf16, all on this library (frames as uint8 in HBM)
+    try:
+        torch.manual_seed(0)
+        pr = pkg.PoseResNet(synth.make_cfg(101, JOINTS), precision="bf16", encoder_precision="bf16").to(dev).eval()
+        nb = 128
+        frames = torch.randint(0, 256, (2 * nb, 256, 256, 3), dtype=torch.uint8, device=dev)
+        cams = synth.make_cameras(nb, seed=5)
+        row4 = np.tile([[[0, 0, 0, 1.0]]], (nb, 1, 1))
+        P1 = torch.from_numpy(np.concatenate([cams["P_l"], row4], 1).astype(np.float64)).to(dev)
+        P2 = torch.from_numpy(np.concatenate([cams["P_r"], row4], 1).astype(np.float64)).to(dev)
+
+        def baseline_step():
+            pts = pkg.baseline_keypoints(pr(frames))
+            return pkg.triangulation(P1, P2, pts[:nb], pts[nb:])
+        ms = timed(baseline_step)
+        out["baseline_poseresnet101_bf16_batch256"] = {"pairs_per_s": nb / (ms / 1e3), "images_per_s": 2 * nb / (ms / 1e3),
+                                                       "ms_per_step": ms, "images_per_step": 2 * nb}
+        del pr, frames
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["baseline_poseresnet101_bf16_batch256"] = {"error": repr(e)[:200]}
     out["note"] = ("ResNet-101 encoder = 40.7 GF/pair on torch/cuDNN (out of scope, SURVEY §8f rank 1); head = "
                    f"{precision} kernels of this repo; images resident in HBM")
     del model, xs

@@ -73,6 +73,7 @@ _SIGNATURES = {
     "cdr_head_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_int, C.c_int,
                                    _vp, _vp, _vp, C.POINTER(CdrHeadTaps), _vp, C.c_size_t, _vp]),
     "cdr_decoder_forward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_size_t, _vp]),
+    "cdr_decoder_forward_rows": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_size_t, _vp]),
     "cdr_head_forward_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_int, C.c_int,
                                         _vp, _vp, _vp, C.POINTER(CdrHeadTaps), _vp, C.c_size_t, _vp]),
     "cdr_encoder_create": (C.c_int, [C.POINTER(CdrEncoderSpec), _vp, C.POINTER(_vp)]),

@@ -101,6 +101,24 @@ class PoseDecoder(nn.Module):
                                          nbytes.value, _lib.current_stream_ptr(x.device)))
         return out
 
+    def forward_rows(self, rows):
+        """The same on latents given as bf16 pixel-major rows (n*64, 2048) — the tcgen05 encoder's output."""
+        _require_eval(self)
+        if not (rows.is_cuda and rows.dtype == torch.bfloat16 and rows.is_contiguous() and rows.dim() == 2
+                and rows.shape[1] == 2048 and rows.shape[0] % 64 == 0):
+            raise ValueError("forward_rows expects a contiguous CUDA bf16 tensor of shape (n*64, 2048)")
+        n = rows.shape[0] // 64
+        handle = self._packed.get(_decoder_tensors(self, ""), rows.device)
+        L = _lib.lib()
+        nbytes = C.c_size_t()
+        _lib.check(L.cdr_decoder_workspace_bytes(handle, n, C.byref(nbytes)))
+        ws = _workspace(rows.device, nbytes.value)
+        out = torch.empty((n, self.num_joints, 64, 64), dtype=torch.float32, device=rows.device)
+        with torch.cuda.device(rows.device):
+            _lib.check(L.cdr_decoder_forward_rows(handle, _lib.ptr(rows), n, _lib.ptr(out), _lib.ptr(ws),
+                                                  nbytes.value, _lib.current_stream_ptr(rows.device)))
+        return out
+
 
 def _require_eval(m):
     if m.training:
@@ -351,12 +369,21 @@ class CDRNet(nn.Module):
 class PoseResNet(nn.Module):
     """models/poseresnet.py:10-38: ResNet encoder (torch/cuDNN) + PoseDecoder (libcdrhead)."""
 
-    def __init__(self, cfg, precision="fp32"):
+    def __init__(self, cfg, precision="fp32", encoder_precision="torch"):
         super().__init__()
+        if encoder_precision not in ("torch", "bf16"):
+            raise ValueError(f"encoder_precision must be 'torch' or 'bf16', got {encoder_precision!r}")
         self.encoder = ResNet(cfg)
         self.decoder = PoseDecoder(cfg, precision)
+        self.encoder_precision = encoder_precision
+        self._tc_encoder = TcEncoder(self.encoder) if encoder_precision == "bf16" else None
 
     def forward(self, x):
+        """x: (N,3,256,256) float images — or, with encoder_precision='bf16', raw (N,256,256,3) uint8 frames."""
+        if self._tc_encoder is not None and self.decoder._packed.precision != "fp32_ffma" and \
+                tuple(x.shape[-3:] if x.dtype == torch.uint8 else x.shape[-2:])[:2] == (256, 256):
+            rows, _ = self._tc_encoder.rows(x)
+            return self.decoder.forward_rows(rows)
         with torch.no_grad():
             feats = self.encoder(x)
         return self.decoder(feats)

@@ -444,7 +444,7 @@ extern "C" int cdr_decoder_forward(const CdrWeights* w, const float* feat, int n
   CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "cdr_decoder_forward: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (w->precision != CDR_PREC_FP32)
-    return tc_decoder_forward(w->tc, feat, n_images, heatmaps, workspace, workspace_bytes, st);
+    return tc_decoder_forward(w->tc, nullptr, feat, n_images, heatmaps, workspace, workspace_bytes, st);
   DecWs ws = plan_dec_f32(workspace, n_images);
   if (ws.bytes > workspace_bytes) {
     set_error("cdr_decoder_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
@@ -560,4 +560,15 @@ extern "C" const unsigned int* cdr_debug_words(void) {
     g_debug_host = h;
   }
   return g_debug_host;
+}
+
+extern "C" int cdr_decoder_forward_rows(const CdrWeights* w, const void* feat_rows, int n_images, float* heatmaps,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  CDR_CHECK_ARG(w && feat_rows && heatmaps && workspace && n_images > 0, "cdr_decoder_forward_rows: bad args");
+  CDR_CHECK_ARG(w->precision != CDR_PREC_FP32, "cdr_decoder_forward_rows: needs a tensor-core precision");
+  CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)feat_rows & 15) == 0,
+                "cdr_decoder_forward_rows: workspace must be 256-byte, features 16-byte aligned");
+  timing_restart();
+  return tc_decoder_forward(w->tc, feat_rows, nullptr, n_images, heatmaps, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
 }

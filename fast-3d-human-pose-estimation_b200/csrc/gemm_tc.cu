@@ -1489,12 +1489,57 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
   return CDR_OK;
 }
 
-int tc_decoder_forward(const TcWeights& w, const float* feat, int n_images, float* heatmaps,
+// scaled fp16 planes from bf16 rows (a bf16 value times a power of two is an fp16 value unless it underflows)
+__global__ void bf16_rows_to_f16p_kernel(const __nv_bfloat16* __restrict__ in, __half* __restrict__ hi,
+                                         __half* __restrict__ lo, long long n, const float* __restrict__ amax,
+                                         float* __restrict__ scale_out) {
+  const float a = __ldg(amax);
+  const float s = (a > 0.f && a < 3.0e38f) ? ldexpf(1.f, kF16TargetExp - ilogbf(a)) : 1.f;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *scale_out = s;
+  if (i >= n) return;
+  const float X = __bfloat162float(in[i]) * s;
+  const __half h = __float2half_rn(X);
+  hi[i] = h;
+  lo[i] = __float2half_rn((X - __half2float(h)) * kLoScale);
+}
+__global__ void amax_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long n, float* __restrict__ amax) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(__bfloat162float(in[i])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(m));
+}
+
+// feat_rows != NULL: latents as bf16 pixel-major rows (n_images*64, 2048) instead of NCHW fp32
+int tc_decoder_forward(const TcWeights& w, const void* feat_rows, const float* feat, int n_images, float* heatmaps,
                        void* workspace, size_t workspace_bytes, cudaStream_t st) {
   TcDecWs ws = plan_tc_dec(workspace, n_images, w.kind);
   if (ws.bytes > workspace_bytes) {
     set_error("cdr_decoder_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
     return CDR_ERR_WORKSPACE;
+  }
+  if (feat_rows) {
+    Act x1 = ws.x1;
+    const long long n = (long long)n_images * kFeatHW * kFeatC;
+    set_stage("rows_to_planes");
+    if (x1.fmt == kFmtBF16) {
+      x1.p[0] = const_cast<void*>(feat_rows);
+    } else if (x1.fmt == kFmtTF32P) {
+      bf16_rows_to_tf32p_kernel<<<(unsigned)ceil_div<long long>(n / 8, 256), 256, 0, st>>>(
+          (const __nv_bfloat16*)feat_rows, (float*)x1.p[0], (float*)x1.p[1], n / 8);
+      CDR_LAUNCH_OK("bf16_rows_to_tf32p_kernel");
+    } else {
+      CDR_CUDA(cudaMemsetAsync(ws.slots, 0, 2 * kNumSlots * sizeof(float), st));
+      const ScaleSlot sl = slot(ws.slots, 1);
+      amax_bf16_kernel<<<4 * num_sms(), 256, 0, st>>>((const __nv_bfloat16*)feat_rows, n, sl.amax);
+      CDR_LAUNCH_OK("amax_bf16_kernel");
+      bf16_rows_to_f16p_kernel<<<(unsigned)ceil_div<long long>(n, 256), 256, 0, st>>>(
+          (const __nv_bfloat16*)feat_rows, (__half*)x1.p[0], (__half*)x1.p[1], n, sl.amax, sl.scale);
+      CDR_LAUNCH_OK("bf16_rows_to_f16p_kernel");
+    }
+    return tc_decoder(w, x1, n_images, ws.d1, ws.d2, ws.d3, ws.slots, heatmaps, st);
   }
   if (ws.x1.fmt == kFmtF16P) CDR_CUDA(cudaMemsetAsync(ws.slots, 0, 2 * kNumSlots * sizeof(float), st));
   set_stage("nchw_to_rows");

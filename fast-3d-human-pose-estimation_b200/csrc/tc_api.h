@@ -21,7 +21,7 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
                     int batch, float scale, float* kp2d_l, float* kp2d_r, float* xyz,
                     const CdrHeadTaps* taps, void* workspace, size_t workspace_bytes,
                     cudaStream_t st);
-int tc_decoder_forward(const TcWeights& w, const float* feat, int n_images, float* heatmaps,
+int tc_decoder_forward(const TcWeights& w, const void* feat_rows, const float* feat, int n_images, float* heatmaps,
                        void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 // ResNet bottleneck encoder (bf16, tcgen05) — gemm_tc.cu

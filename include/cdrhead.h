@@ -146,6 +146,11 @@ int cdr_head_forward_rows(const CdrWeights* w, const void* feat_rows, const floa
                           int img_size, float* kp2d_l, float* kp2d_r, float* xyz, const CdrHeadTaps* taps,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* cdr_decoder_forward on bf16 pixel-major latents (n_images*64, 2048) — PoseResNet.forward with the encoder
+ * of this library (models/poseresnet.py:17-21).  Tensor-core precisions only. */
+int cdr_decoder_forward_rows(const CdrWeights* w, const void* feat_rows, int n_images, float* heatmaps,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- the ResNet bottleneck stages of the encoder (models/encoder.py:38-131,
  * layer1..layer4) on the same tcgen05 tap-GEMM kernel, bf16 activations, eval-mode BN folded.
  * The 7x7 stem + max-pool (models/encoder.py:93-97,122-125) stay with the caller (torch/cuDNN);

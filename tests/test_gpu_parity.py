@@ -696,3 +696,37 @@ def test_tc_encoder_shapes_and_errors(cuda_pkg):
         enc(torch.randn(1, 3, 256, 256))               # no CPU path
     with pytest.raises(NotImplementedError):
         TcEncoder(_seeded_resnet(18))                  # BasicBlock ResNets stay on torch
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_poseresnet_tc_encoder_baseline_path(cuda_pkg, precision):
+    """baseline.py's path (BASELINE configs[2]) on this library end to end: PoseResNet with the tcgen05
+    encoder feeding cdr_decoder_forward_rows, then get_max_preds x4 -> uint8 -> triangulation.  Heat-maps
+    stay within the stated bf16 bounds of the fp32 torch-encoder path and the arg-max pixels agree
+    wherever the top-2 logit gap exceeds the bf16 error."""
+    n, joints = 4, 19
+    torch.manual_seed(0)
+    m = cuda_pkg.PoseResNet(synth.make_cfg(50, joints), precision=precision, encoder_precision="bf16")
+    sd = synth.make_head_state_dict(seed=3, joints=joints, calibrated=True, decoder_only=True)
+    m.decoder.load_state_dict({k[len("decoder."):]: v for k, v in sd.items()})
+    m = m.cuda().eval()
+    x = torch.randn(n, 3, 256, 256, generator=torch.Generator().manual_seed(2)).cuda()
+    got = m(x)
+    with torch.no_grad():
+        ref = m.decoder(m.encoder(x))                       # torch fp32 encoder + the same decoder kernels
+    torch.cuda.synchronize()
+    rel = float((got - ref).abs().max() / ref.abs().max())
+    pts = cuda_pkg.baseline_keypoints(got)
+    pts_ref = cuda_pkg.baseline_keypoints(ref)
+    top2 = torch.topk(ref.reshape(n, joints, -1), 2, dim=-1).values
+    decisive = (top2[..., 0] - top2[..., 1]) > 4 * float((got - ref).abs().max())
+    agree = (pts == pts_ref).all(-1)
+    print(f"\nPoseResNet-50 [{precision}] tcgen05 encoder vs torch encoder: heat rel {rel:.2e}, "
+          f"arg-max agree {int(agree.sum())}/{agree.numel()} (decisive {int(decisive.sum())})")
+    assert got.shape == (n, joints, 64, 64) and rel < 6e-2
+    assert bool(agree[decisive].all())
+    P = synth.make_cameras(n // 2, seed=2)
+    P1 = np.concatenate([P["P_l"], np.tile([[[0, 0, 0, 1.0]]], (n // 2, 1, 1))], 1).astype(np.float64)
+    P2 = np.concatenate([P["P_r"], np.tile([[[0, 0, 0, 1.0]]], (n // 2, 1, 1))], 1).astype(np.float64)
+    xyz = cuda_pkg.triangulation(torch.from_numpy(P1), torch.from_numpy(P2), pts[: n // 2], pts[n // 2:])
+    assert tuple(xyz.shape) == (n // 2, joints, 3) and bool(torch.isfinite(xyz).all())
