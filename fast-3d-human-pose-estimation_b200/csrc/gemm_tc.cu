@@ -956,6 +956,8 @@ static int launch_tc(const TcLaunch& l, cudaStream_t st) {
     if (bn == 32) return launch_tc_t<32, kKindTF32X3, kFmtTF32P>(l, st);
   } else if (kind == kKindTF32X3 && ofmt == kFmtF16P) {
     if (bn == 128) return launch_tc_t<128, kKindTF32X3, kFmtF16P>(l, st);
+  } else if (kind == kKindF16X2 && ofmt == kFmtTF32P) {
+    if (bn == 128) return launch_tc_t<128, kKindF16X2, kFmtTF32P>(l, st);
   } else if (kind == kKindF16X2 && ofmt == kFmtF16P) {
     if (bn == 128) return launch_tc_t<128, kKindF16X2, kFmtF16P>(l, st);
     if (bn == 32) return launch_tc_t<32, kKindF16X2, kFmtF16P>(l, st);
@@ -1131,7 +1133,9 @@ static size_t plan_tc_weights(TcPack& pk, const TcWeights& w, void* base) {
   const int bn_f = fk == kKindBF16 ? 256 : 128, bn_d = dk == kKindBF16 ? 256 : 128;
   const bool scaled = dk == kKindF16X2;          // outputs feeding the decoder are stored in kFmtF16P
   if (w.has_fusion) {
-    plan_layer(pk.cf1, b, fk, 384, kFeatC, kFeatC, 128, 384, 384, false);
+    // conv_layer1 reads the encoder's latents (post-ReLU, bounded): in hybrid mode it runs f16x2 like the
+    // decoder (half the MMA time of 3xTF32 at K = 2048); its output feeds the FTL, so it stays tf32 planes
+    plan_layer(pk.cf1, b, pk.mode == kModeHybrid ? kKindF16X2 : fk, 384, kFeatC, kFeatC, 128, 384, 384, false);
     plan_layer(pk.cf2a, b, fk, 512, 2 * kHid2, 2 * kHid2, 128, 512, 512, false);
     plan_layer(pk.cf2b, b, fk, 512, kHid2, kHid2, 128, 512, 512, false);
     plan_layer(pk.out, b, fk, 2 * kFeatC, kHid1, kHid1Pad, bn_f, kFeatC, 2 * kFeatC, scaled);
@@ -1233,7 +1237,7 @@ void tc_weights_destroy(TcWeights& w) {
 }
 
 // ------------------------------------------------------------------------------------------
-constexpr int kNumSlots = 8;       // ScaleSlot pairs: 0 g (amax only), 1 x1, 2 d1, 3 d2, 4 d3
+constexpr int kNumSlots = 8;       // ScaleSlot pairs: 0 g (amax only), 1 x1, 2 d1, 3 d2, 4 d3, 5 x0 (hybrid mode)
 struct TcHeadWs {
   float* pinv;
   float* slots;
@@ -1261,7 +1265,7 @@ static TcHeadWs plan_tc_head(void* base, int B, int J, int mode) {
   TcHeadWs w;
   w.pinv = (float*)b.take(N * 12 * sizeof(float));
   w.slots = (float*)b.take(2 * kNumSlots * sizeof(float));
-  w.x0 = take_act(b, N * kFeatHW * kFeatC, ff);
+  w.x0 = take_act(b, N * kFeatHW * kFeatC, mode == kModeHybrid ? kFmtF16P : ff);
   w.y1 = take_act(b, N * kFeatHW * kHid1Pad, ff);
   w.z = take_act(b, (size_t)B * kFeatHW * 2 * kHid2, ff);
   w.f1 = take_act(b, (size_t)B * kFeatHW * kHid2, ff);
@@ -1310,9 +1314,10 @@ static int to_rows(const float* feat, const float* feat2, int n_img, const Act& 
     return launch_nchw_to_rows_bf16(feat, feat2, n_img, kFeatC, kFeatHW, (__nv_bfloat16*)out.p[0], kFeatC, st);
   if (out.fmt == kFmtTF32P)
     return launch_nchw_to_rows_split(feat, feat2, n_img, kFeatC, kFeatHW, (float*)out.p[0], (float*)out.p[1], kFeatC, st);
-  CDR_CHECK_ARG(!feat2, "to_rows: the fp16-plane format takes one tensor");
   if (int rc = launch_amax_f32(feat, (long long)n_img * kFeatC * kFeatHW, sl.amax, st)) return rc;
-  return launch_nchw_to_rows_f16p(feat, n_img, kFeatC, kFeatHW, out.p[0], out.p[1], kFeatC, sl.amax, sl.scale, st);
+  if (feat2)
+    if (int rc = launch_amax_f32(feat2, (long long)n_img * kFeatC * kFeatHW, sl.amax, st)) return rc;
+  return launch_nchw_to_rows_f16p(feat, feat2, n_img, kFeatC, kFeatHW, out.p[0], out.p[1], kFeatC, sl.amax, sl.scale, st);
 }
 // FTL of both views in one launch
 static int ftl_act2(const Act& in0, const Act& in1, int in_pitch, const float* const mats[2], int rows, int cols, int n,
@@ -1371,6 +1376,29 @@ static int tap_to_f32(float* dst, const Act& src, const float* scale, long long 
   return CDR_OK;
 }
 
+// scaled fp16 planes from bf16 rows (a bf16 value times a power of two is an fp16 value unless it underflows)
+__global__ void bf16_rows_to_f16p_kernel(const __nv_bfloat16* __restrict__ in, __half* __restrict__ hi,
+                                         __half* __restrict__ lo, long long n, const float* __restrict__ amax,
+                                         float* __restrict__ scale_out) {
+  const float a = __ldg(amax);
+  const float s = (a > 0.f && a < 3.0e38f) ? ldexpf(1.f, kF16TargetExp - ilogbf(a)) : 1.f;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *scale_out = s;
+  if (i >= n) return;
+  const float X = __bfloat162float(in[i]) * s;
+  const __half h = __float2half_rn(X);
+  hi[i] = h;
+  lo[i] = __float2half_rn((X - __half2float(h)) * kLoScale);
+}
+__global__ void amax_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long n, float* __restrict__ amax) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(__bfloat162float(in[i])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(m));
+}
+
 // encoder output (bf16 rows) -> the fusion block's fp32 hi/lo planes: a bf16 value is a tf32 value, lo = 0
 __global__ void bf16_rows_to_tf32p_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ hi,
                                           float* __restrict__ lo, long long n8) {
@@ -1417,16 +1445,25 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
     // latents already pixel-major bf16 rows, views stacked (the tcgen05 encoder's output layout)
     if (x0.fmt == kFmtBF16) {
       x0.p[0] = const_cast<void*>(feat_rows);
-    } else {
+    } else if (x0.fmt == kFmtTF32P) {
       set_stage("rows_to_planes");
       const long long n8 = (long long)N * kFeatHW * kFeatC / 8;
       bf16_rows_to_tf32p_kernel<<<(unsigned)ceil_div<long long>(n8, 256), 256, 0, st>>>(
           (const __nv_bfloat16*)feat_rows, (float*)x0.p[0], (float*)x0.p[1], n8);
       CDR_LAUNCH_OK("bf16_rows_to_tf32p_kernel");
+    } else {
+      set_stage("rows_to_planes");
+      const long long n = (long long)N * kFeatHW * kFeatC;
+      const ScaleSlot sl = slot(ws.slots, 5);
+      amax_bf16_kernel<<<4 * num_sms(), 256, 0, st>>>((const __nv_bfloat16*)feat_rows, n, sl.amax);
+      CDR_LAUNCH_OK("amax_bf16_kernel");
+      bf16_rows_to_f16p_kernel<<<(unsigned)ceil_div<long long>(n, 256), 256, 0, st>>>(
+          (const __nv_bfloat16*)feat_rows, (__half*)x0.p[0], (__half*)x0.p[1], n, sl.amax, sl.scale);
+      CDR_LAUNCH_OK("bf16_rows_to_f16p_kernel");
     }
   } else {
     set_stage("nchw_to_rows");
-    if ((rc = to_rows(feat_l, feat_r, B, ws.x0, ScaleSlot(), st))) return rc;
+    if ((rc = to_rows(feat_l, feat_r, B, ws.x0, slot(ws.slots, 5), st))) return rc;
   }
   set_stage("cf_conv1");
   {
@@ -1435,6 +1472,7 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
     l.a_rows_total = (long long)N * kFeatHW;
     l.layer = &pk->cf1; l.n = kHid1;
     l.C = ws.y1; l.c_pitch = kHid1Pad; l.c_fill = kHid1Pad; l.relu = 1; l.out_mode = kOutRows;
+    l.in_slot = slot(ws.slots, 5);
     if ((rc = launch_tc(l, st))) return rc;
   }
   set_stage("ftl_inv");
@@ -1487,29 +1525,6 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
       CDR_CUDA(cudaMemcpyAsync(taps->heatmaps, ws.hm, (size_t)N * J * 4096 * 4, cudaMemcpyDeviceToDevice, st));
   }
   return CDR_OK;
-}
-
-// scaled fp16 planes from bf16 rows (a bf16 value times a power of two is an fp16 value unless it underflows)
-__global__ void bf16_rows_to_f16p_kernel(const __nv_bfloat16* __restrict__ in, __half* __restrict__ hi,
-                                         __half* __restrict__ lo, long long n, const float* __restrict__ amax,
-                                         float* __restrict__ scale_out) {
-  const float a = __ldg(amax);
-  const float s = (a > 0.f && a < 3.0e38f) ? ldexpf(1.f, kF16TargetExp - ilogbf(a)) : 1.f;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) *scale_out = s;
-  if (i >= n) return;
-  const float X = __bfloat162float(in[i]) * s;
-  const __half h = __float2half_rn(X);
-  hi[i] = h;
-  lo[i] = __float2half_rn((X - __half2float(h)) * kLoScale);
-}
-__global__ void amax_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long n, float* __restrict__ amax) {
-  float m = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(__bfloat162float(in[i])));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(m));
 }
 
 // feat_rows != NULL: latents as bf16 pixel-major rows (n_images*64, 2048) instead of NCHW fp32

@@ -50,8 +50,8 @@ int launch_ftl2(const T* const in[2], int in_pitch, const float* const mats[2], 
 int launch_pinv2(const float* P_a, const float* P_b, int n, double rtol, float* out, cudaStream_t st);
 // scaled fp16 hi/lo planes for the f16x2 tensor-core path (gemm_tc.cu: kFmtF16P)
 int launch_amax_f32(const float* in, long long n, float* amax, cudaStream_t st);
-int launch_nchw_to_rows_f16p(const float* in, int n_img, int C, int HW, void* out_hi, void* out_lo, int out_pitch,
-                             const float* amax, float* scale_out, cudaStream_t st);
+int launch_nchw_to_rows_f16p(const float* in, const float* in2, int n_img, int C, int HW, void* out_hi, void* out_lo,
+                             int out_pitch, const float* amax, float* scale_out, cudaStream_t st);
 template <typename T>
 int launch_ftl(const T* in, int in_pitch, const float* mats, int rows, int cols, int blk, int n,
                int hw, T* out, int out_pitch, int out_fill, cudaStream_t st);

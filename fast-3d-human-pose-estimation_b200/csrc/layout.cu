@@ -119,17 +119,18 @@ int launch_amax_f32(const float* in, long long n, float* amax, cudaStream_t st) 
 // scaled fp16 hi/lo planes (gemm_tc.cu: kFmtF16P): X = x * s with s = 2^(13 - ilogb(amax)),
 // hi = rn_f16(X), lo = rn_f16((X - hi) * 2^11); block (0,0,0) publishes s.
 __global__ void __launch_bounds__(256)
-nchw_to_rows_f16p_kernel(const float* __restrict__ in, int C, int HW, __half* __restrict__ out_hi,
-                         __half* __restrict__ out_lo, int out_pitch, const float* __restrict__ amax,
-                         float* __restrict__ scale_out) {
+nchw_to_rows_f16p_kernel(const float* __restrict__ in, const float* __restrict__ in2, int n_first, int C, int HW,
+                         __half* __restrict__ out_hi, __half* __restrict__ out_lo, int out_pitch,
+                         const float* __restrict__ amax, float* __restrict__ scale_out) {
   __shared__ float tile[32][65];
   const float a = __ldg(amax);
   const float s = (a > 0.f && a < 3.0e38f) ? ldexpf(1.f, 13 - ilogbf(a)) : 1.f;
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *scale_out = s;
   const int c0 = blockIdx.x * 32, p0 = blockIdx.y * 64, img = blockIdx.z;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* base = img < n_first ? in + (size_t)img * C * HW : in2 + (size_t)(img - n_first) * C * HW;
   for (int c = ty; c < 32; c += 8) {
-    const float* src = in + ((size_t)img * C + c0 + c) * HW + p0;
+    const float* src = base + (size_t)(c0 + c) * HW + p0;
     if (c0 + c < C) {
       if (p0 + tx < HW) tile[c][tx] = src[tx];
       if (p0 + tx + 32 < HW) tile[c][tx + 32] = src[tx + 32];
@@ -148,12 +149,13 @@ nchw_to_rows_f16p_kernel(const float* __restrict__ in, int C, int HW, __half* __
     }
   }
 }
-int launch_nchw_to_rows_f16p(const float* in, int n_img, int C, int HW, void* out_hi, void* out_lo, int out_pitch,
-                             const float* amax, float* scale_out, cudaStream_t st) {
+int launch_nchw_to_rows_f16p(const float* in, const float* in2, int n_img, int C, int HW, void* out_hi, void* out_lo,
+                             int out_pitch, const float* amax, float* scale_out, cudaStream_t st) {
   CDR_CHECK_ARG(in && out_hi && out_lo && amax && scale_out && n_img > 0 && C > 0 && HW > 0 && out_pitch >= C,
                 "nchw_to_rows_f16p: bad args");
-  dim3 grid(ceil_div(C, 32), ceil_div(HW, 64), n_img);
-  nchw_to_rows_f16p_kernel<<<grid, 256, 0, st>>>(in, C, HW, (__half*)out_hi, (__half*)out_lo, out_pitch, amax, scale_out);
+  dim3 grid(ceil_div(C, 32), ceil_div(HW, 64), in2 ? 2 * n_img : n_img);
+  nchw_to_rows_f16p_kernel<<<grid, 256, 0, st>>>(in, in2, n_img, C, HW, (__half*)out_hi, (__half*)out_lo, out_pitch, amax,
+                                                 scale_out);
   CDR_LAUNCH_OK("nchw_to_rows_f16p_kernel");
   return CDR_OK;
 }
