@@ -1314,9 +1314,7 @@ static int to_rows(const float* feat, const float* feat2, int n_img, const Act& 
     return launch_nchw_to_rows_bf16(feat, feat2, n_img, kFeatC, kFeatHW, (__nv_bfloat16*)out.p[0], kFeatC, st);
   if (out.fmt == kFmtTF32P)
     return launch_nchw_to_rows_split(feat, feat2, n_img, kFeatC, kFeatHW, (float*)out.p[0], (float*)out.p[1], kFeatC, st);
-  if (int rc = launch_amax_f32(feat, (long long)n_img * kFeatC * kFeatHW, sl.amax, st)) return rc;
-  if (feat2)
-    if (int rc = launch_amax_f32(feat2, (long long)n_img * kFeatC * kFeatHW, sl.amax, st)) return rc;
+  if (int rc = launch_amax_f32(feat, feat2, (long long)n_img * kFeatC * kFeatHW, sl.amax, st)) return rc;
   return launch_nchw_to_rows_f16p(feat, feat2, n_img, kFeatC, kFeatHW, out.p[0], out.p[1], kFeatC, sl.amax, sl.scale, st);
 }
 // FTL of both views in one launch

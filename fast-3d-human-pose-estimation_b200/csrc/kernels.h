@@ -49,7 +49,7 @@ int launch_ftl2(const T* const in[2], int in_pitch, const float* const mats[2], 
 // pinv of two (n,3,4) stacks in one launch: out[0..n) from P_a, out[n..2n) from P_b
 int launch_pinv2(const float* P_a, const float* P_b, int n, double rtol, float* out, cudaStream_t st);
 // scaled fp16 hi/lo planes for the f16x2 tensor-core path (gemm_tc.cu: kFmtF16P)
-int launch_amax_f32(const float* in, long long n, float* amax, cudaStream_t st);
+int launch_amax_f32(const float* in, const float* in2, long long n, float* amax, cudaStream_t st);   // in2 may be NULL
 int launch_nchw_to_rows_f16p(const float* in, const float* in2, int n_img, int C, int HW, void* out_hi, void* out_lo,
                              int out_pitch, const float* amax, float* scale_out, cudaStream_t st);
 template <typename T>

@@ -33,6 +33,45 @@ nchw_to_rows_kernel(const float* __restrict__ in, const float* __restrict__ in2,
   }
 }
 
+// 16-bit outputs, fast path (C % 64 == 0, HW % 64 == 0): 64-channel x 64-pixel tiles, float2 loads along
+// pixels, one packed pair of channels (4 bytes) per lane on the way out, so a warp writes a full 128-byte
+// line per instruction.  kF16P: scaled fp16 hi/lo planes (scale from *amax, gemm_tc.cu: kFmtF16P).
+template <bool kF16P>
+__global__ void __launch_bounds__(256)
+nchw_to_rows16_kernel(const float* __restrict__ in, const float* __restrict__ in2, int n_first, int C, int HW,
+                      void* __restrict__ out_hi, void* __restrict__ out_lo, int out_pitch,
+                      const float* __restrict__ amax, float* __restrict__ scale_out) {
+  __shared__ float tile[64][65];
+  float s = 1.f;
+  if constexpr (kF16P) {
+    const float a = __ldg(amax);
+    if (a > 0.f && a < 3.0e38f) s = ldexpf(1.f, 13 - ilogbf(a));
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *scale_out = s;
+  }
+  const int c0 = blockIdx.x * 64, p0 = blockIdx.y * 64, img = blockIdx.z;
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* base = img < n_first ? in + (size_t)img * C * HW : in2 + (size_t)(img - n_first) * C * HW;
+  for (int c = ty; c < 64; c += 8) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(base + (size_t)(c0 + c) * HW + p0) + lane);
+    tile[c][2 * lane] = v.x;
+    tile[c][2 * lane + 1] = v.y;
+  }
+  __syncthreads();
+  for (int pp = ty; pp < 64; pp += 8) {
+    const float x0 = tile[2 * lane][pp] * s, x1 = tile[2 * lane + 1][pp] * s;
+    const size_t o = ((size_t)img * HW + p0 + pp) * out_pitch + c0 + 2 * lane;
+    if constexpr (kF16P) {
+      const __half2 h = __floats2half2_rn(x0, x1);
+      const float2 hf = __half22float2(h);
+      *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(out_hi) + o) = h;
+      *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(out_lo) + o) =
+          __floats2half2_rn((x0 - hf.x) * 2048.f, (x1 - hf.y) * 2048.f);
+    } else {
+      *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(out_hi) + o) = __floats2bfloat162_rn(x0, x1);
+    }
+  }
+}
+
 // in2 (optional): a second (n_img, C, HW) tensor whose rows follow the first one's in `out`
 template <typename TOut>
 static int launch_nchw_to_rows(const float* in, const float* in2, int n_img, int C, int HW, TOut* out, int out_pitch,
@@ -49,6 +88,13 @@ int launch_nchw_to_rows_f32(const float* in, const float* in2, int n_img, int C,
 }
 int launch_nchw_to_rows_bf16(const float* in, const float* in2, int n_img, int C, int HW, __nv_bfloat16* out,
                              int out_pitch, cudaStream_t st) {
+  if (C % 64 == 0 && HW % 64 == 0 && out_pitch % 2 == 0 && ((uintptr_t)in & 7) == 0 && (!in2 || ((uintptr_t)in2 & 7) == 0)) {
+    CDR_CHECK_ARG(in && out && n_img > 0 && out_pitch >= C, "nchw_to_rows: bad args");
+    dim3 grid(C / 64, HW / 64, in2 ? 2 * n_img : n_img);
+    nchw_to_rows16_kernel<false><<<grid, 256, 0, st>>>(in, in2, n_img, C, HW, out, nullptr, out_pitch, nullptr, nullptr);
+    CDR_LAUNCH_OK("nchw_to_rows16_kernel");
+    return CDR_OK;
+  }
   return launch_nchw_to_rows<__nv_bfloat16>(in, in2, n_img, C, HW, out, out_pitch, st);
 }
 
@@ -93,7 +139,8 @@ int launch_nchw_to_rows_split(const float* in, const float* in2, int n_img, int 
 // max |x| over a flat fp32 array -> atomicMax into *amax (pre-zeroed; non-negative floats order
 // like their bit patterns)
 __global__ void __launch_bounds__(256)
-amax_f32_kernel(const float* __restrict__ in, long long n, float* __restrict__ amax) {
+amax_f32_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, long long n, float* __restrict__ amax) {
+  const float* __restrict__ in = blockIdx.y == 0 ? in_a : in_b;     // grid.y = number of tensors (1 or 2)
   float m = 0.f;
   const long long n4 = n >> 2;
   const float4* in4 = reinterpret_cast<const float4*>(in);
@@ -107,11 +154,11 @@ amax_f32_kernel(const float* __restrict__ in, long long n, float* __restrict__ a
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(m));
 }
-int launch_amax_f32(const float* in, long long n, float* amax, cudaStream_t st) {
-  CDR_CHECK_ARG(in && amax && n > 0 && ((uintptr_t)in & 15) == 0, "amax_f32: bad args");
+int launch_amax_f32(const float* in, const float* in2, long long n, float* amax, cudaStream_t st) {
+  CDR_CHECK_ARG(in && amax && n > 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)in2 & 15) == 0, "amax_f32: bad args");
   const long long want = ceil_div<long long>(n >> 2, 256 * 4);
-  const unsigned grid = (unsigned)(want < 1 ? 1 : want > 8 * num_sms() ? 8 * num_sms() : want);
-  amax_f32_kernel<<<grid, 256, 0, st>>>(in, n, amax);
+  const unsigned gx = (unsigned)(want < 1 ? 1 : want > 4 * num_sms() ? 4 * num_sms() : want);
+  amax_f32_kernel<<<dim3(gx, in2 ? 2 : 1), 256, 0, st>>>(in, in2, n, amax);
   CDR_LAUNCH_OK("amax_f32_kernel");
   return CDR_OK;
 }
@@ -153,6 +200,12 @@ int launch_nchw_to_rows_f16p(const float* in, const float* in2, int n_img, int C
                              int out_pitch, const float* amax, float* scale_out, cudaStream_t st) {
   CDR_CHECK_ARG(in && out_hi && out_lo && amax && scale_out && n_img > 0 && C > 0 && HW > 0 && out_pitch >= C,
                 "nchw_to_rows_f16p: bad args");
+  if (C % 64 == 0 && HW % 64 == 0 && out_pitch % 2 == 0 && ((uintptr_t)in & 7) == 0 && (!in2 || ((uintptr_t)in2 & 7) == 0)) {
+    dim3 grid16(C / 64, HW / 64, in2 ? 2 * n_img : n_img);
+    nchw_to_rows16_kernel<true><<<grid16, 256, 0, st>>>(in, in2, n_img, C, HW, out_hi, out_lo, out_pitch, amax, scale_out);
+    CDR_LAUNCH_OK("nchw_to_rows16_kernel");
+    return CDR_OK;
+  }
   dim3 grid(ceil_div(C, 32), ceil_div(HW, 64), in2 ? 2 * n_img : n_img);
   nchw_to_rows_f16p_kernel<<<grid, 256, 0, st>>>(in, in2, n_img, C, HW, (__half*)out_hi, (__half*)out_lo, out_pitch, amax,
                                                  scale_out);
