@@ -369,6 +369,185 @@ def stream_microbench(dev, poses=8192, reps=5):
             "traffic": ncu_traffic().get("softargmax_dlt_stream") if poses == 8192 else None}
 
 
+def config4_1m_poses(dev, chunk=8192, total=1 << 20):
+    """BASELINE configs[3]: soft-argmax + DLT over 2^20 stereo poses x 19 joints x 2 views x 64x64 fp32 logits
+    (653 GB of heat-maps: does not fit HBM).  SURVEY §8d recipe: `total/chunk` launches of `chunk` poses each
+    over two alternating device buffers (2 x 5.1 GB, each >> L2), kernels only, one CUDA-event pair around
+    all of them.  Heat-maps = Gaussian blobs (sigma 3 px, amplitude 10) on the projections of a synthetic
+    3D ground truth + N(0,0.1) noise, so the triangulation has a truth to land on (reported, not gated)."""
+    from fast_3d_human_pose_estimation_b200 import synth, _lib
+    L = _lib.lib()
+    cams = synth.make_cameras(chunk, seed=4)
+    gt = synth.make_gt(cams, seed=5)
+    P_l = torch.from_numpy(cams["P_l"]).to(dev)
+    P_r = torch.from_numpy(cams["P_r"]).to(dev)
+    bufs = []
+    for b in range(2):
+        heat = torch.empty((2, chunk, JOINTS, 64, 64), dtype=torch.float32, device=dev)
+        for v, key in enumerate(("gt2d_l", "gt2d_r")):
+            c = torch.from_numpy(gt[key] / 4.0).float().to(dev)
+            for lo in range(0, chunk, 512):
+                heat[v, lo:lo + 512] = synth.blob_heatmaps(c[lo:lo + 512], seed=100 * b + 10 * v + lo)
+        bufs.append(heat)
+    kl = torch.empty((chunk, JOINTS, 2), device=dev)
+    kr = torch.empty_like(kl)
+    xyz = torch.empty((chunk, JOINTS, 3), device=dev)
+    st = _lib.current_stream_ptr(dev)
+    n_launch = total // chunk
+
+    def run(k):
+        for i in range(k):
+            h = bufs[i & 1]
+            _lib.check(L.cdr_softargmax_dlt(_lib.ptr(h[0]), _lib.ptr(h[1]), 0, _lib.ptr(P_l), _lib.ptr(P_r), chunk,
+                                            JOINTS, 64, 64, 4.0, _lib.ptr(kl), _lib.ptr(kr), _lib.ptr(xyz), None, None,
+                                            None, None, None, st))
+    run(4)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); run(n_launch); b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    err = (xyz.double().cpu().numpy() - gt["gt3d"])
+    err3 = float(np.sqrt((err ** 2).sum(-1)).mean())
+    err2 = float(np.abs(kl.double().cpu().numpy() - gt["gt2d_l"]).mean())
+    pk = peaks()
+    gbs = SOFTARGMAX_DLT_BYTES_PER_POSE * total / (ms / 1e3) / 1e9
+    del bufs
+    torch.cuda.empty_cache()
+    return {"workload": "BASELINE configs[3]: soft-argmax + DLT, 2^20 poses x 19 joints x 2 views x 64x64 fp32",
+            "poses": total, "launches": n_launch, "poses_per_launch": chunk, "ms_total": ms,
+            "poses_per_s": total / (ms / 1e3), "bytes_per_pose": SOFTARGMAX_DLT_BYTES_PER_POSE,
+            "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "bound": "hbm",
+            "input": "two alternating 5.1 GB device buffers of Gaussian-blob logits (each >> 126 MB L2)",
+            "mean_3d_err_vs_truth_mm": err3, "mean_2d_err_vs_truth_px": err2}
+
+
+def ftl_stream(dev, n=4096, reps=5):
+    """CanonicalFusion.ftl (models/cdrnet.py:45-56) at a size that leaves L2: n samples x 64 pixels, fp32
+    rows, through the C ABI `cdr_ftl`.  Algorithmic bytes per sample and direction = (300 + 400) channels x
+    64 pixels x 4 B = 179 200 (76 800 + 102 400).  The B=64 head launches are latency-bound."""
+    from fast_3d_human_pose_estimation_b200 import _lib
+    L = _lib.lib()
+    st = _lib.current_stream_ptr(dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    x3 = torch.zeros((n * 64, 304), device=dev)
+    x3[:, :300].normal_(generator=g)
+    x4 = torch.empty((n * 64, 400), device=dev)
+    m43 = torch.randn((n, 4, 3), device=dev, generator=g)
+    m34 = torch.randn((n, 3, 4), device=dev, generator=g)
+    out = {}
+    pk = peaks()
+    for name, (src, sp, mats, r, c, dst, dp, fill) in {"inverse_4x3": (x3, 304, m43, 4, 3, x4, 400, 400),
+                                                       "forward_3x4": (x4, 400, m34, 3, 4, x3, 304, 304)}.items():
+        def run():
+            _lib.check(L.cdr_ftl(_lib.ptr(src), sp, _lib.ptr(mats), r, c, 100, n, 64, _lib.ptr(dst), dp, fill, st))
+        run(); run()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); run(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = float(np.median(ts))
+        gbs = 179200.0 * n / (ms / 1e3) / 1e9
+        out[name] = {"launch_ms": ms, "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]}
+    # spot check against the definition: out[row, r*100+c] = sum_k m[r,k] * in[row, k*100+c]   (last launch: forward)
+    rows = torch.arange(0, n * 64, max(1, n * 64 // 257), device=dev)
+    want = torch.einsum("nrk,nkc->nrc", m34[rows // 64].double(), x4[rows].double().reshape(-1, 4, 100)).reshape(-1, 300)
+    out["max_abs_err_vs_fp64"] = float((x3[rows, :300].double() - want).abs().max())
+    out.update({"kernel": "ftl_vec_kernel<float> via cdr_ftl", "bound": "hbm", "samples": n, "bytes_per_sample": 179200,
+                "input": f"{n} samples x 64 px fp32 rows ({x3.numel() * 4 / 1e6:.0f} + {x4.numel() * 4 / 1e6:.0f} MB, >> L2)"})
+    return out
+
+
+def config5(args, ctx, precision, total=1024):
+    """BASELINE configs[4]: the full pipeline (uint8 stereo frames in pinned HOST memory -> ResNet-101 encoder
+    + head on this repo's kernels -> 3D joints + MPJPE sums on the host) over a batch of `total` stereo pairs
+    sharded across the ranks (strong scaling: total/N pairs per GPU), processed in chunks of --batch pairs
+    through FramePipeline, ONE final all-gather of every rank's (total/N,19,3) joints + MPJPE sums."""
+    import torch.distributed as dist
+    import fast_3d_human_pose_estimation_b200 as pkg
+    from fast_3d_human_pose_estimation_b200 import synth, dist as cdist
+    dev, B, world, rank = ctx["dev"], args.batch, ctx["world"], ctx["rank"]
+    per = total // world
+    n_chunks = max(1, per // B)
+    per = n_chunks * B
+    pipe, err = None, None
+    try:
+        torch.manual_seed(0)
+        m = pkg.CDRNet(synth.make_cfg(101, JOINTS), precision=precision, encoder_precision="bf16")
+        m.load_state_dict(ctx["sd"], strict=False)
+        m = m.to(dev).eval()
+        gen = torch.Generator().manual_seed(7 + rank)
+        frames_h = [torch.randint(0, 256, (2, B, 256, 256, 3), dtype=torch.uint8, generator=gen).pin_memory()
+                    for _ in range(n_chunks)]
+        pipe = pkg.FramePipeline(m, B, gt={"gt3d": ctx["g3"], "gt2d_l": ctx["g2l"], "gt2d_r": ctx["g2r"], "vis": ctx["vis"]})
+    except Exception as e:
+        err = repr(e)[:200]
+    if world > 1:
+        ok = torch.tensor([0.0 if pipe is None else 1.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)        # enter the collective section only if every rank is ready
+        if float(ok[0]) < 1.0:
+            return {"error": err or "another rank failed to build the pipeline"}
+    elif pipe is None:
+        return {"error": err}
+    xyz_all = torch.zeros((per, JOINTS, 3), dtype=torch.float32, device=dev)
+    sums_all = torch.zeros(4, dtype=torch.float64, device=dev)
+    xyz_h = torch.empty((per * world, JOINTS, 3), dtype=torch.float32).pin_memory()
+    sums_h = torch.empty(4, dtype=torch.float64).pin_memory()
+    state = {"i": 0}
+
+    def post(slot):                       # on the compute stream, after the chunk's graph
+        i = state["i"]
+        xyz_all[i * B:(i + 1) * B].copy_(pipe.xyz_dev[slot])
+        sums_all.add_(pipe.sums_dev[slot])
+        state["i"] = i + 1
+
+    def run():
+        state["i"] = 0
+        sums_all.zero_()
+        pipe.submit(frames_h[0], ctx["P_h"], post)
+        for c in range(1, n_chunks):
+            pipe.submit(frames_h[c], ctx["P_h"], post)
+            pipe.collect()
+        pipe.collect()
+        with torch.cuda.stream(pipe.compute_stream):
+            x, s = cdist.gather_results(xyz_all, sums_all, per * world)
+            xyz_h.copy_(x, non_blocking=True)
+            sums_h.copy_(s, non_blocking=True)
+        pipe.compute_stream.synchronize()
+        return float(sums_h[3])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    run()
+    barrier()
+    reps, ms = 3, []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(pipe.compute_stream):
+            a.record()
+        count = run()
+        with torch.cuda.stream(pipe.compute_stream):
+            b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms.append(float(t[0]))
+    best = float(np.median(ms))
+    return {"workload": "BASELINE configs[4]: full pipeline, %d stereo pairs sharded over %d GPU(s)" % (per * world, world),
+            "pairs_per_s": per * world / (best / 1e3), "ms_total": best, "n_gpus": world, "pairs_per_gpu": per,
+            "chunk_pairs": B, "chunks_per_gpu": n_chunks, "scaling": "strong", "head_precision": precision,
+            "mpjpe_count": count, "h2d_bytes_per_gpu": n_chunks * (frames_h[0].numel() + 2 * B * 48),
+            "collective": "1 all-gather of (%d,19,3) fp32 + 32 B per rank at the end" % per,
+            "api": "FramePipeline per rank (uint8 frames in pinned host memory; ResNet-101 encoder + head on this repo's kernels)"}
+
+
 def full_pipeline(args, ctx, precision):
     """pairs/s of the whole CDRNet.forward — ResNet-101 encoder on torch/cuDNN (not
     ours, by decree) + our head — on device-resident (B,3,256,256) image pairs.  Two encoder
@@ -594,6 +773,14 @@ def run_ours(args):
     fp_multi = None
     if world > 1 and not args.no_full_pipeline:
         fp_multi = full_pipeline_sharded(args, ctx, args.precision)      # every rank takes part (collectives)
+    c5 = None
+    if not args.no_full_pipeline and not args.no_config5:
+        try:
+            c5 = config5(args, ctx, args.precision)                      # every rank takes part (collectives)
+        except Exception as e:
+            if world > 1:
+                raise
+            c5 = {"error": repr(e)[:200]}
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -627,6 +814,11 @@ def run_ours(args):
         line["cpu_baseline"] = cpu
         if world == 1 and not args.no_stream_microbench:
             line["roofline_hbm_stream"] = stream_microbench(dev)
+            for key, fn in (("config4_softargmax_dlt_1m_poses", config4_1m_poses), ("roofline_hbm_ftl", ftl_stream)):
+                try:
+                    line[key] = fn(dev)
+                except Exception as e:                  # secondary numbers: never lose the main line
+                    line[key] = {"error": repr(e)[:200]}
         if other is not None:
             line["bf16"] = other
         if world == 1 and not args.no_full_pipeline:
@@ -636,6 +828,8 @@ def run_ours(args):
                 line["full_pipeline"] = {"error": repr(e)[:200]}
         if fp_multi is not None:
             line["full_pipeline"] = fp_multi
+        if c5 is not None:
+            line["config5_full_pipeline_1024_pairs"] = c5
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -659,6 +853,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stream-microbench", action="store_true")
     ap.add_argument("--no-full-pipeline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the 1024-pair sharded full-pipeline run")
     ap.add_argument("--single-precision", action="store_true",
                     help="fp32 run only: skip the bf16 tensor-core measurement reported alongside")
     args = ap.parse_args()

@@ -1,36 +1,40 @@
 // Streaming heat-map kernels: soft-argmax (+ fused DLT + MPJPE partial sums) and the
 // baseline's hard arg-max.  HBM-bound: 16 KB of logits in, 8 bytes out per heat-map.
 //
-// Structure (one persistent CTA per SM, 320 threads):
+// Structure (one persistent CTA per SM, 32 * (NW + 2) threads, NW = 10 by default):
 //   warp 0      producer: one elected lane streams whole heat-maps (one 16 KB tile each) into a
-//               8-deep shared-memory ring with 1-D TMA bulk copies (cp.async.bulk) that
-//               complete on per-stage mbarriers -> 128 KB in flight per SM with one thread.
-//   warps 1..8  consumers: one warp per tile, two passes over the tile in shared memory
+//               NW-deep shared-memory ring with 1-D TMA bulk copies (cp.async.bulk) that
+//               complete on per-stage mbarriers -> 160 KB in flight per SM with one thread.
+//   warps 1..NW consumers: one warp per tile, two passes over the tile in shared memory
 //               (max, then exp/sum/centre of mass) with warp-shuffle reductions; exact
 //               "global max first" softmax like ATen, sums carried in fp64.
-//   warp 9      DLT: when all 2J tiles of a pose have landed their 2D joints in shared
+//   warp NW+1   DLT: when all 2J tiles of a pose have landed their 2D joints in shared
 //               memory, lanes 0..J-1 each solve one joint's 4x4 system in fp64 registers
 //               (one-sided Jacobi, jacobi.cuh) and optionally accumulate the MPJPE terms.
 // Reference: models/cdrnet.py:120-149 (process_heatmap), :250 (scale), :151-179,262-266
 // (dlt per joint), models/metrics.py:82-95 (MPJPE terms), tools/utils.py:30-58 (arg-max).
 #include "common.cuh"
 #include "jacobi.cuh"
+#include <stdlib.h>
+
 #include "ptx.cuh"
 
 namespace cdr {
 
 constexpr int kTileBytes = 16384;  // one 64x64 fp32 heat-map
-constexpr int kConsumerWarps = 8;
-// The ring depth must be a multiple of the consumer-warp count: tiles q and q+kStages share a
-// stage and its mbarrier, and only if the SAME warp consumes both (q % warps) is its wait for
-// phase(q+kStages) ordered after phase(q).  With 12 stages and 8 warps a starved warp could reach
-// the barrier while it was still in the older, incomplete phase, whose parity test reads as
-// "complete" — stale data, then a protocol deadlock (seen in the arg-max stress at 20 000 maps).
-constexpr int kStages = 8;
-static_assert(kStages % kConsumerWarps == 0, "see above");
+// Consumer warps = ring stages = NW (template parameter of the kernel).  The ring depth must be a
+// multiple of the consumer-warp count: tiles q and q+stages share a stage and its mbarrier, and only if
+// the SAME warp consumes both (q % warps) is its wait for phase(q+stages) ordered after phase(q).  With
+// 12 stages and 8 warps a starved warp could reach the barrier while it was still in the older,
+// incomplete phase, whose parity test reads as "complete" — stale data, then a protocol deadlock (seen in
+// the arg-max stress at 20 000 maps).  With stages == warps every warp owns one stage.
+// A stage is busy for (HBM latency + one warp's two passes over the tile), so bytes in flight per SM and
+// consumer parallelism both bound the stream: 8 x 16 KB reached 5.1 TB/s (78 % of the measured HBM peak)
+// with the XU pipe (EX2 + fp64 conversions) at 46 %.  CDR_HEAT_WARPS=8|10|12 overrides the default.
+constexpr int kHeatWarpsDefault = 10;   // B200, 8192-pose stream: 8 -> 5.40, 10 -> 5.91, 12 -> 5.33 TB/s (12: 14 warps cap ptxas at 128 registers, the DLT warp spills)
+constexpr int kHeatWarpsMin = 8;   // smallest instantiation: the fused pose hand-off needs 2J >= warps
 constexpr int kPoseBufs = 4;
 constexpr int kMaxTilesPerPose = 2 * kMaxJoints;
-constexpr int kHeatThreads = 32 * (kConsumerWarps + 2);
 
 struct HeatParams {
   const void* heat[2];   // per view: (B, J, H*W)
@@ -48,11 +52,12 @@ struct HeatParams {
   float scale;
 };
 
+template <int NW>
 struct __align__(128) HeatSmem {
-  uint8_t tiles[kStages][kTileBytes];
+  uint8_t tiles[NW][kTileBytes];
   double kps[kPoseBufs][kMaxTilesPerPose][2];
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[NW];
+  uint64_t empty[NW];
   uint64_t pose_full[kPoseBufs];
   uint64_t pose_empty[kPoseBufs];
 };
@@ -141,11 +146,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Exact fp32 -> fp64 widening of a NON-NEGATIVE float on the integer pipe (F2F.F64.F32 issues on the XU
+// pipe, 4 lanes/clk/SMSP, which it would share with the EX2s: ncu had XU at 46 % with two conversions per
+// step).  exponent + 896, mantissa << 29; +0 maps to 2^-127 (harmless in sums that contain e(max) = 1),
+// Inf/NaN do NOT survive — the caller keeps an fp32 check sum for them.
+__device__ __forceinline__ double widen_nonneg(float x) {
+  const uint32_t b = __float_as_uint(x);
+  return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+}
+
 // Fast path for the decoder's 64x64 maps.  With 32 lanes x 16 bytes per step a lane always sits in
 // the same columns (col0..col0+E-1) and walks R = 32*E/64 rows per step, so the centre of mass is
 //   sum_x = col0 * S + sum(k * e),   sum_y = row0 * S + R * sum(step * S_step)
 // and the inner loop carries no index arithmetic: 1 LDS.128 + E x (FFMA, EX2, FADD, FFMA) + two
-// fp32->fp64 conversions and four fp64 adds/FMAs per step.
+// integer-pipe fp32->fp64 widenings and four fp64 adds/FMAs per step.
 template <typename T>
 __device__ __forceinline__ void tile_softargmax_64(const uint8_t* tile, int lane, double& cx, double& cy) {
   constexpr int E = Vec16<T>::kElems;        // 4 (fp32) / 8 (bf16)
@@ -164,6 +178,7 @@ __device__ __forceinline__ void tile_softargmax_64(const uint8_t* tile, int lane
   const float kLog2e = 1.4426950408889634f;
   const float ml2 = m * kLog2e;
   double S = 0.0, SXL = 0.0, TY = 0.0, itd = 0.0;
+  float chk = 0.f;                           // fp32 shadow of S: carries Inf/NaN (see widen_nonneg)
 #pragma unroll 4
   for (int it = 0; it < IT; ++it) {
     float v[E];
@@ -175,12 +190,14 @@ __device__ __forceinline__ void tile_softargmax_64(const uint8_t* tile, int lane
       se += e;
       sxl = fmaf((float)k, e, sxl);
     }
-    const double sed = (double)se;
+    chk += se;
+    const double sed = widen_nonneg(se);
     S += sed;
-    SXL += (double)sxl;
+    SXL += widen_nonneg(sxl);
     TY = fma(itd, sed, TY);
     itd += 1.0;
   }
+  if (!(chk <= 3.0e38f)) S = (double)chk;    // NaN / Inf logits: propagate like the reference's softmax
   const double col0 = (double)((lane % LPR) * E), row0 = (double)(lane / LPR);
   double SX = fma(col0, S, SXL);
   double SY = fma(row0, S, (double)R * TY);
@@ -215,10 +232,11 @@ __device__ __forceinline__ void tile_argmax(const uint8_t* tile, int hw, int lan
   if (best_idx == 0x7fffffff) best_idx = 0;  // all -inf / NaN map
 }
 
-template <typename T, bool kArgmax>
-__global__ void __launch_bounds__(kHeatThreads, 1) heat_stream_kernel(const HeatParams p) {
+template <typename T, bool kArgmax, int NW>
+__global__ void __launch_bounds__(32 * (NW + 2), 1) heat_stream_kernel(const HeatParams p) {
+  constexpr int kStages = NW, kConsumerWarps = NW;
   extern __shared__ uint8_t smem_raw[];
-  HeatSmem& sm = *reinterpret_cast<HeatSmem*>(
+  HeatSmem<NW>& sm = *reinterpret_cast<HeatSmem<NW>*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
 
   const int warp = threadIdx.x >> 5;
@@ -366,19 +384,42 @@ __global__ void __launch_bounds__(kHeatThreads, 1) heat_stream_kernel(const Heat
   }
 }
 
-template <typename T, bool kArgmax>
-static int launch_heat(const HeatParams& p, cudaStream_t st) {
-  const size_t smem = sizeof(HeatSmem) + 128;
+static int heat_warps() {
+  static int nw = 0;
+  if (nw == 0) {
+    const char* e = getenv("CDR_HEAT_WARPS");
+    const int v = e ? atoi(e) : kHeatWarpsDefault;
+    nw = (v == 8 || v == 10 || v == 12) ? v : kHeatWarpsDefault;
+  }
+  return nw;
+}
+
+template <typename T, bool kArgmax, int NW>
+static int launch_heat_nw(const HeatParams& p, cudaStream_t st) {
+  const size_t smem = sizeof(HeatSmem<NW>) + 128;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    CDR_CUDA(cudaFuncSetAttribute(heat_stream_kernel<T, kArgmax>,
+    CDR_CUDA(cudaFuncSetAttribute(heat_stream_kernel<T, kArgmax, NW>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   long long grid = p.batch < num_sms() ? p.batch : num_sms();
-  heat_stream_kernel<T, kArgmax><<<(unsigned)grid, kHeatThreads, smem, st>>>(p);
+  heat_stream_kernel<T, kArgmax, NW><<<(unsigned)grid, 32 * (NW + 2), smem, st>>>(p);
   CDR_LAUNCH_OK("heat_stream_kernel");
   return CDR_OK;
+}
+
+template <typename T, bool kArgmax>
+static int launch_heat(const HeatParams& p, cudaStream_t st) {
+  // the fused pose hand-off needs every consumer warp to see every pose (2J >= warps)
+  int nw = heat_warps();
+  const bool fused = !kArgmax && p.P[0] != nullptr;
+  if (fused && 2 * p.joints < nw) nw = 2 * p.joints >= 10 ? 10 : 8;
+  switch (nw) {
+    case 8: return launch_heat_nw<T, kArgmax, 8>(p, st);
+    case 10: return launch_heat_nw<T, kArgmax, 10>(p, st);
+    default: return launch_heat_nw<T, kArgmax, 12>(p, st);
+  }
 }
 
 static int check_heat_shape(const char* who, int H, int W, int elem_bytes) {
@@ -433,11 +474,11 @@ extern "C" int cdr_softargmax_dlt(const void* heat_l, const void* heat_r, int he
                 "cdr_softargmax_dlt: gt3d given without gt2d/pose_err");
   if (batch == 0) return CDR_OK;
   // the pose hand-off (pose_empty) assumes every consumer warp sees every pose: 2J >= #warps
-  CDR_CHECK_ARG(2 * joints >= kConsumerWarps || !gt3d,
-                "cdr_softargmax_dlt: fused MPJPE needs joints >= %d", kConsumerWarps / 2);
-  if (2 * joints < kConsumerWarps) {   // tiny skeletons: unfused (two soft-argmax launches + cdr_dlt)
+  CDR_CHECK_ARG(2 * joints >= kHeatWarpsMin || !gt3d,
+                "cdr_softargmax_dlt: fused MPJPE needs joints >= %d", kHeatWarpsMin / 2);
+  if (2 * joints < kHeatWarpsMin) {   // tiny skeletons: unfused (two soft-argmax launches + cdr_dlt)
     CDR_CHECK_ARG(!heat_is_bf16 && kp2d_l && kp2d_r, "cdr_softargmax_dlt: joints < %d needs fp32 maps and 2D outputs",
-                  kConsumerWarps / 2);
+                  kHeatWarpsMin / 2);
     if (int rc = cdr_softargmax((const float*)heat_l, batch * joints, H, W, scale, kp2d_l, stream)) return rc;
     if (int rc = cdr_softargmax((const float*)heat_r, batch * joints, H, W, scale, kp2d_r, stream)) return rc;
     CDR_CHECK_ARG(batch <= 0x7fffffff, "cdr_softargmax_dlt: batch too large for the unfused path");

@@ -1,6 +1,7 @@
 // Layout kernels: NCHW -> pixel-major rows, and the feature transform layer (FTL).
 // Both are pure data movement / AXPY work: HBM-bound, coalesced 128-byte accesses.
 #include <cuda_fp16.h>
+#include <initializer_list>
 
 #include "kernels.h"
 
@@ -252,6 +253,112 @@ ftl_kernel(const FtlViews<T> fv, int in_pitch, int blk, long long total, int hw,
   if (c < out_fill - ROWS * blk) o[ROWS * blk + c] = (T)0.f;  // zero the pad columns
 }
 
+// 128-bit form of the two FTL kernels (blk, pitches and pad all multiples of 4 channels, 16-byte aligned
+// planes — the head's 100-channel blocks at pitch 304 / 400 / 800): one thread per (row, 4 channels), so a
+// warp reads and writes whole 128-byte lines (fp32) and issues a quarter of the memory instructions.
+struct Vec4 { float v[4]; };
+__device__ __forceinline__ Vec4 ld4(const float* p) {
+  const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+  return Vec4{{q.x, q.y, q.z, q.w}};
+}
+__device__ __forceinline__ Vec4 ld4(const __nv_bfloat16* p) {
+  const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+  return Vec4{{__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y << 16),
+               __uint_as_float(q.y & 0xffff0000u)}};
+}
+__device__ __forceinline__ void st4(float* p, const Vec4& a) {
+  *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+__device__ __forceinline__ void st4(__nv_bfloat16* p, const Vec4& a) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a.v[0], a.v[1]), hi = __floats2bfloat162_rn(a.v[2], a.v[3]);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+
+template <typename T, int ROWS, int COLS>
+__global__ void __launch_bounds__(256)
+ftl_vec_kernel(const FtlViews<T> fv, int in_pitch, int blk, long long total4, int hw, int out_pitch, int out_fill) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const bool v1 = blockIdx.y != 0;   // select, not index: a dynamically indexed __grid_constant__ struct is copied to local memory
+  const int blk4 = blk >> 2;
+  const long long row = idx / blk4;
+  const int c = (int)(idx - row * blk4) << 2;
+  const float* m = (v1 ? fv.mats[1] : fv.mats[0]) + (row / hw) * (ROWS * COLS);
+  const T* __restrict__ in = (v1 ? fv.in[1] : fv.in[0]) + row * in_pitch + c;
+  Vec4 x[COLS];
+#pragma unroll
+  for (int k = 0; k < COLS; ++k) x[k] = ld4(in + k * blk);
+  T* __restrict__ o = (v1 ? fv.out[1] : fv.out[0]) + row * out_pitch + c;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    Vec4 acc{{0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) {
+      const float mk = __ldg(m + r * COLS + k);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc.v[e] = fmaf(mk, x[k].v[e], acc.v[e]);
+    }
+    st4(o + r * blk, acc);
+  }
+  if (c < out_fill - ROWS * blk) st4(o + ROWS * blk, Vec4{{0.f, 0.f, 0.f, 0.f}});   // zero the pad columns
+}
+
+template <int ROWS, int COLS>
+__global__ void __launch_bounds__(256)
+ftl_split_vec_kernel(const FtlViews<float> fv, int in_pitch, int blk, long long total4, int hw, int out_pitch,
+                     int out_fill, float* __restrict__ amax_out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool v1 = blockIdx.y != 0;   // select, not index: a dynamically indexed __grid_constant__ struct is copied to local memory
+  float amax = 0.f;
+  if (idx < total4) {
+    const int blk4 = blk >> 2;
+    const long long row = idx / blk4;
+    const int c = (int)(idx - row * blk4) << 2;
+    const float* m = (v1 ? fv.mats[1] : fv.mats[0]) + (row / hw) * (ROWS * COLS);
+    const long long i0 = row * in_pitch + c;
+    Vec4 x[COLS];
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) {
+      const Vec4 h = ld4((v1 ? fv.in[1] : fv.in[0]) + i0 + k * blk), l = ld4((v1 ? fv.in_lo[1] : fv.in_lo[0]) + i0 + k * blk);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) x[k].v[e] = h.v[e] + l.v[e];     // exact: hi + lo reconstructs the fp32 value
+    }
+    const long long o = row * out_pitch + c;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      Vec4 hi, lo;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) acc = fmaf(__ldg(m + r * COLS + k), x[k].v[e], acc);
+        split_tf32(acc, hi.v[e], lo.v[e]);
+        amax = fmaxf(amax, fabsf(acc));
+      }
+      st4((v1 ? fv.out[1] : fv.out[0]) + o + r * blk, hi);
+      st4((v1 ? fv.out_lo[1] : fv.out_lo[0]) + o + r * blk, lo);
+    }
+    if (c < out_fill - ROWS * blk) {
+      st4((v1 ? fv.out[1] : fv.out[0]) + o + ROWS * blk, Vec4{{0.f, 0.f, 0.f, 0.f}});
+      st4((v1 ? fv.out_lo[1] : fv.out_lo[0]) + o + ROWS * blk, Vec4{{0.f, 0.f, 0.f, 0.f}});
+    }
+  }
+  if (amax_out) {   // max |out| for the scale of the tensor the next conv writes (gemm_tc.cu: kFmtF16P)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(amax_out), __float_as_uint(amax));
+  }
+}
+
+// can the 128-bit kernels run?  every plane pointer 4-element aligned, every stride a multiple of 4 channels
+static bool ftl_vec_ok(int elem_bytes, int in_pitch, int blk, int out_pitch, int out_fill, int rows,
+                       std::initializer_list<const void*> ptrs) {
+  if ((blk | in_pitch | out_pitch | (out_fill - rows * blk)) & 3) return false;
+  for (const void* p : ptrs)
+    if (p && ((uintptr_t)p & (uintptr_t)(4 * elem_bytes - 1))) return false;
+  return true;
+}
+
 template <int ROWS, int COLS>
 __global__ void __launch_bounds__(256)
 ftl_split_kernel(const FtlViews<float> fv, int in_pitch, int blk, long long total, int hw, int out_pitch, int out_fill,
@@ -309,6 +416,18 @@ int launch_ftl_split2(const float* const in_hi[2], const float* const in_lo[2], 
   }
   CDR_CHECK_ARG(n > 0 && hw > 0 && blk > 0, "ftl_split: bad args");
   const long long total = (long long)n * hw * blk;
+  if ((rows == 4 && cols == 3 || rows == 3 && cols == 4) &&
+      ftl_vec_ok(4, in_pitch, blk, out_pitch, out_fill, rows,
+                 {in_hi[0], in_lo[0], out_hi[0], out_lo[0], views > 1 ? in_hi[1] : nullptr, views > 1 ? in_lo[1] : nullptr,
+                  views > 1 ? out_hi[1] : nullptr, views > 1 ? out_lo[1] : nullptr})) {
+    const dim3 grid4((unsigned)ceil_div<long long>(total / 4, 256), views);
+    if (rows == 4)
+      ftl_split_vec_kernel<4, 3><<<grid4, 256, 0, st>>>(fv, in_pitch, blk, total / 4, hw, out_pitch, out_fill, amax_out);
+    else
+      ftl_split_vec_kernel<3, 4><<<grid4, 256, 0, st>>>(fv, in_pitch, blk, total / 4, hw, out_pitch, out_fill, amax_out);
+    CDR_LAUNCH_OK("ftl_split_vec_kernel");
+    return CDR_OK;
+  }
   const dim3 grid((unsigned)ceil_div<long long>(total, 256), views);
   if (rows == 4 && cols == 3)
     ftl_split_kernel<4, 3><<<grid, 256, 0, st>>>(fv, in_pitch, blk, total, hw, out_pitch, out_fill, amax_out);
@@ -336,6 +455,17 @@ int launch_ftl2(const T* const in[2], int in_pitch, const float* const mats[2], 
                     out_fill <= out_pitch && out_fill - rows * blk <= blk,
                 "cdr_ftl: pitches too small for %dx%d blocks of %d", rows, cols, blk);
   const long long total = (long long)n * hw * blk;
+  if ((rows == 4 && cols == 3 || rows == 3 && cols == 4) &&
+      ftl_vec_ok((int)sizeof(T), in_pitch, blk, out_pitch, out_fill, rows,
+                 {in[0], out[0], views > 1 ? in[1] : nullptr, views > 1 ? out[1] : nullptr})) {
+    const dim3 grid4((unsigned)ceil_div<long long>(total / 4, 256), views);
+    if (rows == 4)
+      ftl_vec_kernel<T, 4, 3><<<grid4, 256, 0, st>>>(fv, in_pitch, blk, total / 4, hw, out_pitch, out_fill);
+    else
+      ftl_vec_kernel<T, 3, 4><<<grid4, 256, 0, st>>>(fv, in_pitch, blk, total / 4, hw, out_pitch, out_fill);
+    CDR_LAUNCH_OK("ftl_vec_kernel");
+    return CDR_OK;
+  }
   const dim3 grid((unsigned)ceil_div<long long>(total, 256), views);
   if (rows == 4 && cols == 3)
     ftl_kernel<T, 4, 3><<<grid, 256, 0, st>>>(fv, in_pitch, blk, total, hw, out_pitch, out_fill);

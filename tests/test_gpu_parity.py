@@ -348,6 +348,50 @@ def test_ftl_identity_and_oracle(cuda_pkg):
         L.check(L.lib().cdr_ftl(L.ptr(xin), 304, L.ptr(P_d), 2, 2, 100, b, 64, L.ptr(out), 400, 400, st))
 
 
+def test_ftl_scalar_and_vector_paths(cuda_pkg):
+    """The 128-bit FTL kernel (blk, pitches, pad multiples of 4 channels) and the scalar kernel
+    (anything else: blk = 25 here, and a mis-aligned plane) against the definition
+    out[row, r*blk + c] = sum_k m[r,k] * in[row, k*blk + c]  (models/cdrnet.py:45-56)."""
+    L = cuda_pkg._lib
+    st = L.current_stream_ptr()
+    g = torch.Generator().manual_seed(9)
+    n, hw = 5, 64
+    for blk, in_pitch, out_pitch, out_fill, off in [(100, 304, 400, 400, 0), (100, 304, 800, 400, 400),
+                                                    (25, 80, 101, 101, 0), (100, 304, 401, 400, 1)]:
+        x = torch.randn(n * hw, in_pitch, generator=g)
+        m = torch.randn(n, 4, 3, generator=g)
+        xd, md = x.cuda(), m.cuda()
+        out = torch.full((n * hw, out_pitch), float("nan"), device="cuda")
+        L.check(L.lib().cdr_ftl(L.ptr(xd), in_pitch, L.ptr(md), 4, 3, blk, n, hw, out.data_ptr() + 4 * off, out_pitch,
+                                out_fill, st))
+        torch.cuda.synchronize()
+        want = torch.einsum("nrk,npkc->nprc", m.double(), x[:, :3 * blk].double().reshape(n, hw, 3, blk)).reshape(n * hw, 4 * blk)
+        got = out.cpu()
+        got = got[:, off:off + out_fill]
+        assert float((got[:, :4 * blk].double() - want).abs().max()) < 1e-5 * float(want.abs().max()), (blk, in_pitch)
+        assert torch.all(got[:, 4 * blk:] == 0)
+        if off == 0 and out_fill < out_pitch:
+            assert torch.isnan(out.cpu()[:, out_fill:]).all()       # never writes past out_fill
+
+
+def test_softargmax_nonfinite_logits_propagate(cuda_pkg):
+    """torch.softmax gives NaN for a map that holds NaN or +Inf (models/cdrnet.py:131-133); the 64x64 fast
+    path widens its partial sums on the integer pipe, which alone would lose them."""
+    L = cuda_pkg._lib
+    h = torch.randn(6, 64, 64, generator=torch.Generator().manual_seed(2))
+    h[1, 3, 5] = float("nan")
+    h[2, 60, 1] = float("inf")
+    h[4, 0, 0] = float("-inf")                      # -Inf is an ordinary zero-weight pixel
+    want = (O.process_heatmap(h.double().unsqueeze(0))[0] * 4.0).numpy()
+    assert np.isnan(want[1]).all() and np.isnan(want[2]).all() and np.isfinite(want[[0, 3, 4, 5]]).all()
+    hd, kp = h.cuda(), torch.empty(6, 2, device="cuda")
+    L.check(L.lib().cdr_softargmax(L.ptr(hd), 6, 64, 64, 4.0, L.ptr(kp), L.current_stream_ptr()))
+    torch.cuda.synchronize()
+    got = kp.cpu().numpy()
+    assert np.isnan(got[1]).all() and np.isnan(got[2]).all()
+    np.testing.assert_allclose(got[[0, 3, 4, 5]], want[[0, 3, 4, 5]], rtol=0, atol=1e-4)
+
+
 @pytest.mark.parametrize("gain", [1.0, 3.0e4, 1.0e-5])
 def test_decoder_f16x2_dynamic_range(cuda_pkg, gain):
     """The f16x2 decoder scales every tensor by a data-dependent power of two: the relative error of
