@@ -165,6 +165,7 @@ struct TcGemmParams {
   int has_res;            // residual tensor (rows like C, bf16) added before the ReLU: its 128 x 128 tile travels
                           // through the operand ring as one extra stage per tile (BN = 128, bf16 kind)
   int box_rows, box_imgs; // 4-D box: W x box_rows x box_imgs pixels = 128
+  int half_dim, half_step;// CTA pairs: coordinate (2 = row, 3 = image) and step that separate the two 64-pixel half boxes
   int groups;             // phases (deconv) or independent problems stacked along rows
   int a_group_rows;       // 2-D A: row offset per group
   int b_group_rows;       // weight-row offset per group
@@ -329,7 +330,15 @@ __device__ __forceinline__ void tma_store_block(const TcGemmParams& p, const voi
 // done by the epilogue warps in registers with round-to-nearest.
 constexpr int kSplitChunk = 4;
 
-template <int BN, int KIND, int OFMT>
+// CL = 1: CTA pairs (thread-block clusters of 2).  The two CTAs of a pair work on the two N tiles of the SAME
+// 128-pixel block and output phase, so they need the same A tile: each loads half of it (64 pixels) and
+// multicasts it into both CTAs' stage (tmap_a / tmap_a_lo then carry the half box) — one L2 read feeds two
+// SMs.  ncu on the f16x2 transposed convs (BN = 128: 64 KB of operands per 12 MMAs) showed 12.3 TB/s of
+// L2->SM traffic and the tensor pipe at 84 % of what the bf16 kernel reaches; with the shared A tile the
+// traffic drops by a quarter.  Protocol: a stage may be refilled only when BOTH CTAs' MMAs have released
+// it, so empty[s] counts two arrivals and every release is a multicast commit to both CTAs; everything
+// else (TMEM, epilogue) stays per CTA.  Both CTAs run the same number of tiles (even n_tiles and grid).
+template <int BN, int KIND, int OFMT, int CL>
 __global__ void __launch_bounds__(TcCfg<BN, KIND, OFMT>::kThreads, 1)
 tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
                    const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo,
@@ -378,7 +387,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&empty[s], 1);
+      ptx::mbar_init(&empty[s], CL ? 2 : 1);         // CL: released by the MMA issuers of both CTAs of the pair
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
@@ -392,7 +401,9 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_base_slot);
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL != 0) ptx::cluster_sync();       // the peer's barriers exist before anything is multicast
   ptx::tc_fence_after();
+  const uint32_t cta_rank = CL ? ptx::cluster_ctarank() : 0u;
   // ... and do not touch anything the previous kernel wrote (activations, scale slots) before it is complete
   ptx::grid_dep_wait();
   const uint32_t tmem_base = *tmem_base_slot;
@@ -429,8 +440,22 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1;
             }
             const int ys = p.stride * y0 + dy;
-            ptx::tma_load_4d(stage_a(s, 0), &tmap_a, &full[s], k0, dx, ys, img0);
-            if (kSplit) ptx::tma_load_4d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, dx, ys, img0);
+            if constexpr (CL != 0) {
+              // my half of the tile (64 pixels = 8 KB per plane), delivered to both CTAs of the pair
+              const int yh = ys + (p.half_dim == 2 ? (int)cta_rank * p.half_step : 0);
+              const int ih = img0 + (p.half_dim == 3 ? (int)cta_rank * p.half_step : 0);
+              const uint32_t off = cta_rank * (uint32_t)(kABytes / 2);
+              ptx::tma_load_4d_mc(stage_a(s, 0) + off, &tmap_a, &full[s], k0, dx, yh, ih, 3);
+              if (kSplit) ptx::tma_load_4d_mc(stage_a(s, 1) + off, &tmap_a_lo, &full[s], k0, dx, yh, ih, 3);
+            } else {
+              ptx::tma_load_4d(stage_a(s, 0), &tmap_a, &full[s], k0, dx, ys, img0);
+              if (kSplit) ptx::tma_load_4d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, dx, ys, img0);
+            }
+          } else if constexpr (CL != 0) {
+            const int row = g * p.a_group_rows + m0 + (int)cta_rank * (kTcBM / 2);
+            const uint32_t off = cta_rank * (uint32_t)(kABytes / 2);
+            ptx::tma_load_2d_mc(stage_a(s, 0) + off, &tmap_a, &full[s], k0, row, 3);
+            if (kSplit) ptx::tma_load_2d_mc(stage_a(s, 1) + off, &tmap_a_lo, &full[s], k0, row, 3);
           } else {
             ptx::tma_load_2d(stage_a(s, 0), &tmap_a, &full[s], k0, g * p.a_group_rows + m0);
             if (kSplit) ptx::tma_load_2d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, g * p.a_group_rows + m0);
@@ -469,6 +494,10 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       constexpr uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
                                    ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
       auto desc = [&](const uint8_t* ptr) { return desc_hi | (uint64_t)((ptx::smem_u32(ptr) >> 4) & 0x3FFF); };
+      auto release_stage = [&](int s) {
+        if constexpr (CL != 0) ptx::umma_commit_mc(&empty[s], 3);   // the peer multicasts into this stage too
+        else ptx::umma_commit(&empty[s]);
+      };
       uint32_t it = 0, tl = 0, ch = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
         const int acc = tl & 1;
@@ -484,7 +513,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
             for (int k = 0; k < 4; ++k)    // +32 bytes (= 2 x 16 B) per K step (16 bf16) inside the swizzle row
               mma(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (kb | k) != 0);
-            ptx::umma_commit(&empty[s]);           // smem stage reusable once these MMAs retire
+            release_stage(s);                      // smem stage reusable once these MMAs retire
           }
         } else {
           const uint32_t d_corr = tmem_base + (uint32_t)((2 + acc) * BN);
@@ -507,7 +536,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 mma(d_corr, da + o, dbl + o, 1u);                  // hi*lo  } terms are 2^-11 of the main one
                 mma(d_main, da + o, db + o, (kb > kb0 || k > 0));  // hi*hi, short chain
               }
-              ptx::umma_commit(&empty[s]);
+              release_stage(s);
             }
             ptx::umma_commit(&chunk_full[buf]);    // main-term chunk ready to be drained
           }
@@ -731,6 +760,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   // ------------------------------------------------------------------ teardown
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL != 0) ptx::cluster_sync();       // the peer's last stage releases arrive on OUR barriers
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -813,7 +843,29 @@ static bool tc_use_pdl() {
   return v == 1;
 }
 
-template <int BN, int KIND, int OFMT>
+// CTA pairs with a multicast A tile (kernel template parameter CL): CDR_CLUSTER=0 turns them off for A/B timing
+static bool tc_use_cluster() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CDR_CLUSTER");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+// can this launch run as CTA pairs?  the pair shares one A tile: an even number of N tiles per pixel block
+static bool tc_cluster_ok(const TcLaunch& l, int bn) {
+  if (!tc_use_cluster() || l.res || l.stride > 1 || (l.layer->n_pad / bn) % 2 != 0) return false;
+  if (l.deconv || l.conv3) {
+    if (l.W > kTcBM || kTcBM % l.W != 0) return false;
+    int rows = kTcBM / l.W;
+    if (rows > l.H) rows = l.H;
+    const int imgs = kTcBM / (l.W * rows);
+    return imgs >= 2 ? imgs % 2 == 0 : rows % 2 == 0;
+  }
+  return true;
+}
+
+template <int BN, int KIND, int OFMT, int CL = 0>
 static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
   using Cfg = TcCfg<BN, KIND, OFMT>;
   constexpr int kElem = KindTraits<KIND>::kElem;
@@ -821,7 +873,7 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
   constexpr int kAFmt = KindTraits<KIND>::kFmt;
   static bool attr_set = false;
   if (!attr_set) {
-    CDR_CUDA(cudaFuncSetAttribute(tap_gemm_tc_kernel<BN, KIND, OFMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CDR_CUDA(cudaFuncSetAttribute(tap_gemm_tc_kernel<BN, KIND, OFMT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -876,17 +928,23 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
       CDR_CHECK_ARG(l.H % rows == 0 && l.cin % kBK == 0 && stride * l.W <= 256 && stride * rows <= 256,
                     "tap_gemm_tc: unsupported tap-conv geometry");
       p.box_rows = rows; p.box_imgs = imgs;
+      int brows = rows, bimgs = imgs;
+      if (CL) {                               // each CTA of a pair loads (and multicasts) half of the box
+        CDR_CHECK_ARG(stride == 1 && (imgs >= 2 ? imgs % 2 == 0 : rows % 2 == 0), "tap_gemm_tc: box cannot be halved");
+        if (imgs >= 2) { bimgs = imgs / 2; p.half_dim = 3; p.half_step = bimgs; }
+        else { brows = rows / 2; p.half_dim = 2; p.half_step = brows; }
+      }
       const uint64_t iw = (uint64_t)stride * l.W, ih = (uint64_t)stride * l.H;      // input pixel grid
       const uint64_t dims[4] = {(uint64_t)l.cin, iw, ih, (uint64_t)l.n_img};
       const uint64_t strides[3] = {(uint64_t)l.a_pitch, (uint64_t)l.a_pitch * iw, (uint64_t)l.a_pitch * iw * ih};
       // a strided box spans stride*count input pixels and the TMA unit keeps every stride-th of them
-      const uint32_t box[4] = {(uint32_t)kBK, (uint32_t)(stride * l.W), (uint32_t)(stride * rows), (uint32_t)imgs};
+      const uint32_t box[4] = {(uint32_t)kBK, (uint32_t)(stride * l.W), (uint32_t)(stride * brows), (uint32_t)bimgs};
       const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
       if (int rc = make_tmap(&tmap_a[pl], l.A.p[pl], kAFmt, 4, dims, strides, box, estr)) return rc;
     } else {
       const uint64_t dims[2] = {(uint64_t)l.cin, (uint64_t)l.a_rows_total};
       const uint64_t strides[1] = {(uint64_t)l.a_pitch};
-      const uint32_t box[2] = {(uint32_t)kBK, (uint32_t)kTcBM};
+      const uint32_t box[2] = {(uint32_t)kBK, (uint32_t)(CL ? kTcBM / 2 : kTcBM)};
       if (int rc = make_tmap(&tmap_a[pl], l.A.p[pl], kAFmt, 2, dims, strides, box)) return rc;
     }
   }
@@ -926,18 +984,32 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
     const uint32_t box[3] = {64, 128, 1};     // half a residual tile: 128 rows x 64 channels
     if (int rc = make_tmap(&tmap_r, l.res, kFmtBF16, 3, dims, strides, box)) return rc;
   }
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
+  if (CL) {
+    // pairs: CTA 2i / 2i+1 take tiles t / t+1 = the two N tiles of one pixel block, for the same number of rounds
+    CDR_CHECK_ARG(p.n_tiles % 2 == 0 && !l.res, "tap_gemm_tc: CTA pairs need an even number of N tiles and no residual");
+    grid &= ~1;
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = 2;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+  }
+  if (tc_use_pdl()) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = tc_use_pdl() ? 1 : 0;
-  CDR_CUDA(cudaLaunchKernelEx(&cfg, tap_gemm_tc_kernel<BN, KIND, OFMT>, tmap_a[0], tmap_a[1], l.layer->map[0],
+  cfg.numAttrs = n_attr;
+  CDR_CUDA(cudaLaunchKernelEx(&cfg, tap_gemm_tc_kernel<BN, KIND, OFMT, CL>, tmap_a[0], tmap_a[1], l.layer->map[0],
                               l.layer->map[KindTraits<KIND>::kPlanes - 1], tmap_c[0], tmap_c[1], tmap_r, p));
   CDR_LAUNCH_OK("tap_gemm_tc_kernel");
   return CDR_OK;
@@ -959,6 +1031,7 @@ static int launch_tc(const TcLaunch& l, cudaStream_t st) {
   } else if (kind == kKindF16X2 && ofmt == kFmtTF32P) {
     if (bn == 128) return launch_tc_t<128, kKindF16X2, kFmtTF32P>(l, st);
   } else if (kind == kKindF16X2 && ofmt == kFmtF16P) {
+    if (bn == 128 && tc_cluster_ok(l, bn)) return launch_tc_t<128, kKindF16X2, kFmtF16P, 1>(l, st);
     if (bn == 128) return launch_tc_t<128, kKindF16X2, kFmtF16P>(l, st);
     if (bn == 32) return launch_tc_t<32, kKindF16X2, kFmtF16P>(l, st);
   }
