@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcdrhead.so")
+LIB_PATH = os.environ.get("CDR_LIB_PATH") or os.path.join(_HERE, "libcdrhead.so")   # override: A/B builds of the same ABI
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cdrhead.h")
 
 CDR_PREC_FP32 = 0

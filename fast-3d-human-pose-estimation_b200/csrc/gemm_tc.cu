@@ -316,11 +316,13 @@ __device__ __forceinline__ void tma_store_block(const TcGemmParams& p, const voi
                       words[4 * j + 3]);
   ptx::fence_proxy_async();
   __syncwarp();
+#ifndef CDR_EXP_NO_TMASTORE   /* timing experiment only: all epilogue math and staging, no store */
   if (lane == 0) {
     if (p.out_mode == kOutDeconv) ptx::tma_store_5d(tmap, stage, c0, sc.px, sc.x0, sc.py, sc.r0);
     else ptx::tma_store_3d(tmap, stage, c0, sc.m, sc.g);
     ptx::bulk_commit();
   }
+#endif
 }
 
 // K-blocks accumulated inside TMEM before the split kinds' main term is drained into fp32 registers.
@@ -328,7 +330,10 @@ __device__ __forceinline__ void tma_store_block(const TcGemmParams& p, const voi
 // of same-signed partial sums that bias grows linearly (measured: 1e-5 relative at K=2048, 40x
 // worse than FFMA).  Chains of 4 K-blocks (16 MMAs) keep it below 1e-6; the cross-chunk sum is
 // done by the epilogue warps in registers with round-to-nearest.
-constexpr int kSplitChunk = 4;
+#ifndef CDR_SPLIT_CHUNK
+#define CDR_SPLIT_CHUNK 4
+#endif
+constexpr int kSplitChunk = CDR_SPLIT_CHUNK;
 
 // CL = 1: CTA pairs (thread-block clusters of 2).  The two CTAs of a pair work on the two N tiles of the SAME
 // 128-pixel block and output phase, so they need the same A tile: each loads half of it (64 pixels) and
@@ -348,6 +353,11 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   constexpr int S = Cfg::kStages;
   constexpr int kTcBK = Cfg::kBK;
   constexpr bool kSplit = KIND != kKindBF16;
+#ifdef CDR_EXP_NO_LO
+  constexpr bool kLoadLo = false;   // timing experiment: hi planes only
+#else
+  constexpr bool kLoadLo = kSplit;
+#endif
   constexpr int kEpiWarps = Cfg::kEpiWarps;
   constexpr int kCols = Cfg::kColsPerWarp;       // columns of the tile owned by one epilogue warp
   extern __shared__ uint8_t smem_raw[];
@@ -429,7 +439,11 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           const int s = it % S;
           const uint32_t par = (it / S) & 1;
           ptx::mbar_wait(&empty[s], par ^ 1u);
+#ifdef CDR_EXP_NO_LO
+          ptx::mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes / (kSplit ? 2 : 1));
+#else
           ptx::mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+#endif
           const int tap = kb / kb_per_tap;
           const int k0 = (kb - tap * kb_per_tap) * kTcBK;
           if (p.a4d) {
@@ -446,22 +460,22 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               const int ih = img0 + (p.half_dim == 3 ? (int)cta_rank * p.half_step : 0);
               const uint32_t off = cta_rank * (uint32_t)(kABytes / 2);
               ptx::tma_load_4d_mc(stage_a(s, 0) + off, &tmap_a, &full[s], k0, dx, yh, ih, 3);
-              if (kSplit) ptx::tma_load_4d_mc(stage_a(s, 1) + off, &tmap_a_lo, &full[s], k0, dx, yh, ih, 3);
+              if (kLoadLo) ptx::tma_load_4d_mc(stage_a(s, 1) + off, &tmap_a_lo, &full[s], k0, dx, yh, ih, 3);
             } else {
               ptx::tma_load_4d(stage_a(s, 0), &tmap_a, &full[s], k0, dx, ys, img0);
-              if (kSplit) ptx::tma_load_4d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, dx, ys, img0);
+              if (kLoadLo) ptx::tma_load_4d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, dx, ys, img0);
             }
           } else if constexpr (CL != 0) {
             const int row = g * p.a_group_rows + m0 + (int)cta_rank * (kTcBM / 2);
             const uint32_t off = cta_rank * (uint32_t)(kABytes / 2);
             ptx::tma_load_2d_mc(stage_a(s, 0) + off, &tmap_a, &full[s], k0, row, 3);
-            if (kSplit) ptx::tma_load_2d_mc(stage_a(s, 1) + off, &tmap_a_lo, &full[s], k0, row, 3);
+            if (kLoadLo) ptx::tma_load_2d_mc(stage_a(s, 1) + off, &tmap_a_lo, &full[s], k0, row, 3);
           } else {
             ptx::tma_load_2d(stage_a(s, 0), &tmap_a, &full[s], k0, g * p.a_group_rows + m0);
-            if (kSplit) ptx::tma_load_2d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, g * p.a_group_rows + m0);
+            if (kLoadLo) ptx::tma_load_2d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, g * p.a_group_rows + m0);
           }
           ptx::tma_load_2d(stage_b(s, 0), &tmap_b, &full[s], tap * p.cin + k0, g * p.b_group_rows + n_tile * BN);
-          if (kSplit)
+          if (kLoadLo)
             ptx::tma_load_2d(stage_b(s, 1), &tmap_b_lo, &full[s], tap * p.cin + k0, g * p.b_group_rows + n_tile * BN);
         }
         if constexpr (KIND == kKindBF16 && BN == 128) {
@@ -532,8 +546,10 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
               for (int k = 0; k < 4; ++k) {        // K step = 8 tf32 / 16 f16 = 32 bytes
                 const uint64_t o = (uint64_t)(2 * k);
+#ifndef CDR_EXP_NO_CORR   /* timing experiment only: results are wrong without the correction terms */
                 mma(d_corr, dal + o, db + o, (kb | k) != 0);       // lo*hi  } whole-tile chain: these
                 mma(d_corr, da + o, dbl + o, 1u);                  // hi*lo  } terms are 2^-11 of the main one
+#endif
                 mma(d_main, da + o, db + o, (kb > kb0 || k > 0));  // hi*hi, short chain
               }
               release_stage(s);
@@ -609,6 +625,9 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       bool has_res_vals = false;
       auto emit = [&](const float (&a32)[32], int c, auto half_c, uint32_t (&wh)[32], uint32_t (&wl)[32]) {
         constexpr int half = decltype(half_c)::value;     // which 32-column half of a 64-column store block
+#ifdef CDR_EXP_NO_STORE   /* timing experiment only: the epilogue drains TMEM but neither converts nor stores */
+        if (a32[0] != 12345.678f) return;
+#endif
         // c = column inside the warp's range; TMA path gathers two slabs (64 columns) per store
         if (!use_tma) {
           store_slab<KIND, OFMT>(p, a32, n0 + c, g, row_ok, orow, img, pix, HW, bias, wsi, es);
@@ -1203,7 +1222,10 @@ static void plan_layer(TcLayer& L, Bump1K& b, int kind, int rows, int k, int k_p
 static size_t plan_tc_weights(TcPack& pk, const TcWeights& w, void* base) {
   Bump1K b(base);
   const int fk = mode_fusion_kind(pk.mode), dk = mode_decoder_kind(pk.mode);
-  const int bn_f = fk == kKindBF16 ? 256 : 128, bn_d = dk == kKindBF16 ? 256 : 128;
+  const int bn_f = fk == kKindBF16 ? 256 : 128;
+  int bn_d = dk == kKindBF16 ? 256 : 128;
+  if (const char* e = getenv("CDR_BF16_DECONV_BN"))     // experiment knob: UMMA N = 128 vs 256 at equal math
+    if (dk == kKindBF16 && atoi(e) == 128) bn_d = 128;
   const bool scaled = dk == kKindF16X2;          // outputs feeding the decoder are stored in kFmtF16P
   if (w.has_fusion) {
     // conv_layer1 reads the encoder's latents (post-ReLU, bounded): in hybrid mode it runs f16x2 like the

@@ -117,6 +117,14 @@ def traffic(rnd):
         u, l = d["units"], d["launches"][0]
         out["softargmax_dlt_stream"] = to_bytes(l["dram__bytes_read.sum"], u["dram__bytes_read.sum"]) + \
             to_bytes(l["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
+    path = os.path.join(ROOT, "profiles", f"{rnd}_prof_ftl_raw.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        u = d["units"]
+        out["ftl_stream"] = {f"inverse_4x3_launch{i}":
+                             to_bytes(l["dram__bytes_read.sum"], u["dram__bytes_read.sum"]) +
+                             to_bytes(l["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
+                             for i, l in enumerate(d["launches"][:2])}
     out["source"] = f"ncu --set full --clock-control none, profiles/{rnd}_prof_*_raw.json (B=64 head; 8192-pose stream)"
     json.dump(out, open(os.path.join(ROOT, "profiles", f"{rnd}_traffic.json"), "w"), indent=1)
     print("wrote", f"profiles/{rnd}_traffic.json", out)
@@ -126,6 +134,6 @@ if __name__ == "__main__":
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
     for tag in ("bf16", "fp32"):
         launches(tag, rnd)
-    for rep in ("prof_tc", "prof_f16x2", "prof_tf32", "prof_ffma", "prof_heat"):
+    for rep in ("prof_tc", "prof_f16x2", "prof_tf32", "prof_ffma", "prof_heat", "prof_ftl"):
         full(rep, rnd)
     traffic(rnd)
