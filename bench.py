@@ -461,6 +461,50 @@ def ftl_stream(dev, n=4096, reps=5):
     return out
 
 
+def backward_stream(dev, poses=4096, reps=5):
+    """SURVEY §8f rank 3 (first slice): backward of soft-argmax (HBM-bound: 16 KB of logits in, 16 KB of gradient out
+    per map) and of the DLT, at a size that leaves L2.  Algorithmic bytes per pose = 2 * 19 * (2 * 16384 + 8)."""
+    from fast_3d_human_pose_estimation_b200 import synth, _lib
+    L = _lib.lib()
+    st = _lib.current_stream_ptr(dev)
+    n_maps = 2 * poses * JOINTS
+    g = torch.Generator(device=dev).manual_seed(0)
+    heat = torch.empty((n_maps, 64, 64), dtype=torch.float32, device=dev)
+    for lo in range(0, n_maps, 16384):
+        heat[lo:lo + 16384].normal_(0.0, 3.0, generator=g)
+    gk = torch.randn((n_maps, 2), device=dev, generator=g)
+    gh = torch.empty_like(heat)
+    cams = synth.make_cameras(64, seed=4)
+    P_l = torch.from_numpy(cams["P_l"]).to(dev).repeat(poses // 64, 1, 1).contiguous()
+    P_r = torch.from_numpy(cams["P_r"]).to(dev).repeat(poses // 64, 1, 1).contiguous()
+    kl = torch.rand((poses, JOINTS, 2), device=dev, generator=g) * 256
+    kr = torch.rand((poses, JOINTS, 2), device=dev, generator=g) * 256
+    gx = torch.randn((poses, JOINTS, 3), device=dev, generator=g)
+    gl, gr = torch.empty_like(kl), torch.empty_like(kr)
+
+    def timed(fn):
+        fn(); fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+    ms_sa = timed(lambda: _lib.check(L.cdr_softargmax_backward(_lib.ptr(heat), _lib.ptr(gk), n_maps, 64, 64, 4.0,
+                                                               _lib.ptr(gh), st)))
+    ms_dlt = timed(lambda: _lib.check(L.cdr_dlt_backward(_lib.ptr(P_l), _lib.ptr(P_r), _lib.ptr(kl), _lib.ptr(kr),
+                                                         _lib.ptr(gx), poses, JOINTS, _lib.ptr(gl), _lib.ptr(gr), st)))
+    pk = peaks()
+    bytes_sa = n_maps * (2 * 16384 + 8)
+    gbs = bytes_sa / (ms_sa / 1e3) / 1e9
+    return {"softargmax_backward": {"launch_ms": ms_sa, "maps": n_maps, "algorithmic_bytes": bytes_sa, "achieved": gbs,
+                                    "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "bound": "hbm"},
+            "dlt_backward": {"launch_ms": ms_dlt, "joints_per_s": poses * JOINTS / (ms_dlt / 1e3), "bound": "latency / fp64"},
+            "input": f"{poses} poses x 19 joints x 2 views of 64x64 fp32 logits ({heat.numel() * 4 / 1e9:.1f} GB in, the same out)"}
+
+
 def config5(args, ctx, precision, total=1024):
     """BASELINE configs[4]: the full pipeline (uint8 stereo frames in pinned HOST memory -> ResNet-101 encoder
     + head on this repo's kernels -> 3D joints + MPJPE sums on the host) over a batch of `total` stereo pairs
@@ -814,7 +858,8 @@ def run_ours(args):
         line["cpu_baseline"] = cpu
         if world == 1 and not args.no_stream_microbench:
             line["roofline_hbm_stream"] = stream_microbench(dev)
-            for key, fn in (("config4_softargmax_dlt_1m_poses", config4_1m_poses), ("roofline_hbm_ftl", ftl_stream)):
+            for key, fn in (("config4_softargmax_dlt_1m_poses", config4_1m_poses), ("roofline_hbm_ftl", ftl_stream),
+                            ("backward_ops", backward_stream)):
                 try:
                     line[key] = fn(dev)
                 except Exception as e:                  # secondary numbers: never lose the main line

@@ -15,7 +15,8 @@ from .encoder import ResNet
 from .graph import HeadGraph, HeadPipeline, FramePipeline
 from .geometry import baseline_keypoints, get_max_preds, triangulation
 from .metrics import calc_mpjpe, mpjpe_sums
+from .autograd import soft_argmax_2d, dlt, ftl
 
 __all__ = ["CDRNet", "CanonicalFusion", "PoseDecoder", "PoseResNet", "ResNet", "calc_mpjpe",
-           "mpjpe_sums", "HeadGraph", "HeadPipeline", "FramePipeline", "get_max_preds", "baseline_keypoints", "triangulation", "build",
+           "mpjpe_sums", "HeadGraph", "HeadPipeline", "FramePipeline", "get_max_preds", "baseline_keypoints", "triangulation", "soft_argmax_2d", "dlt", "ftl", "build",
            "CdrError"]

@@ -101,6 +101,8 @@ _SIGNATURES = {
     "cdr_mpjpe_partial": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int,
                                     C.c_longlong, C.c_int, _vp, _vp, _vp]),
     "cdr_mpjpe_reduce": (C.c_int, [_vp, C.c_longlong, C.c_int, _vp, _vp, _vp]),
+    "cdr_softargmax_backward": (C.c_int, [_vp, _vp, C.c_longlong, C.c_int, C.c_int, C.c_float, _vp, _vp]),
+    "cdr_dlt_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

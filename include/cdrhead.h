@@ -259,6 +259,21 @@ int cdr_mpjpe_partial(const void* pred2d_l, const void* pred2d_r, const void* pr
 int cdr_mpjpe_reduce(const double* pose_err, long long n, int joints, double* sums, void* scratch,
                      void* stream);
 
+/* ---- SURVEY §8f rank 3 (first slice): backward passes of the non-conv operators — what train_cdr.py:105-127
+ * back-propagates through (`loss.backward()` via process_heatmap and dlt).  fp32 in/out, fp64 internals.
+ * The FTL is linear: its backward is cdr_ftl with the transposed matrices (no extra entry point). */
+
+/* d/d heat of process_heatmap (+ scale), models/cdrnet.py:120-149,250.  heat (n_maps,H,W), grad_kp (n_maps,2)
+ * -> grad_heat (n_maps,H,W) = scale * p * (gx (x - cx) + gy (y - cy)), p = softmax(heat).  W % 4 == 0, H*W <= 4096. */
+int cdr_softargmax_backward(const float* heat, const float* grad_kp, long long n_maps, int H, int W,
+                            float scale, float* grad_heat, void* stream);
+
+/* d/d (kp_l, kp_r) of CDRNet.dlt, models/cdrnet.py:151-179 (the gradient torch.svd's backward gives for
+ * X = V[:3,3] / V[3,3]; P carries no gradient in the reference).  grad_xyz (B,J,3) -> grad_kp_l/r (B,J,2). */
+int cdr_dlt_backward(const float* P_l, const float* P_r, const float* kp_l, const float* kp_r,
+                     const float* grad_xyz, int batch, int joints, float* grad_kp_l, float* grad_kp_r,
+                     void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
