@@ -78,11 +78,11 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
             except Exception:
                 continue
             for n, v in zip(names, r[5:9]):
@@ -92,7 +92,7 @@ class ClockSampler:
         sm_sorted = sorted(sm)
         load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
         return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 def cpu_model():
@@ -791,6 +791,9 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from fast_3d_human_pose_estimation_b200 import dist as cdist
+    orig_affinity = os.sched_getaffinity(0)
+    numa_cpus = cdist.bind_to_gpu_numa(local)      # before any pinned allocation (first touch)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, K, W = args.batch, args.steps, max(3, args.warmup)
@@ -809,6 +812,7 @@ def run_ours(args):
     ctx["vis"] = torch.from_numpy(gt["vis"]).to(dev)
     ctx["flush"] = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    ctx["numa_cpus"] = numa_cpus
     main_res = measure(args, args.precision, ctx)
     other = None
     if args.precision != "bf16" and not args.single_precision:
@@ -829,6 +833,7 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
+            os.sched_setaffinity(0, orig_affinity)      # the CPU arm uses every host core again
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
             cb = min(B, 32)
@@ -850,7 +855,9 @@ def run_ours(args):
                        "weights": "seeded random init (final_layer x0.1)",
                        "l2": "flushed between steps (256 MB write)",
                        "collective": "1 all-gather of (B,19,3)+32 B per step" if world > 1 else "none",
-                       "parallelism": f"dp{world}"},
+                       "parallelism": f"dp{world}",
+                       "host_binding": (f"rank 0 bound to {len(numa_cpus)} CPUs local to its GPU (NVML affinity)"
+                                        if numa_cpus else "none")},
         }
         for k in ("e2e", "gpu_launches", "launches_per_step", "roofline", "roofline_hbm", "stages_ms",
                   "decoder_tflops", "decoder_frac_of_peak", "head_tflops", "clocks", "wall_s_timed_region", "mpjpe"):

@@ -71,3 +71,29 @@ def mpjpe_from_sums(sums):
     """(error_2d, error_3d) of models/metrics.py:90-95 from the global sums."""
     s = sums.detach().cpu().double()
     return float((s[0] / s[3] + s[1] / s[3]) / 2), float(s[2] / s[3])
+
+
+def bind_to_gpu_numa(local_rank):
+    """Pin the calling process to the CPUs NVML reports as local to GPU `local_rank` (its NUMA node), so the pinned
+    host buffers it allocates afterwards are first-touched next to the GPU's PCIe root port.  With one process per GPU
+    and no binding, half of the ranks of a two-socket box stream their H2D copies across the socket interconnect.
+    Returns the CPU list, or None if NVML / the affinity call is unavailable (then nothing changes)."""
+    import os
+    if os.environ.get("CDR_NO_NUMA_BIND") == "1":
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus or None
+    except Exception:
+        return None

@@ -75,3 +75,23 @@ def test_synth_is_deterministic():
     assert np.array_equal(synth.make_cameras(3, seed=2)["P_l"], synth.make_cameras(3, seed=2)["P_l"])
     s1, s2 = synth.make_head_state_dict(seed=0), synth.make_head_state_dict(seed=0)
     assert all(torch.equal(s1[k], s2[k]) for k in s1)
+
+
+def test_autograd_ops_refuse_cpu_tensors(pkg):
+    """SURVEY §8f rank 3 slice: the differentiable ops run on the library only — CPU tensors are an error, never a
+    silent torch fallback."""
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        pkg.soft_argmax_2d(torch.zeros(1, 2, 64, 64), 4.0)
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        pkg.dlt(torch.zeros(1, 3, 4), torch.zeros(1, 3, 4), torch.zeros(1, 2, 2), torch.zeros(1, 2, 2))
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        pkg.ftl(torch.zeros(1, 300, 8, 8), torch.zeros(1, 4, 3))
+
+
+def test_numa_binding_is_harmless(pkg):
+    import os
+    from fast_3d_human_pose_estimation_b200 import dist
+    before = os.sched_getaffinity(0)
+    cpus = dist.bind_to_gpu_numa(0)            # None without NVML / a GPU; a subset of the allowed CPUs otherwise
+    assert cpus is None or set(cpus) <= before
+    os.sched_setaffinity(0, before)
