@@ -71,16 +71,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples taken inside the host-time window [t0, t1] (the timed region); the process is
+        started before the warm-up so that it is already streaming when the region begins."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 is None or (t0 <= t <= t1 + 0.03)]
+        window = "timed region"
+        if not rows:                      # region shorter than one sampling period: nearest samples around it
+            rows = [r for t, r in self.rows if t0 - 0.1 <= t <= t1 + 0.1] or [r for _, r in self.rows[-3:]]
+            window = "nearest samples (region shorter than the sampling period)"
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
             except Exception:
@@ -88,11 +95,9 @@ class ClockSampler:
             for n, v in zip(names, r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        # under-load samples = upper half of the observed clocks
-        sm_sorted = sorted(sm)
-        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
-        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None,
+                "window": window, "period_ms": 20}
 
 
 def cpu_model():
@@ -186,21 +191,26 @@ def measure(args, precision, ctx):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(ctx["local"])
+    if rank == 0:
+        sampler.start()                 # already streaming when the timed region begins
     for _ in range(W):
         flush.fill_(1)
         out = step(feats, Ps)
     barrier()
 
+    if rank == 0 and sampler.proc is not None:      # nvidia-smi needs ~0.1 s to produce its first sample
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 1.0:
+            time.sleep(0.01)
+
     # ---- device-resident timing: K steps, L2 flushed between steps (outside the event pairs)
-    sampler = ClockSampler(ctx["local"])
-    if rank == 0:
-        sampler.start()
     L = _lib.lib()
     L.cdr_launch_count_reset()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     barrier()
-    t_wall = time.perf_counter()
+    t_wall = t_region0 = time.perf_counter()
     for i in range(K):
         flush.fill_(i & 0xff)
         starts[i].record()
@@ -210,7 +220,7 @@ def measure(args, precision, ctx):
     t_wall = time.perf_counter() - t_wall
     launches = L.cdr_launch_count()
     dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, t_region0 + t_wall) if rank == 0 else None
     xyz, sums = out
     e2d, e3d = cdist.mpjpe_from_sums(sums)
 
