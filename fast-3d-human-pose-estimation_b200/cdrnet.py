@@ -237,10 +237,12 @@ class CDRNet(nn.Module):
     Extra keyword ``precision`` ('fp32' parity kernels | 'bf16' tcgen05 kernels)."""
 
     def __init__(self, cfg, n_views=2, nj=19, fusion_in_dim=2048, fusion_hid_ch1=300,
-                 fusion_hid_ch2=400, precision="fp32", encoder_precision="torch"):
+                 fusion_hid_ch2=400, precision="fp32", encoder_precision="torch", trainable=False):
         """encoder_precision: 'torch' (default — the reference's nn.Module on torch/cuDNN, fp32) or
-        'bf16' (Bottleneck stages on libcdrhead's tcgen05 kernels, stem on cuDNN bf16)."""
+        'bf16' (Bottleneck stages on libcdrhead's tcgen05 kernels, stem on cuDNN bf16).
+        trainable: opt in to ``forward`` in training mode (``forward_train``, SURVEY §8f rank 3 slice)."""
         super().__init__()
+        self.trainable = bool(trainable)
         if encoder_precision not in ("torch", "bf16"):
             raise ValueError(f"encoder_precision must be 'torch' or 'bf16', got {encoder_precision!r}")
         self.encoder_precision = encoder_precision
@@ -342,6 +344,8 @@ class CDRNet(nn.Module):
     def forward(self, xs, proj_list):
         """xs: list[2] of (B,3,S,S) images; proj_list: list[2] of (B,3,4).
         Returns ([kp_left, kp_right] each (B,J,2) in image pixels, xyz (B,J,3))."""
+        if self.training and self.trainable:
+            return self.forward_train(xs, proj_list)
         _require_eval(self)
         img_size = int(xs[0].size(2))                             # models/cdrnet.py:229
         if self._tc_encoder is not None and xs[0].shape[-1] == 256 and xs[0].shape[-2] == 256:
@@ -352,6 +356,38 @@ class CDRNet(nn.Module):
             zs = [self.encoder(xs[i]) for i in range(self.n_views)]  # :231-234 (torch/cuDNN)
         return self.head(zs, proj_list, img_size=img_size)
 
+
+    def forward_train(self, xs, proj_list):
+        """The training-mode forward of train_cdr.py:105 (models/cdrnet.py:224-268 with autograd), SURVEY §8f rank 3
+        first slice — an explicit HYBRID, not a fallback of the inference path: the convolutions and train-mode
+        BatchNorm are this module's own torch children (cuDNN + torch autograd, like the encoder), while the three
+        operators the reference hand-rolls — ``ftl`` (:45-56), ``process_heatmap`` (:120-149) and ``dlt`` (:151-179)
+        — and the pseudo-inverse run forward AND backward in libcdrhead.so (autograd.py).  Needs
+        ``CDRNet(..., trainable=True)``; projection matrices get no gradient (data in the reference)."""
+        from .autograd import dlt, ftl, soft_argmax_2d
+        if not self.trainable:
+            raise RuntimeError("forward_train needs CDRNet(..., trainable=True)")
+        pl = _as_f32_cuda(proj_list[0], "proj_list")
+        pr = _as_f32_cuda(proj_list[1], "proj_list")
+        b = pl.shape[0]
+        img_size = int(xs[0].size(2))                                         # :229
+        pinv = torch.empty((2, b, 4, 3), dtype=torch.float32, device=pl.device)
+        with torch.cuda.device(pl.device):
+            st = _lib.current_stream_ptr(pl.device)
+            for v, p in enumerate((pl, pr)):                                  # :236-237
+                _lib.check(_lib.lib().cdr_pinv(_lib.ptr(p), b, PINV_RTOL_FP32, _lib.ptr(pinv[v]), st))
+        feats = [self.encoder(xs[v]) for v in range(2)]                       # :231-234
+        cf = self.CF
+        z = torch.cat([ftl(cf.conv_layer1(feats[v]), pinv[v]) for v in range(2)], dim=1)      # :62-70
+        f = cf.conv_layer2(z)                                                 # :74
+        projs = (pl, pr)
+        kps = []
+        for v in range(2):
+            o = cf.out_layer[v](ftl(f, projs[v]))                             # :79-81
+            d = self.decoder
+            h = d.final_layer(d.deconv3(d.deconv2(d.deconv1(o))))             # models/decoder.py:39-46
+            kps.append(soft_argmax_2d(h, img_size / h.shape[2]))              # :243-250
+        return kps, dlt(pl, pr, kps[0], kps[1])                               # :252-268
 
     def forward_frames(self, frames, proj_list, mean=None, std=None, img_size=None):
         """Device-side input pipeline: frames = [left, right] raw uint8 CUDA tensors

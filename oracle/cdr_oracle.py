@@ -104,8 +104,8 @@ def process_heatmap(heatmap):
     centre of mass, output order (x, y)."""
     b, j, h, w = heatmap.shape
     hm = F.softmax(heatmap.reshape(b, j, -1), dim=2).reshape(b, j, h, w)
-    x = torch.arange(w, dtype=heatmap.dtype)
-    y = torch.arange(h, dtype=heatmap.dtype)
+    x = torch.arange(w, dtype=heatmap.dtype, device=heatmap.device)
+    y = torch.arange(h, dtype=heatmap.dtype, device=heatmap.device)
     grid_x, grid_y = torch.meshgrid(x, y, indexing="xy")
     cx = torch.sum(grid_x * hm, dim=[2, 3])
     cy = torch.sum(grid_y * hm, dim=[2, 3])

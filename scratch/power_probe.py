@@ -8,22 +8,32 @@ from fast_3d_human_pose_estimation_b200 import synth
 prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
 dev = torch.device("cuda", 0)
 sd = synth.make_head_state_dict(seed=0, calibrated=True)
-m = pkg.CDRNet(synth.make_cfg(18, 19), precision=prec); m.load_state_dict(sd, strict=False); m = m.to(dev).eval()
+full = prec.startswith("full")
+if full:
+    prec = prec[5:] or "fp32"
+    torch.manual_seed(0)
+    m = pkg.CDRNet(synth.make_cfg(101, 19), precision=prec, encoder_precision="bf16")
+else:
+    m = pkg.CDRNet(synth.make_cfg(18, 19), precision=prec)
+m.load_state_dict(sd, strict=False); m = m.to(dev).eval()
 feats = [f.to(dev) for f in synth.make_features(64, seed=1)]
+if full:
+    frames = torch.randint(0, 256, (128, 256, 256, 3), dtype=torch.uint8, device=dev)
+step = (lambda: m.forward_frames(frames, Ps)) if full else (lambda: m.head(feats, Ps))
 cams = synth.make_cameras(64, seed=2)
 Ps = [torch.from_numpy(cams["P_l"]).to(dev), torch.from_numpy(cams["P_r"]).to(dev)]
 Q = "clocks.sm,clocks.mem,power.draw,power.limit,temperature.gpu,clocks_event_reasons.sw_power_cap,clocks_event_reasons.hw_slowdown,clocks_event_reasons.sw_thermal_slowdown"
 rows = []
 proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", "0"], stdout=subprocess.PIPE, text=True)
 threading.Thread(target=lambda: [rows.append((time.perf_counter(), l.strip())) for l in proc.stdout], daemon=True).start()
-for _ in range(5): m.head(feats, Ps)
+for _ in range(5): step()
 torch.cuda.synchronize(); time.sleep(0.5)
 t0 = time.perf_counter()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 n = 0
 a.record()
 while time.perf_counter() - t0 < 3.0:
-    for _ in range(50): m.head(feats, Ps)
+    for _ in range(50): step()
     n += 50
 b.record(); torch.cuda.synchronize()
 t1 = time.perf_counter()

@@ -118,3 +118,80 @@ def test_differentiable_tail_end_to_end(cuda_pkg):
     assert abs(loss.item() - l64.item()) < 1e-2 * max(1.0, l64.item())
     for got, want in ((hld.grad, hl64.grad), (hrd.grad, hr64.grad)):
         assert _rel(got.cpu().double(), want) < 5e-3          # fp32 2D joints feed an ill-conditioned-at-times DLT
+
+
+def test_forward_train_hybrid_matches_pure_torch_fp64(cuda_pkg):
+    """CDRNet(trainable=True).train()(imgs, Ps): torch convs / train-mode BN + this library's ftl / soft-argmax / dlt
+    (forward and backward) against the same modules in fp64 with the oracle's pure-torch operators."""
+    import copy
+    torch.manual_seed(0)
+    b = 2
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False     # fp32 convs vs the fp64 copy
+    try:
+        _forward_train_case(cuda_pkg, copy, b)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+def _forward_train_case(cuda_pkg, copy, b):
+    m = cuda_pkg.CDRNet(synth.make_cfg(50, 19), trainable=True)
+    with torch.no_grad():
+        m.decoder.final_layer.weight.mul_(10.0)      # train-mode BN keeps activations O(1): peaky heat-maps need gain
+    m = m.cuda().train()
+    m64 = copy.deepcopy(m).double()
+    imgs = [x.cuda() for x in synth.make_images(b, seed=1)]
+    cams = synth.make_cameras(b, seed=2)
+    gt = synth.make_gt(cams, seed=3)
+    Ps = [torch.from_numpy(cams["P_l"]).cuda(), torch.from_numpy(cams["P_r"]).cuda()]
+    g2 = [torch.from_numpy(gt["gt2d_l"]).cuda(), torch.from_numpy(gt["gt2d_r"]).cuda()]
+
+    def pure_torch(mod, xs, projs):                      # models/cdrnet.py:224-268, operators from the oracle
+        pinv = [torch.linalg.pinv(p) for p in projs]
+        feats = [mod.encoder(x) for x in xs]
+        z = torch.cat([O.ftl(mod.CF.conv_layer1(feats[v]), pinv[v]) for v in range(2)], 1)
+        f = mod.CF.conv_layer2(z)
+        kps = []
+        for v in range(2):
+            o = mod.CF.out_layer[v](O.ftl(f, projs[v]))
+            d = mod.decoder
+            h = d.final_layer(d.deconv3(d.deconv2(d.deconv1(o))))
+            kps.append(O.process_heatmap(h) * (256 / h.shape[2]))
+        return kps
+
+    kps, xyz = m(imgs, Ps)
+    assert xyz.shape == (b, 19, 3) and xyz.requires_grad and bool(torch.isfinite(xyz).all())
+    loss = sum(((kps[v] - g2[v].float()) ** 2).mean() for v in range(2))
+    loss.backward(retain_graph=True)
+    names = ("decoder.final_layer.weight", "decoder.deconv1.0.weight", "CF.conv_layer2.3.weight",
+             "CF.conv_layer1.0.weight", "CF.out_layer.1.0.weight", "encoder.layer4.2.conv3.weight")
+    ours = {n: dict(m.named_parameters())[n].grad.detach().clone() for n in names}
+    # forward against the fp64 copy of the network with the oracle's operators
+    with torch.no_grad():
+        kps64 = pure_torch(m64, [x.double() for x in imgs], [p.double() for p in Ps])
+    loss64 = sum(((kps64[v] - g2[v]) ** 2).mean() for v in range(2))
+    for v in range(2):
+        assert float((kps[v].detach().double() - kps64[v]).abs().max()) < 0.2           # px: a whole fp32 ResNet-50 + head vs fp64
+    assert abs(loss.item() - loss64.item()) < 1e-2 * loss64.item()
+    # gradients against the SAME fp32 modules with the oracle's pure-torch operators (an fp64 network takes other
+    # ReLU branches near zero, which is not what this test is about)
+    m.zero_grad()
+    kps_t = pure_torch(m, imgs, Ps)
+    loss_t = sum(((kps_t[v] - g2[v].float()) ** 2).mean() for v in range(2))
+    loss_t.backward()
+    assert abs(loss.item() - loss_t.item()) < 1e-3 * abs(loss_t.item())
+    report = {}
+    for n in names:
+        a, g_t = ours[n].double().flatten(), dict(m.named_parameters())[n].grad.double().flatten()
+        report[n] = (float(torch.dot(a, g_t) / (a.norm() * g_t.norm())), float(a.norm() / g_t.norm()), _rel(a, g_t))
+    print("\nforward_train gradients vs pure torch (cosine, norm ratio, max rel):", report)
+    for n, (cos, ratio, _) in report.items():       # direction and size: train-mode BN backward cancels heavily, so
+        assert cos > 0.995 and abs(ratio - 1) < 0.05, (n, report[n])    # element-wise ulps are not the criterion
+    # the 3D branch reaches the parameters too (its operator-level gradient is checked above)
+    m.zero_grad()
+    xyz.abs().mean().backward()
+    g = m.CF.conv_layer1[0].weight.grad
+    assert g is not None and bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0
+    # and the opt-in is required
+    with pytest.raises(RuntimeError, match="inference-only"):
+        cuda_pkg.CDRNet(synth.make_cfg(50, 19)).cuda().train()(imgs, Ps)
