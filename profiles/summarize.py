@@ -125,6 +125,12 @@ def traffic(rnd):
                              to_bytes(l["dram__bytes_read.sum"], u["dram__bytes_read.sum"]) +
                              to_bytes(l["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
                              for i, l in enumerate(d["launches"][:2])}
+    path = os.path.join(ROOT, "profiles", f"{rnd}_prof_bwd_raw.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        u, l = d["units"], d["launches"][0]
+        out["softargmax_backward_stream"] = to_bytes(l["dram__bytes_read.sum"], u["dram__bytes_read.sum"]) + \
+            to_bytes(l["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
     out["source"] = f"ncu --set full --clock-control none, profiles/{rnd}_prof_*_raw.json (B=64 head; 8192-pose stream)"
     json.dump(out, open(os.path.join(ROOT, "profiles", f"{rnd}_traffic.json"), "w"), indent=1)
     print("wrote", f"profiles/{rnd}_traffic.json", out)
@@ -134,6 +140,6 @@ if __name__ == "__main__":
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
     for tag in ("bf16", "fp32"):
         launches(tag, rnd)
-    for rep in ("prof_tc", "prof_f16x2", "prof_tf32", "prof_ffma", "prof_heat", "prof_ftl"):
+    for rep in ("prof_tc", "prof_f16x2", "prof_tf32", "prof_ffma", "prof_heat", "prof_ftl", "prof_bwd"):
         full(rep, rnd)
     traffic(rnd)
