@@ -95,3 +95,28 @@ def test_numa_binding_is_harmless(pkg):
     cpus = dist.bind_to_gpu_numa(0)            # None without NVML / a GPU; a subset of the allowed CPUs otherwise
     assert cpus is None or set(cpus) <= before
     os.sched_setaffinity(0, before)
+
+
+def test_checkpoint_contract_matches_reference_exactly(pkg, tmp_path):
+    """SURVEY §8f rank 4 (checkpoint I/O): `inference.py:31-33` loads `best.pth` with a strict
+    `load_state_dict`, `train_cdr.py:223-232` saves `model.state_dict()`.  The drop-in modules expose the
+    reference's keys, shapes and dtypes in the reference's order (fixture generated from the reference by
+    tests/golden/make_state_dict_keys.py), and a saved checkpoint round-trips."""
+    import json
+    import os
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_state_dict_keys.json")))
+
+    def describe(m):
+        return [[k, list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in m.state_dict().items()]
+    assert describe(pkg.CDRNet(synth.make_cfg(50, 19))) == want["CDRNet50"]
+    m = pkg.CDRNet(synth.make_cfg(101, 19))
+    assert describe(m) == want["CDRNet101"]
+    assert describe(pkg.PoseResNet(synth.make_cfg(101, 16))) == want["PoseResNet101_j16"]
+    # a reference-format checkpoint (plain state_dict, as train_cdr.py writes it) loads strictly, also into the
+    # variants with extra constructor keywords
+    path = tmp_path / "best.pth"
+    torch.save(m.state_dict(), path)
+    for kw in ({}, {"precision": "bf16"}, {"encoder_precision": "bf16"}, {"trainable": True}):
+        m2 = pkg.CDRNet(synth.make_cfg(101, 19), **kw)
+        m2.load_state_dict(torch.load(path), strict=True)
+        assert torch.equal(m2.state_dict()["CF.out_layer.1.0.weight"], m.state_dict()["CF.out_layer.1.0.weight"])
