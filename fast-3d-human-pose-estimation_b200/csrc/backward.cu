@@ -90,57 +90,10 @@ __global__ void dlt_backward_kernel(const float* __restrict__ P_l, const float* 
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long b = i / joints;
-  const float* Pl = P_l + b * 12;
-  const float* Pr = P_r + b * 12;
-  double G[4][4], V[4][4];
-  dlt_rows(Pl, (double)kp_l[i * 2], (double)kp_l[i * 2 + 1], G, 0);
-  dlt_rows(Pr, (double)kp_r[i * 2], (double)kp_r[i * 2 + 1], G, 2);
-  jacobi_onesided<4, 4>(G, V);                     // G = A V: column c = sigma_c u_c = A v_c
-  double s2[4], best = INFINITY;
-  int k = 0;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    s2[c] = 0.0;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) s2[c] = fma(G[r][c], G[r][c], s2[c]);
-    if (s2[c] < best) { best = s2[c]; k = c; }
-  }
-  double v[4] = {0, 0, 0, 0}, Av[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int c = 0; c < 4; ++c)
-    if (c == k) {
-#pragma unroll
-      for (int r = 0; r < 4; ++r) { v[r] = V[r][c]; Av[r] = G[r][c]; }
-    }
-  // X = v[:3] / v[3]
-  const double gX0 = grad_xyz[i * 3], gX1 = grad_xyz[i * 3 + 1], gX2 = grad_xyz[i * 3 + 2];
-  const double iw = 1.0 / v[3];
-  const double gv[4] = {gX0 * iw, gX1 * iw, gX2 * iw, -(gX0 * v[0] + gX1 * v[1] + gX2 * v[2]) * iw * iw};
-  // w = -(M - s_k^2 I)^+ g_v = sum_{c != k} coef_c v_c,  A w = sum coef_c G[:,c]
-  double w[4] = {0, 0, 0, 0}, Aw[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (c == k) continue;
-    double dot = 0.0;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) dot = fma(V[r][c], gv[r], dot);
-    const double coef = -dot / (s2[c] - best);
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      w[r] = fma(coef, V[r][c], w[r]);
-      Aw[r] = fma(coef, G[r][c], Aw[r]);
-    }
-  }
-  // dL/dA[r][c] = Av[r] w[c] + Aw[r] v[c];  dA[row]/d(coordinate) = P_view[2][:]
+  const double gX[3] = {(double)grad_xyz[i * 3], (double)grad_xyz[i * 3 + 1], (double)grad_xyz[i * 3 + 2]};
   double gl[4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const float* P2 = (r < 2 ? Pl : Pr) + 8;
-    double acc = 0.0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc = fma(Av[r] * w[c] + Aw[r] * v[c], (double)P2[c], acc);
-    gl[r] = acc;
-  }
+  dlt_backward4(P_l + b * 12, P_r + b * 12, (double)kp_l[i * 2], (double)kp_l[i * 2 + 1], (double)kp_r[i * 2],
+                (double)kp_r[i * 2 + 1], gX, gl);     // jacobi.cuh (also exercised on the host: tests/test_host_math.py)
   grad_kp_l[i * 2] = (float)gl[0];
   grad_kp_l[i * 2 + 1] = (float)gl[1];
   grad_kp_r[i * 2] = (float)gl[2];

@@ -106,6 +106,61 @@ __host__ __device__ __forceinline__ void dlt_rows(const TP* __restrict__ P, doub
   }
 }
 
+// Backward of the two-view DLT (models/cdrnet.py:151-179) for one joint: given dL/dX for X = v[:3] / v[3], v the
+// right singular vector of the smallest singular value of A(u_l, v_l, u_r, v_r), returns dL/d(u_l, v_l, u_r, v_r).
+// With M = A^T A: dv = -(M - s^2 I)^+ dM v (the gauge of torch.svd's backward; X does not see the sign of v), so
+// for w = -(M - s^2 I)^+ g_v:  dL/dA = (A v) w^T + (A w) v^T, and dA[row]/d(coordinate) is the row P_view[2].
+// The one-sided Jacobi yields G = A V (columns sigma_c u_c) and V at once.
+template <typename TP>
+__host__ __device__ __forceinline__ void dlt_backward4(const TP* __restrict__ Pl, const TP* __restrict__ Pr, double ul,
+                                                       double vl, double ur, double vr, const double (&gX)[3],
+                                                       double (&g_kp)[4]) {
+  double G[4][4], V[4][4];
+  dlt_rows(Pl, ul, vl, G, 0);
+  dlt_rows(Pr, ur, vr, G, 2);
+  jacobi_onesided<4, 4>(G, V);
+  double s2[4], best = INFINITY;
+  int k = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    s2[c] = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s2[c] = fma(G[r][c], G[r][c], s2[c]);
+    if (s2[c] < best) { best = s2[c]; k = c; }
+  }
+  double v[4] = {0, 0, 0, 0}, Av[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    if (c == k) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { v[r] = V[r][c]; Av[r] = G[r][c]; }
+    }
+  const double iw = 1.0 / v[3];
+  const double gv[4] = {gX[0] * iw, gX[1] * iw, gX[2] * iw, -(gX[0] * v[0] + gX[1] * v[1] + gX[2] * v[2]) * iw * iw};
+  double w[4] = {0, 0, 0, 0}, Aw[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c == k) continue;
+    double dot = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) dot = fma(V[r][c], gv[r], dot);
+    const double coef = -dot / (s2[c] - best);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      w[r] = fma(coef, V[r][c], w[r]);
+      Aw[r] = fma(coef, G[r][c], Aw[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const TP* P2 = (r < 2 ? Pl : Pr) + 8;
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc = fma(Av[r] * w[c] + Aw[r] * v[c], (double)P2[c], acc);
+    g_kp[r] = acc;
+  }
+}
+
 // Moore-Penrose pseudo-inverse of a row-major 3x4 matrix with torch.linalg.pinv's
 // semantics (models/cdrnet.py:236-237): singular values <= rtol*sigma_max are dropped.
 // Works on G = P^T (4x3): G V = U Sigma, so pinv(P) = sum_i G_i V_i^T / sigma_i^2 (4x3).

@@ -1,5 +1,5 @@
 // Host harness for the __host__ __device__ math in csrc/jacobi.cuh (tests/test_host_math.py).
-// stdin-free: argv[1] = mode (dlt|pinv|tri), argv[2] = input file, argv[3] = output file.
+// stdin-free: argv[1] = mode (dlt|dltbwd|pinv), argv[2] = input file, argv[3] = output file.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -23,6 +23,18 @@ int main(int argc, char** argv) {
       cdr::dlt_rows(p, (double)p[24], (double)p[25], A, 0);
       cdr::dlt_rows(p + 12, (double)p[26], (double)p[27], A, 2);
       cdr::dlt_solve4(A, out[i * 3], out[i * 3 + 1], out[i * 3 + 2]);
+    }
+    fwrite(out.data(), 8, out.size(), o);
+  } else if (!strcmp(argv[1], "dltbwd")) {   // per item: P_l[12] P_r[12] kp[4] grad_xyz[3] float -> grad_kp[4] double
+    std::vector<float> in(n * 31);
+    if (fread(in.data(), 4, in.size(), f) != in.size()) return 5;
+    std::vector<double> out(n * 4);
+    for (long long i = 0; i < n; ++i) {
+      const float* p = &in[i * 31];
+      const double gX[3] = {p[28], p[29], p[30]};
+      double g[4];
+      cdr::dlt_backward4(p, p + 12, (double)p[24], (double)p[25], (double)p[26], (double)p[27], gX, g);
+      for (int c = 0; c < 4; ++c) out[i * 4 + c] = g[c];
     }
     fwrite(out.data(), 8, out.size(), o);
   } else if (!strcmp(argv[1], "pinv")) {   // per item: P[12] float ; rtol double first

@@ -77,3 +77,27 @@ def test_pinv_rank_deficient_cutoff(harness, tmp_path):
     want = torch.linalg.pinv(torch.from_numpy(P[0]).double(), rtol=rtol).numpy()
     np.testing.assert_allclose(got, want, atol=1e-9)
     assert got[2, 2] == 0.0
+
+
+@pytest.mark.parametrize("rig", ["wide", "narrow"])
+def test_dlt_backward_matches_autograd(harness, tmp_path, rig):
+    """cdr::dlt_backward4 (csrc/jacobi.cuh, the body of cdr_dlt_backward's kernel) compiled for the host against
+    torch autograd through the oracle's svd-based dlt in fp64 — SURVEY §8f rank 3 slice."""
+    b, j = 8, 19
+    cams = synth.make_cameras(b, seed=41, rig=rig)
+    gt = synth.make_gt(cams, seed=42)
+    rng = np.random.default_rng(43)
+    kp_l = (gt["gt2d_l"] + rng.normal(scale=1.5, size=(b, j, 2))).astype(np.float32)
+    kp_r = (gt["gt2d_r"] + rng.normal(scale=1.5, size=(b, j, 2))).astype(np.float32)
+    gx = rng.normal(size=(b, j, 3)).astype(np.float32)
+    items = np.concatenate([np.repeat(cams["P_l"].reshape(b, 1, 12), j, 1),
+                            np.repeat(cams["P_r"].reshape(b, 1, 12), j, 1), kp_l, kp_r, gx], axis=2)
+    payload = struct.pack("q", b * j) + items.astype(np.float32).tobytes()
+    got = _run(harness, "dltbwd", payload, tmp_path, np.float64, b * j * 4).reshape(b, j, 4)
+    kl = torch.from_numpy(kp_l).double().requires_grad_(True)
+    kr = torch.from_numpy(kp_r).double().requires_grad_(True)
+    projs = torch.stack([torch.from_numpy(cams["P_l"]).double(), torch.from_numpy(cams["P_r"]).double()], 1)
+    x = torch.stack([O.dlt(projs, torch.stack([kl[:, k], kr[:, k]], 1)) for k in range(j)], 1)
+    (x * torch.from_numpy(gx).double()).sum().backward()
+    want = torch.cat([kl.grad, kr.grad], -1).numpy()
+    assert np.abs(got - want).max() <= 1e-7 * np.abs(want).max()
