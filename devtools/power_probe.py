@@ -1,5 +1,5 @@
 """Clocks / power / throttle reasons while the head runs back to back for a few seconds (is the
-tensor-core rate power-limited?).  Usage: python scratch/power_probe.py [fp32|bf16]"""
+tensor-core rate power-limited?).  Usage: python devtools/power_probe.py [fp32|bf16]"""
 import subprocess, sys, threading, time
 import numpy as np, torch
 sys.path.insert(0, '.')

@@ -30,6 +30,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from . import workspace as _wsmod
 from .encoder import ResNet, TcEncoder
 
 PINV_RTOL_FP32 = 4 * float(torch.finfo(torch.float32).eps)  # torch.linalg.pinv default, (3,4) fp32
@@ -133,17 +134,10 @@ def _as_f32_cuda(t, what):
     return t.detach().to(torch.float32).contiguous()
 
 
-_WS = {}
-
-
-def _workspace(device, nbytes):
-    """One growing scratch buffer per device (torch-owned; the library never allocates
-    caller-visible memory).  256-byte aligned by the caching allocator."""
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
-    buf = _WS.get(key)
-    if buf is None or buf.numel() < nbytes:
-        _WS[key] = buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
-    return buf
+def _workspace(device, nbytes, slot="head"):
+    """Scratch for one forward (torch-owned; the library never allocates caller-visible memory): the buffer of
+    the current (device, stream), or of the enclosing graph/pipeline (workspace.py)."""
+    return _wsmod.current(device).get(slot, device, nbytes)
 
 
 def _convbn(conv, bn):
@@ -163,33 +157,70 @@ def _decoder_tensors(dec, _prefix):
 
 
 class _PackedWeights:
-    """Owns the CdrWeights handle of one module and re-packs it when parameters change."""
+    """Owns the CdrWeights handle of one module and re-packs it when parameters change.
+
+    The handle lives in a reference-counted ``HandleBox``: captured CUDA graphs ``retain()`` it, so a re-pack
+    (load_state_dict, optimizer step, ``.to()``) after a capture cannot free the pool the graph's kernels read —
+    the graph holder notices the changed signature at its next replay and refuses to run on stale weights."""
+
+    BN_EPS = 1e-5            # folded by the packing kernels (csrc/pack.cu, gemm_tc.cu)
 
     def __init__(self, owner, precision, has_fusion):
         if precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
         self.precision = precision
         self.has_fusion = has_fusion
-        self._handle = None
+        self._box = None
         self._sig = None
+        self._last = None          # (modules, device, cf) of the last get(): lets signature_now() recompute
 
-    def _signature(self, tensors, device):
-        return (str(device), self.precision) + tuple((t.data_ptr(), t._version) for t in tensors)
+    @property
+    def _handle(self):
+        return self._box.handle if self._box is not None else None
 
-    def get(self, modules, device, cf=None):
-        dec = modules
+    def _collect(self, dec, device, cf):
         params = []
         mods = ([cf.conv_layer1, cf.conv_layer2, cf.out_layer[0], cf.out_layer[1]] if cf is not None
                 else []) + list(dec)
         for m in mods:
             params += list(m.parameters()) + list(m.buffers())
+        return mods, params
+
+    def _signature(self, tensors, device):
+        return (str(device), self.precision) + tuple((t.data_ptr(), t._version) for t in tensors)
+
+    def signature_now(self):
+        """Signature of the parameters as they are now (None before the first get())."""
+        if self._last is None:
+            return None
+        dec, device, cf = self._last
+        return self._signature(self._collect(dec, device, cf)[1], device)
+
+    def retain(self):
+        """(box, signature) of the current handle for a graph holder; the box must be release()d."""
+        if self._box is None:
+            raise RuntimeError("nothing packed yet: run one forward before capturing")
+        return self._box.retain(), self._sig
+
+    def get(self, modules, device, cf=None):
+        dec = modules
+        mods, params = self._collect(dec, device, cf)
         for t in params:
             if t.is_floating_point() and (t.dtype != torch.float32 or t.device != device):
                 raise RuntimeError("head parameters must be float32 on the input's device "
                                    f"(found {t.dtype} on {t.device}, input on {device})")
         sig = self._signature(params, device)
-        if self._handle is not None and sig == self._sig:
-            return self._handle
+        self._last = (dec, device, cf)
+        if self._box is not None and sig == self._sig:
+            return self._box.handle
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("head parameters changed (or were never packed) while a CUDA graph is being captured: "
+                               "packing allocates and synchronises; run one eager forward first")
+        for m in mods:
+            for sub in m.modules():
+                if isinstance(sub, nn.BatchNorm2d) and abs(sub.eps - self.BN_EPS) > 1e-12:
+                    raise ValueError(f"BatchNorm eps={sub.eps}: the packing kernels fold the default eps "
+                                     f"{self.BN_EPS} (models/cdrnet.py:19, models/decoder.py:34)")
         self.release()
         src = _lib.CdrWeightPtrs()
         src.num_joints = dec[3].out_channels
@@ -208,13 +239,14 @@ class _PackedWeights:
             _lib.check(_lib.lib().cdr_weights_create(
                 C.byref(src), _lib.PRECISIONS[self.precision], _lib.current_stream_ptr(device),
                 C.byref(handle)))
-        self._handle, self._sig = handle, sig
+        self._box = _wsmod.HandleBox(handle, lambda h: _lib.lib().cdr_weights_destroy(h))
+        self._sig = sig
         return handle
 
     def release(self):
-        if self._handle is not None:
-            _lib.lib().cdr_weights_destroy(self._handle)
-            self._handle = None
+        if self._box is not None:
+            self._box.release()          # destroyed now unless a captured graph still holds it
+            self._box = None
             self._sig = None
 
     def __deepcopy__(self, memo):
@@ -222,7 +254,7 @@ class _PackedWeights:
 
     def __getstate__(self):
         return {"precision": self.precision, "has_fusion": self.has_fusion,
-                "_handle": None, "_sig": None}
+                "_box": None, "_sig": None, "_last": None}
 
     def __del__(self):
         try:
@@ -234,7 +266,9 @@ class _PackedWeights:
 class CDRNet(nn.Module):
     """Reference models/cdrnet.py:88-268 with the post-encoder path on libcdrhead.so.
 
-    Extra keyword ``precision`` ('fp32' parity kernels | 'bf16' tcgen05 kernels)."""
+    Extra keyword ``precision``: 'fp32' (default) = fp32-accurate results on the tcgen05 tensor cores — decoder and
+    conv_layer1 on scaled fp16 two-term operands (f16x2), the rest of the fusion block on 3xTF32; 'tf32x3' = 3xTF32
+    everywhere; 'fp32_ffma' = the same arithmetic on CUDA cores (cross-check); 'bf16' = bf16 operands on tcgen05."""
 
     def __init__(self, cfg, n_views=2, nj=19, fusion_in_dim=2048, fusion_hid_ch1=300,
                  fusion_hid_ch2=400, precision="fp32", encoder_precision="torch", trainable=False):
@@ -398,7 +432,8 @@ class CDRNet(nn.Module):
         if self._tc_encoder is None:
             raise RuntimeError("forward_frames needs CDRNet(..., encoder_precision='bf16')")
         x = frames if isinstance(frames, torch.Tensor) else torch.cat([frames[0], frames[1]], 0)
-        rows, _ = self._tc_encoder.rows(x, mean=mean or IMAGENET_MEAN, std=std or IMAGENET_STD)
+        rows, _ = self._tc_encoder.rows(x, mean=IMAGENET_MEAN if mean is None else tuple(float(v) for v in mean),
+                                        std=IMAGENET_STD if std is None else tuple(float(v) for v in std))
         return self.head(None, proj_list, img_size=int(img_size or x.shape[1]), feat_rows=rows)
 
 

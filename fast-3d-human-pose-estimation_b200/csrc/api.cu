@@ -167,6 +167,7 @@ extern "C" int cdr_weights_create(const CdrWeightPtrs* src, int precision, void*
   int rc = CDR_OK;
   auto fail = [&](int code) {
     if (w->pool) cudaFree(w->pool);
+    tc_weights_destroy(w->tc);          // frees the TcPack and its device pool if packing got that far (no-op otherwise)
     delete w;
     return code;
   };
@@ -203,7 +204,6 @@ extern "C" int cdr_weights_create(const CdrWeightPtrs* src, int precision, void*
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {
     set_error("cdr_weights_create: packing failed: %s", cudaGetErrorString(e));
-    if (precision != CDR_PREC_FP32) tc_weights_destroy(w->tc);
     return fail(CDR_ERR_CUDA);
   }
   *out = w;

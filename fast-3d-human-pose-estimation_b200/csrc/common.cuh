@@ -46,16 +46,31 @@ void timing_restart();
     cdr::count_launch(name);                                                        \
   } while (0)
 
-inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  }
-  return n;
+// Per-device caches: a process may drive several GPUs (the Python shim wraps every call in
+// torch.cuda.device(dev)), and both the SM count and a kernel's opt-in to > 48 KB of dynamic shared
+// memory (cudaFuncSetAttribute) belong to the CURRENT device, not to the process.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return dev;
 }
+inline int num_sms() {
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
+  }
+  return n[dev];
+}
+// one flag word per kernel instantiation (a function-local static at the call site), one bit per device
+struct DeviceOnce {
+  unsigned long long mask = 0;
+  bool need() const { return !((mask >> current_device()) & 1ull); }
+  void done() { mask |= 1ull << current_device(); }
+};
 
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }

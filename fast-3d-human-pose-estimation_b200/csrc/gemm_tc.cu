@@ -890,11 +890,11 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
   constexpr int kElem = KindTraits<KIND>::kElem;
   constexpr int kBK = Cfg::kBK;
   constexpr int kAFmt = KindTraits<KIND>::kFmt;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;   // per instantiation AND per device
+  if (attr_set.need()) {
     CDR_CUDA(cudaFuncSetAttribute(tap_gemm_tc_kernel<BN, KIND, OFMT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)Cfg::kSmemBytes));
-    attr_set = true;
+    attr_set.done();
   }
   TcGemmParams p{};
   const int HW = l.H * l.W;

@@ -397,11 +397,11 @@ static int heat_warps() {
 template <typename T, bool kArgmax, int NW>
 static int launch_heat_nw(const HeatParams& p, cudaStream_t st) {
   const size_t smem = sizeof(HeatSmem<NW>) + 128;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  static DeviceOnce attr_set;  // per instantiation AND per device
+  if (attr_set.need()) {
     CDR_CUDA(cudaFuncSetAttribute(heat_stream_kernel<T, kArgmax, NW>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set.done();
   }
   long long grid = p.batch < num_sms() ? p.batch : num_sms();
   heat_stream_kernel<T, kArgmax, NW><<<(unsigned)grid, 32 * (NW + 2), smem, st>>>(p);

@@ -104,9 +104,29 @@ class TcEncoder:
         if any(b.kind != "bottleneck" for b in blocks):
             raise NotImplementedError("the tcgen05 encoder covers the Bottleneck ResNets (50/101/152)")
         self.resnet, self.blocks = resnet, blocks
-        self._handle, self._key, self._stem = None, None, None
-        self._ws = {}
+        self._box, self._key, self._stem = None, None, None
         self.torch_stem = False          # True: force the cuDNN stem (A/B timing)
+
+    @property
+    def _handle(self):
+        return self._box.handle if self._box is not None else None
+
+    def retain(self):
+        """(box, key) of the packed encoder for a captured graph (workspace.HandleBox)."""
+        if self._box is None:
+            raise RuntimeError("nothing packed yet: run one forward before capturing")
+        return self._box.retain(), self._key
+
+    def key_now(self, device):
+        return (str(device),) + tuple((t.data_ptr(), t._version) for t in self._tensors())
+
+    def __deepcopy__(self, memo):
+        import copy
+        return TcEncoder(copy.deepcopy(self.resnet, memo))     # device handles are never shared or copied
+
+    def __getstate__(self):
+        return {"resnet": self.resnet, "blocks": self.blocks, "_box": None, "_key": None, "_stem": None,
+                "torch_stem": self.torch_stem}
 
     def _tensors(self):
         r = self.resnet
@@ -120,11 +140,16 @@ class TcEncoder:
         return ts
 
     def _pack(self, device):
-        from . import _lib
-        ts = self._tensors()
-        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in ts)
+        from . import _lib, workspace as _wsmod
+        key = self.key_now(device)
         if key == self._key:
-            return self._handle
+            return self._box.handle
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("encoder parameters changed (or were never packed) during a CUDA-graph capture")
+        r = self.resnet
+        for bn in [r.bn1] + [m for b in self.blocks for m in b.modules() if isinstance(m, nn.BatchNorm2d)]:
+            if abs(bn.eps - 1e-5) > 1e-12:
+                raise ValueError(f"BatchNorm eps={bn.eps}: the packing kernels fold the default 1e-5")
         self.release()
         L = _lib.lib()
         keep = []
@@ -154,14 +179,13 @@ class TcEncoder:
         w = (r.conv1.weight.double() * sc.reshape(-1, 1, 1, 1)).to(device=device, dtype=torch.bfloat16)
         bias = (r.bn1.bias.double() - r.bn1.running_mean.double() * sc).to(device=device, dtype=torch.bfloat16)
         self._stem = (w.contiguous(memory_format=torch.channels_last), bias)
-        self._handle, self._key = handle, key
+        self._box, self._key = _wsmod.HandleBox(handle, lambda h: _lib.lib().cdr_encoder_destroy(h)), key
         return handle
 
     def release(self):
-        if self._handle is not None:
-            from . import _lib
-            _lib.lib().cdr_encoder_destroy(self._handle)
-        self._handle, self._key = None, None
+        if self._box is not None:
+            self._box.release()          # destroyed now unless a captured graph still holds it
+        self._box, self._key = None, None
 
     def __del__(self):
         try:
@@ -182,7 +206,7 @@ class TcEncoder:
         """x: (n,3,S,S) float CUDA images as the reference feeds its model, or raw (n,S,S,3) uint8 CUDA
         frames, normalised on the fly with torchvision's ToTensor + Normalize(mean, std)
         (inference.py:40-44).  -> (rows (n*h*w, C) bf16, (h, w, C))."""
-        from . import _lib
+        from . import _lib, workspace as _wsmod
         if not x.is_cuda:
             raise RuntimeError("the tcgen05 encoder has no CPU path")
         if self.resnet.training:
@@ -216,11 +240,7 @@ class TcEncoder:
             _lib.check(L.cdr_encoder_workspace_bytes_images(handle, n, H, W, C.byref(nbytes)))
         else:
             _lib.check(L.cdr_encoder_workspace_bytes(handle, n, h, w, C.byref(nbytes)))
-        key = (str(dev), nbytes.value)
-        ws = self._ws.get(key)
-        if ws is None:
-            self._ws.clear()
-            ws = self._ws[key] = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
+        ws = _wsmod.current(dev).get("encoder", dev, nbytes.value)     # per stream, or the enclosing pipeline's own
         if out is None:
             out = torch.empty((n * oh.value * ow.value, oc.value), dtype=torch.bfloat16, device=dev)
         st = _lib.current_stream_ptr(dev)

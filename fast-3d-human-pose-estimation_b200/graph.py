@@ -14,11 +14,48 @@ from __future__ import annotations
 
 import torch
 
-from . import cdrnet as _cdrnet
+from . import workspace as _wsmod
 from .metrics import mpjpe_sums
 
 
-class HeadGraph:
+class _GraphHolder:
+    """What every captured pipeline shares: a PRIVATE workspace — the scratch pointers baked into the
+    graph belong to nobody else, whatever stream replays it — and a reference on the packed weights (and packed
+    encoder) it was captured with, so a later re-pack cannot free them under the graph.  ``_check_weights`` runs
+    before every replay: parameters changed since the capture -> RuntimeError instead of stale results."""
+
+    def _init_holder(self):
+        self._ws = _wsmod.Workspace()
+        self._held = []            # [(owner, box, signature, signature_fn)]
+
+    def _hold_weights(self, model, with_encoder=False):
+        box, sig = model._packed.retain()
+        self._held.append((box, sig, model._packed.signature_now))
+        if with_encoder:
+            enc = model._tc_encoder
+            box, key = enc.retain()
+            self._held.append((box, key, lambda enc=enc, dev=self.dev: enc.key_now(dev)))
+
+    def _check_weights(self):
+        for _, sig, now in self._held:
+            if now() != sig:
+                raise RuntimeError(f"{type(self).__name__}: model parameters changed after the CUDA graph was captured "
+                                   "(load_state_dict / .to() / in-place update); build a new pipeline")
+
+    def close(self):
+        """Drop the graph's references (packed weights are destroyed once their module re-packed or died too)."""
+        held, self._held = getattr(self, "_held", []), []
+        for box, _, _ in held:
+            box.release()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HeadGraph(_GraphHolder):
     def __init__(self, model, feats_host, P_host, gt=None, img_size=256, warmup=2, chunks=None):
         """feats_host: list[2] of pinned (B,2048,8,8) fp32; P_host: list[2] of pinned (B,3,4) fp32;
         gt: optional dict of DEVICE tensors gt3d/gt2d_l/gt2d_r/vis for fused MPJPE sums.
@@ -43,19 +80,18 @@ class HeadGraph:
         self.sums_host = torch.empty(4, dtype=torch.float64).pin_memory() if gt is not None else None
         self.xyz_dev = torch.empty((b, j, 3), dtype=torch.float32, device=self.dev)
         self.sums_dev = torch.zeros(4, dtype=torch.float64, device=self.dev) if gt is not None else None
+        self._init_holder()
         cur = torch.cuda.current_stream(self.dev)
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(cur)
-        with torch.cuda.stream(side):          # warm-up: packs weights, sizes the workspace, sets kernel attributes
+        with torch.cuda.stream(side), _wsmod.scope(self._ws):   # warm-up: packs weights, sizes the workspace, sets kernel attributes
             for _ in range(max(1, warmup)):
                 self._step()
         cur.wait_stream(side)
         torch.cuda.synchronize(self.dev)
-        # keep the workspace this graph's pointers refer to alive even if eager calls grow it later
-        key = (self.dev.type, self.dev.index if self.dev.index is not None else torch.cuda.current_device())
-        self._workspace = _cdrnet._WS.get(key)
+        self._hold_weights(model)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph), _wsmod.scope(self._ws):
             self._step()
 
     def _step(self):
@@ -91,13 +127,14 @@ class HeadGraph:
     def replay(self, sync=True):
         """One end-to-end step on the current contents of the pinned input tensors.
         Returns (kp_host list[2], xyz_host, sums_host) — valid after the sync."""
+        self._check_weights()
         self.graph.replay()
         if sync:
             torch.cuda.current_stream(self.dev).synchronize()
         return self.kp_host, self.xyz_host, self.sums_host
 
 
-class HeadPipeline:
+class HeadPipeline(_GraphHolder):
     """Throughput form of the end-to-end step: a depth-2 software pipeline over batches.
 
         submit(i):  copy stream    pinned host latents / P  --H2D-->  device input buffers [i % 2]
@@ -108,8 +145,8 @@ class HeadPipeline:
 
     While batch i computes, batch i+1 crosses PCIe, so a steady-state step costs
     max(H2D, compute) instead of their sum.  Every batch is still copied host->device and its
-    results device->host; only the order of waiting changes.  The two graphs share the library
-    workspace — legal because both replay on the one compute stream, in submission order.
+    results device->host; only the order of waiting changes.  The two graphs share this pipeline's
+    private workspace — legal because both replay on the one compute stream, in submission order.
     """
 
     def __init__(self, model, batch, gt=None, img_size=256, warmup=2):
@@ -131,9 +168,10 @@ class HeadPipeline:
         self.done = [torch.cuda.Event() for _ in range(2)]
         self.n_submitted = 0
         self.n_collected = 0
+        self._init_holder()
         cur = torch.cuda.current_stream(dev)
         self.compute_stream.wait_stream(cur)
-        with torch.cuda.stream(self.compute_stream):
+        with torch.cuda.stream(self.compute_stream), _wsmod.scope(self._ws):
             for s in range(2):
                 for t in self.feats_dev[s] + self.P_dev[s]:
                     t.zero_()
@@ -142,12 +180,11 @@ class HeadPipeline:
             for _ in range(max(1, warmup)):
                 self._compute(0)
         torch.cuda.synchronize(dev)
-        key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
-        self._workspace = _cdrnet._WS.get(key)
+        self._hold_weights(model)
         self.graphs = []
-        for s in range(2):
+        for s in range(2):               # both graphs share this pipeline's workspace: they replay on ONE stream, in order
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=self.compute_stream):
+            with torch.cuda.graph(g, stream=self.compute_stream), _wsmod.scope(self._ws):
                 self._compute(s)
             self.graphs.append(g)
         torch.cuda.synchronize(dev)
@@ -168,6 +205,7 @@ class HeadPipeline:
         compute stream after the head (e.g. the multi-GPU gather)."""
         if self.n_submitted - self.n_collected >= 2:
             raise RuntimeError("HeadPipeline: two batches already in flight — collect() first")
+        self._check_weights()
         s = self.n_submitted % 2
         with torch.cuda.stream(self.copy_stream):
             # the compute that last read these device buffers (batch n-2) was collected => finished
@@ -193,7 +231,7 @@ class HeadPipeline:
         return s, self.kp_host[s], self.xyz_host[s], (self.sums_host[s] if self.sums_host is not None else None)
 
 
-class FramePipeline:
+class FramePipeline(_GraphHolder):
     """The whole CDRNet pipeline as a depth-2 software pipeline over batches of raw stereo frames:
 
         submit(i):  copy stream    pinned host uint8 frames (2,B,H,W,3) + P  --H2D-->  device buffers [i % 2]
@@ -223,21 +261,20 @@ class FramePipeline:
         self.h2d_done = [torch.cuda.Event() for _ in range(2)]
         self.done = [torch.cuda.Event() for _ in range(2)]
         self.n_submitted = self.n_collected = 0
+        self._init_holder()
         self.compute_stream.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(self.compute_stream):
+        with torch.cuda.stream(self.compute_stream), _wsmod.scope(self._ws):
             for s in range(2):
                 for v in range(2):
                     self.P_dev[s][v][:, :, :3] = torch.eye(3, device=dev)    # any full-rank P for the warm-up
             for _ in range(max(1, warmup)):
                 self._compute(0)
         torch.cuda.synchronize(dev)
-        key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
-        self._workspace = _cdrnet._WS.get(key)
-        self._enc_workspace = dict(model._tc_encoder._ws)       # keep the encoder scratch the graphs point into alive
+        self._hold_weights(model, with_encoder=True)
         self.graphs = []
-        for s in range(2):
+        for s in range(2):               # head AND encoder scratch come from this pipeline's own workspace
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=self.compute_stream):
+            with torch.cuda.graph(g, stream=self.compute_stream), _wsmod.scope(self._ws):
                 self._compute(s)
             self.graphs.append(g)
         torch.cuda.synchronize(dev)
@@ -257,6 +294,7 @@ class FramePipeline:
         """frames_host: pinned uint8 (2,B,H,W,3) or [left, right] each (B,H,W,3); P_host: [P_l, P_r] pinned fp32."""
         if self.n_submitted - self.n_collected >= 2:
             raise RuntimeError("FramePipeline: two batches already in flight — collect() first")
+        self._check_weights()
         s = self.n_submitted % 2
         b = self.batch
         with torch.cuda.stream(self.copy_stream):

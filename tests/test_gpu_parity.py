@@ -61,7 +61,7 @@ def _dlt_sensitivity(cams, kp_l, kp_r, delta=1e-3):
     return k
 
 
-def check_3d(cams, kl, kr, xyz, o2, o3, label=""):
+def check_3d(cams, kl, kr, xyz, o2, o3, label="", flat=True):
     """The 3D gates: (1) our DLT against the fp64 oracle DLT on OUR 2D joints: <= 1e-2 mm
     (isolates the kernel); (2) end to end against the fp64 oracle: <= 1e-2 mm plus what the
     2D difference explains through the oracle's own sensitivity."""
@@ -77,6 +77,11 @@ def check_3d(cams, kl, kr, xyz, o2, o3, label=""):
           f"their d3D max {d3[kappa <= 25].max() if (kappa <= 25).any() else float('nan'):.2e} mm")
     assert np.all(same2d <= TOL_3D_MM + ulp3 + 4 * kappa * 2.0 ** -24 * 256)   # 2D inputs are fp32
     assert np.all(d3 <= TOL_3D_MM + ulp3 + 4 * kappa * d2)
+    good = kappa <= 25
+    if flat and good.any():
+        # the flat north-star tolerance, end to end, wherever the reference's own DLT is well conditioned
+        assert d3[good].max() <= TOL_3D_MM, f"{label} well-conditioned joints: {d3[good].max():.2e} mm > {TOL_3D_MM}"
+        assert d2[good].max() <= TOL_2D_PX
     return d2.max(), d3.max()
 
 
@@ -232,9 +237,12 @@ def test_dlt_kernel(cuda_pkg):
     assert np.abs(xyz.cpu().numpy() - gt["gt3d"]).max() < 5.0     # P and 2D were rounded to fp32
 
 
-@pytest.mark.parametrize("bf16", [False, True])
-def test_fused_softargmax_dlt_mpjpe(cuda_pkg, bf16):
-    b, j = 21, 19
+@pytest.mark.parametrize("bf16,b", [(False, 21), (True, 21), (False, 64)])
+def test_fused_softargmax_dlt_mpjpe(cuda_pkg, bf16, b):
+    """Blob heat-maps centred on consistent projections (a well-conditioned DLT) through the whole fused
+    soft-argmax + DLT + MPJPE kernel, at B = 64 too: the flat tolerances end to end against the oracle chain
+    process_heatmap -> dlt -> calc_mpjpe."""
+    j = 19
     cams = synth.make_cameras(b, seed=10)
     gt = synth.make_gt(cams, seed=11)
     cl = torch.from_numpy(gt["gt2d_l"] / 4.0).float()
@@ -264,12 +272,17 @@ def test_fused_softargmax_dlt_mpjpe(cuda_pkg, bf16):
     torch.cuda.synchronize()
     np.testing.assert_allclose(kl.cpu().numpy(), o_l.numpy(), atol=1e-4)
     np.testing.assert_allclose(kr.cpu().numpy(), o_r.numpy(), atol=1e-4)
-    np.testing.assert_allclose(xyz.cpu().numpy(), want3, atol=5e-3)
     e2, e3 = O.calc_mpjpe([kl.cpu().numpy(), kr.cpu().numpy()], xyz.cpu().numpy(), gt["gt3d"], gt["gt2d_l"],
                           gt["gt2d_r"], gt["vis"])
     s = sums.cpu().numpy()
     assert s[3] == b * j
     np.testing.assert_allclose([(s[0] + s[1]) / (2 * s[3]), s[2] / s[3]], [e2, e3], rtol=1e-10)
+    o2e, o3e = O.calc_mpjpe([o_l.numpy(), o_r.numpy()], want3, gt["gt3d"], gt["gt2d_l"], gt["gt2d_r"], gt["vis"])
+    d3 = np.abs(xyz.cpu().numpy() - want3).max()
+    print(f"\nfused kernel B={b} bf16={bf16}: d3D {d3:.2e} mm, MPJPE kernel ({(s[0] + s[1]) / (2 * s[3]):.6f}, {s[2] / s[3]:.6f}) "
+          f"oracle chain ({o2e:.6f}, {o3e:.6f})")
+    assert d3 <= TOL_3D_MM
+    assert abs(s[2] / s[3] - o3e) <= TOL_MPJPE_MM and abs((s[0] + s[1]) / (2 * s[3]) - o2e) <= TOL_2D_PX
     # blobs sit on the projections of the ground truth -> triangulation lands near it
     if not bf16:
         assert np.abs(xyz.cpu().numpy() - gt["gt3d"]).mean() < 25.0   # blob truncation at the borders biases a few mm
@@ -463,11 +476,15 @@ def test_full_size_properties(cuda_pkg):
     cams_s = {k: (v[lo:hi] if isinstance(v, np.ndarray) and v.shape[:1] == (b,) else v) for k, v in cams.items()}
     (kls, _), xyzs = _run_head(m, [f[lo:hi] for f in feats], cams_s)
     assert torch.equal(kls, kl[lo:hi]) and torch.equal(xyzs, xyz[lo:hi])
-    # spot-check 2 of the 64 against the fp64 oracle
-    o2, o3 = _oracle64(sd, [f[:2] for f in feats], {k: (v[:2] if isinstance(v, np.ndarray) and v.shape[:1] == (b,) else v) for k, v in cams.items()})
-    assert np.abs(kl[:2].cpu().numpy() - o2[0]).max() <= TOL_2D_PX
-    cams2 = {k: (v[:2] if isinstance(v, np.ndarray) and v.shape[:1] == (b,) else v) for k, v in cams.items()}
-    check_3d(cams2, kl[:2], kr[:2], xyz[:2], o2, o3, "B=64 spot check:")
+    # 8 of the 64 pairs, spread over the batch (every 128-row tile of the fusion block holds one), against the fp64 oracle
+    idx = np.arange(3, b, 8)
+    sub = lambda v: ([v[i] for i in idx] if isinstance(v, list) and len(v) == b else
+                     v[idx] if isinstance(v, np.ndarray) and v.shape[:1] == (b,) else v)
+    cams8 = {k: sub(v) for k, v in cams.items()}
+    o2, o3 = _oracle64(sd, [f[idx] for f in feats], cams8)
+    ti = torch.from_numpy(idx).cuda()
+    assert np.abs(kl[ti].cpu().numpy() - o2[0]).max() <= TOL_2D_PX and np.abs(kr[ti].cpu().numpy() - o2[1]).max() <= TOL_2D_PX
+    check_3d(cams8, kl[ti], kr[ti], xyz[ti], o2, o3, "B=64, 8 pairs spread over the batch:")
 
 
 def test_full_pipeline_vs_reference_golden(cuda_pkg, golden):
@@ -491,7 +508,8 @@ def test_full_pipeline_vs_reference_golden(cuda_pkg, golden):
     r3 = np.abs(golden["full_b1.f32.xyz"] - golden["full_b1.f64.xyz"]).max()
     print(f"\nfull pipeline: d2D={d2:.2e}px d3D={d3:.2e}mm | reference fp32 vs fp64: {r2:.2e}px {r3:.2e}mm")
     assert kl.shape == (1, 19, 2) and xyz.shape == (1, 19, 3) and kl.is_cuda
-    assert d2 <= max(10 * r2, 5e-3) and d3 <= max(10 * r3, 5e-2)
+    # flat north-star tolerances against the reference's fp64 forward (the reference's own fp32 sits at r2 / r3)
+    assert d2 <= TOL_2D_PX and d3 <= TOL_3D_MM
 
 
 # ------------------------------------------------------------------------------------------
@@ -664,29 +682,48 @@ def test_tc_encoder_resnet50_vs_emulated_and_fp32(cuda_pkg):
     assert e_32 < 6e-2 and m_32 < 2e-2          # stated bf16 bounds for ~50 layers of bf16 activations
 
 
+def _head_sd_of(m):
+    return {k: v.detach().cpu() for k, v in m.state_dict().items() if k.startswith(("CF.", "decoder."))}
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_full_pipeline_tc_encoder(cuda_pkg, precision):
-    """CDRNet.forward with encoder_precision='bf16': encoder rows feed cdr_head_forward_rows directly.
-    Compared with the same head fed the fp32 torch encoder's latents (the head's sensitivity to
-    bf16 latents) under the stated bf16 bounds."""
+    """CDRNet.forward with encoder_precision='bf16' (encoder rows feed cdr_head_forward_rows directly) against
+    the ORACLE of the same pipeline: the reference network evaluated in fp64 with bf16 rounding where the
+    tcgen05 encoder rounds (tests/bf16_emulation.py: encoder_bf16), followed by the fp64 oracle head (fp32
+    head) or the bf16-emulated oracle head (bf16 head).  Gate: the stated bf16 bound, 2D <= 1 px."""
+    from bf16_emulation import encoder_bf16, head_bf16
     b = 2
     torch.manual_seed(0)
     m = cuda_pkg.CDRNet(synth.make_cfg(50, 19), precision=precision, encoder_precision="bf16")
     m.load_state_dict(synth.make_head_state_dict(seed=0, calibrated=True), strict=False)
-    m = m.cuda().eval()
     cams = synth.make_cameras(b, seed=2)
-    Ps = [torch.from_numpy(cams["P_l"]).cuda(), torch.from_numpy(cams["P_r"]).cuda()]
+    P_cpu = [torch.from_numpy(cams["P_l"]), torch.from_numpy(cams["P_r"])]
     g = torch.Generator().manual_seed(1)
-    xs = [torch.randn(b, 3, 256, 256, generator=g).cuda() for _ in range(2)]
+    xs_cpu = [torch.randn(b, 3, 256, 256, generator=g) for _ in range(2)]
+    sd = _head_sd_of(m)
+    with torch.no_grad():
+        lat = [encoder_bf16(m.encoder.eval(), x.double()) for x in xs_cpu]          # fp64 values on the bf16 grid
+        if precision == "fp32":
+            o2, _ = O.head_forward(O.cast_state_dict(sd, torch.float64), lat, [p.double() for p in P_cpu])
+        else:
+            pinvs = [torch.linalg.pinv(p.double()).float() for p in P_cpu]
+            o2, _ = head_bf16(sd, [x.float() for x in lat], P_cpu, pinvs)
+    m = m.cuda().eval()
+    Ps = [p.cuda() for p in P_cpu]
+    xs = [x.cuda() for x in xs_cpu]
     (kl, kr), xyz = m(xs, Ps)
     with torch.no_grad():
         zs = [m.encoder(x) for x in xs]
     (rl, rr), rxyz = m.head(zs, Ps)
     torch.cuda.synchronize()
+    d2o = max(float((kl.cpu().double() - o2[0]).abs().max()), float((kr.cpu().double() - o2[1]).abs().max()))
     d2 = max(float((kl - rl).abs().max()), float((kr - rr).abs().max()))
-    print(f"\nfull pipeline [{precision}] tcgen05 bf16 encoder vs torch fp32 encoder: d2D max {d2:.3f} px")
+    print(f"\nfull pipeline [{precision}] tcgen05 bf16 encoder: vs bf16-emulated oracle pipeline d2D max {d2o:.3f} px | "
+          f"vs the same head on the torch fp32 encoder {d2:.3f} px")
     assert torch.isfinite(xyz).all() and kl.shape == (b, 19, 2) and xyz.shape == (b, 19, 3)
-    assert d2 < 1.5
+    assert d2o <= 1.0
+    assert d2 <= 1.0
 
 
 def test_frames_u8_match_reference_preprocessing(cuda_pkg):
@@ -745,27 +782,35 @@ def test_tc_encoder_shapes_and_errors(cuda_pkg):
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
 def test_poseresnet_tc_encoder_baseline_path(cuda_pkg, precision):
     """baseline.py's path (BASELINE configs[2]) on this library end to end: PoseResNet with the tcgen05
-    encoder feeding cdr_decoder_forward_rows, then get_max_preds x4 -> uint8 -> triangulation.  Heat-maps
-    stay within the stated bf16 bounds of the fp32 torch-encoder path and the arg-max pixels agree
-    wherever the top-2 logit gap exceeds the bf16 error."""
+    encoder feeding cdr_decoder_forward_rows, then get_max_preds x4 -> uint8 -> triangulation, against the
+    ORACLE of the same pipeline (fp64 evaluation with bf16 rounding where the kernels round).  Heat-maps stay
+    within the stated bf16 bound and the uint8 key points are identical wherever the oracle's top-2 logit gap
+    exceeds the heat-map error."""
     n, joints = 4, 19
     torch.manual_seed(0)
     m = cuda_pkg.PoseResNet(synth.make_cfg(50, joints), precision=precision, encoder_precision="bf16")
     sd = synth.make_head_state_dict(seed=3, joints=joints, calibrated=True, decoder_only=True)
     m.decoder.load_state_dict({k[len("decoder."):]: v for k, v in sd.items()})
+    from bf16_emulation import encoder_bf16, decoder_bf16
+    x_cpu = torch.randn(n, 3, 256, 256, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():                                   # the ORACLE of this pipeline (CPU, fp64, bf16 grid)
+        lat = encoder_bf16(m.encoder.cpu().eval(), x_cpu.double())
+        if precision == "bf16":
+            want = decoder_bf16(sd, lat)
+        else:
+            want = O.decoder(O.cast_state_dict(sd, torch.float64), lat)
     m = m.cuda().eval()
-    x = torch.randn(n, 3, 256, 256, generator=torch.Generator().manual_seed(2)).cuda()
+    x = x_cpu.cuda()
     got = m(x)
-    with torch.no_grad():
-        ref = m.decoder(m.encoder(x))                       # torch fp32 encoder + the same decoder kernels
     torch.cuda.synchronize()
+    ref = want.float().cuda()
     rel = float((got - ref).abs().max() / ref.abs().max())
     pts = cuda_pkg.baseline_keypoints(got)
-    pts_ref = cuda_pkg.baseline_keypoints(ref)
+    pts_ref = torch.from_numpy((O.get_max_preds(want.float().numpy())[0] * 4.0).astype(np.uint8)).cuda()   # baseline.py:51-53
     top2 = torch.topk(ref.reshape(n, joints, -1), 2, dim=-1).values
     decisive = (top2[..., 0] - top2[..., 1]) > 4 * float((got - ref).abs().max())
     agree = (pts == pts_ref).all(-1)
-    print(f"\nPoseResNet-50 [{precision}] tcgen05 encoder vs torch encoder: heat rel {rel:.2e}, "
+    print(f"\nPoseResNet-50 [{precision}] tcgen05 encoder + decoder vs the bf16-emulated oracle pipeline: heat rel {rel:.2e}, "
           f"arg-max agree {int(agree.sum())}/{agree.numel()} (decisive {int(decisive.sum())})")
     assert got.shape == (n, joints, 64, 64) and rel < 6e-2
     assert bool(agree[decisive].all())

@@ -108,3 +108,33 @@ def test_kats(golden):
     for j in range(19):
         pts = torch.stack([torch.from_numpy(gt["gt2d_l"][:, j]), torch.from_numpy(gt["gt2d_r"][:, j])], 1)
         np.testing.assert_allclose(O.dlt(projs, pts).numpy(), gt["gt3d"][:, j], atol=1e-6)
+
+
+def test_oracle_matches_live_reference():
+    """Where the reference itself is importable (oracle/refload.py): the UNMODIFIED CDRNet.forward (encoder
+    replaced by a feature stub, as in make_golden.py) and the oracle, side by side in fp64 on seeds the golden
+    file does not contain, plus calc_mpjpe / get_max_preds / triangulation on the same arrays."""
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("reference sources not present")
+    ref = refload.load()
+    b, joints = 2, 19
+    sd = synth.make_head_state_dict(seed=21, joints=joints, calibrated=True, randomize_bn=True)
+    feats, cams = synth.make_features(b, seed=22), synth.make_cameras(b, seed=23)
+    Ps = [torch.from_numpy(cams["P_l"]).double(), torch.from_numpy(cams["P_r"]).double()]
+    m = ref.CDRNet(synth.make_cfg(18, joints), nj=joints)
+    m.load_state_dict(sd, strict=False)
+    m.encoder = refload.feature_stub([f.double() for f in feats])
+    m = m.double().eval()
+    with torch.no_grad():
+        r2, r3 = m([torch.zeros(b, 3, 256, 256, dtype=torch.float64)] * 2, Ps)
+        o2, o3 = O.head_forward(O.cast_state_dict(sd, torch.float64), [f.double() for f in feats], Ps)
+    for a, w in zip(o2, r2):
+        np.testing.assert_allclose(a.numpy(), w.numpy(), rtol=0, atol=1e-9)
+    np.testing.assert_allclose(o3.numpy(), r3.numpy(), rtol=1e-9, atol=1e-6)
+    gt = synth.make_gt(cams, seed=24)
+    args = ([x.numpy() for x in r2], r3.numpy(), gt["gt3d"], gt["gt2d_l"], gt["gt2d_r"], gt["vis"])
+    np.testing.assert_allclose(np.array(O.calc_mpjpe(*args)), np.array(ref.calc_mpjpe(*args)), rtol=1e-13)
+    h = np.random.default_rng(5).normal(size=(2, joints, 64, 64)).astype(np.float32)
+    for a, w in zip(O.get_max_preds(h), ref.get_max_preds(h)):
+        assert np.array_equal(a, w)

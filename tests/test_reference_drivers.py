@@ -1,0 +1,140 @@
+"""Drop-in proof through the reference's OWN drivers (VERDICT r1 "missing 3"):
+
+``CDRNetInferencer`` (inference.py:23-114) and ``BaseLine`` (baseline.py:22-103) are imported
+unmodified (oracle/refload.py: /root/reference in the build container, the git-ignored copy
+baseline/_ref/ on the GPU box), the names they import from ``models/`` and ``tools/`` are pointed at
+this repo's drop-ins (the two-line import swap of INTEGRATION.md), and what ``inference()`` /
+``estimate()`` return is compared with tests/golden/driver_golden.npz — the unmodified reference's
+outputs on the same frame and checkpoint, CPU fp32 (tests/golden/make_driver_golden.py).  Nothing in
+the drivers is bypassed: their constructors strict-load ``weights/<NAME>/best.pth|latest.pth``.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import refdrivers as RD
+from oracle import refload
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TOL_2D_PX, TOL_3D_MM, TOL_MPJPE_MM = 1e-3, 1e-2, 1e-3
+
+needs_ref = pytest.mark.skipif(not RD.available(), reason="reference sources not present (build() copies them to "
+                               "baseline/_ref while /root/reference is mounted)")
+
+
+@pytest.fixture(scope="module")
+def dgolden():
+    return dict(np.load(os.path.join(HERE, "golden", "driver_golden.npz")))
+
+
+@pytest.fixture(scope="module")
+def drivers():
+    return refload.load_drivers()
+
+
+@needs_ref
+def test_reference_cdrnet_driver_reproduces_golden(drivers, dgolden, tmp_path, pkg):
+    """The unmodified reference through its own driver == the committed golden (pins the golden to the
+    reference wherever the reference is present; bit-exact on the CPU that generated it, fp32 noise
+    elsewhere).  Also: this repo's constructor creates the reference's parameters bit for bit."""
+    inference_mod, _ = drivers
+    ref = refload.load()
+    cfg = refload.load_config("mads_3d.yaml")
+    sd = RD.seeded_state_dict(ref.CDRNet, cfg)
+    ours = RD.seeded_state_dict(pkg.CDRNet, cfg)
+    assert list(sd) == list(ours) and all(torch.equal(sd[k], ours[k]) for k in sd)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with RD.workdir_with_checkpoint(tmp_path, cfg, sd, "best.pth"):
+        r = RD.run_cdrnet_driver(inference_mod, cfg, RD.driver_case())
+    d2 = max(np.abs(r["kp_l"] - dgolden["cdrnet.kp_l"]).max(), np.abs(r["kp_r"] - dgolden["cdrnet.kp_r"]).max())
+    d3 = np.abs(r["xyz"] - dgolden["cdrnet.xyz"]).max()
+    print(f"\nreference CDRNetInferencer on {r['device']} vs golden (CPU fp32): d2D={d2:.2e}px d3D={d3:.2e}mm")
+    assert d2 <= 5e-3 and d3 <= 5e-2            # the reference against itself across devices / BLAS builds
+    np.testing.assert_allclose(r["err"], dgolden["cdrnet.err"], atol=1e-2)
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cdrnet_inferencer_with_dropin(cuda_pkg, drivers, dgolden, tmp_path):
+    """inference.py's CDRNetInferencer with ``CDRNet`` and ``calc_mpjpe`` swapped for this repo's:
+    constructor (strict checkpoint load, .to(device), .eval()), inference() and estimate() run
+    unmodified; 2D / 3D / MPJPE inside the flat north-star tolerances of the reference's own output."""
+    inference_mod, baseline_mod = drivers
+    cfg = refload.load_config("mads_3d.yaml")
+    case = RD.driver_case()
+    sd = RD.seeded_state_dict(cuda_pkg.CDRNet, cfg)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with RD.workdir_with_checkpoint(tmp_path, cfg, sd, "best.pth"):
+        live = RD.run_cdrnet_driver(inference_mod, cfg, case)            # the reference itself on this GPU
+        saved = RD.substitute_shim(inference_mod, baseline_mod, cuda_pkg)
+        try:
+            cuda_pkg._lib.lib().cdr_launch_count_reset()
+            ours = RD.run_cdrnet_driver(inference_mod, cfg, case)
+            launches = cuda_pkg._lib.lib().cdr_launch_count()
+        finally:
+            RD.restore(saved)
+    assert launches > 0, "the drop-in must run libcdrhead kernels"
+    g = dgolden
+
+    def dist(a):
+        return (max(np.abs(a["kp_l"] - g["cdrnet.kp_l"]).max(), np.abs(a["kp_r"] - g["cdrnet.kp_r"]).max()),
+                np.abs(a["xyz"] - g["cdrnet.xyz"]).max())
+    d2, d3 = dist(ours)
+    r2, r3 = dist(live)
+    print(f"\nCDRNetInferencer drop-in vs reference golden: d2D={d2:.2e}px d3D={d3:.2e}mm MPJPE "
+          f"{ours['err']} vs {g['cdrnet.err']} | the reference on this GPU vs its CPU golden: {r2:.2e}px {r3:.2e}mm")
+    assert ours["kp_l"].shape == (19, 2) and ours["xyz"].shape == (19, 3) and ours["kp_l"].dtype == np.float32
+    assert d2 <= TOL_2D_PX
+    assert d3 <= TOL_3D_MM
+    assert abs(ours["err"][1] - g["cdrnet.err"][1]) <= TOL_MPJPE_MM
+    assert abs(ours["err"][0] - g["cdrnet.err"][0]) <= TOL_2D_PX
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_baseline_driver_with_dropin(cuda_pkg, drivers, dgolden, tmp_path):
+    """baseline.py's BaseLine with ``PoseResNet`` / ``get_max_preds`` / ``triangulation`` / ``calc_mpjpe``
+    swapped.  uint8 key points are bit-identical to the reference's wherever the reference's own top-2
+    logit gap exceeds fp32 noise (a random-init network has near-flat maps: gaps down to 6e-6 of the
+    maximum); on identical points the triangulation is inside 1e-2 mm and the MPJPE inside 1e-3 mm."""
+    inference_mod, baseline_mod = drivers
+    ref = refload.load()
+    cfg = refload.load_config("mads_2d.yaml")
+    case = RD.driver_case()
+    sd = RD.seeded_state_dict(cuda_pkg.PoseResNet, cfg)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with RD.workdir_with_checkpoint(tmp_path, cfg, sd, "latest.pth"):
+        saved = RD.substitute_shim(inference_mod, baseline_mod, cuda_pkg)
+        try:
+            ours = RD.run_baseline_driver(baseline_mod, cfg, case)
+        finally:
+            RD.restore(saved)
+    g = dgolden
+    assert ours["u8_l"].dtype == np.uint8 and ours["u8_l"].shape == (19, 2)
+    decisive = g["baseline.top2_gap"] > 1e-4 * g["baseline.heat_absmax"]          # (view, joint)
+    same = np.stack([(ours["u8_l"] == g["baseline.u8_l"]).all(-1), (ours["u8_r"] == g["baseline.u8_r"]).all(-1)])
+    print(f"\nBaseLine drop-in: key points identical {int(same.sum())}/38 (decisive {int(decisive.sum())}), "
+          f"err {ours['err']} vs {g['baseline.err']}")
+    assert same[decisive].all()
+    both = same.all(0)
+    assert both.sum() >= 5
+    np.testing.assert_allclose(ours["xyz"][both], g["baseline.xyz"][both], rtol=0, atol=TOL_3D_MM)
+    # the reference's triangulation and calc_mpjpe on OUR key points (no tie ambiguity left)
+    img_l, img_r, meta = case
+    PL = ref.get_projection_matrix(meta["cam_left"]["intrinsics"], meta["cam_left"]["rotation"], meta["cam_left"]["translation"])
+    PR = ref.get_projection_matrix(meta["cam_right"]["intrinsics"], meta["cam_right"]["rotation"], meta["cam_right"]["translation"])
+    want3 = ref.triangulation(PL, PR, ours["u8_l"], ours["u8_r"])
+    np.testing.assert_allclose(ours["xyz"], want3, rtol=0, atol=TOL_3D_MM)
+    pose = np.array(meta["pose_3d"]); mask = np.isnan(pose); pose[mask] = 0
+    vis = np.ones_like(pose); vis[mask] = 0
+    vis = np.logical_and.reduce(vis, axis=1, keepdims=True)
+    from fast_3d_human_pose_estimation_b200 import synth
+    g2l = synth._project(pose, meta["cam_left"]["intrinsics"], meta["cam_left"]["rotation"], meta["cam_left"]["translation"])
+    g2r = synth._project(pose, meta["cam_right"]["intrinsics"], meta["cam_right"]["rotation"], meta["cam_right"]["translation"])
+    want_err = ref.calc_mpjpe([ours["u8_l"], ours["u8_r"]], want3, pose, g2l, g2r, vis)
+    assert abs(ours["err"][1] - want_err[1]) <= TOL_MPJPE_MM and abs(ours["err"][0] - want_err[0]) <= TOL_2D_PX
