@@ -58,6 +58,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking poll: has the phase with this parity completed?  (try_wait may suspend the thread, test_wait never does)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Spin on try_wait (which itself suspends the thread for a HW-defined time).  A protocol bug
 // must not hang the GPU: after ~4 s of waiting the kernel traps (cudaErrorLaunchFailure).
 // host-mapped words a timed-out wait writes before trapping (api.cu: cdr_debug_words) — device printf
