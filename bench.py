@@ -31,6 +31,7 @@ UNIT = "stereo pairs/s"
 JOINTS = 19
 # algorithmic work per stereo pair
 FLOP_PER_PAIR = {"deconv1": 2147.5e6, "deconv2": 1073.7e6, "deconv3": 4295.0e6, "final_1x1": 79.7e6,
+                 "deconv3_tail": 4295.0e6 + 79.7e6,      # fused deconv3 + final 1x1 (+ soft-argmax partials)
                  "cf_conv1": 157.3e6, "cf_conv2": 61.5e6, "cf_out": 157.3e6}
 HEAD_FLOP_PER_PAIR = 7972.5e6
 SOFTARGMAX_DLT_BYTES_PER_POSE = 623220.0
@@ -454,6 +455,7 @@ def measure(args, precision, ctx):
                 "traffic_source": ncu_traffic().get("source"),
                 "peak_source": pk["source"] + " bf16 sustained (cuBLAS)", "launch_ms": stage_ms[top],
                 "share_of_step": share,
+                "fused": "deconv3 + final 1x1 + soft-argmax partial sums in one kernel" if top == "deconv3_tail" else None,
                 "note": {"bf16": "tcgen05 kind::f16, bf16 operands",
                          "fp32": "tcgen05 kind::f16 on fp16 two-term operands, 3 MMAs per product at the full 16-bit "
                                  "rate: at most 1/3 of the bf16 peak in algorithmic FLOPs",
@@ -465,7 +467,7 @@ def measure(args, precision, ctx):
         roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
                 "launch_ms": stage_ms[top], "share_of_step": share}
-    sa = stage_ms.get("softargmax_dlt")
+    sa = stage_ms.get("softargmax_dlt")          # absent when the decoder tail is fused (deconv3_tail + merge_dlt)
     hbm = None
     if sa:
         a = SOFTARGMAX_DLT_BYTES_PER_POSE * B / (sa / 1e3) / 1e9
@@ -473,7 +475,7 @@ def measure(args, precision, ctx):
                "unit": "GB/s", "frac": a / pk["hbm_gbs"], "launch_ms": sa,
                "note": "latency-bound launch at this batch (64 CTAs on 148 SMs, 40 MB of logits still in L2); the "
                        "kernel's HBM roofline is roofline_hbm_stream / config4_softargmax_dlt_1m_poses"}
-    dec_ms = sum(stage_ms.get(k, 0.0) for k in ("deconv1", "deconv2", "deconv3", "final_1x1"))
+    dec_ms = sum(stage_ms.get(k, 0.0) for k in ("deconv1", "deconv2", "deconv3", "final_1x1", "deconv3_tail"))
     dec_tf = 7595.9e6 * B / (dec_ms / 1e3) / 1e12 if dec_ms else None
     return {
         "value": value, "ms_per_step": dev_ms / K, "dtype": precision,

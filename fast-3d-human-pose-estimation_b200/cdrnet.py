@@ -307,13 +307,15 @@ class CDRNet(nn.Module):
         self.load_state_dict({k: v for k, v in ckpt.items() if k.startswith("encoder")},
                              strict=False)
 
-    def head(self, feats, proj_list, proj_inv_list=None, taps=False, img_size=256, feat_rows=None):
+    def head(self, feats, proj_list, proj_inv_list=None, taps=False, img_size=256, feat_rows=None, out_xyz=None):
         """The hot path: encoder latents -> (pred_2ds, pred_3ds).  models/cdrnet.py:236-268.
 
         feats: list[2] of (B,2048,8,8); proj_list: list[2] of (B,3,4).  ``proj_inv_list``
         overrides the on-device pseudo-inverse.  ``taps=True`` also returns the stage
         tensors the parity tests compare.  ``feat_rows`` (instead of ``feats``): the latents as
-        bf16 pixel-major rows (2*B*64, 2048), left view first — the tcgen05 encoder's output."""
+        bf16 pixel-major rows (2*B*64, 2048), left view first — the tcgen05 encoder's output.
+        ``out_xyz``: a contiguous (B,J,3) fp32 CUDA tensor the 3D joints are written into (e.g. this rank's slot
+        of a multi-GPU gather buffer, dist.GatherBuffer) instead of a fresh tensor."""
         _require_eval(self)
         pl = _as_f32_cuda(proj_list[0], "proj_list")
         pr = _as_f32_cuda(proj_list[1], "proj_list")
@@ -345,7 +347,13 @@ class CDRNet(nn.Module):
         ws = _workspace(dev, nbytes.value)
         kp_l = torch.empty((b, j, 2), dtype=torch.float32, device=dev)
         kp_r = torch.empty((b, j, 2), dtype=torch.float32, device=dev)
-        xyz = torch.empty((b, j, 3), dtype=torch.float32, device=dev)
+        if out_xyz is not None:
+            if not (out_xyz.is_cuda and out_xyz.dtype == torch.float32 and out_xyz.is_contiguous()
+                    and tuple(out_xyz.shape) == (b, j, 3) and out_xyz.device == dev):
+                raise ValueError(f"out_xyz must be a contiguous ({b},{j},3) float32 tensor on {dev}")
+            xyz = out_xyz
+        else:
+            xyz = torch.empty((b, j, 3), dtype=torch.float32, device=dev)
         tap_struct, tap_out = None, None
         if taps:
             tap_out = {

@@ -29,6 +29,7 @@
 #include <stdlib.h>
 #include <type_traits>
 
+#include "jacobi.cuh"
 #include "ptx.cuh"
 #include "tc_api.h"
 
@@ -1059,6 +1060,99 @@ static int launch_tc(const TcLaunch& l, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
+// fused decoder tail: deconv3 + final 1x1 + soft-argmax partials (tail_tc.cuh)
+}  // namespace cdr
+#include "tail_tc.cuh"
+namespace cdr {
+
+// CDR_FUSED_TAIL=0 keeps deconv3 / final 1x1 / soft-argmax as three launches (A/B timing, cross-check).  Read at
+// every forward (one getenv) so a test can compare both paths inside one process.
+static bool tc_use_fused_tail() {
+  const char* e = getenv("CDR_FUSED_TAIL");
+  return !(e && e[0] == '0');
+}
+
+struct TailLaunch {
+  Act A;                    // d2: (n_img, 32, 32, 256) pixel-major
+  int n_img, joints;
+  const TcLayer* dc3;       // packed deconv3
+  const TcLayer* fin;       // packed final layer (32 padded rows)
+  ScaleSlot in_slot;        // f16x2: scale / amax of d2
+  float* heat;              // optional planar heat-maps
+  float4* part;             // optional soft-argmax partial records
+};
+
+template <int KIND>
+static int launch_tail_t(const TailLaunch& l, cudaStream_t st) {
+  using Cfg = TailCfg<KIND>;
+  constexpr int kAFmt = KindTraits<KIND>::kFmt;
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
+    CDR_CUDA(cudaFuncSetAttribute(deconv_tail_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)TailSmem<KIND>::kBytes));
+    attr_set.done();
+  }
+  CDR_CHECK_ARG(l.A.fmt == kAFmt && l.dc3->kind == KIND && l.fin->kind == KIND && l.dc3->bn == Cfg::kBN &&
+                    l.fin->n_pad == 32 && l.joints <= 32 && (l.heat || l.part),
+                "deconv_tail: operand formats / packing do not match the kernel");
+  CUtensorMap tmap_a[2];
+  for (int pl = 0; pl < Cfg::kPlanes; ++pl) {
+    const uint64_t dims[4] = {(uint64_t)kDecC, 32, 32, (uint64_t)l.n_img};
+    const uint64_t strides[3] = {(uint64_t)kDecC, (uint64_t)kDecC * 32, (uint64_t)kDecC * 1024};
+    const uint32_t box[4] = {64, 32, 4, 1};
+    if (int rc = make_tmap(&tmap_a[pl], l.A.p[pl], kAFmt, 4, dims, strides, box)) return rc;
+  }
+  if (Cfg::kPlanes == 1) tmap_a[1] = tmap_a[0];
+  TailParams p{};
+  p.n_img = l.n_img;
+  p.num_units = (l.n_img * 1024 / kTcBM) * 4;
+  p.joints = l.joints;
+  p.bias = l.dc3->bias;
+  p.wsi = l.dc3->wsi;
+  p.scale_in = l.in_slot.scale;
+  p.amax_in = l.in_slot.amax;
+  p.norms = l.dc3->norms;
+  p.bias_fin = l.fin->bias;
+  p.wsi_fin = l.fin->wsi;
+  p.heat = l.heat;
+  p.part = l.part;
+  if (KIND == kKindF16X2)
+    CDR_CHECK_ARG(p.wsi && p.scale_in && p.amax_in && p.norms && p.wsi_fin, "deconv_tail: f16x2 operands need their scales");
+  const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  int n_attr = 0;
+  if (tc_use_pdl()) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kTailThreads);
+  cfg.dynamicSmemBytes = TailSmem<KIND>::kBytes;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = n_attr;
+  CDR_CUDA(cudaLaunchKernelEx(&cfg, deconv_tail_kernel<KIND>, tmap_a[0], tmap_a[1], l.dc3->map[0],
+                              l.dc3->map[Cfg::kPlanes - 1], l.fin->map[0], l.fin->map[Cfg::kPlanes - 1], p));
+  CDR_LAUNCH_OK("deconv_tail_kernel");
+  return CDR_OK;
+}
+
+static int launch_tail_merge(const float4* part, const float* P_l, const float* P_r, int batch, int joints, float scale,
+                             float* kp_l, float* kp_r, float* xyz, cudaStream_t st) {
+  TailMergeParams p{};
+  p.part = part;
+  p.P[0] = P_l; p.P[1] = P_r;
+  p.kp[0] = kp_l; p.kp[1] = kp_r;
+  p.xyz = xyz;
+  p.batch = batch; p.joints = joints; p.scale = scale;
+  tail_merge_dlt_kernel<<<batch, 256, 0, st>>>(p);
+  CDR_LAUNCH_OK("tail_merge_dlt_kernel");
+  return CDR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // weight packing (K-major B operands) — BN folded in fp64 as in pack.cu
 constexpr double kBnEpsTc = 1e-5;
 __device__ __forceinline__ double tc_bn_scale(const CdrConvBn& s, int co) {
@@ -1338,6 +1432,7 @@ struct TcHeadWs {
   float* slots;
   Act x0, y1, z, f1, f2, g, x1, d1, d2, d3;
   float* hm;
+  float4* part;             // fused decoder tail: soft-argmax partial records (2B, J, kTailSlots)
   size_t bytes;
 };
 static ScaleSlot slot(float* slots, int i) {
@@ -1371,6 +1466,7 @@ static TcHeadWs plan_tc_head(void* base, int B, int J, int mode) {
   w.d2 = take_act(b, N * 1024 * kDecC, df);
   w.d3 = take_act(b, N * 4096 * kDecC, df);
   w.hm = (float*)b.take(N * J * 4096 * sizeof(float));
+  w.part = (float4*)b.take(N * J * kTailSlots * sizeof(float4));
   w.bytes = b.off;
   return w;
 }
@@ -1428,15 +1524,26 @@ static int ftl_act2(const Act& in0, const Act& in1, int in_pitch, const float* c
                            amax_out, st);
 }
 
-// slots: x1 -> 1, d1 -> 2, d2 -> 3, d3 -> 4
+// Can this pack run deconv3 + final 1x1 (+ soft-argmax partials) as the one kernel of tail_tc.cuh?
+static bool tail_fusable(const TcWeights& w) {
+  const int dk = mode_decoder_kind(w.kind);
+  const TcPack* pk = (const TcPack*)w.impl;
+  return tc_use_fused_tail() && (dk == kKindBF16 || dk == kKindF16X2) && w.fin_npad == 32 &&
+         pk->dc[2].bn == (dk == kKindBF16 ? 256 : 128);
+}
+
+// slots: x1 -> 1, d1 -> 2, d2 -> 3, d3 -> 4.  heat (planar fp32 heat-maps) and part (soft-argmax partial records) are
+// the two possible products; part != NULL requires tail_fusable().
 static int tc_decoder(const TcWeights& w, const Act& x1, int N, const Act& d1, const Act& d2, const Act& d3,
-                      float* slots, float* heat, cudaStream_t st) {
+                      float* slots, float* heat, float4* part, cudaStream_t st) {
   const TcPack* pk = (const TcPack*)w.impl;
   static const char* const kDcName[3] = {"deconv1", "deconv2", "deconv3"};
+  const bool fused = tail_fusable(w);
+  CDR_CHECK_ARG(fused || !part, "tc_decoder: soft-argmax partials need the fused tail");
   Act in = x1;
   const Act outs[3] = {d1, d2, d3};
   int side = 8;
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < (fused ? 2 : 3); ++i) {
     set_stage(kDcName[i]);
     TcLaunch l{};
     l.A = in; l.a_pitch = kTcDcCin[i]; l.n_img = N; l.H = l.W = side; l.cin = kTcDcCin[i];
@@ -1447,6 +1554,17 @@ static int tc_decoder(const TcWeights& w, const Act& x1, int N, const Act& d1, c
     if (int rc = launch_tc(l, st)) return rc;
     in = outs[i];
     side *= 2;
+  }
+  if (fused) {
+    set_stage("deconv3_tail");
+    TailLaunch t{};
+    t.A = d2; t.n_img = N; t.joints = w.joints;
+    t.dc3 = &pk->dc[2]; t.fin = &pk->fin;
+    t.in_slot = slot(slots, 3);
+    t.heat = heat; t.part = part;
+    const int rc = mode_decoder_kind(w.kind) == kKindBF16 ? launch_tail_t<kKindBF16>(t, st) : launch_tail_t<kKindF16X2>(t, st);
+    set_stage(nullptr);
+    return rc;
   }
   set_stage("final_1x1");
   TcLaunch l{};
@@ -1599,11 +1717,20 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
     l.amax_in = slot(ws.slots, 0).amax; l.out_slot = slot(ws.slots, 1);
     if ((rc = launch_tc(l, st))) return rc;
   }
-  if ((rc = tc_decoder(w, ws.x1, N, ws.d1, ws.d2, ws.d3, ws.slots, ws.hm, st))) return rc;
-  set_stage("softargmax_dlt");
-  if ((rc = cdr_softargmax_dlt(ws.hm, ws.hm + (size_t)B * J * 4096, 0, P_l, P_r, B, J, kHeat, kHeat, scale,
-                               kp2d_l, kp2d_r, xyz, nullptr, nullptr, nullptr, nullptr, nullptr, st)))
-    return rc;
+  if (tail_fusable(w)) {
+    // deconv3 + final 1x1 + soft-argmax partials in one kernel: neither deconv3's activation nor (unless a tap asks
+    // for them) the heat-maps touch HBM; a 64-CTA merge kernel finishes soft-argmax, scale and DLT
+    float* heat = (taps && taps->heatmaps) ? ws.hm : nullptr;
+    if ((rc = tc_decoder(w, ws.x1, N, ws.d1, ws.d2, ws.d3, ws.slots, heat, ws.part, st))) return rc;
+    set_stage("merge_dlt");
+    if ((rc = launch_tail_merge(ws.part, P_l, P_r, B, J, scale, kp2d_l, kp2d_r, xyz, st))) return rc;
+  } else {
+    if ((rc = tc_decoder(w, ws.x1, N, ws.d1, ws.d2, ws.d3, ws.slots, ws.hm, nullptr, st))) return rc;
+    set_stage("softargmax_dlt");
+    if ((rc = cdr_softargmax_dlt(ws.hm, ws.hm + (size_t)B * J * 4096, 0, P_l, P_r, B, J, kHeat, kHeat, scale,
+                                 kp2d_l, kp2d_r, xyz, nullptr, nullptr, nullptr, nullptr, nullptr, st)))
+      return rc;
+  }
   set_stage(nullptr);
   if (taps) {
     if (taps->pinv) {
@@ -1647,12 +1774,12 @@ int tc_decoder_forward(const TcWeights& w, const void* feat_rows, const float* f
           (const __nv_bfloat16*)feat_rows, (__half*)x1.p[0], (__half*)x1.p[1], n, sl.amax, sl.scale);
       CDR_LAUNCH_OK("bf16_rows_to_f16p_kernel");
     }
-    return tc_decoder(w, x1, n_images, ws.d1, ws.d2, ws.d3, ws.slots, heatmaps, st);
+    return tc_decoder(w, x1, n_images, ws.d1, ws.d2, ws.d3, ws.slots, heatmaps, nullptr, st);
   }
   if (ws.x1.fmt == kFmtF16P) CDR_CUDA(cudaMemsetAsync(ws.slots, 0, 2 * kNumSlots * sizeof(float), st));
   set_stage("nchw_to_rows");
   if (int rc = to_rows(feat, nullptr, n_images, ws.x1, slot(ws.slots, 1), st)) return rc;
-  return tc_decoder(w, ws.x1, n_images, ws.d1, ws.d2, ws.d3, ws.slots, heatmaps, st);
+  return tc_decoder(w, ws.x1, n_images, ws.d1, ws.d2, ws.d3, ws.slots, heatmaps, nullptr, st);
 }
 
 

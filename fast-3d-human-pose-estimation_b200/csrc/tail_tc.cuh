@@ -65,6 +65,12 @@ template <int KIND> struct TailSmem {
 };
 constexpr int kTailThreads = 32 * 14;     // producer, MMA issuer, 8 convert warps, 4 heat warps
 
+__device__ __forceinline__ float ptx_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // one MUFU.EX2, rel. error 2^-22
+  return y;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kTailThreads, 1)
 deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
@@ -90,9 +96,11 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint64_t* chunk_empty = bars + 2 * S + 6;  // [2]
   uint64_t* heat_full = bars + 2 * S + 8;    // [2]
   uint64_t* a2_full = bars + 2 * S + 10;     // one phase per hand-off round
-  uint64_t* a2_empty = bars + 2 * S + 11;
-  uint64_t* wf_full = bars + 2 * S + 12;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 13);
+  uint64_t* a2_empty = bars + 2 * S + 11;    // [2] heat MMAs of column group j's round complete (bf16: [0] only).  One
+                                             // barrier per group: its waiter is the OTHER group, which cannot fall two
+                                             // phases behind (a parity wait only tells the current phase from the last)
+  uint64_t* wf_full = bars + 2 * S + 13;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 14);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,7 +127,8 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       ptx::mbar_init(&heat_full[a], 1);
     }
     ptx::mbar_init(a2_full, Cfg::kRoundWarps);
-    ptx::mbar_init(a2_empty, 1);
+    ptx::mbar_init(&a2_empty[0], 1);
+    ptx::mbar_init(&a2_empty[1], 1);
     ptx::mbar_init(wf_full, 1);
     ptx::fence_mbar_init();
   }
@@ -229,7 +238,7 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             ptx::umma_f16(d_hm, da + o, dw + o, idesc_heat, (j | (uint32_t)k) != 0);    // hi * hi
           }
         }
-        ptx::umma_commit(a2_empty);
+        ptx::umma_commit(&a2_empty[j]);
         if (j == Cfg::kRounds - 1) ptx::umma_commit(&heat_full[acc]);
       };
       auto poll_rounds = [&]() {
@@ -275,7 +284,15 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const uint32_t d_corr = tmem_base + (2 + acc) * BN;
             for (int kb0 = 0; kb0 < kNumKb; kb0 += kSplitChunk, ++ch) {
               const int buf = ch & 1;
-              ptx::mbar_wait(&chunk_empty[buf], ((ch >> 1) & 1) ^ 1u);
+              // The drain of this chunk buffer may sit behind a hand-off only this thread can complete (column group 1
+              // waits for group 0's heat MMAs before it writes A2, then drains): keep serving rounds while waiting.
+              if (!ptx::mbar_test_wait(&chunk_empty[buf], ((ch >> 1) & 1) ^ 1u)) {
+                const long long t0 = clock64();
+                while (!ptx::mbar_test_wait(&chunk_empty[buf], ((ch >> 1) & 1) ^ 1u)) {
+                  poll_rounds();
+                  if (clock64() - t0 > 8000000000LL) __trap();     // protocol bug: fail the launch, never hang the GPU
+                }
+              }
               ptx::tc_fence_after();
               const uint32_t d_main = tmem_base + (uint32_t)(buf * BN);
               const int kb1 = kb0 + kSplitChunk < kNumKb ? kb0 + kSplitChunk : kNumKb;
@@ -315,18 +332,22 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int cb0 = grp * kCols;
     const int row = q * 32 + lane;                 // this thread's pixel inside the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t tl = 0, ch = 0, seen = 0;             // seen: phases of a2_empty this warp has observed
+    uint32_t tl = 0, ch = 0;
     float a_inv = 1.f, s_out = 1.f;
     if constexpr (kSplit) {
       a_inv = 1.f / __ldg(p.scale_in);
       const float bound = __ldg(p.amax_in) * __ldg(p.norms) + __ldg(p.norms + 1);
       if (bound > 0.f && bound < 3.0e38f) s_out = ldexpf(1.f, kF16TargetExp - ilogbf(bound));
     }
-    auto wait_a2_free = [&](uint32_t round) {      // every phase is observed, in order (mbarrier parity aliasing)
-      while (seen < round) {
-        ptx::mbar_wait(a2_empty, seen & 1);
-        ++seen;
-      }
+    // A2 is free for this warp's round of tile tl once the heat MMAs of the round BEFORE it have completed:
+    //   bf16 (one round per tile)   : round of tile tl-1                     -> a2_empty[0], phase tl-1
+    //   f16x2, column group 0       : group 1's round of tile tl-1           -> a2_empty[1], phase tl-1
+    //   f16x2, column group 1       : group 0's round of tile tl             -> a2_empty[0], phase tl
+    // ("phase -1" of a fresh barrier reads as complete.)
+    auto wait_a2_free = [&]() {
+      if constexpr (!kSplit) ptx::mbar_wait(&a2_empty[0], (tl & 1) ^ 1u);
+      else if (grp == 0) ptx::mbar_wait(&a2_empty[1], (tl & 1) ^ 1u);
+      else ptx::mbar_wait(&a2_empty[0], tl & 1);
     };
     auto publish_a2 = [&]() {
       ptx::fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core's smem reads
@@ -343,7 +364,7 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if constexpr (!kSplit) {
           ptx::mbar_wait(&tmem_full[acc], (tl >> 1) & 1);
           ptx::tc_fence_after();
-          wait_a2_free(tl);
+          wait_a2_free();
 #pragma unroll 1
           for (int c = 0; c < kCols; c += 64) {
             uint32_t r0[32], r1[32];
@@ -425,7 +446,7 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             wl[2 * j4] = *reinterpret_cast<const uint32_t*>(&l01);
             wl[2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&l23);
           }
-          wait_a2_free(tl * 2 + grp);              // round of this tile written by this column group
+          wait_a2_free();                          // round of this tile written by this column group
           const uint32_t base = ptx::smem_u32(a2) + (uint32_t)row * 128u;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -491,18 +512,20 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           if constexpr (kSplit) v *= fin_scale * __ldg(p.wsi_fin + j);
           v += __ldg(p.bias_fin + j);
           if (p.heat) p.heat[((size_t)img * J + j) * 4096 + oy * 64 + ox] = v;
-          float m = v;
+          if (p.part) {                            // warp-uniform
+            float m = v;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-          float e = ptx_ex2((v - m) * kLog2e);
-          if (m == -INFINITY) e = 0.f;             // a row of -inf logits carries no weight (and no NaN)
-          float se = e, sl = e * (float)lane;
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            float e = ptx_ex2((v - m) * kLog2e);
+            if (m == -INFINITY) e = 0.f;           // a row of -inf logits carries no weight (and no NaN)
+            float se = e, sl = e * (float)lane;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            se += __shfl_xor_sync(0xffffffffu, se, o);
-            sl += __shfl_xor_sync(0xffffffffu, sl, o);
+            for (int o = 16; o > 0; o >>= 1) {
+              se += __shfl_xor_sync(0xffffffffu, se, o);
+              sl += __shfl_xor_sync(0xffffffffu, sl, o);
+            }
+            if (lane == j) { rec_m = m; rec_s = se; rec_l = sl; }
           }
-          if (lane == j) { rec_m = m; rec_s = se; rec_l = sl; }
         }
       }
       if (p.part && lane < J) p.part[((size_t)img * J + lane) * kTailSlots + slot] = make_float4(rec_m, rec_s, rec_l, 0.f);

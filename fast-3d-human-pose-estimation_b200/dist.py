@@ -67,6 +67,49 @@ def gather_results(xyz_local, sums_local, n_total, group=None):
     return unpack_results(out, n_total, joints, world)
 
 
+class GatherBuffer:
+    """The result exchange without a single packing kernel: one pre-allocated device buffer of `world` fixed-size
+    slots, [ (per, J, 3) fp32 3D joints | pad to 8 bytes | 4 fp64 MPJPE sums ].  The head writes this rank's 3D joints
+    straight into ``xyz_slot`` (``CDRNet.head(..., out_xyz=...)``), ``mpjpe_sums(..., out=sums_slot)`` lands in its
+    trailing 32 bytes, ``all_gather()`` is ONE in-place NCCL all-gather of the buffer (capturable in a CUDA graph:
+    fixed pointers), and ``to_host()`` is one D2H copy; unpacking — slicing off short tail shards, adding the sums in
+    rank order — happens on the host on views of the pinned copy."""
+
+    def __init__(self, n_total, joints, device, group=None, rank=None, world=None):
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
+        self.group, self.n_total, self.joints = group, n_total, joints
+        self.per = -(-n_total // self.world)
+        self.body = -(-(self.per * joints * 12) // 8) * 8
+        self.msg = self.body + _SUM_BYTES
+        self.buf = torch.zeros(self.world * self.msg, dtype=torch.uint8, device=device)
+        lo, hi = shard_range(n_total, self.rank, self.world)
+        self.n_local = hi - lo
+        mine = self.buf[self.rank * self.msg:(self.rank + 1) * self.msg]
+        self.slot = mine
+        self.xyz_slot = mine[: self.n_local * joints * 12].view(torch.float32).view(self.n_local, joints, 3)
+        self.sums_slot = mine[self.body:].view(torch.float64)
+        self.host = torch.zeros(self.world * self.msg, dtype=torch.uint8).pin_memory() if device.type == "cuda" else \
+            torch.zeros(self.world * self.msg, dtype=torch.uint8)
+
+    def all_gather(self):
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.buf, self.slot, group=self.group)      # in place: slot is buf[rank]
+
+    def to_host(self):
+        self.host.copy_(self.buf, non_blocking=True)
+
+    def unpack_host(self):
+        """After the copy has completed: (xyz (n_total,J,3) float32, sums (4,) float64), views / sums of the host copy."""
+        g = self.host.view(self.world, self.msg)
+        xyz = g[:, : self.per * self.joints * 12].contiguous().view(torch.float32).view(self.world * self.per, self.joints, 3)
+        parts = g[:, self.body:].contiguous().view(torch.float64).view(self.world, 4)
+        sums = parts[0].clone()
+        for r in range(1, self.world):          # fixed order -> bit-reproducible
+            sums += parts[r]
+        return xyz[: self.n_total], sums
+
+
 def mpjpe_from_sums(sums):
     """(error_2d, error_3d) of models/metrics.py:90-95 from the global sums."""
     s = sums.detach().cpu().double()

@@ -32,10 +32,11 @@ def _is_f32(a):
     return (a.dtype == torch.float32) if isinstance(a, torch.Tensor) else (a.dtype == np.float32)
 
 
-def mpjpe_sums(pred_2ds, pred_3ds, gt_3d, gt_2d_left, gt_2d_right, target_weight=None, device=None):
+def mpjpe_sums(pred_2ds, pred_3ds, gt_3d, gt_2d_left, gt_2d_right, target_weight=None, device=None, out=None):
     """Device-side partial sums: returns a (4,) float64 CUDA tensor
     [sum ||d2d_left||, sum ||d2d_right||, sum ||d3d||, n_poses * n_joints] — the quantity that is
-    all-reduced across ranks in the multi-GPU path (dist.py)."""
+    gathered across ranks in the multi-GPU path (dist.py).  ``out``: a (4,) float64 CUDA tensor to write into
+    (e.g. the trailing 32 bytes of this rank's gather slot)."""
     p3 = pred_3ds
     if isinstance(p3, torch.Tensor) and p3.is_cuda and device is None:
         device = p3.device
@@ -64,7 +65,12 @@ def mpjpe_sums(pred_2ds, pred_3ds, gt_3d, gt_2d_left, gt_2d_right, target_weight
         else:
             raise ValueError(f"target_weight has {w.numel()} elements; expected J={j} or n*J={n * j}")
     L = _lib.lib()
-    sums = torch.empty(4, dtype=torch.float64, device=device)
+    if out is not None:
+        if not (out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and out.numel() == 4):
+            raise ValueError("out must be a contiguous (4,) float64 CUDA tensor")
+        sums = out
+    else:
+        sums = torch.empty(4, dtype=torch.float64, device=device)
     scratch = torch.empty(L.cdr_mpjpe_scratch_bytes(n), dtype=torch.uint8, device=device)
     with torch.cuda.device(device):
         _lib.check(L.cdr_mpjpe_partial(

@@ -64,6 +64,7 @@ def test_peaks_and_constants():
     assert p["hbm_gbs"] > 1000 and p["tflops_sustained"] <= p["tflops_burst"]
     # algorithmic work per stereo pair: decoder 7595.9 MF, fused soft-argmax + DLT 623 220 B
     dec = sum(b.FLOP_PER_PAIR[k] for k in ("deconv1", "deconv2", "deconv3", "final_1x1"))
+    assert b.FLOP_PER_PAIR["deconv3_tail"] == b.FLOP_PER_PAIR["deconv3"] + b.FLOP_PER_PAIR["final_1x1"]
     assert abs(dec - 7595.9e6) < 1e5 and b.SOFTARGMAX_DLT_BYTES_PER_POSE == 2 * 19 * 4096 * 4 + 96 + 304 + 228
     t = b.ncu_traffic()
     assert "fp32" in t and t["fp32"]["deconv3"] > 5e8 and json.dumps(t)

@@ -94,3 +94,36 @@ def test_pack_unpack_roundtrip_single_rank():
     sums = torch.tensor([1.5, 2.5, 3.5, 95.0], dtype=torch.float64)
     out, s = cdist.gather_results(xyz, sums, 5)
     assert torch.equal(out, xyz) and torch.equal(s, sums)
+
+
+def _gbuf_worker(rank, world, port, n_total, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = cdist.GatherBuffer(n_total, 19, torch.device("cpu"))
+        lo, hi = cdist.shard_range(n_total, rank, world)
+        ref = torch.arange(n_total * 19 * 3, dtype=torch.float32).reshape(n_total, 19, 3) * 0.5
+        g.xyz_slot.copy_(ref[lo:hi])                       # what CDRNet.head(out_xyz=...) does on the GPU
+        g.sums_slot.copy_(torch.tensor([1.0 + rank, 2.0 * rank, 0.25, float((hi - lo) * 19)], dtype=torch.float64))
+        g.all_gather()                                     # ONE in-place collective, no packing kernels
+        g.to_host()
+        xyz, sums = g.unpack_host()
+        ret[rank] = (xyz.numpy().copy(), sums.numpy().copy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [5, 4, 1])
+def test_gather_buffer_inplace_allgather(n_total):
+    """dist.GatherBuffer: results written straight into this rank's slot, one in-place all-gather, host-side unpack
+    (ragged and empty tail shards included)."""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_gbuf_worker, args=(world, _free_port(), n_total, ret), nprocs=world, join=True)
+    ref = (torch.arange(n_total * 19 * 3, dtype=torch.float32).reshape(n_total, 19, 3) * 0.5).numpy()
+    for r in range(world):
+        xyz, sums = ret[r]
+        assert np.array_equal(xyz, ref)
+        assert sums[3] == n_total * 19 and sums[0] == sum(1.0 + q for q in range(world)) and sums[2] == 0.25 * world
+    assert np.array_equal(ret[0][1], ret[1][1])

@@ -819,3 +819,63 @@ def test_poseresnet_tc_encoder_baseline_path(cuda_pkg, precision):
     P2 = np.concatenate([P["P_r"], np.tile([[[0, 0, 0, 1.0]]], (n // 2, 1, 1))], 1).astype(np.float64)
     xyz = cuda_pkg.triangulation(torch.from_numpy(P1), torch.from_numpy(P2), pts[: n // 2], pts[n // 2:])
     assert tuple(xyz.shape) == (n // 2, joints, 3) and bool(torch.isfinite(xyz).all())
+
+
+@pytest.mark.parametrize("precision,b", [("bf16", 3), ("fp32", 3), ("fp32", 64), ("bf16", 64)])
+def test_fused_decoder_tail_matches_unfused_and_oracle(cuda_pkg, precision, b, monkeypatch):
+    """deconv3 -> ReLU -> final 1x1 -> soft-argmax partials as ONE kernel (tail_tc.cuh: second tcgen05.mma on the ReLU'd
+    tile, per-row online-softmax partials merged in fp64) against the three-launch path of the same library
+    (CDR_FUSED_TAIL=0) — heat-maps to accumulation-order rounding, 2D joints <= 1e-4 px — and, at B = 3, against the
+    fp64 oracle with the flat tolerance."""
+    sd = synth.make_head_state_dict(seed=0, calibrated=True, randomize_bn=True)
+    feats, cams = synth.make_features(b, seed=1), synth.make_cameras(b, seed=2)
+    m = _model(cuda_pkg, sd, precision=precision)
+    L = cuda_pkg._lib.lib()
+    monkeypatch.setenv("CDR_FUSED_TAIL", "1")
+    (kl, kr), xyz, taps = _run_head(m, feats, cams, taps=True)      # (the first call also packs the weights)
+    L.cdr_launch_count_reset()
+    (kl_nt, kr_nt), xyz_nt = _run_head(m, feats, cams)              # without taps: heat-maps never written
+    n_fused = L.cdr_launch_count()
+    monkeypatch.setenv("CDR_FUSED_TAIL", "0")
+    (ul, ur), uxyz, utaps = _run_head(m, feats, cams, taps=True)
+    L.cdr_launch_count_reset()
+    _run_head(m, feats, cams)
+    n_unfused = L.cdr_launch_count()
+    monkeypatch.setenv("CDR_FUSED_TAIL", "1")
+    assert torch.equal(kl, kl_nt) and torch.equal(kr, kr_nt) and torch.equal(xyz, xyz_nt)
+    hm, uhm = taps["heatmaps"], utaps["heatmaps"]
+    rel = float((hm - uhm).abs().max() / uhm.abs().max())
+    d2 = max(float((kl - ul).abs().max()), float((kr - ur).abs().max()))
+    print(f"\nfused tail [{precision}, B={b}]: heat-maps vs unfused rel {rel:.2e}, 2D {d2:.2e} px; launches {n_fused} vs {n_unfused}")
+    assert rel <= (1e-6 if precision == "fp32" else 1e-5)
+    assert d2 <= 1e-4
+    assert n_fused < n_unfused
+    if b <= 4:
+        o2, o3 = _oracle64(sd, feats, cams)
+        d2o = max(np.abs(kl.cpu().numpy() - o2[0]).max(), np.abs(kr.cpu().numpy() - o2[1]).max())
+        print(f"fused tail [{precision}] vs fp64 oracle: d2D {d2o:.2e} px")
+        if precision == "fp32":
+            assert d2o <= TOL_2D_PX
+            check_3d(cams, kl, kr, xyz, o2, o3, f"fused tail B={b}:")
+        else:
+            assert d2o <= 1.0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_tail_decoder_only_heatmaps(cuda_pkg, precision, monkeypatch):
+    """PoseDecoder.forward (PoseResNet's decoder half) through the fused tail: same heat-maps as the unfused path."""
+    n, joints = 3, 19
+    sd = synth.make_head_state_dict(seed=3, joints=joints, calibrated=True, randomize_bn=True, decoder_only=True)
+    feats = synth.make_features(n, seed=4)[0].cuda()
+    dec = cuda_pkg.PoseDecoder(synth.make_cfg(18, joints), precision=precision)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items()})
+    dec = dec.cuda().eval()
+    monkeypatch.setenv("CDR_FUSED_TAIL", "1")
+    a = dec(feats)
+    monkeypatch.setenv("CDR_FUSED_TAIL", "0")
+    bb = dec(feats)
+    monkeypatch.setenv("CDR_FUSED_TAIL", "1")
+    torch.cuda.synchronize()
+    rel = float((a - bb).abs().max() / bb.abs().max())
+    print(f"\nfused tail decoder-only [{precision}]: heat-maps vs unfused rel {rel:.2e}")
+    assert rel <= (1e-6 if precision == "fp32" else 1e-5)
