@@ -285,12 +285,18 @@ def measure(args, precision, ctx):
     model.load_state_dict(ctx["sd"], strict=False)
     model = model.to(dev).eval()
 
+    # N > 1: the 3D joints and MPJPE sums land directly in this rank's slot of a pre-allocated gather buffer; the ONE
+    # collective of the path is an in-place ncclAllGather of that buffer — no packing / unpacking kernels (dist.GatherBuffer)
+    gb = cdist.GatherBuffer(n_total, JOINTS, dev) if world > 1 else None
+
     def step(f, p):
-        (kl, kr), xyz = model.head(f, p)
-        sums = pkg.mpjpe_sums([kl, kr], xyz, g3, g2l, g2r, vis)
-        if world > 1:
-            return cdist.gather_results(xyz, sums, n_total)
-        return xyz, sums
+        if gb is None:
+            (kl, kr), xyz = model.head(f, p)
+            return xyz, pkg.mpjpe_sums([kl, kr], xyz, g3, g2l, g2r, vis)
+        (kl, kr), xyz = model.head(f, p, out_xyz=gb.xyz_slot)
+        pkg.mpjpe_sums([kl, kr], xyz, g3, g2l, g2r, vis, out=gb.sums_slot)
+        gb.all_gather()
+        return gb
 
     def barrier():
         if world > 1:
@@ -327,7 +333,13 @@ def measure(args, precision, ctx):
     launches = L.cdr_launch_count()
     dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
     clocks = sampler.stop(t_region0, t_region0 + t_wall) if rank == 0 else None
-    xyz, sums = out
+    if gb is not None:                      # outside the timed region: one D2H of the gathered buffer, host-side unpack
+        gb.to_host()
+        torch.cuda.synchronize()
+        xyz, sums = gb.unpack_host()
+        xyz, sums = xyz.clone(), sums.clone()
+    else:
+        xyz, sums = out
     e2d, e3d = cdist.mpjpe_from_sums(sums)
 
     # ---- N > 1, outside every timed region: the gathered result of the sharded run against an UNSHARDED recompute —
@@ -343,8 +355,8 @@ def measure(args, precision, ctx):
             (kl_r, kr_r), x_r = model.head(f_r, P_r)
             ss += pkg.mpjpe_sums([kl_r, kr_r], x_r, *[torch.from_numpy(gt_r[k]).to(dev) for k in ("gt3d", "gt2d_l", "gt2d_r", "vis")])
             xs.append(x_r)
-        x_all = torch.cat(xs, 0)
-        torch.cuda.synchronize()
+        x_all = torch.cat(xs, 0).cpu()
+        ss = ss.cpu()
         shard_check = {"sharded_equals_unsharded": bool(torch.equal(x_all, xyz) and torch.equal(ss, sums)),
                        "xyz_max_abs_diff_mm": float((x_all - xyz).abs().max()),
                        "mpjpe_sums_max_abs_diff": float((ss - sums).abs().max()), "pairs": int(x_all.shape[0]),
@@ -361,23 +373,23 @@ def measure(args, precision, ctx):
     # stream, one CUDA graph (head -> MPJPE sums -> D2H of 2D/3D joints + sums) on the compute stream;
     # batch i+1 crosses PCIe while batch i computes (depth 2).  Every step copies its inputs in and its
     # results out; a step's results are read on the host one submit later.
-    pipe = pkg.HeadPipeline(model, B, gt={"gt3d": g3, "gt2d_l": g2l, "gt2d_r": g2r, "vis": vis})
+    pipe = pkg.HeadPipeline(model, B, gt={"gt3d": g3, "gt2d_l": g2l, "gt2d_r": g2r, "vis": vis},
+                            gather_total=n_total if world > 1 else None)
+    if world > 1:
+        d2h = pipe.gather[0].host.numel()              # the gathered buffer: N slots of (B,19,3) fp32 + 32 B
 
-    def post(slot):
-        if world > 1:
-            x, s = cdist.gather_results(pipe.xyz_dev[slot], pipe.sums_dev[slot], n_total)
-            xyz_h.copy_(x, non_blocking=True)
-            sums_h.copy_(s, non_blocking=True)
+    def first(res):                                    # the caller reads every step's result on the host
+        return float(res.host[:4].view(torch.float32)[0]) if world > 1 else float(res[0, 0, 0])
 
     def e2e_run(k):
         checksum = 0.0
-        pipe.submit(feats_h, P_h, post)
+        pipe.submit(feats_h, P_h)
         for _ in range(k - 1):
-            pipe.submit(feats_h, P_h, post)
+            pipe.submit(feats_h, P_h)
             _, _, x_h, s_h = pipe.collect()
-            checksum += float(x_h[0, 0, 0])            # the caller reads every step's result
+            checksum += first(x_h)
         _, _, x_h, s_h = pipe.collect()
-        return checksum + float(x_h[0, 0, 0])
+        return checksum + first(x_h)
     e2e_run(3)
     barrier()
     e_s.record()
@@ -385,6 +397,33 @@ def measure(args, precision, ctx):
     e_e.record()
     barrier()
     e2e_ms = e_s.elapsed_time(e_e)
+    # bf16 head: the same end-to-end step fed bf16 pixel-major latent rows from the host (what a bf16 producer holds; the
+    # bf16 head rounds fp32 latents to bf16 anyway) — half the PCIe bytes of the reference-shaped fp32 tensors
+    e2e_rows = None
+    if precision == "bf16" and world == 1:
+        rows_h = torch.cat([f.permute(0, 2, 3, 1).reshape(-1, 2048) for f in feats_h], 0).to(torch.bfloat16).contiguous().pin_memory()
+        pipe_r = pkg.HeadPipeline(model, B, gt={"gt3d": g3, "gt2d_l": g2l, "gt2d_r": g2r, "vis": vis}, latents="rows_bf16")
+
+        def rows_run(k):
+            pipe_r.submit(rows_h, P_h)
+            for _ in range(k - 1):
+                pipe_r.submit(rows_h, P_h)
+                x = pipe_r.collect()[2]
+                float(x[0, 0, 0])
+            return float(pipe_r.collect()[2][0, 0, 0])
+        rows_run(3)
+        torch.cuda.synchronize()
+        r_s, r_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r_s.record()
+        rows_run(K)
+        r_e.record()
+        torch.cuda.synchronize()
+        r_ms = r_s.elapsed_time(r_e) / K
+        e2e_rows = {"value": B / (r_ms / 1e3), "unit": UNIT, "ms_per_step": r_ms,
+                    "h2d_bytes_per_step": rows_h.numel() * 2 + sum(t.numel() * 4 for t in P_h),
+                    "api": "HeadPipeline(latents='rows_bf16'): bf16 pixel-major latent rows (2B*64, 2048) from pinned host memory"}
+        pipe_r.close()
+        del pipe_r
     # latency form (no cross-step overlap): one CUDA graph of H2D -> head -> D2H, synchronised per step
     hg = pkg.HeadGraph(model, feats_h, P_h, gt={"gt3d": g3, "gt2d_l": g2l, "gt2d_r": g2r, "vis": vis})
     for _ in range(2):
@@ -481,7 +520,9 @@ def measure(args, precision, ctx):
         "value": value, "ms_per_step": dev_ms / K, "dtype": precision,
         "e2e": {"value": n_total * K / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
-                "api": "HeadPipeline (depth-2: H2D of batch i+1 overlaps compute of batch i)",
+                "api": "HeadPipeline (depth-2: H2D of batch i+1 overlaps compute of batch i)"
+                       + ("; in-place all-gather %s" % ("captured in the step's CUDA graph" if pipe.gather_in_graph
+                                                        else "issued after the graph replay") if world > 1 else ""),
                 "unpipelined_ms_per_step": e2e_latency_ms},
         "gpu_launches": int(launches), "launches_per_step": launches / K,
         "roofline": roof, "roofline_hbm": hbm, "stages_ms": stage_ms,
@@ -489,7 +530,7 @@ def measure(args, precision, ctx):
         "head_tflops": HEAD_FLOP_PER_PAIR * value / 1e12,
         "clocks": clocks, "wall_s_timed_region": t_wall, "sustained": sustained,
         "mpjpe": {"error_2d_px": e2d, "error_3d_mm": e3d},
-        "sharded_check": shard_check,
+        "sharded_check": shard_check, "e2e_bf16_rows": e2e_rows,
     }
 
 

@@ -65,6 +65,13 @@ template <int KIND> struct TailSmem {
 };
 constexpr int kTailThreads = 32 * 14;     // producer, MMA issuer, 8 convert warps, 4 heat warps
 
+__device__ __forceinline__ void tail_st(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+#ifdef CDR_EXP_TAIL_NO_HANDOFF   /* timing experiment: the converted tile is computed and dropped */
+  if (a == 0x12345678u && b == 0x9abcdef0u) ptx::st_shared_v4(addr, a, b, c, d);
+#else
+  ptx::st_shared_v4(addr, a, b, c, d);
+#endif
+}
 __device__ __forceinline__ float ptx_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // one MUFU.EX2, rel. error 2^-22
@@ -215,7 +222,14 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         ptx::tc_fence_after();
         const uint32_t t = r / Cfg::kRounds, j = r % Cfg::kRounds;
         const uint32_t acc = t & 1;
-        if constexpr (!kSplit) {
+#if defined(CDR_EXP_TAIL_NO_HANDOFF) || defined(CDR_EXP_TAIL_NO_HEAT_MMA)   /* timing experiments: results are wrong */
+        constexpr bool kHeatMma = false;
+#else
+        constexpr bool kHeatMma = true;
+#endif
+        if constexpr (!kHeatMma) {
+          (void)acc;
+        } else if constexpr (!kSplit) {
           const uint32_t d = tmem_base + acc * BN;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -345,6 +359,9 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     //   f16x2, column group 1       : group 0's round of tile tl             -> a2_empty[0], phase tl
     // ("phase -1" of a fresh barrier reads as complete.)
     auto wait_a2_free = [&]() {
+#ifdef CDR_EXP_TAIL_NO_HANDOFF
+      return;
+#endif
       if constexpr (!kSplit) ptx::mbar_wait(&a2_empty[0], (tl & 1) ^ 1u);
       else if (grp == 0) ptx::mbar_wait(&a2_empty[1], (tl & 1) ^ 1u);
       else ptx::mbar_wait(&a2_empty[0], tl & 1);
@@ -393,7 +410,7 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const uint32_t base = ptx::smem_u32(a2) + (uint32_t)(((cb0 + c) >> 6) * kABytes) + (uint32_t)row * 128u;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              ptx::st_shared_v4(base + (uint32_t)((j ^ (row & 7)) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+              tail_st(base + (uint32_t)((j ^ (row & 7)) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
           }
           publish_a2();
         } else {
@@ -451,8 +468,8 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint32_t o = (uint32_t)((j ^ (row & 7)) << 4);
-            ptx::st_shared_v4(base + o, wh[4 * j], wh[4 * j + 1], wh[4 * j + 2], wh[4 * j + 3]);
-            ptx::st_shared_v4(base + kABytes + o, wl[4 * j], wl[4 * j + 1], wl[4 * j + 2], wl[4 * j + 3]);
+            tail_st(base + o, wh[4 * j], wh[4 * j + 1], wh[4 * j + 2], wh[4 * j + 3]);
+            tail_st(base + kABytes + o, wl[4 * j], wl[4 * j + 1], wl[4 * j + 2], wl[4 * j + 3]);
           }
           publish_a2();
         }

@@ -149,7 +149,15 @@ class HeadPipeline(_GraphHolder):
     private workspace — legal because both replay on the one compute stream, in submission order.
     """
 
-    def __init__(self, model, batch, gt=None, img_size=256, warmup=2):
+    def __init__(self, model, batch, gt=None, img_size=256, warmup=2, gather_total=None, group=None, latents="nchw_f32"):
+        """latents: 'nchw_f32' — submit() takes the reference's two (B,2048,8,8) fp32 tensors (67 MB per 64 pairs
+        over PCIe); 'rows_bf16' — ONE pinned bf16 tensor (2*B*64, 2048) of pixel-major rows, left view first (what
+        the tcgen05 encoder emits and ``cdr_head_forward_rows`` consumes): half the host->device bytes, for
+        producers that already hold bf16 latents (the bf16 head rounds them to bf16 anyway).
+        gather_total: multi-GPU — the global number of stereo pairs; this rank's 3D joints and MPJPE sums are then
+        written straight into its slot of a ``dist.GatherBuffer`` and ONE in-place all-gather (captured in the step's
+        CUDA graph when NCCL allows, else issued right after the replay) + one D2H of the gathered buffer follow the
+        head; ``collect()`` hands the buffer back and ``.unpack_host()`` slices it on the host."""
         self.model = model
         self.dev = next(model.CF.parameters()).device
         self.gt, self.img_size, self.batch = gt, img_size, batch
@@ -157,13 +165,31 @@ class HeadPipeline(_GraphHolder):
         dev = self.dev
         self.copy_stream = torch.cuda.Stream(dev)
         self.compute_stream = torch.cuda.Stream(dev)
-        self.feats_dev = [[torch.empty((b, 2048, 8, 8), dtype=torch.float32, device=dev) for _ in range(2)] for _ in range(2)]
+        if latents not in ("nchw_f32", "rows_bf16"):
+            raise ValueError("latents must be 'nchw_f32' or 'rows_bf16'")
+        self.latents = latents
+        if latents == "rows_bf16":
+            self.feats_dev = [[torch.empty((2 * b * 64, 2048), dtype=torch.bfloat16, device=dev)] for _ in range(2)]
+        else:
+            self.feats_dev = [[torch.empty((b, 2048, 8, 8), dtype=torch.float32, device=dev) for _ in range(2)] for _ in range(2)]
         self.P_dev = [[torch.empty((b, 3, 4), dtype=torch.float32, device=dev) for _ in range(2)] for _ in range(2)]
         self.kp_host = [[torch.empty((b, j, 2), dtype=torch.float32).pin_memory() for _ in range(2)] for _ in range(2)]
         self.xyz_host = [torch.empty((b, j, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.xyz_dev = [torch.empty((b, j, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.gather = None
+        if gather_total is not None:
+            from .dist import GatherBuffer
+            self.gather = [GatherBuffer(gather_total, j, dev, group=group) for _ in range(2)]
+            if self.gather[0].n_local != b:
+                raise ValueError(f"this rank's shard of {gather_total} pairs is {self.gather[0].n_local}, pipeline batch is {b}")
+            self.xyz_dev = [g.xyz_slot for g in self.gather]
+        else:
+            self.xyz_dev = [torch.empty((b, j, 3), dtype=torch.float32, device=dev) for _ in range(2)]
         self.sums_host = [torch.empty(4, dtype=torch.float64).pin_memory() for _ in range(2)] if gt is not None else None
-        self.sums_dev = [torch.zeros(4, dtype=torch.float64, device=dev) for _ in range(2)] if gt is not None else None
+        if gt is not None:
+            self.sums_dev = [g.sums_slot for g in self.gather] if self.gather else \
+                [torch.zeros(4, dtype=torch.float64, device=dev) for _ in range(2)]
+        else:
+            self.sums_dev = None
         self.h2d_done = [torch.cuda.Event() for _ in range(2)]
         self.done = [torch.cuda.Event() for _ in range(2)]
         self.n_submitted = 0
@@ -171,6 +197,7 @@ class HeadPipeline(_GraphHolder):
         self._init_holder()
         cur = torch.cuda.current_stream(dev)
         self.compute_stream.wait_stream(cur)
+        self.gather_in_graph = self.gather is not None
         with torch.cuda.stream(self.compute_stream), _wsmod.scope(self._ws):
             for s in range(2):
                 for t in self.feats_dev[s] + self.P_dev[s]:
@@ -178,31 +205,57 @@ class HeadPipeline(_GraphHolder):
                 self.P_dev[s][0][:, :, :3] = torch.eye(3, device=dev)   # any full-rank P for the warm-up
                 self.P_dev[s][1][:, :, :3] = torch.eye(3, device=dev)
             for _ in range(max(1, warmup)):
-                self._compute(0)
+                self._compute(0)          # (also creates the NCCL communicator before any capture)
         torch.cuda.synchronize(dev)
         self._hold_weights(model)
+        try:
+            self._capture()
+        except Exception:
+            if not self.gather_in_graph:
+                raise
+            torch.cuda.synchronize(dev)
+            self.gather_in_graph = False          # this NCCL / torch build cannot capture the collective: issue it after the replay
+            self._capture()
+        torch.cuda.synchronize(dev)
+
+    def _capture(self):
         self.graphs = []
         for s in range(2):               # both graphs share this pipeline's workspace: they replay on ONE stream, in order
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self.compute_stream), _wsmod.scope(self._ws):
                 self._compute(s)
             self.graphs.append(g)
-        torch.cuda.synchronize(dev)
 
-    def _compute(self, s):
-        (kl, kr), xyz = self.model.head(self.feats_dev[s], self.P_dev[s], img_size=self.img_size)
-        self.xyz_dev[s].copy_(xyz)
+    def _gather(self, s):
+        self.gather[s].all_gather()
+        self.gather[s].to_host()
+
+    def _compute(self, s, in_capture=True):
+        rows = self.latents == "rows_bf16"
+        (kl, kr), xyz = self.model.head(None if rows else self.feats_dev[s], self.P_dev[s], img_size=self.img_size,
+                                        feat_rows=self.feats_dev[s][0] if rows else None,
+                                        out_xyz=self.xyz_dev[s] if self.gather else None)
+        if not self.gather:
+            self.xyz_dev[s].copy_(xyz)
+            self.xyz_host[s].copy_(xyz, non_blocking=True)
         self.kp_host[s][0].copy_(kl, non_blocking=True)
         self.kp_host[s][1].copy_(kr, non_blocking=True)
-        self.xyz_host[s].copy_(xyz, non_blocking=True)
         if self.gt is not None:
             g = self.gt
-            self.sums_dev[s].copy_(mpjpe_sums([kl, kr], xyz, g["gt3d"], g["gt2d_l"], g["gt2d_r"], g.get("vis")))
-            self.sums_host[s].copy_(self.sums_dev[s], non_blocking=True)
+            if self.gather:
+                mpjpe_sums([kl, kr], xyz, g["gt3d"], g["gt2d_l"], g["gt2d_r"], g.get("vis"), out=self.sums_dev[s])
+            else:
+                self.sums_dev[s].copy_(mpjpe_sums([kl, kr], xyz, g["gt3d"], g["gt2d_l"], g["gt2d_r"], g.get("vis")))
+                self.sums_host[s].copy_(self.sums_dev[s], non_blocking=True)
+        if self.gather and self.gather_in_graph:
+            self._gather(s)
 
     def submit(self, feats_host, P_host, post=None):
-        """Enqueue one batch (pinned fp32 host tensors).  `post(slot)` — optional — runs under the
-        compute stream after the head (e.g. the multi-GPU gather)."""
+        """Enqueue one batch: feats_host = the two pinned fp32 (B,2048,8,8) latents, or (latents='rows_bf16') one
+        pinned bf16 (2*B*64, 2048) tensor; P_host = [P_l, P_r] pinned fp32.  `post(slot)` — optional — runs under the
+        compute stream after the head."""
+        if isinstance(feats_host, torch.Tensor):
+            feats_host = [feats_host]
         if self.n_submitted - self.n_collected >= 2:
             raise RuntimeError("HeadPipeline: two batches already in flight — collect() first")
         self._check_weights()
@@ -215,6 +268,8 @@ class HeadPipeline(_GraphHolder):
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(self.h2d_done[s])
             self.graphs[s].replay()
+            if self.gather and not self.gather_in_graph:
+                self._gather(s)
             if post is not None:
                 post(s)
             self.done[s].record(self.compute_stream)
@@ -222,12 +277,16 @@ class HeadPipeline(_GraphHolder):
         return s
 
     def collect(self):
-        """Wait for the oldest batch in flight; returns (slot, kp_host list[2], xyz_host, sums_host)."""
+        """Wait for the oldest batch in flight; returns (slot, kp_host list[2], xyz_host, sums_host) — with
+        ``gather_total``: (slot, kp_host, GatherBuffer, None); ``GatherBuffer.unpack_host()`` gives the global
+        (xyz, sums)."""
         if self.n_collected >= self.n_submitted:
             raise RuntimeError("HeadPipeline: nothing in flight")
         s = self.n_collected % 2
         self.done[s].synchronize()
         self.n_collected += 1
+        if self.gather:
+            return s, self.kp_host[s], self.gather[s], None
         return s, self.kp_host[s], self.xyz_host[s], (self.sums_host[s] if self.sums_host is not None else None)
 
 

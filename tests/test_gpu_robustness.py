@@ -153,3 +153,31 @@ def test_second_device_in_one_process(cuda_pkg):
         torch.cuda.synchronize(dev)
         outs.append((kl.cpu(), xyz.cpu(), pts.cpu()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_pipeline_rows_latents_and_gather_buffer(cuda_pkg):
+    """HeadPipeline fed bf16 latent rows (half the H2D bytes) == the eager head on the same rows; with gather_total the 3D
+    joints and MPJPE sums land in this rank's slot of a dist.GatherBuffer (world 1 here: the collective is a no-op, the
+    in-place plumbing and the host-side unpack are what is checked; NCCL at N > 1: bench.py's sharded_check)."""
+    b = 3
+    sd = synth.make_head_state_dict(seed=0, calibrated=True)
+    m = _model(cuda_pkg, sd, precision="bf16")
+    feats = synth.make_features(b, seed=4)
+    cams = synth.make_cameras(b, seed=5)
+    gt = synth.make_gt(cams, seed=6)
+    gtd = {k: torch.from_numpy(gt[k]).cuda() for k in ("gt3d", "gt2d_l", "gt2d_r", "vis")}
+    P_h = [torch.from_numpy(cams["P_l"]).pin_memory(), torch.from_numpy(cams["P_r"]).pin_memory()]
+    rows_h = torch.cat([f.permute(0, 2, 3, 1).reshape(-1, 2048) for f in feats], 0).to(torch.bfloat16).contiguous().pin_memory()
+    (kl, kr), xyz = m.head(None, [p.cuda() for p in P_h], feat_rows=rows_h.cuda())
+    sums = cuda_pkg.mpjpe_sums([kl, kr], xyz, gtd["gt3d"], gtd["gt2d_l"], gtd["gt2d_r"], gtd["vis"])
+    torch.cuda.synchronize()
+    pipe = cuda_pkg.HeadPipeline(m, b, gt=gtd, latents="rows_bf16")
+    pipe.submit(rows_h, P_h)
+    _, kp_h, xyz_h, sums_h = pipe.collect()
+    assert torch.equal(kp_h[0], kl.cpu()) and torch.equal(xyz_h, xyz.cpu()) and torch.equal(sums_h, sums.cpu())
+    pipe2 = cuda_pkg.HeadPipeline(m, b, gt=gtd, latents="rows_bf16", gather_total=b)
+    for _ in range(2):
+        pipe2.submit(rows_h, P_h)
+        _, kp_h, gbuf, _ = pipe2.collect()
+        gx, gs = gbuf.unpack_host()
+        assert torch.equal(gx, xyz.cpu()) and torch.equal(gs, sums.cpu()) and torch.equal(kp_h[1], kr.cpu())
