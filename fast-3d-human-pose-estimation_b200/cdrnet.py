@@ -98,8 +98,9 @@ class PoseDecoder(nn.Module):
         _lib.check(L.cdr_decoder_workspace_bytes(handle, n, C.byref(nbytes)))
         ws = _workspace(x.device, nbytes.value)
         out = torch.empty((n, self.num_joints, 64, 64), dtype=torch.float32, device=x.device)
-        _lib.check(L.cdr_decoder_forward(handle, _lib.ptr(x), n, _lib.ptr(out), _lib.ptr(ws),
-                                         nbytes.value, _lib.current_stream_ptr(x.device)))
+        with torch.cuda.device(x.device):        # launches go to the CURRENT device: make it the tensors' device
+            _lib.check(L.cdr_decoder_forward(handle, _lib.ptr(x), n, _lib.ptr(out), _lib.ptr(ws),
+                                             nbytes.value, _lib.current_stream_ptr(x.device)))
         return out
 
     def forward_rows(self, rows):

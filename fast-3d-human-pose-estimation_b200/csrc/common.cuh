@@ -31,6 +31,7 @@ void timing_restart();
     if (_e != cudaSuccess) {                                                        \
       cdr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),        \
                      __FILE__, __LINE__);                                           \
+      (void)cudaGetLastError(); /* reported here: do not leave it for the next call's launch check */ \
       return CDR_ERR_CUDA;                                                          \
     }                                                                               \
   } while (0)

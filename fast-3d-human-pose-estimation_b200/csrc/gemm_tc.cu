@@ -124,11 +124,12 @@ template <> struct KindTraits<kKindBF16>   { static constexpr int kElem = 2, kBK
 template <> struct KindTraits<kKindTF32X3> { static constexpr int kElem = 4, kBK = 32, kPlanes = 2, kFmt = kFmtTF32P; };
 template <> struct KindTraits<kKindF16X2>  { static constexpr int kElem = 2, kBK = 64, kPlanes = 2, kFmt = kFmtF16P; };
 
-template <int BN, int KIND, int OFMT>
+template <int BN, int KIND, int OFMT, int CL = 0>
 struct TcCfg {
   static constexpr int kBK = KindTraits<KIND>::kBK;
   static constexpr int kPlanes = KindTraits<KIND>::kPlanes;
-  static constexpr int kBBytes = BN * 128;
+  static constexpr int kBRows = CL == 2 ? BN / 2 : BN;           // CL = 2 (cta_group::2): each CTA of the pair stages half of B
+  static constexpr int kBBytes = kBRows * 128;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   // Epilogue: 8 warps for wide tiles — two per TMEM lane quarter, each owning half of the columns —
   // because with short K loops (the 256-channel transposed convs: 16 K-blocks per tile) the epilogue,
@@ -344,16 +345,30 @@ constexpr int kSplitChunk = CDR_SPLIT_CHUNK;
 // traffic drops by a quarter.  Protocol: a stage may be refilled only when BOTH CTAs' MMAs have released
 // it, so empty[s] counts two arrivals and every release is a multicast commit to both CTAs; everything
 // else (TMEM, epilogue) stays per CTA.  Both CTAs run the same number of tiles (even n_tiles and grid).
+//
+// CL = 2: CTA pairs driving ONE tensor-core op (tcgen05.mma.cta_group::2, M = 256).  The pair takes two consecutive
+// 128-pixel blocks of the same output phase and N tile; each CTA stages its own A rows and HALF of the B tile (BN/2
+// weight rows), the leader (rank 0) issues every MMA for both, each CTA's accumulator rows live in its own TMEM and its
+// own epilogue warps drain them.  Per SM and MMA the tensor core then reads A + B/2 from shared memory instead of
+// A + B, and a stage shrinks from 64 to 48 KB (f16x2, BN = 128): 4 stages instead of 3.  Why it matters: with BN = 128
+// an MMA reads 8 KB of operands in the 64 cycles it computes — exactly the 128 B/clk the shared memory delivers, on
+// top of the TMA writes into the same memory (measured on the fused tail: 16 extra N = 32 MMAs per tile, 3 % of the
+// math but 8 % of the operand reads, cost 6.5 %).  Protocol: one "full" barrier per stage, the leader's — both CTAs'
+// TMA loads count their bytes on it (cp.async.bulk.tensor.cta_group::2); stage release, chunk / tile completion are
+// multicast commits to both CTAs' barriers; "accumulator drained" arrivals of the peer's epilogue warps go to the
+// leader's barriers through the cluster window (mapa + mbarrier.arrive.shared::cluster).
 template <int BN, int KIND, int OFMT, int CL>
-__global__ void __launch_bounds__(TcCfg<BN, KIND, OFMT>::kThreads, 1)
+__global__ void __launch_bounds__(TcCfg<BN, KIND, OFMT, CL>::kThreads, 1)
 tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
                    const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c_lo,
                    const __grid_constant__ CUtensorMap tmap_r, const TcGemmParams p) {
-  using Cfg = TcCfg<BN, KIND, OFMT>;
+  using Cfg = TcCfg<BN, KIND, OFMT, CL>;
   constexpr int S = Cfg::kStages;
   constexpr int kTcBK = Cfg::kBK;
   constexpr bool kSplit = KIND != kKindBF16;
+  constexpr bool kPair2 = CL == 2;
+  static_assert(!kPair2 || KIND != kKindTF32X3, "cta_group::2 is wired for the kind::f16 operand kinds");
 #ifdef CDR_EXP_NO_LO
   constexpr bool kLoadLo = false;   // timing experiment: hi planes only
 #else
@@ -398,23 +413,38 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&empty[s], CL ? 2 : 1);         // CL: released by the MMA issuers of both CTAs of the pair
+      ptx::mbar_init(&empty[s], CL == 1 ? 2 : 1);    // CL = 1: released by the MMA issuers of both CTAs of the pair
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], kEpiWarps);     // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty[a], kPair2 ? 2 * kEpiWarps : kEpiWarps);     // one arrive per epilogue warp (of both CTAs)
       ptx::mbar_init(&chunk_full[a], 1);
-      ptx::mbar_init(&chunk_empty[a], kEpiWarps);
+      ptx::mbar_init(&chunk_empty[a], kPair2 ? 2 * kEpiWarps : kEpiWarps);
     }
     for (int s = 0; s < S; ++s) res_cnt[s] = 0;
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_base_slot);
+  if (warp == 1) {
+    if constexpr (kPair2) ptx::tmem_alloc_2sm<Cfg::kTmemCols>(tmem_base_slot);
+    else ptx::tmem_alloc<Cfg::kTmemCols>(tmem_base_slot);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if constexpr (CL != 0) ptx::cluster_sync();       // the peer's barriers exist before anything is multicast
   ptx::tc_fence_after();
   const uint32_t cta_rank = CL ? ptx::cluster_ctarank() : 0u;
+  // tile walk: CL = 2 pairs walk PAIR tiles (two consecutive pixel blocks), everything else walks tiles
+  const int tile0 = kPair2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = kPair2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_m0 = [&](int tile) {
+    const int mt = tile / (p.n_tiles * p.groups);
+    return (kPair2 ? mt * 2 + (int)cta_rank : mt) * kTcBM;
+  };
+  // "this accumulator / chunk buffer is drained": to the leader's barrier when a pair shares one MMA issuer
+  auto arrive_issuer = [&](uint64_t* bar) {
+    if (kPair2 && cta_rank != 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(bar), 0));
+    else ptx::mbar_arrive(bar);
+  };
   // ... and do not touch anything the previous kernel wrote (activations, scale slots) before it is complete
   ptx::grid_dep_wait();
   const uint32_t tmem_base = *tmem_base_slot;
@@ -430,16 +460,41 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // ===================================================================== TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
         const int n_tile = tile % p.n_tiles;
         const int g = (tile / p.n_tiles) % p.groups;
-        const int m0 = (tile / (p.n_tiles * p.groups)) * kTcBM;
+        const int m0 = tile_m0(tile);
         const int py = g >> 1, px = g & 1;
         const int img0 = m0 / HW, y0 = (m0 - img0 * HW) / p.W;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t par = (it / S) & 1;
           ptx::mbar_wait(&empty[s], par ^ 1u);
+          if constexpr (kPair2) {
+            // both CTAs count their bytes on the LEADER's barrier of this stage; the leader expects the sum
+            const uint32_t full_leader = ptx::mapa_u32(ptx::smem_u32(&full[s]), 0);
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);
+            const int tap = kb / kb_per_tap;
+            const int k0 = (kb - tap * kb_per_tap) * kTcBK;
+            if (p.a4d) {
+              int dy = 0, dx = 0;
+              if (p.tap_mode == kTapDeconv) {
+                dy = py - (tap >> 1); dx = px - (tap & 1);
+              } else if (p.tap_mode == kTapConv3) {
+                dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1;
+              }
+              const int ys = p.stride * y0 + dy;
+              ptx::tma_load_4d_2sm(stage_a(s, 0), &tmap_a, full_leader, k0, dx, ys, img0);
+              if (kLoadLo) ptx::tma_load_4d_2sm(stage_a(s, 1), &tmap_a_lo, full_leader, k0, dx, ys, img0);
+            } else {
+              ptx::tma_load_2d_2sm(stage_a(s, 0), &tmap_a, full_leader, k0, g * p.a_group_rows + m0);
+              if (kLoadLo) ptx::tma_load_2d_2sm(stage_a(s, 1), &tmap_a_lo, full_leader, k0, g * p.a_group_rows + m0);
+            }
+            const int brow = g * p.b_group_rows + n_tile * BN + (int)cta_rank * (BN / 2);      // my half of the B tile
+            ptx::tma_load_2d_2sm(stage_b(s, 0), &tmap_b, full_leader, tap * p.cin + k0, brow);
+            if (kLoadLo) ptx::tma_load_2d_2sm(stage_b(s, 1), &tmap_b_lo, full_leader, tap * p.cin + k0, brow);
+            continue;
+          }
 #ifdef CDR_EXP_NO_LO
           ptx::mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes / (kSplit ? 2 : 1));
 #else
@@ -494,27 +549,33 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (CL = 2: the leader's, for the pair)
+    if (lane == 0 && (!kPair2 || cta_rank == 0)) {
       // instruction descriptor: D=f32, A/B format (kind::f16: 0 = f16, 1 = bf16; kind::tf32: 2), both K-major,
       // N=BN, M=128
       constexpr uint32_t fmt = KIND == kKindTF32X3 ? 2u : KIND == kKindBF16 ? 1u : 0u;
       constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                 ((uint32_t)(kTcBM >> 4) << 24);
+                                 ((uint32_t)((kPair2 ? 2 * kTcBM : kTcBM) >> 4) << 24);
       auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc_flag) {
         if constexpr (KIND == kKindTF32X3) ptx::umma_tf32(d, a, b, idesc, acc_flag);
+        else if constexpr (kPair2) ptx::umma_f16_2sm(d, a, b, idesc, acc_flag);
         else ptx::umma_f16(d, a, b, idesc, acc_flag);
+      };
+      // completion of everything issued so far -> `bar` (CL = 2: the barrier at that offset in BOTH CTAs)
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (kPair2) ptx::umma_commit_2sm_mc(bar, 3);
+        else ptx::umma_commit(bar);
       };
       // smem matrix descriptor (K-major, SWIZZLE_128B): LBO=1, SBO=1024 B, version=1, layout=2
       constexpr uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
                                    ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
       auto desc = [&](const uint8_t* ptr) { return desc_hi | (uint64_t)((ptx::smem_u32(ptr) >> 4) & 0x3FFF); };
       auto release_stage = [&](int s) {
-        if constexpr (CL != 0) ptx::umma_commit_mc(&empty[s], 3);   // the peer multicasts into this stage too
-        else ptx::umma_commit(&empty[s]);
+        if constexpr (CL == 1) ptx::umma_commit_mc(&empty[s], 3);   // the peer multicasts into this stage too
+        else commit(&empty[s]);
       };
       uint32_t it = 0, tl = 0, ch = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++tl) {
         const int acc = tl & 1;
         ptx::mbar_wait(&tmem_empty[acc], ((tl >> 1) & 1) ^ 1u);
         ptx::tc_fence_after();
@@ -555,10 +616,10 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               }
               release_stage(s);
             }
-            ptx::umma_commit(&chunk_full[buf]);    // main-term chunk ready to be drained
+            commit(&chunk_full[buf]);              // main-term chunk ready to be drained
           }
         }
-        ptx::umma_commit(&tmem_full[acc]);         // tile (bf16) / correction accumulator (split) complete
+        commit(&tmem_full[acc]);                   // tile (bf16) / correction accumulator (split) complete
         if constexpr (KIND == kKindBF16 && BN == 128) {
           if (p.has_res) {
             // The residual stage belongs to the epilogue, but this thread must still OBSERVE its phase: an
@@ -592,10 +653,10 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     const bool use_tma = Cfg::kTmaStore && p.out_mode != kOutPlanar;
     const float relu_floor = p.relu ? 0.f : -INFINITY;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++tl) {
       const int n_tile = tile % p.n_tiles;
       const int g = (tile / p.n_tiles) % p.groups;
-      const int m0 = (tile / (p.n_tiles * p.groups)) * kTcBM;
+      const int m0 = tile_m0(tile);
       const int acc = tl & 1;
       const int mw = m0 + q * 32;                  // first pixel of this warp
       const int m = mw + lane;                     // this thread's pixel
@@ -677,7 +738,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             // all TMEM reads of this accumulator are complete -> hand it back before the stores
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) arrive_issuer(&tmem_empty[acc]);
           }
           if constexpr (KIND == kKindBF16 && BN == 128) {
             if (p.has_res) {
@@ -730,7 +791,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&chunk_empty[buf]);
+          if (lane == 0) arrive_issuer(&chunk_empty[buf]);
         }
         ptx::mbar_wait(&tmem_full[acc], (tl >> 1) & 1);
         ptx::tc_fence_after();
@@ -747,7 +808,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) arrive_issuer(&tmem_empty[acc]);
         uint32_t wh[32], wl[32];
 #pragma unroll
         for (int c = 0; c < kCols; c += 64) {
@@ -783,7 +844,8 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if constexpr (CL != 0) ptx::cluster_sync();       // the peer's last stage releases arrive on OUR barriers
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if constexpr (kPair2) ptx::tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+    else ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -872,6 +934,17 @@ static bool tc_use_cluster() {
   }
   return v == 1;
 }
+// cta_group::2 pairs (kernel template parameter CL = 2): CDR_CTA_PAIR=0 turns them off for A/B timing.  The pair takes
+// two consecutive 128-pixel blocks: an even number of pixel blocks, no residual, unit stride.
+static bool tc_use_pair2() {
+  const char* e = getenv("CDR_CTA_PAIR");
+  return !(e && e[0] == '0');
+}
+static bool tc_pair2_ok(const TcLaunch& l) {
+  if (!tc_use_pair2() || l.res || l.stride > 1) return false;
+  const long long m = (long long)l.n_img * l.H * l.W;
+  return m % (2 * kTcBM) == 0;
+}
 // can this launch run as CTA pairs?  the pair shares one A tile: an even number of N tiles per pixel block
 static bool tc_cluster_ok(const TcLaunch& l, int bn) {
   if (!tc_use_cluster() || l.res || l.stride > 1 || (l.layer->n_pad / bn) % 2 != 0) return false;
@@ -887,7 +960,7 @@ static bool tc_cluster_ok(const TcLaunch& l, int bn) {
 
 template <int BN, int KIND, int OFMT, int CL = 0>
 static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
-  using Cfg = TcCfg<BN, KIND, OFMT>;
+  using Cfg = TcCfg<BN, KIND, OFMT, CL>;
   constexpr int kElem = KindTraits<KIND>::kElem;
   constexpr int kBK = Cfg::kBK;
   constexpr int kAFmt = KindTraits<KIND>::kFmt;
@@ -924,6 +997,11 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
   p.amax_out = l.out_slot.amax; p.scale_out = l.out_slot.scale;
   const int m_tiles = ceil_div(p.M, kTcBM);
   p.num_tiles = m_tiles * p.groups * p.n_tiles;
+  if (CL == 2) {                      // the kernel walks PAIR tiles: two consecutive pixel blocks each
+    CDR_CHECK_ARG(p.M % (2 * kTcBM) == 0 && !l.res && stride == 1, "tap_gemm_tc: cta_group::2 needs an even number of "
+                  "full 128-pixel blocks, unit stride and no residual");
+    p.num_tiles = (m_tiles / 2) * p.groups * p.n_tiles;
+  }
   CDR_CHECK_ARG(l.layer->bn == BN && l.layer->n_pad % BN == 0, "tap_gemm_tc: layer packed for BN=%d, launched with %d",
                 l.layer->bn, BN);
   CDR_CHECK_ARG(p.bias != nullptr, "tap_gemm_tc: every packed layer carries a (possibly zero) bias vector");
@@ -949,7 +1027,7 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
                     "tap_gemm_tc: unsupported tap-conv geometry");
       p.box_rows = rows; p.box_imgs = imgs;
       int brows = rows, bimgs = imgs;
-      if (CL) {                               // each CTA of a pair loads (and multicasts) half of the box
+      if (CL == 1) {                          // each CTA of a pair loads (and multicasts) half of the box
         CDR_CHECK_ARG(stride == 1 && (imgs >= 2 ? imgs % 2 == 0 : rows % 2 == 0), "tap_gemm_tc: box cannot be halved");
         if (imgs >= 2) { bimgs = imgs / 2; p.half_dim = 3; p.half_step = bimgs; }
         else { brows = rows / 2; p.half_dim = 2; p.half_step = brows; }
@@ -964,7 +1042,7 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
     } else {
       const uint64_t dims[2] = {(uint64_t)l.cin, (uint64_t)l.a_rows_total};
       const uint64_t strides[1] = {(uint64_t)l.a_pitch};
-      const uint32_t box[2] = {(uint32_t)kBK, (uint32_t)(CL ? kTcBM / 2 : kTcBM)};
+      const uint32_t box[2] = {(uint32_t)kBK, (uint32_t)(CL == 1 ? kTcBM / 2 : kTcBM)};
       if (int rc = make_tmap(&tmap_a[pl], l.A.p[pl], kAFmt, 2, dims, strides, box)) return rc;
     }
   }
@@ -1004,13 +1082,26 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
     const uint32_t box[3] = {64, 128, 1};     // half a residual tile: 128 rows x 64 channels
     if (int rc = make_tmap(&tmap_r, l.res, kFmtBF16, 3, dims, strides, box)) return rc;
   }
+  // weight maps: the layer's own (box = BN rows), or for cta_group::2 a box of BN/2 rows — each CTA stages its half
+  CUtensorMap tmap_b[2] = {l.layer->map[0], l.layer->map[KindTraits<KIND>::kPlanes - 1]};
+  if (CL == 2) {
+    for (int pl = 0; pl < KindTraits<KIND>::kPlanes; ++pl) {
+      const uint64_t dims[2] = {(uint64_t)l.layer->k, (uint64_t)l.layer->rows};
+      const uint64_t strides[1] = {(uint64_t)l.layer->k_pitch};
+      const uint32_t box[2] = {(uint32_t)kBK, (uint32_t)(BN / 2)};
+      if (int rc = make_tmap(&tmap_b[pl], l.layer->w[pl], kAFmt, 2, dims, strides, box)) return rc;
+    }
+    if (KindTraits<KIND>::kPlanes == 1) tmap_b[1] = tmap_b[0];
+  }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  if (CL == 2) grid = 2 * p.num_tiles < num_sms() ? 2 * p.num_tiles : num_sms();     // two CTAs per pair tile
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[2];
   int n_attr = 0;
   if (CL) {
-    // pairs: CTA 2i / 2i+1 take tiles t / t+1 = the two N tiles of one pixel block, for the same number of rounds
-    CDR_CHECK_ARG(p.n_tiles % 2 == 0 && !l.res, "tap_gemm_tc: CTA pairs need an even number of N tiles and no residual");
+    // CL = 1: CTA 2i / 2i+1 take tiles t / t+1 = the two N tiles of one pixel block, for the same number of rounds
+    if (CL == 1)
+      CDR_CHECK_ARG(p.n_tiles % 2 == 0 && !l.res, "tap_gemm_tc: CTA pairs need an even number of N tiles and no residual");
     grid &= ~1;
     attr[n_attr].id = cudaLaunchAttributeClusterDimension;
     attr[n_attr].val.clusterDim.x = 2;
@@ -1029,8 +1120,8 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
   cfg.stream = st;
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
-  CDR_CUDA(cudaLaunchKernelEx(&cfg, tap_gemm_tc_kernel<BN, KIND, OFMT, CL>, tmap_a[0], tmap_a[1], l.layer->map[0],
-                              l.layer->map[KindTraits<KIND>::kPlanes - 1], tmap_c[0], tmap_c[1], tmap_r, p));
+  CDR_CUDA(cudaLaunchKernelEx(&cfg, tap_gemm_tc_kernel<BN, KIND, OFMT, CL>, tmap_a[0], tmap_a[1], tmap_b[0], tmap_b[1],
+                              tmap_c[0], tmap_c[1], tmap_r, p));
   CDR_LAUNCH_OK("tap_gemm_tc_kernel");
   return CDR_OK;
 }
@@ -1039,6 +1130,7 @@ static int launch_tc(const TcLaunch& l, cudaStream_t st) {
   const int bn = l.layer->bn, kind = l.layer->kind;
   const int ofmt = l.out_mode == kOutPlanar ? kind_fmt(kind) : l.C.fmt;
   if (kind == kKindBF16 && ofmt == kFmtBF16) {
+    if (bn == 256 && getenv("CDR_BF16_PAIR") && tc_pair2_ok(l)) return launch_tc_t<256, kKindBF16, kFmtBF16, 2>(l, st);   // experiment
     if (bn == 256) return launch_tc_t<256, kKindBF16, kFmtBF16>(l, st);
     if (bn == 128) return launch_tc_t<128, kKindBF16, kFmtBF16>(l, st);
     if (bn == 64) return launch_tc_t<64, kKindBF16, kFmtBF16>(l, st);
@@ -1051,6 +1143,7 @@ static int launch_tc(const TcLaunch& l, cudaStream_t st) {
   } else if (kind == kKindF16X2 && ofmt == kFmtTF32P) {
     if (bn == 128) return launch_tc_t<128, kKindF16X2, kFmtTF32P>(l, st);
   } else if (kind == kKindF16X2 && ofmt == kFmtF16P) {
+    if (bn == 128 && tc_pair2_ok(l)) return launch_tc_t<128, kKindF16X2, kFmtF16P, 2>(l, st);
     if (bn == 128 && tc_cluster_ok(l, bn)) return launch_tc_t<128, kKindF16X2, kFmtF16P, 1>(l, st);
     if (bn == 128) return launch_tc_t<128, kKindF16X2, kFmtF16P>(l, st);
     if (bn == 32) return launch_tc_t<32, kKindF16X2, kFmtF16P>(l, st);
