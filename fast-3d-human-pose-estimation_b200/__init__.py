@@ -13,7 +13,7 @@ from ._lib import CdrError, build
 from .cdrnet import CDRNet, CanonicalFusion, PoseDecoder, PoseResNet
 from .encoder import ResNet
 from .graph import HeadGraph, HeadPipeline, FramePipeline
-from .geometry import baseline_keypoints, get_max_preds, triangulation
+from .geometry import baseline_keypoints, get_max_preds, projection_matrices, triangulation
 from .metrics import calc_mpjpe, mpjpe_sums
 from .autograd import soft_argmax_2d, dlt, ftl
 

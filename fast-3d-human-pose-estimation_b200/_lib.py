@@ -90,6 +90,7 @@ _SIGNATURES = {
     "cdr_encoder_forward_frames_u8": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int,
                                                 C.c_int, _vp, _vp, C.c_size_t, _vp]),
     "cdr_pinv": (C.c_int, [_vp, C.c_int, C.c_double, _vp, _vp]),
+    "cdr_projection_matrices": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "cdr_ftl": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
                           C.c_int, C.c_int, _vp]),
     "cdr_softargmax": (C.c_int, [_vp, C.c_longlong, C.c_int, C.c_int, C.c_float, _vp, _vp]),

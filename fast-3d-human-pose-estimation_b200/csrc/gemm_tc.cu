@@ -350,10 +350,12 @@ constexpr int kSplitChunk = CDR_SPLIT_CHUNK;
 // 128-pixel blocks of the same output phase and N tile; each CTA stages its own A rows and HALF of the B tile (BN/2
 // weight rows), the leader (rank 0) issues every MMA for both, each CTA's accumulator rows live in its own TMEM and its
 // own epilogue warps drain them.  Per SM and MMA the tensor core then reads A + B/2 from shared memory instead of
-// A + B, and a stage shrinks from 64 to 48 KB (f16x2, BN = 128): 4 stages instead of 3.  Why it matters: with BN = 128
-// an MMA reads 8 KB of operands in the 64 cycles it computes — exactly the 128 B/clk the shared memory delivers, on
-// top of the TMA writes into the same memory (measured on the fused tail: 16 extra N = 32 MMAs per tile, 3 % of the
-// math but 8 % of the operand reads, cost 6.5 %).  Protocol: one "full" barrier per stage, the leader's — both CTAs'
+// A + B, and a stage shrinks from 64 to 48 KB (f16x2, BN = 128): 4 stages instead of 3.  The idea: with BN = 128 an MMA
+// reads 8 KB of operands in the 64 cycles it computes — the 128 B/clk the shared memory delivers.  MEASURED on B200
+// (B = 64, parity green): f16x2 deconv1 / 2 / 3 344 / 176 / 674 us with the multicast pairs (CL = 1) -> 353 / 189 / 716 us
+// with cta_group::2 — 3-8 % SLOWER: the pair advances at the pace of its slower CTA and every chunk-buffer hand-back
+// crosses the cluster; bf16 (BN = 256) gains 2-3 % (111 -> 108, 212 -> 205 us).  Kept as an opt-in experiment
+// (CDR_CTA_PAIR=1 / CDR_BF16_PAIR=1), off by default.  Protocol: one "full" barrier per stage, the leader's — both CTAs'
 // TMA loads count their bytes on it (cp.async.bulk.tensor.cta_group::2); stage release, chunk / tile completion are
 // multicast commits to both CTAs' barriers; "accumulator drained" arrivals of the peer's epilogue warps go to the
 // leader's barriers through the cluster window (mapa + mbarrier.arrive.shared::cluster).
@@ -937,8 +939,8 @@ static bool tc_use_cluster() {
 // cta_group::2 pairs (kernel template parameter CL = 2): CDR_CTA_PAIR=0 turns them off for A/B timing.  The pair takes
 // two consecutive 128-pixel blocks: an even number of pixel blocks, no residual, unit stride.
 static bool tc_use_pair2() {
-  const char* e = getenv("CDR_CTA_PAIR");
-  return !(e && e[0] == '0');
+  const char* e = getenv("CDR_CTA_PAIR");      // opt-in: measured SLOWER than the multicast pairs on B200 (see the kernel comment)
+  return e && e[0] == '1';
 }
 static bool tc_pair2_ok(const TcLaunch& l) {
   if (!tc_use_pair2() || l.res || l.stride > 1) return false;
@@ -1240,7 +1242,20 @@ static int launch_tail_merge(const float4* part, const float* P_l, const float* 
   p.kp[0] = kp_l; p.kp[1] = kp_r;
   p.xyz = xyz;
   p.batch = batch; p.joints = joints; p.scale = scale;
-  tail_merge_dlt_kernel<<<batch, 256, 0, st>>>(p);
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  int n_attr = 0;
+  if (tc_use_pdl()) {           // its launch latency hides behind the tail kernel (which lets dependents launch early)
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  cfg.gridDim = dim3(batch);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = n_attr;
+  CDR_CUDA(cudaLaunchKernelEx(&cfg, tail_merge_dlt_kernel, p));
   CDR_LAUNCH_OK("tail_merge_dlt_kernel");
   return CDR_OK;
 }
@@ -1722,6 +1737,31 @@ __global__ void bf16_rows_to_tf32p_kernel(const __nv_bfloat16* __restrict__ in, 
   reinterpret_cast<float4*>(lo)[2 * i + 1] = z;
 }
 
+// A side stream per (host thread, device) for work that can overlap the main chain of a forward (the pseudo-inverses).
+// CDR_SIDE_LANE=0 keeps everything on the caller's stream.
+struct SideLane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static bool tc_use_side_lane() {
+  const char* e = getenv("CDR_SIDE_LANE");
+  return !(e && e[0] == '0');
+}
+static SideLane* side_lane() {
+  static thread_local SideLane lanes[kMaxDevices];
+  SideLane& l = lanes[current_device()];
+  if (!l.stream) {
+    if (cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) {
+      (void)cudaGetLastError();
+      l.stream = nullptr;
+      return nullptr;
+    }
+  }
+  return &l;
+}
+
 int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat_l, const float* feat_r, const float* P_l,
                     const float* P_r, const float* pinv_l, const float* pinv_r, double pinv_rtol,
                     int batch, float scale, float* kp2d_l, float* kp2d_r, float* xyz,
@@ -1739,8 +1779,20 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
   if (scaled) CDR_CUDA(cudaMemsetAsync(ws.slots, 0, 2 * kNumSlots * sizeof(float), st));
   set_stage("pinv");
   const float* pinv[2] = {pinv_l, pinv_r};
+  SideLane* lane = nullptr;
   if (!pinv_l) {
-    if ((rc = launch_pinv2(P_l, P_r, B, pinv_rtol, ws.pinv, st))) return rc;
+    // The pseudo-inverses (2B threads of fp64 Jacobi: ~14 us of pure latency) are not needed before the inverse
+    // FTL: they run on a side stream forked here and joined there, under the layout pass and conv_layer1.  The fork /
+    // join are plain event record / wait pairs, which a CUDA-graph capture of `st` turns into graph edges.
+    lane = tc_use_side_lane() ? side_lane() : nullptr;
+    cudaStream_t ps = st;
+    if (lane) {
+      CDR_CUDA(cudaEventRecord(lane->fork, st));
+      CDR_CUDA(cudaStreamWaitEvent(lane->stream, lane->fork, 0));
+      ps = lane->stream;
+    }
+    if ((rc = launch_pinv2(P_l, P_r, B, pinv_rtol, ws.pinv, ps))) return rc;
+    if (lane) CDR_CUDA(cudaEventRecord(lane->join, lane->stream));
     pinv[0] = ws.pinv;
     pinv[1] = ws.pinv + (size_t)B * 12;
   }
@@ -1780,6 +1832,7 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
     if ((rc = launch_tc(l, st))) return rc;
   }
   set_stage("ftl_inv");
+  if (lane) CDR_CUDA(cudaStreamWaitEvent(st, lane->join, 0));      // join: the pseudo-inverses are complete
   if ((rc = ftl_act2(ws.y1, act_offset(ws.y1, (size_t)B * kFeatHW * kHid1Pad), kHid1Pad, pinv, 4, 3, B, ws.z,
                      act_offset(ws.z, (size_t)kHid2), 2 * kHid2, kHid2, nullptr, st)))
     return rc;

@@ -167,9 +167,60 @@ static int reduce_pose_err(const double* pose_err, long long n, int joints, doub
   return CDR_OK;
 }
 
+// P = T * K * [R | t] (fp64, numpy's left-to-right order), first three rows as fp32 — what the model consumes:
+// tools/common.py:28-32 (get_projection_matrix: K @ hstack(R, T)), dataset/mads_3d.py:223-226 / tools/load.py:60-67
+// (T = eye(4) with the 2x3 crop/resize affine in its top-left: `T @ P`, resp. `trans @ K`), inference.py:53-56
+// (`numpy2torch(P[:3])`: float32).  One thread per camera.
+__global__ void projection_kernel(const double* __restrict__ K, int k_stride, const double* __restrict__ R,
+                                  const double* __restrict__ t, const double* __restrict__ trans, int n,
+                                  float* __restrict__ P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* k = K + (size_t)i * k_stride;
+  const double* r = R + (size_t)i * 9;
+  const double* tt = t + (size_t)i * 3;
+  double Rt[3][4], KP[3][4];
+  for (int a = 0; a < 3; ++a) {
+    for (int b = 0; b < 3; ++b) Rt[a][b] = r[a * 3 + b];
+    Rt[a][3] = tt[a];
+  }
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 4; ++b) {
+      double s = __dmul_rn(k[a * 3], Rt[0][b]);       // no FMA contraction: numpy rounds every product
+      s = __dadd_rn(s, __dmul_rn(k[a * 3 + 1], Rt[1][b]));
+      s = __dadd_rn(s, __dmul_rn(k[a * 3 + 2], Rt[2][b]));
+      KP[a][b] = s;
+    }
+  float* out = P + (size_t)i * 12;
+  if (trans) {
+    // T @ KP with T = [[a00 a01 a02 0] [a10 a11 a12 0] [0 0 1 0] [0 0 0 1]] and KP's 4th row = (0,0,0,1)
+    const double* m = trans + (size_t)i * 6;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 4; ++b) {
+        double s = __dmul_rn(m[a * 3], KP[0][b]);
+        s = __dadd_rn(s, __dmul_rn(m[a * 3 + 1], KP[1][b]));
+        s = __dadd_rn(s, __dmul_rn(m[a * 3 + 2], KP[2][b]));
+        out[a * 4 + b] = (float)s;
+      }
+    for (int b = 0; b < 4; ++b) out[8 + b] = (float)KP[2][b];
+  } else {
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 4; ++b) out[a * 4 + b] = (float)KP[a][b];
+  }
+}
+
 }  // namespace cdr
 
 using namespace cdr;
+
+extern "C" int cdr_projection_matrices(const double* K, int k_batched, const double* R, const double* t,
+                                       const double* trans, int n, float* P, void* stream) {
+  CDR_CHECK_ARG(K && R && t && P && n >= 0, "cdr_projection_matrices: null pointer or negative n");
+  if (n == 0) return CDR_OK;
+  projection_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(K, k_batched ? 9 : 0, R, t, trans, n, P);
+  CDR_LAUNCH_OK("projection_kernel");
+  return CDR_OK;
+}
 
 extern "C" int cdr_pinv(const float* P, int n, double rtol, float* pinv, void* stream) {
   CDR_CHECK_ARG(P && pinv && n >= 0, "cdr_pinv: null pointer or negative n");

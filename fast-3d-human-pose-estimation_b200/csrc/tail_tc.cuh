@@ -240,16 +240,20 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
         } else {
           const uint32_t nh = t % NH;           // tiles alternate between the two channel halves of a unit
+          // [hi.Wh | hi.Wl] in ONE N = 64 MMA: the hi and lo planes of the 32 final-layer rows are adjacent 32-row blocks
+          // in shared memory (one 64-row K-major tile) and their accumulators adjacent 32-column blocks in TMEM — the
+          // hi plane of A2 is read once instead of twice (the heat MMAs are bound by their operand reads: N = 32 computes
+          // in 16 cycles what takes 40 to read); lo.Wh then adds into the correction columns.
+          constexpr uint32_t idesc_heat64 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) |
+                                            ((uint32_t)(kTcBM >> 4) << 24);
           const uint32_t d_hm = tmem_base + (2 + acc) * BN, d_hc = d_hm + 32;
           const uint64_t da = desc(a2), dal = desc(a2 + kABytes);
-          const uint8_t* w = wf + (size_t)((nh * 2 + j) * 2) * 4096;
-          const uint64_t dw = desc(w), dwl = desc(w + 4096);
+          const uint64_t dw = desc(wf + (size_t)((nh * 2 + j) * 2) * 4096);      // rows 0-31 hi, 32-63 lo
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t o = (uint64_t)(2 * k);
-            ptx::umma_f16(d_hc, dal + o, dw + o, idesc_heat, (j | (uint32_t)k) != 0);   // lo * hi
-            ptx::umma_f16(d_hc, da + o, dwl + o, idesc_heat, 1u);                       // hi * lo
-            ptx::umma_f16(d_hm, da + o, dw + o, idesc_heat, (j | (uint32_t)k) != 0);    // hi * hi
+            ptx::umma_f16(d_hm, da + o, dw + o, idesc_heat64, (j | (uint32_t)k) != 0);   // hi * [hi ; lo]
+            ptx::umma_f16(d_hc, dal + o, dw + o, idesc_heat, 1u);                        // lo * hi
           }
         }
         ptx::umma_commit(&a2_empty[j]);
@@ -579,6 +583,7 @@ struct TailMergeParams {
 
 __global__ void __launch_bounds__(256) tail_merge_dlt_kernel(const TailMergeParams p) {
   __shared__ double kps[2 * kMaxJoints][2];
+  ptx::grid_dep_wait();         // launched with programmatic stream serialization: the tail kernel's records are complete
   const int pose = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int J = p.joints;

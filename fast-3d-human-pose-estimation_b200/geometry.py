@@ -92,3 +92,31 @@ def triangulation(P1, P2, pts1, pts2):
     if single:
         out = out[0]
     return out if is_tensor else out.cpu().numpy()
+
+
+def projection_matrices(K, R, T, trans=None, device=None):
+    """Per-camera projection matrices built on the device: ``P = A @ K @ [R | t]`` as the
+    reference's hosts build them — ``get_projection_matrix`` (tools/common.py:28-32), the crop / resize affine ``trans``
+    (2,3) of ``dataset/mads_3d.py:223-226`` / ``tools/load.py:60-67`` folded in as ``T @ P`` — first three rows,
+    float32 (``inference.py:53-56``).  K: (3,3) shared or (n,3,3); R: (n,3,3); T: (n,3) or (n,3,1); trans: (n,2,3) or
+    None.  numpy arrays or tensors in, (n,3,4) float32 CUDA tensor out — what ``CDRNet.forward`` takes as ``proj_list[v]``."""
+    dev = device if device is not None else _cuda_device()
+
+    def to64(a):
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64)))
+        return t.detach().to(device=dev, dtype=torch.float64).contiguous()
+    r = to64(R).reshape(-1, 3, 3)
+    n = r.shape[0]
+    t = to64(T).reshape(n, 3)
+    k = to64(K)
+    k_batched = int(k.dim() == 3)
+    if k.shape[-2:] != (3, 3) or (k_batched and k.shape[0] != n):
+        raise ValueError("K must be (3,3) or (n,3,3)")
+    a = None
+    if trans is not None:
+        a = to64(trans).reshape(n, 2, 3)
+    out = torch.empty((n, 3, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cdr_projection_matrices(_lib.ptr(k), k_batched, _lib.ptr(r), _lib.ptr(t), _lib.ptr(a), n,
+                                                      _lib.ptr(out), _lib.current_stream_ptr(dev)))
+    return out

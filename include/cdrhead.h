@@ -236,6 +236,14 @@ int cdr_softargmax_dlt(const void* heat_l, const void* heat_r, int heat_is_bf16,
 int cdr_argmax(const float* heat, long long n_maps, int H, int W, float scale, float* preds,
                float* maxvals, uint8_t* pts_u8, void* stream);
 
+/* Projection matrices on the device — tools/common.py:28-32 (get_projection_matrix: P = K @ [R | t]), the crop /
+ * resize affine of dataset/mads_3d.py:223-226 and tools/load.py:60-67 (T = eye(4), T[:2,:3] = trans; P = T @ P) and
+ * inference.py:53-56 (first three rows, float32).  K (3,3) fp64 shared (k_batched = 0) or per camera (n,3,3);
+ * R (n,3,3), t (n,3) fp64; trans (n,2,3) fp64 or NULL (T = identity) -> P (n,3,4) fp32, products and sums in fp64 in
+ * numpy's order. */
+int cdr_projection_matrices(const double* K, int k_batched, const double* R, const double* t, const double* trans,
+                            int n, float* P, void* stream);
+
 /* triangulation — tools/common.py:51-71.  P1/P2: fp64, `p_rows` x 4 row-major per sample
  * (3 or 4 rows; only the first three are read); p_batched = 0 shares one P pair across
  * all n_poses.  pts1/pts2 (n_poses,J,2) uint8 -> xyz (n_poses,J,3) fp64. */

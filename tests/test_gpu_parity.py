@@ -879,3 +879,30 @@ def test_fused_tail_decoder_only_heatmaps(cuda_pkg, precision, monkeypatch):
     rel = float((a - bb).abs().max() / bb.abs().max())
     print(f"\nfused tail decoder-only [{precision}]: heat-maps vs unfused rel {rel:.2e}")
     assert rel <= (1e-6 if precision == "fp32" else 1e-5)
+
+
+def test_projection_matrices_on_device(cuda_pkg):
+    """SURVEY §8f rank 2 remainder: P = T @ K @ [R | t] built on the device against the reference's host construction
+    (tools/common.py:28-32 get_projection_matrix, dataset/mads_3d.py:223-226 `T @ P`, inference.py:53-56 `[:3]` float32)."""
+    n = 37
+    cams = synth.make_cameras(n, seed=31)
+    rng = np.random.default_rng(32)
+    trans = np.stack([np.array([[s * np.cos(a), -s * np.sin(a), tx], [s * np.sin(a), s * np.cos(a), ty]])
+                      for s, a, tx, ty in zip(rng.uniform(0.3, 1.2, n), rng.uniform(-0.5, 0.5, n),
+                                              rng.uniform(-40, 40, n), rng.uniform(-40, 40, n))])
+    for view in ("l", "r"):
+        R, T = np.stack(cams[f"R_{view}"]), np.stack(cams[f"T_{view}"])
+        want_plain = np.stack([O.get_projection_matrix(cams["K"], R[i], T[i])[:3] for i in range(n)])
+        got = cuda_pkg.projection_matrices(cams["K"], R, T).cpu().numpy()
+        assert got.dtype == np.float32 and got.shape == (n, 3, 4)
+        assert np.array_equal(got, want_plain.astype(np.float32))
+        assert np.array_equal(got, cams[f"P_{view}"])                 # what every other test feeds the head
+        want_t = []
+        for i in range(n):
+            Tm = np.eye(4)
+            Tm[:2, :3] = trans[i]
+            want_t.append((Tm @ O.get_projection_matrix(cams["K"], R[i], T[i]))[:3])
+        got_t = cuda_pkg.projection_matrices(np.stack([cams["K"]] * n), torch.from_numpy(R), T, trans=trans).cpu().numpy()
+        want32 = np.stack(want_t).astype(np.float32)
+        ulp = np.abs(got_t.view(np.int32) - want32.view(np.int32)).max()
+        assert ulp <= 1, f"{ulp} ulp"                                  # BLAS may contract / reorder a sum; never more than 1 fp32 ulp
