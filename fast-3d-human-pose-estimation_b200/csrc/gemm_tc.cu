@@ -396,7 +396,9 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
   uint32_t* res_cnt = reinterpret_cast<uint32_t*>(bars + 2 * S + 9);   // [S] epilogue warps done with a residual stage
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: ptxas then KNOWS it is warp-uniform, so the role branches below are uniform control
+  // flow and whatever the MMA-issuer warp computes inside them can live in uniform registers (see the issuer)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   // Programmatic dependent launch: let the next tap-GEMM's CTAs take over SMs as ours retire (its barrier
@@ -552,7 +554,16 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (CL = 2: the leader's, for the pair)
-    if (lane == 0 && (!kPair2 || cta_rank == 0)) {
+    // The WHOLE warp runs this loop, converged; one elected lane issues the tcgen05 instructions.  Round 1 ran it as
+    // `if (lane == 0)`: inside that divergent region ptxas cannot prove any value uniform, and UTCHMMA takes its
+    // descriptors / TMEM address from UNIFORM registers — so every MMA was wrapped in an ELECT / R2UR.BROADCAST /
+    // BRA.U.ANY loop: 244 SASS instructions per K block of the f16x2 kernel, one thread, ~1650 cycles for 12 MMAs whose
+    // tensor-core floor is 768 (ncu source page, profiles/r02_*: the issuing warp never waited on a barrier, the TMA
+    // producer sat on a full ring, the epilogue warps on chunk_full — the kernel was ISSUE-bound).  Converged, the
+    // operands are warp-uniform by construction (kernel parameters, block index, loop counters, the TMEM base through
+    // a shuffle) and the loop shrinks to the MMAs plus a handful of uniform adds.
+    if (!kPair2 || cta_rank == 0) {
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       // instruction descriptor: D=f32, A/B format (kind::f16: 0 = f16, 1 = bf16; kind::tf32: 2), both K-major,
       // N=BN, M=128
       constexpr uint32_t fmt = KIND == kKindTF32X3 ? 2u : KIND == kKindBF16 ? 1u : 0u;
@@ -582,24 +593,27 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         ptx::mbar_wait(&tmem_empty[acc], ((tl >> 1) & 1) ^ 1u);
         ptx::tc_fence_after();
         if constexpr (!kSplit) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+          const uint32_t d_tmem = tb + (uint32_t)(acc * BN);
           for (int kb = 0; kb < num_kb; ++kb, ++it) {
             const int s = it % S;
             ptx::mbar_wait(&full[s], (it / S) & 1);
             ptx::tc_fence_after();
             const uint64_t da = desc(stage_a(s, 0)), db = desc(stage_b(s, 0));
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)    // +32 bytes (= 2 x 16 B) per K step (16 bf16) inside the swizzle row
-              mma(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (kb | k) != 0);
-            release_stage(s);                      // smem stage reusable once these MMAs retire
+              for (int k = 0; k < 4; ++k)    // +32 bytes (= 2 x 16 B) per K step (16 bf16) inside the swizzle row
+                mma(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (kb | k) != 0);
+              release_stage(s);                    // smem stage reusable once these MMAs retire
+            }
+            __syncwarp();
           }
         } else {
-          const uint32_t d_corr = tmem_base + (uint32_t)((2 + acc) * BN);
+          const uint32_t d_corr = tb + (uint32_t)((2 + acc) * BN);
           for (int kb0 = 0; kb0 < num_kb; kb0 += kSplitChunk, ++ch) {
             const int buf = ch & 1;
             ptx::mbar_wait(&chunk_empty[buf], ((ch >> 1) & 1) ^ 1u);
             ptx::tc_fence_after();
-            const uint32_t d_main = tmem_base + (uint32_t)(buf * BN);
+            const uint32_t d_main = tb + (uint32_t)(buf * BN);
             const int kb1 = kb0 + kSplitChunk < num_kb ? kb0 + kSplitChunk : num_kb;
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
               const int s = it % S;
@@ -607,24 +621,30 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               ptx::tc_fence_after();
               const uint64_t da = desc(stage_a(s, 0)), dal = desc(stage_a(s, 1));
               const uint64_t db = desc(stage_b(s, 0)), dbl = desc(stage_b(s, 1));
+              const uint32_t first = kb != 0, first_main = kb > kb0;
+              if (ptx::elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {        // K step = 8 tf32 / 16 f16 = 32 bytes
-                const uint64_t o = (uint64_t)(2 * k);
+                for (int k = 0; k < 4; ++k) {        // K step = 8 tf32 / 16 f16 = 32 bytes
+                  const uint64_t o = (uint64_t)(2 * k);
 #ifndef CDR_EXP_NO_CORR   /* timing experiment only: results are wrong without the correction terms */
-                mma(d_corr, dal + o, db + o, (kb | k) != 0);       // lo*hi  } whole-tile chain: these
-                mma(d_corr, da + o, dbl + o, 1u);                  // hi*lo  } terms are 2^-11 of the main one
+                  mma(d_corr, dal + o, db + o, k ? 1u : first);            // lo*hi  } whole-tile chain: these
+                  mma(d_corr, da + o, dbl + o, 1u);                        // hi*lo  } terms are 2^-11 of the main one
 #endif
-                mma(d_main, da + o, db + o, (kb > kb0 || k > 0));  // hi*hi, short chain
+                  mma(d_main, da + o, db + o, k ? 1u : first_main);        // hi*hi, short chain
+                }
+                release_stage(s);
               }
-              release_stage(s);
+              __syncwarp();
             }
-            commit(&chunk_full[buf]);              // main-term chunk ready to be drained
+            if (ptx::elect_one()) commit(&chunk_full[buf]);   // main-term chunk ready to be drained
+            __syncwarp();
           }
         }
-        commit(&tmem_full[acc]);                   // tile (bf16) / correction accumulator (split) complete
+        if (ptx::elect_one()) commit(&tmem_full[acc]);         // tile (bf16) / correction accumulator (split) complete
+        __syncwarp();
         if constexpr (KIND == kKindBF16 && BN == 128) {
           if (p.has_res) {
-            // The residual stage belongs to the epilogue, but this thread must still OBSERVE its phase: an
+            // The residual stage belongs to the epilogue, but this warp must still OBSERVE its phase: an
             // mbarrier wait can only tell the current phase from the one before it.  Skipping the phase let a
             // later wait on the same stage (S uses on) mistake "residual still loading" for "next K-block
             // landed" whenever the residual's HBM load outlasted S-1 K-blocks of MMAs — the tensor core then

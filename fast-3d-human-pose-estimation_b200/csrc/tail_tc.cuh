@@ -109,7 +109,7 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint64_t* wf_full = bars + 2 * S + 13;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 14);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (see the issuer)
   const int lane = threadIdx.x & 31;
 
   ptx::grid_dep_launch();
@@ -200,7 +200,11 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the loop converged and one elected lane issues (gemm_tc.cu explains why: inside an
+    // `if (lane == 0)` region ptxas wraps every UTCHMMA in an ELECT / R2UR.BROADCAST loop and the kernel becomes
+    // issue-bound).  Barrier polls that steer control flow are made warp-uniform with a vote.
+    {
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       constexpr uint32_t fmt = KIND == kKindBF16 ? 1u : 0u;
       constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
                                  ((uint32_t)(kTcBM >> 4) << 24);
@@ -227,16 +231,21 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #else
         constexpr bool kHeatMma = true;
 #endif
-        if constexpr (!kHeatMma) {
-          (void)acc;
-        } else if constexpr (!kSplit) {
-          const uint32_t d = tmem_base + acc * BN;
+        if constexpr (!kSplit) {
+          const uint32_t d = tb + acc * BN;
+          const uint64_t da0 = desc(a2), dw0 = desc(wf);
+          if (ptx::elect_one()) {
+            if constexpr (kHeatMma) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint64_t da = desc(a2 + c * kABytes), dw = desc(wf + c * 4096);
+              for (int c = 0; c < 4; ++c) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_f16(d, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc_heat, (c | k) != 0);
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_f16(d, da0 + (uint64_t)(c * (kABytes >> 4) + 2 * k), dw0 + (uint64_t)(c * (4096 >> 4) + 2 * k),
+                                idesc_heat, (c | k) != 0);
+              }
+            }
+            ptx::umma_commit(&a2_empty[j]);
+            ptx::umma_commit(&heat_full[acc]);
           }
         } else {
           const uint32_t nh = t % NH;           // tiles alternate between the two channel halves of a unit
@@ -246,27 +255,37 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           // in 16 cycles what takes 40 to read); lo.Wh then adds into the correction columns.
           constexpr uint32_t idesc_heat64 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) |
                                             ((uint32_t)(kTcBM >> 4) << 24);
-          const uint32_t d_hm = tmem_base + (2 + acc) * BN, d_hc = d_hm + 32;
+          const uint32_t d_hm = tb + (2 + acc) * BN, d_hc = d_hm + 32;
           const uint64_t da = desc(a2), dal = desc(a2 + kABytes);
-          const uint64_t dw = desc(wf + (size_t)((nh * 2 + j) * 2) * 4096);      // rows 0-31 hi, 32-63 lo
+          const uint64_t dw = desc(wf) + (uint64_t)(((nh * 2 + j) * 2) * (4096 >> 4));      // rows 0-31 hi, 32-63 lo
+          const uint32_t first = j != 0;
+          if (ptx::elect_one()) {
+            if constexpr (kHeatMma) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t o = (uint64_t)(2 * k);
-            ptx::umma_f16(d_hm, da + o, dw + o, idesc_heat64, (j | (uint32_t)k) != 0);   // hi * [hi ; lo]
-            ptx::umma_f16(d_hc, dal + o, dw + o, idesc_heat, 1u);                        // lo * hi
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t o = (uint64_t)(2 * k);
+                ptx::umma_f16(d_hm, da + o, dw + o, idesc_heat64, k ? 1u : first);         // hi * [hi ; lo]
+                ptx::umma_f16(d_hc, dal + o, dw + o, idesc_heat, 1u);                      // lo * hi
+              }
+            }
+            ptx::umma_commit(&a2_empty[j]);
+            if (j == Cfg::kRounds - 1) ptx::umma_commit(&heat_full[acc]);
           }
         }
-        ptx::umma_commit(&a2_empty[j]);
-        if (j == Cfg::kRounds - 1) ptx::umma_commit(&heat_full[acc]);
+        __syncwarp();
+      };
+      // has the next due hand-off round been written?  (a vote makes the answer — and the branch — warp-uniform)
+      auto round_ready = [&]() {
+        return rounds_issued < rounds_due && __all_sync(0xffffffffu, ptx::mbar_test_wait(a2_full, rounds_issued & 1));
       };
       auto poll_rounds = [&]() {
-        while (rounds_issued < rounds_due && ptx::mbar_test_wait(a2_full, rounds_issued & 1)) {
+        while (round_ready()) {
           issue_round(rounds_issued);
           ++rounds_issued;
         }
       };
-      auto flush_rounds = [&]() {
-        while (rounds_issued < rounds_due) {
+      auto force_rounds = [&](uint32_t upto) {
+        while (rounds_issued < upto) {
           ptx::mbar_wait(a2_full, rounds_issued & 1);
           issue_round(rounds_issued);
           ++rounds_issued;
@@ -276,43 +295,40 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         for (int nh = 0; nh < NH; ++nh, ++tl) {
           const uint32_t acc = tl & 1;
           // the heat of the tile that used this accumulator must have been issued before we can wait for its readers
-          if (tl >= 2) {
-            while (rounds_issued < (tl - 1) * Cfg::kRounds) {
-              ptx::mbar_wait(a2_full, rounds_issued & 1);
-              issue_round(rounds_issued);
-              ++rounds_issued;
-            }
-          }
+          if (tl >= 2) force_rounds((tl - 1) * Cfg::kRounds);
           ptx::mbar_wait(&tmem_empty[acc], ((tl >> 1) & 1) ^ 1u);
           ptx::tc_fence_after();
           if constexpr (!kSplit) {
-            const uint32_t d_tmem = tmem_base + acc * BN;
+            const uint32_t d_tmem = tb + acc * BN;
             for (int kb = 0; kb < kNumKb; ++kb, ++pos) {
               poll_rounds();
               const int s = pos % S;
               ptx::mbar_wait(&full[s], (pos / S) & 1);
               ptx::tc_fence_after();
               const uint64_t da = desc(slot_ptr(s)), db = desc(slot_ptr(s) + kABytes);
+              if (ptx::elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-              ptx::umma_commit(&empty[s]);
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                ptx::umma_commit(&empty[s]);
+              }
+              __syncwarp();
             }
           } else {
-            const uint32_t d_corr = tmem_base + (2 + acc) * BN;
+            const uint32_t d_corr = tb + (2 + acc) * BN;
             for (int kb0 = 0; kb0 < kNumKb; kb0 += kSplitChunk, ++ch) {
               const int buf = ch & 1;
-              // The drain of this chunk buffer may sit behind a hand-off only this thread can complete (column group 1
+              // The drain of this chunk buffer may sit behind a hand-off only this warp can complete (column group 1
               // waits for group 0's heat MMAs before it writes A2, then drains): keep serving rounds while waiting.
-              if (!ptx::mbar_test_wait(&chunk_empty[buf], ((ch >> 1) & 1) ^ 1u)) {
+              {
                 const long long t0 = clock64();
-                while (!ptx::mbar_test_wait(&chunk_empty[buf], ((ch >> 1) & 1) ^ 1u)) {
+                while (!__all_sync(0xffffffffu, ptx::mbar_test_wait(&chunk_empty[buf], ((ch >> 1) & 1) ^ 1u))) {
                   poll_rounds();
                   if (clock64() - t0 > 8000000000LL) __trap();     // protocol bug: fail the launch, never hang the GPU
                 }
               }
               ptx::tc_fence_after();
-              const uint32_t d_main = tmem_base + (uint32_t)(buf * BN);
+              const uint32_t d_main = tb + (uint32_t)(buf * BN);
               const int kb1 = kb0 + kSplitChunk < kNumKb ? kb0 + kSplitChunk : kNumKb;
               for (int kb = kb0; kb < kb1; ++kb, pos += 2) {
                 poll_rounds();
@@ -322,24 +338,30 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 ptx::tc_fence_after();
                 const uint64_t da = desc(slot_ptr(sa)), dal = desc(slot_ptr(sa) + kABytes);
                 const uint64_t db = desc(slot_ptr(sb)), dbl = desc(slot_ptr(sb) + kABytes);
+                const uint32_t first = kb != 0, first_main = kb > kb0;
+                if (ptx::elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint64_t o = (uint64_t)(2 * k);
-                  ptx::umma_f16(d_corr, dal + o, db + o, idesc, (kb | k) != 0);       // lo*hi
-                  ptx::umma_f16(d_corr, da + o, dbl + o, idesc, 1u);                  // hi*lo
-                  ptx::umma_f16(d_main, da + o, db + o, idesc, (kb > kb0 || k > 0));  // hi*hi, short chain
+                  for (int k = 0; k < 4; ++k) {
+                    const uint64_t o = (uint64_t)(2 * k);
+                    ptx::umma_f16(d_corr, dal + o, db + o, idesc, k ? 1u : first);        // lo*hi
+                    ptx::umma_f16(d_corr, da + o, dbl + o, idesc, 1u);                    // hi*lo
+                    ptx::umma_f16(d_main, da + o, db + o, idesc, k ? 1u : first_main);    // hi*hi, short chain
+                  }
+                  ptx::umma_commit(&empty[sa]);
+                  ptx::umma_commit(&empty[sb]);
                 }
-                ptx::umma_commit(&empty[sa]);
-                ptx::umma_commit(&empty[sb]);
+                __syncwarp();
               }
-              ptx::umma_commit(&chunk_full[buf]);
+              if (ptx::elect_one()) ptx::umma_commit(&chunk_full[buf]);
+              __syncwarp();
             }
           }
-          ptx::umma_commit(&tmem_full[acc]);
+          if (ptx::elect_one()) ptx::umma_commit(&tmem_full[acc]);
+          __syncwarp();
           rounds_due += Cfg::kRounds;
         }
       }
-      flush_rounds();
+      force_rounds(rounds_due);
     }
   } else if (warp < 10) {
     // ===================================================================== convert warps (2..9)
