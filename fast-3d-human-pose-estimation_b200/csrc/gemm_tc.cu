@@ -462,7 +462,9 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    // converged like the MMA issuer (UTMALDG takes its tensor-map pointer / barrier from uniform registers too): the
+    // whole warp walks the tiles and waits, one elected lane arms the barrier and issues the loads of a K block
+    {
       uint32_t it = 0;
       for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
         const int n_tile = tile % p.n_tiles;
@@ -474,69 +476,66 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           const int s = it % S;
           const uint32_t par = (it / S) & 1;
           ptx::mbar_wait(&empty[s], par ^ 1u);
+          // every coordinate is computed here, in warp-uniform code; the elected lane only issues
+          const int tap = kb / kb_per_tap;
+          const int k0 = (kb - tap * kb_per_tap) * kTcBK;
+          int dy = 0, dx = 0;
+          if (p.tap_mode == kTapDeconv) {
+            dy = py - (tap >> 1); dx = px - (tap & 1);
+          } else if (p.tap_mode == kTapConv3) {
+            dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1;
+          }
+          const int ys = p.stride * y0 + dy;
+          const int arow = g * p.a_group_rows + m0;
+          const int bk = tap * p.cin + k0;
+          const int brow = g * p.b_group_rows + n_tile * BN + (kPair2 ? (int)cta_rank * (BN / 2) : 0);   // CL = 2: my half of B
           if constexpr (kPair2) {
             // both CTAs count their bytes on the LEADER's barrier of this stage; the leader expects the sum
             const uint32_t full_leader = ptx::mapa_u32(ptx::smem_u32(&full[s]), 0);
-            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);
-            const int tap = kb / kb_per_tap;
-            const int k0 = (kb - tap * kb_per_tap) * kTcBK;
-            if (p.a4d) {
-              int dy = 0, dx = 0;
-              if (p.tap_mode == kTapDeconv) {
-                dy = py - (tap >> 1); dx = px - (tap & 1);
-              } else if (p.tap_mode == kTapConv3) {
-                dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1;
+            if (ptx::elect_one()) {
+              if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);
+              if (p.a4d) {
+                ptx::tma_load_4d_2sm(stage_a(s, 0), &tmap_a, full_leader, k0, dx, ys, img0);
+                if (kLoadLo) ptx::tma_load_4d_2sm(stage_a(s, 1), &tmap_a_lo, full_leader, k0, dx, ys, img0);
+              } else {
+                ptx::tma_load_2d_2sm(stage_a(s, 0), &tmap_a, full_leader, k0, arow);
+                if (kLoadLo) ptx::tma_load_2d_2sm(stage_a(s, 1), &tmap_a_lo, full_leader, k0, arow);
               }
-              const int ys = p.stride * y0 + dy;
-              ptx::tma_load_4d_2sm(stage_a(s, 0), &tmap_a, full_leader, k0, dx, ys, img0);
-              if (kLoadLo) ptx::tma_load_4d_2sm(stage_a(s, 1), &tmap_a_lo, full_leader, k0, dx, ys, img0);
-            } else {
-              ptx::tma_load_2d_2sm(stage_a(s, 0), &tmap_a, full_leader, k0, g * p.a_group_rows + m0);
-              if (kLoadLo) ptx::tma_load_2d_2sm(stage_a(s, 1), &tmap_a_lo, full_leader, k0, g * p.a_group_rows + m0);
+              ptx::tma_load_2d_2sm(stage_b(s, 0), &tmap_b, full_leader, bk, brow);
+              if (kLoadLo) ptx::tma_load_2d_2sm(stage_b(s, 1), &tmap_b_lo, full_leader, bk, brow);
             }
-            const int brow = g * p.b_group_rows + n_tile * BN + (int)cta_rank * (BN / 2);      // my half of the B tile
-            ptx::tma_load_2d_2sm(stage_b(s, 0), &tmap_b, full_leader, tap * p.cin + k0, brow);
-            if (kLoadLo) ptx::tma_load_2d_2sm(stage_b(s, 1), &tmap_b_lo, full_leader, tap * p.cin + k0, brow);
-            continue;
-          }
-#ifdef CDR_EXP_NO_LO
-          ptx::mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes / (kSplit ? 2 : 1));
-#else
-          ptx::mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
-#endif
-          const int tap = kb / kb_per_tap;
-          const int k0 = (kb - tap * kb_per_tap) * kTcBK;
-          if (p.a4d) {
-            int dy = 0, dx = 0;
-            if (p.tap_mode == kTapDeconv) {
-              dy = py - (tap >> 1); dx = px - (tap & 1);
-            } else if (p.tap_mode == kTapConv3) {
-              dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1;
-            }
-            const int ys = p.stride * y0 + dy;
-            if constexpr (CL != 0) {
-              // my half of the tile (64 pixels = 8 KB per plane), delivered to both CTAs of the pair
-              const int yh = ys + (p.half_dim == 2 ? (int)cta_rank * p.half_step : 0);
-              const int ih = img0 + (p.half_dim == 3 ? (int)cta_rank * p.half_step : 0);
-              const uint32_t off = cta_rank * (uint32_t)(kABytes / 2);
-              ptx::tma_load_4d_mc(stage_a(s, 0) + off, &tmap_a, &full[s], k0, dx, yh, ih, 3);
-              if (kLoadLo) ptx::tma_load_4d_mc(stage_a(s, 1) + off, &tmap_a_lo, &full[s], k0, dx, yh, ih, 3);
-            } else {
-              ptx::tma_load_4d(stage_a(s, 0), &tmap_a, &full[s], k0, dx, ys, img0);
-              if (kLoadLo) ptx::tma_load_4d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, dx, ys, img0);
-            }
-          } else if constexpr (CL != 0) {
-            const int row = g * p.a_group_rows + m0 + (int)cta_rank * (kTcBM / 2);
-            const uint32_t off = cta_rank * (uint32_t)(kABytes / 2);
-            ptx::tma_load_2d_mc(stage_a(s, 0) + off, &tmap_a, &full[s], k0, row, 3);
-            if (kLoadLo) ptx::tma_load_2d_mc(stage_a(s, 1) + off, &tmap_a_lo, &full[s], k0, row, 3);
           } else {
-            ptx::tma_load_2d(stage_a(s, 0), &tmap_a, &full[s], k0, g * p.a_group_rows + m0);
-            if (kLoadLo) ptx::tma_load_2d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, g * p.a_group_rows + m0);
+            // CL = 1: my half of the A tile (64 pixels = 8 KB per plane), delivered to both CTAs of the pair
+            const int yh = ys + (CL == 1 && p.half_dim == 2 ? (int)cta_rank * p.half_step : 0);
+            const int ih = img0 + (CL == 1 && p.half_dim == 3 ? (int)cta_rank * p.half_step : 0);
+            const uint32_t off = CL == 1 ? cta_rank * (uint32_t)(kABytes / 2) : 0u;
+            const int arow_h = arow + (CL == 1 ? (int)cta_rank * (kTcBM / 2) : 0);
+            if (ptx::elect_one()) {
+#ifdef CDR_EXP_NO_LO
+              ptx::mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes / (kSplit ? 2 : 1));
+#else
+              ptx::mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+#endif
+              if (p.a4d) {
+                if constexpr (CL == 1) {
+                  ptx::tma_load_4d_mc(stage_a(s, 0) + off, &tmap_a, &full[s], k0, dx, yh, ih, 3);
+                  if (kLoadLo) ptx::tma_load_4d_mc(stage_a(s, 1) + off, &tmap_a_lo, &full[s], k0, dx, yh, ih, 3);
+                } else {
+                  ptx::tma_load_4d(stage_a(s, 0), &tmap_a, &full[s], k0, dx, ys, img0);
+                  if (kLoadLo) ptx::tma_load_4d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, dx, ys, img0);
+                }
+              } else if constexpr (CL == 1) {
+                ptx::tma_load_2d_mc(stage_a(s, 0) + off, &tmap_a, &full[s], k0, arow_h, 3);
+                if (kLoadLo) ptx::tma_load_2d_mc(stage_a(s, 1) + off, &tmap_a_lo, &full[s], k0, arow_h, 3);
+              } else {
+                ptx::tma_load_2d(stage_a(s, 0), &tmap_a, &full[s], k0, arow);
+                if (kLoadLo) ptx::tma_load_2d(stage_a(s, 1), &tmap_a_lo, &full[s], k0, arow);
+              }
+              ptx::tma_load_2d(stage_b(s, 0), &tmap_b, &full[s], bk, brow);
+              if (kLoadLo) ptx::tma_load_2d(stage_b(s, 1), &tmap_b_lo, &full[s], bk, brow);
+            }
           }
-          ptx::tma_load_2d(stage_b(s, 0), &tmap_b, &full[s], tap * p.cin + k0, g * p.b_group_rows + n_tile * BN);
-          if (kLoadLo)
-            ptx::tma_load_2d(stage_b(s, 1), &tmap_b_lo, &full[s], tap * p.cin + k0, g * p.b_group_rows + n_tile * BN);
+          __syncwarp();
         }
         if constexpr (KIND == kKindBF16 && BN == 128) {
           if (p.has_res) {
@@ -544,9 +543,12 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             // up to S stages ahead of the epilogue that consumes it, released by the epilogue warps
             const int s = it % S;
             ptx::mbar_wait(&empty[s], ((it / S) & 1) ^ 1u);
-            ptx::mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
-            ptx::tma_load_3d(stage_a(s, 0), &tmap_r, &full[s], n_tile * BN, m0, 0);
-            ptx::tma_load_3d(stage_a(s, 0) + kABytes, &tmap_r, &full[s], n_tile * BN + 64, m0, 0);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+              ptx::tma_load_3d(stage_a(s, 0), &tmap_r, &full[s], n_tile * BN, m0, 0);
+              ptx::tma_load_3d(stage_a(s, 0) + kABytes, &tmap_r, &full[s], n_tile * BN + 64, m0, 0);
+            }
+            __syncwarp();
             ++it;
           }
         }

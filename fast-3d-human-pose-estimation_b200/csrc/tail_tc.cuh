@@ -151,18 +151,21 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   //                       heat of tile t in columns [0,32) (main) and [32,64) (correction) of its correction accumulator.
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================================== TMA producer (converged; an elected lane issues)
+    {
       // final-layer weights: resident for the whole kernel
-      ptx::mbar_arrive_expect_tx(wf_full, Cfg::kWfBytes);
-      if constexpr (!kSplit) {
-        for (int c = 0; c < 4; ++c) ptx::tma_load_2d(wf + c * 4096, &tmap_w, wf_full, 64 * c, 0);
-      } else {
-        for (int c = 0; c < 4; ++c) {            // c = half * 2 + chunk: channels [64c, 64c + 64)
-          ptx::tma_load_2d(wf + (c * 2 + 0) * 4096, &tmap_w, wf_full, 64 * c, 0);
-          ptx::tma_load_2d(wf + (c * 2 + 1) * 4096, &tmap_w_lo, wf_full, 64 * c, 0);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(wf_full, Cfg::kWfBytes);
+        if constexpr (!kSplit) {
+          for (int c = 0; c < 4; ++c) ptx::tma_load_2d(wf + c * 4096, &tmap_w, wf_full, 64 * c, 0);
+        } else {
+          for (int c = 0; c < 4; ++c) {            // c = half * 2 + chunk: channels [64c, 64c + 64)
+            ptx::tma_load_2d(wf + (c * 2 + 0) * 4096, &tmap_w, wf_full, 64 * c, 0);
+            ptx::tma_load_2d(wf + (c * 2 + 1) * 4096, &tmap_w_lo, wf_full, 64 * c, 0);
+          }
         }
       }
+      __syncwarp();
       uint32_t pos = 0;                          // ring position (slots)
       for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
         const int g = unit & 3, m0 = (unit >> 2) * kTcBM;
@@ -173,25 +176,35 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const int tap = kb >> 2, k0 = (kb & 3) * 64;
             const int dy = py - (tap >> 1), dx = px - (tap & 1);
             const int brow = g * kDecC + nh * BN;
+            const int bk = tap * kDecC + k0, ys = y0 + dy;
             if constexpr (!kSplit) {
               const int s = pos % S;
               ptx::mbar_wait(&empty[s], ((pos / S) & 1) ^ 1u);
-              ptx::mbar_arrive_expect_tx(&full[s], Cfg::kSlotBytes);
-              ptx::tma_load_4d(slot_ptr(s), &tmap_a, &full[s], k0, dx, y0 + dy, img0);
-              ptx::tma_load_2d(slot_ptr(s) + kABytes, &tmap_b, &full[s], tap * kDecC + k0, brow);
+              if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(&full[s], Cfg::kSlotBytes);
+                ptx::tma_load_4d(slot_ptr(s), &tmap_a, &full[s], k0, dx, ys, img0);
+                ptx::tma_load_2d(slot_ptr(s) + kABytes, &tmap_b, &full[s], bk, brow);
+              }
+              __syncwarp();
               ++pos;
             } else {
               int s = pos % S;
               ptx::mbar_wait(&empty[s], ((pos / S) & 1) ^ 1u);
-              ptx::mbar_arrive_expect_tx(&full[s], Cfg::kSlotBytes);
-              ptx::tma_load_4d(slot_ptr(s), &tmap_a, &full[s], k0, dx, y0 + dy, img0);
-              ptx::tma_load_4d(slot_ptr(s) + kABytes, &tmap_a_lo, &full[s], k0, dx, y0 + dy, img0);
+              if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(&full[s], Cfg::kSlotBytes);
+                ptx::tma_load_4d(slot_ptr(s), &tmap_a, &full[s], k0, dx, ys, img0);
+                ptx::tma_load_4d(slot_ptr(s) + kABytes, &tmap_a_lo, &full[s], k0, dx, ys, img0);
+              }
+              __syncwarp();
               ++pos;
               s = pos % S;
               ptx::mbar_wait(&empty[s], ((pos / S) & 1) ^ 1u);
-              ptx::mbar_arrive_expect_tx(&full[s], Cfg::kSlotBytes);
-              ptx::tma_load_2d(slot_ptr(s), &tmap_b, &full[s], tap * kDecC + k0, brow);
-              ptx::tma_load_2d(slot_ptr(s) + kABytes, &tmap_b_lo, &full[s], tap * kDecC + k0, brow);
+              if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(&full[s], Cfg::kSlotBytes);
+                ptx::tma_load_2d(slot_ptr(s), &tmap_b, &full[s], bk, brow);
+                ptx::tma_load_2d(slot_ptr(s) + kABytes, &tmap_b_lo, &full[s], bk, brow);
+              }
+              __syncwarp();
               ++pos;
             }
           }
