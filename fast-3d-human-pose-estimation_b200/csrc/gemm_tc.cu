@@ -330,10 +330,13 @@ __device__ __forceinline__ void tma_store_block(const TcGemmParams& p, const voi
 // K-blocks accumulated inside TMEM before the split kinds' main term is drained into fp32 registers.
 // The tensor core adds into its fp32 accumulator with round-toward-zero; over a long K chain
 // of same-signed partial sums that bias grows linearly (measured: 1e-5 relative at K=2048, 40x
-// worse than FFMA).  Chains of 4 K-blocks (16 MMAs) keep it below 1e-6; the cross-chunk sum is
-// done by the epilogue warps in registers with round-to-nearest.
+// worse than FFMA).  The cross-chunk sum is done by the epilogue warps in registers with round-to-nearest.
+// Chains of 8 K-blocks (32 MMAs): heat-maps 3.1e-6 of max vs the fp64 oracle, 2D joints 2.9e-4 px (gates 2e-5 / 1e-3;
+// the reference's own fp32 sits at 5.8e-4 px); chains of 4 gave 1.7e-6 / 1.8e-4 px.  8 halves the number of chunk
+// hand-backs between the MMA issuer and the epilogue warps — what made cta_group::2 pairs lose on the 16-K-block layers
+// (every hand-back crosses the cluster): f16x2 deconv2 / deconv3 on pairs 154 / 600 us with chunks of 4, 132 / 527 with 8.
 #ifndef CDR_SPLIT_CHUNK
-#define CDR_SPLIT_CHUNK 4
+#define CDR_SPLIT_CHUNK 8
 #endif
 constexpr int kSplitChunk = CDR_SPLIT_CHUNK;
 
@@ -353,9 +356,14 @@ constexpr int kSplitChunk = CDR_SPLIT_CHUNK;
 // A + B, and a stage shrinks from 64 to 48 KB (f16x2, BN = 128): 4 stages instead of 3.  The idea: with BN = 128 an MMA
 // reads 8 KB of operands in the 64 cycles it computes — the 128 B/clk the shared memory delivers.  MEASURED on B200
 // (B = 64, parity green): f16x2 deconv1 / 2 / 3 344 / 176 / 674 us with the multicast pairs (CL = 1) -> 353 / 189 / 716 us
-// with cta_group::2 — 3-8 % SLOWER: the pair advances at the pace of its slower CTA and every chunk-buffer hand-back
-// crosses the cluster; bf16 (BN = 256) gains 2-3 % (111 -> 108, 212 -> 205 us).  Kept as an opt-in experiment
-// (CDR_CTA_PAIR=1 / CDR_BF16_PAIR=1), off by default.  Protocol: one "full" barrier per stage, the leader's — both CTAs'
+// with cta_group::2 — 3-8 % SLOWER, while the kernel was still ISSUE-bound (one thread fed the tensor cores of two SMs
+// through the ELECT loops described at the issuer).  With the converged issuer the picture is the expected one: ncu
+// shows the f16x2 tail's tensor pipe active 65 % with the issuer stalled ON the UTCHMMA instructions and the TMA
+// producer on a full ring — operand reads (8 KB per 64-cycle MMA) plus TMA fills (64 KB per K block) ask 213 B/clk of
+// a 128 B/clk shared memory.  Re-measured: f16x2 deconv1 (128 K blocks per tile) 310 -> 274 us; deconv2 / deconv3 (16 K
+// blocks per tile) 153 -> 154 / 604 -> 600 with main-term chunks of 4 K blocks (every chunk hand-back crosses the
+// cluster) and 153 -> 132 / 604 -> 527 with chunks of 8 (now the default); bf16 deconv1 / 2 / 3 103 -> 95, 57 -> 53,
+// 208 -> 180 us.  Enabled for the decoder's transposed convs (tc_decoder sets TcLaunch::pair2).  Protocol: one "full" barrier per stage, the leader's — both CTAs'
 // TMA loads count their bytes on it (cp.async.bulk.tensor.cta_group::2); stage release, chunk / tile completion are
 // multicast commits to both CTAs' barriers; "accumulator drained" arrivals of the peer's epilogue warps go to the
 // leader's barriers through the cluster window (mapa + mbarrier.arrive.shared::cluster).
@@ -936,6 +944,7 @@ struct TcLaunch {
   int stride;                    // 0/1 or 2
   const void* res;               // residual rows (bf16, n channels, pitch res_pitch) added before the ReLU
   int res_pitch;
+  int pair2;                     // run as cta_group::2 CTA pairs (kernel parameter CL = 2) if the geometry allows
 };
 
 // Programmatic dependent launch of consecutive tap-GEMMs (CDR_PDL=0 turns it off for A/B timing).  Measured on
@@ -960,12 +969,12 @@ static bool tc_use_cluster() {
 }
 // cta_group::2 pairs (kernel template parameter CL = 2): CDR_CTA_PAIR=0 turns them off for A/B timing.  The pair takes
 // two consecutive 128-pixel blocks: an even number of pixel blocks, no residual, unit stride.
-static bool tc_use_pair2() {
-  const char* e = getenv("CDR_CTA_PAIR");      // opt-in: measured SLOWER than the multicast pairs on B200 (see the kernel comment)
-  return e && e[0] == '1';
-}
+// Where they pay (measured, see the kernel comment) the caller asks for them with TcLaunch::pair2; CDR_CTA_PAIR=0 turns
+// them off, CDR_CTA_PAIR=1 forces them on every eligible launch.
 static bool tc_pair2_ok(const TcLaunch& l) {
-  if (!tc_use_pair2() || l.res || l.stride > 1) return false;
+  const char* e = getenv("CDR_CTA_PAIR");
+  if (e && e[0] == '0') return false;
+  if (!(l.pair2 || (e && e[0] == '1')) || l.res || l.stride > 1) return false;
   const long long m = (long long)l.n_img * l.H * l.W;
   return m % (2 * kTcBM) == 0;
 }
@@ -1154,7 +1163,7 @@ static int launch_tc(const TcLaunch& l, cudaStream_t st) {
   const int bn = l.layer->bn, kind = l.layer->kind;
   const int ofmt = l.out_mode == kOutPlanar ? kind_fmt(kind) : l.C.fmt;
   if (kind == kKindBF16 && ofmt == kFmtBF16) {
-    if (bn == 256 && getenv("CDR_BF16_PAIR") && tc_pair2_ok(l)) return launch_tc_t<256, kKindBF16, kFmtBF16, 2>(l, st);   // experiment
+    if (bn == 256 && tc_pair2_ok(l)) return launch_tc_t<256, kKindBF16, kFmtBF16, 2>(l, st);
     if (bn == 256) return launch_tc_t<256, kKindBF16, kFmtBF16>(l, st);
     if (bn == 128) return launch_tc_t<128, kKindBF16, kFmtBF16>(l, st);
     if (bn == 64) return launch_tc_t<64, kKindBF16, kFmtBF16>(l, st);
@@ -1681,6 +1690,8 @@ static int tc_decoder(const TcWeights& w, const Act& x1, int N, const Act& d1, c
     l.bias_group_stride = 0;
     l.C = outs[i]; l.c_pitch = kDecC; l.c_fill = kDecC; l.relu = 1; l.out_mode = kOutDeconv;
     l.in_slot = slot(slots, 1 + i); l.out_slot = slot(slots, 2 + i);
+    // cta_group::2 pairs: measured to pay on every bf16 (BN = 256) and f16x2 transposed conv (see the kernel comment)
+    l.pair2 = mode_decoder_kind(w.kind) == kKindBF16 || mode_decoder_kind(w.kind) == kKindF16X2;
     if (int rc = launch_tc(l, st)) return rc;
     in = outs[i];
     side *= 2;
