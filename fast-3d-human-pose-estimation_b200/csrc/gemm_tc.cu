@@ -1189,6 +1189,7 @@ static int launch_tc(const TcLaunch& l, cudaStream_t st) {
 // fused decoder tail: deconv3 + final 1x1 + soft-argmax partials (tail_tc.cuh)
 }  // namespace cdr
 #include "tail_tc.cuh"
+#include "tail_pair_tc.cuh"
 namespace cdr {
 
 // CDR_FUSED_TAIL=0 keeps deconv3 / final 1x1 / soft-argmax as three launches (A/B timing, cross-check).  Read at
@@ -1262,6 +1263,92 @@ static int launch_tail_t(const TailLaunch& l, cudaStream_t st) {
   CDR_CUDA(cudaLaunchKernelEx(&cfg, deconv_tail_kernel<KIND>, tmap_a[0], tmap_a[1], l.dc3->map[0],
                               l.dc3->map[Cfg::kPlanes - 1], l.fin->map[0], l.fin->map[Cfg::kPlanes - 1], p));
   CDR_LAUNCH_OK("deconv_tail_kernel");
+  return CDR_OK;
+}
+
+// The same on cta_group::2 CTA pairs (tail_pair_tc.cuh).  Measured on B200 at B = 64: f16x2 653 -> 556 us; bf16 200 -> 203 us
+// (its tile is 256 channels wide — operand reads were never its limit), so bf16 stays on the single-CTA kernel.
+// CDR_TAIL_PAIR=0 / 1 forces the single-CTA / the pair kernel for both kinds.
+static bool tc_use_tail_pair(int kind) {
+  const char* e = getenv("CDR_TAIL_PAIR");
+  if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
+  return kind == kKindF16X2;
+}
+
+template <int KIND>
+static int launch_tail_pair_t(const TailLaunch& l, cudaStream_t st) {
+  using Cfg = TailPairCfg<KIND>;
+  constexpr int kAFmt = KindTraits<KIND>::kFmt;
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
+    CDR_CUDA(cudaFuncSetAttribute(deconv_tail_pair_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)TailPairSmem<KIND>::kBytes));
+    attr_set.done();
+  }
+  CDR_CHECK_ARG(l.A.fmt == kAFmt && l.dc3->kind == KIND && l.fin->kind == KIND && l.dc3->bn == Cfg::kBN &&
+                    l.fin->n_pad == 32 && l.joints <= 32 && (l.heat || l.part),
+                "deconv_tail_pair: operand formats / packing do not match the kernel");
+  CUtensorMap tmap_a[2], tmap_b[2], tmap_w16;
+  for (int pl = 0; pl < Cfg::kPlanes; ++pl) {
+    const uint64_t dims[4] = {(uint64_t)kDecC, 32, 32, (uint64_t)l.n_img};
+    const uint64_t strides[3] = {(uint64_t)kDecC, (uint64_t)kDecC * 32, (uint64_t)kDecC * 1024};
+    const uint32_t box[4] = {64, 32, 4, 1};
+    if (int rc = make_tmap(&tmap_a[pl], l.A.p[pl], kAFmt, 4, dims, strides, box)) return rc;
+    // each CTA of the pair stages half of the weight tile: a box of BN/2 rows
+    const uint64_t bdims[2] = {(uint64_t)l.dc3->k, (uint64_t)l.dc3->rows};
+    const uint64_t bstr[1] = {(uint64_t)l.dc3->k_pitch};
+    const uint32_t bbox[2] = {64, (uint32_t)(Cfg::kBN / 2)};
+    if (int rc = make_tmap(&tmap_b[pl], l.dc3->w[pl], kAFmt, 2, bdims, bstr, bbox)) return rc;
+  }
+  if (Cfg::kPlanes == 1) {
+    tmap_a[1] = tmap_a[0];
+    tmap_b[1] = tmap_b[0];
+  }
+  {   // 16-row boxes of the final layer's (hi) plane: each CTA's half of an N = 32 operand
+    const uint64_t dims[2] = {(uint64_t)l.fin->k, (uint64_t)l.fin->rows};
+    const uint64_t strides[1] = {(uint64_t)l.fin->k_pitch};
+    const uint32_t box[2] = {64, 16};
+    if (int rc = make_tmap(&tmap_w16, l.fin->w[0], kAFmt, 2, dims, strides, box)) return rc;
+  }
+  TailParams p{};
+  p.n_img = l.n_img;
+  p.num_units = (l.n_img * 1024 / kTcBM) * 4;
+  p.joints = l.joints;
+  p.bias = l.dc3->bias;
+  p.wsi = l.dc3->wsi;
+  p.scale_in = l.in_slot.scale;
+  p.amax_in = l.in_slot.amax;
+  p.norms = l.dc3->norms;
+  p.bias_fin = l.fin->bias;
+  p.wsi_fin = l.fin->wsi;
+  p.heat = l.heat;
+  p.part = l.part;
+  if (KIND == kKindF16X2)
+    CDR_CHECK_ARG(p.wsi && p.scale_in && p.amax_in && p.norms && p.wsi_fin, "deconv_tail_pair: f16x2 operands need their scales");
+  int grid = p.num_units < num_sms() ? p.num_units : num_sms();
+  grid &= ~1;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
+  attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+  attr[n_attr].val.clusterDim.x = 2;
+  attr[n_attr].val.clusterDim.y = 1;
+  attr[n_attr].val.clusterDim.z = 1;
+  ++n_attr;
+  if (tc_use_pdl()) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kTailThreads);
+  cfg.dynamicSmemBytes = TailPairSmem<KIND>::kBytes;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = n_attr;
+  CDR_CUDA(cudaLaunchKernelEx(&cfg, deconv_tail_pair_kernel<KIND>, tmap_a[0], tmap_a[1], tmap_b[0], tmap_b[1], l.fin->map[0],
+                              l.fin->map[Cfg::kPlanes - 1], tmap_w16, p));
+  CDR_LAUNCH_OK("deconv_tail_pair_kernel");
   return CDR_OK;
 }
 
@@ -1703,7 +1790,10 @@ static int tc_decoder(const TcWeights& w, const Act& x1, int N, const Act& d1, c
     t.dc3 = &pk->dc[2]; t.fin = &pk->fin;
     t.in_slot = slot(slots, 3);
     t.heat = heat; t.part = part;
-    const int rc = mode_decoder_kind(w.kind) == kKindBF16 ? launch_tail_t<kKindBF16>(t, st) : launch_tail_t<kKindF16X2>(t, st);
+    const bool bf = mode_decoder_kind(w.kind) == kKindBF16;
+    // (n_img * 8 pixel blocks: always an even number, so the pair form applies to every batch)
+    const int rc = tc_use_tail_pair(mode_decoder_kind(w.kind)) ? (bf ? launch_tail_pair_t<kKindBF16>(t, st) : launch_tail_pair_t<kKindF16X2>(t, st))
+                                      : (bf ? launch_tail_t<kKindBF16>(t, st) : launch_tail_t<kKindF16X2>(t, st));
     set_stage(nullptr);
     return rc;
   }

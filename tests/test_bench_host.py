@@ -67,4 +67,5 @@ def test_peaks_and_constants():
     assert b.FLOP_PER_PAIR["deconv3_tail"] == b.FLOP_PER_PAIR["deconv3"] + b.FLOP_PER_PAIR["final_1x1"]
     assert abs(dec - 7595.9e6) < 1e5 and b.SOFTARGMAX_DLT_BYTES_PER_POSE == 2 * 19 * 4096 * 4 + 96 + 304 + 228
     t = b.ncu_traffic()
-    assert "fp32" in t and t["fp32"]["deconv3"] > 5e8 and json.dumps(t)
+    top = t["fp32"].get("deconv3_tail", t["fp32"].get("deconv3"))          # r02: fused tail; r01: deconv3
+    assert "fp32" in t and top > 1e8 and json.dumps(t)

@@ -821,12 +821,17 @@ def test_poseresnet_tc_encoder_baseline_path(cuda_pkg, precision):
     assert tuple(xyz.shape) == (n // 2, joints, 3) and bool(torch.isfinite(xyz).all())
 
 
+@pytest.mark.parametrize("pair", ["default", "0", "1"])
 @pytest.mark.parametrize("precision,b", [("bf16", 3), ("fp32", 3), ("fp32", 64), ("bf16", 64)])
-def test_fused_decoder_tail_matches_unfused_and_oracle(cuda_pkg, precision, b, monkeypatch):
+def test_fused_decoder_tail_matches_unfused_and_oracle(cuda_pkg, precision, b, pair, monkeypatch):
     """deconv3 -> ReLU -> final 1x1 -> soft-argmax partials as ONE kernel (tail_tc.cuh: second tcgen05.mma on the ReLU'd
     tile, per-row online-softmax partials merged in fp64) against the three-launch path of the same library
     (CDR_FUSED_TAIL=0) — heat-maps to accumulation-order rounding, 2D joints <= 1e-4 px — and, at B = 3, against the
     fp64 oracle with the flat tolerance."""
+    if pair != "default":                        # single-CTA kernel / cta_group::2 pair kernel (tail_pair_tc.cuh), both kinds
+        if b == 64 and pair == "0":
+            pytest.skip("covered at B=3")
+        monkeypatch.setenv("CDR_TAIL_PAIR", pair)
     sd = synth.make_head_state_dict(seed=0, calibrated=True, randomize_bn=True)
     feats, cams = synth.make_features(b, seed=1), synth.make_cameras(b, seed=2)
     m = _model(cuda_pkg, sd, precision=precision)
