@@ -2274,6 +2274,10 @@ static int enc_conv(const TcLayer& L, const __nv_bfloat16* in, int cin, int n, i
   l.layer = &L; l.n = cout;
   l.C.p[0] = out; l.C.fmt = kFmtBF16; l.c_pitch = cout; l.c_fill = cout; l.relu = relu; l.out_mode = kOutRows;
   l.res = res; l.res_pitch = cout;
+  // cta_group::2 pairs for the MMA-bound wide layers (BN = 256: conv1 / conv2 of a block), as on the decoder's bf16
+  // transposed convs (layer4 conv2 38.2 -> 35.1 us, conv1 24.6 -> 23.6 us); CDR_ENC_PAIR=0 turns them off
+  const char* ep = getenv("CDR_ENC_PAIR");
+  l.pair2 = L.bn == 256 && !res && stride <= 1 && !(ep && ep[0] == '0');
   return launch_tc(l, st);
 }
 
