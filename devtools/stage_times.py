@@ -19,12 +19,15 @@ feats = [f.to(dev) for f in synth.make_features(B, seed=1)]
 cams = synth.make_cameras(B, seed=2)
 Ps = [torch.from_numpy(cams["P_l"]).to(dev), torch.from_numpy(cams["P_r"]).to(dev)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+flush_r = torch.zeros(256 << 20, dtype=torch.uint8, device=dev) if os.environ.get("STAGE_FLUSH_READ") else None
 for _ in range(3):
     m.head(feats, Ps)
 torch.cuda.synchronize()
 acc = {}
 for _ in range(reps):
     flush.fill_(1)
+    if flush_r is not None:
+        flush_r.max()        # a read pass after the write: L2 is left with CLEAN foreign lines (no write-backs owed)
     torch.cuda.synchronize()
     _lib.stage_timing_begin(dev)
     m.head(feats, Ps)

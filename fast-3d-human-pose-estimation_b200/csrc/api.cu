@@ -361,7 +361,7 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
   set_stage("pinv");
   const float* pinv[2] = {pinv_l, pinv_r};
   if (!pinv_l) {
-    if ((rc = launch_pinv2(P_l, P_r, B, pinv_rtol, ws.pinv, st))) return rc;
+    if ((rc = launch_pinv2(P_l, P_r, B, pinv_rtol, ws.pinv, nullptr, st))) return rc;
     pinv[0] = ws.pinv;
     pinv[1] = ws.pinv + (size_t)B * 12;
   }

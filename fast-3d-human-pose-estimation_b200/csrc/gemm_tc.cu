@@ -181,6 +181,7 @@ struct TcGemmParams {
   const float* wsi;       // per packed weight row: 2^-t (undoes the weight scale)
   int wsi_group_stride;
   const float* scale_in;  // s of the A tensor
+  const float* scale_in_rows;   // (optional) one s per A row instead (2-D A only): layout.cu's per-pixel scales
   const float* amax_in;   // max |x| of the A tensor (unscaled)   } bound for the output scale
   const float* norms;     // layer {max_row ||W||_1, max |bias|}   }
   float* amax_out;        // atomicMax target: max |out| (unscaled), pre-zeroed
@@ -675,7 +676,8 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     int sbuf = 0;                                  // staging buffer of this warp's next store
     uint32_t tl = 0, ch = 0, it_e = 0;             // it_e: ring position of the current tile's residual stage
     EpiScale es;
-    if constexpr (KIND == kKindF16X2) es.a_inv = 1.f / __ldg(p.scale_in);   // powers of two: exact
+    if constexpr (KIND == kKindF16X2)
+      if (!p.scale_in_rows) es.a_inv = 1.f / __ldg(p.scale_in);   // powers of two: exact
     if constexpr (OFMT == kFmtF16P) {
       if (p.out_mode != kOutPlanar) {
         const float bound = __ldg(p.amax_in) * __ldg(p.norms) + __ldg(p.norms + 1);
@@ -693,6 +695,8 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int mw = m0 + q * 32;                  // first pixel of this warp
       const int m = mw + lane;                     // this thread's pixel
       const bool row_ok = m < p.M;
+      if constexpr (KIND == kKindF16X2)
+        if (p.scale_in_rows) es.a_inv = row_ok ? 1.f / __ldg(p.scale_in_rows + (size_t)g * p.a_group_rows + m) : 1.f;
       const int n0 = n_tile * BN + cb0;            // first output channel of this warp
       const float* __restrict__ bias = p.bias + (size_t)g * p.bias_group_stride;
       const float* __restrict__ wsi = KIND == kKindF16X2 ? p.wsi + (size_t)g * p.wsi_group_stride : nullptr;
@@ -896,6 +900,12 @@ struct TcLayer {            // one packed conv: K-major B operand (1 plane bf16 
 // 2 = "hybrid" fp32: fusion block 3xTF32 (its activations carry P's 1e5 dynamic range between
 //     the two FTLs, and it is 5 % of the FLOPs), decoder f16x2.
 enum TcMode { kModeBF16 = 0, kModeTF32X3 = 1, kModeHybrid = 2 };
+// hybrid (the library's "fp32" precision): the whole fusion block runs on scaled fp16 hi/lo planes like the decoder
+// (half the MMA time of 3xTF32); CDR_FUSION_F16=0 at pack time keeps conv_layer2 / out_layer on 3xTF32 (A/B, cross-check)
+static bool tc_fusion_f16() {
+  const char* e = getenv("CDR_FUSION_F16");
+  return !(e && e[0] == '0');
+}
 static inline int mode_fusion_kind(int mode) { return mode == kModeBF16 ? kKindBF16 : kKindTF32X3; }
 static inline int mode_decoder_kind(int mode) {
   return mode == kModeBF16 ? kKindBF16 : mode == kModeTF32X3 ? kKindTF32X3 : kKindF16X2;
@@ -905,6 +915,7 @@ static inline int kind_fmt(int kind) {
 }
 struct TcPack {
   int mode = kModeBF16;
+  int fusion_kind = kKindBF16;     // kind of conv_layer2 / out_layer (and of every fusion activation but x0)
   TcLayer cf1, cf2a, cf2b, out, dc[3], fin;
 };
 struct Act {                // an activation buffer: 1 plane (bf16) or hi/lo planes
@@ -938,6 +949,7 @@ struct TcLaunch {
   long long c_group_stride;
   int c_pitch, c_fill, relu, out_mode;
   ScaleSlot in_slot, out_slot;   // kFmtF16P tensors
+  const float* in_row_scale;     // overrides in_slot.scale: one scale per A row (2-D A)
   const float* amax_in;          // overrides in_slot.amax (input stored in another format)
   // encoder convs: H, W above are the OUTPUT pixel grid; the input grid is (stride*H, stride*W)
   int conv3;                     // 3x3, pad 1 (9 taps)
@@ -1025,6 +1037,7 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
   p.relu = l.relu; p.out_mode = l.out_mode;
   p.wsi = l.layer->wsi; p.wsi_group_stride = l.b_group_rows;
   p.scale_in = l.in_slot.scale;
+  p.scale_in_rows = l.in_row_scale;
   p.amax_in = l.amax_in ? l.amax_in : l.in_slot.amax;
   p.norms = l.layer->norms;
   p.amax_out = l.out_slot.amax; p.scale_out = l.out_slot.scale;
@@ -1047,7 +1060,10 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
     if (OFMT == kFmtF16P)
       CDR_CHECK_ARG(p.amax_in && p.norms && p.scale_out, "tap_gemm_tc: fp16-plane output needs its scale slots");
   }
-  if (KIND == kKindF16X2) CDR_CHECK_ARG(p.wsi && p.scale_in, "tap_gemm_tc: f16x2 operands need their scales");
+  if (KIND == kKindF16X2) {
+    CDR_CHECK_ARG(p.wsi && (p.scale_in || p.scale_in_rows), "tap_gemm_tc: f16x2 operands need their scales");
+    CDR_CHECK_ARG(!p.scale_in_rows || !p.a4d, "tap_gemm_tc: per-row scales need a 2-D A operand");
+  }
 
   CUtensorMap tmap_a[2];
   for (int pl = 0; pl < KindTraits<KIND>::kPlanes; ++pl) {
@@ -1369,7 +1385,7 @@ static int launch_tail_merge(const float4* part, const float* P_l, const float* 
     ++n_attr;
   }
   cfg.gridDim = dim3(batch);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(32 * (joints < 1 ? 1 : joints > 32 ? 32 : joints));   // a half-warp per heat-map
   cfg.stream = st;
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
@@ -1541,7 +1557,8 @@ static void plan_layer(TcLayer& L, Bump1K& b, int kind, int rows, int k, int k_p
 
 static size_t plan_tc_weights(TcPack& pk, const TcWeights& w, void* base) {
   Bump1K b(base);
-  const int fk = mode_fusion_kind(pk.mode), dk = mode_decoder_kind(pk.mode);
+  if (!base) pk.fusion_kind = pk.mode == kModeHybrid && tc_fusion_f16() ? kKindF16X2 : mode_fusion_kind(pk.mode);
+  const int fk = pk.fusion_kind, dk = mode_decoder_kind(pk.mode);
   const int bn_f = fk == kKindBF16 ? 256 : 128;
   int bn_d = dk == kKindBF16 ? 256 : 128;
   if (const char* e = getenv("CDR_BF16_DECONV_BN"))     // experiment knob: UMMA N = 128 vs 256 at equal math
@@ -1550,9 +1567,10 @@ static size_t plan_tc_weights(TcPack& pk, const TcWeights& w, void* base) {
   if (w.has_fusion) {
     // conv_layer1 reads the encoder's latents (post-ReLU, bounded): in hybrid mode it runs f16x2 like the
     // decoder (half the MMA time of 3xTF32 at K = 2048); its output feeds the FTL, so it stays tf32 planes
-    plan_layer(pk.cf1, b, pk.mode == kModeHybrid ? kKindF16X2 : fk, 384, kFeatC, kFeatC, 128, 384, 384, false);
-    plan_layer(pk.cf2a, b, fk, 512, 2 * kHid2, 2 * kHid2, 128, 512, 512, false);
-    plan_layer(pk.cf2b, b, fk, 512, kHid2, kHid2, 128, 512, 512, false);
+    const bool f16 = fk == kKindF16X2;      // every fusion output is stored in kFmtF16P: each layer needs its norms
+    plan_layer(pk.cf1, b, pk.mode == kModeHybrid ? kKindF16X2 : fk, 384, kFeatC, kFeatC, 128, 384, 384, f16);
+    plan_layer(pk.cf2a, b, fk, 512, 2 * kHid2, 2 * kHid2, 128, 512, 512, f16);
+    plan_layer(pk.cf2b, b, fk, 512, kHid2, kHid2, 128, 512, 512, f16);
     plan_layer(pk.out, b, fk, 2 * kFeatC, kHid1, kHid1Pad, bn_f, kFeatC, 2 * kFeatC, scaled);
   }
   for (int i = 0; i < 3; ++i)
@@ -1652,10 +1670,12 @@ void tc_weights_destroy(TcWeights& w) {
 }
 
 // ------------------------------------------------------------------------------------------
-constexpr int kNumSlots = 8;       // ScaleSlot pairs: 0 g (amax only), 1 x1, 2 d1, 3 d2, 4 d3, 5 x0 (hybrid mode)
+constexpr int kNumSlots = 12;      // ScaleSlot pairs: 0 g (amax only), 1 x1, 2 d1, 3 d2, 4 d3, 5 x0 (hybrid mode);
+                                   // fp16 fusion block: 6 y1, 7 z, 8 f1, 9 f2, 10 g, 11 {max row L1 of P+, of P}
 struct TcHeadWs {
   float* pinv;
   float* slots;
+  float* x0_rs;             // hybrid mode: one scale per x0 row (layout.cu: nchw_to_rows_f16p_rowscale_kernel)
   Act x0, y1, z, f1, f2, g, x1, d1, d2, d3;
   float* hm;
   float4* part;             // fused decoder tail: soft-argmax partial records (2B, J, kTailSlots)
@@ -1674,13 +1694,14 @@ static Act take_act(Bump1K& b, size_t elems, int fmt) {
   a.p[1] = fmt_planes(fmt) == 2 ? b.take(elems * fmt_elem(fmt)) : nullptr;
   return a;
 }
-static TcHeadWs plan_tc_head(void* base, int B, int J, int mode) {
+static TcHeadWs plan_tc_head(void* base, int B, int J, int mode, int fusion_kind) {
   Bump1K b(base);
   const size_t N = 2 * (size_t)B;
-  const int ff = kind_fmt(mode_fusion_kind(mode)), df = kind_fmt(mode_decoder_kind(mode));
+  const int ff = kind_fmt(fusion_kind), df = kind_fmt(mode_decoder_kind(mode));
   TcHeadWs w;
   w.pinv = (float*)b.take(N * 12 * sizeof(float));
   w.slots = (float*)b.take(2 * kNumSlots * sizeof(float));
+  w.x0_rs = (float*)b.take(N * kFeatHW * sizeof(float));
   w.x0 = take_act(b, N * kFeatHW * kFeatC, mode == kModeHybrid ? kFmtF16P : ff);
   w.y1 = take_act(b, N * kFeatHW * kHid1Pad, ff);
   w.z = take_act(b, (size_t)B * kFeatHW * 2 * kHid2, ff);
@@ -1715,7 +1736,7 @@ static TcDecWs plan_tc_dec(void* base, int N, int mode) {
 }
 
 int tc_head_workspace_bytes(const TcWeights& w, int batch, size_t* bytes) {
-  *bytes = plan_tc_head(nullptr, batch, w.joints, w.kind).bytes;
+  *bytes = plan_tc_head(nullptr, batch, w.joints, w.kind, ((const TcPack*)w.impl)->fusion_kind).bytes;
   return CDR_OK;
 }
 int tc_decoder_workspace_bytes(const TcWeights& w, int n_images, size_t* bytes) {
@@ -1726,17 +1747,40 @@ int tc_decoder_workspace_bytes(const TcWeights& w, int n_images, size_t* bytes) 
 // NCHW fp32 latents (one tensor, or two whose rows are stacked: the stereo views) -> pixel-major rows
 // in the format of `out`.  kFmtF16P (single tensor only): the tensor scale comes from the exact amax
 // of the input (one extra pass over 0.5 MB / image).
-static int to_rows(const float* feat, const float* feat2, int n_img, const Act& out, ScaleSlot sl, cudaStream_t st) {
+// CDR_ROW_SCALE=0: keep the two-launch {amax, transposition} form with one tensor scale (A/B timing, cross-check)
+static bool tc_use_row_scale() {
+  const char* e = getenv("CDR_ROW_SCALE");
+  return !(e && e[0] == '0');
+}
+// *row_scale (in: buffer of n rows or NULL; out: NULL when the tensor-scale form ran)
+static int to_rows(const float* feat, const float* feat2, int n_img, const Act& out, ScaleSlot sl, float** row_scale,
+                   cudaStream_t st) {
+  float* rs = row_scale ? *row_scale : nullptr;
+  if (row_scale) *row_scale = nullptr;
   if (out.fmt == kFmtBF16)
     return launch_nchw_to_rows_bf16(feat, feat2, n_img, kFeatC, kFeatHW, (__nv_bfloat16*)out.p[0], kFeatC, st);
   if (out.fmt == kFmtTF32P)
     return launch_nchw_to_rows_split(feat, feat2, n_img, kFeatC, kFeatHW, (float*)out.p[0], (float*)out.p[1], kFeatC, st);
+  if (rs && tc_use_row_scale() && nchw_rowscale_ok(feat, feat2, n_img, kFeatC, kFeatHW, kFeatC)) {
+    *row_scale = rs;
+    return launch_nchw_to_rows_f16p_rowscale(feat, feat2, n_img, kFeatC, kFeatHW, out.p[0], out.p[1], kFeatC, rs, sl.amax, st);
+  }
   if (int rc = launch_amax_f32(feat, feat2, (long long)n_img * kFeatC * kFeatHW, sl.amax, st)) return rc;
   return launch_nchw_to_rows_f16p(feat, feat2, n_img, kFeatC, kFeatHW, out.p[0], out.p[1], kFeatC, sl.amax, sl.scale, st);
 }
 // FTL of both views in one launch
+// kFmtF16P: in_slot = scale / amax of the input, out_slot = where the output's go, l1max = max row L1 norm of `mats`
 static int ftl_act2(const Act& in0, const Act& in1, int in_pitch, const float* const mats[2], int rows, int cols, int n,
-                    const Act& out0, const Act& out1, int out_pitch, int out_fill, float* amax_out, cudaStream_t st) {
+                    const Act& out0, const Act& out1, int out_pitch, int out_fill, float* amax_out, ScaleSlot in_slot,
+                    ScaleSlot out_slot, const float* l1max, cudaStream_t st) {
+  if (in0.fmt == kFmtF16P) {
+    const void* ih[2] = {in0.p[0], in1.p[0]};
+    const void* il[2] = {in0.p[1], in1.p[1]};
+    void* oh[2] = {out0.p[0], out1.p[0]};
+    void* ol[2] = {out0.p[1], out1.p[1]};
+    return launch_ftl_f16p2(ih, il, in_pitch, mats, rows, cols, kFtlBlk, n, kFeatHW, oh, ol, out_pitch, out_fill,
+                            in_slot.scale, in_slot.amax, l1max, out_slot.scale, out_slot.amax, st);
+  }
   if (in0.fmt == kFmtBF16) {
     const __nv_bfloat16* ins[2] = {(const __nv_bfloat16*)in0.p[0], (const __nv_bfloat16*)in1.p[0]};
     __nv_bfloat16* outs[2] = {(__nv_bfloat16*)out0.p[0], (__nv_bfloat16*)out1.p[0]};
@@ -1892,8 +1936,9 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
   const TcPack* pk = (const TcPack*)w.impl;
   const int mode = w.kind;
   const bool scaled = mode_decoder_kind(mode) == kKindF16X2;
+  const bool fus16 = w.has_fusion && pk->fusion_kind == kKindF16X2;   // fusion activations in kFmtF16P (slots 6..11)
   const int B = batch, N = 2 * batch, J = w.joints;
-  TcHeadWs ws = plan_tc_head(workspace, B, J, mode);
+  TcHeadWs ws = plan_tc_head(workspace, B, J, mode, pk->fusion_kind);
   if (ws.bytes > workspace_bytes) {
     set_error("cdr_head_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
     return CDR_ERR_WORKSPACE;
@@ -1914,12 +1959,15 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
       CDR_CUDA(cudaStreamWaitEvent(lane->stream, lane->fork, 0));
       ps = lane->stream;
     }
-    if ((rc = launch_pinv2(P_l, P_r, B, pinv_rtol, ws.pinv, ps))) return rc;
-    if (lane) CDR_CUDA(cudaEventRecord(lane->join, lane->stream));
+    if ((rc = launch_pinv2(P_l, P_r, B, pinv_rtol, ws.pinv, fus16 ? ws.slots + 2 * 11 : nullptr, ps))) return rc;
     pinv[0] = ws.pinv;
     pinv[1] = ws.pinv + (size_t)B * 12;
+    if (lane) CDR_CUDA(cudaEventRecord(lane->join, lane->stream));
+  } else if (fus16) {
+    if ((rc = launch_mats_l1max(pinv[0], pinv[1], 4, 3, P_l, P_r, 3, 4, B, ws.slots + 2 * 11, st))) return rc;
   }
   Act x0 = ws.x0;
+  float* x0_rs = nullptr;          // per-row scales of x0, when the layout pass produced them
   if (feat_rows) {
     // latents already pixel-major bf16 rows, views stacked (the tcgen05 encoder's output layout)
     if (x0.fmt == kFmtBF16) {
@@ -1942,7 +1990,8 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
     }
   } else {
     set_stage("nchw_to_rows");
-    if ((rc = to_rows(feat_l, feat_r, B, ws.x0, slot(ws.slots, 5), st))) return rc;
+    x0_rs = ws.x0_rs;
+    if ((rc = to_rows(feat_l, feat_r, B, ws.x0, slot(ws.slots, 5), &x0_rs, st))) return rc;
   }
   set_stage("cf_conv1");
   {
@@ -1952,12 +2001,16 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
     l.layer = &pk->cf1; l.n = kHid1;
     l.C = ws.y1; l.c_pitch = kHid1Pad; l.c_fill = kHid1Pad; l.relu = 1; l.out_mode = kOutRows;
     l.in_slot = slot(ws.slots, 5);
+    l.in_row_scale = x0_rs;
+    if (fus16) l.out_slot = slot(ws.slots, 6);
+    l.pair2 = fus16;                 // cta_group::2 pairs: cf_conv1 49.5 -> 46.3 us, conv_layer2 38.0 -> 36.4 us (out_layer: slower)
     if ((rc = launch_tc(l, st))) return rc;
   }
   set_stage("ftl_inv");
   if (lane) CDR_CUDA(cudaStreamWaitEvent(st, lane->join, 0));      // join: the pseudo-inverses are complete
   if ((rc = ftl_act2(ws.y1, act_offset(ws.y1, (size_t)B * kFeatHW * kHid1Pad), kHid1Pad, pinv, 4, 3, B, ws.z,
-                     act_offset(ws.z, (size_t)kHid2), 2 * kHid2, kHid2, nullptr, st)))
+                     act_offset(ws.z, (size_t)kHid2), 2 * kHid2, kHid2, nullptr, slot(ws.slots, 6), slot(ws.slots, 7),
+                     ws.slots + 2 * 11, st)))
     return rc;
   set_stage("cf_conv2");
   {
@@ -1966,14 +2019,17 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
     l.a_rows_total = (long long)B * kFeatHW;
     l.layer = &pk->cf2a; l.n = kHid2;
     l.C = ws.f1; l.c_pitch = kHid2; l.c_fill = kHid2; l.relu = 1; l.out_mode = kOutRows;
+    if (fus16) { l.in_slot = slot(ws.slots, 7); l.out_slot = slot(ws.slots, 8); l.pair2 = 1; }
     if ((rc = launch_tc(l, st))) return rc;
     l.A = ws.f1; l.a_pitch = kHid2; l.cin = kHid2; l.layer = &pk->cf2b; l.C = ws.f2;
+    if (fus16) { l.in_slot = slot(ws.slots, 8); l.out_slot = slot(ws.slots, 9); }
     if ((rc = launch_tc(l, st))) return rc;
   }
   set_stage("ftl_fwd");
   const float* Pv[2] = {P_l, P_r};
   if ((rc = ftl_act2(ws.f2, ws.f2, kHid2, Pv, 3, 4, B, ws.g, act_offset(ws.g, (size_t)B * kFeatHW * kHid1Pad),
-                     kHid1Pad, kHid1Pad, scaled ? slot(ws.slots, 0).amax : nullptr, st)))
+                     kHid1Pad, kHid1Pad, scaled ? slot(ws.slots, 0).amax : nullptr, slot(ws.slots, 9), slot(ws.slots, 10),
+                     ws.slots + 2 * 11 + 1, st)))
     return rc;
   set_stage("cf_out");
   {
@@ -1984,6 +2040,7 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
     l.C = ws.x1; l.c_group_stride = (long long)B * kFeatHW * kFeatC; l.c_pitch = kFeatC; l.c_fill = kFeatC;
     l.relu = 1; l.out_mode = kOutRows;
     l.amax_in = slot(ws.slots, 0).amax; l.out_slot = slot(ws.slots, 1);
+    if (fus16) { l.amax_in = nullptr; l.in_slot = slot(ws.slots, 10); }
     if ((rc = launch_tc(l, st))) return rc;
   }
   if (tail_fusable(w)) {
@@ -2006,8 +2063,8 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
       CDR_CUDA(cudaMemcpyAsync(taps->pinv, pinv[0], (size_t)B * 48, cudaMemcpyDeviceToDevice, st));
       CDR_CUDA(cudaMemcpyAsync(taps->pinv + (size_t)B * 12, pinv[1], (size_t)B * 48, cudaMemcpyDeviceToDevice, st));
     }
-    if ((rc = tap_to_f32(taps->cf_cat, ws.z, nullptr, (long long)B * kFeatHW, 2 * kHid2, 2 * kHid2, st))) return rc;
-    if ((rc = tap_to_f32(taps->cf_f, ws.f2, nullptr, (long long)B * kFeatHW, kHid2, kHid2, st))) return rc;
+    if ((rc = tap_to_f32(taps->cf_cat, ws.z, slot(ws.slots, 7).scale, (long long)B * kFeatHW, 2 * kHid2, 2 * kHid2, st))) return rc;
+    if ((rc = tap_to_f32(taps->cf_f, ws.f2, slot(ws.slots, 9).scale, (long long)B * kFeatHW, kHid2, kHid2, st))) return rc;
     if ((rc = tap_to_f32(taps->f_out, ws.x1, slot(ws.slots, 1).scale, (long long)N * kFeatHW, kFeatC, kFeatC, st)))
       return rc;
     if (taps->heatmaps)
@@ -2047,7 +2104,7 @@ int tc_decoder_forward(const TcWeights& w, const void* feat_rows, const float* f
   }
   if (ws.x1.fmt == kFmtF16P) CDR_CUDA(cudaMemsetAsync(ws.slots, 0, 2 * kNumSlots * sizeof(float), st));
   set_stage("nchw_to_rows");
-  if (int rc = to_rows(feat, nullptr, n_images, ws.x1, slot(ws.slots, 1), st)) return rc;
+  if (int rc = to_rows(feat, nullptr, n_images, ws.x1, slot(ws.slots, 1), nullptr, st)) return rc;
   return tc_decoder(w, ws.x1, n_images, ws.d1, ws.d2, ws.d3, ws.slots, heatmaps, nullptr, st);
 }
 

@@ -13,16 +13,38 @@ __global__ void pinv_kernel(const float* __restrict__ P, int n, double rtol,
   pinv_3x4<float, float>(P + (size_t)i * 12, rtol, out + (size_t)i * 12);
 }
 
+// l1max (optional, pre-zeroed): [0] <- max row L1 norm of the pseudo-inverses, [1] <- of the matrices themselves
+// (inflated by 2^-20: upper bounds) — the output-scale bounds of the fp16-plane FTL (layout.cu: ftl_f16p_vec_kernel)
 __global__ void pinv2_kernel(const float* __restrict__ P_a, const float* __restrict__ P_b, int n, double rtol,
-                             float* __restrict__ out) {
+                             float* __restrict__ out, float* __restrict__ l1max) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * n) return;
-  const float* P = i < n ? P_a + (size_t)i * 12 : P_b + (size_t)(i - n) * 12;
-  pinv_3x4<float, float>(P, rtol, out + (size_t)i * 12);
+  float la = 0.f, lb = 0.f;
+  if (i < 2 * n) {
+    const float* P = i < n ? P_a + (size_t)i * 12 : P_b + (size_t)(i - n) * 12;
+    float* o = out + (size_t)i * 12;
+    pinv_3x4<float, float>(P, rtol, o);
+    if (l1max) {
+      for (int r = 0; r < 4; ++r) la = fmaxf(la, fabsf(o[r * 3]) + fabsf(o[r * 3 + 1]) + fabsf(o[r * 3 + 2]));
+      for (int r = 0; r < 3; ++r)
+        lb = fmaxf(lb, fabsf(P[r * 4]) + fabsf(P[r * 4 + 1]) + fabsf(P[r * 4 + 2]) + fabsf(P[r * 4 + 3]));
+    }
+  }
+  if (l1max) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      la = fmaxf(la, __shfl_xor_sync(0xffffffffu, la, o));
+      lb = fmaxf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      const float infl = 1.f + 9.5367431640625e-07f;
+      atomicMax(reinterpret_cast<unsigned int*>(l1max), __float_as_uint(la * infl));       // non-negative floats
+      atomicMax(reinterpret_cast<unsigned int*>(l1max + 1), __float_as_uint(lb * infl));
+    }
+  }
 }
-int launch_pinv2(const float* P_a, const float* P_b, int n, double rtol, float* out, cudaStream_t st) {
+int launch_pinv2(const float* P_a, const float* P_b, int n, double rtol, float* out, float* l1max, cudaStream_t st) {
   CDR_CHECK_ARG(P_a && P_b && out && n > 0, "pinv2: bad args");
-  pinv2_kernel<<<ceil_div(2 * n, 32), 32, 0, st>>>(P_a, P_b, n, rtol, out);   // one warp per block: spread over SMs
+  pinv2_kernel<<<ceil_div(2 * n, 32), 32, 0, st>>>(P_a, P_b, n, rtol, out, l1max);   // one warp per block: spread over SMs
   CDR_LAUNCH_OK("pinv_kernel");
   return CDR_OK;
 }

@@ -14,6 +14,35 @@ static long long cdr_jacobi_sweeps = 0;   // host-side instrumentation (tests/ho
 
 namespace cdr {
 
+// 1/x and 1/sqrt(x) for the rotation parameters.  Device: the hardware's 20-bit fp64 seed (MUFU.RCP64H / RSQ64H, full
+// exponent range) + two Newton steps — ~4x shorter dependent chains than DDIV / DSQRT, which dominated the latency of
+// the per-joint solve (one thread per joint: the chain IS the kernel time).  The results are good to a few ulp; the
+// Jacobi iteration is self-correcting (an angle off by 1e-15 leaves an off-diagonal the next sweep removes, and a
+// rotation scaled by 1 + 1e-16 scales both columns of G and V alike — the de-homogenised point only sees ratios).
+__host__ __device__ __forceinline__ double jacobi_rcp(double x) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+__host__ __device__ __forceinline__ double jacobi_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = fma(y, fma(-hx * y, y, 0.5), y);
+  y = fma(y, fma(-hx * y, y, 0.5), y);
+  return y;
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
 // Orthogonalise the C columns of G (R x C, column access G[r][c]) in place by plane
 // rotations from the right, accumulating them into V (C x C, starts as identity).
 // On exit G = U*Sigma (column norms are the singular values) and A_original * V = G.
@@ -40,11 +69,15 @@ __host__ __device__ __forceinline__ void jacobi_onesided(double (&G)[R][C], doub
         }
         // skip when the pair is already orthogonal to working precision (also covers
         // zero columns: gamma == 0)
-        if (fabs(gamma) > tol * sqrt(alpha * beta) && gamma != 0.0) {
+        if (gamma * gamma > (tol * tol) * (alpha * beta) && gamma != 0.0) {
           rotated = true;
-          const double zeta = (beta - alpha) / (2.0 * gamma);
-          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double c = 1.0 / sqrt(1.0 + t * t);
+          // tan(theta) = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (beta - alpha) / (2 gamma), in the
+          // division-free form t = sign(d) * 2 gamma / (|d| + sqrt(d^2 + 4 gamma^2)): one rsqrt + one reciprocal
+          const double d = beta - alpha, g2 = 2.0 * gamma;
+          const double h2 = fma(d, d, g2 * g2);
+          const double h = h2 * jacobi_rsqrt(h2);
+          const double t = (d < 0.0 ? -g2 : g2) * jacobi_rcp(fabs(d) + h);
+          const double c = jacobi_rsqrt(fma(t, t, 1.0));
           const double s = c * t;
 #pragma unroll
           for (int r = 0; r < R; ++r) {

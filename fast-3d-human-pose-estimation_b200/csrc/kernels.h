@@ -43,15 +43,24 @@ int launch_nchw_to_rows_split(const float* in, const float* in2, int n_img, int 
 int launch_ftl_split2(const float* const in_hi[2], const float* const in_lo[2], int in_pitch, const float* const mats[2],
                       int rows, int cols, int blk, int n, int hw, float* const out_hi[2], float* const out_lo[2],
                       int out_pitch, int out_fill, int views, float* amax_out, cudaStream_t st);
+int launch_ftl_f16p2(const void* const in_hi[2], const void* const in_lo[2], int in_pitch, const float* const mats[2],
+                     int rows, int cols, int blk, int n, int hw, void* const out_hi[2], void* const out_lo[2],
+                     int out_pitch, int out_fill, const float* scale_in, const float* amax_in, const float* l1max,
+                     float* scale_out, float* amax_out, cudaStream_t st);
+int launch_mats_l1max(const float* a0, const float* a1, int ra, int ca, const float* b0, const float* b1, int rb, int cb,
+                      int n, float* out, cudaStream_t st);
 template <typename T>
 int launch_ftl2(const T* const in[2], int in_pitch, const float* const mats[2], int rows, int cols, int blk, int n,
                 int hw, T* const out[2], int out_pitch, int out_fill, int views, cudaStream_t st);
 // pinv of two (n,3,4) stacks in one launch: out[0..n) from P_a, out[n..2n) from P_b
-int launch_pinv2(const float* P_a, const float* P_b, int n, double rtol, float* out, cudaStream_t st);
+int launch_pinv2(const float* P_a, const float* P_b, int n, double rtol, float* out, float* l1max, cudaStream_t st);
 // scaled fp16 hi/lo planes for the f16x2 tensor-core path (gemm_tc.cu: kFmtF16P)
 int launch_amax_f32(const float* in, const float* in2, long long n, float* amax, cudaStream_t st);   // in2 may be NULL
 int launch_nchw_to_rows_f16p(const float* in, const float* in2, int n_img, int C, int HW, void* out_hi, void* out_lo,
                              int out_pitch, const float* amax, float* scale_out, cudaStream_t st);
+bool nchw_rowscale_ok(const float* in, const float* in2, int n_img, int C, int HW, int out_pitch);
+int launch_nchw_to_rows_f16p_rowscale(const float* in, const float* in2, int n_img, int C, int HW, void* out_hi,
+                                      void* out_lo, int out_pitch, float* row_scale, float* amax_out, cudaStream_t st);
 template <typename T>
 int launch_ftl(const T* in, int in_pitch, const float* mats, int rows, int cols, int blk, int n,
                int hw, T* out, int out_pitch, int out_fill, cudaStream_t st);

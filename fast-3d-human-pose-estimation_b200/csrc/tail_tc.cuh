@@ -616,25 +616,29 @@ struct TailMergeParams {
   float scale;
 };
 
-__global__ void __launch_bounds__(256) tail_merge_dlt_kernel(const TailMergeParams p) {
+// blockDim = 32 * joints: one HALF-warp per heat-map (8 records per lane, all loads in flight at once), so the merge of
+// a pose's 2J heat-maps is a single round; warp 0 then runs the J DLT solves.
+__global__ void __launch_bounds__(1024) tail_merge_dlt_kernel(const TailMergeParams p) {
   __shared__ double kps[2 * kMaxJoints][2];
   ptx::grid_dep_wait();         // launched with programmatic stream serialization: the tail kernel's records are complete
   const int pose = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15;
   const int J = p.joints;
-  for (int item = warp; item < 2 * J; item += 8) {
+  for (int item = 2 * warp + (lane >> 4); item < 2 * J; item += 2 * (int)(blockDim.x >> 5)) {   // uniform per half-warp
     const int v = item / J, j = item - v * J;
     const float4* rec = p.part + ((size_t)(v * p.batch + pose) * J + j) * kTailSlots;
-    float4 r[4];
+    float4 r[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) r[i] = __ldg(rec + lane + 32 * i);
-    float M = fmaxf(fmaxf(r[0].x, r[1].x), fmaxf(r[2].x, r[3].x));
+    for (int i = 0; i < 8; ++i) r[i] = __ldg(rec + l16 + 16 * i);
+    float M = -INFINITY;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+    for (int i = 0; i < 8; ++i) M = fmaxf(M, r[i].x);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
     double S = 0.0, SX = 0.0, SY = 0.0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t = lane + 32 * i;                  // slot = ((pixel block * 4 + phase) * 4 + warp)
+    for (int i = 0; i < 8; ++i) {
+      const int t = l16 + 16 * i;                   // slot = ((pixel block * 4 + phase) * 4 + warp)
       const int blk = t >> 4, g = (t >> 2) & 3, q = t & 3;
       const double Y = (double)(2 * (blk * 4 + q) + (g >> 1));
       const double px = (double)(g & 1);
@@ -645,12 +649,12 @@ __global__ void __launch_bounds__(256) tail_merge_dlt_kernel(const TailMergePara
       SY += Y * s;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 8; o > 0; o >>= 1) {
       S += __shfl_xor_sync(0xffffffffu, S, o);
       SX += __shfl_xor_sync(0xffffffffu, SX, o);
       SY += __shfl_xor_sync(0xffffffffu, SY, o);
     }
-    if (lane == 0) {
+    if (l16 == 0) {
       const double cx = SX / S * (double)p.scale, cy = SY / S * (double)p.scale;
       kps[item][0] = cx;
       kps[item][1] = cy;
