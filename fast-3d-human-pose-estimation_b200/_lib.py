@@ -79,7 +79,12 @@ _SIGNATURES = {
     "cdr_decoder_forward_rows": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_size_t, _vp]),
     "cdr_head_forward_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_int, C.c_int,
                                         _vp, _vp, _vp, C.POINTER(CdrHeadTaps), _vp, C.c_size_t, _vp]),
+    "cdr_head_forward_planes": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_int, C.c_int,
+                                          _vp, _vp, _vp, C.POINTER(CdrHeadTaps), _vp, C.c_size_t, _vp]),
+    "cdr_decoder_forward_planes": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_size_t, _vp]),
     "cdr_encoder_create": (C.c_int, [C.POINTER(CdrEncoderSpec), _vp, C.POINTER(_vp)]),
+    "cdr_encoder_create_prec": (C.c_int, [C.POINTER(CdrEncoderSpec), C.c_int, _vp, C.POINTER(_vp)]),
+    "cdr_encoder_out_bytes": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "cdr_encoder_destroy": (C.c_int, [_vp]),
     "cdr_encoder_workspace_bytes": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "cdr_encoder_out_shape": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),

@@ -103,13 +103,18 @@ class PoseDecoder(nn.Module):
                                              nbytes.value, _lib.current_stream_ptr(x.device)))
         return out
 
-    def forward_rows(self, rows):
-        """The same on latents given as bf16 pixel-major rows (n*64, 2048) — the tcgen05 encoder's output."""
+    def forward_rows(self, rows, n_images=None):
+        """The same on latents given as bf16 pixel-major rows (n*64, 2048) — the tcgen05 encoder's output — or
+        (uint8 buffer + n_images) as the fp32 tcgen05 encoder's "fp16 planes" buffer (include/cdrhead.h)."""
         _require_eval(self)
-        if not (rows.is_cuda and rows.dtype == torch.bfloat16 and rows.is_contiguous() and rows.dim() == 2
-                and rows.shape[1] == 2048 and rows.shape[0] % 64 == 0):
+        planes = rows.dtype == torch.uint8
+        if planes:
+            if not (rows.is_cuda and rows.is_contiguous() and n_images):
+                raise ValueError("forward_rows on an fp16-planes buffer needs a contiguous CUDA uint8 tensor and n_images")
+        elif not (rows.is_cuda and rows.dtype == torch.bfloat16 and rows.is_contiguous() and rows.dim() == 2
+                  and rows.shape[1] == 2048 and rows.shape[0] % 64 == 0):
             raise ValueError("forward_rows expects a contiguous CUDA bf16 tensor of shape (n*64, 2048)")
-        n = rows.shape[0] // 64
+        n = int(n_images) if planes else rows.shape[0] // 64
         handle = self._packed.get(_decoder_tensors(self, ""), rows.device)
         L = _lib.lib()
         nbytes = C.c_size_t()
@@ -117,8 +122,9 @@ class PoseDecoder(nn.Module):
         ws = _workspace(rows.device, nbytes.value)
         out = torch.empty((n, self.num_joints, 64, 64), dtype=torch.float32, device=rows.device)
         with torch.cuda.device(rows.device):
-            _lib.check(L.cdr_decoder_forward_rows(handle, _lib.ptr(rows), n, _lib.ptr(out), _lib.ptr(ws),
-                                                  nbytes.value, _lib.current_stream_ptr(rows.device)))
+            fn = L.cdr_decoder_forward_planes if planes else L.cdr_decoder_forward_rows
+            _lib.check(fn(handle, _lib.ptr(rows), n, _lib.ptr(out), _lib.ptr(ws), nbytes.value,
+                          _lib.current_stream_ptr(rows.device)))
         return out
 
 
@@ -273,13 +279,16 @@ class CDRNet(nn.Module):
 
     def __init__(self, cfg, n_views=2, nj=19, fusion_in_dim=2048, fusion_hid_ch1=300,
                  fusion_hid_ch2=400, precision="fp32", encoder_precision="torch", trainable=False):
-        """encoder_precision: 'torch' (default — the reference's nn.Module on torch/cuDNN, fp32) or
+        """encoder_precision: 'fp32' — this library's tcgen05 encoder at the reference's precision (scaled fp16 hi/lo
+        planes, 3 MMAs per product; needs precision='fp32'); 'torch' (default — the reference's nn.Module on torch/cuDNN, fp32) or
         'bf16' (Bottleneck stages on libcdrhead's tcgen05 kernels, stem on cuDNN bf16).
         trainable: opt in to ``forward`` in training mode (``forward_train``, SURVEY §8f rank 3 slice)."""
         super().__init__()
         self.trainable = bool(trainable)
-        if encoder_precision not in ("torch", "bf16"):
-            raise ValueError(f"encoder_precision must be 'torch' or 'bf16', got {encoder_precision!r}")
+        if encoder_precision not in ("torch", "bf16", "fp32"):
+            raise ValueError(f"encoder_precision must be 'torch', 'bf16' or 'fp32', got {encoder_precision!r}")
+        if encoder_precision == "fp32" and precision not in ("fp32", "f16x2"):
+            raise ValueError("encoder_precision='fp32' (fp16-plane latents) needs the fp32 head (precision='fp32')")
         self.encoder_precision = encoder_precision
         if n_views != 2 or fusion_in_dim != 2048 or fusion_hid_ch1 != 300 or fusion_hid_ch2 != 400:
             raise NotImplementedError(
@@ -292,7 +301,7 @@ class CDRNet(nn.Module):
         self.n_views = n_views
         self.nj = nj
         self._packed = _PackedWeights(self, precision, has_fusion=True)
-        self._tc_encoder = TcEncoder(self.encoder) if encoder_precision == "bf16" else None
+        self._tc_encoder = TcEncoder(self.encoder, encoder_precision) if encoder_precision != "torch" else None
 
     @property
     def precision(self):
@@ -322,7 +331,11 @@ class CDRNet(nn.Module):
         pr = _as_f32_cuda(proj_list[1], "proj_list")
         b = pl.shape[0]
         fl = fr = None
-        if feat_rows is not None:
+        planes = feat_rows is not None and feat_rows.dtype == torch.uint8     # the fp32 encoder's fp16-planes buffer
+        if planes:
+            if not (feat_rows.is_cuda and feat_rows.is_contiguous() and feat_rows.numel() >= 2 * (2 * b * 64 * 2048 * 2) + 8):
+                raise ValueError("feat_rows (fp16 planes) must be the contiguous CUDA uint8 buffer TcEncoder.rows returned")
+        elif feat_rows is not None:
             if not (feat_rows.is_cuda and feat_rows.dtype == torch.bfloat16 and feat_rows.is_contiguous()
                     and tuple(feat_rows.shape) == (2 * b * 64, 2048)):
                 raise ValueError("feat_rows must be a contiguous CUDA bf16 tensor of shape (2*B*64, 2048)")
@@ -369,7 +382,7 @@ class CDRNet(nn.Module):
                 setattr(tap_struct, k, t.data_ptr())
         with torch.cuda.device(dev):
             if feat_rows is not None:
-                _lib.check(L.cdr_head_forward_rows(
+                _lib.check((L.cdr_head_forward_planes if planes else L.cdr_head_forward_rows)(
                     handle, _lib.ptr(feat_rows), _lib.ptr(pl), _lib.ptr(pr), _lib.ptr(pil),
                     _lib.ptr(pir), PINV_RTOL_FP32, b, int(img_size), _lib.ptr(kp_l), _lib.ptr(kp_r),
                     _lib.ptr(xyz), C.byref(tap_struct) if taps else None, _lib.ptr(ws), nbytes.value,
@@ -451,19 +464,21 @@ class PoseResNet(nn.Module):
 
     def __init__(self, cfg, precision="fp32", encoder_precision="torch"):
         super().__init__()
-        if encoder_precision not in ("torch", "bf16"):
-            raise ValueError(f"encoder_precision must be 'torch' or 'bf16', got {encoder_precision!r}")
+        if encoder_precision not in ("torch", "bf16", "fp32"):
+            raise ValueError(f"encoder_precision must be 'torch', 'bf16' or 'fp32', got {encoder_precision!r}")
+        if encoder_precision == "fp32" and precision not in ("fp32", "f16x2"):
+            raise ValueError("encoder_precision='fp32' (fp16-plane latents) needs the fp32 decoder (precision='fp32')")
         self.encoder = ResNet(cfg)
         self.decoder = PoseDecoder(cfg, precision)
         self.encoder_precision = encoder_precision
-        self._tc_encoder = TcEncoder(self.encoder) if encoder_precision == "bf16" else None
+        self._tc_encoder = TcEncoder(self.encoder, encoder_precision) if encoder_precision != "torch" else None
 
     def forward(self, x):
         """x: (N,3,256,256) float images — or, with encoder_precision='bf16', raw (N,256,256,3) uint8 frames."""
         if self._tc_encoder is not None and self.decoder._packed.precision != "fp32_ffma" and \
                 tuple(x.shape[-3:] if x.dtype == torch.uint8 else x.shape[-2:])[:2] == (256, 256):
             rows, _ = self._tc_encoder.rows(x)
-            return self.decoder.forward_rows(rows)
+            return self.decoder.forward_rows(rows, n_images=x.shape[0])
         with torch.no_grad():
             feats = self.encoder(x)
         return self.decoder(feats)

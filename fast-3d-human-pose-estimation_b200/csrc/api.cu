@@ -347,7 +347,7 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
   timing_restart();
   const float scale = (float)img_size / (float)kHeat;   // models/cdrnet.py:250
   if (w->precision != CDR_PREC_FP32)
-    return tc_head_forward(w->tc, nullptr, feat_l, feat_r, P_l, P_r, pinv_l, pinv_r, pinv_rtol, batch, scale,
+    return tc_head_forward(w->tc, nullptr, 0, feat_l, feat_r, P_l, P_r, pinv_l, pinv_r, pinv_rtol, batch, scale,
                            kp2d_l, kp2d_r, xyz, taps, workspace, workspace_bytes, st);
 
   const int B = batch, N = 2 * batch, J = w->joints;
@@ -444,7 +444,7 @@ extern "C" int cdr_decoder_forward(const CdrWeights* w, const float* feat, int n
   CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "cdr_decoder_forward: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (w->precision != CDR_PREC_FP32)
-    return tc_decoder_forward(w->tc, nullptr, feat, n_images, heatmaps, workspace, workspace_bytes, st);
+    return tc_decoder_forward(w->tc, nullptr, 0, feat, n_images, heatmaps, workspace, workspace_bytes, st);
   DecWs ws = plan_dec_f32(workspace, n_images);
   if (ws.bytes > workspace_bytes) {
     set_error("cdr_decoder_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
@@ -470,7 +470,25 @@ extern "C" int cdr_head_forward_rows(const CdrWeights* w, const void* feat_rows,
   CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)feat_rows & 15) == 0,
                 "cdr_head_forward_rows: workspace must be 256-byte, features 16-byte aligned");
   timing_restart();
-  return tc_head_forward(w->tc, feat_rows, nullptr, nullptr, P_l, P_r, pinv_l, pinv_r, pinv_rtol, batch,
+  return tc_head_forward(w->tc, feat_rows, 0, nullptr, nullptr, P_l, P_r, pinv_l, pinv_r, pinv_rtol, batch,
+                         (float)img_size / (float)kHeat, kp2d_l, kp2d_r, xyz, taps, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
+}
+extern "C" int cdr_head_forward_planes(const CdrWeights* w, const void* feat_planes, const float* P_l, const float* P_r,
+                                       const float* pinv_l, const float* pinv_r, double pinv_rtol, int batch,
+                                       int img_size, float* kp2d_l, float* kp2d_r, float* xyz,
+                                       const CdrHeadTaps* taps, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+  CDR_CHECK_ARG(w && feat_planes && P_l && P_r && kp2d_l && kp2d_r && xyz && workspace,
+                "cdr_head_forward_planes: null pointer");
+  CDR_CHECK_ARG(w->has_fusion, "cdr_head_forward_planes: weights were created without the fusion block");
+  CDR_CHECK_ARG(w->precision == CDR_PREC_F16X2, "cdr_head_forward_planes: needs the f16x2 (\"fp32\") precision");
+  CDR_CHECK_ARG(batch > 0 && img_size > 0, "cdr_head_forward_planes: bad batch/img_size");
+  CDR_CHECK_ARG((pinv_l == nullptr) == (pinv_r == nullptr), "cdr_head_forward_planes: give both pseudo-inverses or neither");
+  CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)feat_planes & 255) == 0,
+                "cdr_head_forward_planes: workspace must be 256-byte, the planes buffer 256-byte aligned");
+  timing_restart();
+  return tc_head_forward(w->tc, feat_planes, 1, nullptr, nullptr, P_l, P_r, pinv_l, pinv_r, pinv_rtol, batch,
                          (float)img_size / (float)kHeat, kp2d_l, kp2d_r, xyz, taps, workspace, workspace_bytes,
                          (cudaStream_t)stream);
 }
@@ -480,10 +498,15 @@ struct CdrEncoder {
 };
 
 extern "C" int cdr_encoder_create(const CdrEncoderSpec* spec, void* stream, CdrEncoder** out) {
+  return cdr_encoder_create_prec(spec, CDR_PREC_BF16, stream, out);
+}
+extern "C" int cdr_encoder_create_prec(const CdrEncoderSpec* spec, int precision, void* stream, CdrEncoder** out) {
   CDR_CHECK_ARG(spec && out, "cdr_encoder_create: null argument");
+  CDR_CHECK_ARG(precision == CDR_PREC_BF16 || precision == CDR_PREC_F16X2,
+                "cdr_encoder_create: precision must be CDR_PREC_BF16 or CDR_PREC_F16X2");
   CdrEncoder* e = new (std::nothrow) CdrEncoder();
   CDR_CHECK_ARG(e, "cdr_encoder_create: out of host memory");
-  int rc = tc_encoder_create(*spec, &e->impl, (cudaStream_t)stream);
+  int rc = tc_encoder_create(*spec, precision == CDR_PREC_F16X2 ? 2 : 0, &e->impl, (cudaStream_t)stream);
   if (rc == CDR_OK && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
     set_error("cdr_encoder_create: packing failed: %s", cudaGetErrorString(cudaGetLastError()));
     rc = CDR_ERR_CUDA;
@@ -505,6 +528,10 @@ extern "C" int cdr_encoder_destroy(CdrEncoder* e) {
 extern "C" int cdr_encoder_workspace_bytes(const CdrEncoder* e, int n_images, int in_h, int in_w, size_t* bytes) {
   CDR_CHECK_ARG(e && bytes && n_images > 0 && in_h > 0 && in_w > 0, "cdr_encoder_workspace_bytes: bad args");
   return tc_encoder_workspace_bytes(e->impl, n_images, in_h, in_w, bytes);
+}
+extern "C" int cdr_encoder_out_bytes(const CdrEncoder* e, int n_images, int in_h, int in_w, size_t* bytes) {
+  CDR_CHECK_ARG(e && bytes && n_images > 0 && in_h > 0 && in_w > 0, "cdr_encoder_out_bytes: bad args");
+  return tc_encoder_out_bytes(e->impl, n_images, in_h, in_w, bytes);
 }
 extern "C" int cdr_encoder_out_shape(const CdrEncoder* e, int in_h, int in_w, int* out_h, int* out_w, int* out_c) {
   CDR_CHECK_ARG(e && out_h && out_w && out_c, "cdr_encoder_out_shape: bad args");
@@ -569,6 +596,16 @@ extern "C" int cdr_decoder_forward_rows(const CdrWeights* w, const void* feat_ro
   CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)feat_rows & 15) == 0,
                 "cdr_decoder_forward_rows: workspace must be 256-byte, features 16-byte aligned");
   timing_restart();
-  return tc_decoder_forward(w->tc, feat_rows, nullptr, n_images, heatmaps, workspace, workspace_bytes,
+  return tc_decoder_forward(w->tc, feat_rows, 0, nullptr, n_images, heatmaps, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
+}
+extern "C" int cdr_decoder_forward_planes(const CdrWeights* w, const void* feat_planes, int n_images, float* heatmaps,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
+  CDR_CHECK_ARG(w && feat_planes && heatmaps && workspace && n_images > 0, "cdr_decoder_forward_planes: bad args");
+  CDR_CHECK_ARG(w->precision == CDR_PREC_F16X2, "cdr_decoder_forward_planes: needs the f16x2 (\"fp32\") precision");
+  CDR_CHECK_ARG(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)feat_planes & 255) == 0,
+                "cdr_decoder_forward_planes: workspace must be 256-byte, the planes buffer 256-byte aligned");
+  timing_restart();
+  return tc_decoder_forward(w->tc, feat_planes, 1, nullptr, n_images, heatmaps, workspace, workspace_bytes,
                             (cudaStream_t)stream);
 }

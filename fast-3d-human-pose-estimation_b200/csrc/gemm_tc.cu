@@ -164,8 +164,10 @@ struct TcGemmParams {
   int a4d;                // 1: A through the 4-D NHWC map (shifted / strided taps), 0: 2-D (rows, channels)
   int tap_mode;           // kTapNone: 1 tap; kTapDeconv: 4 taps of output phase g; kTapConv3: 9 taps (3x3, pad 1)
   int stride;             // 4-D A: input pixel = stride * output pixel + tap shift (map carries the element stride)
-  int has_res;            // residual tensor (rows like C, bf16) added before the ReLU: its 128 x 128 tile travels
-                          // through the operand ring as one extra stage per tile (BN = 128, bf16 kind)
+  int has_res;            // residual tensor (rows like C, same format) added before the ReLU: its 128 x 128 tile travels
+                          // through the operand ring as one extra stage per tile (BN = 128; bf16, or f16x2 hi/lo planes)
+  const float* res_scale; // kFmtF16P residual: its tensor scale s and max |x| (unscaled; enters the output-scale bound)
+  const float* res_amax;
   int box_rows, box_imgs; // 4-D box: W x box_rows x box_imgs pixels = 128
   int half_dim, half_step;// CTA pairs: coordinate (2 = row, 3 = image) and step that separate the two 64-pixel half boxes
   int groups;             // phases (deconv) or independent problems stacked along rows
@@ -195,6 +197,7 @@ struct TcGemmParams {
 
 struct EpiScale {          // per-thread epilogue constants of the scaled formats
   float a_inv = 1.f;       // 1 / s(A tensor)
+  float r_inv = 1.f;       // 1 / s(residual tensor)
   float s_out = 1.f;       // s(output tensor)
   float amax = 0.f;        // running max |out| of this thread
 };
@@ -373,8 +376,11 @@ __global__ void __launch_bounds__(TcCfg<BN, KIND, OFMT, CL>::kThreads, 1)
 tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
                    const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c_lo,
-                   const __grid_constant__ CUtensorMap tmap_r, const TcGemmParams p) {
+                   const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_r_lo,
+                   const TcGemmParams p) {
   using Cfg = TcCfg<BN, KIND, OFMT, CL>;
+  // layers that may carry a residual: the bf16 and the f16x2 -> fp16-plane kernels with BN = 128, one CTA per tile
+  constexpr bool kResOK = BN == 128 && CL == 0 && ((KIND == kKindBF16 && OFMT == kFmtBF16) || (KIND == kKindF16X2 && OFMT == kFmtF16P));
   constexpr int S = Cfg::kStages;
   constexpr int kTcBK = Cfg::kBK;
   constexpr bool kSplit = KIND != kKindBF16;
@@ -546,16 +552,21 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
           __syncwarp();
         }
-        if constexpr (KIND == kKindBF16 && BN == 128) {
+        if constexpr (kResOK) {
           if (p.has_res) {
-            // the tile's residual (128 rows x 128 channels bf16 = one 32 KB stage) rides the ring: prefetched
-            // up to S stages ahead of the epilogue that consumes it, released by the epilogue warps
+            // the tile's residual (128 rows x 128 channels: bf16 = one 32 KB stage, fp16 hi/lo planes = one 64 KB
+            // stage) rides the ring: prefetched up to S stages ahead of the epilogue that consumes it, released by
+            // the epilogue warps.  Boxes of 64 channels: [hi c0 | hi c0+64 | lo c0 | lo c0+64], 16 KB each
             const int s = it % S;
             ptx::mbar_wait(&empty[s], ((it / S) & 1) ^ 1u);
             if (ptx::elect_one()) {
               ptx::mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
               ptx::tma_load_3d(stage_a(s, 0), &tmap_r, &full[s], n_tile * BN, m0, 0);
               ptx::tma_load_3d(stage_a(s, 0) + kABytes, &tmap_r, &full[s], n_tile * BN + 64, m0, 0);
+              if constexpr (KIND == kKindF16X2) {
+                ptx::tma_load_3d(stage_a(s, 0) + 2 * kABytes, &tmap_r_lo, &full[s], n_tile * BN, m0, 0);
+                ptx::tma_load_3d(stage_a(s, 0) + 3 * kABytes, &tmap_r_lo, &full[s], n_tile * BN + 64, m0, 0);
+              }
             }
             __syncwarp();
             ++it;
@@ -653,7 +664,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         if (ptx::elect_one()) commit(&tmem_full[acc]);         // tile (bf16) / correction accumulator (split) complete
         __syncwarp();
-        if constexpr (KIND == kKindBF16 && BN == 128) {
+        if constexpr (kResOK) {
           if (p.has_res) {
             // The residual stage belongs to the epilogue, but this warp must still OBSERVE its phase: an
             // mbarrier wait can only tell the current phase from the one before it.  Skipping the phase let a
@@ -680,11 +691,15 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       if (!p.scale_in_rows) es.a_inv = 1.f / __ldg(p.scale_in);   // powers of two: exact
     if constexpr (OFMT == kFmtF16P) {
       if (p.out_mode != kOutPlanar) {
-        const float bound = __ldg(p.amax_in) * __ldg(p.norms) + __ldg(p.norms + 1);
+        float bound = __ldg(p.amax_in) * __ldg(p.norms) + __ldg(p.norms + 1);
+        if constexpr (kResOK)
+          if (p.has_res && p.res_amax) bound += __ldg(p.res_amax);       // |conv + residual| <= bound(conv) + max |residual|
         if (bound > 0.f && bound < 3.0e38f) es.s_out = ldexpf(1.f, kF16TargetExp - ilogbf(bound));
         if (blockIdx.x == 0 && threadIdx.x == 64) *p.scale_out = es.s_out;
       }
     }
+    if constexpr (kResOK && KIND == kKindF16X2)
+      if (p.has_res) es.r_inv = 1.f / __ldg(p.res_scale);
     const bool use_tma = Cfg::kTmaStore && p.out_mode != kOutPlanar;
     const float relu_floor = p.relu ? 0.f : -INFINITY;
     for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++tl) {
@@ -721,6 +736,8 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       // one finished 32-column slab (fp32, scale/bias/ReLU still to apply) -> its destination
       uint32_t resw[32];               // this thread's 64 residual values (bf16 pairs) of the current tile
       bool has_res_vals = false;
+      uint32_t res_row = 0;            // f16x2: smem address of this thread's residual row in the hi box (lo: + 2 boxes)
+      bool res_in_smem = false;
       auto emit = [&](const float (&a32)[32], int c, auto half_c, uint32_t (&wh)[32], uint32_t (&wl)[32]) {
         constexpr int half = decltype(half_c)::value;     // which 32-column half of a 64-column store block
 #ifdef CDR_EXP_NO_STORE   /* timing experiment only: the epilogue drains TMEM but neither converts nor stores */
@@ -733,12 +750,32 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         if constexpr (Cfg::kTmaStore) {
           float v[32];
-          finish_slab<KIND>(p, a32, v, n0 + c, bias, wsi, es, has_res_vals ? -INFINITY : relu_floor);
+          finish_slab<KIND>(p, a32, v, n0 + c, bias, wsi, es, (has_res_vals || res_in_smem) ? -INFINITY : relu_floor);
           if (has_res_vals) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               v[2 * j] = fmaxf(v[2 * j] + __uint_as_float(resw[half * 16 + j] << 16), relu_floor);
               v[2 * j + 1] = fmaxf(v[2 * j + 1] + __uint_as_float(resw[half * 16 + j] & 0xffff0000u), relu_floor);
+            }
+          }
+          if constexpr (kResOK && KIND == kKindF16X2) {
+            if (res_in_smem) {
+              // 32 columns of this row = four 16-byte chunks per plane, at swizzled positions (chunk ^ (row & 7))
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t o = (uint32_t)(((half * 4 + j) ^ (lane & 7)) << 4);
+                uint32_t h4[4], l4[4];
+                ptx::ld_shared_v4(res_row + o, h4[0], h4[1], h4[2], h4[3]);
+                ptx::ld_shared_v4(res_row + 2 * kABytes + o, l4[0], l4[1], l4[2], l4[3]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h4[e]));
+                  const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&l4[e]));
+                  const int c8 = 8 * j + 2 * e;
+                  v[c8] = fmaxf(v[c8] + fmaf(lf.x, 1.f / kLoScale, hf.x) * es.r_inv, relu_floor);
+                  v[c8 + 1] = fmaxf(v[c8 + 1] + fmaf(lf.y, 1.f / kLoScale, hf.y) * es.r_inv, relu_floor);
+                }
+              }
             }
           }
           uint32_t h16[16], l16[16];
@@ -845,6 +882,19 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_issuer(&tmem_empty[acc]);
+        int res_stage = -1;
+        if constexpr (kResOK && KIND == kKindF16X2) {
+          if (p.has_res) {
+            // residual stage of this tile: after the tile's K-blocks in ring order; this warp's 64 columns are box
+            // (ew >> 2) of each plane, this thread's row is q * 32 + lane
+            it_e += (uint32_t)num_kb;
+            res_stage = (int)(it_e % S);
+            ptx::mbar_wait(&full[res_stage], (it_e / S) & 1);
+            res_row = ptx::smem_u32(stage_a(res_stage, 0)) + (uint32_t)((ew >> 2) * kABytes) + (uint32_t)(q * 32 + lane) * 128u;
+            res_in_smem = true;
+            ++it_e;
+          }
+        }
         uint32_t wh[32], wl[32];
 #pragma unroll
         for (int c = 0; c < kCols; c += 64) {
@@ -856,6 +906,16 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; ++j) a32[j] = sum[(c + 32) % kCols + j];
             emit(a32, c + 32, std::integral_constant<int, 1>{}, wh, wl);
+          }
+        }
+        if constexpr (kResOK && KIND == kKindF16X2) {
+          if (res_stage >= 0) {
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0 && atomicAdd(&res_cnt[res_stage], 1u) == (uint32_t)(kEpiWarps - 1)) {
+              res_cnt[res_stage] = 0;
+              ptx::mbar_arrive(&empty[res_stage]);     // last of the 8 warps hands the stage back to the producer
+            }
           }
         }
       }
@@ -936,6 +996,8 @@ struct ScaleSlot {
   float* amax = nullptr;    // max |x| (atomicMax by the producer; zeroed at the start of a forward)
   float* scale = nullptr;   // s
 };
+// an "fp16 planes" buffer (include/cdrhead.h): [hi plane | lo plane | {amax, scale}] — defined with the encoder
+static Act planes_act(const void* buf, size_t rows, int channels, ScaleSlot* sl);
 
 struct TcLaunch {
   Act A;                    // activations
@@ -954,7 +1016,9 @@ struct TcLaunch {
   // encoder convs: H, W above are the OUTPUT pixel grid; the input grid is (stride*H, stride*W)
   int conv3;                     // 3x3, pad 1 (9 taps)
   int stride;                    // 0/1 or 2
-  const void* res;               // residual rows (bf16, n channels, pitch res_pitch) added before the ReLU
+  const void* res;               // residual rows (n channels, pitch res_pitch; bf16, or the hi plane of kFmtF16P) added
+  const void* res_lo;            // before the ReLU; kFmtF16P: the lo plane and the residual tensor's scale slot
+  ScaleSlot res_slot;
   int res_pitch;
   int pair2;                     // run as cta_group::2 CTA pairs (kernel parameter CL = 2) if the geometry allows
 };
@@ -1120,16 +1184,23 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
     }
     if (fmt_planes(OFMT) == 1) tmap_c[1] = tmap_c[0];
   }
-  CUtensorMap tmap_r = tmap_a[0];
+  CUtensorMap tmap_r = tmap_a[0], tmap_r_lo = tmap_a[0];
   if (l.res) {
-    CDR_CHECK_ARG(BN == 128 && KIND == kKindBF16 && OFMT == kFmtBF16 && l.out_mode == kOutRows && l.groups == 1 &&
-                      l.n % BN == 0 && l.c_fill == l.n,
-                  "tap_gemm_tc: the residual add needs the bf16 BN=128 kernel and a multiple of 128 channels");
+    constexpr bool kResKernel = BN == 128 && CL == 0 && ((KIND == kKindBF16 && OFMT == kFmtBF16) ||
+                                                         (KIND == kKindF16X2 && OFMT == kFmtF16P));
+    CDR_CHECK_ARG(kResKernel && l.out_mode == kOutRows && l.groups == 1 && l.n % BN == 0 && l.c_fill == l.n,
+                  "tap_gemm_tc: the residual add needs the bf16 / f16x2 BN=128 kernel and a multiple of 128 channels");
     CDR_CHECK_ARG(((uintptr_t)l.res & 15) == 0 && (l.res_pitch * 2) % 16 == 0, "tap_gemm_tc: residual alignment");
     const uint64_t dims[3] = {(uint64_t)l.c_fill, (uint64_t)p.M, 1};
     const uint64_t strides[2] = {(uint64_t)l.res_pitch, (uint64_t)p.M * l.res_pitch};
     const uint32_t box[3] = {64, 128, 1};     // half a residual tile: 128 rows x 64 channels
-    if (int rc = make_tmap(&tmap_r, l.res, kFmtBF16, 3, dims, strides, box)) return rc;
+    if (int rc = make_tmap(&tmap_r, l.res, OFMT, 3, dims, strides, box)) return rc;
+    if (OFMT == kFmtF16P) {
+      CDR_CHECK_ARG(l.res_lo && ((uintptr_t)l.res_lo & 15) == 0 && l.res_slot.scale && l.res_slot.amax,
+                    "tap_gemm_tc: an fp16-plane residual needs its lo plane and scale slot");
+      if (int rc = make_tmap(&tmap_r_lo, l.res_lo, OFMT, 3, dims, strides, box)) return rc;
+      p.res_scale = l.res_slot.scale; p.res_amax = l.res_slot.amax;
+    }
   }
   // weight maps: the layer's own (box = BN rows), or for cta_group::2 a box of BN/2 rows — each CTA stages its half
   CUtensorMap tmap_b[2] = {l.layer->map[0], l.layer->map[KindTraits<KIND>::kPlanes - 1]};
@@ -1170,7 +1241,7 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
   CDR_CUDA(cudaLaunchKernelEx(&cfg, tap_gemm_tc_kernel<BN, KIND, OFMT, CL>, tmap_a[0], tmap_a[1], tmap_b[0], tmap_b[1],
-                              tmap_c[0], tmap_c[1], tmap_r, p));
+                              tmap_c[0], tmap_c[1], tmap_r, tmap_r_lo, p));
   CDR_LAUNCH_OK("tap_gemm_tc_kernel");
   return CDR_OK;
 }
@@ -1456,7 +1527,15 @@ __global__ void pack_deconv_tc_kernel(CdrConvBn s, int cin, int cout, int n_pad,
 // One block per packed weight row: max |w| and ||w||_1 of the row (block reduction), then
 //   kWrite: the row scaled by 2^t (max lands in [2^13, 2^14)) as fp16 hi/lo planes, wsi[row] = 2^-t;
 //   always: atomicMax of the row's L1 norm and |bias| into norms[0..1] (the output-scale bound).
-template <bool kDeconv, bool kWrite>
+// folded weight of a conv (Cout,Cin,kh,kw) with `taps` = kh*kw at packed position (n, tap*Cin + ci), tap = ky*kw + kx
+__device__ __forceinline__ float conv_taps_weight(const CdrConvBn& s, int cout, int cin, int taps, int n, int kk) {
+  if (n >= cout || kk >= taps * cin) return 0.f;
+  const int tap = kk / cin, ci = kk - tap * cin;
+  return (float)((double)s.weight[((size_t)n * cin + ci) * taps + tap] * tc_bn_scale(s, n));
+}
+// kDeconv: 0 = 1x1 conv, 1 = transposed conv (4 phases), >= 2: conv with kDeconv taps in encoder order (use 9; the 1x1
+// convs of the encoder go through mode 0)
+template <int kDeconv, bool kWrite>
 __global__ void __launch_bounds__(256)
 pack_rows_f16_kernel(CdrConvBn s, int cout, int cin, int k_pitch, int n_pad, __half* __restrict__ w_hi,
                      __half* __restrict__ w_lo, float* __restrict__ wsi, float* __restrict__ bias_out,
@@ -1465,6 +1544,7 @@ pack_rows_f16_kernel(CdrConvBn s, int cout, int cin, int k_pitch, int n_pad, __h
   const int row = blockIdx.x;
   const int n = row % n_pad, phase = row / n_pad;
   auto val = [&](int kk) -> float {
+    if constexpr (kDeconv >= 2) return conv_taps_weight(s, cout, cin, kDeconv, n, kk);
     return kDeconv ? deconv_weight(s, cin, cout, phase, n, kk) : conv1x1_weight(s, cout, cin, n, kk);
   };
   float mx = 0.f, l1 = 0.f;
@@ -1612,7 +1692,7 @@ int tc_weights_create(const CdrWeightPtrs& src, int mode, TcWeights& w, cudaStre
     void* w1 = L.w[1] ? (uint8_t*)L.w[1] + row_off * L.k_pitch * elem : nullptr;
     const unsigned grid = (unsigned)ceil_div<long long>(total, 256);
     if (L.kind == kKindF16X2) {
-      pack_rows_f16_kernel<false, true><<<rows, 256, 0, st>>>(s, cout, cin, L.k_pitch, rows, (__half*)w0, (__half*)w1,
+      pack_rows_f16_kernel<0, true><<<rows, 256, 0, st>>>(s, cout, cin, L.k_pitch, rows, (__half*)w0, (__half*)w1,
                                                               L.wsi + row_off, L.bias + bias_off, L.norms);
       CDR_LAUNCH_OK("pack_rows_f16_kernel");
       return CDR_OK;
@@ -1623,7 +1703,7 @@ int tc_weights_create(const CdrWeightPtrs& src, int mode, TcWeights& w, cudaStre
       pack_conv1x1_tc_kernel<false><<<grid, 256, 0, st>>>(s, cout, cin, L.k_pitch, rows, w0, w1, L.bias + bias_off);
     CDR_LAUNCH_OK("pack_conv1x1_tc_kernel");
     if (L.norms) {   // only the norms (the layer itself is not fp16-scaled, its output is)
-      pack_rows_f16_kernel<false, false><<<rows, 256, 0, st>>>(s, cout, cin, L.k_pitch, rows, nullptr, nullptr, nullptr,
+      pack_rows_f16_kernel<0, false><<<rows, 256, 0, st>>>(s, cout, cin, L.k_pitch, rows, nullptr, nullptr, nullptr,
                                                                nullptr, L.norms);
       CDR_LAUNCH_OK("pack_rows_f16_kernel");
     }
@@ -1644,7 +1724,7 @@ int tc_weights_create(const CdrWeightPtrs& src, int mode, TcWeights& w, cudaStre
     TcLayer& L = pk->dc[i];
     const int K = 4 * kTcDcCin[i];
     if (L.kind == kKindF16X2) {
-      pack_rows_f16_kernel<true, true><<<4 * kDecC, 256, 0, st>>>(src.deconv[i], kDecC, kTcDcCin[i], K, kDecC,
+      pack_rows_f16_kernel<1, true><<<4 * kDecC, 256, 0, st>>>(src.deconv[i], kDecC, kTcDcCin[i], K, kDecC,
                                                                   (__half*)L.w[0], (__half*)L.w[1], L.wsi, L.bias, L.norms);
       CDR_LAUNCH_OK("pack_rows_f16_kernel");
     } else {
@@ -1929,8 +2009,8 @@ static SideLane* side_lane() {
   return &l;
 }
 
-int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat_l, const float* feat_r, const float* P_l,
-                    const float* P_r, const float* pinv_l, const float* pinv_r, double pinv_rtol,
+int tc_head_forward(const TcWeights& w, const void* feat_rows, int feat_planes, const float* feat_l, const float* feat_r,
+                    const float* P_l, const float* P_r, const float* pinv_l, const float* pinv_r, double pinv_rtol,
                     int batch, float scale, float* kp2d_l, float* kp2d_r, float* xyz,
                     const CdrHeadTaps* taps, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const TcPack* pk = (const TcPack*)w.impl;
@@ -1968,7 +2048,12 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
   }
   Act x0 = ws.x0;
   float* x0_rs = nullptr;          // per-row scales of x0, when the layout pass produced them
-  if (feat_rows) {
+  ScaleSlot x0_slot = slot(ws.slots, 5);
+  if (feat_rows && feat_planes) {
+    // latents as scaled fp16 hi/lo planes + {amax, scale} (the f16x2 encoder's output): conv_layer1's operand as is
+    CDR_CHECK_ARG(x0.fmt == kFmtF16P, "cdr_head_forward_planes: fp16-plane latents need the fp32 (f16x2) head");
+    x0 = planes_act(feat_rows, (size_t)N * kFeatHW, kFeatC, &x0_slot);
+  } else if (feat_rows) {
     // latents already pixel-major bf16 rows, views stacked (the tcgen05 encoder's output layout)
     if (x0.fmt == kFmtBF16) {
       x0.p[0] = const_cast<void*>(feat_rows);
@@ -2000,7 +2085,7 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
     l.a_rows_total = (long long)N * kFeatHW;
     l.layer = &pk->cf1; l.n = kHid1;
     l.C = ws.y1; l.c_pitch = kHid1Pad; l.c_fill = kHid1Pad; l.relu = 1; l.out_mode = kOutRows;
-    l.in_slot = slot(ws.slots, 5);
+    l.in_slot = x0_slot;
     l.in_row_scale = x0_rs;
     if (fus16) l.out_slot = slot(ws.slots, 6);
     l.pair2 = fus16;                 // cta_group::2 pairs: cf_conv1 49.5 -> 46.3 us, conv_layer2 38.0 -> 36.4 us (out_layer: slower)
@@ -2074,12 +2159,21 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, const float* feat
 }
 
 // feat_rows != NULL: latents as bf16 pixel-major rows (n_images*64, 2048) instead of NCHW fp32
-int tc_decoder_forward(const TcWeights& w, const void* feat_rows, const float* feat, int n_images, float* heatmaps,
-                       void* workspace, size_t workspace_bytes, cudaStream_t st) {
+int tc_decoder_forward(const TcWeights& w, const void* feat_rows, int feat_planes, const float* feat, int n_images,
+                       float* heatmaps, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   TcDecWs ws = plan_tc_dec(workspace, n_images, w.kind);
   if (ws.bytes > workspace_bytes) {
     set_error("cdr_decoder_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
     return CDR_ERR_WORKSPACE;
+  }
+  if (feat_rows && feat_planes) {
+    // fp16 hi/lo planes + {amax, scale} from the f16x2 encoder: deconv1's operand as is; its slot (1) gets a copy
+    CDR_CHECK_ARG(ws.x1.fmt == kFmtF16P, "cdr_decoder_forward_planes: fp16-plane latents need the fp32 (f16x2) decoder");
+    ScaleSlot sl;
+    const Act x1 = planes_act(feat_rows, (size_t)n_images * kFeatHW, kFeatC, &sl);
+    CDR_CUDA(cudaMemsetAsync(ws.slots, 0, 2 * kNumSlots * sizeof(float), st));
+    CDR_CUDA(cudaMemcpyAsync(slot(ws.slots, 1).amax, sl.amax, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return tc_decoder(w, x1, n_images, ws.d1, ws.d2, ws.d3, ws.slots, heatmaps, nullptr, st);
   }
   if (feat_rows) {
     Act x1 = ws.x1;
@@ -2137,38 +2231,47 @@ struct EncPack {
   void* pool = nullptr;
   void* stem_w = nullptr;        // stem.cu: packed conv1 + bn1 (NULL: no stem in this handle)
   float* stem_b = nullptr;
+  int kind = kKindBF16;          // kKindBF16: bf16 rows; kKindF16X2: scaled fp16 hi/lo planes (fp32-accurate)
   int n_blocks = 0, in_channels = 0, out_channels = 0, total_stride = 1;
   EncBlock* blocks = nullptr;
 };
 
-// N tile: 128 for the layers that carry a residual (it rides the ring as one 32 KB stage) and for the
-// memory-bound 1x1 projections (two staging buffers per warp); 256 for the MMA-bound 3x3 / reduce convs
+// N tile: 128 for the layers that carry a residual (it rides the ring as one stage) and for the
+// memory-bound 1x1 projections (two staging buffers per warp); 256 for the MMA-bound 3x3 / reduce convs.
+// f16x2: 128 everywhere (4 accumulators of BN columns fill the 512 TMEM columns).
 static int enc_bn(int n, bool wide) { return n >= 256 && wide ? 256 : n >= 128 ? 128 : 64; }
 
 static size_t plan_encoder(EncPack& e, const CdrEncoderSpec& spec, void* base) {
   Bump1K b(base);
   int cin = spec.in_channels;
+  const bool f16 = e.kind == kKindF16X2;
+  auto plan = [&](TcLayer& L, int n, int k, bool wide) {
+    const int bn = f16 ? 128 : enc_bn(n, wide);
+    const int n_pad = round_up(n, bn);
+    plan_layer(L, b, e.kind, n_pad, k, k, bn, n_pad, n_pad, f16);
+  };
   for (int i = 0; i < spec.num_blocks; ++i) {
     const CdrEncoderBlock& sb = spec.blocks[i];
     EncBlock& blk = e.blocks[i];
     blk.cin = cin; blk.planes = sb.planes; blk.stride = sb.stride; blk.has_ds = sb.downsample.weight != nullptr;
     const int p = sb.planes, o = 4 * sb.planes;
-    plan_layer(blk.c1, b, kKindBF16, p, cin, cin, enc_bn(p, true), p, p, false);
-    plan_layer(blk.c2, b, kKindBF16, p, 9 * p, 9 * p, enc_bn(p, true), p, p, false);
-    plan_layer(blk.c3, b, kKindBF16, o, p, p, enc_bn(o, false), o, o, false);
-    if (blk.has_ds) plan_layer(blk.ds, b, kKindBF16, o, cin, cin, enc_bn(o, false), o, o, false);
+    plan(blk.c1, p, cin, true);
+    plan(blk.c2, p, 9 * p, true);
+    plan(blk.c3, o, p, false);
+    if (blk.has_ds) plan(blk.ds, o, cin, false);
     cin = o;
   }
   if (spec.stem.weight) {
-    e.stem_w = b.take(stem_weight_bytes());
+    e.stem_w = b.take(f16 ? stem_weight_bytes_f32() : stem_weight_bytes());
     e.stem_b = (float*)b.take(64 * sizeof(float));
   }
   return b.off;
 }
 
-int tc_encoder_create(const CdrEncoderSpec& spec, void** out, cudaStream_t st) {
+int tc_encoder_create(const CdrEncoderSpec& spec, int kind, void** out, cudaStream_t st) {
   CDR_CHECK_ARG(spec.num_blocks > 0 && spec.blocks && spec.in_channels > 0 && spec.in_channels % 64 == 0,
                 "cdr_encoder_create: bad spec");
+  CDR_CHECK_ARG(kind == kKindBF16 || kind == kKindF16X2, "cdr_encoder_create: precision must be bf16 or f16x2");
   int cin = spec.in_channels, total_stride = 1;
   for (int i = 0; i < spec.num_blocks; ++i) {
     const CdrEncoderBlock& sb = spec.blocks[i];
@@ -2185,6 +2288,7 @@ int tc_encoder_create(const CdrEncoderSpec& spec, void** out, cudaStream_t st) {
     total_stride *= sb.stride;
   }
   EncPack* e = new EncPack();
+  e->kind = kind;
   e->n_blocks = spec.num_blocks;
   e->in_channels = spec.in_channels;
   e->out_channels = cin;
@@ -2193,8 +2297,19 @@ int tc_encoder_create(const CdrEncoderSpec& spec, void** out, cudaStream_t st) {
   *out = e;
   const size_t bytes = plan_encoder(*e, spec, nullptr);
   CDR_CUDA(cudaMalloc(&e->pool, bytes));
+  CDR_CUDA(cudaMemsetAsync(e->pool, 0, bytes, st));       // norms start at 0 for the atomicMax
   plan_encoder(*e, spec, e->pool);
   auto pack = [&](const CdrConvBn& s, TcLayer& L, int cout, int cin_l, int taps) -> int {
+    if (L.kind == kKindF16X2) {
+      if (taps == 9)
+        pack_rows_f16_kernel<9, true><<<L.n_pad, 256, 0, st>>>(s, cout, cin_l, L.k_pitch, L.n_pad, (__half*)L.w[0],
+                                                                (__half*)L.w[1], L.wsi, L.bias, L.norms);
+      else
+        pack_rows_f16_kernel<0, true><<<L.n_pad, 256, 0, st>>>(s, cout, cin_l, L.k_pitch, L.n_pad, (__half*)L.w[0],
+                                                                (__half*)L.w[1], L.wsi, L.bias, L.norms);
+      CDR_LAUNCH_OK("pack_rows_f16_kernel");
+      return layer_maps(L);
+    }
     const long long total = (long long)L.n_pad * taps * cin_l;
     pack_conv_tc_kernel<<<(unsigned)ceil_div<long long>(total, 256), 256, 0, st>>>(s, cout, cin_l, taps, L.n_pad,
                                                                                     (__nv_bfloat16*)L.w[0], L.bias);
@@ -2203,7 +2318,9 @@ int tc_encoder_create(const CdrEncoderSpec& spec, void** out, cudaStream_t st) {
   };
   if (spec.stem.weight) {
     CDR_CHECK_ARG(spec.in_channels == 64, "cdr_encoder_create: the stem produces 64 channels");
-    if (int rc = launch_pack_stem(spec.stem, e->stem_w, e->stem_b, st)) return rc;
+    if (int rc = kind == kKindF16X2 ? launch_pack_stem_f32(spec.stem, (float*)e->stem_w, e->stem_b, st)
+                                    : launch_pack_stem(spec.stem, e->stem_w, e->stem_b, st))
+      return rc;
   }
   for (int i = 0; i < spec.num_blocks; ++i) {
     const CdrEncoderBlock& sb = spec.blocks[i];
@@ -2225,9 +2342,34 @@ void tc_encoder_destroy(void* enc) {
   delete e;
 }
 
+int tc_encoder_kind(const void* enc) { return ((const EncPack*)enc)->kind; }
+
+// Output of an f16x2 encoder: [hi plane | lo plane | {amax, scale}] — planes of rows*channels fp16, each starting
+// on a 1024-byte boundary (include/cdrhead.h: "fp16 planes")
+static size_t planes_stride_bytes(size_t rows, int channels) { return round_up<size_t>(rows * channels * 2, 1024); }
+static Act planes_act(const void* buf, size_t rows, int channels, ScaleSlot* sl) {
+  Act a;
+  a.fmt = kFmtF16P;
+  const size_t stride = planes_stride_bytes(rows, channels);
+  a.p[0] = const_cast<void*>(buf);
+  a.p[1] = (uint8_t*)const_cast<void*>(buf) + stride;
+  if (sl) {
+    sl->amax = (float*)((uint8_t*)const_cast<void*>(buf) + 2 * stride);
+    sl->scale = sl->amax + 1;
+  }
+  return a;
+}
+int tc_encoder_out_bytes(const void* enc, int n, int h, int w, size_t* bytes) {
+  const EncPack& e = *(const EncPack*)enc;
+  const size_t rows = (size_t)n * (h / e.total_stride) * (w / e.total_stride);
+  *bytes = e.kind == kKindF16X2 ? 2 * planes_stride_bytes(rows, e.out_channels) + 1024 : rows * e.out_channels * 2;
+  return CDR_OK;
+}
+
 struct EncWs {
-  __nv_bfloat16 *x[2], *t1, *t2, *r;
-  size_t bytes;
+  Act x[2], t1, t2, r;
+  float* slots;            // f16x2: {amax, scale} pairs — 0: the input, 1 + 4*i ..: block i's t1, t2, r, out
+  size_t slot_bytes, bytes;
 };
 static EncWs plan_enc_ws(const EncPack& e, void* base, int n, int h, int w) {
   size_t mx = 0, mt1 = 0, mt2 = 0, mr = 0;
@@ -2244,11 +2386,14 @@ static EncWs plan_enc_ws(const EncPack& e, void* base, int n, int h, int w) {
   }
   Bump1K bp(base);
   EncWs ws;
-  ws.x[0] = (__nv_bfloat16*)bp.take(mx * 2);
-  ws.x[1] = (__nv_bfloat16*)bp.take(mx * 2);
-  ws.t1 = (__nv_bfloat16*)bp.take(mt1 * 2);
-  ws.t2 = (__nv_bfloat16*)bp.take(mt2 * 2);
-  ws.r = (__nv_bfloat16*)bp.take(mr * 2);
+  const int fmt = kind_fmt(e.kind);
+  ws.slot_bytes = (size_t)(2 + 8 * e.n_blocks) * sizeof(float);
+  ws.slots = (float*)bp.take(ws.slot_bytes);
+  ws.x[0] = take_act(bp, mx, fmt);
+  ws.x[1] = take_act(bp, mx, fmt);
+  ws.t1 = take_act(bp, mt1, fmt);
+  ws.t2 = take_act(bp, mt2, fmt);
+  ws.r = take_act(bp, mr, fmt);
   ws.bytes = bp.off;
   return ws;
 }
@@ -2275,15 +2420,19 @@ int tc_encoder_workspace_bytes(const void* enc, int n, int h, int w, size_t* byt
 }
 
 // images (n,3,H,W): [conv_out (n,H/2,W/2,64) | pooled (n,H/4,W/4,64) | layer workspace]
+// (bf16: both bf16; f16x2: conv_out fp32, pooled as fp16 hi/lo planes whose scale is slot 0 of the layer workspace)
 struct EncImgWs {
-  void *conv_out, *pooled, *layers;
+  void* conv_out;
+  Act pooled;
+  void* layers;
   size_t layer_bytes, bytes;
 };
 static EncImgWs plan_enc_img_ws(const EncPack& e, void* base, int n, int H, int W) {
   Bump1K bp(base);
   EncImgWs ws;
-  ws.conv_out = bp.take((size_t)n * (H / 2) * (W / 2) * 64 * 2);
-  ws.pooled = bp.take((size_t)n * (H / 4) * (W / 4) * 64 * 2);
+  const bool f16 = e.kind == kKindF16X2;
+  ws.conv_out = bp.take((size_t)n * (H / 2) * (W / 2) * 64 * (f16 ? 4 : 2));
+  ws.pooled = take_act(bp, (size_t)n * (H / 4) * (W / 4) * 64, kind_fmt(e.kind));
   ws.layer_bytes = plan_enc_ws(e, nullptr, n, H / 4, W / 4).bytes;
   ws.layers = bp.take(ws.layer_bytes);
   ws.bytes = bp.off;
@@ -2297,8 +2446,8 @@ int tc_encoder_workspace_bytes_images(const void* enc, int n, int H, int W, size
   *bytes = plan_enc_img_ws(e, nullptr, n, H, W).bytes;
   return CDR_OK;
 }
-int tc_encoder_forward(const void* enc, const void* x, int n, int h, int w, void* out_rows, void* workspace,
-                       size_t workspace_bytes, cudaStream_t st);
+static int enc_layers(const EncPack& e, const Act& x, bool x_scaled, int n, int h, int w, void* out_rows, void* workspace,
+                      size_t workspace_bytes, cudaStream_t st);
 int tc_encoder_forward_images(const void* enc, const void* images, int is_u8, const float* mean, const float* std,
                               int n, int H, int W, void* out_rows, void* workspace, size_t workspace_bytes,
                               cudaStream_t st) {
@@ -2311,8 +2460,17 @@ int tc_encoder_forward_images(const void* enc, const void* images, int is_u8, co
     return CDR_ERR_WORKSPACE;
   }
   set_stage("enc_stem");
-  if (int rc = launch_stem(images, is_u8, mean, std, n, H, W, e.stem_w, e.stem_b, ws.conv_out, ws.pooled, st)) return rc;
-  return tc_encoder_forward(enc, ws.pooled, n, H / 4, W / 4, out_rows, ws.layers, ws.layer_bytes, st);
+  if (e.kind == kKindF16X2) {
+    // slot 0 of the layer workspace = {amax, scale} of the pooled tensor; every slot is zeroed here, before the stem
+    EncWs lw = plan_enc_ws(e, ws.layers, n, H / 4, W / 4);
+    CDR_CUDA(cudaMemsetAsync(lw.slots, 0, lw.slot_bytes, st));
+    if (int rc = launch_stem_f32(images, is_u8, mean, std, n, H, W, (const float*)e.stem_w, e.stem_b, (float*)ws.conv_out,
+                                 ws.pooled.p[0], ws.pooled.p[1], lw.slots, st))
+      return rc;
+    return enc_layers(e, ws.pooled, true, n, H / 4, W / 4, out_rows, ws.layers, ws.layer_bytes, st);
+  }
+  if (int rc = launch_stem(images, is_u8, mean, std, n, H, W, e.stem_w, e.stem_b, ws.conv_out, ws.pooled.p[0], st)) return rc;
+  return enc_layers(e, ws.pooled, false, n, H / 4, W / 4, out_rows, ws.layers, ws.layer_bytes, st);
 }
 
 int tc_encoder_out_shape(const void* enc, int h, int w, int* oh, int* ow, int* oc) {
@@ -2321,62 +2479,100 @@ int tc_encoder_out_shape(const void* enc, int h, int w, int* oh, int* ow, int* o
   return CDR_OK;
 }
 
-static int enc_conv(const TcLayer& L, const __nv_bfloat16* in, int cin, int n, int H, int W, int conv3, int stride,
-                    __nv_bfloat16* out, int cout, int relu, const __nv_bfloat16* res, cudaStream_t st) {
+// H, W: the conv's OUTPUT grid.  res (optional): residual tensor with the output's shape, added before the ReLU.
+static int enc_conv(const TcLayer& L, const Act& in, ScaleSlot in_slot, int cin, int n, int H, int W, int conv3, int stride,
+                    const Act& out, ScaleSlot out_slot, int cout, int relu, const Act* res, ScaleSlot res_slot,
+                    cudaStream_t st) {
   TcLaunch l{};
-  l.A.p[0] = (void*)in; l.A.fmt = kFmtBF16; l.a_pitch = cin;
-  l.n_img = n; l.H = H; l.W = W; l.cin = cin; l.groups = 1;       // H, W: output grid
+  l.A = in; l.a_pitch = cin;
+  l.n_img = n; l.H = H; l.W = W; l.cin = cin; l.groups = 1;
   l.conv3 = conv3; l.stride = stride;
   l.a_rows_total = (long long)n * H * W;
   l.layer = &L; l.n = cout;
-  l.C.p[0] = out; l.C.fmt = kFmtBF16; l.c_pitch = cout; l.c_fill = cout; l.relu = relu; l.out_mode = kOutRows;
-  l.res = res; l.res_pitch = cout;
-  // cta_group::2 pairs for the MMA-bound wide layers (BN = 256: conv1 / conv2 of a block), as on the decoder's bf16
-  // transposed convs (layer4 conv2 38.2 -> 35.1 us, conv1 24.6 -> 23.6 us); CDR_ENC_PAIR=0 turns them off
+  l.C = out; l.c_pitch = cout; l.c_fill = cout; l.relu = relu; l.out_mode = kOutRows;
+  l.in_slot = in_slot; l.out_slot = out_slot;
+  if (res) {
+    l.res = res->p[0]; l.res_lo = res->p[1]; l.res_slot = res_slot;
+  }
+  l.res_pitch = cout;
+  // cta_group::2 pairs for the MMA-bound wide layers (conv1 / conv2 of a block: BN = 256 in bf16, every f16x2 one), as
+  // on the decoder's transposed convs (layer4 conv2 38.2 -> 35.1 us, conv1 24.6 -> 23.6 us); CDR_ENC_PAIR=0: off
   const char* ep = getenv("CDR_ENC_PAIR");
-  l.pair2 = L.bn == 256 && !res && stride <= 1 && !(ep && ep[0] == '0');
+  l.pair2 = (L.bn == 256 || L.kind == kKindF16X2) && !res && stride <= 1 && !(ep && ep[0] == '0');
   return launch_tc(l, st);
 }
 
-int tc_encoder_forward(const void* enc, const void* x, int n, int h, int w, void* out_rows, void* workspace,
-                       size_t workspace_bytes, cudaStream_t st) {
-  const EncPack& e = *(const EncPack*)enc;
+// layer1..layer4 on x (n, h, w, in_channels) in the handle's activation format.  f16x2: the workspace's slots are
+// already zeroed and slot 0 holds x's {amax, scale} (x_scaled)
+static int enc_layers(const EncPack& e, const Act& x, bool x_scaled, int n, int h, int w, void* out_rows, void* workspace,
+                      size_t workspace_bytes, cudaStream_t st) {
   if (int rc = enc_check_grid(e, h, w)) return rc;
   EncWs ws = plan_enc_ws(e, workspace, n, h, w);
   if (ws.bytes > workspace_bytes) {
     set_error("cdr_encoder_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
     return CDR_ERR_WORKSPACE;
   }
-  const __nv_bfloat16* cur = (const __nv_bfloat16*)x;
+  const bool f16 = e.kind == kKindF16X2;
+  CDR_CHECK_ARG(!f16 || x_scaled, "cdr_encoder_forward: the f16x2 encoder starts from images (its stem sets the input scale)");
+  Act cur = x;
+  ScaleSlot cur_slot = f16 ? slot(ws.slots, 0) : ScaleSlot{};
   int H = h, W = w, pp = 0;
   char label[48];
   for (int i = 0; i < e.n_blocks; ++i) {
     const EncBlock& b = e.blocks[i];
     const int s = b.stride, Ho = H / s, Wo = W / s, o = 4 * b.planes;
-    __nv_bfloat16* out = i + 1 == e.n_blocks ? (__nv_bfloat16*)out_rows : ws.x[pp];
+    const bool last = i + 1 == e.n_blocks;
+    Act out = ws.x[pp];
+    ScaleSlot s_t1{}, s_t2{}, s_r{}, s_out{};
+    if (f16) {
+      s_t1 = slot(ws.slots, 1 + 4 * i); s_t2 = slot(ws.slots, 2 + 4 * i);
+      s_r = slot(ws.slots, 3 + 4 * i); s_out = slot(ws.slots, 4 + 4 * i);
+    }
+    if (last) {
+      if (f16) {
+        out = planes_act(out_rows, (size_t)n * Ho * Wo, o, &s_out);
+        CDR_CUDA(cudaMemsetAsync(s_out.amax, 0, 2 * sizeof(float), st));
+      } else {
+        out.p[0] = out_rows;
+      }
+    }
     int rc;
     auto stage = [&](const char* conv) {
       snprintf(label, sizeof(label), "enc_block%d.%s", i, conv);
       set_stage(label);
     };
     stage("conv1");
-    if ((rc = enc_conv(b.c1, cur, b.cin, n, H, W, 0, 1, ws.t1, b.planes, 1, nullptr, st))) return rc;
+    if ((rc = enc_conv(b.c1, cur, cur_slot, b.cin, n, H, W, 0, 1, ws.t1, s_t1, b.planes, 1, nullptr, ScaleSlot{}, st))) return rc;
     stage("conv2");
-    if ((rc = enc_conv(b.c2, ws.t1, b.planes, n, Ho, Wo, 1, s, ws.t2, b.planes, 1, nullptr, st))) return rc;
-    const __nv_bfloat16* res = cur;
+    if ((rc = enc_conv(b.c2, ws.t1, s_t1, b.planes, n, Ho, Wo, 1, s, ws.t2, s_t2, b.planes, 1, nullptr, ScaleSlot{}, st))) return rc;
+    Act res = cur;
+    ScaleSlot res_slot = cur_slot;
     if (b.has_ds) {
       stage("downsample");
-      if ((rc = enc_conv(b.ds, cur, b.cin, n, Ho, Wo, 0, s, ws.r, o, 0, nullptr, st))) return rc;
+      if ((rc = enc_conv(b.ds, cur, cur_slot, b.cin, n, Ho, Wo, 0, s, ws.r, s_r, o, 0, nullptr, ScaleSlot{}, st))) return rc;
       res = ws.r;
+      res_slot = s_r;
     }
     stage("conv3");
-    if ((rc = enc_conv(b.c3, ws.t2, b.planes, n, Ho, Wo, 0, 1, out, o, 1, res, st))) return rc;
+    if ((rc = enc_conv(b.c3, ws.t2, s_t2, b.planes, n, Ho, Wo, 0, 1, out, s_out, o, 1, &res, res_slot, st))) return rc;
     cur = out;
+    cur_slot = s_out;
     pp ^= 1;
     H = Ho; W = Wo;
   }
   set_stage(nullptr);
   return CDR_OK;
+}
+
+// x: (n, h, w, in_channels) bf16 NHWC from the caller's own stem (bf16 handles only)
+int tc_encoder_forward(const void* enc, const void* x, int n, int h, int w, void* out_rows, void* workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
+  const EncPack& e = *(const EncPack*)enc;
+  CDR_CHECK_ARG(e.kind == kKindBF16, "cdr_encoder_forward: an f16x2 encoder starts from images (cdr_encoder_forward_images)");
+  Act xa;
+  xa.fmt = kFmtBF16;
+  xa.p[0] = const_cast<void*>(x);
+  return enc_layers(e, xa, false, n, h, w, out_rows, workspace, workspace_bytes, st);
 }
 
 int tc_set_debug(unsigned int* d) {

@@ -79,5 +79,11 @@ size_t stem_weight_bytes();
 // x: fp32 NCHW (is_u8 = 0) or uint8 NHWC frames normalised on the fly with HOST arrays mean[3], std[3]
 int launch_stem(const void* x, int is_u8, const float* mean, const float* std, int n, int H, int W, const void* w,
                 const float* bias, void* conv_out, void* pooled, cudaStream_t st);
+// the same at fp32 accuracy (FFMA): fp32 weights [147][64], conv_out fp32 NHWC scratch, pooled as scaled fp16 hi/lo
+// planes; slot = {amax, scale} of the pooled tensor (amax pre-zeroed)
+int launch_pack_stem_f32(const CdrConvBn& s, float* w, float* bias, cudaStream_t st);
+size_t stem_weight_bytes_f32();
+int launch_stem_f32(const void* x, int is_u8, const float* mean, const float* std, int n, int H, int W, const float* w,
+                    const float* bias, float* conv_out, void* pooled_hi, void* pooled_lo, float* slot, cudaStream_t st);
 
 }  // namespace cdr

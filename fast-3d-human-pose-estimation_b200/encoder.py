@@ -99,10 +99,17 @@ class TcEncoder:
     pixel-major rows (n*h*w, 2048) — what ``cdr_head_forward_rows`` consumes; ``__call__`` returns
     the reference's (n, 2048, h, w) fp32 tensor."""
 
-    def __init__(self, resnet):
+    def __init__(self, resnet, precision="bf16"):
         blocks = [b for li in range(1, 5) for b in getattr(resnet, f"layer{li}")]
         if any(b.kind != "bottleneck" for b in blocks):
+            # (the reference's BasicBlock puts the stride on BOTH 3x3 convs, models/encoder.py:9-14, so its ResNet-18/34
+            # fail with a shape mismatch at layer2's residual add: there is nothing to accelerate)
             raise NotImplementedError("the tcgen05 encoder covers the Bottleneck ResNets (50/101/152)")
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"TcEncoder precision must be 'bf16' or 'fp32', got {precision!r}")
+        # 'fp32': the reference's precision on the tensor cores — scaled fp16 hi/lo planes, 3 MMAs per product, fp32
+        # FFMA stem (include/cdrhead.h: cdr_encoder_create_prec).  rows() then returns the opaque "fp16 planes" buffer
+        self.precision = precision
         self.resnet, self.blocks = resnet, blocks
         self._box, self._key, self._stem = None, None, None
         self.torch_stem = False          # True: force the cuDNN stem (A/B timing)
@@ -122,11 +129,11 @@ class TcEncoder:
 
     def __deepcopy__(self, memo):
         import copy
-        return TcEncoder(copy.deepcopy(self.resnet, memo))     # device handles are never shared or copied
+        return TcEncoder(copy.deepcopy(self.resnet, memo), self.precision)     # device handles are never shared or copied
 
     def __getstate__(self):
         return {"resnet": self.resnet, "blocks": self.blocks, "_box": None, "_key": None, "_stem": None,
-                "torch_stem": self.torch_stem}
+                "torch_stem": self.torch_stem, "precision": self.precision}
 
     def _tensors(self):
         r = self.resnet
@@ -172,7 +179,8 @@ class TcEncoder:
                                    cb(self.resnet.conv1, self.resnet.bn1))
         handle = C.c_void_p()
         with torch.cuda.device(device):
-            _lib.check(L.cdr_encoder_create(C.byref(spec), _lib.current_stream_ptr(device), C.byref(handle)))
+            prec = _lib.CDR_PREC_F16X2 if self.precision == "fp32" else _lib.CDR_PREC_BF16
+            _lib.check(L.cdr_encoder_create_prec(C.byref(spec), prec, _lib.current_stream_ptr(device), C.byref(handle)))
         # stem: BN folded into the conv, bf16 channels-last
         r = self.resnet
         sc = (r.bn1.weight.double() / torch.sqrt(r.bn1.running_var.double() + r.bn1.eps))
@@ -224,6 +232,9 @@ class TcEncoder:
         else:
             n, _, H, W = x.shape
         native_stem = H % 16 == 0 and W % 64 == 0 and (u8 or not self.torch_stem)
+        planes = self.precision == "fp32"
+        if planes and not native_stem:
+            raise ValueError("the fp32 tcgen05 encoder needs images with H % 16 == 0 and W % 64 == 0")
         if native_stem:
             xin = x.detach().contiguous() if u8 else x.detach().to(torch.float32).contiguous()
             h, w = H // 4, W // 4
@@ -241,7 +252,14 @@ class TcEncoder:
         else:
             _lib.check(L.cdr_encoder_workspace_bytes(handle, n, h, w, C.byref(nbytes)))
         ws = _wsmod.current(dev).get("encoder", dev, nbytes.value)     # per stream, or the enclosing pipeline's own
-        if out is None:
+        if planes:
+            obytes = C.c_size_t()
+            _lib.check(L.cdr_encoder_out_bytes(handle, n, h, w, C.byref(obytes)))
+            if out is None:
+                out = torch.empty(obytes.value, dtype=torch.uint8, device=dev)
+            elif out.dtype != torch.uint8 or out.numel() < obytes.value:
+                raise ValueError(f"out must be a uint8 CUDA buffer of {obytes.value} bytes")
+        elif out is None:
             out = torch.empty((n * oh.value * ow.value, oc.value), dtype=torch.bfloat16, device=dev)
         st = _lib.current_stream_ptr(dev)
         with torch.cuda.device(dev):
@@ -257,6 +275,19 @@ class TcEncoder:
                                                  nbytes.value, st))
         return out, (oh.value, ow.value, oc.value)
 
+    @staticmethod
+    def planes_to_rows(buf, rows, channels):
+        """Decode an "fp16 planes" buffer (include/cdrhead.h) into an fp32 (rows, channels) tensor — a format
+        conversion for tests and ``__call__``; the head consumes the buffer as it is."""
+        stride = -(-rows * channels * 2 // 1024) * 1024
+        hi = buf[:rows * channels * 2].view(torch.float16).reshape(rows, channels)
+        lo = buf[stride:stride + rows * channels * 2].view(torch.float16).reshape(rows, channels)
+        scale = buf[2 * stride + 4:2 * stride + 8].view(torch.float32)
+        return (hi.double() + lo.double() / 2048.0) / scale.double()
+
     def __call__(self, x):
         rows, (h, w, c) = self.rows(x)
-        return rows.reshape(x.shape[0], h, w, c).permute(0, 3, 1, 2).float()
+        n = x.shape[0]
+        if self.precision == "fp32":
+            rows = self.planes_to_rows(rows, n * h * w, c)
+        return rows.reshape(n, h, w, c).permute(0, 3, 1, 2).float()

@@ -146,6 +146,15 @@ int cdr_head_forward_rows(const CdrWeights* w, const void* feat_rows, const floa
                           int img_size, float* kp2d_l, float* kp2d_r, float* xyz, const CdrHeadTaps* taps,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* cdr_head_forward / cdr_decoder_forward on the fp16 planes buffer of a CDR_PREC_F16X2 encoder (see
+ * cdr_encoder_create_prec); CDR_PREC_F16X2 weights only. */
+int cdr_head_forward_planes(const CdrWeights* w, const void* feat_planes, const float* P_l, const float* P_r,
+                            const float* pinv_l, const float* pinv_r, double pinv_rtol, int batch,
+                            int img_size, float* kp2d_l, float* kp2d_r, float* xyz, const CdrHeadTaps* taps,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int cdr_decoder_forward_planes(const CdrWeights* w, const void* feat_planes, int n_images, float* heatmaps,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* cdr_decoder_forward on bf16 pixel-major latents (n_images*64, 2048) — PoseResNet.forward with the encoder
  * of this library (models/poseresnet.py:17-21).  Tensor-core precisions only. */
 int cdr_decoder_forward_rows(const CdrWeights* w, const void* feat_rows, int n_images, float* heatmaps,
@@ -169,7 +178,20 @@ typedef struct CdrEncoderSpec {
                                      caller runs the stem itself and uses cdr_encoder_forward only      */
 } CdrEncoderSpec;
 typedef struct CdrEncoder CdrEncoder;
-int cdr_encoder_create(const CdrEncoderSpec* spec, void* stream, CdrEncoder** out);
+int cdr_encoder_create(const CdrEncoderSpec* spec, void* stream, CdrEncoder** out);   /* CDR_PREC_BF16 */
+/* The same encoder at the reference's precision (models/encoder.py runs in fp32): precision = CDR_PREC_F16X2 keeps
+ * every activation as scaled fp16 hi/lo planes (2^-24 relative) and runs every conv as 3 kind::f16 MMAs per product
+ * (gemm_tc.cu: kKindF16X2), the residual add in the epilogue; the 7x7 stem runs in fp32 FFMA.  Such a handle
+ *   - starts from images only (cdr_encoder_forward_images / _frames_u8; cdr_encoder_forward returns CDR_ERR_INVALID),
+ *   - writes its latents as an "fp16 planes" buffer instead of bf16 rows:
+ *       [hi plane: rows*C fp16 | lo plane: rows*C fp16 | float amax, float scale]
+ *     each plane padded to a multiple of 1024 bytes, x = (hi + lo * 2^-11) / scale; size from cdr_encoder_out_bytes,
+ *     1024-byte aligned.  cdr_head_forward_planes / cdr_decoder_forward_planes consume it as conv_layer1's /
+ *     deconv1's operand without a conversion pass. */
+int cdr_encoder_create_prec(const CdrEncoderSpec* spec, int precision, void* stream, CdrEncoder** out);
+/* bytes of the latent buffer the forward functions write for (n_images, in_h, in_w) = the stem's OUTPUT grid
+ * (img/4): bf16 rows, or the fp16 planes buffer above */
+int cdr_encoder_out_bytes(const CdrEncoder* e, int n_images, int in_h, int in_w, size_t* bytes);
 int cdr_encoder_destroy(CdrEncoder* e);
 int cdr_encoder_workspace_bytes(const CdrEncoder* e, int n_images, int in_h, int in_w, size_t* bytes);
 int cdr_encoder_out_shape(const CdrEncoder* e, int in_h, int in_w, int* out_h, int* out_w, int* out_c);

@@ -682,6 +682,75 @@ def test_tc_encoder_resnet50_vs_emulated_and_fp32(cuda_pkg):
     assert e_32 < 6e-2 and m_32 < 2e-2          # stated bf16 bounds for ~50 layers of bf16 activations
 
 
+def test_tc_encoder_fp32_resnet50_vs_fp64(cuda_pkg):
+    """SURVEY §8f rank 1 at the reference's precision: the f16x2 tcgen05 encoder (scaled fp16 hi/lo planes, 3 MMAs
+    per product, residual add on planes in the epilogue, fp32 FFMA stem) against the fp64 evaluation of the same
+    network, beside the reference's own fp32 module (torch, TF32 off) against that fp64."""
+    from fast_3d_human_pose_estimation_b200.encoder import TcEncoder
+    r = _seeded_resnet(50)
+    x = torch.randn(3, 3, 256, 256, generator=torch.Generator().manual_seed(5))      # odd image count
+    with torch.no_grad():
+        import copy
+        want = copy.deepcopy(r).double()(x.double()).numpy()
+        ref32 = r(x).numpy()
+    enc = TcEncoder(r.cuda(), precision="fp32")
+    got = enc(x.cuda()).cpu().numpy()
+    assert got.shape == (3, 2048, 8, 8)
+    e = np.abs(got - want).max() / np.abs(want).max()
+    e_ref = np.abs(ref32 - want).max() / np.abs(want).max()
+    print(f"\ntcgen05 f16x2 ResNet-50 encoder vs fp64: {e:.2e} of max (reference's own fp32 on CPU: {e_ref:.2e})")
+    assert e <= 2e-5
+    # uint8 frames: the fused ToTensor + Normalize stem gives the latents of the preprocessed fp32 tensor bit for bit
+    from fast_3d_human_pose_estimation_b200.encoder import IMAGENET_MEAN, IMAGENET_STD
+    fr = torch.randint(0, 256, (2, 256, 256, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(3))
+    mean = torch.tensor(IMAGENET_MEAN).reshape(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD).reshape(1, 3, 1, 1)
+    pre = fr.permute(0, 3, 1, 2).float().div(255).sub_(mean).div_(std)
+    b_u8, _ = enc.rows(fr.cuda())
+    b_f32, _ = enc.rows(pre.cuda())
+    torch.cuda.synchronize()
+    used = 2 * (2 * 64 * 2048 * 2) + 8                # two planes + {amax, scale}; the rest of the buffer is padding
+    assert torch.equal(b_u8[:used], b_f32[:used])
+
+
+def test_full_pipeline_fp32_tc_encoder(cuda_pkg):
+    """CDRNet.forward entirely on this library at the reference's precision (encoder_precision='fp32': the encoder's
+    fp16 planes feed conv_layer1 without a conversion pass) against the fp64 oracle pipeline; flat north-star
+    tolerance on the 2D joints, 3D through the sensitivity-aware gate of check_3d."""
+    b = 2
+    torch.manual_seed(0)
+    m = cuda_pkg.CDRNet(synth.make_cfg(50, 19), precision="fp32", encoder_precision="fp32")
+    m.load_state_dict(synth.make_head_state_dict(seed=0, calibrated=True), strict=False)
+    cams = synth.make_cameras(b, seed=2)
+    P_cpu = [torch.from_numpy(cams["P_l"]), torch.from_numpy(cams["P_r"])]
+    g = torch.Generator().manual_seed(1)
+    xs_cpu = [torch.randn(b, 3, 256, 256, generator=g) for _ in range(2)]
+    sd = _head_sd_of(m)
+    with torch.no_grad():
+        import copy
+        e64 = copy.deepcopy(m.encoder).double().eval()
+        lat = [e64(x.double()) for x in xs_cpu]
+        o2, o3 = O.head_forward(O.cast_state_dict(sd, torch.float64), lat, [p.double() for p in P_cpu])
+    m = m.cuda().eval()
+    (kl, kr), xyz = m([x.cuda() for x in xs_cpu], [p.cuda() for p in P_cpu])
+    torch.cuda.synchronize()
+    d2 = max(float((kl.cpu().double() - o2[0]).abs().max()), float((kr.cpu().double() - o2[1]).abs().max()))
+    print(f"\nfull pipeline, f16x2 encoder + fp32 head vs the fp64 oracle pipeline: d2D max {d2:.2e} px")
+    assert d2 <= 1e-3
+    check_3d(cams, kl, kr, xyz, [o.numpy() for o in o2], o3.numpy(), label="full pipeline f16x2 encoder", flat=False)
+    # PoseResNet on the same encoder: heat-maps vs the fp64 oracle decoder
+    pr = cuda_pkg.PoseResNet(synth.make_cfg(50, 19), precision="fp32", encoder_precision="fp32")
+    pr.encoder.load_state_dict(m.encoder.state_dict())
+    pr.decoder.load_state_dict(m.decoder.state_dict())
+    pr = pr.cuda().eval()
+    hm = pr(xs_cpu[0].cuda()).cpu().double()
+    with torch.no_grad():
+        want = O.decoder(O.cast_state_dict(sd, torch.float64), lat[0])
+    e = float((hm - want).abs().max() / want.abs().max())
+    print(f"PoseResNet f16x2 encoder + decoder heat-maps vs fp64: {e:.2e} of max")
+    assert e <= 2e-5
+
+
 def _head_sd_of(m):
     return {k: v.detach().cpu() for k, v in m.state_dict().items() if k.startswith(("CF.", "decoder."))}
 
