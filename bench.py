@@ -880,9 +880,14 @@ def full_pipeline(args, ctx, precision):
     del enc, xcl
     x2 = torch.cat(xs, 0)
     gt = {"gt3d": ctx["g3"], "gt2d_l": ctx["g2l"], "gt2d_r": ctx["g2r"], "vis": ctx["vis"]}
-    for head_prec in dict.fromkeys([precision, "bf16"]):
+    # (encoder precision, head precision): the bf16 encoder with this run's head and with the bf16 head; and — the
+    # pipeline at the REFERENCE's precision end to end — the f16x2 encoder feeding the fp32 head fp16 planes
+    combos = [("bf16", hp) for hp in dict.fromkeys([precision, "bf16"])]
+    if precision in ("fp32", "f16x2"):
+        combos.append(("fp32", precision))
+    for enc_prec, head_prec in combos:
         torch.manual_seed(0)
-        m2 = pkg.CDRNet(synth.make_cfg(101, JOINTS), precision=head_prec, encoder_precision="bf16")
+        m2 = pkg.CDRNet(synth.make_cfg(101, JOINTS), precision=head_prec, encoder_precision=enc_prec)
         m2.load_state_dict(ctx["sd"], strict=False)
         m2 = m2.to(dev).eval()
         ms = timed(lambda: m2(xs, ctx["Ps"]))
@@ -930,7 +935,13 @@ def full_pipeline(args, ctx, precision):
                 del pipe, frames_h
             except Exception as e:
                 rec["e2e_uint8_frames_host" + ("" if bb == B else f"_batch{bb}")] = {"error": repr(e)[:200]}
-        out["encoder_bf16_tcgen05" + ("" if head_prec == precision else "_head_bf16")] = rec
+        if enc_prec == "fp32":
+            rec["precision"] = ("encoder: scaled fp16 hi/lo planes, 3 kind::f16 MMAs per product, fp32 FFMA stem (latents "
+                                "1.5e-6 of max vs fp64 on ResNet-50); head: fp32 mode")
+            rec["encoder_tflops_issued_mma"] = 3 * rec["encoder_tflops"]
+            out["encoder_f16x2_tcgen05"] = rec
+        else:
+            out["encoder_bf16_tcgen05" + ("" if head_prec == precision else "_head_bf16")] = rec
         del m2
         torch.cuda.empty_cache()
     del x2

@@ -6,7 +6,7 @@ from fast_3d_human_pose_estimation_b200 import synth, _lib
 from fast_3d_human_pose_estimation_b200.encoder import ResNet, TcEncoder
 torch.manual_seed(0)
 r = ResNet(synth.make_cfg(101, 19)).cuda().eval()
-enc = TcEncoder(r)
+enc = TcEncoder(r, precision=sys.argv[1] if len(sys.argv) > 1 else "bf16")
 x = torch.randn(128, 3, 256, 256, device="cuda")
 print("native stem" if not enc.torch_stem else "torch stem")
 for _ in range(3):
@@ -20,7 +20,7 @@ for _ in range(reps):
     for name, ms in _lib.stage_timing_end():
         acc[name] = acc.get(name, 0.0) + ms / reps
 tot = sum(acc.values())
-print(f"total layers {tot:.3f} ms")
+print(f"total layers {tot:.3f} ms;", " ".join(f"{k}={v*1e3:.0f}" for k, v in acc.items() if not k.startswith("enc_block")))
 # geometry per block for flops / bytes
 H = 64; cin = 64
 spec = [(64, 3, 1), (128, 4, 2), (256, 23, 2), (512, 3, 2)]
