@@ -11,9 +11,9 @@ for p in fp32 bf16; do
   ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_$p.csv $B > $O/ncu_bench_$p.log 2>&1
   S="python devtools/stage_times.py $p 64 2"
   $S > $O/plain_stage_$p.log 2>&1 &&
-  # 3 warm-up steps of 13 (fp32: with the amax pass) / 12 (bf16) kernels of this library: start at a step boundary
-  if [ $p = fp32 ]; then SKIP=39; else SKIP=36; fi
-  ncu --set full --clock-control none -k "$K" -s $SKIP -c 13 -f -o /tmp/prof_step_$p $S > $O/ncu_step_$p.log 2>&1
+  # 3 warm-up steps of 12 kernels of this library (both modes: the fp32 layout pass is one launch now): start at a step boundary
+  SKIP=36
+  ncu --set full --clock-control none -k "$K" -s $SKIP -c 12 -f -o /tmp/prof_step_$p $S > $O/ncu_step_$p.log 2>&1
   ncu -i /tmp/prof_step_$p.ncu-rep --page raw --csv > $O/prof_step_$p.raw.csv 2>/dev/null
   $S > /dev/null 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:deconv_tail -s 3 -c 1 -f -o $O/prof_tail_$p $S > $O/ncu_tail_$p.log 2>&1

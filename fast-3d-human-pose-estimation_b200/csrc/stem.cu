@@ -260,7 +260,7 @@ __global__ void pack_stem_f32_kernel(CdrConvBn s, float* __restrict__ w, float* 
 // pxg + 8*i, i < 4; cg = lane & 3: channels 16*j + 4*cg .. +3, j < 4) -> 4 x 16 outputs per thread.  Patch reads of a
 // warp hit 8 distinct banks (stride 6 floats), weight reads are one 64-byte segment per float4 load.
 template <bool kU8>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)      // two CTAs per SM: one loads its patch while the other runs its FMAs
 stem_conv_f32_kernel(const void* __restrict__ xin, int H, int W, const StemNorm nrm, const float* __restrict__ wpk,
                      const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ amax_out) {
   extern __shared__ __align__(16) float smem_f[];

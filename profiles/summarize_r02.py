@@ -106,8 +106,8 @@ def traffic():
             continue
         unit, recs = res
         # the capture starts at a step boundary (devtools/ncu_r02.sh): stages in launch order
-        order = ["pinv"] + (["amax"] if tag == "fp32" else []) + ["nchw_to_rows", "cf_conv1", "ftl_inv", "cf_conv2a", "cf_conv2b",
-                                                                  "ftl_fwd", "cf_out", "deconv1", "deconv2", "deconv3_tail", "merge_dlt"]
+        order = ["pinv", "nchw_to_rows", "cf_conv1", "ftl_inv", "cf_conv2a", "cf_conv2b", "ftl_fwd", "cf_out", "deconv1", "deconv2",
+                 "deconv3_tail", "merge_dlt"]
         t = {}
         if recs and recs[0]["kernel"].startswith("pinv2"):
             for nm, r in zip(order, recs):
