@@ -714,7 +714,7 @@ def backward_stream(dev, poses=4096, reps=5):
             "input": f"{poses} poses x 19 joints x 2 views of 64x64 fp32 logits ({heat.numel() * 4 / 1e9:.1f} GB in, the same out)"}
 
 
-def config5(args, ctx, precision, total=1024):
+def config5(args, ctx, precision, total=1024, encoder_precision="bf16"):
     """BASELINE configs[4]: the full pipeline (uint8 stereo frames in pinned HOST memory -> ResNet-101 encoder
     + head on this repo's kernels -> 3D joints + MPJPE sums on the host) over a batch of `total` stereo pairs
     sharded across the ranks (strong scaling: total/N pairs per GPU), processed in chunks of --batch pairs
@@ -729,7 +729,7 @@ def config5(args, ctx, precision, total=1024):
     pipe, err = None, None
     try:
         torch.manual_seed(0)
-        m = pkg.CDRNet(synth.make_cfg(101, JOINTS), precision=precision, encoder_precision="bf16")
+        m = pkg.CDRNet(synth.make_cfg(101, JOINTS), precision=precision, encoder_precision=encoder_precision)
         m.load_state_dict(ctx["sd"], strict=False)
         m = m.to(dev).eval()
         gen = torch.Generator().manual_seed(7 + rank)
@@ -824,6 +824,8 @@ def config5(args, ctx, precision, total=1024):
             "workload": "BASELINE configs[4]: full pipeline, %d stereo pairs sharded over %d GPU(s)" % (per * world, world),
             "pairs_per_s": per * world / (best / 1e3), "ms_total": best, "n_gpus": world, "pairs_per_gpu": per,
             "chunk_pairs": B, "chunks_per_gpu": n_chunks, "scaling": "strong", "head_precision": precision,
+            "encoder_precision": {"bf16": "bf16 (tcgen05, below the reference's fp32)",
+                                  "fp32": "f16x2 (tcgen05, fp32-accurate: the reference's precision)"}[encoder_precision],
             "mpjpe_count": count, "h2d_bytes_per_gpu": n_chunks * (frames_h[0].numel() + 2 * B * 48),
             "collective": "1 all-gather of (%d,19,3) fp32 + 32 B per rank at the end" % per,
             "api": "FramePipeline per rank (uint8 frames in pinned host memory; ResNet-101 encoder + head on this repo's kernels)"}
@@ -985,7 +987,7 @@ def full_pipeline_sharded(args, ctx, precision):
     pipe, err = None, None
     try:
         torch.manual_seed(0)
-        m = pkg.CDRNet(synth.make_cfg(101, JOINTS), precision=precision, encoder_precision="bf16")
+        m = pkg.CDRNet(synth.make_cfg(101, JOINTS), precision=precision, encoder_precision=encoder_precision)
         m.load_state_dict(ctx["sd"], strict=False)
         m = m.to(dev).eval()
         gen = torch.Generator().manual_seed(7 + rank)
@@ -1069,10 +1071,15 @@ def run_ours(args):
     fp_multi = None
     if world > 1 and not args.no_full_pipeline:
         fp_multi = full_pipeline_sharded(args, ctx, args.precision)      # every rank takes part (collectives)
-    c5 = None
+    c5, c5_bf16 = None, None
     if not args.no_full_pipeline and not args.no_config5:
+        # at the reference's precision end to end (f16x2 encoder + fp32 head) when this run's head is the fp32 one; the
+        # bf16 encoder (faster, below the reference's precision) is reported next to it
+        ref_prec = args.precision in ("fp32", "f16x2")
         try:
-            c5 = config5(args, ctx, args.precision)                      # every rank takes part (collectives)
+            c5 = config5(args, ctx, args.precision, encoder_precision="fp32" if ref_prec else "bf16")   # every rank takes part
+            if ref_prec:
+                c5_bf16 = config5(args, ctx, args.precision, encoder_precision="bf16")
         except Exception as e:
             if world > 1:
                 raise
@@ -1127,6 +1134,8 @@ def run_ours(args):
             line["full_pipeline"] = fp_multi
         if c5 is not None:
             line["config5_full_pipeline_1024_pairs"] = c5
+            if c5_bf16 is not None:
+                line["config5_full_pipeline_1024_pairs_encoder_bf16"] = c5_bf16
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
