@@ -39,7 +39,8 @@ class CdrConvBn(C.Structure):
 class CdrWeightPtrs(C.Structure):
     _fields_ = [("num_joints", C.c_int), ("has_fusion", C.c_int),
                 ("cf_conv1", CdrConvBn), ("cf_conv2a", CdrConvBn), ("cf_conv2b", CdrConvBn),
-                ("cf_out", CdrConvBn * 2), ("deconv", CdrConvBn * 3), ("final_layer", CdrConvBn)]
+                ("cf_out", CdrConvBn * 2), ("deconv", CdrConvBn * 3), ("final_layer", CdrConvBn),
+                ("fusion_hid_ch1", C.c_int), ("fusion_hid_ch2", C.c_int)]
 
 
 class CdrHeadTaps(C.Structure):

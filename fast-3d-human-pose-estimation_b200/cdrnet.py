@@ -238,6 +238,8 @@ class _PackedWeights:
             src.cf_conv2b = _convbn(cf.conv_layer2[3], cf.conv_layer2[4])
             for v in range(2):
                 src.cf_out[v] = _convbn(cf.out_layer[v][0], cf.out_layer[v][1])
+            src.fusion_hid_ch1 = cf.conv_layer1[0].out_channels          # 0 / 0 would mean the defaults 300 / 400
+            src.fusion_hid_ch2 = cf.conv_layer2[3].out_channels
         for i in range(3):
             src.deconv[i] = _convbn(dec[i][0], dec[i][1])
         src.final_layer = _convbn(dec[3], None)
@@ -290,10 +292,19 @@ class CDRNet(nn.Module):
         if encoder_precision == "fp32" and precision not in ("fp32", "f16x2"):
             raise ValueError("encoder_precision='fp32' (fp16-plane latents) needs the fp32 head (precision='fp32')")
         self.encoder_precision = encoder_precision
-        if n_views != 2 or fusion_in_dim != 2048 or fusion_hid_ch1 != 300 or fusion_hid_ch2 != 400:
+        if n_views != 2 or fusion_in_dim != 2048:
+            # the reference itself only runs in this configuration: CanonicalFusion has exactly two out_layer heads and
+            # forward returns views 0 and 1 (models/cdrnet.py:32-43,255), the decoder takes 2048 channels
+            # (models/decoder.py:8-9) — shown on the unmodified reference in tests/test_oracle_golden.py
             raise NotImplementedError(
-                "libcdrhead is built for the reference's stereo configuration "
-                "(n_views=2, fusion 2048/300/400, models/cdrnet.py:89-91)")
+                "n_views must be 2 and fusion_in_dim 2048: the reference's own forward fails otherwise "
+                "(models/cdrnet.py:32-43,255, models/decoder.py:8-9)")
+        if fusion_hid_ch2 * 3 != fusion_hid_ch1 * 4:
+            raise ValueError(
+                f"fusion_hid_ch2 must be 4/3 of fusion_hid_ch1 (got {fusion_hid_ch1} / {fusion_hid_ch2}): the 4x3 / 3x4 "
+                "feature transforms map 3 channel blocks to 4 and back (models/cdrnet.py:45-56,65,79)")
+        if fusion_hid_ch1 % 12 != 0 or not 12 <= fusion_hid_ch1 <= 3072:
+            raise NotImplementedError("fusion_hid_ch1 must be a multiple of 12 in 12..3072 (FTL blocks of whole 128-bit vectors)")
         self.encoder = ResNet(cfg)
         self.CF = CanonicalFusion(in_dim=fusion_in_dim, hid_ch1=fusion_hid_ch1,
                                   hid_ch2=fusion_hid_ch2, n_views=n_views)
@@ -372,8 +383,8 @@ class CDRNet(nn.Module):
         if taps:
             tap_out = {
                 "pinv": torch.empty((2, b, 4, 3), dtype=torch.float32, device=dev),
-                "cf_cat": torch.empty((b, 64, 800), dtype=torch.float32, device=dev),
-                "cf_f": torch.empty((b, 64, 400), dtype=torch.float32, device=dev),
+                "cf_cat": torch.empty((b, 64, 2 * self.CF.conv_layer2[3].out_channels), dtype=torch.float32, device=dev),
+                "cf_f": torch.empty((b, 64, self.CF.conv_layer2[3].out_channels), dtype=torch.float32, device=dev),
                 "f_out": torch.empty((2, b, 64, 2048), dtype=torch.float32, device=dev),
                 "heatmaps": torch.empty((2, b, j, 64, 64), dtype=torch.float32, device=dev),
             }

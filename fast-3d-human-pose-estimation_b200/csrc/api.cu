@@ -72,6 +72,7 @@ using namespace cdr;
 // ------------------------------------------------------------------------------------------
 struct CdrWeights {
   int precision = 0, joints = 0, has_fusion = 0, fin_npad = 0;
+  FusionDims fd;
   void* pool = nullptr;
   // fp32 path: B operands as [K][n_pad]
   float *w_cf1 = nullptr, *b_cf1 = nullptr, *w_cf2a = nullptr, *b_cf2a = nullptr;
@@ -81,18 +82,18 @@ struct CdrWeights {
   TcWeights tc;  // bf16 tensor-core path (gemm_tc.cu)
 };
 
-static constexpr int kCf1NPad = 384, kCf2NPad = 512;
 static const int kDcCin[3] = {kFeatC, kDecC, kDecC};
 
 static void plan_fp32_weights(CdrWeights& w, Bump& b) {
+  const FusionDims& fd = w.fd;
   if (w.has_fusion) {
-    w.w_cf1 = b.take<float>((size_t)kFeatC * kCf1NPad);
-    w.b_cf1 = b.take<float>(kCf1NPad);
-    w.w_cf2a = b.take<float>((size_t)2 * kHid2 * kCf2NPad);
-    w.b_cf2a = b.take<float>(kCf2NPad);
-    w.w_cf2b = b.take<float>((size_t)kHid2 * kCf2NPad);
-    w.b_cf2b = b.take<float>(kCf2NPad);
-    w.w_out = b.take<float>((size_t)2 * kHid1Pad * kFeatC);
+    w.w_cf1 = b.take<float>((size_t)kFeatC * fd.n1_pad());
+    w.b_cf1 = b.take<float>(fd.n1_pad());
+    w.w_cf2a = b.take<float>((size_t)2 * fd.h2 * fd.n2_pad());
+    w.b_cf2a = b.take<float>(fd.n2_pad());
+    w.w_cf2b = b.take<float>((size_t)fd.h2 * fd.n2_pad());
+    w.b_cf2b = b.take<float>(fd.n2_pad());
+    w.w_out = b.take<float>((size_t)2 * fd.h1p * kFeatC);
     w.b_out = b.take<float>((size_t)2 * kFeatC);
   }
   for (int i = 0; i < 3; ++i) {
@@ -163,6 +164,15 @@ extern "C" int cdr_weights_create(const CdrWeightPtrs* src, int precision, void*
   w->joints = src->num_joints;
   w->has_fusion = src->has_fusion;
   w->fin_npad = src->num_joints <= 32 ? 32 : round_up(src->num_joints, 128);
+  if (src->has_fusion && (src->fusion_hid_ch1 || src->fusion_hid_ch2)) {
+    if (!fusion_dims_ok(src->fusion_hid_ch1, src->fusion_hid_ch2)) {
+      set_error("cdr_weights_create: fusion widths %d / %d: need hid_ch2 = 4/3 hid_ch1 (the reference's ftl) and "
+                "hid_ch1 %% 12 == 0", src->fusion_hid_ch1, src->fusion_hid_ch2);
+      delete w;
+      return CDR_ERR_UNSUPPORTED;
+    }
+    w->fd = make_fusion_dims(src->fusion_hid_ch1, src->fusion_hid_ch2);
+  }
 
   int rc = CDR_OK;
   auto fail = [&](int code) {
@@ -183,12 +193,12 @@ extern "C" int cdr_weights_create(const CdrWeightPtrs* src, int precision, void*
     Bump b(w->pool);
     plan_fp32_weights(*w, b);
     if (w->has_fusion) {
-      if ((rc = launch_pack_conv1x1_f32(src->cf_conv1, kHid1, kFeatC, kFeatC, kCf1NPad, w->w_cf1, w->b_cf1, st))) return fail(rc);
-      if ((rc = launch_pack_conv1x1_f32(src->cf_conv2a, kHid2, 2 * kHid2, 2 * kHid2, kCf2NPad, w->w_cf2a, w->b_cf2a, st))) return fail(rc);
-      if ((rc = launch_pack_conv1x1_f32(src->cf_conv2b, kHid2, kHid2, kHid2, kCf2NPad, w->w_cf2b, w->b_cf2b, st))) return fail(rc);
+      if ((rc = launch_pack_conv1x1_f32(src->cf_conv1, w->fd.h1, kFeatC, kFeatC, w->fd.n1_pad(), w->w_cf1, w->b_cf1, st))) return fail(rc);
+      if ((rc = launch_pack_conv1x1_f32(src->cf_conv2a, w->fd.h2, 2 * w->fd.h2, 2 * w->fd.h2, w->fd.n2_pad(), w->w_cf2a, w->b_cf2a, st))) return fail(rc);
+      if ((rc = launch_pack_conv1x1_f32(src->cf_conv2b, w->fd.h2, w->fd.h2, w->fd.h2, w->fd.n2_pad(), w->w_cf2b, w->b_cf2b, st))) return fail(rc);
       for (int v = 0; v < 2; ++v)
-        if ((rc = launch_pack_conv1x1_f32(src->cf_out[v], kFeatC, kHid1, kHid1Pad, kFeatC,
-                                          w->w_out + (size_t)v * kHid1Pad * kFeatC,
+        if ((rc = launch_pack_conv1x1_f32(src->cf_out[v], kFeatC, w->fd.h1, w->fd.h1p, kFeatC,
+                                          w->w_out + (size_t)v * w->fd.h1p * kFeatC,
                                           w->b_out + (size_t)v * kFeatC, st)))
           return fail(rc);
     }
@@ -224,17 +234,17 @@ struct HeadWs {
   float *pinv, *x0, *y1, *z, *f1, *f2, *g, *x1, *d1, *d2, *d3, *hm;
   size_t bytes;
 };
-static HeadWs plan_head_f32(void* base, int B, int J) {
+static HeadWs plan_head_f32(void* base, int B, int J, const FusionDims& fd) {
   Bump b(base);
   const size_t N = 2 * (size_t)B;
   HeadWs w;
   w.pinv = b.take<float>(N * 12);
   w.x0 = b.take<float>(N * kFeatHW * kFeatC);
-  w.y1 = b.take<float>(N * kFeatHW * kHid1Pad);
-  w.z = b.take<float>((size_t)B * kFeatHW * 2 * kHid2);
-  w.f1 = b.take<float>((size_t)B * kFeatHW * kHid2);
-  w.f2 = b.take<float>((size_t)B * kFeatHW * kHid2);
-  w.g = b.take<float>(N * kFeatHW * kHid1Pad);
+  w.y1 = b.take<float>(N * kFeatHW * fd.h1p);
+  w.z = b.take<float>((size_t)B * kFeatHW * 2 * fd.h2);
+  w.f1 = b.take<float>((size_t)B * kFeatHW * fd.h2);
+  w.f2 = b.take<float>((size_t)B * kFeatHW * fd.h2);
+  w.g = b.take<float>(N * kFeatHW * fd.h1p);
   w.x1 = b.take<float>(N * kFeatHW * kFeatC);
   w.d1 = b.take<float>(N * 256 * kDecC);
   w.d2 = b.take<float>(N * 1024 * kDecC);
@@ -262,7 +272,7 @@ extern "C" int cdr_head_workspace_bytes(const CdrWeights* w, int batch, size_t* 
   CDR_CHECK_ARG(w && bytes && batch > 0, "cdr_head_workspace_bytes: bad args");
   CDR_CHECK_ARG(w->has_fusion, "cdr_head_workspace_bytes: decoder-only weights");
   if (w->precision != CDR_PREC_FP32) return tc_head_workspace_bytes(w->tc, batch, bytes);
-  *bytes = plan_head_f32(nullptr, batch, w->joints).bytes;
+  *bytes = plan_head_f32(nullptr, batch, w->joints, w->fd).bytes;
   return CDR_OK;
 }
 extern "C" int cdr_decoder_workspace_bytes(const CdrWeights* w, int n_images, size_t* bytes) {
@@ -351,12 +361,13 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
                            kp2d_l, kp2d_r, xyz, taps, workspace, workspace_bytes, st);
 
   const int B = batch, N = 2 * batch, J = w->joints;
-  HeadWs ws = plan_head_f32(workspace, B, J);
+  HeadWs ws = plan_head_f32(workspace, B, J, w->fd);
   if (ws.bytes > workspace_bytes) {
     set_error("cdr_head_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
     return CDR_ERR_WORKSPACE;
   }
   int rc;
+  const FusionDims& fd = w->fd;
   // (1) P^+  — models/cdrnet.py:236-237
   set_stage("pinv");
   const float* pinv[2] = {pinv_l, pinv_r};
@@ -373,27 +384,27 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
   {
     TapGemmParams p{};
     p.A = ws.x0; p.a_pitch = kFeatC; p.n_img = N; p.H = p.W = 8; p.cin = kFeatC;
-    p.Wp = w->w_cf1; p.bias = w->b_cf1; p.n_pad = kCf1NPad; p.n = kHid1;
-    p.C = ws.y1; p.c_pitch = kHid1Pad; p.c_fill = kHid1Pad; p.relu = 1; p.out_mode = kOutRows;
+    p.Wp = w->w_cf1; p.bias = w->b_cf1; p.n_pad = fd.n1_pad(); p.n = fd.h1;
+    p.C = ws.y1; p.c_pitch = fd.h1p; p.c_fill = fd.h1p; p.relu = 1; p.out_mode = kOutRows;
     if ((rc = launch_tap_gemm_ffma(p, 1, st))) return rc;
   }
   // (4) inverse FTL into the concatenated (B,64,800) buffer — :65,70
   set_stage("ftl_inv");
   {
-    const float* ins[2] = {ws.y1, ws.y1 + (size_t)B * kFeatHW * kHid1Pad};
-    float* outs[2] = {ws.z, ws.z + kHid2};
-    if ((rc = launch_ftl2<float>(ins, kHid1Pad, pinv, 4, 3, kFtlBlk, B, kFeatHW, outs, 2 * kHid2, kHid2, 2, st)))
+    const float* ins[2] = {ws.y1, ws.y1 + (size_t)B * kFeatHW * fd.h1p};
+    float* outs[2] = {ws.z, ws.z + fd.h2};
+    if ((rc = launch_ftl2<float>(ins, fd.h1p, pinv, 4, 3, fd.blk, B, kFeatHW, outs, 2 * fd.h2, fd.h2, 2, st)))
       return rc;
   }
   // (5) conv_layer2: 800 -> 400 -> 400 — :74
   set_stage("cf_conv2");
   {
     TapGemmParams p{};
-    p.A = ws.z; p.a_pitch = 2 * kHid2; p.n_img = B; p.H = p.W = 8; p.cin = 2 * kHid2;
-    p.Wp = w->w_cf2a; p.bias = w->b_cf2a; p.n_pad = kCf2NPad; p.n = kHid2;
-    p.C = ws.f1; p.c_pitch = kHid2; p.c_fill = kHid2; p.relu = 1; p.out_mode = kOutRows;
+    p.A = ws.z; p.a_pitch = 2 * fd.h2; p.n_img = B; p.H = p.W = 8; p.cin = 2 * fd.h2;
+    p.Wp = w->w_cf2a; p.bias = w->b_cf2a; p.n_pad = fd.n2_pad(); p.n = fd.h2;
+    p.C = ws.f1; p.c_pitch = fd.h2; p.c_fill = fd.h2; p.relu = 1; p.out_mode = kOutRows;
     if ((rc = launch_tap_gemm_ffma(p, 1, st))) return rc;
-    p.A = ws.f1; p.a_pitch = kHid2; p.cin = kHid2; p.Wp = w->w_cf2b; p.bias = w->b_cf2b; p.C = ws.f2;
+    p.A = ws.f1; p.a_pitch = fd.h2; p.cin = fd.h2; p.Wp = w->w_cf2b; p.bias = w->b_cf2b; p.C = ws.f2;
     if ((rc = launch_tap_gemm_ffma(p, 1, st))) return rc;
   }
   // (6) forward FTL per view — :79
@@ -401,17 +412,17 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
   const float* Pv[2] = {P_l, P_r};
   {
     const float* ins[2] = {ws.f2, ws.f2};
-    float* outs[2] = {ws.g, ws.g + (size_t)B * kFeatHW * kHid1Pad};
-    if ((rc = launch_ftl2<float>(ins, kHid2, Pv, 3, 4, kFtlBlk, B, kFeatHW, outs, kHid1Pad, kHid1Pad, 2, st)))
+    float* outs[2] = {ws.g, ws.g + (size_t)B * kFeatHW * fd.h1p};
+    if ((rc = launch_ftl2<float>(ins, fd.h2, Pv, 3, 4, fd.blk, B, kFeatHW, outs, fd.h1p, fd.h1p, 2, st)))
       return rc;
   }
   // (7) out_layer[v] 300 -> 2048, per-view weights = 2 groups — :81
   set_stage("cf_out");
   {
     TapGemmParams p{};
-    p.A = ws.g; p.a_group_stride = (long long)B * kFeatHW * kHid1Pad; p.a_pitch = kHid1Pad;
-    p.n_img = B; p.H = p.W = 8; p.cin = kHid1Pad;
-    p.Wp = w->w_out; p.w_group_stride = (long long)kHid1Pad * kFeatC;
+    p.A = ws.g; p.a_group_stride = (long long)B * kFeatHW * fd.h1p; p.a_pitch = fd.h1p;
+    p.n_img = B; p.H = p.W = 8; p.cin = fd.h1p;
+    p.Wp = w->w_out; p.w_group_stride = (long long)fd.h1p * kFeatC;
     p.bias = w->b_out; p.bias_group_stride = kFeatC; p.n_pad = kFeatC; p.n = kFeatC;
     p.C = ws.x1; p.c_group_stride = (long long)B * kFeatHW * kFeatC; p.c_pitch = kFeatC;
     p.c_fill = kFeatC; p.relu = 1; p.out_mode = kOutRows;
@@ -429,8 +440,8 @@ extern "C" int cdr_head_forward(const CdrWeights* w, const float* feat_l, const 
   if (taps) {
     if ((rc = copy_tap(taps->pinv, pinv[0], (size_t)B * 12, st))) return rc;
     if ((rc = copy_tap(taps->pinv ? taps->pinv + (size_t)B * 12 : nullptr, pinv[1], (size_t)B * 12, st))) return rc;
-    if ((rc = copy_tap(taps->cf_cat, ws.z, (size_t)B * kFeatHW * 2 * kHid2, st))) return rc;
-    if ((rc = copy_tap(taps->cf_f, ws.f2, (size_t)B * kFeatHW * kHid2, st))) return rc;
+    if ((rc = copy_tap(taps->cf_cat, ws.z, (size_t)B * kFeatHW * 2 * fd.h2, st))) return rc;
+    if ((rc = copy_tap(taps->cf_f, ws.f2, (size_t)B * kFeatHW * fd.h2, st))) return rc;
     if ((rc = copy_tap(taps->f_out, ws.x1, (size_t)N * kFeatHW * kFeatC, st))) return rc;
     if ((rc = copy_tap(taps->heatmaps, ws.hm, (size_t)N * J * 4096, st))) return rc;
   }

@@ -101,6 +101,20 @@ constexpr int kHid1 = 300;     // fusion_hid_ch1
 constexpr int kHid1Pad = 304;  // channel pitch of 300-channel buffers (16-B rows for bf16, K%16 for fp32)
 constexpr int kHid2 = 400;     // fusion_hid_ch2
 constexpr int kFtlBlk = 100;   // channels per FTL "coordinate" block: 300/3 = 400/4
+// Runtime fusion widths (models/cdrnet.py:89-91: fusion_hid_ch1 / fusion_hid_ch2; the defaults above).  The reference's
+// forward only type-checks when hid_ch2 = 4/3 hid_ch1 (the 4x3 / 3x4 feature transforms map 3 blocks to 4 and back);
+// this library additionally wants the block size to be a multiple of 4 (128-bit FTL, 16-byte rows): hid_ch1 % 12 == 0.
+struct FusionDims {
+  int h1 = kHid1, h1p = kHid1Pad, h2 = kHid2, blk = kFtlBlk;
+  int n1_pad() const { return (h1 + 127) / 128 * 128; }     // packed output channels of conv_layer1 (N tiles of 128)
+  int n2_pad() const { return (h2 + 127) / 128 * 128; }
+};
+inline bool fusion_dims_ok(int h1, int h2) { return h1 >= 12 && h1 % 12 == 0 && h1 <= 3072 && h2 * 3 == h1 * 4; }
+inline FusionDims make_fusion_dims(int h1, int h2) {
+  FusionDims d;
+  if (h1 > 0) { d.h1 = h1; d.h2 = h2; d.h1p = (h1 + 15) / 16 * 16; d.blk = h1 / 3; }
+  return d;
+}
 constexpr int kDecC = 256;     // deconv output channels
 constexpr int kHeat = 64;      // heat-map side
 constexpr int kMaxJoints = 64;

@@ -1648,10 +1648,12 @@ static size_t plan_tc_weights(TcPack& pk, const TcWeights& w, void* base) {
     // conv_layer1 reads the encoder's latents (post-ReLU, bounded): in hybrid mode it runs f16x2 like the
     // decoder (half the MMA time of 3xTF32 at K = 2048); its output feeds the FTL, so it stays tf32 planes
     const bool f16 = fk == kKindF16X2;      // every fusion output is stored in kFmtF16P: each layer needs its norms
-    plan_layer(pk.cf1, b, pk.mode == kModeHybrid ? kKindF16X2 : fk, 384, kFeatC, kFeatC, 128, 384, 384, f16);
-    plan_layer(pk.cf2a, b, fk, 512, 2 * kHid2, 2 * kHid2, 128, 512, 512, f16);
-    plan_layer(pk.cf2b, b, fk, 512, kHid2, kHid2, 128, 512, 512, f16);
-    plan_layer(pk.out, b, fk, 2 * kFeatC, kHid1, kHid1Pad, bn_f, kFeatC, 2 * kFeatC, scaled);
+    const FusionDims& fd = w.fd;
+    const int n1 = fd.n1_pad(), n2 = fd.n2_pad();
+    plan_layer(pk.cf1, b, pk.mode == kModeHybrid ? kKindF16X2 : fk, n1, kFeatC, kFeatC, 128, n1, n1, f16);
+    plan_layer(pk.cf2a, b, fk, n2, 2 * fd.h2, 2 * fd.h2, 128, n2, n2, f16);
+    plan_layer(pk.cf2b, b, fk, n2, fd.h2, fd.h2, 128, n2, n2, f16);
+    plan_layer(pk.out, b, fk, 2 * kFeatC, fd.h1, fd.h1p, bn_f, kFeatC, 2 * kFeatC, scaled);
   }
   for (int i = 0; i < 3; ++i)
     plan_layer(pk.dc[i], b, dk, 4 * kDecC, 4 * kTcDcCin[i], 4 * kTcDcCin[i], bn_d, kDecC, kDecC, scaled);
@@ -1676,6 +1678,7 @@ int tc_weights_create(const CdrWeightPtrs& src, int mode, TcWeights& w, cudaStre
   w.has_fusion = src.has_fusion;
   w.fin_npad = round_up(src.num_joints, 32);
   w.kind = mode;
+  w.fd = make_fusion_dims(src.fusion_hid_ch1, src.fusion_hid_ch2);     // validated by cdr_weights_create
   TcPack* pk = new TcPack();
   pk->mode = mode;
   w.impl = pk;
@@ -1711,11 +1714,12 @@ int tc_weights_create(const CdrWeightPtrs& src, int mode, TcWeights& w, cudaStre
   };
   int rc;
   if (w.has_fusion) {
-    if ((rc = pack1(src.cf_conv1, kHid1, kFeatC, pk->cf1, 0, 0))) return rc;
-    if ((rc = pack1(src.cf_conv2a, kHid2, 2 * kHid2, pk->cf2a, 0, 0))) return rc;
-    if ((rc = pack1(src.cf_conv2b, kHid2, kHid2, pk->cf2b, 0, 0))) return rc;
+    const FusionDims& fd = w.fd;
+    if ((rc = pack1(src.cf_conv1, fd.h1, kFeatC, pk->cf1, 0, 0))) return rc;
+    if ((rc = pack1(src.cf_conv2a, fd.h2, 2 * fd.h2, pk->cf2a, 0, 0))) return rc;
+    if ((rc = pack1(src.cf_conv2b, fd.h2, fd.h2, pk->cf2b, 0, 0))) return rc;
     for (int v = 0; v < 2; ++v)
-      if ((rc = pack1(src.cf_out[v], kFeatC, kHid1, pk->out, (size_t)v * kFeatC, (size_t)v * kFeatC))) return rc;
+      if ((rc = pack1(src.cf_out[v], kFeatC, fd.h1, pk->out, (size_t)v * kFeatC, (size_t)v * kFeatC))) return rc;
     if ((rc = layer_maps(pk->cf1)) || (rc = layer_maps(pk->cf2a)) || (rc = layer_maps(pk->cf2b)) ||
         (rc = layer_maps(pk->out)))
       return rc;
@@ -1774,7 +1778,7 @@ static Act take_act(Bump1K& b, size_t elems, int fmt) {
   a.p[1] = fmt_planes(fmt) == 2 ? b.take(elems * fmt_elem(fmt)) : nullptr;
   return a;
 }
-static TcHeadWs plan_tc_head(void* base, int B, int J, int mode, int fusion_kind) {
+static TcHeadWs plan_tc_head(void* base, int B, int J, int mode, int fusion_kind, const FusionDims& fd) {
   Bump1K b(base);
   const size_t N = 2 * (size_t)B;
   const int ff = kind_fmt(fusion_kind), df = kind_fmt(mode_decoder_kind(mode));
@@ -1783,11 +1787,11 @@ static TcHeadWs plan_tc_head(void* base, int B, int J, int mode, int fusion_kind
   w.slots = (float*)b.take(2 * kNumSlots * sizeof(float));
   w.x0_rs = (float*)b.take(N * kFeatHW * sizeof(float));
   w.x0 = take_act(b, N * kFeatHW * kFeatC, mode == kModeHybrid ? kFmtF16P : ff);
-  w.y1 = take_act(b, N * kFeatHW * kHid1Pad, ff);
-  w.z = take_act(b, (size_t)B * kFeatHW * 2 * kHid2, ff);
-  w.f1 = take_act(b, (size_t)B * kFeatHW * kHid2, ff);
-  w.f2 = take_act(b, (size_t)B * kFeatHW * kHid2, ff);
-  w.g = take_act(b, N * kFeatHW * kHid1Pad, ff);
+  w.y1 = take_act(b, N * kFeatHW * fd.h1p, ff);
+  w.z = take_act(b, (size_t)B * kFeatHW * 2 * fd.h2, ff);
+  w.f1 = take_act(b, (size_t)B * kFeatHW * fd.h2, ff);
+  w.f2 = take_act(b, (size_t)B * kFeatHW * fd.h2, ff);
+  w.g = take_act(b, N * kFeatHW * fd.h1p, ff);
   w.x1 = take_act(b, N * kFeatHW * kFeatC, df);
   w.d1 = take_act(b, N * 256 * kDecC, df);
   w.d2 = take_act(b, N * 1024 * kDecC, df);
@@ -1816,7 +1820,7 @@ static TcDecWs plan_tc_dec(void* base, int N, int mode) {
 }
 
 int tc_head_workspace_bytes(const TcWeights& w, int batch, size_t* bytes) {
-  *bytes = plan_tc_head(nullptr, batch, w.joints, w.kind, ((const TcPack*)w.impl)->fusion_kind).bytes;
+  *bytes = plan_tc_head(nullptr, batch, w.joints, w.kind, ((const TcPack*)w.impl)->fusion_kind, w.fd).bytes;
   return CDR_OK;
 }
 int tc_decoder_workspace_bytes(const TcWeights& w, int n_images, size_t* bytes) {
@@ -1850,7 +1854,7 @@ static int to_rows(const float* feat, const float* feat2, int n_img, const Act& 
 }
 // FTL of both views in one launch
 // kFmtF16P: in_slot = scale / amax of the input, out_slot = where the output's go, l1max = max row L1 norm of `mats`
-static int ftl_act2(const Act& in0, const Act& in1, int in_pitch, const float* const mats[2], int rows, int cols, int n,
+static int ftl_act2(const Act& in0, const Act& in1, int in_pitch, const float* const mats[2], int rows, int cols, int blk, int n,
                     const Act& out0, const Act& out1, int out_pitch, int out_fill, float* amax_out, ScaleSlot in_slot,
                     ScaleSlot out_slot, const float* l1max, cudaStream_t st) {
   if (in0.fmt == kFmtF16P) {
@@ -1858,19 +1862,19 @@ static int ftl_act2(const Act& in0, const Act& in1, int in_pitch, const float* c
     const void* il[2] = {in0.p[1], in1.p[1]};
     void* oh[2] = {out0.p[0], out1.p[0]};
     void* ol[2] = {out0.p[1], out1.p[1]};
-    return launch_ftl_f16p2(ih, il, in_pitch, mats, rows, cols, kFtlBlk, n, kFeatHW, oh, ol, out_pitch, out_fill,
+    return launch_ftl_f16p2(ih, il, in_pitch, mats, rows, cols, blk, n, kFeatHW, oh, ol, out_pitch, out_fill,
                             in_slot.scale, in_slot.amax, l1max, out_slot.scale, out_slot.amax, st);
   }
   if (in0.fmt == kFmtBF16) {
     const __nv_bfloat16* ins[2] = {(const __nv_bfloat16*)in0.p[0], (const __nv_bfloat16*)in1.p[0]};
     __nv_bfloat16* outs[2] = {(__nv_bfloat16*)out0.p[0], (__nv_bfloat16*)out1.p[0]};
-    return launch_ftl2<__nv_bfloat16>(ins, in_pitch, mats, rows, cols, kFtlBlk, n, kFeatHW, outs, out_pitch, out_fill, 2, st);
+    return launch_ftl2<__nv_bfloat16>(ins, in_pitch, mats, rows, cols, blk, n, kFeatHW, outs, out_pitch, out_fill, 2, st);
   }
   const float* ih[2] = {(const float*)in0.p[0], (const float*)in1.p[0]};
   const float* il[2] = {(const float*)in0.p[1], (const float*)in1.p[1]};
   float* oh[2] = {(float*)out0.p[0], (float*)out1.p[0]};
   float* ol[2] = {(float*)out0.p[1], (float*)out1.p[1]};
-  return launch_ftl_split2(ih, il, in_pitch, mats, rows, cols, kFtlBlk, n, kFeatHW, oh, ol, out_pitch, out_fill, 2,
+  return launch_ftl_split2(ih, il, in_pitch, mats, rows, cols, blk, n, kFeatHW, oh, ol, out_pitch, out_fill, 2,
                            amax_out, st);
 }
 
@@ -2018,7 +2022,8 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, int feat_planes, 
   const bool scaled = mode_decoder_kind(mode) == kKindF16X2;
   const bool fus16 = w.has_fusion && pk->fusion_kind == kKindF16X2;   // fusion activations in kFmtF16P (slots 6..11)
   const int B = batch, N = 2 * batch, J = w.joints;
-  TcHeadWs ws = plan_tc_head(workspace, B, J, mode, pk->fusion_kind);
+  TcHeadWs ws = plan_tc_head(workspace, B, J, mode, pk->fusion_kind, w.fd);
+  const FusionDims& fd = w.fd;
   if (ws.bytes > workspace_bytes) {
     set_error("cdr_head_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
     return CDR_ERR_WORKSPACE;
@@ -2083,8 +2088,8 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, int feat_planes, 
     TcLaunch l{};
     l.A = x0; l.a_pitch = kFeatC; l.n_img = N; l.H = l.W = 8; l.cin = kFeatC; l.groups = 1;
     l.a_rows_total = (long long)N * kFeatHW;
-    l.layer = &pk->cf1; l.n = kHid1;
-    l.C = ws.y1; l.c_pitch = kHid1Pad; l.c_fill = kHid1Pad; l.relu = 1; l.out_mode = kOutRows;
+    l.layer = &pk->cf1; l.n = fd.h1;
+    l.C = ws.y1; l.c_pitch = fd.h1p; l.c_fill = fd.h1p; l.relu = 1; l.out_mode = kOutRows;
     l.in_slot = x0_slot;
     l.in_row_scale = x0_rs;
     if (fus16) l.out_slot = slot(ws.slots, 6);
@@ -2093,33 +2098,33 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, int feat_planes, 
   }
   set_stage("ftl_inv");
   if (lane) CDR_CUDA(cudaStreamWaitEvent(st, lane->join, 0));      // join: the pseudo-inverses are complete
-  if ((rc = ftl_act2(ws.y1, act_offset(ws.y1, (size_t)B * kFeatHW * kHid1Pad), kHid1Pad, pinv, 4, 3, B, ws.z,
-                     act_offset(ws.z, (size_t)kHid2), 2 * kHid2, kHid2, nullptr, slot(ws.slots, 6), slot(ws.slots, 7),
+  if ((rc = ftl_act2(ws.y1, act_offset(ws.y1, (size_t)B * kFeatHW * fd.h1p), fd.h1p, pinv, 4, 3, fd.blk, B, ws.z,
+                     act_offset(ws.z, (size_t)fd.h2), 2 * fd.h2, fd.h2, nullptr, slot(ws.slots, 6), slot(ws.slots, 7),
                      ws.slots + 2 * 11, st)))
     return rc;
   set_stage("cf_conv2");
   {
     TcLaunch l{};
-    l.A = ws.z; l.a_pitch = 2 * kHid2; l.n_img = B; l.H = l.W = 8; l.cin = 2 * kHid2; l.groups = 1;
+    l.A = ws.z; l.a_pitch = 2 * fd.h2; l.n_img = B; l.H = l.W = 8; l.cin = 2 * fd.h2; l.groups = 1;
     l.a_rows_total = (long long)B * kFeatHW;
-    l.layer = &pk->cf2a; l.n = kHid2;
-    l.C = ws.f1; l.c_pitch = kHid2; l.c_fill = kHid2; l.relu = 1; l.out_mode = kOutRows;
+    l.layer = &pk->cf2a; l.n = fd.h2;
+    l.C = ws.f1; l.c_pitch = fd.h2; l.c_fill = fd.h2; l.relu = 1; l.out_mode = kOutRows;
     if (fus16) { l.in_slot = slot(ws.slots, 7); l.out_slot = slot(ws.slots, 8); l.pair2 = 1; }
     if ((rc = launch_tc(l, st))) return rc;
-    l.A = ws.f1; l.a_pitch = kHid2; l.cin = kHid2; l.layer = &pk->cf2b; l.C = ws.f2;
+    l.A = ws.f1; l.a_pitch = fd.h2; l.cin = fd.h2; l.layer = &pk->cf2b; l.C = ws.f2;
     if (fus16) { l.in_slot = slot(ws.slots, 8); l.out_slot = slot(ws.slots, 9); }
     if ((rc = launch_tc(l, st))) return rc;
   }
   set_stage("ftl_fwd");
   const float* Pv[2] = {P_l, P_r};
-  if ((rc = ftl_act2(ws.f2, ws.f2, kHid2, Pv, 3, 4, B, ws.g, act_offset(ws.g, (size_t)B * kFeatHW * kHid1Pad),
-                     kHid1Pad, kHid1Pad, scaled ? slot(ws.slots, 0).amax : nullptr, slot(ws.slots, 9), slot(ws.slots, 10),
+  if ((rc = ftl_act2(ws.f2, ws.f2, fd.h2, Pv, 3, 4, fd.blk, B, ws.g, act_offset(ws.g, (size_t)B * kFeatHW * fd.h1p),
+                     fd.h1p, fd.h1p, scaled ? slot(ws.slots, 0).amax : nullptr, slot(ws.slots, 9), slot(ws.slots, 10),
                      ws.slots + 2 * 11 + 1, st)))
     return rc;
   set_stage("cf_out");
   {
     TcLaunch l{};
-    l.A = ws.g; l.a_pitch = kHid1Pad; l.n_img = B; l.H = l.W = 8; l.cin = kHid1; l.groups = 2;
+    l.A = ws.g; l.a_pitch = fd.h1p; l.n_img = B; l.H = l.W = 8; l.cin = fd.h1; l.groups = 2;
     l.a_rows_total = (long long)N * kFeatHW;
     l.layer = &pk->out; l.b_group_rows = kFeatC; l.n = kFeatC; l.bias_group_stride = kFeatC;
     l.C = ws.x1; l.c_group_stride = (long long)B * kFeatHW * kFeatC; l.c_pitch = kFeatC; l.c_fill = kFeatC;
@@ -2148,8 +2153,8 @@ int tc_head_forward(const TcWeights& w, const void* feat_rows, int feat_planes, 
       CDR_CUDA(cudaMemcpyAsync(taps->pinv, pinv[0], (size_t)B * 48, cudaMemcpyDeviceToDevice, st));
       CDR_CUDA(cudaMemcpyAsync(taps->pinv + (size_t)B * 12, pinv[1], (size_t)B * 48, cudaMemcpyDeviceToDevice, st));
     }
-    if ((rc = tap_to_f32(taps->cf_cat, ws.z, slot(ws.slots, 7).scale, (long long)B * kFeatHW, 2 * kHid2, 2 * kHid2, st))) return rc;
-    if ((rc = tap_to_f32(taps->cf_f, ws.f2, slot(ws.slots, 9).scale, (long long)B * kFeatHW, kHid2, kHid2, st))) return rc;
+    if ((rc = tap_to_f32(taps->cf_cat, ws.z, slot(ws.slots, 7).scale, (long long)B * kFeatHW, 2 * fd.h2, 2 * fd.h2, st))) return rc;
+    if ((rc = tap_to_f32(taps->cf_f, ws.f2, slot(ws.slots, 9).scale, (long long)B * kFeatHW, fd.h2, fd.h2, st))) return rc;
     if ((rc = tap_to_f32(taps->f_out, ws.x1, slot(ws.slots, 1).scale, (long long)N * kFeatHW, kFeatC, kFeatC, st)))
       return rc;
     if (taps->heatmaps)

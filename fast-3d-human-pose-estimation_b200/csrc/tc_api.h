@@ -9,6 +9,7 @@ struct TcWeights {
   void* impl = nullptr;   // TcPack (gemm_tc.cu): per-layer pointers + weight tensor maps
   int joints = 0, has_fusion = 0, fin_npad = 0;
   int kind = 0;           // pack mode: 0 = bf16, 1 = tf32x3, 2 = hybrid (fusion tf32x3, decoder f16x2)
+  FusionDims fd;          // fusion widths (common.cuh)
 };
 
 int tc_weights_create(const CdrWeightPtrs& src, int mode, TcWeights& w, cudaStream_t st);

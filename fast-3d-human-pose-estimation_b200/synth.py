@@ -92,7 +92,7 @@ def make_images(batch, seed=1, size=256, device="cpu"):
     return [torch.randn(batch, 3, size, size, generator=g).to(device) for _ in range(2)]
 
 
-def make_head_state_dict(seed=0, joints=19, calibrated=True, randomize_bn=False, decoder_only=False):
+def make_head_state_dict(seed=0, joints=19, calibrated=True, randomize_bn=False, decoder_only=False, hid=(300, 400)):
     """Seeded PyTorch-default init of the head (CF.* + decoder.*, reference key names).
     calibrated: final_layer.weight *= 0.1 so heat-map logits have std ~3 (SURVEY.md §6.2);
     randomize_bn: non-trivial BN affine / running stats so BN folding is exercised."""
@@ -100,7 +100,7 @@ def make_head_state_dict(seed=0, joints=19, calibrated=True, randomize_bn=False,
     torch.manual_seed(seed)
     sd = {}
     if not decoder_only:
-        cf = CanonicalFusion(2048, 300, 400, 2)
+        cf = CanonicalFusion(2048, hid[0], hid[1], 2)
         sd.update({"CF." + k: v.detach().clone() for k, v in cf.state_dict().items()})
     dec = PoseDecoder(make_cfg(num_joints=joints))
     sd.update({"decoder." + k: v.detach().clone() for k, v in dec.state_dict().items()})

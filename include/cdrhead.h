@@ -84,6 +84,12 @@ typedef struct CdrWeightPtrs {
   CdrConvBn cf_out[2];   /* CF.out_layer.{0,1}.{0,1}: 300 -> 2048 per view */
   CdrConvBn deconv[3];   /* decoder.deconv{1,2,3}.{0,1}                    */
   CdrConvBn final_layer; /* decoder.final_layer: 256 -> J, bias, no BN     */
+  /* CDRNet(cfg, fusion_hid_ch1=.., fusion_hid_ch2=..), models/cdrnet.py:89-101.  0 / 0 = the defaults 300 / 400.  The
+   * reference's forward only type-checks when hid_ch2 = 4/3 hid_ch1 (ftl maps 3 channel blocks to 4 and back,
+   * :45-56,65,79); this library also needs hid_ch1 % 12 == 0 (block size a multiple of 4).  n_views and fusion_in_dim
+   * are not parameters here: the reference itself only runs with n_views = 2 (two out_layer heads, :32-43,255) and
+   * 2048 channels (the decoder's input, models/decoder.py:8-9). */
+  int fusion_hid_ch1, fusion_hid_ch2;
 } CdrWeightPtrs;
 
 typedef struct CdrWeights CdrWeights; /* opaque: BN-folded, re-laid-out device buffers */

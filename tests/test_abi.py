@@ -27,7 +27,7 @@ def test_exports_match_header(pkg):
 def test_struct_layout_matches_header(pkg):
     L = pkg._lib
     assert C.sizeof(L.CdrConvBn) == 6 * 8
-    assert C.sizeof(L.CdrWeightPtrs) == 8 + 9 * 48
+    assert C.sizeof(L.CdrWeightPtrs) == 8 + 9 * 48 + 8          # + fusion_hid_ch1 / fusion_hid_ch2
     assert C.sizeof(L.CdrHeadTaps) == 5 * 8
 
 

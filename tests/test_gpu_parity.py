@@ -137,6 +137,42 @@ def test_head_fp32_vs_fp64_oracle_stagewise(cuda_pkg, precision):
     assert abs(e_gpu[1] - e_ora[1]) <= max(TOL_MPJPE_MM, d3)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "fp32_ffma", "bf16"])
+@pytest.mark.parametrize("hid", [(96, 128), (192, 256), (444, 592)])
+def test_head_other_fusion_widths(cuda_pkg, precision, hid):
+    """CDRNet(cfg, fusion_hid_ch1=h1, fusion_hid_ch2=h2) (models/cdrnet.py:89-101) for widths other than the default
+    300 / 400, every precision, stage taps and joints against the fp64 oracle (the oracle is shape-generic)."""
+    b = 3
+    sd = synth.make_head_state_dict(seed=4, calibrated=True, randomize_bn=True, hid=hid)
+    feats, cams = synth.make_features(b, seed=1), synth.make_cameras(b, seed=2)
+    otaps = {}
+    o2, o3 = _oracle64(sd, feats, cams, otaps)
+    m = cuda_pkg.CDRNet(synth.make_cfg(18, 19), precision=precision, fusion_hid_ch1=hid[0], fusion_hid_ch2=hid[1])
+    assert not m.load_state_dict(sd, strict=False).unexpected_keys
+    m = m.cuda().eval()
+    (kl, kr), xyz, taps = _run_head(m, feats, cams, taps=True)
+
+    def rel(got, want):
+        return float(np.abs(got - want).max() / np.abs(want).max())
+    cat = _nhwc_to_nchw(taps["cf_cat"].cpu(), 2 * hid[1]).numpy()
+    f = _nhwc_to_nchw(taps["cf_f"].cpu(), hid[1]).numpy()
+    fo = _nhwc_to_nchw(taps["f_out"].cpu(), 2048).numpy()
+    r = {"cf_cat": rel(cat, otaps["cf_cat"].numpy()), "cf_f": rel(f, otaps["cf_f"].numpy()),
+         "f_out": rel(fo, torch.stack(otaps["f_out"]).numpy()),
+         "heat": rel(taps["heatmaps"].cpu().numpy(), torch.stack(otaps["heatmaps"]).numpy())}
+    d2 = max(np.abs(kl.cpu().numpy() - o2[0]).max(), np.abs(kr.cpu().numpy() - o2[1]).max())
+    print(f"\nfusion widths {hid} [{precision}]: " + " ".join(f"{k}={v:.2e}" for k, v in r.items()) + f" d2D={d2:.2e} px")
+    if precision == "bf16":
+        assert max(r.values()) < 3e-2 and d2 <= 2.0      # bf16 noise of a random-init head (flat heat-maps); taps are the gate
+    else:
+        assert max(r.values()) < 2e-5 and d2 <= TOL_2D_PX
+        check_3d(cams, kl, kr, xyz, o2, o3, f"widths {hid} [{precision}]:", flat=False)
+    with pytest.raises(ValueError):
+        cuda_pkg.CDRNet(synth.make_cfg(18, 19), fusion_hid_ch1=300, fusion_hid_ch2=300)    # the reference's ftl cannot reshape
+    with pytest.raises(NotImplementedError):
+        cuda_pkg.CDRNet(synth.make_cfg(18, 19), n_views=3)
+
+
 @pytest.mark.parametrize("name,b,joints,calib,rbn,rig,t2,t3", [
     ("head_b2", 2, 19, True, True, "wide", TOL_2D_PX, TOL_3D_MM),
     ("head_b3_default_init", 3, 19, False, False, "wide", 5e-2, None),   # stress: logit std ~34

@@ -138,3 +138,29 @@ def test_oracle_matches_live_reference():
     h = np.random.default_rng(5).normal(size=(2, joints, 64, 64)).astype(np.float32)
     for a, w in zip(O.get_max_preds(h), ref.get_max_preds(h)):
         assert np.array_equal(a, w)
+
+
+def test_reference_scope_limits_are_the_references_own():
+    """Where this library raises NotImplementedError the reference itself cannot run — shown on the UNMODIFIED reference:
+    (i) its BasicBlock puts the stride on BOTH 3x3 convs (models/encoder.py:9-14), so ResNet-18/34 fail at layer2's
+    residual add: only the Bottleneck ResNets (50/101/152) exist as working encoders; (ii) CanonicalFusion builds
+    exactly two out_layer heads (models/cdrnet.py:32-43) and CDRNet.forward returns views 0 and 1 (:255): n_views = 3
+    fails in out_layer[2], n_views = 1 in kps[:, :, 1]."""
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("reference sources not present")
+    ref = refload.load()
+    import importlib
+    enc = importlib.import_module("models.encoder")
+    r18 = enc.ResNet(synth.make_cfg(18, 19)).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="size of tensor"):
+        r18(torch.zeros(1, 3, 64, 64))
+    b = 1
+    cams = synth.make_cameras(b, seed=2)
+    P = torch.from_numpy(cams["P_l"])
+    for n_views, exc in ((3, IndexError), (1, IndexError)):
+        m = ref.CDRNet(synth.make_cfg(50, 19), n_views=n_views, fusion_hid_ch2=400)
+        m.encoder = refload.feature_stub([torch.zeros(b, 2048, 8, 8)] * n_views)
+        m = m.eval()
+        with torch.no_grad(), pytest.raises(exc):
+            m([torch.zeros(b, 3, 256, 256)] * n_views, [P] * n_views)
