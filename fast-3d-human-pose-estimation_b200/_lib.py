@@ -95,6 +95,12 @@ _SIGNATURES = {
     "cdr_encoder_forward_images": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_size_t, _vp]),
     "cdr_encoder_forward_frames_u8": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int,
                                                 C.c_int, _vp, _vp, C.c_size_t, _vp]),
+    "cdr_bn_train_forward": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_double, _vp, _vp, C.c_int,
+                                       _vp, _vp, _vp, _vp]),
+    "cdr_bn_train_backward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "cdr_joint_loss_scratch_bytes": (C.c_size_t, []),
+    "cdr_joint_loss_forward": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_longlong, C.c_int, C.c_double, _vp, _vp, _vp]),
+    "cdr_joint_loss_backward": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_longlong, C.c_int, C.c_double, _vp, _vp, _vp]),
     "cdr_pinv": (C.c_int, [_vp, C.c_int, C.c_double, _vp, _vp]),
     "cdr_projection_matrices": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "cdr_ftl": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp,

@@ -620,3 +620,39 @@ extern "C" int cdr_decoder_forward_planes(const CdrWeights* w, const void* feat_
   return tc_decoder_forward(w->tc, feat_planes, 1, nullptr, n_images, heatmaps, workspace, workspace_bytes,
                             (cudaStream_t)stream);
 }
+
+// ------------------------------------------------------------------------------------------
+// SURVEY 8f rank 3, second slice (train_ops.cu): train-mode BatchNorm2d and the reference's losses
+extern "C" int cdr_bn_train_forward(const float* x, int n, int c, int hw, const float* gamma, const float* beta,
+                                    double eps, double momentum, float* running_mean, float* running_var, int relu,
+                                    float* y, float* save_mean, float* save_invstd, void* stream) {
+  CDR_CHECK_ARG(x && y && save_mean && save_invstd && n > 0 && c > 0 && hw > 0, "cdr_bn_train_forward: bad args");
+  CDR_CHECK_ARG((long long)n * hw > 1, "cdr_bn_train_forward: more than one value per channel expected (as torch)");
+  return launch_bn_train_forward(x, n, c, hw, gamma, beta, eps, momentum, running_mean, running_var, relu, y, save_mean,
+                                 save_invstd, (cudaStream_t)stream);
+}
+extern "C" int cdr_bn_train_backward(const float* x, const float* dy, int n, int c, int hw, const float* gamma,
+                                     const float* beta, const float* save_mean, const float* save_invstd, int relu,
+                                     float* dx, float* dgamma, float* dbeta, void* stream) {
+  CDR_CHECK_ARG(x && dy && save_mean && save_invstd && dx && dgamma && dbeta && n > 0 && c > 0 && hw > 0,
+                "cdr_bn_train_backward: bad args");
+  return launch_bn_train_backward(x, dy, n, c, hw, gamma, beta, save_mean, save_invstd, relu, dx, dgamma, dbeta,
+                                  (cudaStream_t)stream);
+}
+extern "C" size_t cdr_joint_loss_scratch_bytes(void) { return joint_loss_scratch_bytes(); }
+extern "C" int cdr_joint_loss_forward(int kind, const float* pred, const float* target, const float* weight,
+                                      long long rows, int d, double threshold, float* loss, void* scratch, void* stream) {
+  CDR_CHECK_ARG(kind >= 0 && kind <= 2 && pred && target && loss && scratch && rows > 0 && d > 0,
+                "cdr_joint_loss_forward: bad args");
+  CDR_CHECK_ARG(((uintptr_t)scratch & 7) == 0, "cdr_joint_loss_forward: scratch must be 8-byte aligned");
+  return launch_joint_loss_forward(kind, pred, target, weight, rows, d, threshold, loss, (double*)scratch,
+                                   (cudaStream_t)stream);
+}
+extern "C" int cdr_joint_loss_backward(int kind, const float* pred, const float* target, const float* weight,
+                                       long long rows, int d, double threshold, const float* grad_loss, float* grad_pred,
+                                       void* stream) {
+  CDR_CHECK_ARG(kind >= 0 && kind <= 2 && pred && target && grad_loss && grad_pred && rows > 0 && d > 0,
+                "cdr_joint_loss_backward: bad args");
+  return launch_joint_loss_backward(kind, pred, target, weight, rows, d, threshold, grad_loss, grad_pred,
+                                    (cudaStream_t)stream);
+}

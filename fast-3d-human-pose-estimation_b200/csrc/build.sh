@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 OUT=${CDR_OUT:-../libcdrhead.so}
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xptxas -v"
-SRCS="api.cu geometry.cu heatmap.cu layout.cu pack.cu gemm_ffma.cu gemm_tc.cu stem.cu backward.cu"
+SRCS="api.cu geometry.cu heatmap.cu layout.cu pack.cu gemm_ffma.cu gemm_tc.cu stem.cu backward.cu train_ops.cu"
 BUILD=${CDR_BUILD_DIR:-build}
 mkdir -p $BUILD
 pids=()

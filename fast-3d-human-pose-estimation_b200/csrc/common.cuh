@@ -1,5 +1,6 @@
 // Shared helpers for libcdrhead.so (sm_100a only).
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -67,6 +68,15 @@ inline int num_sms() {
   return n[dev];
 }
 // one flag word per kernel instantiation (a function-local static at the call site), one bit per device
+// Device scalars written by a predecessor kernel (scale / amax slots) are read with __ldcg (L2), never through the
+// non-coherent L1 path.  MEASURED (round 2): with the FTL / layout kernels launched by programmatic dependent launch too,
+// a kernel that starts early shares an SM with its still-running predecessors, whose own __ldg of the same 128-byte
+// line (all slots live in one) left a stale copy in that SM's L1 — conv outputs scaled by 1/0 in ~1 of 10 runs.  With
+// every predecessor-written word read through L2 the race is gone, but the L2-only loads cost the FTL kernels more
+// (12 -> 20 us) than the overlapped prologues returned (+2 % -> -1 % on the step), so the layout kernels are plain
+// launches again; only the tap-GEMM / tail kernels (which never co-reside: one 220 KB CTA per SM) and the merge kernel
+// (it shares SMs with the tail's last CTAs but reads only their records, which no co-resident CTA ever loads) chain by PDL.
+
 struct DeviceOnce {
   unsigned long long mask = 0;
   bool need() const { return !((mask >> current_device()) & 1ull); }

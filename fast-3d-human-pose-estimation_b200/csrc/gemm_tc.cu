@@ -688,18 +688,18 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     uint32_t tl = 0, ch = 0, it_e = 0;             // it_e: ring position of the current tile's residual stage
     EpiScale es;
     if constexpr (KIND == kKindF16X2)
-      if (!p.scale_in_rows) es.a_inv = 1.f / __ldg(p.scale_in);   // powers of two: exact
+      if (!p.scale_in_rows) es.a_inv = 1.f / __ldcg(p.scale_in);   // powers of two: exact
     if constexpr (OFMT == kFmtF16P) {
       if (p.out_mode != kOutPlanar) {
-        float bound = __ldg(p.amax_in) * __ldg(p.norms) + __ldg(p.norms + 1);
+        float bound = __ldcg(p.amax_in) * __ldg(p.norms) + __ldg(p.norms + 1);
         if constexpr (kResOK)
-          if (p.has_res && p.res_amax) bound += __ldg(p.res_amax);       // |conv + residual| <= bound(conv) + max |residual|
+          if (p.has_res && p.res_amax) bound += __ldcg(p.res_amax);       // |conv + residual| <= bound(conv) + max |residual|
         if (bound > 0.f && bound < 3.0e38f) es.s_out = ldexpf(1.f, kF16TargetExp - ilogbf(bound));
         if (blockIdx.x == 0 && threadIdx.x == 64) *p.scale_out = es.s_out;
       }
     }
     if constexpr (kResOK && KIND == kKindF16X2)
-      if (p.has_res) es.r_inv = 1.f / __ldg(p.res_scale);
+      if (p.has_res) es.r_inv = 1.f / __ldcg(p.res_scale);
     const bool use_tma = Cfg::kTmaStore && p.out_mode != kOutPlanar;
     const float relu_floor = p.relu ? 0.f : -INFINITY;
     for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++tl) {
@@ -711,7 +711,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int m = mw + lane;                     // this thread's pixel
       const bool row_ok = m < p.M;
       if constexpr (KIND == kKindF16X2)
-        if (p.scale_in_rows) es.a_inv = row_ok ? 1.f / __ldg(p.scale_in_rows + (size_t)g * p.a_group_rows + m) : 1.f;
+        if (p.scale_in_rows) es.a_inv = row_ok ? 1.f / __ldcg(p.scale_in_rows + (size_t)g * p.a_group_rows + m) : 1.f;
       const int n0 = n_tile * BN + cb0;            // first output channel of this warp
       const float* __restrict__ bias = p.bias + (size_t)g * p.bias_group_stride;
       const float* __restrict__ wsi = KIND == kKindF16X2 ? p.wsi + (size_t)g * p.wsi_group_stride : nullptr;

@@ -86,4 +86,17 @@ size_t stem_weight_bytes_f32();
 int launch_stem_f32(const void* x, int is_u8, const float* mean, const float* std, int n, int H, int W, const float* w,
                     const float* bias, float* conv_out, void* pooled_hi, void* pooled_lo, float* slot, cudaStream_t st);
 
+// train_ops.cu: BatchNorm2d in training mode (+ optional fused ReLU) and the reference's three losses, forward / backward
+int launch_bn_train_forward(const float* x, int n, int c, int hw, const float* gamma, const float* beta, double eps,
+                            double momentum, float* running_mean, float* running_var, int relu, float* y, float* save_mean,
+                            float* save_invstd, cudaStream_t st);
+int launch_bn_train_backward(const float* x, const float* dy, int n, int c, int hw, const float* gamma, const float* beta,
+                             const float* save_mean, const float* save_invstd, int relu, float* dx, float* dgamma,
+                             float* dbeta, cudaStream_t st);
+int launch_joint_loss_forward(int kind, const float* pred, const float* target, const float* weight, long long rows, int D,
+                              double threshold, float* loss, double* scratch, cudaStream_t st);
+int launch_joint_loss_backward(int kind, const float* pred, const float* target, const float* weight, long long rows, int D,
+                               double threshold, const float* grad_loss, float* grad_pred, cudaStream_t st);
+size_t joint_loss_scratch_bytes();
+
 }  // namespace cdr

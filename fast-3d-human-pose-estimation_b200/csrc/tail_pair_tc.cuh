@@ -323,8 +323,8 @@ deconv_tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     uint32_t tl = 0, ch = 0;
     float a_inv = 1.f, s_out = 1.f;
     if constexpr (kSplit) {
-      a_inv = 1.f / __ldg(p.scale_in);
-      const float bound = __ldg(p.amax_in) * __ldg(p.norms) + __ldg(p.norms + 1);
+      a_inv = 1.f / __ldcg(p.scale_in);
+      const float bound = __ldcg(p.amax_in) * __ldg(p.norms) + __ldg(p.norms + 1);
       if (bound > 0.f && bound < 3.0e38f) s_out = ldexpf(1.f, kF16TargetExp - ilogbf(bound));
     }
     auto wait_a2_free = [&]() {              // own a2_empty[]: released for both CTAs by multicast commits (tail_tc.cuh)
@@ -447,7 +447,7 @@ deconv_tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     uint32_t tl = 0;
     float fin_scale = 1.f;
     if constexpr (kSplit) {
-      const float bound = __ldg(p.amax_in) * __ldg(p.norms) + __ldg(p.norms + 1);
+      const float bound = __ldcg(p.amax_in) * __ldg(p.norms) + __ldg(p.norms + 1);
       if (bound > 0.f && bound < 3.0e38f) fin_scale = ldexpf(1.f, -(kF16TargetExp - ilogbf(bound)));
     }
     const float kLog2e = 1.4426950408889634f;

@@ -388,8 +388,8 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     uint32_t tl = 0, ch = 0;
     float a_inv = 1.f, s_out = 1.f;
     if constexpr (kSplit) {
-      a_inv = 1.f / __ldg(p.scale_in);
-      const float bound = __ldg(p.amax_in) * __ldg(p.norms) + __ldg(p.norms + 1);
+      a_inv = 1.f / __ldcg(p.scale_in);
+      const float bound = __ldcg(p.amax_in) * __ldg(p.norms) + __ldg(p.norms + 1);
       if (bound > 0.f && bound < 3.0e38f) s_out = ldexpf(1.f, kF16TargetExp - ilogbf(bound));
     }
     // A2 is free for this warp's round of tile tl once the heat MMAs of the round BEFORE it have completed:
@@ -522,7 +522,7 @@ deconv_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     uint32_t tl = 0;
     float fin_scale = 1.f;                         // 1 / s(deconv3 activation)
     if constexpr (kSplit) {
-      const float bound = __ldg(p.amax_in) * __ldg(p.norms) + __ldg(p.norms + 1);
+      const float bound = __ldcg(p.amax_in) * __ldg(p.norms) + __ldg(p.norms + 1);
       if (bound > 0.f && bound < 3.0e38f) fin_scale = ldexpf(1.f, -(kF16TargetExp - ilogbf(bound)));
     }
     const float kLog2e = 1.4426950408889634f;

@@ -313,6 +313,28 @@ int cdr_dlt_backward(const float* P_l, const float* P_r, const float* kp_l, cons
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
+/* ---- SURVEY §8f rank 3, second slice: what a training step of the head needs besides the differentiable operators
+ * above (train_cdr.py:82-143) — BatchNorm2d in TRAINING mode and the three losses of models/loss.py — forward and
+ * backward on the reference's layouts.  (The convolutions of a training step stay library GEMMs: cuDNN through torch.)
+ *
+ * nn.BatchNorm2d(train) on x (n, c, h*w) fp32 NCHW — models/cdrnet.py:19,25,28,36,41, models/decoder.py:34 — with the
+ * ReLU that follows it fused when relu != 0: batch mean / biased variance over (n, h, w), running_mean / running_var
+ * updated in place (momentum; unbiased variance), save_mean / save_invstd (c) kept for the backward. */
+int cdr_bn_train_forward(const float* x, int n, int c, int hw, const float* gamma, const float* beta, double eps,
+                         double momentum, float* running_mean, float* running_var, int relu, float* y,
+                         float* save_mean, float* save_invstd, void* stream);
+int cdr_bn_train_backward(const float* x, const float* dy, int n, int c, int hw, const float* gamma, const float* beta,
+                          const float* save_mean, const float* save_invstd, int relu, float* dx, float* dgamma,
+                          float* dbeta, void* stream);
+/* The reference's losses on (rows = B*J, d) tensors, weight = target_weight as (rows) or NULL:
+ *   kind 0 JointsMSELoss (models/loss.py:5-32), 1 JointsMSESmoothLoss (:35-66, `threshold`), 2 MPJPELoss (:69-98).
+ * loss: 1 float; scratch: cdr_joint_loss_scratch_bytes() bytes, 8-byte aligned; fixed-order fp64 sums (deterministic). */
+size_t cdr_joint_loss_scratch_bytes(void);
+int cdr_joint_loss_forward(int kind, const float* pred, const float* target, const float* weight, long long rows, int d,
+                           double threshold, float* loss, void* scratch, void* stream);
+int cdr_joint_loss_backward(int kind, const float* pred, const float* target, const float* weight, long long rows, int d,
+                            double threshold, const float* grad_loss, float* grad_pred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
