@@ -16,7 +16,8 @@ from .graph import HeadGraph, HeadPipeline, FramePipeline
 from .geometry import baseline_keypoints, get_max_preds, projection_matrices, triangulation
 from .metrics import calc_mpjpe, mpjpe_sums
 from .autograd import soft_argmax_2d, dlt, ftl
+from .losses import JointsMSELoss, JointsMSESmoothLoss, MPJPELoss, batch_norm_train
 
 __all__ = ["CDRNet", "CanonicalFusion", "PoseDecoder", "PoseResNet", "ResNet", "calc_mpjpe",
-           "mpjpe_sums", "HeadGraph", "HeadPipeline", "FramePipeline", "get_max_preds", "baseline_keypoints", "triangulation", "soft_argmax_2d", "dlt", "ftl", "build",
+           "mpjpe_sums", "HeadGraph", "HeadPipeline", "FramePipeline", "get_max_preds", "baseline_keypoints", "triangulation", "soft_argmax_2d", "dlt", "ftl", "JointsMSELoss", "JointsMSESmoothLoss", "MPJPELoss", "batch_norm_train", "build",
            "CdrError"]

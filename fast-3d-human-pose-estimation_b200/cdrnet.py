@@ -426,10 +426,11 @@ class CDRNet(nn.Module):
 
     def forward_train(self, xs, proj_list):
         """The training-mode forward of train_cdr.py:105 (models/cdrnet.py:224-268 with autograd), SURVEY §8f rank 3
-        first slice — an explicit HYBRID, not a fallback of the inference path: the convolutions and train-mode
-        BatchNorm are this module's own torch children (cuDNN + torch autograd, like the encoder), while the three
-        operators the reference hand-rolls — ``ftl`` (:45-56), ``process_heatmap`` (:120-149) and ``dlt`` (:151-179)
-        — and the pseudo-inverse run forward AND backward in libcdrhead.so (autograd.py).  Needs
+        — an explicit HYBRID, not a fallback of the inference path: the convolutions are this module's own torch
+        children (library GEMMs: cuDNN + torch autograd, like the encoder), while the head's train-mode BatchNorm + ReLU
+        (losses.py: batch statistics, running-stat update) and the three operators the reference hand-rolls — ``ftl``
+        (:45-56), ``process_heatmap`` (:120-149) and ``dlt`` (:151-179) — and the pseudo-inverse run forward AND
+        backward in libcdrhead.so (autograd.py, losses.py).  Needs
         ``CDRNet(..., trainable=True)``; projection matrices get no gradient (data in the reference)."""
         from .autograd import dlt, ftl, soft_argmax_2d
         if not self.trainable:
@@ -443,16 +444,21 @@ class CDRNet(nn.Module):
             st = _lib.current_stream_ptr(pl.device)
             for v, p in enumerate((pl, pr)):                                  # :236-237
                 _lib.check(_lib.lib().cdr_pinv(_lib.ptr(p), b, PINV_RTOL_FP32, _lib.ptr(pinv[v]), st))
+        from .losses import batch_norm_train
+
+        def cbr(seq, x, i=0):
+            """conv (a library GEMM through torch, like the encoder) -> train-mode BatchNorm + ReLU on libcdrhead"""
+            return batch_norm_train(seq[i](x), seq[i + 1], relu=True)
         feats = [self.encoder(xs[v]) for v in range(2)]                       # :231-234
         cf = self.CF
-        z = torch.cat([ftl(cf.conv_layer1(feats[v]), pinv[v]) for v in range(2)], dim=1)      # :62-70
-        f = cf.conv_layer2(z)                                                 # :74
+        z = torch.cat([ftl(cbr(cf.conv_layer1, feats[v]), pinv[v]) for v in range(2)], dim=1)      # :62-70
+        f = cbr(cf.conv_layer2, cbr(cf.conv_layer2, z), 3)                    # :74
         projs = (pl, pr)
         kps = []
         for v in range(2):
-            o = cf.out_layer[v](ftl(f, projs[v]))                             # :79-81
+            o = cbr(cf.out_layer[v], ftl(f, projs[v]))                        # :79-81
             d = self.decoder
-            h = d.final_layer(d.deconv3(d.deconv2(d.deconv1(o))))             # models/decoder.py:39-46
+            h = d.final_layer(cbr(d.deconv3, cbr(d.deconv2, cbr(d.deconv1, o))))   # models/decoder.py:39-46
             kps.append(soft_argmax_2d(h, img_size / h.shape[2]))              # :243-250
         return kps, dlt(pl, pr, kps[0], kps[1])                               # :252-268
 

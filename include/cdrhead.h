@@ -310,9 +310,6 @@ int cdr_dlt_backward(const float* P_l, const float* P_r, const float* kp_l, cons
                      const float* grad_xyz, int batch, int joints, float* grad_kp_l, float* grad_kp_r,
                      void* stream);
 
-#if defined(__GNUC__)
-#pragma GCC visibility pop
-#endif
 /* ---- SURVEY §8f rank 3, second slice: what a training step of the head needs besides the differentiable operators
  * above (train_cdr.py:82-143) — BatchNorm2d in TRAINING mode and the three losses of models/loss.py — forward and
  * backward on the reference's layouts.  (The convolutions of a training step stay library GEMMs: cuDNN through torch.)
@@ -335,6 +332,9 @@ int cdr_joint_loss_forward(int kind, const float* pred, const float* target, con
 int cdr_joint_loss_backward(int kind, const float* pred, const float* target, const float* weight, long long rows, int d,
                             double threshold, const float* grad_loss, float* grad_pred, void* stream);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

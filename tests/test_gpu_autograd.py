@@ -195,3 +195,80 @@ def _forward_train_case(cuda_pkg, copy, b):
     # and the opt-in is required
     with pytest.raises(RuntimeError, match="inference-only"):
         cuda_pkg.CDRNet(synth.make_cfg(50, 19)).cuda().train()(imgs, Ps)
+
+
+def _ref_losses():
+    """The reference's own loss modules where its sources are present, else a verbatim-semantics torch restatement."""
+    from oracle import refload
+    if refload.available():
+        refload.load()
+        import importlib
+        return importlib.import_module("models.loss")
+    pytest.skip("reference sources not present")
+
+
+@pytest.mark.parametrize("name,args", [("MPJPELoss", ()), ("JointsMSESmoothLoss", ()), ("JointsMSESmoothLoss", (4.0,)),
+                                       ("JointsMSELoss", ())])
+@pytest.mark.parametrize("shape", [(8, 19, 3), (8, 19, 2), (1, 19, 3), (3, 5, 16, 16)])
+@pytest.mark.parametrize("use_w", [True, False])
+def test_losses_vs_reference_modules(cuda_pkg, name, args, shape, use_w):
+    """models/loss.py:5-98 on libcdrhead (forward and backward) against the UNMODIFIED reference
+    modules evaluated in fp64 with torch autograd, on joints (B,J,D) as train_cdr.py:113-125 feeds them and on heat-maps
+    (B,J,H,W) as train.py does."""
+    ref = _ref_losses()
+    if len(shape) == 4 and name != "JointsMSELoss":
+        pytest.skip("only JointsMSELoss is applied to heat-maps in the reference")
+    g = torch.Generator().manual_seed(sum(map(ord, name)) + sum(shape) + int(use_w))
+    scale = 30.0 if name != "JointsMSELoss" else 1.0                  # mm-sized errors: both branches of the smooth loss
+    pred = (torch.randn(shape, generator=g) * scale)
+    tgt = (torch.randn(shape, generator=g) * scale)
+    w = (torch.rand(shape[0], shape[1], 1, generator=g) > 0.2).float()
+    up = torch.randn((), generator=g).abs() + 0.5                      # upstream gradient
+    p64 = pred.double().requires_grad_(True)
+    want = getattr(ref, name)(use_w, *args)(p64, tgt.double(), w.double())
+    (want * up.double()).sum().backward()
+    pd = pred.cuda().requires_grad_(True)
+    got = getattr(cuda_pkg, name)(use_w, *args)(pd, tgt.cuda(), w.cuda())
+    (got * up.cuda()).sum().backward()
+    assert tuple(got.shape) == tuple(want.shape)
+    np.testing.assert_allclose(got.detach().cpu().double().numpy(), want.detach().numpy(), rtol=2e-6)
+    assert _rel(pd.grad.cpu().double(), p64.grad) < 2e-5
+    # deterministic: the same bits on a second evaluation
+    got2 = getattr(cuda_pkg, name)(use_w, *args)(pd, tgt.cuda(), w.cuda())
+    assert torch.equal(got2, got)
+
+
+@pytest.mark.parametrize("shape,relu", [((4, 300, 8, 8), True), ((6, 256, 32, 32), True), ((3, 64, 16, 16), False),
+                                        ((2, 2048, 8, 8), True)])
+def test_bn_train_vs_torch(cuda_pkg, shape, relu):
+    """nn.BatchNorm2d in training mode (+ the ReLU that follows every BN of the head) on libcdrhead: outputs, running
+    statistics and the gradients of x / weight / bias against torch's own module evaluated in fp64."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(shape, generator=g) * 2.0 + 0.3
+    c = shape[1]
+    bn = torch.nn.BatchNorm2d(c, momentum=0.1)
+    bn.weight.data = 1.0 + 0.3 * torch.randn(c, generator=g)
+    bn.bias.data = 0.2 * torch.randn(c, generator=g)
+    bn.running_mean.data = 0.1 * torch.randn(c, generator=g)
+    bn.running_var.data = 1.0 + 0.2 * torch.rand(c, generator=g)
+    import copy
+    ref = copy.deepcopy(bn).double().train()
+    ours = copy.deepcopy(bn).cuda().train()
+    up = torch.randn(shape, generator=g)
+    x64 = x.double().requires_grad_(True)
+    y64 = ref(x64)
+    if relu:
+        y64 = torch.relu(y64)
+    (y64 * up.double()).sum().backward()
+    xd = x.cuda().requires_grad_(True)
+    y = cuda_pkg.batch_norm_train(xd, ours, relu=relu)
+    (y * up.cuda()).sum().backward()
+    assert _rel(y.detach().cpu().double(), y64.detach()) < 2e-6
+    assert _rel(ours.running_mean.cpu().double(), ref.running_mean) < 1e-6
+    assert _rel(ours.running_var.cpu().double(), ref.running_var) < 1e-6
+    assert int(ours.num_batches_tracked) == int(ref.num_batches_tracked) == 1
+    assert _rel(xd.grad.cpu().double(), x64.grad) < 2e-5
+    assert _rel(ours.weight.grad.cpu().double(), ref.weight.grad) < 2e-5
+    assert _rel(ours.bias.grad.cpu().double(), ref.bias.grad) < 2e-5
+    with pytest.raises(RuntimeError):
+        cuda_pkg.batch_norm_train(xd, ours.eval())
