@@ -708,10 +708,34 @@ def backward_stream(dev, poses=4096, reps=5):
     pk = peaks()
     bytes_sa = n_maps * (2 * 16384 + 8)
     gbs = bytes_sa / (ms_sa / 1e3) / 1e9
-    return {"softargmax_backward": {"launch_ms": ms_sa, "maps": n_maps, "algorithmic_bytes": bytes_sa, "achieved": gbs,
+    # train-mode BatchNorm2d + ReLU (second slice) on deconv3's activation at B = 64: (128, 256, 64, 64) fp32 = 537 MB.
+    # forward: x read twice (statistics, normalise) + y written = 3 passes; backward: x and dy read twice + dx written = 5
+    del heat, gh
+    torch.cuda.empty_cache()
+    n, c, hw = 128, 256, 4096
+    xb = torch.randn((n, c, 64, 64), device=dev, generator=g)
+    yb, dyb, dxb = torch.empty_like(xb), torch.randn((n, c, 64, 64), device=dev, generator=g), torch.empty_like(xb)
+    gam, bet = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+    rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+    sm, si = torch.empty(c, device=dev), torch.empty(c, device=dev)
+    dg, db = torch.empty(c, device=dev), torch.empty(c, device=dev)
+    ms_bf = timed(lambda: _lib.check(L.cdr_bn_train_forward(_lib.ptr(xb), n, c, hw, _lib.ptr(gam), _lib.ptr(bet), 1e-5, 0.1,
+                                                            _lib.ptr(rm), _lib.ptr(rv), 1, _lib.ptr(yb), _lib.ptr(sm),
+                                                            _lib.ptr(si), st)))
+    ms_bb = timed(lambda: _lib.check(L.cdr_bn_train_backward(_lib.ptr(xb), _lib.ptr(dyb), n, c, hw, _lib.ptr(gam),
+                                                             _lib.ptr(bet), _lib.ptr(sm), _lib.ptr(si), 1, _lib.ptr(dxb),
+                                                             _lib.ptr(dg), _lib.ptr(db), st)))
+    tb = xb.numel() * 4
+    bn = {"tensor": "(128, 256, 64, 64) fp32 (deconv3's activation at B = 64)",
+          "forward": {"launch_ms": ms_bf, "algorithmic_bytes": 3 * tb, "achieved": 3 * tb / (ms_bf / 1e3) / 1e9,
+                      "frac": 3 * tb / (ms_bf / 1e3) / 1e9 / pk["hbm_gbs"]},
+          "backward": {"launch_ms": ms_bb, "algorithmic_bytes": 5 * tb, "achieved": 5 * tb / (ms_bb / 1e3) / 1e9,
+                       "frac": 5 * tb / (ms_bb / 1e3) / 1e9 / pk["hbm_gbs"]},
+          "peak": pk["hbm_gbs"], "unit": "GB/s", "bound": "hbm"}
+    return {"bn_train_relu": bn, "softargmax_backward": {"launch_ms": ms_sa, "maps": n_maps, "algorithmic_bytes": bytes_sa, "achieved": gbs,
                                     "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "bound": "hbm"},
             "dlt_backward": {"launch_ms": ms_dlt, "joints_per_s": poses * JOINTS / (ms_dlt / 1e3), "bound": "latency / fp64"},
-            "input": f"{poses} poses x 19 joints x 2 views of 64x64 fp32 logits ({heat.numel() * 4 / 1e9:.1f} GB in, the same out)"}
+            "input": f"{poses} poses x 19 joints x 2 views of 64x64 fp32 logits ({n_maps * 16384 / 1e9:.1f} GB in, the same out)"}
 
 
 def config5(args, ctx, precision, total=1024, encoder_precision="bf16"):

@@ -42,14 +42,27 @@ bn_train_stats_kernel(const float* __restrict__ x, int N, int C, int HW, double 
   __shared__ double sh[kBnThreads / 32];
   const int c = blockIdx.x;
   double s = 0.0, q = 0.0;
-  if ((HW & 3) == 0) {
+  if ((HW & 3) == 0 && ((uintptr_t)x & 15) == 0) {
     const int hw4 = HW >> 2;
-    for (long long i = threadIdx.x; i < (long long)N * hw4; i += kBnThreads) {
-      const long long n = i / hw4;
-      const int p = (int)(i - n * hw4);
-      const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)n * C + c) * HW) + p);
-      s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
-      q += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    const long long tot = (long long)N * hw4;
+    // four independent 16-byte loads in flight per thread
+    for (long long i0 = threadIdx.x; i0 < tot; i0 += 4 * kBnThreads) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + (long long)u * kBnThreads;
+        if (i < tot) {
+          const long long n = i / hw4;
+          v[u] = __ldg(reinterpret_cast<const float4*>(x + ((size_t)n * C + c) * HW) + (int)(i - n * hw4));
+        } else {
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s += (double)v[u].x + (double)v[u].y + (double)v[u].z + (double)v[u].w;
+        q += (double)v[u].x * v[u].x + (double)v[u].y * v[u].y + (double)v[u].z * v[u].z + (double)v[u].w * v[u].w;
+      }
     }
   } else {
     for (long long i = threadIdx.x; i < (long long)N * HW; i += kBnThreads) {
@@ -101,14 +114,46 @@ bn_train_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__
   const float mu = __ldg(mean + c), is = __ldg(invstd + c);
   const float g = gamma ? __ldg(gamma + c) : 1.f, b = beta ? __ldg(beta + c) : 0.f;
   double s = 0.0, q = 0.0;
-  for (long long i = threadIdx.x; i < (long long)N * HW; i += kBnThreads) {
-    const long long n = i / HW;
-    const size_t o = ((size_t)n * C + c) * HW + (i - n * HW);
-    const float xh = (__ldg(x + o) - mu) * is;
-    float d = __ldg(dy + o);
-    if (relu && !(fmaf(xh, g, b) > 0.f)) d = 0.f;
-    s += d;
-    q += (double)d * xh;
+  if ((HW & 3) == 0 && (((uintptr_t)x | (uintptr_t)dy) & 15) == 0) {
+    const int hw4 = HW >> 2;
+    const long long tot = (long long)N * hw4;
+    for (long long i0 = threadIdx.x; i0 < tot; i0 += 2 * kBnThreads) {
+      float4 xv[2], dv[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const long long i = i0 + (long long)u * kBnThreads;
+        if (i < tot) {
+          const long long n = i / hw4;
+          const size_t o = ((size_t)n * C + c) * HW;
+          xv[u] = __ldg(reinterpret_cast<const float4*>(x + o) + (int)(i - n * hw4));
+          dv[u] = __ldg(reinterpret_cast<const float4*>(dy + o) + (int)(i - n * hw4));
+        } else {
+          xv[u] = make_float4(mu, mu, mu, mu);
+          dv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, ds[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float xh = (xs[e] - mu) * is;
+          const float d = (relu && !(fmaf(xh, g, b) > 0.f)) ? 0.f : ds[e];
+          s += d;
+          q += (double)d * xh;
+        }
+      }
+    }
+  } else {
+    for (long long i = threadIdx.x; i < (long long)N * HW; i += kBnThreads) {
+      const long long n = i / HW;
+      const size_t o = ((size_t)n * C + c) * HW + (i - n * HW);
+      const float xh = (__ldg(x + o) - mu) * is;
+      float d = __ldg(dy + o);
+      if (relu && !(fmaf(xh, g, b) > 0.f)) d = 0.f;
+      s += d;
+      q += (double)d * xh;
+    }
   }
   s = block_sum(s, sh);
   q = block_sum(q, sh);
@@ -118,21 +163,36 @@ bn_train_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__
   }
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(256)
 bn_train_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long total, int C, int HW,
                           double inv_m, const float* __restrict__ gamma, const float* __restrict__ beta,
                           const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
                           const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ dx) {
+  // `total` counts groups of VEC elements (VEC = 4 when H*W % 4 == 0 and the tensors are 16-byte aligned, else 1)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int c = (int)((i / HW) % C);
+  const int c = (int)((i / (HW / VEC)) % C);
   const float mu = __ldg(mean + c), is = __ldg(invstd + c);
   const float g = gamma ? __ldg(gamma + c) : 1.f, b = beta ? __ldg(beta + c) : 0.f;
-  const float xh = (__ldg(x + i) - mu) * is;
-  float d = __ldg(dy + i);
-  if (relu && !(fmaf(xh, g, b) > 0.f)) d = 0.f;
   const float k1 = (float)((double)__ldg(dbeta + c) * inv_m), k2 = (float)((double)__ldg(dgamma + c) * inv_m);
-  dx[i] = g * is * (d - k1 - xh * k2);
+  float xs[VEC], ds[VEC], o[VEC];
+  if constexpr (VEC == 4) {
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i), dv = __ldg(reinterpret_cast<const float4*>(dy) + i);
+    xs[0] = xv.x; xs[1] = xv.y; xs[2] = xv.z; xs[3] = xv.w;
+    ds[0] = dv.x; ds[1] = dv.y; ds[2] = dv.z; ds[3] = dv.w;
+  } else {
+    xs[0] = __ldg(x + i);
+    ds[0] = __ldg(dy + i);
+  }
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    const float xh = (xs[e] - mu) * is;
+    const float d = (relu && !(fmaf(xh, g, b) > 0.f)) ? 0.f : ds[e];
+    o[e] = g * is * (d - k1 - xh * k2);
+  }
+  if constexpr (VEC == 4) reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  else dx[i] = o[0];
 }
 
 int launch_bn_train_forward(const float* x, int n, int c, int hw, const float* gamma, const float* beta, double eps,
@@ -157,8 +217,12 @@ int launch_bn_train_backward(const float* x, const float* dy, int n, int c, int 
   bn_train_bwd_stats_kernel<<<c, kBnThreads, 0, st>>>(x, dy, n, c, hw, gamma, beta, save_mean, save_invstd, relu, dgamma, dbeta);
   CDR_LAUNCH_OK("bn_train_bwd_stats_kernel");
   const long long total = (long long)n * c * hw;
-  bn_train_bwd_apply_kernel<<<(unsigned)ceil_div<long long>(total, 256), 256, 0, st>>>(
-      x, dy, total, c, hw, 1.0 / ((double)n * hw), gamma, beta, save_mean, save_invstd, relu, dgamma, dbeta, dx);
+  if ((hw & 3) == 0 && (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0)
+    bn_train_bwd_apply_kernel<4><<<(unsigned)ceil_div<long long>(total / 4, 256), 256, 0, st>>>(
+        x, dy, total / 4, c, hw, 1.0 / ((double)n * hw), gamma, beta, save_mean, save_invstd, relu, dgamma, dbeta, dx);
+  else
+    bn_train_bwd_apply_kernel<1><<<(unsigned)ceil_div<long long>(total, 256), 256, 0, st>>>(
+        x, dy, total, c, hw, 1.0 / ((double)n * hw), gamma, beta, save_mean, save_invstd, relu, dgamma, dbeta, dx);
   CDR_LAUNCH_OK("bn_train_bwd_apply_kernel");
   return CDR_OK;
 }
