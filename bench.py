@@ -1000,7 +1000,7 @@ def full_pipeline(args, ctx, precision):
     return out
 
 
-def full_pipeline_sharded(args, ctx, precision):
+def full_pipeline_sharded(args, ctx, precision, encoder_precision="bf16"):
     """BASELINE configs[4] shape at N GPUs: every rank runs the whole pipeline (uint8 frames in pinned host
     memory -> FramePipeline -> 3D joints) on its shard, one all-gather of the 3D joints + MPJPE sums per
     step; aggregate pairs/s = all ranks' pairs / max-over-ranks device time."""
@@ -1050,6 +1050,7 @@ def full_pipeline_sharded(args, ctx, precision):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0]) / kk
     return {"e2e_uint8_frames_host": {"pairs_per_s": n_total / (ms / 1e3), "ms_per_step": ms, "n_gpus": world,
+                                      "encoder_precision": encoder_precision,
                                       "pairs_per_gpu": B, "h2d_bytes_per_step_per_gpu": frames_h.numel() + 2 * B * 48,
                                       "collective": "1 all-gather of (B,19,3)+32 B per step",
                                       "api": "FramePipeline per rank (ResNet-101 encoder + head on this repo's kernels)"}}
@@ -1094,7 +1095,14 @@ def run_ours(args):
 
     fp_multi = None
     if world > 1 and not args.no_full_pipeline:
-        fp_multi = full_pipeline_sharded(args, ctx, args.precision)      # every rank takes part (collectives)
+        # every rank takes part (collectives).  fp32 head: the reference-precision pipeline (f16x2 encoder) and, beside
+        # it, the bf16 encoder
+        if args.precision in ("fp32", "f16x2"):
+            fp_multi = full_pipeline_sharded(args, ctx, args.precision, "fp32")
+            extra = full_pipeline_sharded(args, ctx, args.precision, "bf16")
+            fp_multi["e2e_uint8_frames_host_encoder_bf16"] = extra.get("e2e_uint8_frames_host", extra)
+        else:
+            fp_multi = full_pipeline_sharded(args, ctx, args.precision)
     c5, c5_bf16 = None, None
     if not args.no_full_pipeline and not args.no_config5:
         # at the reference's precision end to end (f16x2 encoder + fp32 head) when this run's head is the fp32 one; the

@@ -926,6 +926,49 @@ def test_poseresnet_tc_encoder_baseline_path(cuda_pkg, precision):
     assert tuple(xyz.shape) == (n // 2, joints, 3) and bool(torch.isfinite(xyz).all())
 
 
+def test_baseline_config3_full_size(cuda_pkg):
+    """BASELINE configs[2] at its full size — PoseResNet-101, 256 uint8 frames (128 stereo pairs), bf16 — through
+    size-independent properties: determinism, per-image independence (a 16-image slice run alone gives the same bits),
+    and for ALL 128 pairs the arg-max x4 -> uint8 -> triangulation chain against the reference's functions
+    (tools/utils.py:30-58, baseline.py:51-53, tools/common.py:51-71): key points bit-exact on the SAME heat-maps, 3D
+    <= 1e-2 mm on view-consistent uint8 points."""
+    n, joints = 256, 19
+    torch.manual_seed(0)
+    m = cuda_pkg.PoseResNet(synth.make_cfg(101, joints), precision="bf16", encoder_precision="bf16")
+    sd = synth.make_head_state_dict(seed=3, joints=joints, calibrated=True, decoder_only=True)
+    m.decoder.load_state_dict({k[len("decoder."):]: v for k, v in sd.items()})
+    m = m.cuda().eval()
+    frames = torch.randint(0, 256, (n, 256, 256, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(9)).cuda()
+    hm = m(frames)
+    hm2 = m(frames)
+    assert hm.shape == (n, joints, 64, 64) and torch.equal(hm, hm2) and bool(torch.isfinite(hm).all())
+    part = m(frames[96:112].contiguous())
+    assert torch.equal(part, hm[96:112])
+    pts = cuda_pkg.baseline_keypoints(hm)
+    h_np = hm.cpu().numpy()
+    want_pts = (O.get_max_preds(h_np)[0] * 4.0).astype(np.uint8)
+    assert np.array_equal(pts.cpu().numpy(), want_pts)
+    nb = n // 2
+    cams = synth.make_cameras(nb, seed=5)
+    row4 = np.tile([[[0, 0, 0, 1.0]]], (nb, 1, 1))
+    P1 = np.concatenate([cams["P_l"], row4], 1).astype(np.float64)
+    P2 = np.concatenate([cams["P_r"], row4], 1).astype(np.float64)
+    xyz = cuda_pkg.triangulation(torch.from_numpy(P1).cuda(), torch.from_numpy(P2).cuda(), pts[:nb], pts[nb:])
+    assert tuple(xyz.shape) == (nb, joints, 3)
+    # triangulation at this size against the reference's function: on view-consistent uint8 points (the key points of
+    # a random-init network point at rays that barely intersect: both answers are then noise of eig / SVD)
+    gt = synth.make_gt(cams, seed=6)
+    u_l = np.clip(np.rint(gt["gt2d_l"]), 0, 255).astype(np.uint8)
+    u_r = np.clip(np.rint(gt["gt2d_r"]), 0, 255).astype(np.uint8)
+    got = cuda_pkg.triangulation(torch.from_numpy(P1).cuda(), torch.from_numpy(P2).cuda(), torch.from_numpy(u_l).cuda(),
+                                 torch.from_numpy(u_r).cuda()).cpu().numpy()
+    want = np.stack([O.triangulation(P1[i], P2[i], u_l[i], u_r[i]) for i in range(nb)])
+    err = np.abs(got - want).max()
+    print(f"\nconfigs[2] full size: {pts.numel() // 2} key points bit-exact; triangulation of {nb} pairs vs the reference's "
+          f"eig form: max {err:.2e} mm")
+    assert err <= TOL_3D_MM
+
+
 @pytest.mark.parametrize("pair", ["default", "0", "1"])
 @pytest.mark.parametrize("precision,b", [("bf16", 3), ("fp32", 3), ("fp32", 64), ("bf16", 64)])
 def test_fused_decoder_tail_matches_unfused_and_oracle(cuda_pkg, precision, b, pair, monkeypatch):
