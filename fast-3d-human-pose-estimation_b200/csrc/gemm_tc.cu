@@ -380,7 +380,8 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                    const TcGemmParams p) {
   using Cfg = TcCfg<BN, KIND, OFMT, CL>;
   // layers that may carry a residual: the bf16 and the f16x2 -> fp16-plane kernels with BN = 128, one CTA per tile
-  constexpr bool kResOK = BN == 128 && CL == 0 && ((KIND == kKindBF16 && OFMT == kFmtBF16) || (KIND == kKindF16X2 && OFMT == kFmtF16P));
+  // (CL = 1: the multicast pair shares the A tile, every CTA loads ITS N tile's residual into its own copy of the stage)
+  constexpr bool kResOK = BN == 128 && CL != 2 && ((KIND == kKindBF16 && OFMT == kFmtBF16) || (KIND == kKindF16X2 && OFMT == kFmtF16P));
   constexpr int S = Cfg::kStages;
   constexpr int kTcBK = Cfg::kBK;
   constexpr bool kSplit = KIND != kKindBF16;
@@ -463,6 +464,12 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   auto arrive_issuer = [&](uint64_t* bar) {
     if (kPair2 && cta_rank != 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(bar), 0));
     else ptx::mbar_arrive(bar);
+  };
+  // a residual stage is free again: CL = 1 stages are refilled by BOTH CTAs of the pair (each multicasts half of the next A
+  // tile into both), so empty[s] counts two arrivals — this CTA's epilogue and the peer's, each arriving on both barriers
+  auto release_res_stage = [&](int s) {
+    ptx::mbar_arrive(&empty[s]);
+    if constexpr (CL == 1) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&empty[s]), cta_rank ^ 1u));
   };
   // ... and do not touch anything the previous kernel wrote (activations, scale slots) before it is complete
   ptx::grid_dep_wait();
@@ -813,7 +820,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             __syncwarp();
             if (lane == 0) arrive_issuer(&tmem_empty[acc]);
           }
-          if constexpr (KIND == kKindBF16 && BN == 128) {
+          if constexpr (kResOK && KIND == kKindBF16) {
             if (p.has_res) {
               // residual stage of this tile: after the tile's K-blocks in ring order
               it_e += (uint32_t)num_kb;
@@ -830,7 +837,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               __syncwarp();
               if (lane == 0 && atomicAdd(&res_cnt[s], 1u) == (uint32_t)(kEpiWarps - 1)) {
                 res_cnt[s] = 0;
-                ptx::mbar_arrive(&empty[s]);       // last of the 8 warps hands the stage back to the producer
+                release_res_stage(s);              // last of the 8 warps hands the stage back to the producer(s)
               }
               ++it_e;
             }
@@ -914,7 +921,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             __syncwarp();
             if (lane == 0 && atomicAdd(&res_cnt[res_stage], 1u) == (uint32_t)(kEpiWarps - 1)) {
               res_cnt[res_stage] = 0;
-              ptx::mbar_arrive(&empty[res_stage]);     // last of the 8 warps hands the stage back to the producer
+              release_res_stage(res_stage);            // last of the 8 warps hands the stage back to the producer(s)
             }
           }
         }
@@ -1056,7 +1063,11 @@ static bool tc_pair2_ok(const TcLaunch& l) {
 }
 // can this launch run as CTA pairs?  the pair shares one A tile: an even number of N tiles per pixel block
 static bool tc_cluster_ok(const TcLaunch& l, int bn) {
-  if (!tc_use_cluster() || l.res || l.stride > 1 || (l.layer->n_pad / bn) % 2 != 0) return false;
+  if (!tc_use_cluster() || l.stride > 1 || (l.layer->n_pad / bn) % 2 != 0) return false;
+  if (l.res) {      // residual layers (1x1 projections): CDR_RES_CLUSTER=0 keeps them on single CTAs (A/B timing)
+    const char* e = getenv("CDR_RES_CLUSTER");
+    if (e && e[0] == '0') return false;
+  }
   if (l.deconv || l.conv3) {
     if (l.W > kTcBM || kTcBM % l.W != 0) return false;
     int rows = kTcBM / l.W;
@@ -1186,7 +1197,7 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
   }
   CUtensorMap tmap_r = tmap_a[0], tmap_r_lo = tmap_a[0];
   if (l.res) {
-    constexpr bool kResKernel = BN == 128 && CL == 0 && ((KIND == kKindBF16 && OFMT == kFmtBF16) ||
+    constexpr bool kResKernel = BN == 128 && CL != 2 && ((KIND == kKindBF16 && OFMT == kFmtBF16) ||
                                                          (KIND == kKindF16X2 && OFMT == kFmtF16P));
     CDR_CHECK_ARG(kResKernel && l.out_mode == kOutRows && l.groups == 1 && l.n % BN == 0 && l.c_fill == l.n,
                   "tap_gemm_tc: the residual add needs the bf16 / f16x2 BN=128 kernel and a multiple of 128 channels");
@@ -1221,7 +1232,7 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
   if (CL) {
     // CL = 1: CTA 2i / 2i+1 take tiles t / t+1 = the two N tiles of one pixel block, for the same number of rounds
     if (CL == 1)
-      CDR_CHECK_ARG(p.n_tiles % 2 == 0 && !l.res, "tap_gemm_tc: CTA pairs need an even number of N tiles and no residual");
+      CDR_CHECK_ARG(p.n_tiles % 2 == 0, "tap_gemm_tc: CTA pairs need an even number of N tiles");
     grid &= ~1;
     attr[n_attr].id = cudaLaunchAttributeClusterDimension;
     attr[n_attr].val.clusterDim.x = 2;
@@ -1252,6 +1263,7 @@ static int launch_tc(const TcLaunch& l, cudaStream_t st) {
   if (kind == kKindBF16 && ofmt == kFmtBF16) {
     if (bn == 256 && tc_pair2_ok(l)) return launch_tc_t<256, kKindBF16, kFmtBF16, 2>(l, st);
     if (bn == 256) return launch_tc_t<256, kKindBF16, kFmtBF16>(l, st);
+    if (bn == 128 && l.res && tc_cluster_ok(l, bn)) return launch_tc_t<128, kKindBF16, kFmtBF16, 1>(l, st);
     if (bn == 128) return launch_tc_t<128, kKindBF16, kFmtBF16>(l, st);
     if (bn == 64) return launch_tc_t<64, kKindBF16, kFmtBF16>(l, st);
     if (bn == 32) return launch_tc_t<32, kKindBF16, kFmtBF16>(l, st);
