@@ -58,6 +58,16 @@ def test_training_mode_rejected(pkg):
 def test_reference_argument_errors(pkg):
     with pytest.raises(NotImplementedError):
         pkg.CDRNet(synth.make_cfg(18, 19), n_views=3)
+    with pytest.raises(NotImplementedError):
+        pkg.CDRNet(synth.make_cfg(18, 19), fusion_in_dim=512)
+    with pytest.raises(ValueError, match="4/3"):          # the reference's ftl cannot reshape 2*300 channels into 4 blocks of 3
+        pkg.CDRNet(synth.make_cfg(18, 19), fusion_hid_ch1=300, fusion_hid_ch2=300)
+    with pytest.raises(NotImplementedError):
+        pkg.CDRNet(synth.make_cfg(18, 19), fusion_hid_ch1=30, fusion_hid_ch2=40)      # not a multiple of 12
+    m = pkg.CDRNet(synth.make_cfg(18, 19), fusion_hid_ch1=192, fusion_hid_ch2=256)
+    assert m.CF.conv_layer1[0].out_channels == 192 and m.CF.conv_layer2[0].in_channels == 512
+    with pytest.raises(ValueError):
+        pkg.CDRNet(synth.make_cfg(18, 19), precision="bf16", encoder_precision="fp32")   # fp16-plane latents need the fp32 head
     with pytest.raises(ValueError):
         pkg.CDRNet(synth.make_cfg(18, 19), precision="fp8")
     with pytest.raises(ValueError, match="does not exist"):
