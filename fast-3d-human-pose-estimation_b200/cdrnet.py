@@ -465,11 +465,11 @@ class CDRNet(nn.Module):
     def forward_frames(self, frames, proj_list, mean=None, std=None, img_size=None):
         """Device-side input pipeline: frames = [left, right] raw uint8 CUDA tensors
         (B,H,W,3) — or one (2B,H,W,3) tensor, left half first — instead of inference.py:40-52's
-        PIL -> ToTensor -> Normalize -> .to(device).  Needs ``encoder_precision='bf16'``."""
+        PIL -> ToTensor -> Normalize -> .to(device).  Needs ``encoder_precision='fp32'`` or ``'bf16'``."""
         from .encoder import IMAGENET_MEAN, IMAGENET_STD
         _require_eval(self)
         if self._tc_encoder is None:
-            raise RuntimeError("forward_frames needs CDRNet(..., encoder_precision='bf16')")
+            raise RuntimeError("forward_frames needs CDRNet(..., encoder_precision='fp32' or 'bf16')")
         x = frames if isinstance(frames, torch.Tensor) else torch.cat([frames[0], frames[1]], 0)
         rows, _ = self._tc_encoder.rows(x, mean=IMAGENET_MEAN if mean is None else tuple(float(v) for v in mean),
                                         std=IMAGENET_STD if std is None else tuple(float(v) for v in std))
@@ -491,7 +491,7 @@ class PoseResNet(nn.Module):
         self._tc_encoder = TcEncoder(self.encoder, encoder_precision) if encoder_precision != "torch" else None
 
     def forward(self, x):
-        """x: (N,3,256,256) float images — or, with encoder_precision='bf16', raw (N,256,256,3) uint8 frames."""
+        """x: (N,3,256,256) float images — or, with encoder_precision='fp32' / 'bf16', raw (N,256,256,3) uint8 frames."""
         if self._tc_encoder is not None and self.decoder._packed.precision != "fp32_ffma" and \
                 tuple(x.shape[-3:] if x.dtype == torch.uint8 else x.shape[-2:])[:2] == (256, 256):
             rows, _ = self._tc_encoder.rows(x)

@@ -92,11 +92,13 @@ IMAGENET_STD = (0.229, 0.224, 0.225)
 class TcEncoder:
     """A Bottleneck ``ResNet`` on libcdrhead (include/cdrhead.h ``cdr_encoder_*``):
     layer1..layer4 on the tcgen05 tap-GEMM kernel, the 7x7 stem + max-pool on a warp-MMA kernel
-    (``cdr_encoder_forward_images``; images with H % 16 or W % 64 != 0 fall back to a cuDNN bf16
-    stem whose channels-last output is the same NHWC layout).  bf16 activations, eval-mode BN
-    folded, fp32 accumulation.  Inference only;
+    (``cdr_encoder_forward_images``; in bf16 mode images with H % 16 or W % 64 != 0 fall back to a cuDNN bf16
+    stem whose channels-last output is the same NHWC layout).  Eval-mode BN folded, fp32 accumulation.
+    ``precision='bf16'``: bf16 activations; ``precision='fp32'``: the reference's precision — scaled fp16 hi/lo planes,
+    3 MMAs per product, residual add on planes, fp32 FFMA stem (1.5e-6 of max from the fp64 network).  Inference only;
     weights are re-packed when a parameter changes.  ``rows(x)`` returns the latents as bf16
-    pixel-major rows (n*h*w, 2048) — what ``cdr_head_forward_rows`` consumes; ``__call__`` returns
+    pixel-major rows (n*h*w, 2048) — what ``cdr_head_forward_rows`` consumes — or, in fp32 mode, the opaque
+    "fp16 planes" uint8 buffer ``cdr_head_forward_planes`` consumes; ``__call__`` returns
     the reference's (n, 2048, h, w) fp32 tensor."""
 
     def __init__(self, resnet, precision="bf16"):

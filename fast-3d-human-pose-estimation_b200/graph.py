@@ -299,11 +299,11 @@ class FramePipeline(_GraphHolder):
         collect():  waits for the oldest batch in flight, returns its pinned host results.
 
     12 bytes per pixel of fp32 tensors shrink to 3 on PCIe and the host never runs torchvision.
-    Needs ``CDRNet(..., encoder_precision='bf16')``."""
+    Needs ``CDRNet(..., encoder_precision='fp32')`` (the reference's precision) or ``'bf16'``."""
 
     def __init__(self, model, batch, img_hw=(256, 256), gt=None, mean=None, std=None, warmup=2):
         if model._tc_encoder is None:
-            raise RuntimeError("FramePipeline needs CDRNet(..., encoder_precision='bf16')")
+            raise RuntimeError("FramePipeline needs CDRNet(..., encoder_precision='fp32' or 'bf16')")
         self.model, self.gt, self.batch = model, gt, batch
         self.mean, self.std = mean, std
         self.dev = dev = next(model.CF.parameters()).device
