@@ -7,6 +7,7 @@
 // image patch: A[m][k] = patch[base(m) + off(k)], with the K axis laid out as 7 rows of 22 (21 taps*
 // channels + 1 zero pad) so that a fragment's (k, k+1) pair is one aligned 32-bit LDS.  HBM-bound by
 // design (100 MB in, 268 MB out per 128 images); the pool is a second, purely streaming kernel.
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -405,13 +406,202 @@ maxpool3s2_f16p_kernel(const float* __restrict__ in, int Hi, int Wi, int C8, lon
   *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l8);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// The fp32-accurate stem on the tensor cores (round 2, replaces the FFMA kernel above in the f16x2 encoder: 1.02 ->
+// see DESIGN.md §7): the bf16 kernel's implicit GEMM on warp-level mma.sync.m16n8k16, with BOTH operands as fp16 hi/lo
+// pairs and three MMAs per product — x w = xh wh + 2^-11 (xh wl + xl wh) (+ 2^-22 xl wl, dropped) — exactly the f16x2
+// scheme of gemm_tc.cu.  fp16 products are exact in the fp32 accumulators; main and correction terms accumulate
+// separately (K = 147: no long same-signed chain).  Pixels need no scale (|x| < 65504; the lo plane keeps values down
+// to 2^-36 absolute), weights carry one power-of-two scale per output channel (2^-t undone in the epilogue).
+constexpr int kT16W = 16;                          // conv-output tile of one CTA pass: 8 rows x 16 columns, one row per warp
+constexpr int kP16W = 2 * kT16W + 5;               // 37 input columns
+constexpr int kP16Pitch = 112;                     // 37 * 3 = 111 elements per patch row, padded to even
+constexpr int kStem16SmemBytes = (2 * kStemCo * kStemWPitch + 2 * kPatchH * kP16Pitch) * (int)sizeof(__half);
+
+// conv1 (64,3,7,7) + bn1 -> fp16 hi / lo [64][kStemWPitch] in the K' order of the bf16 kernel, wsi[64] = 2^-t, bias[64]
+__global__ void pack_stem_f16x2_kernel(CdrConvBn s, __half* __restrict__ w_hi, __half* __restrict__ w_lo,
+                                       float* __restrict__ wsi, float* __restrict__ bias) {
+  const int n = blockIdx.x;                        // one block per output channel
+  __shared__ float red[8];
+  const double sc = (double)s.bn_weight[n] / sqrt((double)s.bn_var[n] + 1e-5);
+  auto val = [&](int k) -> float {
+    const int ky = k / kStemRow, r = k - ky * kStemRow;
+    if (ky >= kStemKy || r >= 21) return 0.f;
+    const int kx = r / 3, ci = r - kx * 3;
+    return (float)((double)s.weight[((n * 3 + ci) * 7 + ky) * 7 + kx] * sc);
+  };
+  float mx = 0.f;
+  for (int k = threadIdx.x; k < kStemWPitch; k += blockDim.x) mx = fmaxf(mx, fabsf(val(k)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  const int t = mx > 0.f ? 13 - ilogbf(mx) : 0;
+  if (threadIdx.x == 0) {
+    wsi[n] = ldexpf(1.f, -t);
+    bias[n] = (float)((double)s.bn_bias[n] - (double)s.bn_mean[n] * sc);
+  }
+  const float up = ldexpf(1.f, t);
+  for (int k = threadIdx.x; k < kStemWPitch; k += blockDim.x) {
+    const float X = val(k) * up;
+    const __half h = __float2half_rn(X);
+    w_hi[n * kStemWPitch + k] = h;
+    w_lo[n * kStemWPitch + k] = __float2half_rn((X - __half2float(h)) * 2048.f);
+  }
+}
+
+__device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// grid (conv rows / 8, images); each CTA walks the W/32 column tiles of its row band; fp32 NHWC output + amax
+template <bool kU8>
+__global__ void __launch_bounds__(256, 2)
+stem_conv_f16x2_kernel(const void* __restrict__ xin, int H, int W, const StemNorm nrm, const __half* __restrict__ wpk_hi,
+                       const __half* __restrict__ wpk_lo, const float* __restrict__ wsi, const float* __restrict__ bias,
+                       float* __restrict__ out, float* __restrict__ amax_out) {
+  extern __shared__ __align__(16) unsigned char smem_h[];
+  __half* s_wh = reinterpret_cast<__half*>(smem_h);                 // [64][168]
+  __half* s_wl = s_wh + kStemCo * kStemWPitch;
+  __half* s_ph = s_wl + kStemCo * kStemWPitch;                      // [21][112]
+  __half* s_pl = s_ph + kPatchH * kP16Pitch;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int img = blockIdx.y, oy0 = blockIdx.x * kTileH;
+  const int Ho = H >> 1, Wo = W >> 1;
+  for (int i = threadIdx.x; i < kStemCo * kStemWPitch / 8; i += 256) {
+    reinterpret_cast<uint4*>(s_wh)[i] = __ldg(reinterpret_cast<const uint4*>(wpk_hi) + i);
+    reinterpret_cast<uint4*>(s_wl)[i] = __ldg(reinterpret_cast<const uint4*>(wpk_lo) + i);
+  }
+  float bv[8][2], sv[8][2];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    bv[nt][0] = __ldg(bias + nt * 8 + 2 * t);
+    bv[nt][1] = __ldg(bias + nt * 8 + 2 * t + 1);
+    sv[nt][0] = __ldg(wsi + nt * 8 + 2 * t);
+    sv[nt][1] = __ldg(wsi + nt * 8 + 2 * t + 1);
+  }
+  int koff[kStemK / 16][2];
+#pragma unroll
+  for (int s = 0; s < kStemK / 16; ++s) {
+#pragma unroll
+    for (int hk = 0; hk < 2; ++hk) {
+      const int k = 16 * s + 8 * hk + 2 * t;
+      const int ky = k / kStemRow, r = k - ky * kStemRow;
+      koff[s][hk] = ky < kStemKy ? ky * kP16Pitch + r : 0;         // padded k: weight is zero, any address does
+    }
+  }
+  const float* xi = reinterpret_cast<const float*>(xin) + (size_t)img * 3 * H * W;
+  const uint8_t* xu = reinterpret_cast<const uint8_t*>(xin) + (size_t)img * 3 * H * W;
+  float mx = 0.f;
+  for (int ox0 = 0; ox0 < Wo; ox0 += kT16W) {
+    __syncthreads();                                   // previous pass done with the patch (and the weights visible)
+    const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
+    for (int i = threadIdx.x; i < kPatchH * 3 * kP16W; i += 256) {
+      int row, e;
+      float v = 0.f;
+      if constexpr (!kU8) {
+        const int col = i % kP16W, rc = i / kP16W;
+        const int ci = rc % 3;
+        row = rc / 3;
+        e = col * 3 + ci;
+        const int iy = iy0 + row, ix = ix0 + col;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xi + ((size_t)ci * H + iy) * W + ix);
+      } else {
+        e = i % (3 * kP16W);
+        row = i / (3 * kP16W);
+        const int col = e / 3, ci = e - col * 3;
+        const int iy = iy0 + row, ix = ix0 + col;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {                // zero padding applies AFTER normalisation
+          const float u = (float)__ldg(xu + ((size_t)iy * W + ix) * 3 + ci);
+          v = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.f), nrm.mean[ci]), nrm.std[ci]);
+        }
+      }
+      const __half h = __float2half_rn(v);
+      s_ph[row * kP16Pitch + e] = h;
+      s_pl[row * kP16Pitch + e] = __float2half_rn((v - __half2float(h)) * 2048.f);
+    }
+    if (threadIdx.x < kPatchH) {
+      s_ph[threadIdx.x * kP16Pitch + 111] = __float2half_rn(0.f);
+      s_pl[threadIdx.x * kP16Pitch + 111] = __float2half_rn(0.f);
+    }
+    __syncthreads();
+    float am[8][4], ac[8][4];                          // main (hi hi) and correction (hi lo + lo hi) accumulators
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) am[nt][e] = ac[nt][e] = 0.f;
+    // this warp: conv row `warp` of the tile, columns {g, g + 8}
+    const int base0 = (2 * warp) * kP16Pitch + 6 * g;
+#pragma unroll
+    for (int s = 0; s < kStemK / 16; ++s) {
+      uint32_t ah[4], al[4];
+      ah[0] = *reinterpret_cast<const uint32_t*>(s_ph + base0 + koff[s][0]);
+      ah[1] = *reinterpret_cast<const uint32_t*>(s_ph + base0 + 48 + koff[s][0]);       // column g + 8
+      ah[2] = *reinterpret_cast<const uint32_t*>(s_ph + base0 + koff[s][1]);
+      ah[3] = *reinterpret_cast<const uint32_t*>(s_ph + base0 + 48 + koff[s][1]);
+      al[0] = *reinterpret_cast<const uint32_t*>(s_pl + base0 + koff[s][0]);
+      al[1] = *reinterpret_cast<const uint32_t*>(s_pl + base0 + 48 + koff[s][0]);
+      al[2] = *reinterpret_cast<const uint32_t*>(s_pl + base0 + koff[s][1]);
+      al[3] = *reinterpret_cast<const uint32_t*>(s_pl + base0 + 48 + koff[s][1]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int wo = (nt * 8 + g) * kStemWPitch + 16 * s + 2 * t;
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(s_wh + wo), bh1 = *reinterpret_cast<const uint32_t*>(s_wh + wo + 8);
+        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(s_wl + wo), bl1 = *reinterpret_cast<const uint32_t*>(s_wl + wo + 8);
+        mma_f16_16816(am[nt], ah, bh0, bh1);
+        mma_f16_16816(ac[nt], ah, bl0, bl1);
+        mma_f16_16816(ac[nt], al, bh0, bh1);
+      }
+    }
+    // (main + 2^-11 corr) * 2^-t + bias, ReLU, fp32 NHWC: pixel (oy0 + warp, ox0 + g [+8]), channels nt*8 + 2t, +1
+    const int oy = oy0 + warp;
+    if (oy < Ho) {
+#pragma unroll
+      for (int hr = 0; hr < 2; ++hr) {
+        const int ox = ox0 + g + 8 * hr;
+        if (ox < Wo) {
+          float* o = out + (((size_t)img * Ho + oy) * Wo + ox) * kStemCo + 2 * t;
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            const float v0 = fmaxf(fmaf(fmaf(ac[nt][2 * hr], 1.f / 2048.f, am[nt][2 * hr]), sv[nt][0], bv[nt][0]), 0.f);
+            const float v1 = fmaxf(fmaf(fmaf(ac[nt][2 * hr + 1], 1.f / 2048.f, am[nt][2 * hr + 1]), sv[nt][1], bv[nt][1]), 0.f);
+            mx = fmaxf(mx, fmaxf(v0, v1));
+            *reinterpret_cast<float2*>(o + nt * 8) = make_float2(v0, v1);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(amax_out), __float_as_uint(mx));   // mx >= 0
+}
+
+// packed buffer of the fp32-accurate stem: [fp32 weights [147][64] (FFMA cross-check) | fp16 hi [64][168] | fp16 lo | wsi [64]]
+constexpr size_t kStem32WBytes = (size_t)kStemK32 * kStemCo * sizeof(float);                     // 37632
+constexpr size_t kStem16PlaneBytes = (size_t)kStemCo * kStemWPitch * sizeof(__half);             // 21504
+static bool stem_use_ffma() {          // CDR_STEM_FFMA=1: the CUDA-core kernel (A/B timing, cross-check)
+  const char* e = getenv("CDR_STEM_FFMA");
+  return e && e[0] == '1';
+}
 int launch_pack_stem_f32(const CdrConvBn& s, float* w, float* bias, cudaStream_t st) {
   CDR_CHECK_ARG(s.weight && s.bn_weight && s.bn_bias && s.bn_mean && s.bn_var && w && bias, "pack_stem: bad args");
   pack_stem_f32_kernel<<<ceil_div(kStemK32 * kStemCo, 256), 256, 0, st>>>(s, w, bias);
   CDR_LAUNCH_OK("pack_stem_f32_kernel");
+  uint8_t* b = reinterpret_cast<uint8_t*>(w) + kStem32WBytes;
+  pack_stem_f16x2_kernel<<<kStemCo, 64, 0, st>>>(s, reinterpret_cast<__half*>(b), reinterpret_cast<__half*>(b + kStem16PlaneBytes),
+                                                 reinterpret_cast<float*>(b + 2 * kStem16PlaneBytes), bias);
+  CDR_LAUNCH_OK("pack_stem_f16x2_kernel");
   return CDR_OK;
 }
-size_t stem_weight_bytes_f32() { return (size_t)kStemK32 * kStemCo * sizeof(float); }
+size_t stem_weight_bytes_f32() { return kStem32WBytes + 2 * kStem16PlaneBytes + kStemCo * sizeof(float); }
 
 int launch_stem_f32(const void* x, int is_u8, const float* mean, const float* std, int n, int H, int W, const float* w,
                     const float* bias, float* conv_out, void* pooled_hi, void* pooled_lo, float* slot, cudaStream_t st) {
@@ -425,9 +615,29 @@ int launch_stem_f32(const void* x, int is_u8, const float* mean, const float* st
   CDR_CHECK_ARG(H % 16 == 0 && W % 64 == 0, "stem: image %dx%d must have H %% 16 == 0 and W %% 64 == 0", H, W);
   CDR_CHECK_ARG(((uintptr_t)conv_out & 15) == 0 && ((uintptr_t)pooled_hi & 15) == 0 && ((uintptr_t)pooled_lo & 15) == 0 &&
                     ((uintptr_t)w & 15) == 0, "stem: alignment");
-  static DeviceOnce attr_set[2];
+  static DeviceOnce attr_set[2], attr16_set[2];
   const int Ho = H / 2, Wo = W / 2;
-  if (is_u8) {
+  if (!stem_use_ffma()) {
+    // tensor-core form: fp16 hi/lo operands, 3 mma.sync per product
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(w) + kStem32WBytes;
+    const __half* wh = reinterpret_cast<const __half*>(b);
+    const __half* wl = reinterpret_cast<const __half*>(b + kStem16PlaneBytes);
+    const float* wsi = reinterpret_cast<const float*>(b + 2 * kStem16PlaneBytes);
+    if (is_u8) {
+      if (attr16_set[1].need()) {
+        CDR_CUDA(cudaFuncSetAttribute(stem_conv_f16x2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStem16SmemBytes));
+        attr16_set[1].done();
+      }
+      stem_conv_f16x2_kernel<true><<<dim3(Ho / kTileH, n), 256, kStem16SmemBytes, st>>>(x, H, W, nrm, wh, wl, wsi, bias, conv_out, slot);
+    } else {
+      if (attr16_set[0].need()) {
+        CDR_CUDA(cudaFuncSetAttribute(stem_conv_f16x2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStem16SmemBytes));
+        attr16_set[0].done();
+      }
+      stem_conv_f16x2_kernel<false><<<dim3(Ho / kTileH, n), 256, kStem16SmemBytes, st>>>(x, H, W, nrm, wh, wl, wsi, bias, conv_out, slot);
+    }
+    CDR_LAUNCH_OK("stem_conv_f16x2_kernel");
+  } else if (is_u8) {
     if (attr_set[1].need()) {
       CDR_CUDA(cudaFuncSetAttribute(stem_conv_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStem32SmemBytes));
       attr_set[1].done();
@@ -440,7 +650,7 @@ int launch_stem_f32(const void* x, int is_u8, const float* mean, const float* st
     }
     stem_conv_f32_kernel<false><<<dim3(Ho / kTileH, n), 256, kStem32SmemBytes, st>>>(x, H, W, nrm, w, bias, conv_out, slot);
   }
-  CDR_LAUNCH_OK("stem_conv_f32_kernel");
+  if (stem_use_ffma()) CDR_LAUNCH_OK("stem_conv_f32_kernel");
   const long long total = (long long)n * (Ho / 2) * (Wo / 2) * (kStemCo / 8);
   maxpool3s2_f16p_kernel<<<(unsigned)ceil_div<long long>(total, 256), 256, 0, st>>>(
       conv_out, Ho, Wo, kStemCo / 8, total, (__half*)pooled_hi, (__half*)pooled_lo, slot);
