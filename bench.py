@@ -962,7 +962,7 @@ def full_pipeline(args, ctx, precision):
             except Exception as e:
                 rec["e2e_uint8_frames_host" + ("" if bb == B else f"_batch{bb}")] = {"error": repr(e)[:200]}
         if enc_prec == "fp32":
-            rec["precision"] = ("encoder: scaled fp16 hi/lo planes, 3 kind::f16 MMAs per product, fp32 FFMA stem (latents "
+            rec["precision"] = ("encoder: scaled fp16 hi/lo planes, 3 kind::f16 MMAs per product, three-term fp16 mma.sync stem (latents "
                                 "1.5e-6 of max vs fp64 on ResNet-50); head: fp32 mode")
             rec["encoder_tflops_issued_mma"] = 3 * rec["encoder_tflops"]
             out["encoder_f16x2_tcgen05"] = rec

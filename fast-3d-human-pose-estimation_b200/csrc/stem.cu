@@ -237,7 +237,8 @@ int launch_stem(const void* x, int is_u8, const float* mean, const float* std, i
 
 
 // ------------------------------------------------------------------------------------------
-// The same stem at fp32 accuracy for the f16x2 ("fp32") encoder: fp32 FFMA (the conv is 2.3 % of the encoder's
+// The same stem at fp32 accuracy for the f16x2 ("fp32") encoder, first version (kept as the CDR_STEM_FFMA=1 cross-check of the
+// tensor-core form further down): fp32 FFMA (the conv is 2.3 % of the encoder's
 // FLOPs), fp32 NHWC scratch, then the max-pool writes the scaled fp16 hi/lo planes the tcgen05 layers read.  The
 // pooled tensor's scale comes from the EXACT maximum (max-pool commutes with max): the conv kernel atomicMax-es its
 // post-ReLU outputs into slot[0], the pool kernel turns that into slot[1] = 2^(13 - ilogb(amax)).

@@ -95,7 +95,7 @@ class TcEncoder:
     (``cdr_encoder_forward_images``; in bf16 mode images with H % 16 or W % 64 != 0 fall back to a cuDNN bf16
     stem whose channels-last output is the same NHWC layout).  Eval-mode BN folded, fp32 accumulation.
     ``precision='bf16'``: bf16 activations; ``precision='fp32'``: the reference's precision — scaled fp16 hi/lo planes,
-    3 MMAs per product, residual add on planes, fp32 FFMA stem (1.5e-6 of max from the fp64 network).  Inference only;
+    3 MMAs per product, residual add on planes, three-term fp16 stem (1.5e-6 of max from the fp64 network).  Inference only;
     weights are re-packed when a parameter changes.  ``rows(x)`` returns the latents as bf16
     pixel-major rows (n*h*w, 2048) — what ``cdr_head_forward_rows`` consumes — or, in fp32 mode, the opaque
     "fp16 planes" uint8 buffer ``cdr_head_forward_planes`` consumes; ``__call__`` returns
@@ -110,7 +110,7 @@ class TcEncoder:
         if precision not in ("bf16", "fp32"):
             raise ValueError(f"TcEncoder precision must be 'bf16' or 'fp32', got {precision!r}")
         # 'fp32': the reference's precision on the tensor cores — scaled fp16 hi/lo planes, 3 MMAs per product, fp32
-        # FFMA stem (include/cdrhead.h: cdr_encoder_create_prec).  rows() then returns the opaque "fp16 planes" buffer
+        # three-term fp16 stem (include/cdrhead.h: cdr_encoder_create_prec).  rows() then returns the opaque "fp16 planes" buffer
         self.precision = precision
         self.resnet, self.blocks = resnet, blocks
         self._box, self._key, self._stem = None, None, None

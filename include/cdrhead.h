@@ -187,7 +187,7 @@ typedef struct CdrEncoder CdrEncoder;
 int cdr_encoder_create(const CdrEncoderSpec* spec, void* stream, CdrEncoder** out);   /* CDR_PREC_BF16 */
 /* The same encoder at the reference's precision (models/encoder.py runs in fp32): precision = CDR_PREC_F16X2 keeps
  * every activation as scaled fp16 hi/lo planes (2^-24 relative) and runs every conv as 3 kind::f16 MMAs per product
- * (gemm_tc.cu: kKindF16X2), the residual add in the epilogue; the 7x7 stem runs in fp32 FFMA.  Such a handle
+ * (gemm_tc.cu: kKindF16X2), the residual add in the epilogue; the 7x7 stem runs as three fp16 mma.sync per product.  Such a handle
  *   - starts from images only (cdr_encoder_forward_images / _frames_u8; cdr_encoder_forward returns CDR_ERR_INVALID),
  *   - writes its latents as an "fp16 planes" buffer instead of bf16 rows:
  *       [hi plane: rows*C fp16 | lo plane: rows*C fp16 | float amax, float scale]

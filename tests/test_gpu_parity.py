@@ -720,7 +720,7 @@ def test_tc_encoder_resnet50_vs_emulated_and_fp32(cuda_pkg):
 
 def test_tc_encoder_fp32_resnet50_vs_fp64(cuda_pkg):
     """SURVEY §8f rank 1 at the reference's precision: the f16x2 tcgen05 encoder (scaled fp16 hi/lo planes, 3 MMAs
-    per product, residual add on planes in the epilogue, fp32 FFMA stem) against the fp64 evaluation of the same
+    per product, residual add on planes in the epilogue, three-term fp16 tensor-core stem) against the fp64 evaluation of the same
     network, beside the reference's own fp32 module (torch, TF32 off) against that fp64."""
     from fast_3d_human_pose_estimation_b200.encoder import TcEncoder
     r = _seeded_resnet(50)
