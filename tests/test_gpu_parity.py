@@ -862,6 +862,42 @@ def test_frames_u8_match_reference_preprocessing(cuda_pkg):
         assert torch.equal(kp_h[0], kl.cpu()) and torch.equal(kp_h[1], kr.cpu()) and torch.equal(xyz_h, xyz.cpu())
 
 
+def test_frame_pipeline_reference_precision(cuda_pkg):
+    """The reference-precision pipeline as a service: uint8 frames in pinned host memory -> FramePipeline on the f16x2
+    encoder + fp32 head (one CUDA graph per slot: fused normalisation, three-term stem, planes through layer1-4 into
+    conv_layer1, MPJPE sums) gives the eager forward_frames result bit for bit, replay after replay; PoseResNet on raw
+    frames equals PoseResNet on the preprocessed tensor."""
+    from fast_3d_human_pose_estimation_b200.encoder import IMAGENET_MEAN, IMAGENET_STD
+    b = 3
+    torch.manual_seed(0)
+    m = cuda_pkg.CDRNet(synth.make_cfg(50, 19), precision="fp32", encoder_precision="fp32")
+    m.load_state_dict(synth.make_head_state_dict(seed=0, calibrated=True), strict=False)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(3)
+    frames = [torch.randint(0, 256, (b, 256, 256, 3), dtype=torch.uint8, generator=g) for _ in range(2)]
+    cams = synth.make_cameras(b, seed=2)
+    gt = synth.make_gt(cams, seed=3)
+    Ps = [torch.from_numpy(cams["P_l"]), torch.from_numpy(cams["P_r"])]
+    gtd = {k: torch.from_numpy(gt[k]).cuda() for k in ("gt3d", "gt2d_l", "gt2d_r", "vis")}
+    (kl, kr), xyz = m.forward_frames([f.cuda() for f in frames], [p.cuda() for p in Ps])
+    sums = cuda_pkg.mpjpe_sums([kl, kr], xyz, gtd["gt3d"], gtd["gt2d_l"], gtd["gt2d_r"], gtd["vis"])
+    pipe = cuda_pkg.FramePipeline(m, b, gt=gtd)
+    fh = torch.stack(frames, 0).pin_memory()
+    for _ in range(2):
+        pipe.submit(fh, [p.pin_memory() for p in Ps])
+        pipe.submit([f.pin_memory() for f in frames], [p.pin_memory() for p in Ps])
+        for _ in range(2):
+            _, kp_h, xyz_h, sums_h = pipe.collect()
+            assert torch.equal(kp_h[0], kl.cpu()) and torch.equal(kp_h[1], kr.cpu()) and torch.equal(xyz_h, xyz.cpu())
+            assert torch.equal(sums_h, sums.cpu())
+    # the same images as floats through CDRNet.forward (host-side ToTensor + Normalize, inference.py:40-44)
+    mean = torch.tensor(IMAGENET_MEAN).reshape(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD).reshape(1, 3, 1, 1)
+    pre = [(f.permute(0, 3, 1, 2).float().div(255).sub_(mean).div_(std)).cuda() for f in frames]
+    (kl2, kr2), xyz2 = m(pre, [p.cuda() for p in Ps])
+    assert torch.equal(kl2, kl) and torch.equal(kr2, kr) and torch.equal(xyz2, xyz)
+
+
 def test_tc_encoder_shapes_and_errors(cuda_pkg):
     """Other image sizes / batch 1 through the tcgen05 encoder; unsupported geometry fails loudly."""
     from fast_3d_human_pose_estimation_b200.encoder import TcEncoder
