@@ -90,3 +90,12 @@ def test_evaluate_sequence_matches_reference_loop(cuda_pkg, tmp_path):
     assert got["frames"] == 4 and got["pred_3d"].shape == (4, 19, 3) and got["pred_2d"].shape == (2, 4, 19, 2)
     assert abs(got["mpjpe_2d"] - want[0]) <= 1e-3
     assert abs(got["mpjpe_3d"] - want[1]) <= max(1e-2, 1e-4 * want[1])
+    # the same loop with the ENCODER on this library too, at the reference's precision (raw uint8 frames -> fused
+    # normalisation -> f16x2 ResNet -> fp32 head): the whole of inference.py's arithmetic without torch kernels
+    m2 = cuda_pkg.CDRNet(cfg, encoder_precision="fp32")
+    m2.load_state_dict(sd)
+    m2 = m2.cuda().eval()
+    got2 = mads.evaluate_sequence(m2, mads.MADSFrames(data, cfg.MODEL.IMAGE_SIZE, "HipHop"), batch=3)
+    print(f"MADS loop, f16x2 encoder: MPJPE2D {got2['mpjpe_2d']:.6f} MPJPE3D {got2['mpjpe_3d']:.6f}")
+    assert abs(got2["mpjpe_2d"] - want[0]) <= 1e-3
+    assert abs(got2["mpjpe_3d"] - want[1]) <= max(1e-2, 1e-4 * want[1])
