@@ -25,6 +25,7 @@ training mode raises.  There is no CPU / PyTorch fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 from torch import nn
@@ -126,6 +127,16 @@ class PoseDecoder(nn.Module):
             _lib.check(fn(handle, _lib.ptr(rows), n, _lib.ptr(out), _lib.ptr(ws), nbytes.value,
                           _lib.current_stream_ptr(rows.device)))
         return out
+
+
+def _default_encoder_precision(value):
+    """``encoder_precision=None`` (the default of CDRNet / PoseResNet): the environment variable
+    ``CDR_ENCODER_PRECISION`` ('fp32' | 'bf16' | 'torch') or 'torch'.  It lets the reference's unmodified drivers, which
+    construct ``CDRNet(config)`` with no extra arguments (inference.py:28, baseline.py:27), run the ENCODER on this
+    library too — ``CDR_ENCODER_PRECISION=fp32 python inference.py`` — without touching their source."""
+    if value is not None:
+        return value
+    return os.environ.get("CDR_ENCODER_PRECISION", "torch")
 
 
 def _require_eval(m):
@@ -280,13 +291,14 @@ class CDRNet(nn.Module):
     everywhere; 'fp32_ffma' = the same arithmetic on CUDA cores (cross-check); 'bf16' = bf16 operands on tcgen05."""
 
     def __init__(self, cfg, n_views=2, nj=19, fusion_in_dim=2048, fusion_hid_ch1=300,
-                 fusion_hid_ch2=400, precision="fp32", encoder_precision="torch", trainable=False):
+                 fusion_hid_ch2=400, precision="fp32", encoder_precision=None, trainable=False):
         """encoder_precision: 'fp32' — this library's tcgen05 encoder at the reference's precision (scaled fp16 hi/lo
         planes, 3 MMAs per product; needs precision='fp32'); 'torch' (default — the reference's nn.Module on torch/cuDNN, fp32) or
         'bf16' (Bottleneck stages on libcdrhead's tcgen05 kernels, stem on cuDNN bf16).
         trainable: opt in to ``forward`` in training mode (``forward_train``, SURVEY §8f rank 3 slice)."""
         super().__init__()
         self.trainable = bool(trainable)
+        encoder_precision = _default_encoder_precision(encoder_precision)
         if encoder_precision not in ("torch", "bf16", "fp32"):
             raise ValueError(f"encoder_precision must be 'torch', 'bf16' or 'fp32', got {encoder_precision!r}")
         if encoder_precision == "fp32" and precision not in ("fp32", "f16x2"):
@@ -479,8 +491,9 @@ class CDRNet(nn.Module):
 class PoseResNet(nn.Module):
     """models/poseresnet.py:10-38: ResNet encoder (torch/cuDNN) + PoseDecoder (libcdrhead)."""
 
-    def __init__(self, cfg, precision="fp32", encoder_precision="torch"):
+    def __init__(self, cfg, precision="fp32", encoder_precision=None):
         super().__init__()
+        encoder_precision = _default_encoder_precision(encoder_precision)
         if encoder_precision not in ("torch", "bf16", "fp32"):
             raise ValueError(f"encoder_precision must be 'torch', 'bf16' or 'fp32', got {encoder_precision!r}")
         if encoder_precision == "fp32" and precision not in ("fp32", "f16x2"):

@@ -96,6 +96,35 @@ def test_cdrnet_inferencer_with_dropin(cuda_pkg, drivers, dgolden, tmp_path):
 
 @pytest.mark.gpu
 @needs_ref
+def test_cdrnet_inferencer_entirely_on_the_library(cuda_pkg, drivers, dgolden, tmp_path, monkeypatch):
+    """The same unmodified CDRNetInferencer with ``CDR_ENCODER_PRECISION=fp32`` in the environment: its plain
+    ``CDRNet(config)`` then runs the ResNet on this library as well (f16x2 planes, the reference's precision), so
+    inference() / estimate() involve no torch kernel in the network's arithmetic — and stay inside the flat tolerances
+    of the reference's own CPU output."""
+    inference_mod, baseline_mod = drivers
+    cfg = refload.load_config("mads_3d.yaml")
+    case = RD.driver_case()
+    sd = RD.seeded_state_dict(cuda_pkg.CDRNet, cfg)
+    monkeypatch.setenv("CDR_ENCODER_PRECISION", "fp32")
+    with RD.workdir_with_checkpoint(tmp_path, cfg, sd, "best.pth"):
+        saved = RD.substitute_shim(inference_mod, baseline_mod, cuda_pkg)
+        try:
+            inf = inference_mod.CDRNetInferencer(cfg)
+            assert inf.model.encoder_precision == "fp32" and inf.model._tc_encoder is not None
+            ours = RD.run_cdrnet_driver(inference_mod, cfg, case)
+        finally:
+            RD.restore(saved)
+    g = dgolden
+    d2 = max(np.abs(ours["kp_l"] - g["cdrnet.kp_l"]).max(), np.abs(ours["kp_r"] - g["cdrnet.kp_r"]).max())
+    d3 = np.abs(ours["xyz"] - g["cdrnet.xyz"]).max()
+    print(f"\nCDRNetInferencer, encoder AND head on the library vs reference golden: d2D={d2:.2e}px d3D={d3:.2e}mm "
+          f"MPJPE {ours['err']} vs {g['cdrnet.err']}")
+    assert d2 <= TOL_2D_PX and d3 <= TOL_3D_MM
+    assert abs(ours["err"][1] - g["cdrnet.err"][1]) <= TOL_MPJPE_MM and abs(ours["err"][0] - g["cdrnet.err"][0]) <= TOL_2D_PX
+
+
+@pytest.mark.gpu
+@needs_ref
 def test_baseline_driver_with_dropin(cuda_pkg, drivers, dgolden, tmp_path):
     """baseline.py's BaseLine with ``PoseResNet`` / ``get_max_preds`` / ``triangulation`` / ``calc_mpjpe``
     swapped.  uint8 key points are bit-identical to the reference's wherever the reference's own top-2
