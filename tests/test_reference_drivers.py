@@ -125,7 +125,8 @@ def test_cdrnet_inferencer_entirely_on_the_library(cuda_pkg, drivers, dgolden, t
 
 @pytest.mark.gpu
 @needs_ref
-def test_baseline_driver_with_dropin(cuda_pkg, drivers, dgolden, tmp_path):
+@pytest.mark.parametrize("enc", ["torch", "fp32"])
+def test_baseline_driver_with_dropin(cuda_pkg, drivers, dgolden, tmp_path, monkeypatch, enc):
     """baseline.py's BaseLine with ``PoseResNet`` / ``get_max_preds`` / ``triangulation`` / ``calc_mpjpe``
     swapped.  uint8 key points are bit-identical to the reference's wherever the reference's own top-2
     logit gap exceeds fp32 noise (a random-init network has near-flat maps: gaps down to 6e-6 of the
@@ -134,6 +135,7 @@ def test_baseline_driver_with_dropin(cuda_pkg, drivers, dgolden, tmp_path):
     ref = refload.load()
     cfg = refload.load_config("mads_2d.yaml")
     case = RD.driver_case()
+    monkeypatch.setenv("CDR_ENCODER_PRECISION", enc)       # "fp32": PoseResNet(config) runs its ResNet on the library too
     sd = RD.seeded_state_dict(cuda_pkg.PoseResNet, cfg)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -147,7 +149,7 @@ def test_baseline_driver_with_dropin(cuda_pkg, drivers, dgolden, tmp_path):
     assert ours["u8_l"].dtype == np.uint8 and ours["u8_l"].shape == (19, 2)
     decisive = g["baseline.top2_gap"] > 1e-4 * g["baseline.heat_absmax"]          # (view, joint)
     same = np.stack([(ours["u8_l"] == g["baseline.u8_l"]).all(-1), (ours["u8_r"] == g["baseline.u8_r"]).all(-1)])
-    print(f"\nBaseLine drop-in: key points identical {int(same.sum())}/38 (decisive {int(decisive.sum())}), "
+    print(f"\nBaseLine drop-in [encoder {enc}]: key points identical {int(same.sum())}/38 (decisive {int(decisive.sum())}), "
           f"err {ours['err']} vs {g['baseline.err']}")
     assert same[decisive].all()
     both = same.all(0)
