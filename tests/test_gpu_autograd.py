@@ -272,3 +272,62 @@ def test_bn_train_vs_torch(cuda_pkg, shape, relu):
     assert _rel(ours.bias.grad.cpu().double(), ref.bias.grad) < 2e-5
     with pytest.raises(RuntimeError):
         cuda_pkg.batch_norm_train(xd, ours.eval())
+
+
+def test_training_step_vs_the_reference_model(cuda_pkg):
+    """One training step of train_cdr.py (:105-127, warm-up branch: MPJPELoss on both views' 2D joints) — the UNMODIFIED
+    reference CDRNet + its MPJPELoss in train mode on this GPU (fp32, TF32 off) against CDRNet(trainable=True) +
+    this package's MPJPELoss: the head's BatchNorm / ReLU, pinv, FTL, soft-argmax, DLT and the loss run forward and
+    backward on libcdrhead, the convolutions on cuDNN in both.  Loss, the script's grad_norm, the gradient direction of
+    parameters all over the network and the BatchNorm running statistics after the step."""
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("reference sources not present")
+    ref = refload.load()
+    import importlib
+    ref_loss = importlib.import_module("models.loss")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        b, cfg = 2, synth.make_cfg(50, 19)
+        torch.manual_seed(0)
+        ours = cuda_pkg.CDRNet(cfg, trainable=True)
+        with torch.no_grad():
+            ours.decoder.final_layer.weight.mul_(10.0)     # train-mode BN keeps activations O(1): peaky heat-maps need gain
+        theirs = ref.CDRNet(cfg)
+        theirs.load_state_dict(ours.state_dict())
+        ours, theirs = ours.cuda().train(), theirs.cuda().train()
+        imgs = [x.cuda() for x in synth.make_images(b, seed=1)]
+        cams = synth.make_cameras(b, seed=2)
+        gt = synth.make_gt(cams, seed=3)
+        Ps = [torch.from_numpy(cams["P_l"]).cuda(), torch.from_numpy(cams["P_r"]).cuda()]
+        targets = [torch.from_numpy(gt["gt2d_l"]).float().cuda(), torch.from_numpy(gt["gt2d_r"]).float().cuda()]
+        weight = torch.from_numpy(gt["vis"]).float().cuda()
+
+        def step(model, criterion):
+            model.zero_grad()
+            pred_2ds, pred_3ds = model(imgs, Ps)                                   # train_cdr.py:105
+            loss = torch.zeros(1, device="cuda")
+            for pred, target in zip(pred_2ds, targets):                           # :113-115
+                loss = loss + criterion(pred, target, weight)
+            loss.backward()                                                       # :127
+            grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+            return float(loss), float(torch.norm(torch.cat([g.flatten() for g in grads.values()]))), grads, pred_3ds   # :129-130
+        l_t, gn_t, g_t, _ = step(theirs, ref_loss.MPJPELoss(True))
+        l_o, gn_o, g_o, xyz = step(ours, cuda_pkg.MPJPELoss(True))
+        print(f"\ntraining step: loss {l_o:.6f} vs reference {l_t:.6f}; grad_norm {gn_o:.6e} vs {gn_t:.6e}")
+        assert abs(l_o - l_t) <= 1e-4 * abs(l_t)
+        assert abs(gn_o - gn_t) <= 2e-2 * gn_t
+        assert set(g_o) == set(g_t) and bool(torch.isfinite(xyz).all())
+        worst = 1.0
+        for n in ("decoder.final_layer.weight", "decoder.deconv1.0.weight", "decoder.deconv3.1.weight", "CF.conv_layer2.3.weight",
+                  "CF.conv_layer1.1.bias", "CF.out_layer.1.0.weight", "encoder.layer4.2.conv3.weight", "encoder.conv1.weight"):
+            a, w = g_o[n].double().flatten(), g_t[n].double().flatten()
+            worst = min(worst, float(torch.dot(a, w) / (a.norm() * w.norm())))
+        print(f"worst gradient cosine over 8 parameter tensors: {worst:.6f}")
+        assert worst > 0.995
+        for (n, bo), (_, bt) in zip(ours.named_buffers(), theirs.named_buffers()):
+            if n.endswith(("running_mean", "running_var")) and n.startswith(("CF.", "decoder.")):
+                assert _rel(bo.double(), bt.double()) < 1e-4, n
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
