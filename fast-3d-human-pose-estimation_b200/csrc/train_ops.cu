@@ -198,17 +198,17 @@ bn_train_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__
 int launch_bn_train_forward(const float* x, int n, int c, int hw, const float* gamma, const float* beta, double eps,
                             double momentum, float* running_mean, float* running_var, int relu, float* y, float* save_mean,
                             float* save_invstd, cudaStream_t st) {
+  if ((hw & 3) != 0 || ((uintptr_t)x & 15) != 0 || ((uintptr_t)y & 15) != 0) {      // before anything is launched: no partial
+    set_error("cdr_bn_train_forward: H*W must be a multiple of 4 and the tensors 16-byte aligned");   // running-stat update
+    return CDR_ERR_UNSUPPORTED;
+  }
   bn_train_stats_kernel<<<c, kBnThreads, 0, st>>>(x, n, c, hw, eps, momentum, running_mean, running_var, save_mean, save_invstd);
   CDR_LAUNCH_OK("bn_train_stats_kernel");
-  if ((hw & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0) {
-    const long long total4 = (long long)n * c * (hw >> 2);
-    bn_train_apply_kernel<<<(unsigned)ceil_div<long long>(total4, 256), 256, 0, st>>>(x, total4, c, hw >> 2, gamma, beta,
-                                                                                      save_mean, save_invstd, relu, y);
-    CDR_LAUNCH_OK("bn_train_apply_kernel");
-    return CDR_OK;
-  }
-  set_error("cdr_bn_train_forward: H*W must be a multiple of 4 and the tensors 16-byte aligned");
-  return CDR_ERR_UNSUPPORTED;
+  const long long total4 = (long long)n * c * (hw >> 2);
+  bn_train_apply_kernel<<<(unsigned)ceil_div<long long>(total4, 256), 256, 0, st>>>(x, total4, c, hw >> 2, gamma, beta,
+                                                                                    save_mean, save_invstd, relu, y);
+  CDR_LAUNCH_OK("bn_train_apply_kernel");
+  return CDR_OK;
 }
 
 int launch_bn_train_backward(const float* x, const float* dy, int n, int c, int hw, const float* gamma, const float* beta,
