@@ -146,6 +146,7 @@ def batch_norm_train(x, bn, relu=False):
     x = _f32(x, "batch_norm_train: x")
     if x.dim() != 4 or x.shape[1] != bn.num_features:
         raise ValueError(f"batch_norm_train: (N,{bn.num_features},H,W) expected, got {tuple(x.shape)}")
+    y = _BNTrain.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, relu)
     with torch.no_grad():
-        bn.num_batches_tracked += 1                      # bookkeeping only (an int64 counter)
-    return _BNTrain.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, relu)
+        bn.num_batches_tracked += 1                      # bookkeeping only (an int64 counter), after the call succeeded
+    return y
