@@ -192,6 +192,7 @@ struct TcGemmParams {
   int c_pitch, c_fill;
   int relu;
   int out_mode;           // kOutRows / kOutDeconv or kOutPlanar (fp32)
+  int split_store;        // kOutRows + kFmtF16P: planes leave as two 16-row boxes through the two halves of the staging buffer
   int num_tiles;
 };
 
@@ -329,6 +330,36 @@ __device__ __forceinline__ void tma_store_block(const TcGemmParams& p, const voi
     ptx::bulk_commit();
   }
 #endif
+}
+
+// The same for the scaled fp16 hi/lo outputs of row-major layers (kOutRows, OFMT = kFmtF16P), where a warp stores TWO planes
+// through its one 4 KB staging buffer: stored as above, the lo plane had to wait for the TMA engine to finish READING the hi
+// plane's block out of the buffer (ncu source page of out_layer: 13 % of all stall samples on that wait, every tile).  Here
+// the buffer is two 2 KB halves and every plane leaves as two 16-row boxes (hi rows 0-15 -> half 0, hi rows 16-31 -> half 1,
+// lo rows 0-15 -> half 0, ...): a half is rewritten two stores after it was handed to the TMA engine, so
+// cp.async.bulk.wait_group.read 1 is almost always already satisfied.  The output tensor maps carry a 16-row box.
+__device__ __forceinline__ void tma_store_rows_split(const void* tmap, uint8_t* stage, int lane, const uint32_t (&words)[32],
+                                                     int c0, const StoreCoord& sc) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (lane == 0) ptx::bulk_wait_read<1>();          // the store that last used THIS half has read it
+    __syncwarp();
+    if ((lane >> 4) == h) {
+      const uint32_t base = ptx::smem_u32(stage) + (uint32_t)h * 2048u + (uint32_t)(lane & 15) * 128u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        ptx::st_shared_v4(base + (uint32_t)((j ^ (lane & 7)) << 4), words[4 * j], words[4 * j + 1], words[4 * j + 2],
+                          words[4 * j + 3]);
+    }
+    ptx::fence_proxy_async();
+    __syncwarp();
+#ifndef CDR_EXP_NO_TMASTORE
+    if (lane == 0) {
+      ptx::tma_store_3d(tmap, stage + h * 2048, c0, sc.m + 16 * h, sc.g);
+      ptx::bulk_commit();
+    }
+#endif
+  }
 }
 
 // K-blocks accumulated inside TMEM before the split kinds' main term is drained into fp32 registers.
@@ -795,9 +826,14 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           if (half == 1) {
             const int c0 = n0 + c - 32;            // first channel of the 64-column block
             if (c0 < p.c_fill) {
-              tma_store_block<Cfg::kStageBufs - 1>(p, &tmap_c, stage + sbuf * kStageBufBytes, lane, wh, c0, sc);
-              if constexpr (Cfg::kStageBufs > 1) sbuf ^= 1;
-              if constexpr (OFMT == kFmtF16P) tma_store_block<0>(p, &tmap_c_lo, stage, lane, wl, c0, sc);
+              if (OFMT == kFmtF16P && p.split_store) {
+                tma_store_rows_split(&tmap_c, stage, lane, wh, c0, sc);
+                tma_store_rows_split(&tmap_c_lo, stage, lane, wl, c0, sc);
+              } else {
+                tma_store_block<Cfg::kStageBufs - 1>(p, &tmap_c, stage + sbuf * kStageBufBytes, lane, wh, c0, sc);
+                if constexpr (Cfg::kStageBufs > 1) sbuf ^= 1;
+                if constexpr (OFMT == kFmtF16P) tma_store_block<0>(p, &tmap_c_lo, stage, lane, wl, c0, sc);
+              }
             }
           }
         }
@@ -1041,6 +1077,11 @@ static bool tc_use_pdl() {
   return v == 1;
 }
 
+// fp16-plane row outputs as two 16-row boxes per warp and plane (tma_store_rows_split): CDR_SPLIT_STORE=1 turns it on
+static bool tc_use_split_store() {
+  const char* e = getenv("CDR_SPLIT_STORE");
+  return e && e[0] == '1';
+}
 // CTA pairs with a multicast A tile (kernel template parameter CL): CDR_CLUSTER=0 turns them off for A/B timing
 static bool tc_use_cluster() {
   static int v = -1;
@@ -1193,7 +1234,8 @@ static int launch_tc_t(const TcLaunch& l, cudaStream_t st) {
         CDR_CHECK_ARG(gs % 8 == 0, "tap_gemm_tc: output group stride must be a 16-byte multiple");
         const uint64_t dims[3] = {(uint64_t)l.c_fill, (uint64_t)p.M, (uint64_t)l.groups};
         const uint64_t strides[2] = {(uint64_t)l.c_pitch, gs};
-        const uint32_t box[3] = {64, 32, 1};
+        p.split_store = OFMT == kFmtF16P && tc_use_split_store();
+        const uint32_t box[3] = {64, p.split_store ? 16u : 32u, 1};       // fp16 planes: two 16-row boxes per warp and plane
         if (int rc = make_tmap(&tmap_c[pl], l.C.p[pl], OFMT, 3, dims, strides, box)) return rc;
       }
     }
