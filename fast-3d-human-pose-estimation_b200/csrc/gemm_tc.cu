@@ -1077,7 +1077,9 @@ static bool tc_use_pdl() {
   return v == 1;
 }
 
-// fp16-plane row outputs as two 16-row boxes per warp and plane (tma_store_rows_split): CDR_SPLIT_STORE=1 turns it on
+// fp16-plane row outputs as two 16-row boxes per warp and plane (tma_store_rows_split): built, parity-green, MEASURED SLOWER
+// (f16x2 encoder 10.66 -> 10.92 ms, out_layer 43.3 -> 45.3 us: twice the store instructions and half-warp staging writes cost
+// more than the hidden buffer wait returns); opt-in for A/B timing with CDR_SPLIT_STORE=1
 static bool tc_use_split_store() {
   const char* e = getenv("CDR_SPLIT_STORE");
   return e && e[0] == '1';
