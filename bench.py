@@ -221,6 +221,48 @@ def reference_head_runner(batch):
     return step
 
 
+def reference_head_on_gpu(batch, dev, reps=5):
+    """Context number SURVEY §8d asks for: the UNMODIFIED reference head (CDRNet.forward with the encoder stubbed, then the
+    .cpu() + calc_mpjpe of inference.py:62-66,98-101) as torch runs it on the SAME GPU — eager ATen / cuDNN / cuSOLVER
+    kernels, 19 batched SVDs — with TF32 off (the parity configuration) and on.  Not the reference arm: that is the CPU."""
+    from oracle import refload
+    if not refload.available():
+        return None
+    from fast_3d_human_pose_estimation_b200 import synth
+    ref = refload.load()
+    sd = synth.make_head_state_dict(seed=0, calibrated=True)
+    feats = [f.to(dev) for f in synth.make_features(batch, seed=1)]
+    cams = synth.make_cameras(batch, seed=2)
+    gt = synth.make_gt(cams, seed=3)
+    Ps = [torch.from_numpy(cams["P_l"]).to(dev), torch.from_numpy(cams["P_r"]).to(dev)]
+    m = ref.CDRNet(synth.make_cfg(18, JOINTS))
+    m.load_state_dict(sd, strict=False)
+    m.encoder = refload.feature_stub(feats)
+    m = m.to(dev).eval()
+    imgs = [torch.zeros(batch, 3, 256, 256, device=dev) for _ in range(2)]
+
+    def step():
+        with torch.no_grad():
+            p2, p3 = m(imgs, Ps)
+        return ref.calc_mpjpe([x.cpu().numpy() for x in p2], p3.cpu().numpy(), gt["gt3d"], gt["gt2d_l"], gt["gt2d_r"], gt["vis"])
+    out = {}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for tag, flag in (("tf32_off", False), ("tf32_on", True)):
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = flag
+            step(); step()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                t0 = time.perf_counter(); step(); torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+            out[tag] = {"pairs_per_s": batch / float(np.median(ts)), "ms_per_step": 1e3 * float(np.median(ts))}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    out["what"] = (f"unmodified reference CDRNet.forward (encoder stubbed) + .cpu() + calc_mpjpe, {batch} pairs per step, torch "
+                   f"{torch.__version__} eager on this GPU, wall clock incl. the result read-back")
+    return out
+
+
 def cpu_head_runner(batch):
     """(step, kind): the reference itself when it is present, else the oracle port."""
     try:
@@ -1134,6 +1176,12 @@ def run_ours(args):
                              + ("unmodified reference CDRNet.forward (encoder stubbed) + calc_mpjpe"
                                 if ckind == "reference" else "oracle port") + " on torch CPU, median of 3",
                    "cpu": cpu_model()}
+        ref_gpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                ref_gpu = reference_head_on_gpu(B, dev)
+            except Exception as e:
+                ref_gpu = {"error": repr(e)[:200]}
         line = {
             "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -1168,6 +1216,8 @@ def run_ours(args):
             line["config5_full_pipeline_1024_pairs"] = c5
             if c5_bf16 is not None:
                 line["config5_full_pipeline_1024_pairs_encoder_bf16"] = c5_bf16
+        if ref_gpu is not None:
+            line["reference_head_same_gpu"] = ref_gpu
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
