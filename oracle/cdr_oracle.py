@@ -235,3 +235,49 @@ def project_3d_to_2d(pose_3d, K, R, T):
     p2 = (K @ cam.T).T
     p2[:, :2] /= p2[:, 2:]
     return p2
+
+
+# ---- the training losses, models/loss.py:5-98 (restated for when the reference sources are absent;
+# pinned against the reference's own modules by tests/test_oracle_golden.py::test_oracle_losses_match_reference_modules)
+def joints_mse_loss(output, target, target_weight, use_target_weight=True):
+    """JointsMSELoss.forward, models/loss.py:11-32: sum over joints of 0.5 * MSE(pred_j * w_j, gt_j * w_j), / J."""
+    b, j = output.shape[:2]
+    pred = output.reshape(b, j, -1)
+    gt = target.reshape(b, j, -1)
+    loss = 0
+    for i in range(j):
+        p, g = pred[:, i], gt[:, i]
+        if use_target_weight:
+            w = target_weight[:, i]
+            loss = loss + 0.5 * torch.mean((p * w - g * w) ** 2)
+        else:
+            loss = loss + 0.5 * torch.mean((p - g) ** 2)
+    return loss / j
+
+
+def joints_mse_smooth_loss(output, target, target_weight, use_target_weight=True, threshold=400):
+    """JointsMSESmoothLoss.forward, models/loss.py:41-66: squared error, v -> v^0.1 * threshold^0.9 above threshold."""
+    j = output.shape[1]
+    loss = 0
+    for i in range(j):
+        p, g = output[:, i], target[:, i]
+        if use_target_weight:
+            w = target_weight[:, i]
+            p, g = p * w, g * w
+        d = (p - g) ** 2
+        d = torch.where(d > threshold, d.clamp_min(1e-300) ** 0.1 * threshold ** 0.9, d)
+        loss = loss + d.mean()
+    return (loss / j).reshape(1)
+
+
+def mpjpe_loss(output, target, target_weight, use_target_weight=True):
+    """MPJPELoss.forward, models/loss.py:75-98: mean over batch of sqrt(|pred_j - gt_j|^2 + 1e-15), mean over joints."""
+    j = output.shape[1]
+    loss = 0
+    for i in range(j):
+        p, g = output[:, i], target[:, i]
+        if use_target_weight:
+            w = target_weight[:, i]
+            p, g = p * w, g * w
+        loss = loss + torch.sqrt(torch.sum((p - g) ** 2, dim=1) + 1e-15).mean()
+    return (loss / j).reshape(1)

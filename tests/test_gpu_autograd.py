@@ -197,14 +197,33 @@ def _forward_train_case(cuda_pkg, copy, b):
         cuda_pkg.CDRNet(synth.make_cfg(50, 19)).cuda().train()(imgs, Ps)
 
 
+class _OracleLosses:
+    """The oracle's restatement of models/loss.py (pinned against the reference's modules by tests/test_oracle_golden.py),
+    behind the reference's class names — used where the reference sources are absent."""
+
+    @staticmethod
+    def _mk(fn):
+        class _L:
+            def __init__(self, use_target_weight, *args):
+                self.use, self.args = use_target_weight, args
+
+            def __call__(self, output, target, target_weight):
+                return fn(output, target, target_weight, self.use, *self.args)
+        return _L
+
+_OracleLosses.JointsMSELoss = _OracleLosses._mk(O.joints_mse_loss)
+_OracleLosses.JointsMSESmoothLoss = _OracleLosses._mk(O.joints_mse_smooth_loss)
+_OracleLosses.MPJPELoss = _OracleLosses._mk(O.mpjpe_loss)
+
+
 def _ref_losses():
-    """The reference's own loss modules where its sources are present, else a verbatim-semantics torch restatement."""
+    """The reference's own loss modules where its sources are present, else the oracle's restatement."""
     from oracle import refload
     if refload.available():
         refload.load()
         import importlib
         return importlib.import_module("models.loss")
-    pytest.skip("reference sources not present")
+    return _OracleLosses
 
 
 @pytest.mark.parametrize("name,args", [("MPJPELoss", ()), ("JointsMSESmoothLoss", ()), ("JointsMSESmoothLoss", (4.0,)),

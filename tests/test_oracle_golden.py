@@ -164,3 +164,34 @@ def test_reference_scope_limits_are_the_references_own():
         m = m.eval()
         with torch.no_grad(), pytest.raises(exc):
             m([torch.zeros(b, 3, 256, 256)] * n_views, [P] * n_views)
+
+
+def test_oracle_losses_match_reference_modules():
+    """the oracle's restatement of models/loss.py:5-98 against the UNMODIFIED reference modules (fp64,
+    values and gradients), weighted / unweighted, joints and heat-maps, both branches of the smooth loss."""
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("reference sources not present")
+    refload.load()
+    import importlib
+    ref = importlib.import_module("models.loss")
+    g = torch.Generator().manual_seed(0)
+    for shape in ((5, 19, 3), (4, 19, 2), (3, 7, 8, 8)):
+        for use_w in (True, False):
+            pred = (torch.randn(shape, generator=g) * 30).double()
+            tgt = (torch.randn(shape, generator=g) * 30).double()
+            w = (torch.rand(shape[0], shape[1], 1, generator=g) > 0.2).double()
+            cases = [(ref.JointsMSELoss(use_w), lambda p: O.joints_mse_loss(p, tgt, w, use_w))]
+            if len(shape) == 3:
+                cases += [(ref.MPJPELoss(use_w), lambda p: O.mpjpe_loss(p, tgt, w, use_w)),
+                          (ref.JointsMSESmoothLoss(use_w), lambda p: O.joints_mse_smooth_loss(p, tgt, w, use_w)),
+                          (ref.JointsMSESmoothLoss(use_w, 4.0), lambda p: O.joints_mse_smooth_loss(p, tgt, w, use_w, 4.0))]
+            for mod, fn in cases:
+                pa = pred.clone().requires_grad_(True)
+                pb = pred.clone().requires_grad_(True)
+                la = mod(pa, tgt, w)
+                lb = fn(pb)
+                la.sum().backward()
+                lb.sum().backward()
+                np.testing.assert_allclose(float(lb.sum()), float(la.sum()), rtol=1e-6)      # reference sums in an fp32 tensor
+                np.testing.assert_allclose(pb.grad.numpy(), pa.grad.numpy(), rtol=1e-6, atol=1e-12)    # (its 1/J lives in fp32 too)
